@@ -1,0 +1,7 @@
+"""CPU oracle for the DSK counting hot path -- TEST INFRASTRUCTURE ONLY.
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs.
+The product package (dsk_b200) never imports this module.
+"""
+from .pyoracle import (Oracle, OracleResult, count_files, kmers_of, parse_stats, mmer_lut,
+                       ref_available, run_reference, read_maybe_gz, ORACLE_DIR)

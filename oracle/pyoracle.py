@@ -1,0 +1,247 @@
+"""ctypes wrapper over oracle/liboracle.so (dsk_oracle.c) + runner for the reference binaries
+in oracle/_ref/bin (when present).  Test infrastructure only."""
+import ctypes as C
+import gzip
+import os
+import subprocess
+import tempfile
+from dataclasses import dataclass
+
+import numpy as np
+
+ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KINDS = {"sum": 0, "min": 1, "max": 2, "one": 3, "all": 4, "custom": 5}
+
+
+def _lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    src = os.path.join(ORACLE_DIR, "dsk_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "liboracle.so"])
+    L = C.CDLL(so)
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_add_sequence.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
+    L.orc_add_file.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    L.orc_finish.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int64, C.c_int, C.c_char_p, C.c_int]
+    for name in ("nb_valid", "nb_invalid", "nb_seq", "nb_nt", "nb_superkmers", "nb_distinct", "nb_solid"):
+        f = getattr(L, "orc_" + name)
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p]
+    for name in ("keys_lo", "keys_hi", "counts", "sums", "solid", "hist", "hist2d"):
+        f = getattr(L, "orc_" + name)
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p]
+    L.orc_kmers_of.restype = C.c_int
+    L.orc_kmers_of.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+    L.orc_parse_stats.restype = C.c_uint64
+    L.orc_parse_stats.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t]
+    L.orc_mmer_lut.restype = C.c_uint32
+    L.orc_mmer_lut.argtypes = [C.c_uint32, C.c_int]
+    _LIB = L
+    return L
+
+
+def read_maybe_gz(path):
+    with open(path, "rb") as f:
+        head = f.read(2)
+    if head == b"\x1f\x8b":
+        with gzip.open(path, "rb") as f:
+            return f.read()
+    with open(path, "rb") as f:
+        return f.read()
+
+
+@dataclass
+class OracleResult:
+    k: int
+    nbanks: int
+    kmers_nb_valid: int
+    kmers_nb_invalid: int
+    nb_seq: int
+    nb_nt: int
+    nb_superkmers: int
+    keys_lo: np.ndarray      # distinct canonical k-mers, ascending (low 64 bits)
+    keys_hi: np.ndarray      # high 64 bits (all zero for k<=32)
+    counts: np.ndarray       # int32 [ndistinct, nbanks]
+    sums: np.ndarray         # int32 [ndistinct]
+    solid: np.ndarray        # bool  [ndistinct]
+    hist: np.ndarray         # uint64[10001]  (index = abundance; bins 0 and 10000 are always 0)
+    hist2d: np.ndarray       # uint64[11, 10001]  ([dim2, dim1])
+
+    @property
+    def nb_distinct(self):
+        return len(self.keys_lo)
+
+    @property
+    def nb_solid(self):
+        return int(self.solid.sum())
+
+    def solid_kmers(self):
+        s = self.solid
+        return self.keys_lo[s], self.keys_hi[s], self.sums[s]
+
+
+def _np_from(ptr, dtype, n):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+class Oracle:
+    """Accumulate sequences/files per bank, then finish() -> OracleResult."""
+
+    def __init__(self, k, nbanks=1, m=0):
+        self.L = _lib()
+        self.k, self.nbanks = k, nbanks
+        self.h = self.L.orc_create(k, nbanks, m)
+
+    def add_sequence(self, seq, bank=0):
+        if isinstance(seq, str):
+            seq = seq.encode()
+        self.L.orc_add_sequence(self.h, bank, seq, len(seq))
+
+    def add_file_bytes(self, data, bank=0):
+        arr = np.frombuffer(data, dtype=np.uint8)
+        self.L.orc_add_file(self.h, bank, arr.ctypes.data, arr.size)
+
+    def finish(self, abundance_min=2, abundance_max=2**31 - 1, kind="sum", solid_vec=None, histo2d=False):
+        nb = self.nbanks
+        if isinstance(abundance_min, int):
+            abundance_min = [abundance_min] * nb
+        amin = (C.c_int64 * nb)(*abundance_min)
+        sv = bytes(solid_vec if solid_vec is not None else [1] * nb)
+        self.L.orc_finish(self.h, amin, abundance_max, KINDS[kind], sv, int(histo2d))
+        L, h = self.L, self.h
+        nd = L.orc_nb_distinct(h)
+        res = OracleResult(
+            k=self.k, nbanks=nb,
+            kmers_nb_valid=L.orc_nb_valid(h), kmers_nb_invalid=L.orc_nb_invalid(h),
+            nb_seq=L.orc_nb_seq(h), nb_nt=L.orc_nb_nt(h), nb_superkmers=L.orc_nb_superkmers(h),
+            keys_lo=_np_from(L.orc_keys_lo(h), np.uint64, nd),
+            keys_hi=_np_from(L.orc_keys_hi(h), np.uint64, nd),
+            counts=_np_from(L.orc_counts(h), np.int32, nd * nb).reshape(nd, nb),
+            sums=_np_from(L.orc_sums(h), np.int32, nd),
+            solid=_np_from(L.orc_solid(h), np.uint8, nd).astype(bool),
+            hist=_np_from(L.orc_hist(h), np.uint64, 10001),
+            hist2d=_np_from(L.orc_hist2d(h), np.uint64, 10001 * 11).reshape(11, 10001),
+        )
+        L.orc_destroy(h)
+        self.h = None
+        return res
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_destroy(self.h)
+
+
+def count_files(banks, k, m=0, **kw):
+    """banks: list of byte strings (one file image per bank)."""
+    o = Oracle(k, len(banks), m)
+    for b, data in enumerate(banks):
+        o.add_file_bytes(data, b)
+    return o.finish(**kw)
+
+
+def kmers_of(seq, k, m=0, forward=False):
+    if isinstance(seq, str):
+        seq = seq.encode()
+    n = max(0, len(seq) - k + 1)
+    lo = np.zeros(n, np.uint64); hi = np.zeros(n, np.uint64)
+    valid = np.zeros(n, np.uint8); mn = np.zeros(n, np.uint32); mp = np.zeros(n, np.int32)
+    got = _lib().orc_kmers_of(seq, len(seq), k, m, int(forward), lo.ctypes.data, hi.ctypes.data,
+                              valid.ctypes.data, mn.ctypes.data, mp.ctypes.data)
+    assert got == n
+    return lo, hi, valid.astype(bool), mn, mp
+
+
+def parse_stats(data):
+    arr = np.frombuffer(data, dtype=np.uint8)
+    nt = C.c_uint64(0)
+    cap = arr.size + 16
+    out = np.zeros(cap, np.uint8)
+    nrec = _lib().orc_parse_stats(arr.ctypes.data, arr.size, C.byref(nt), out.ctypes.data, cap)
+    concat = out[: nt.value + nrec].tobytes()
+    return nrec, nt.value, concat
+
+
+def mmer_lut(x, m):
+    return _lib().orc_mmer_lut(x, m)
+
+
+# ------------------------------------------------------------------------------------------------
+# the real reference (oracle/_ref/bin/{dsk,dsk2ascii,gatb-h5dump}), when it was built
+# ------------------------------------------------------------------------------------------------
+def _ref_bin(name):
+    return os.path.join(ORACLE_DIR, "_ref", "bin", name)
+
+
+def ref_available():
+    return all(os.access(_ref_bin(n), os.X_OK) for n in ("dsk", "dsk2ascii", "gatb-h5dump"))
+
+
+def run_reference(files, k, abundance_min=2, histo=True, histo2d=False, nb_cores=0, extra=(), workdir=None,
+                  want_kmers=True, solidity_kind=None, abundance_max=None):
+    """Runs the reference `dsk` on `files` (list of paths; comma-joined like the CLI) and returns
+    dict(kmers=[(str,count)...] sorted, hist=np.uint64[10001], hist2d=..., stats=str, seconds=float)."""
+    import time
+    tmp = workdir or tempfile.mkdtemp(prefix="dskref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    out = os.path.join(tmp, "ref")
+    cmd = [_ref_bin("dsk"), "-file", ",".join(files), "-kmer-size", str(k), "-abundance-min", str(abundance_min),
+           "-out", out, "-out-tmp", tmp, "-out-dir", tmp, "-verbose", "1", "-nb-cores", str(nb_cores)]
+    if histo:
+        cmd += ["-histo", "1"]
+    if histo2d:
+        cmd += ["-histo2D", "1"]
+    if solidity_kind:
+        cmd += ["-solidity-kind", solidity_kind]
+    if abundance_max is not None:
+        cmd += ["-abundance-max", str(abundance_max)]
+    cmd += list(extra)
+    t0 = time.time()
+    p = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+    dt = time.time() - t0
+    if p.returncode != 0:
+        raise RuntimeError("reference dsk failed: %s\n%s" % (p.stdout[-2000:], p.stderr[-2000:]))
+    res = {"seconds": dt, "stats": p.stdout, "h5": out + ".h5", "tmp": tmp}
+    if histo and os.path.exists(out + ".histo"):
+        h = np.zeros(10001, np.uint64)
+        for line in open(out + ".histo"):
+            a, b = line.split()
+            h[int(a)] = int(b)
+        res["hist"] = h
+    if histo2d and os.path.exists(out + ".histo2D"):
+        rows = []
+        for line in open(out + ".histo2D"):
+            parts = line.replace(":", " ").split()
+            rows.append([int(x) for x in parts[1:]])
+        res["hist2d"] = np.array(rows, dtype=np.uint64).T   # -> [dim2(11), dim1(10001)]
+    if want_kmers:
+        txt = os.path.join(tmp, "ref.txt")
+        q = subprocess.run([_ref_bin("dsk2ascii"), "-file", out + ".h5", "-out", txt], cwd=tmp, capture_output=True, text=True)
+        if q.returncode != 0:
+            raise RuntimeError("dsk2ascii failed: " + q.stderr[-2000:])
+        km = []
+        if os.path.exists(txt):
+            for line in open(txt):
+                a, b = line.split()
+                km.append((a, int(b)))
+        km.sort()
+        res["kmers"] = km
+    return res
+
+
+def stat_value(stats_text, key):
+    """Pull `key : value` out of the -verbose 1 stats block."""
+    for line in stats_text.splitlines():
+        s = line.strip()
+        if s.startswith(key + " ") or s.startswith(key + ":"):
+            return s.split(":", 1)[1].strip()
+    return None
