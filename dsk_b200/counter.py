@@ -1,0 +1,142 @@
+"""Thin object wrapper over the C ABI (include/dskgpu.h).  All compute happens in libdskgpu.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+FMT = {"auto": 0, "fasta": 1, "fastq": 2, "lines": 3}
+SOLIDITY = {"sum": 0, "min": 1, "max": 2, "one": 3, "all": 4, "custom": 5}
+COUNT_MODE = {"auto": 0, "sort": 1, "vector": 1, "hash": 2}
+
+
+class DskGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("dskgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class GpuCounter:
+    """One counting context on one GPU: push bank bytes, finish, read the solid k-mers + histogram."""
+
+    def __init__(self, kmer_size=31, abundance_min=2, abundance_max=2**31 - 1, nb_banks=1, per_bank_counts=False,
+                 solidity_kind="sum", solid_vec=None, histo2d=False, minimizer_size=10, device=0, count_mode="auto",
+                 hash_log2_slots=0, nb_partitions=0, keep_results_on_device=False, stream=None, rank=0, world_size=1, push_chunk_bytes=0):
+        self.L = _lib.lib()
+        cfg = _lib.Config()
+        self.L.dskgpu_config_default(C.byref(cfg))
+        cfg.kmer_size = kmer_size
+        cfg.minimizer_size = minimizer_size
+        cfg.nb_banks = nb_banks
+        cfg.per_bank_counts = int(per_bank_counts)
+        cfg.solidity_kind = SOLIDITY[solidity_kind] if isinstance(solidity_kind, str) else solidity_kind
+        amin = [abundance_min] * _lib.MAX_BANKS if isinstance(abundance_min, int) else list(abundance_min)
+        amin = amin + [amin[-1]] * (_lib.MAX_BANKS - len(amin))
+        for i in range(_lib.MAX_BANKS):
+            cfg.abundance_min[i] = amin[i]
+        cfg.abundance_max = abundance_max
+        if solid_vec is not None:
+            for i, v in enumerate(solid_vec):
+                cfg.solid_vec[i] = int(v)
+        cfg.histo2d = int(histo2d)
+        cfg.device = device
+        cfg.count_mode = COUNT_MODE[count_mode] if isinstance(count_mode, str) else count_mode
+        cfg.hash_log2_slots = hash_log2_slots
+        cfg.nb_partitions = nb_partitions
+        cfg.keep_results_on_device = int(keep_results_on_device)
+        cfg.stream = stream
+        cfg.rank, cfg.world_size = rank, world_size
+        cfg.push_chunk_bytes = push_chunk_bytes
+        self.cfg = cfg
+        self.k = kmer_size
+        self.h = C.c_void_p()
+        rc = self.L.dskgpu_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.dskgpu_last_error(None).decode() or self.L.dskgpu_strerror(rc).decode()
+            self.h = None
+            raise DskGpuError(rc, msg)
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise DskGpuError(rc, (self.L.dskgpu_last_error(self.h) or b"").decode() or self.L.dskgpu_strerror(rc).decode())
+
+    # -- input --------------------------------------------------------------------------------------
+    def push_bytes(self, data, bank=0, fmt="auto", last=True):
+        """data: bytes / bytearray / numpy uint8 array / (ptr, n) of pinned host memory."""
+        if isinstance(data, tuple):
+            ptr, n = data
+        else:
+            arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+            self._keep = arr
+            ptr, n = arr.ctypes.data, arr.size
+        self._check(self.L.dskgpu_push_bytes(self.h, bank, ptr, n, FMT[fmt], 1 if last else 0))
+
+    def push_device_bytes(self, dev_ptr, n, bank=0, fmt="auto", last=True):
+        self._check(self.L.dskgpu_push_device_bytes(self.h, bank, dev_ptr, n, FMT[fmt], 1 if last else 0))
+
+    def push_reads(self, reads, bank=0):
+        """reads: list of bytes/str sequences (the IBank::iterator() flavour of the input)."""
+        bs = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+        offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8)
+        self._check(self.L.dskgpu_push_reads(self.h, bank, blob.ctypes.data, offs.ctypes.data, len(bs)))
+
+    # -- compute ------------------------------------------------------------------------------------
+    def finish(self):
+        self._check(self.L.dskgpu_finish(self.h))
+
+    def reset(self):
+        self._check(self.L.dskgpu_reset(self.h))
+
+    # -- results ------------------------------------------------------------------------------------
+    def solid(self):
+        """(keys uint64[n, words] low word first, counts uint32[n]) of every partition, concatenated."""
+        ks, cs = [], []
+        words = 1
+        for p in range(self.L.dskgpu_num_partitions(self.h)):
+            kp, cp, n, w = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_int()
+            self._check(self.L.dskgpu_partition(self.h, p, C.byref(kp), C.byref(cp), C.byref(n), C.byref(w)))
+            words = w.value
+            if n.value:
+                kb = (C.c_uint64 * (n.value * words)).from_address(kp.value)
+                cb = (C.c_uint32 * n.value).from_address(cp.value)
+                ks.append(np.frombuffer(kb, dtype=np.uint64).reshape(n.value, words).copy())
+                cs.append(np.frombuffer(cb, dtype=np.uint32).copy())
+        if not ks:
+            return np.zeros((0, words), np.uint64), np.zeros(0, np.uint32)
+        return np.concatenate(ks), np.concatenate(cs)
+
+    def solid_device(self, p=0):
+        kp, cp, n, w = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_int()
+        self._check(self.L.dskgpu_partition_device(self.h, p, C.byref(kp), C.byref(cp), C.byref(n), C.byref(w)))
+        return kp.value, cp.value, n.value, w.value
+
+    def histogram(self):
+        h1 = np.zeros(_lib.HISTO_LEN, np.uint64)
+        h2 = np.zeros((_lib.HISTO2D_DIM2, _lib.HISTO_LEN), np.uint64)
+        self._check(self.L.dskgpu_histogram(self.h, h1.ctypes.data, h2.ctypes.data))
+        return h1, h2
+
+    def stats(self):
+        st = _lib.Stats()
+        self._check(self.L.dskgpu_get_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dskgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -1,0 +1,290 @@
+// count.cuh -- K4/K7/K6: per-partition counting.
+//
+//   hash path : k_hash_insert (expand super-k-mers -> canonical k-mers -> open-addressing table with
+//               atomicCAS claim + atomic increment)  then  k_hash_scan (filter + histogram + compaction).
+//               Replaces PartitionsByHashCommand::execute / Hash16::insert / OAHash::increment
+//               (K/PartitionsCommand.cpp:372-739, G/src/gatb/tools/collections/impl/Hash16.hpp:198-230,
+//               OAHash.hpp:92-99).
+//   sort path : k_expand_keys (ReadSuperKCommand::execute, K/PartitionsCommand.cpp:944-1128) -> LSD radix
+//               sort (radix.cuh) -> k_rle_emit (executeDump's run-length count, K/PartitionsCommand.cpp:1751-1801).
+//   both end in the fused CountProcessor chain: histogram (K/CountProcessorHistogram.hpp:173-184 with the
+//   Histogram.hpp:92,221 quirks) -> solidity (K/CountProcessorSolidity.hpp:186-300) -> dump of Count(kmer,sum)
+//   (K/CountProcessorDump.hpp:85-152).
+#pragma once
+#include "kmer_bits.cuh"
+#include "superk.cuh"
+
+namespace dsk {
+
+constexpr int MAXB = 16;                                         // DSKGPU_MAX_BANKS
+constexpr u32 HASH_MAX_PROBE = 4096;
+
+struct SolidityParams {
+    int kind;                      // 0 sum 1 min 2 max 3 one 4 all 5 custom
+    int nbanks;                    // counts kept per k-mer (1 when banks are summed)
+    int histo2d;
+    long long amin[MAXB];
+    long long amax;
+    unsigned char solid_vec[MAXB];
+};
+
+#ifdef __CUDACC__
+
+constexpr int HIST_SMEM_BINS = 1024;
+
+// ---- the CountProcessor chain for one distinct k-mer --------------------------------------------------------
+// returns true if solid; *sum_out = abundance to dump.  Histograms: bins < HIST_SMEM_BINS go to the block's smem
+// histogram, the rest straight to global.
+__device__ __forceinline__ bool process_counts(const u32* cv, const SolidityParams& sp, u32* s_hist,
+                                               unsigned long long* g_hist, unsigned long long* g_hist2d, int32_t* sum_out)
+{
+    const int nb = sp.nbanks;
+    int32_t sum = 0;
+    if (nb == 1) sum = (int32_t)cv[0];
+    else for (int b = 0; b < nb; b++) if (sp.kind != 5 || sp.solid_vec[b]) sum += (int32_t)cv[b];   // CountProcessorChain.hpp:158-169
+    *sum_out = sum;
+    u32 bin = histo_bin(sum);
+    if (bin) { if (bin < HIST_SMEM_BINS) atomicAdd(&s_hist[bin], 1u); else atomicAdd(&g_hist[bin], 1ULL); }
+    if (sp.histo2d) {
+        u32 i1 = (u32)(sum - (int32_t)cv[0]) & 0xFFFFu, i2 = cv[0] & 0xFFFFu;
+        if (i1 >= 10000u) i1 = 10000u;
+        if (i2 >= 10u) i2 = 10u;
+        atomicAdd(&g_hist2d[i1 + 10001u * i2], 1ULL);
+    }
+    auto inr = [&](long long x, long long lo) { return lo <= x && x <= sp.amax; };
+    switch (sp.kind) {
+    case 0: return inr(sum, sp.amin[0]);
+    case 1: { u32 v = cv[0]; for (int b = 1; b < nb; b++) v = min(v, cv[b]); return inr(v, sp.amin[0]); }
+    case 2: { u32 v = cv[0]; for (int b = 1; b < nb; b++) v = max(v, cv[b]); return inr(v, sp.amin[0]); }
+    case 3: { for (int b = 0; b < nb; b++) if (inr(cv[b], sp.amin[b])) return true; return false; }
+    case 4: { for (int b = 0; b < nb; b++) if (!inr(cv[b], sp.amin[b])) return false; return true; }
+    default: { for (int b = 0; b < nb; b++) { bool in = inr(cv[b], sp.amin[b]); if (sp.solid_vec[b] != in) return false; } return true; }
+    }
+}
+
+__device__ __forceinline__ void flush_hist(const u32* s_hist, unsigned long long* g_hist)
+{
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) { u32 v = s_hist[i]; if (v) atomicAdd(&g_hist[i], (unsigned long long)v); }
+}
+
+// append one solid (k-mer, abundance) with a warp-aggregated cursor bump
+template <int KW>
+__device__ __forceinline__ void emit_solid(bool solid, const Kmer<KW>& key, int32_t sum, u64* out_keys, u32* out_vals,
+                                           u64 out_cap, Counters* ctr)
+{
+    u32 mask = __ballot_sync(__activemask(), solid);
+    if (!solid) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs((int)mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&ctr->solid_n, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    u64 pos = base + __popc(mask & ((1u << lane) - 1u));
+    if (pos < out_cap) {
+#pragma unroll
+        for (int i = 0; i < KW; i++) out_keys[pos * KW + i] = key.w[i];
+        out_vals[pos] = (u32)sum;
+    } else atomicExch(&ctr->overflow, 2u);
+}
+
+// ---- 128-bit compare-and-swap (sm_90+: ATOMG.E.CAS.128) ------------------------------------------------------
+__device__ __forceinline__ void cas128(u64* addr, u64 clo, u64 chi, u64 slo, u64 shi, u64& olo, u64& ohi)
+{
+    asm volatile("{\n\t.reg .b128 c, s, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\t"
+                 "atom.global.relaxed.gpu.cas.b128 d, [%6], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                 : "=l"(olo), "=l"(ohi) : "l"(clo), "l"(chi), "l"(slo), "l"(shi), "l"(addr) : "memory");
+}
+
+// find-or-claim the slot of `key`; returns slot or 0xFFFFFFFF on overflow
+__device__ __forceinline__ u32 table_slot(u64* keys, u32 smask, const Kmer<1>& key)
+{
+    const u64 EMPTY = ~0ULL;
+    u32 slot = (u32)kmer_hash(key) & smask;
+    for (u32 probe = 0; probe < HASH_MAX_PROBE; probe++) {
+        u64 cur = __ldcg(&keys[slot]);
+        if (cur == key.w[0]) return slot;
+        if (cur == EMPTY) {
+            u64 old = atomicCAS((unsigned long long*)&keys[slot], EMPTY, key.w[0]);
+            if (old == EMPTY || old == key.w[0]) return slot;
+        }
+        slot = (slot + 1) & smask;
+    }
+    return 0xFFFFFFFFu;
+}
+__device__ __forceinline__ u32 table_slot(u64* keys, u32 smask, const Kmer<2>& key)
+{
+    const u64 EMPTY = ~0ULL;
+    u32 slot = (u32)kmer_hash(key) & smask;
+    for (u32 probe = 0; probe < HASH_MAX_PROBE; probe++) {
+        // a plain 16-byte load may be torn against a concurrent claim; it is only trusted when it shows a
+        // complete foreign key (neither half all-ones), which can never change again
+        ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(keys) + slot);
+        bool foreign = (cur.x != EMPTY) && (cur.y != EMPTY) && !(cur.x == key.w[0] && cur.y == key.w[1]);
+        if (!foreign) {
+            u64 olo, ohi;
+            cas128(keys + 2 * (u64)slot, EMPTY, EMPTY, key.w[0], key.w[1], olo, ohi);
+            if ((olo == EMPTY && ohi == EMPTY) || (olo == key.w[0] && ohi == key.w[1])) return slot;
+        }
+        slot = (slot + 1) & smask;
+    }
+    return 0xFFFFFFFFu;
+}
+
+// ---- K4+K7: expand records and count into the table ------------------------------------------------------------
+// one thread per super-k-mer record; rolling forward / reverse-complement k-mers (K/Model.hpp:877-884)
+template <int KW>
+__global__ void __launch_bounds__(256) k_hash_insert(const u64* __restrict__ recs, u64 rec_begin, u64 rec_end, int k,
+                                                     u64* keys, u32* counts, u32 smask, int nbanks, Counters* ctr)
+{
+    constexpr int RW = 2 * KW;
+    for (u64 i = rec_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rec_end; i += (u64)gridDim.x * blockDim.x) {
+        u64 r[RW];
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
+        if constexpr (RW == 2) { ulonglong2 v = __ldg(src + i); r[0] = v.x; r[1] = v.y; }
+        else { ulonglong2 v = __ldg(src + 2 * i), u = __ldg(src + 2 * i + 1); r[0] = v.x; r[1] = v.y; r[2] = u.x; r[3] = u.y; }
+        const int nk = (int)((r[RW - 1] >> 8) & 0xFFu);
+        const int bank = (nbanks > 1) ? (int)(r[RW - 1] & 0xFFu) : 0;
+        Kmer<KW> f, rc;
+        if constexpr (KW == 1) f = rec_first_kmer1(r, k); else f = rec_first_kmer2(r, k);
+        rc = kmer_revcomp(f, k);
+        for (int j = 0; j < nk; j++) {
+            if (j) kmer_roll(f, rc, rec_base<RW>(r, k - 1 + j), k);
+            Kmer<KW> c = kmer_canonical(f, rc);
+            u32 slot = table_slot(keys, smask, c);
+            if (slot == 0xFFFFFFFFu) { atomicExch(&ctr->hash_overflow, 1u); return; }
+            atomicAdd(&counts[(u64)slot * nbanks + bank], 1u);
+        }
+    }
+}
+
+// ---- K6 (hash flavour): sweep the table, run the processor chain, reset the slots ---------------------------------
+template <int KW>
+__global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 nslots, SolidityParams sp, int discard,
+                                                   u64* out_keys, u32* out_vals, u64 out_cap,
+                                                   unsigned long long* g_hist, unsigned long long* g_hist2d, Counters* ctr)
+{
+    __shared__ u32 s_hist[HIST_SMEM_BINS];
+    __shared__ u32 s_distinct;
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_distinct = 0;
+    __syncthreads();
+    const u64 EMPTY = ~0ULL;
+    u32 ndist = 0;
+    const u32 nloop = (nslots + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
+    for (u32 it = 0; it < nloop; it++) {
+        u32 slot = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        bool occ = false; Kmer<KW> key; u32 cv[MAXB];
+        if (slot < nslots) {
+            if constexpr (KW == 1) { key.w[0] = keys[slot]; occ = key.w[0] != EMPTY; }
+            else { ulonglong2 v = reinterpret_cast<ulonglong2*>(keys)[slot]; key.w[0] = v.x; key.w[1] = v.y; occ = !(v.x == EMPTY && v.y == EMPTY); }
+        }
+        bool solid = false; int32_t sum = 0;
+        if (occ) {
+            for (int b = 0; b < sp.nbanks; b++) { cv[b] = counts[(u64)slot * sp.nbanks + b]; counts[(u64)slot * sp.nbanks + b] = 0; }
+            if constexpr (KW == 1) keys[slot] = EMPTY;
+            else reinterpret_cast<ulonglong2*>(keys)[slot] = make_ulonglong2(EMPTY, EMPTY);
+            if (!discard) { ndist++; solid = process_counts(cv, sp, s_hist, g_hist, g_hist2d, &sum); }
+        }
+        emit_solid<KW>(solid, key, sum, out_keys, out_vals, out_cap, ctr);
+    }
+    ndist = __reduce_add_sync(0xFFFFFFFFu, ndist);
+    if ((threadIdx.x & 31) == 0 && ndist) atomicAdd(&s_distinct, ndist);
+    __syncthreads();
+    flush_hist(s_hist, g_hist);
+    if (threadIdx.x == 0 && s_distinct) atomicAdd(&ctr->distinct_n, (unsigned long long)s_distinct);
+}
+
+__global__ void k_fill_u64(u64* p, u64 n, u64 v)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---- K4 (sort flavour): expand records into a flat key array -------------------------------------------------------
+template <int KW>
+__global__ void __launch_bounds__(256) k_expand_keys(const u64* __restrict__ recs, u64 rec_begin, u64 rec_end, int k,
+                                                     u64* __restrict__ out_keys, u32* __restrict__ out_bank, int nbanks, Counters* ctr)
+{
+    constexpr int RW = 2 * KW;
+    const int lane = threadIdx.x & 31;
+    const u64 nrec = rec_end - rec_begin;
+    const u64 nloop = (nrec + (u64)blockDim.x * gridDim.x - 1) / ((u64)blockDim.x * gridDim.x);
+    for (u64 it = 0; it < nloop; it++) {
+        u64 i = rec_begin + (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        u64 r[RW]; int nk = 0;
+        if (i < rec_end) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
+            if constexpr (RW == 2) { ulonglong2 v = __ldg(src + i); r[0] = v.x; r[1] = v.y; }
+            else { ulonglong2 v = __ldg(src + 2 * i), u = __ldg(src + 2 * i + 1); r[0] = v.x; r[1] = v.y; r[2] = u.x; r[3] = u.y; }
+            nk = (int)((r[RW - 1] >> 8) & 0xFFu);
+        }
+        u32 inc = (u32)nk;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+        u32 wtot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        unsigned long long base = 0;
+        if (lane == 0 && wtot) base = atomicAdd(&ctr->expand_cursor, (unsigned long long)wtot);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (nk == 0) continue;
+        u64 pos = base + inc - nk;
+        const u32 bank = (u32)(r[RW - 1] & 0xFFu);
+        Kmer<KW> f, rc;
+        if constexpr (KW == 1) f = rec_first_kmer1(r, k); else f = rec_first_kmer2(r, k);
+        rc = kmer_revcomp(f, k);
+        for (int j = 0; j < nk; j++) {
+            if (j) kmer_roll(f, rc, rec_base<RW>(r, k - 1 + j), k);
+            Kmer<KW> c = kmer_canonical(f, rc);
+#pragma unroll
+            for (int q = 0; q < KW; q++) out_keys[(pos + j) * KW + q] = c.w[q];
+            if (nbanks > 1) out_bank[pos + j] = bank;
+        }
+    }
+}
+
+// ---- K6 (sort flavour): run-length count over sorted keys ------------------------------------------------------------
+// the thread at the head of a run gallops to its end (sorted input => O(log count) probes)
+template <int KW>
+__global__ void __launch_bounds__(256) k_rle_emit(const u64* __restrict__ keys, const u32* __restrict__ banks, u64 n,
+                                                  SolidityParams sp, u64* out_keys, u32* out_vals, u64 out_cap,
+                                                  unsigned long long* g_hist, unsigned long long* g_hist2d, Counters* ctr)
+{
+    __shared__ u32 s_hist[HIST_SMEM_BINS];
+    __shared__ u32 s_distinct;
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_distinct = 0;
+    __syncthreads();
+    auto load = [&](u64 i) { Kmer<KW> x;
+#pragma unroll
+        for (int q = 0; q < KW; q++) x.w[q] = keys[i * KW + q];
+        return x; };
+    u32 ndist = 0;
+    const u64 nloop = (n + (u64)blockDim.x * gridDim.x - 1) / ((u64)blockDim.x * gridDim.x);
+    for (u64 it = 0; it < nloop; it++) {
+        u64 i = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        bool solid = false; int32_t sum = 0; Kmer<KW> key;
+        if (i < n) {
+            key = load(i);
+            bool head = (i == 0) || !kmer_eq(load(i - 1), key);
+            if (head) {
+                u64 step = 1, lo = i;                              // keys[lo] == key ; find last equal
+                while (lo + step < n && kmer_eq(load(lo + step), key)) { lo += step; step <<= 1; }
+                u64 hi = (lo + step < n) ? lo + step : n;          // keys[hi] != key or hi == n
+                while (hi - lo > 1) { u64 mid = lo + (hi - lo) / 2; if (kmer_eq(load(mid), key)) lo = mid; else hi = mid; }
+                u64 cnt = lo - i + 1;
+                u32 cv[MAXB];
+                if (sp.nbanks == 1) cv[0] = (u32)cnt;
+                else { for (int b = 0; b < sp.nbanks; b++) cv[b] = 0; for (u64 j = i; j <= lo; j++) cv[banks[j]]++; }
+                ndist++;
+                solid = process_counts(cv, sp, s_hist, g_hist, g_hist2d, &sum);
+            }
+        }
+        emit_solid<KW>(solid, key, sum, out_keys, out_vals, out_cap, ctr);
+    }
+    ndist = __reduce_add_sync(0xFFFFFFFFu, ndist);
+    if ((threadIdx.x & 31) == 0 && ndist) atomicAdd(&s_distinct, ndist);
+    __syncthreads();
+    flush_hist(s_hist, g_hist);
+    if (threadIdx.x == 0 && s_distinct) atomicAdd(&ctr->distinct_n, (unsigned long long)s_distinct);
+}
+
+#endif  // __CUDACC__
+}  // namespace dsk

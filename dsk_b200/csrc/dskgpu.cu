@@ -1,0 +1,855 @@
+// dskgpu.cu -- C ABI (include/dskgpu.h) and host orchestration of the B200 counting path.
+//
+// Stage map (reference -> here; K/ = thirdparty/gatb-core/gatb-core/src/gatb/kmer/impl/):
+//   fillPartitions  (K/SortingCountAlgorithm.cpp:1216-1349)  -> push_*: K1 scan.cuh, K2 superk.cuh (per chunk, streaming)
+//   SuperKmerBinFiles temp tier (Storage.cpp:310-589)        -> records stay in HBM; K3 partition scatter at finish
+//   fillSolidKmers  (K/SortingCountAlgorithm.cpp:1414-1607)  -> finish: groups of partitions counted by the hash path
+//                                                               (count.cuh) or the sort path (radix.cuh + k_rle_emit)
+//   CountProcessor chain                                     -> fused into k_hash_scan / k_rle_emit
+// There is no CPU fallback: without a CUDA device dskgpu_create fails with DSKGPU_ERR_NODEVICE.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/dskgpu.h"
+#include "kmer_bits.cuh"
+#include "scan.cuh"
+#include "superk.cuh"
+#include "count.cuh"
+#include "radix.cuh"
+
+using namespace dsk;
+
+static thread_local std::string g_last_error;
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct dskgpu_ctx {
+    dskgpu_config cfg;
+    int k = 0, m = 0, KW = 1, RW = 2, NB = 1;         // NB = counts kept per k-mer
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;
+    int state = 0;                                   // 0 accepting pushes, 1 finished
+    std::string err;
+    // device state
+    DevBuf ss, ctr, hist, hist2d, raw[2], codes, tabs, tin;
+    DevBuf recs, meta;                               // staging records (input order)
+    DevBuf precs;                                    // partitioned records
+    DevBuf part_recs, part_kmers, cursor, dstbase, gflags;
+    DevBuf tkeys, tcounts;                           // hash table
+    DevBuf skeys[2], svals[2];                       // solid (k-mer, abundance) ping-pong
+    DevBuf keys[2], banks[2];                        // sort path ping-pong
+    DevBuf rs_hist, rs_status, rs_tilectr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_k2 = nullptr;
+    // host pinned mirrors
+    Counters* h_ctr = nullptr; StreamState* h_ss = nullptr;
+    unsigned long long* h_nrec_probe = nullptr;
+    u64* h_skeys = nullptr; u32* h_svals = nullptr; size_t h_solid_cap = 0;
+    unsigned long long* h_hist = nullptr;            // [10001 + 11*10001]
+    // stream bookkeeping
+    int cur_bank = -1, cur_fmt = 0; bool stream_open = false; int pending_cr = 0;
+    u64 rec_cap = 0; u64 nrec_known = 0; int chunk_parity = 0; bool k2_inflight = false;
+    size_t push_chunk = (size_t)64 << 20;
+    // results
+    u64 n_solid = 0; int solid_buf = 0; bool results_on_host = false;
+    std::vector<u64> h_part_recs, h_part_kmers;
+    u32 nparts = 0;
+    // multi-GPU
+    std::vector<u64> xchg_matrix; std::vector<void*> peer_recv; bool xchg_planned = false; bool xchg_scattered = false;
+    u64 my_nrec_owned = 0; std::vector<u64> part_off_owned;     // offsets of my partitions in my receive buffer
+    DevBuf sendbuf;
+    dskgpu_stats st;
+    // timing
+    std::vector<cudaEvent_t> evpool; size_t ev_used = 0;
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    char b_[512]; snprintf(b_, sizeof b_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    if (ctx) ctx->err = b_; g_last_error = b_; return DSKGPU_ERR_CUDA; } } while (0)
+#define FAIL(code, ...) do { char b_[512]; snprintf(b_, sizeof b_, __VA_ARGS__); if (ctx) ctx->err = b_; g_last_error = b_; return (code); } while (0)
+#define LAUNCHED() do { ctx->st.gpu_launches++; } while (0)
+
+static int ensure(dskgpu_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false, size_t keep_bytes = 0)
+{
+    if (bytes <= b.cap) return 0;
+    size_t ncap = std::max(bytes, b.cap + b.cap / 2);
+    ncap = (ncap + 255) & ~(size_t)255;
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); FAIL(DSKGPU_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", ncap, cudaGetErrorString(e)); }
+    if (keep && b.p && keep_bytes) { CK(cudaMemcpyAsync(np, b.p, keep_bytes, cudaMemcpyDeviceToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
+    if (b.p) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(b.p); }
+    b.p = np; b.cap = ncap;
+    return 0;
+}
+
+enum { SPAN_PARSE = 0, SPAN_SUPERK = 1, SPAN_PART = 2, SPAN_COUNT = 3, SPAN_SORT = 4, SPAN_DOM = 5, SPAN_TOTAL = 6 };
+
+static cudaEvent_t get_event(dskgpu_ctx* ctx)
+{
+    if (ctx->ev_used == ctx->evpool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->evpool.push_back(e); }
+    return ctx->evpool[ctx->ev_used++];
+}
+struct SpanGuard {
+    dskgpu_ctx* c; cudaEvent_t a; int kind;
+    SpanGuard(dskgpu_ctx* ctx, int kind_) : c(ctx), kind(kind_) { a = get_event(ctx); cudaEventRecord(a, ctx->stream); }
+    ~SpanGuard() { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({a, b, kind}); }
+};
+
+extern "C" {
+
+void dskgpu_config_default(dskgpu_config* c)
+{
+    memset(c, 0, sizeof(*c));
+    c->abi_version = DSKGPU_ABI_VERSION;
+    c->kmer_size = 31; c->minimizer_size = 10; c->nb_banks = 1; c->per_bank_counts = 0;
+    c->solidity_kind = DSKGPU_SOLIDITY_SUM;
+    for (int i = 0; i < DSKGPU_MAX_BANKS; i++) { c->abundance_min[i] = 2; c->solid_vec[i] = 1; }
+    c->abundance_max = 2147483647LL;
+    c->count_mode = DSKGPU_COUNT_AUTO; c->world_size = 1;
+}
+
+const char* dskgpu_strerror(int code)
+{
+    switch (code) {
+    case DSKGPU_OK: return "ok";
+    case DSKGPU_ERR_ARG: return "bad argument / unhandled kmer size";
+    case DSKGPU_ERR_CUDA: return "CUDA runtime error";
+    case DSKGPU_ERR_NOMEM: return "out of device memory";
+    case DSKGPU_ERR_FORMAT: return "input format not accepted by the device record scanner";
+    case DSKGPU_ERR_STATE: return "call order violated";
+    case DSKGPU_ERR_NODEVICE: return "no CUDA device (the counting path has no CPU fallback)";
+    case DSKGPU_ERR_OVERFLOW: return "internal capacity exceeded";
+    }
+    return "unknown error";
+}
+const char* dskgpu_last_error(dskgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+int dskgpu_abi_version(void) { return DSKGPU_ABI_VERSION; }
+int dskgpu_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; } return n; }
+void* dskgpu_host_alloc(size_t n) { void* p = nullptr; if (cudaMallocHost(&p, n) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; } return p; }
+void dskgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
+{
+    dskgpu_ctx* ctx = nullptr;
+    if (!cfg || !out) FAIL(DSKGPU_ERR_ARG, "null argument");
+    if (cfg->abi_version != DSKGPU_ABI_VERSION) FAIL(DSKGPU_ERR_ARG, "abi version mismatch");
+    if (cfg->kmer_size < 2 || cfg->kmer_size > DSKGPU_MAX_KMER) FAIL(DSKGPU_ERR_ARG, "Failure because of unhandled kmer size %d", cfg->kmer_size);
+    if (cfg->nb_banks < 1 || cfg->nb_banks > DSKGPU_MAX_BANKS) FAIL(DSKGPU_ERR_ARG, "nb_banks %d out of range", cfg->nb_banks);
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) FAIL(DSKGPU_ERR_ARG, "bad rank/world_size");
+    if (dskgpu_device_count() <= 0) FAIL(DSKGPU_ERR_NODEVICE, "no CUDA device visible");
+    ctx = new dskgpu_ctx();
+    ctx->cfg = *cfg;
+    ctx->k = cfg->kmer_size;
+    int m = cfg->minimizer_size > 0 ? cfg->minimizer_size : 10;
+    if (m > ctx->k - 1) m = ctx->k - 1;              // ConfigurationAlgorithm.cpp:249-251
+    if (m > 12) m = 12;                              // meta word packs the minimizer in 24 bits
+    if (m < 2) m = 2;
+    if (m > ctx->k) m = ctx->k;
+    ctx->m = m;
+    ctx->KW = (ctx->k < 32) ? 1 : 2;                 // Integer.hpp:463 : span = first K in KSIZE_LIST with k < K
+    ctx->RW = 2 * ctx->KW;
+    ctx->NB = (cfg->per_bank_counts && cfg->nb_banks > 1) ? cfg->nb_banks : 1;
+    if (cfg->push_chunk_bytes > 0) ctx->push_chunk = (size_t)std::max(cfg->push_chunk_bytes, 64);
+    memset(&ctx->st, 0, sizeof ctx->st);
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { delete ctx; ctx = nullptr; FAIL(DSKGPU_ERR_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e)); }
+    if (cfg->stream) ctx->stream = (cudaStream_t)cfg->stream;
+    else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); }
+    CK(cudaEventCreateWithFlags(&ctx->ev_k2, cudaEventDisableTiming));
+    CK(cudaMallocHost((void**)&ctx->h_ctr, sizeof(Counters)));
+    CK(cudaMallocHost((void**)&ctx->h_ss, sizeof(StreamState)));
+    CK(cudaMallocHost((void**)&ctx->h_nrec_probe, 64));
+    CK(cudaMallocHost((void**)&ctx->h_hist, sizeof(unsigned long long) * (DSKGPU_HISTO_LEN * (1 + DSKGPU_HISTO2D_DIM2))));
+    int rc;
+    if ((rc = ensure(ctx, ctx->ss, sizeof(StreamState)))) return rc;
+    if ((rc = ensure(ctx, ctx->ctr, sizeof(Counters)))) return rc;
+    if ((rc = ensure(ctx, ctx->hist, sizeof(unsigned long long) * DSKGPU_HISTO_LEN))) return rc;
+    if ((rc = ensure(ctx, ctx->hist2d, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2))) return rc;
+    // dynamic shared memory opt-in for the one-sweep kernels
+    const int smem1 = RsCfg<1>::TILE * 8 + RsCfg<1>::TILE * 4, smem2 = RsCfg<2>::TILE * 16 + RsCfg<2>::TILE * 4;
+    CK(cudaFuncSetAttribute(k_rs_onesweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CK(cudaFuncSetAttribute(k_rs_onesweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    CK(cudaFuncSetAttribute(k_rs_onesweep<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    CK(cudaFuncSetAttribute(k_rs_onesweep<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    *out = ctx;
+    int r = dskgpu_reset(ctx);
+    if (r) { *out = nullptr; return r; }
+    return DSKGPU_OK;
+}
+
+int dskgpu_reset(dskgpu_ctx* ctx)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemsetAsync(ctx->ss.p, 0, sizeof(StreamState), ctx->stream));
+    CK(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
+    ctx->state = 0; ctx->cur_bank = -1; ctx->stream_open = false; ctx->pending_cr = 0;
+    ctx->nrec_known = 0; ctx->k2_inflight = false; ctx->chunk_parity = 0;
+    ctx->n_solid = 0; ctx->results_on_host = false; ctx->nparts = 0;
+    ctx->xchg_planned = false; ctx->xchg_scattered = false;
+    ctx->ev_used = 0; ctx->spans.clear();
+    u64 launches = 0;
+    memset(&ctx->st, 0, sizeof ctx->st); ctx->st.gpu_launches = launches;
+    return DSKGPU_OK;
+}
+
+void dskgpu_destroy(dskgpu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
+                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->part_recs, &ctx->part_kmers, &ctx->cursor, &ctx->dstbase, &ctx->gflags,
+                     &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
+                     &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr, &ctx->sendbuf};
+    for (DevBuf* b : all) b->release();
+    for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) { if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
+    if (ctx->ev_k2) cudaEventDestroy(ctx->ev_k2);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->h_ss) cudaFreeHost(ctx->h_ss);
+    if (ctx->h_nrec_probe) cudaFreeHost(ctx->h_nrec_probe);
+    if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
+    if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
+    if (ctx->h_svals) cudaFreeHost(ctx->h_svals);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// push path
+// ---------------------------------------------------------------------------------------------------------------
+static int open_stream(dskgpu_ctx* ctx, int bank, int fmt)
+{
+    if (ctx->stream_open && ctx->cur_bank == bank) return 0;
+    if (bank < 0 || bank >= ctx->cfg.nb_banks) FAIL(DSKGPU_ERR_ARG, "bank %d out of range", bank);
+    k_scan_reset_stream<<<1, 1, 0, ctx->stream>>>((StreamState*)ctx->ss.p, fmt); LAUNCHED();
+    ctx->stream_open = true; ctx->cur_bank = bank; ctx->cur_fmt = fmt; ctx->pending_cr = 0;
+    return 0;
+}
+static void close_stream(dskgpu_ctx* ctx) { ctx->stream_open = false; ctx->cur_bank = -1; ctx->pending_cr = 0; }
+
+// scans bytes [lo, hi) of the 16-byte aligned device buffer `raw` and appends super-k-mer records
+static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int next_after)
+{
+    if (hi <= lo) return 0;
+    const int fmt = ctx->cur_fmt;
+    const u64 n = hi - lo;
+    const u64 tile_first = lo / SCAN_TILE;
+    const u64 ntiles = (hi + SCAN_TILE - 1) / SCAN_TILE - tile_first;
+    int rc;
+    if ((rc = ensure(ctx, ctx->tabs, ntiles * sizeof(TileTab)))) return rc;
+    if ((rc = ensure(ctx, ctx->tin, ntiles * sizeof(TileIn)))) return rc;
+    if ((rc = ensure(ctx, ctx->codes, std::max<u64>(n, 2 * ctx->push_chunk) + 64 + SK_TP + 1024, true, 64))) return rc;
+    // record capacity: worst case one record per position of this chunk on top of what is known to be used
+    if (ctx->k2_inflight) {
+        CK(cudaEventSynchronize(ctx->ev_k2));
+        ctx->nrec_known = *ctx->h_nrec_probe; ctx->k2_inflight = false;
+    }
+    const u64 need = ctx->nrec_known + n + 64;
+    if (need > ctx->rec_cap) {
+        u64 ncap = std::max(need, ctx->rec_cap + ctx->rec_cap / 2);
+        if ((rc = ensure(ctx, ctx->recs, ncap * ctx->RW * 8, true, ctx->nrec_known * ctx->RW * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->meta, ncap * 4, true, ctx->nrec_known * 4))) return rc;
+        ctx->rec_cap = std::min<u64>(ctx->recs.cap / (ctx->RW * 8), ctx->meta.cap / 4);
+    }
+    StreamState* ss = (StreamState*)ctx->ss.p;
+    {
+        SpanGuard g(ctx, SPAN_PARSE);
+        const unsigned gt = (unsigned)ntiles;
+        switch (fmt) {
+        case FMT_FASTA: k_scan_tables<FMT_FASTA><<<gt, SCAN_THREADS, 0, ctx->stream>>>(raw, lo, hi, tile_first, ss, next_after, (TileTab*)ctx->tabs.p); break;
+        case FMT_FASTQ: k_scan_tables<FMT_FASTQ><<<gt, SCAN_THREADS, 0, ctx->stream>>>(raw, lo, hi, tile_first, ss, next_after, (TileTab*)ctx->tabs.p); break;
+        default:        k_scan_tables<FMT_LINES><<<gt, SCAN_THREADS, 0, ctx->stream>>>(raw, lo, hi, tile_first, ss, next_after, (TileTab*)ctx->tabs.p); break;
+        }
+        LAUNCHED();
+        k_scan_tiles<<<1, 1024, 0, ctx->stream>>>((const TileTab*)ctx->tabs.p, ntiles, (TileIn*)ctx->tin.p, ss, raw, lo, hi); LAUNCHED();
+        switch (fmt) {
+        case FMT_FASTA: k_scan_emit<FMT_FASTA><<<gt, SCAN_THREADS, 0, ctx->stream>>>(raw, lo, hi, tile_first, ss, ss, next_after, (const TileIn*)ctx->tin.p, (u8*)ctx->codes.p); break;
+        case FMT_FASTQ: k_scan_emit<FMT_FASTQ><<<gt, SCAN_THREADS, 0, ctx->stream>>>(raw, lo, hi, tile_first, ss, ss, next_after, (const TileIn*)ctx->tin.p, (u8*)ctx->codes.p); break;
+        default:        k_scan_emit<FMT_LINES><<<gt, SCAN_THREADS, 0, ctx->stream>>>(raw, lo, hi, tile_first, ss, ss, next_after, (const TileIn*)ctx->tin.p, (u8*)ctx->codes.p); break;
+        }
+        LAUNCHED();
+    }
+    {
+        SpanGuard g(ctx, SPAN_SUPERK);
+        const unsigned gk = (unsigned)((n + 64 + SK_TP - 1) / SK_TP);
+        const int bank = ctx->NB > 1 ? ctx->cur_bank : 0;
+        if (ctx->KW == 1) k_superkmers<1><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p);
+        else              k_superkmers<2><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p);
+        LAUNCHED();
+        k_scan_carry<<<1, 64, 0, ctx->stream>>>((u8*)ctx->codes.p, ss, ctx->k); LAUNCHED();
+    }
+    CK(cudaMemcpyAsync(ctx->h_nrec_probe, &((Counters*)ctx->ctr.p)->nrec, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_k2, ctx->stream));
+    ctx->k2_inflight = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int detect_format(const char* b, size_t n, size_t* skip)
+{
+    // BankFasta.cpp:492-498 : everything before the first '>' or '@' is skipped
+    for (size_t i = 0; i < n; i++) {
+        if (b[i] == '>') { *skip = i; return FMT_FASTA; }
+        if (b[i] == '@') { *skip = i; return FMT_FASTQ; }
+    }
+    *skip = n; return 0;
+}
+
+extern "C" {
+
+int dskgpu_push_bytes(dskgpu_ctx* ctx, int bank_id, const char* bytes, size_t n, int format, int flags)
+{
+    if (!ctx || (!bytes && n)) return DSKGPU_ERR_ARG;
+    if (ctx->state != 0) FAIL(DSKGPU_ERR_STATE, "push after finish");
+    const bool last = flags & DSKGPU_PUSH_LAST;
+    size_t skip = 0;
+    if (!ctx->stream_open || ctx->cur_bank != bank_id) {
+        int fmt = format;
+        if (fmt == DSKGPU_FMT_AUTO || fmt == DSKGPU_FMT_FASTA || fmt == DSKGPU_FMT_FASTQ) {
+            size_t s = 0; int det = detect_format(bytes, n, &s);
+            if (det == 0) { if (last) return DSKGPU_OK; FAIL(DSKGPU_ERR_FORMAT, "no FASTA/FASTQ header in the first chunk of bank %d", bank_id); }
+            if (fmt == DSKGPU_FMT_AUTO) fmt = det;
+            skip = s;
+        }
+        int rc = open_stream(ctx, bank_id, fmt); if (rc) return rc;
+    }
+    size_t pos = skip;
+    const size_t CH = ctx->push_chunk;
+    for (;;) {
+        const size_t remaining = n - pos;
+        if (remaining == 0 && !(last && ctx->pending_cr)) break;
+        const size_t len = std::min(CH, remaining);
+        const bool final_piece = (pos + len == n);
+        // hold back a trailing CR unless the stream ends here: its fate depends on the next byte (BankFasta.cpp:471)
+        const int hold = (final_piece && !last && len > 0 && bytes[pos + len - 1] == '\r') ? 1 : 0;
+        const size_t eff = len - hold;
+        if (eff == 0 && !ctx->pending_cr) { ctx->pending_cr = hold; pos += len; continue; }
+        const int par = ctx->chunk_parity; ctx->chunk_parity ^= 1;
+        int rc = ensure(ctx, ctx->raw[par], CH + 64); if (rc) return rc;
+        u8* d = (u8*)ctx->raw[par].p;
+        // raw[par] was last read by the kernels of two chunks ago; order the copy after them
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[par], 0));
+        u64 lo = 16;
+        if (ctx->pending_cr) { static const char cr = '\r'; lo = 15; CK(cudaMemcpyAsync(d + 15, &cr, 1, cudaMemcpyHostToDevice, ctx->copy_stream)); ctx->pending_cr = 0; }
+        if (eff) CK(cudaMemcpyAsync(d + 16, bytes + pos, eff, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copy[par], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[par], 0));
+        int next_after;
+        if (!final_piece) next_after = (int)(unsigned char)bytes[pos + len];
+        else if (hold) next_after = '\r';
+        else next_after = last ? -1 : '\n';
+        rc = process_chunk(ctx, d, lo, 16 + eff, next_after);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_done[par], ctx->stream));
+        ctx->pending_cr = hold;
+        pos += len;
+    }
+    if (last) close_stream(ctx);
+    return DSKGPU_OK;
+}
+
+int dskgpu_push_device_bytes(dskgpu_ctx* ctx, int bank_id, const void* dev_bytes, size_t n, int format, int flags)
+{
+    if (!ctx || (!dev_bytes && n)) return DSKGPU_ERR_ARG;
+    if (ctx->state != 0) FAIL(DSKGPU_ERR_STATE, "push after finish");
+    const bool last = flags & DSKGPU_PUSH_LAST;
+    const u8* p = (const u8*)dev_bytes;
+    size_t skip = 0;
+    if (!ctx->stream_open || ctx->cur_bank != bank_id) {
+        int fmt = format;
+        if (fmt != DSKGPU_FMT_LINES) {
+            // sniff the head of the stream on the host (one small D2H copy per bank)
+            size_t hn = std::min<size_t>(n, 1 << 16);
+            std::vector<char> head(hn);
+            CK(cudaMemcpyAsync(head.data(), p, hn, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            size_t s = 0; int det = detect_format(head.data(), hn, &s);
+            if (det == 0) { if (last && hn == n) return DSKGPU_OK; FAIL(DSKGPU_ERR_FORMAT, "no FASTA/FASTQ header in the first 64 KiB of bank %d", bank_id); }
+            if (fmt == DSKGPU_FMT_AUTO) fmt = det;
+            skip = s;
+        }
+        int rc = open_stream(ctx, bank_id, fmt); if (rc) return rc;
+    }
+    // process in place, in pieces that bound the worst-case record reservation
+    const uintptr_t addr = (uintptr_t)p;
+    const u8* base = (const u8*)(addr & ~(uintptr_t)15);
+    const u64 off0 = (u64)(addr - (uintptr_t)base);
+    const size_t CH = ctx->push_chunk * 2;
+    size_t pos = skip;
+    while (pos < n) {
+        size_t len = std::min(CH, n - pos);
+        // keep piece boundaries 16-byte aligned in absolute terms so vector loads stay aligned
+        if (pos + len < n) { u64 endabs = off0 + pos + len; endabs &= ~(u64)(SCAN_TILE - 1); if (endabs > off0 + pos) len = (size_t)(endabs - off0 - pos); }
+        const bool final_piece = (pos + len == n);
+        // next byte: read on the device side would need a copy; non-final pieces pass -2 => kernels read raw[hi]
+        int next_after = final_piece ? (last ? -1 : '\n') : -2;
+        int rc = process_chunk(ctx, base, off0 + pos, off0 + pos + len, next_after); if (rc) return rc;
+        pos += len;
+    }
+    if (last) close_stream(ctx);
+    return DSKGPU_OK;
+}
+
+int dskgpu_push_reads(dskgpu_ctx* ctx, int bank_id, const char* bases, const uint64_t* offsets, size_t nreads)
+{
+    if (!ctx || !bases || !offsets) return DSKGPU_ERR_ARG;
+    // one sequence per line: the separator is inserted on the host while staging
+    size_t total = (size_t)(offsets[nreads] - offsets[0]) + nreads;
+    char* tmp = (char*)dskgpu_host_alloc(total ? total : 1);
+    if (!tmp) FAIL(DSKGPU_ERR_NOMEM, "pinned staging alloc failed");
+    size_t w = 0;
+    for (size_t i = 0; i < nreads; i++) {
+        size_t len = (size_t)(offsets[i + 1] - offsets[i]);
+        memcpy(tmp + w, bases + offsets[i], len); w += len; tmp[w++] = '\n';
+    }
+    int rc = dskgpu_push_bytes(ctx, bank_id, tmp, w, DSKGPU_FMT_LINES, DSKGPU_PUSH_LAST);
+    if (rc == 0) { cudaStreamSynchronize(ctx->copy_stream); }
+    dskgpu_host_free(tmp);
+    return rc;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// finish path
+// ---------------------------------------------------------------------------------------------------------------
+template <int KW, bool HAS_VAL>
+static int radix_sort(dskgpu_ctx* ctx, u64* keys[2], u32* vals[2], u64 n, int npass, int* result_buf)
+{
+    *result_buf = 0;
+    if (n == 0) return 0;
+    if (n >= ((u64)1 << 30)) FAIL(DSKGPU_ERR_OVERFLOW, "radix sort of %llu keys exceeds the 2^30 limit of the tile status words", (unsigned long long)n);
+    constexpr int TILE = RsCfg<KW>::TILE;
+    const u64 ntiles = (n + TILE - 1) / TILE;
+    int rc;
+    if ((rc = ensure(ctx, ctx->rs_hist, (size_t)npass * 256 * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->rs_status, ntiles * 256 * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->rs_tilectr, 64 * 4))) return rc;
+    CK(cudaMemsetAsync(ctx->rs_hist.p, 0, (size_t)npass * 256 * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->rs_tilectr.p, 0, 64 * 4, ctx->stream));
+    const unsigned hb = (unsigned)std::min<u64>((n + RS_THREADS * 8 - 1) / (RS_THREADS * 8), 148 * 8);
+    k_rs_hist<KW><<<hb, RS_THREADS, npass * 256 * 4, ctx->stream>>>(keys[0], n, npass, (unsigned long long*)ctx->rs_hist.p); LAUNCHED();
+    k_rs_scan<<<npass, 256, 0, ctx->stream>>>((unsigned long long*)ctx->rs_hist.p); LAUNCHED();
+    const int smem = TILE * KW * 8 + (HAS_VAL ? TILE * 4 : 16);
+    int cur = 0;
+    for (int p = 0; p < npass; p++) {
+        CK(cudaMemsetAsync(ctx->rs_status.p, 0, ntiles * 256 * 4, ctx->stream));
+        cudaEvent_t a = get_event(ctx), b = get_event(ctx);
+        cudaEventRecord(a, ctx->stream);
+        k_rs_onesweep<KW, HAS_VAL><<<(unsigned)ntiles, RS_THREADS, smem, ctx->stream>>>(
+            keys[cur], keys[cur ^ 1], HAS_VAL ? vals[cur] : nullptr, HAS_VAL ? vals[cur ^ 1] : nullptr, n, p,
+            (const unsigned long long*)ctx->rs_hist.p + (size_t)p * 256, (u32*)ctx->rs_status.p, (u32*)ctx->rs_tilectr.p + p);
+        LAUNCHED();
+        cudaEventRecord(b, ctx->stream);
+        ctx->spans.push_back({a, b, HAS_VAL ? SPAN_SORT : SPAN_DOM});
+        cur ^= 1;
+    }
+    *result_buf = cur;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static SolidityParams make_sp(dskgpu_ctx* ctx)
+{
+    SolidityParams sp; memset(&sp, 0, sizeof sp);
+    sp.kind = ctx->cfg.solidity_kind; sp.nbanks = ctx->NB; sp.histo2d = ctx->cfg.histo2d;
+    for (int i = 0; i < MAXB; i++) { sp.amin[i] = ctx->cfg.abundance_min[i]; sp.solid_vec[i] = ctx->cfg.solid_vec[i]; }
+    sp.amax = ctx->cfg.abundance_max;
+    if (sp.nbanks == 1) sp.kind = DSKGPU_SOLIDITY_SUM;          // ConfigurationAlgorithm.cpp:261-264
+    return sp;
+}
+
+// count records [rb, re) (nk k-mers in total) through the sort path
+template <int KW>
+static int count_by_sort(dskgpu_ctx* ctx, const u64* recs, u64 rb, u64 re, u64 nk, u64 out_cap)
+{
+    if (nk == 0) return 0;
+    int rc;
+    for (int i = 0; i < 2; i++) {
+        if ((rc = ensure(ctx, ctx->keys[i], nk * KW * 8 + 64))) return rc;
+        if (ctx->NB > 1 && (rc = ensure(ctx, ctx->banks[i], nk * 4 + 64))) return rc;
+    }
+    Counters* ctr = (Counters*)ctx->ctr.p;
+    CK(cudaMemsetAsync(&ctr->expand_cursor, 0, 8, ctx->stream));
+    const unsigned gb = (unsigned)std::min<u64>((re - rb + 255) / 256, 148 * 16);
+    k_expand_keys<KW><<<gb, 256, 0, ctx->stream>>>(recs, rb, re, ctx->k, (u64*)ctx->keys[0].p, (u32*)ctx->banks[0].p, ctx->NB, ctr); LAUNCHED();
+    u64* kk[2] = {(u64*)ctx->keys[0].p, (u64*)ctx->keys[1].p};
+    u32* vv[2] = {(u32*)ctx->banks[0].p, (u32*)ctx->banks[1].p};
+    const int npass = (2 * ctx->k + 7) / 8;
+    int res = 0;
+    if (ctx->NB > 1) rc = radix_sort<KW, true>(ctx, kk, vv, nk, npass, &res);
+    else rc = radix_sort<KW, false>(ctx, kk, vv, nk, npass, &res);
+    if (rc) return rc;
+    const unsigned gr = (unsigned)std::min<u64>((nk + 255) / 256, 148 * 16);
+    k_rle_emit<KW><<<gr, 256, 0, ctx->stream>>>(kk[res], vv[res], nk, make_sp(ctx), (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
+                                                (unsigned long long*)ctx->hist.p, (unsigned long long*)ctx->hist2d.p, ctr); LAUNCHED();
+    ctx->st.nb_groups_sort++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int KW>
+static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm, u64 total_kmers)
+{
+    // prec/pkm: records / k-mers of each partition, stored contiguously in `recs` in this order
+    const size_t np = prec.size();
+    std::vector<u64> off(np + 1, 0);
+    for (size_t i = 0; i < np; i++) off[i + 1] = off[i] + prec[i];
+    Counters* ctr = (Counters*)ctx->ctr.p;
+    const SolidityParams sp = make_sp(ctx);
+    int rc;
+    // capacity of the solid set: every solid k-mer holds at least min(abundance_min) occurrences
+    long long amin = ctx->cfg.abundance_min[0];
+    for (int b = 1; b < ctx->NB; b++) amin = std::min<long long>(amin, ctx->cfg.abundance_min[b]);
+    if (amin < 1 || sp.kind == DSKGPU_SOLIDITY_CUSTOM) amin = 1;
+    const u64 out_cap = total_kmers / (u64)amin + 1024;
+    for (int i = 0; i < 2; i++) {
+        if ((rc = ensure(ctx, ctx->skeys[i], out_cap * KW * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->svals[i], out_cap * 4))) return rc;
+    }
+    const int mode = ctx->cfg.count_mode;
+    const int log2s = ctx->cfg.hash_log2_slots > 0 ? ctx->cfg.hash_log2_slots : 22;
+    u64 nslots = (u64)1 << log2s;
+    const double load_max = 0.6;
+    const u64 sort_cap = (u64)1 << 28;                             // keys per sort-path group
+
+    auto run_hash = [&](size_t pb, size_t pe, u64 kmers, u64 slots, int gi) -> int {
+        int rc2;
+        if ((rc2 = ensure(ctx, ctx->tkeys, slots * KW * 8))) return rc2;
+        if ((rc2 = ensure(ctx, ctx->tcounts, slots * 4 * (u64)ctx->NB))) return rc2;
+        const u64 rb = off[pb], re = off[pe];
+        const unsigned gi_blocks = (unsigned)std::min<u64>((re - rb + 255) / 256, 148 * 8);
+        cudaEvent_t a = get_event(ctx), b = get_event(ctx);
+        cudaEventRecord(a, ctx->stream);
+        k_hash_insert<KW><<<gi_blocks ? gi_blocks : 1, 256, 0, ctx->stream>>>(recs, rb, re, ctx->k, (u64*)ctx->tkeys.p, (u32*)ctx->tcounts.p,
+                                                                              (u32)(slots - 1), ctx->NB, ctr); LAUNCHED();
+        cudaEventRecord(b, ctx->stream);
+        ctx->spans.push_back({a, b, SPAN_DOM});
+        const unsigned gs = (unsigned)std::min<u64>((slots + 255) / 256, 148 * 8);
+        k_hash_scan<KW><<<gs, 256, 0, ctx->stream>>>((u64*)ctx->tkeys.p, (u32*)ctx->tcounts.p, (u32)slots, sp, 0, (u64*)ctx->skeys[0].p,
+                                                     (u32*)ctx->svals[0].p, out_cap, (unsigned long long*)ctx->hist.p,
+                                                     (unsigned long long*)ctx->hist2d.p, ctr); LAUNCHED();
+        ctx->st.nb_groups_hash++;
+        (void)gi; (void)kmers;
+        return 0;
+    };
+    auto init_table = [&](u64 slots) -> int {
+        int rc2;
+        if ((rc2 = ensure(ctx, ctx->tkeys, slots * KW * 8))) return rc2;
+        if ((rc2 = ensure(ctx, ctx->tcounts, slots * 4 * (u64)ctx->NB))) return rc2;
+        k_fill_u64<<<148 * 4, 256, 0, ctx->stream>>>((u64*)ctx->tkeys.p, slots * KW, ~0ULL); LAUNCHED();
+        CK(cudaMemsetAsync(ctx->tcounts.p, 0, slots * 4 * (u64)ctx->NB, ctx->stream));
+        return 0;
+    };
+
+    SpanGuard g(ctx, SPAN_COUNT);
+    if (mode == DSKGPU_COUNT_SORT) {
+        size_t p = 0;
+        while (p < np) {
+            size_t q = p; u64 km = 0;
+            while (q < np && (q == p || km + pkm[q] <= sort_cap)) { km += pkm[q]; q++; }
+            if ((rc = count_by_sort<KW>(ctx, recs, off[p], off[q], km, out_cap))) return rc;
+            p = q;
+        }
+        return 0;
+    }
+    // hash (forced) or auto.  The table is sized once; groups of consecutive partitions are sized so that the
+    // estimated number of distinct k-mers stays under load_max * nslots.  The distinct/total ratio r is measured
+    // on the first group (sized for the worst case r = 1).
+    u64 max_part = 0; for (size_t i = 0; i < np; i++) max_part = std::max(max_part, pkm[i]);
+    if (mode == DSKGPU_COUNT_HASH) { while ((double)nslots * load_max < (double)max_part && nslots < ((u64)1 << 31)) nslots <<= 1; }
+    if ((rc = init_table(nslots))) return rc;
+    double r = 1.0; bool have_r = false;
+    size_t p = 0; int gi = 0;
+    while (p < np) {
+        const double capk = (double)nslots * load_max / r;
+        size_t q = p; u64 km = 0;
+        while (q < np && km + pkm[q] <= (u64)capk) { km += pkm[q]; q++; }
+        if (q == p) {
+            // a single partition exceeds the table: occupancy picks the sort path
+            if ((rc = count_by_sort<KW>(ctx, recs, off[p], off[p + 1], pkm[p], out_cap))) return rc;
+            p++; continue;
+        }
+        if (km == 0) { p = q; continue; }
+        u64 d0 = 0;
+        if (!have_r) { CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); d0 = ctx->h_ctr->distinct_n; }
+        if ((rc = run_hash(p, q, km, nslots, gi++))) return rc;
+        if (!have_r) {
+            CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->h_ctr->hash_overflow) FAIL(DSKGPU_ERR_OVERFLOW, "hash table overflow in the calibration group");
+            double dr = (double)(ctx->h_ctr->distinct_n - d0) / (double)km;
+            r = std::min(1.0, std::max(0.02, dr * 1.3 + 0.01)); have_r = true;
+        }
+        p = q;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static float span_ms(dskgpu_ctx* ctx, int kind, u32* count = nullptr)
+{
+    float tot = 0; u32 c = 0;
+    for (auto& s : ctx->spans) if (s.kind == kind) { float ms = 0; if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) tot += ms; c++; }
+    if (count) *count = c;
+    return tot;
+}
+
+template <int KW>
+static int finish_impl(dskgpu_ctx* ctx)
+{
+    Counters* ctr = (Counters*)ctx->ctr.p;
+    int rc;
+    if (ctx->stream_open) close_stream(ctx);
+    CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_ss, ctx->ss.p, sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->k2_inflight = false;
+    if (ctx->h_ss->err) FAIL(DSKGPU_ERR_FORMAT, "device record scanner rejected the input (flags 0x%x): not plain FASTA / 4-line FASTQ", ctx->h_ss->err);
+    if (ctx->h_ctr->overflow) FAIL(DSKGPU_ERR_OVERFLOW, "super-k-mer record buffer overflow");
+    if (ctx->h_ctr->kmers_valid != ctx->h_ctr->kmers_in_recs)
+        FAIL(DSKGPU_ERR_OVERFLOW, "internal: %llu valid k-mers but %llu packed in records", ctx->h_ctr->kmers_valid, ctx->h_ctr->kmers_in_recs);
+    const u64 nrec = ctx->h_ctr->nrec, nkm = ctx->h_ctr->kmers_valid;
+    ctx->st.nb_sequences = ctx->h_ss->nsep; ctx->st.nb_nucleotides = ctx->h_ss->nbase;
+    ctx->st.kmers_nb_valid = nkm; ctx->st.nb_superkmers = nrec; ctx->st.superkmer_bytes = nrec * (u64)ctx->RW * 8;
+
+    // ---- partition plan: P partitions of ~ (table capacity / 4) k-mers each --------------------------------
+    const int log2s = ctx->cfg.hash_log2_slots > 0 ? ctx->cfg.hash_log2_slots : 22;
+    const u64 target = std::max<u64>(((u64)1 << log2s) * 6 / 10 / 4, 4096);
+    u32 P = ctx->cfg.nb_partitions > 0 ? (u32)ctx->cfg.nb_partitions : (u32)std::min<u64>(4096, (nkm + target - 1) / target);
+    if (P < 1) P = 1;
+    if (P > 4096) P = 4096;
+    ctx->nparts = P; ctx->st.nb_partitions = P;
+    std::vector<u64> prec(P, 0), pkm(P, 0);
+    if (nrec) {
+        SpanGuard g(ctx, SPAN_PART);
+        if ((rc = ensure(ctx, ctx->part_recs, P * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->part_kmers, P * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->cursor, P * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->dstbase, P * 8))) return rc;
+        CK(cudaMemsetAsync(ctx->part_recs.p, 0, P * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->part_kmers.p, 0, P * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->cursor.p, 0, P * 8, ctx->stream));
+        const unsigned hb = (unsigned)std::min<u64>((nrec + 2047) / 2048, 148 * 8);
+        k_part_hist<<<hb, 256, 2 * P * 4, ctx->stream>>>((const u32*)ctx->meta.p, nrec, P, (unsigned long long*)ctx->part_recs.p,
+                                                        (unsigned long long*)ctx->part_kmers.p); LAUNCHED();
+        CK(cudaMemcpyAsync(prec.data(), ctx->part_recs.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(pkm.data(), ctx->part_kmers.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if ((rc = ensure(ctx, ctx->precs, nrec * (u64)ctx->RW * 8 + 64))) return rc;
+        std::vector<u64*> dst(P);
+        u64 o = 0;
+        for (u32 i = 0; i < P; i++) { dst[i] = (u64*)ctx->precs.p + o * ctx->RW; o += prec[i]; }
+        CK(cudaMemcpyAsync(ctx->dstbase.p, dst.data(), P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));      // dst is a stack vector
+        const unsigned sb = (unsigned)((nrec + SC_THREADS * SC_RPT - 1) / (SC_THREADS * SC_RPT));
+        const size_t smem = (size_t)((P + 1) & ~1u) * 4 + (size_t)P * 8;
+        k_part_scatter<KW><<<sb, SC_THREADS, smem, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, nrec, P,
+                                                                 (u64* const*)ctx->dstbase.p, (unsigned long long*)ctx->cursor.p); LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    ctx->h_part_recs = prec; ctx->h_part_kmers = pkm;
+
+    // ---- count -----------------------------------------------------------------------------------------------
+    if (nrec) { if ((rc = count_all<KW>(ctx, (const u64*)ctx->precs.p, prec, pkm, nkm))) return rc; }
+    CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ctr->hash_overflow) FAIL(DSKGPU_ERR_OVERFLOW, "hash table overflow (distinct k-mer estimate too low)");
+    if (ctx->h_ctr->overflow) FAIL(DSKGPU_ERR_OVERFLOW, "solid k-mer buffer overflow");
+    ctx->n_solid = ctx->h_ctr->solid_n;
+    ctx->st.kmers_nb_distinct = ctx->h_ctr->distinct_n; ctx->st.kmers_nb_solid = ctx->n_solid;
+
+    // ---- order the solid set (ascending k-mer value, as the reference emits within a partition) ------------------
+    ctx->solid_buf = 0;
+    if (ctx->n_solid) {
+        SpanGuard g(ctx, SPAN_SORT);
+        u64* kk[2] = {(u64*)ctx->skeys[0].p, (u64*)ctx->skeys[1].p};
+        u32* vv[2] = {(u32*)ctx->svals[0].p, (u32*)ctx->svals[1].p};
+        if ((rc = radix_sort<KW, true>(ctx, kk, vv, ctx->n_solid, (2 * ctx->k + 7) / 8, &ctx->solid_buf))) return rc;
+    }
+    // ---- results to the host ---------------------------------------------------------------------------------------
+    CK(cudaMemcpyAsync(ctx->h_hist, ctx->hist.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_hist + DSKGPU_HISTO_LEN, ctx->hist2d.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    if (!ctx->cfg.keep_results_on_device && ctx->n_solid) {
+        if (ctx->n_solid > ctx->h_solid_cap) {
+            if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
+            if (ctx->h_svals) cudaFreeHost(ctx->h_svals);
+            ctx->h_solid_cap = ctx->n_solid + ctx->n_solid / 4;
+            CK(cudaMallocHost((void**)&ctx->h_skeys, ctx->h_solid_cap * KW * 8));
+            CK(cudaMallocHost((void**)&ctx->h_svals, ctx->h_solid_cap * 4));
+        }
+        CK(cudaMemcpyAsync(ctx->h_skeys, ctx->skeys[ctx->solid_buf].p, ctx->n_solid * KW * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_svals, ctx->svals[ctx->solid_buf].p, ctx->n_solid * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->results_on_host = true;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->st.ms_parse = span_ms(ctx, SPAN_PARSE); ctx->st.ms_superk = span_ms(ctx, SPAN_SUPERK);
+    ctx->st.ms_partition = span_ms(ctx, SPAN_PART); ctx->st.ms_count = span_ms(ctx, SPAN_COUNT);
+    ctx->st.ms_sort = span_ms(ctx, SPAN_SORT);
+    ctx->st.ms_dominant_kernel = span_ms(ctx, SPAN_DOM, &ctx->st.dominant_kernel_launches);
+    ctx->st.ms_total = ctx->st.ms_parse + ctx->st.ms_superk + ctx->st.ms_partition + ctx->st.ms_count + ctx->st.ms_sort;
+    ctx->state = 1;
+    return DSKGPU_OK;
+}
+
+extern "C" {
+
+int dskgpu_finish(dskgpu_ctx* ctx)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    if (ctx->state != 0) FAIL(DSKGPU_ERR_STATE, "finish called twice");
+    return ctx->KW == 1 ? finish_impl<1>(ctx) : finish_impl<2>(ctx);
+}
+
+int dskgpu_num_partitions(dskgpu_ctx* ctx) { if (!ctx || ctx->state != 1) return DSKGPU_ERR_STATE; return 1; }
+
+int dskgpu_partition(dskgpu_ctx* ctx, int p, const uint64_t** kmers, const uint32_t** counts, uint64_t* n, int* words)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "results requested before finish");
+    if (p != 0) FAIL(DSKGPU_ERR_ARG, "partition %d out of range", p);
+    if (ctx->n_solid && !ctx->results_on_host) FAIL(DSKGPU_ERR_STATE, "results were kept on the device (keep_results_on_device)");
+    if (kmers) *kmers = ctx->h_skeys; if (counts) *counts = ctx->h_svals; if (n) *n = ctx->n_solid; if (words) *words = ctx->KW;
+    return DSKGPU_OK;
+}
+
+int dskgpu_partition_device(dskgpu_ctx* ctx, int p, const void** d_kmers, const void** d_counts, uint64_t* n, int* words)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "results requested before finish");
+    if (p != 0) FAIL(DSKGPU_ERR_ARG, "partition %d out of range", p);
+    if (d_kmers) *d_kmers = ctx->skeys[ctx->solid_buf].p; if (d_counts) *d_counts = ctx->svals[ctx->solid_buf].p;
+    if (n) *n = ctx->n_solid; if (words) *words = ctx->KW;
+    return DSKGPU_OK;
+}
+
+int dskgpu_histogram(dskgpu_ctx* ctx, uint64_t* hist1d, uint64_t* hist2d)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "histogram requested before finish");
+    if (hist1d) memcpy(hist1d, ctx->h_hist, sizeof(uint64_t) * DSKGPU_HISTO_LEN);
+    if (hist2d) memcpy(hist2d, ctx->h_hist + DSKGPU_HISTO_LEN, sizeof(uint64_t) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2);
+    return DSKGPU_OK;
+}
+
+int dskgpu_get_stats(dskgpu_ctx* ctx, dskgpu_stats* out)
+{
+    if (!ctx || !out) return DSKGPU_ERR_ARG;
+    *out = ctx->st;
+    return DSKGPU_OK;
+}
+
+int dskgpu_record_bytes(dskgpu_ctx* ctx) { return ctx ? ctx->RW * 8 : DSKGPU_ERR_ARG; }
+
+// multi-GPU exchange: implemented in a later section of this file
+int dskgpu_xchg_counts(dskgpu_ctx* ctx, uint64_t*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
+int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
+int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void**, size_t*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
+int dskgpu_xchg_send_buffer(dskgpu_ctx* ctx, void**, size_t*, uint64_t*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
+int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
+int dskgpu_xchg_scatter(dskgpu_ctx* ctx) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// host self checks (same functions the kernels run; no GPU needed)
+// ---------------------------------------------------------------------------------------------------------------
+int64_t dskgpu_selftest_scan(const char* bytes, size_t n, int format, uint8_t* out, size_t out_cap)
+{
+    // emulates the three device passes chunk by chunk: tables -> composition -> emission
+    size_t skip = 0; int fmt = format;
+    if (fmt != DSKGPU_FMT_LINES) { int det = detect_format(bytes, n, &skip); if (!det) return 0; if (fmt == DSKGPU_FMT_AUTO) fmt = det; }
+    const u8* raw = (const u8*)bytes;
+    const u64 lo = skip, hi = n;
+    int state = (fmt == FMT_FASTA) ? ST_HDR : 0;
+    size_t w = 0; int err = 0;
+    const u64 c0 = lo / SCAN_BPT, c1 = (hi + SCAN_BPT - 1) / SCAN_BPT;
+    for (u64 ci = c0; ci < c1; ci++) {
+        Chunk c; c.active = 0; u64 a = ci * SCAN_BPT;
+        for (int i = 0; i < SCAN_BPT; i++) { u64 x = a + i; bool in = x >= lo && x < hi; c.b[i] = in ? raw[x] : 0; c.active |= (in ? 1u : 0u) << i; }
+        c.prev = (a > lo && a <= hi) ? raw[a - 1] : '\n';
+        u64 last_end = (a + SCAN_BPT < hi) ? a + SCAN_BPT : hi;
+        c.next = (last_end < hi) ? (int)raw[last_end] : -1;
+        Tab t = chunk_table(fmt, c);
+        u8 tmp[SCAN_BPT]; u32 ns = 0, nb = 0;
+        int cnt = chunk_emit(fmt, c, state, tmp, err, ns, nb);
+        if ((u32)cnt != tab_count(t, state)) return -1000 - (int64_t)ci;          // table / emission disagreement
+        int st_chk = state;                                                        // state after emission
+        { int s2 = state, e2 = 0, prev = c.prev; for (int i = 0; i < SCAN_BPT; i++) { if (!((c.active >> i) & 1)) continue;
+              int nx = (i + 1 < SCAN_BPT && ((c.active >> (i + 1)) & 1)) ? c.b[i + 1] : c.next; scan_step(fmt, s2, prev, c.b[i], nx, e2); prev = c.b[i]; } st_chk = s2; }
+        // FASTA states are only meaningful modulo "the next byte is a line start"; compare through one more step
+        if (fmt != FMT_FASTA && tab_state(t, state) != st_chk) return -2000 - (int64_t)ci;
+        for (int i = 0; i < cnt; i++) { if (w < out_cap) out[w] = tmp[i]; w++; }
+        state = tab_state(t, state);
+    }
+    if (err) return -(int64_t)err;
+    return (int64_t)w;
+}
+
+int dskgpu_selftest_minimizers(const uint8_t* codes, size_t n, int k, int m, uint32_t* out_min, uint8_t* out_valid)
+{
+    if (n < (size_t)k) return 0;
+    for (size_t p = 0; p + k <= n; p++) {
+        bool ok = true; u32 best = 0xFFFFFFFFu;
+        for (int i = 0; i < k; i++) if (codes[p + i] >> 2) ok = false;
+        for (int j = 0; j + m <= k; j++) {
+            u32 x = 0; for (int i = 0; i < m; i++) x = (x << 2) | (codes[p + j + i] & 3);
+            u32 v = mmer_value(x, m); if (v < best) best = v;
+        }
+        out_min[p] = best; out_valid[p] = ok;
+    }
+    return (int)(n - k + 1);
+}
+
+// host model of K2 + K4: split a code stream into records exactly like the kernel (tile = whole stream),
+// pack them, then expand them again to canonical k-mers
+int64_t dskgpu_selftest_superkmers(const uint8_t* codes, size_t n, int k, int m, uint64_t* out_kmers, size_t cap, uint64_t* n_records)
+{
+    const int KW = k < 32 ? 1 : 2, RW = 2 * KW;
+    const int maxS = rec_max_kmers(KW, k);
+    if (n < (size_t)k) { if (n_records) *n_records = 0; return 0; }
+    const size_t npos = n - k + 1;
+    std::vector<u32> mn(npos); std::vector<u8> valid(npos);
+    dskgpu_selftest_minimizers(codes, n, k, m, mn.data(), valid.data());
+    size_t w = 0; u64 nrec = 0;
+    size_t p = 0;
+    while (p < npos) {
+        if (!valid[p]) { p++; continue; }
+        size_t q = p; while (q < npos && valid[q] && mn[q] == mn[p] && (q - p) < (size_t)maxS) q++;
+        const int nk = (int)(q - p);
+        // pack
+        u64 r[4] = {0, 0, 0, 0};
+        for (int i = 0; i < k - 1 + nk; i++) r[i >> 5] |= (u64)(codes[p + i] & 3) << (62 - 2 * (i & 31));
+        r[RW - 1] = (r[RW - 1] & ~0xFFFFULL) | ((u64)nk << 8);
+        // expand
+        if (KW == 1) {
+            Kmer<1> f = rec_first_kmer1(r, k), rc = kmer_revcomp(f, k);
+            for (int j = 0; j < nk; j++) { if (j) kmer_roll(f, rc, rec_base<2>(r, k - 1 + j), k); Kmer<1> c = kmer_canonical(f, rc); if (w < cap) out_kmers[w] = c.w[0]; w++; }
+        } else {
+            Kmer<2> f = rec_first_kmer2(r, k), rc = kmer_revcomp(f, k);
+            for (int j = 0; j < nk; j++) { if (j) kmer_roll(f, rc, rec_base<4>(r, k - 1 + j), k); Kmer<2> c = kmer_canonical(f, rc);
+                if (w < cap) { out_kmers[2 * w] = c.w[0]; out_kmers[2 * w + 1] = c.w[1]; } w++; }
+        }
+        nrec++; p = q;
+    }
+    if (n_records) *n_records = nrec;
+    return (int64_t)w;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// radix.cuh -- K5: LSD radix sort, 8-bit digits, one-sweep (single pass per digit: chained-scan look-back
+// fused into the scatter), keys of KW 64-bit words with an optional 32-bit payload.
+//
+// Replaces SortCommand::execute / executeSort (std::sort per kx-mer bucket, K/PartitionsCommand.cpp:1400-1504).
+// HBM traffic: one histogram read of the keys for all digits, then per digit pass one read + one write.
+//
+// Layout per pass: tile = 256 threads x ITEMS keys, warp-striped.  Ranking inside the tile is stable
+// (match_any per warp, per-warp digit counters, then cross-warp prefix), tile digit counts are published to
+// `status[tile][digit]` (aggregate, then inclusive prefix) and predecessors are looked back, keys are staged
+// through shared memory in tile-sorted order so that global writes are runs of consecutive addresses per digit.
+#pragma once
+#include "kmer_bits.cuh"
+
+namespace dsk {
+#ifdef __CUDACC__
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr u32 RS_FLAG_AGG = 1u << 30, RS_FLAG_INC = 2u << 30, RS_MASK = (1u << 30) - 1u;
+template <int KW> struct RsCfg { static constexpr int ITEMS = (KW == 1) ? 16 : 8; static constexpr int TILE = RS_THREADS * ITEMS; };
+
+template <int KW> __device__ __forceinline__ u32 rs_digit(const u64* key, int pass)
+{
+    return (u32)(key[pass >> 3] >> ((pass & 7) * 8)) & 0xFFu;
+}
+
+// histogram of every digit of every key in one read: hist[pass][256]
+template <int KW>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ keys, u64 n, int npass, unsigned long long* __restrict__ hist)
+{
+    extern __shared__ u32 s_h[];                                  // [npass][256]
+    for (int i = threadIdx.x; i < npass * 256; i += RS_THREADS) s_h[i] = 0;
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (u64)gridDim.x * RS_THREADS) {
+        u64 key[KW];
+#pragma unroll
+        for (int q = 0; q < KW; q++) key[q] = keys[i * KW + q];
+        for (int p = 0; p < npass; p++) atomicAdd(&s_h[p * 256 + rs_digit<KW>(key, p)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * 256; i += RS_THREADS) { u32 v = s_h[i]; if (v) atomicAdd(&hist[i], (unsigned long long)v); }
+}
+
+// exclusive scan of each pass's 256 bins (one block per pass)
+__global__ void __launch_bounds__(256) k_rs_scan(unsigned long long* hist)
+{
+    __shared__ unsigned long long s[256];
+    unsigned long long* h = hist + (u64)blockIdx.x * 256;
+    unsigned long long v = h[threadIdx.x];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    unsigned long long acc = 0;
+    for (int i = 0; i < (int)threadIdx.x; i++) acc += s[i];
+    h[threadIdx.x] = acc;
+}
+
+template <int KW, bool HAS_VAL>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(const u64* __restrict__ in_keys, u64* __restrict__ out_keys,
+                                                            const u32* __restrict__ in_vals, u32* __restrict__ out_vals,
+                                                            u64 n, int pass, const unsigned long long* __restrict__ gbase /*[256]*/,
+                                                            u32* status /*[ntiles][256]*/, u32* tile_counter)
+{
+    constexpr int ITEMS = RsCfg<KW>::ITEMS;
+    constexpr int TILE = RsCfg<KW>::TILE;
+    __shared__ u32 s_wc[RS_WARPS][256];                           // per-warp digit counters -> exclusive over warps
+    __shared__ u32 s_dstart[256];                                 // first tile-sorted index of each digit
+    __shared__ unsigned long long s_goff[256];                    // global index of tile-sorted index 0 of each digit
+    extern __shared__ __align__(16) unsigned char s_dyn[];          // tile-sorted staging: keys then payloads
+    u64* s_keys = reinterpret_cast<u64*>(s_dyn);
+    u32* s_vals = reinterpret_cast<u32*>(s_dyn + (size_t)TILE * KW * 8);
+    __shared__ u32 s_tile;
+    __shared__ u32 s_wsum[RS_WARPS];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int i = t; i < RS_WARPS * 256; i += RS_THREADS) (&s_wc[0][0])[i] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 tile0 = (u64)tile * TILE;
+    const u32 nvalid = (u32)((n - tile0 < (u64)TILE) ? (n - tile0) : (u64)TILE);
+
+    // 1. load (warp-striped) and rank within the warp, stable
+    u64 key[ITEMS][KW]; u32 val[ITEMS]; u32 rd[ITEMS];              // rd = rank | digit << 16
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        u32 li = (u32)warp * 32 * ITEMS + r * 32 + lane;           // index inside the tile
+        bool ok = li < nvalid;
+#pragma unroll
+        for (int q = 0; q < KW; q++) key[r][q] = ok ? in_keys[(tile0 + li) * KW + q] : ~0ULL;
+        if (HAS_VAL) val[r] = ok ? in_vals[tile0 + li] : 0u;
+        u32 d = ok ? rs_digit<KW>(key[r], pass) : 256u;            // padding sorts after everything, never written
+        u32 peers = __match_any_sync(0xFFFFFFFFu, d);
+        u32 pre = (d < 256u) ? s_wc[warp][d] : 0u;
+        rd[r] = (pre + __popc(peers & ((1u << lane) - 1u))) | (d << 16);
+        __syncwarp();
+        if (d < 256u && lane == (__ffs((int)peers) - 1)) s_wc[warp][d] = pre + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // 2. thread d: exclusive prefix of digit d over warps, tile count, publish + look back
+    {
+        const int d = t;
+        u32 s = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) { u32 c = s_wc[w][d]; s_wc[w][d] = s; s += c; }
+        volatile u32* st = status + (u64)tile * 256 + d;
+        u32 excl = 0;
+        if (tile == 0) { *st = s | RS_FLAG_INC; }
+        else {
+            *st = s | RS_FLAG_AGG;
+            int lt = (int)tile - 1;
+            while (lt >= 0) {
+                u32 v = *(volatile u32*)(status + (u64)lt * 256 + d);
+                if (v & RS_FLAG_INC) { excl += v & RS_MASK; break; }
+                if (v & RS_FLAG_AGG) { excl += v & RS_MASK; lt--; }
+            }
+            *st = (excl + s) | RS_FLAG_INC;
+        }
+        // exclusive scan of s over digits -> s_dstart
+        u32 inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        u32 wpre = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) if (w < warp) wpre += s_wsum[w];
+        u32 dstart = wpre + inc - s;
+        s_dstart[d] = dstart;
+        s_goff[d] = gbase[d] + (unsigned long long)excl - (unsigned long long)dstart;
+    }
+    __syncthreads();
+
+    // 3. stage in tile-sorted order
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        u32 d = rd[r] >> 16;
+        if (d < 256u) {
+            u32 idx = s_dstart[d] + s_wc[warp][d] + (rd[r] & 0xFFFFu);
+#pragma unroll
+            for (int q = 0; q < KW; q++) s_keys[idx * KW + q] = key[r][q];
+            if (HAS_VAL) s_vals[idx] = val[r];
+        }
+    }
+    __syncthreads();
+
+    // 4. write out: consecutive tile-sorted indices of one digit are consecutive in global memory
+    for (u32 i = t; i < nvalid; i += RS_THREADS) {
+        u64 kk[KW];
+#pragma unroll
+        for (int q = 0; q < KW; q++) kk[q] = s_keys[i * KW + q];
+        u32 d = rs_digit<KW>(kk, pass);
+        u64 g = s_goff[d] + i;
+#pragma unroll
+        for (int q = 0; q < KW; q++) out_keys[g * KW + q] = kk[q];
+        if (HAS_VAL) out_vals[g] = s_vals[i];
+    }
+}
+
+#endif  // __CUDACC__
+}  // namespace dsk

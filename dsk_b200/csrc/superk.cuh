@@ -1,0 +1,302 @@
+// superk.cuh -- K2: code stream -> minimizers -> super-k-mer records;  K3: partition histogram + scatter.
+//
+// Replaces (K/ = thirdparty/gatb-core/gatb-core/src/gatb/kmer/impl/):
+//   ModelCanonical::next / ModelMinimizer::next       K/Model.hpp:877-884, :1106-1139
+//   Sequence2SuperKmer::KmerFunctor                   K/Sequence2SuperKmer.hpp:90-133
+//   FillPartitions::processSuperkmer, SuperKmer::save K/SortingCountAlgorithm.cpp:1084-1154, K/Model.hpp:1386-1471
+//
+// The reference walks each read sequentially (rolling k-mer + "did the minimizer fall out" state).  Here the
+// minimizer of a window is recomputed as a pure function (it is one: K/Model.hpp:1254-1287), so every
+// position of the code stream is independent: a tile of 2048 positions is packed to 2 bits in shared memory,
+// every thread evaluates 8 consecutive windows (m-mer values shared through smem, sliding minimum with a
+// prefix/suffix split), and super-k-mer boundaries are found with bit scans over per-tile bitmaps.
+// Super-k-mers never span tiles or invalid windows; their boundaries are not observable in the output.
+#pragma once
+#include "kmer_bits.cuh"
+#include "scan.cuh"
+
+namespace dsk {
+
+constexpr int SK_THREADS = 256;
+constexpr int SK_PPT = 8;                         // positions per thread
+constexpr int SK_TP = SK_THREADS * SK_PPT;        // 2048 positions per tile
+constexpr int SK_HALO = 64;                       // >= k-1
+constexpr u32 SK_NOMIN = 0xFFFFFFFFu;
+
+struct Counters {
+    unsigned long long nrec;          // super-k-mer records written
+    unsigned long long kmers_valid;   // valid k-mers seen
+    unsigned long long kmers_in_recs; // sum of nk over records (must equal kmers_valid)
+    unsigned long long solid_n;       // solid (k-mer,count) pairs emitted
+    unsigned long long distinct_n;    // distinct k-mers seen by the counters
+    unsigned int overflow;            // record buffer overflow
+    unsigned int hash_overflow;
+    unsigned long long expand_cursor; // sort path: keys written
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ u32 sk_pidx(u32 p) { return p + (p >> 3); }     // padded smem index (conflict-free strips)
+
+template <int KW>
+__global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict__ codes, const StreamState* __restrict__ ss,
+                                                           int k, int m, int bank, u64* __restrict__ recs,
+                                                           u32* __restrict__ rec_meta, u64 rec_cap, Counters* ctr)
+{
+    constexpr int RW = 2 * KW;
+    __shared__ u64 s_pk[SK_TP / 32 + 8];                         // 2-bit bases, MSB first, 32 per word
+    __shared__ u64 s_bad[(SK_TP + SK_HALO) / 64 + 2];            // invalid flags, MSB first, 64 per word
+    __shared__ u32 s_mv[SK_TP + SK_HALO + (SK_TP + SK_HALO) / 8 + 8];
+    __shared__ u32 s_start[SK_TP / 32];                          // super-k-mer run starts, MSB first
+    __shared__ u32 s_brk[SK_TP / 32 + 9];                        // run start or invalid window
+    __shared__ u32 s_last[SK_THREADS];                           // minimizer of each thread's last window
+    __shared__ u32 s_wsum[SK_THREADS / 32];
+    __shared__ unsigned long long s_goff;
+    __shared__ u32 s_nvalid;
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const u64 total = ss->total;
+    const u64 limit = (total >= (u64)k) ? total - (u64)(k - 1) : 0;   // windows starting at >= limit are not complete
+    const u64 tile0 = (u64)blockIdx.x * SK_TP;
+    if (tile0 >= limit) return;
+    const int w = k - m + 1;                                     // m-mers per window
+    const int maxS = rec_max_kmers(KW, k);
+    const u32 mmask = (1u << (2 * m)) - 1u;
+
+    // ---- 1. load 8 codes per thread, pack to 2 bits + invalid bitmap ---------------------------------
+    auto load8 = [&](int ti) {
+        u64 v = *reinterpret_cast<const u64*>(codes + tile0 + 8 * (u64)ti);
+        u32 p16 = 0, b8 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            u32 c = (u32)(v >> (8 * j)) & 0xFFu;
+            p16 |= (c & 3u) << (14 - 2 * j);
+            b8 |= ((c >> 2) ? 1u : 0u) << (7 - j);
+        }
+        reinterpret_cast<u16*>(s_pk)[(ti >> 2) * 4 + (3 - (ti & 3))] = (u16)p16;
+        reinterpret_cast<u8*>(s_bad)[(ti >> 3) * 8 + (7 - (ti & 7))] = (u8)b8;
+    };
+    load8(t);
+    if (t < SK_HALO / 8) load8(SK_THREADS + t);
+    if (t < 6) s_pk[(SK_TP + SK_HALO) / 32 + t] = 0;
+    if (t < 2) s_bad[(SK_TP + SK_HALO) / 64 + t] = ~0ULL;
+    if (t < 9) s_brk[SK_TP / 32 + t] = 0xFFFFFFFFu;
+    if (t == 0) s_nvalid = 0;
+    __syncthreads();
+
+    auto get64 = [&](u32 p) -> u64 {                              // 32 bases starting at position p
+        u32 wi = p >> 5, o = p & 31;
+        u64 a = s_pk[wi], b = s_pk[wi + 1];
+        return o ? ((a << (2 * o)) | (b >> (64 - 2 * o))) : a;
+    };
+    auto getbad64 = [&](u32 p) -> u64 {                           // 64 invalid flags starting at position p
+        u32 wi = p >> 6, o = p & 63;
+        u64 a = s_bad[wi], b = s_bad[wi + 1];
+        return o ? ((a << o) | (b >> (64 - o))) : a;
+    };
+
+    // ---- 2. m-mer selection values (the reference's mmer_lut, computed instead of looked up) --------------
+    auto mvals8 = [&](int ti) {
+        u32 p0 = 8 * (u32)ti;
+        u64 W = get64(p0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            u32 x = (u32)(W >> (64 - 2 * (j + m))) & mmask;
+            s_mv[sk_pidx(p0 + j)] = mmer_value(x, m);
+        }
+    };
+    mvals8(t);
+    if (t < SK_HALO / 8) mvals8(SK_THREADS + t);
+    __syncthreads();
+
+    // ---- 3. sliding minimum over w m-mers for my 8 windows, validity, run-start flags ----------------------
+    const u32 p0 = 8 * (u32)t;
+    u32 mn[8];
+    if (w >= 8) {
+        u32 a[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = s_mv[sk_pidx(p0 + j)];
+        u32 common = a[7];
+        for (int i = 8; i < w; i++) common = min(common, s_mv[sk_pidx(p0 + i)]);
+        u32 sfx[8]; sfx[7] = 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 6; j >= 0; j--) sfx[j] = min(a[j], sfx[j + 1]);
+        u32 pfx = 0xFFFFFFFFu;
+        mn[0] = min(common, sfx[0]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            pfx = min(pfx, s_mv[sk_pidx(p0 + w + j - 1)]);
+            mn[j] = min(min(common, sfx[j]), pfx);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            u32 v = 0xFFFFFFFFu;
+            for (int i = 0; i < w; i++) v = min(v, s_mv[sk_pidx(p0 + j + i)]);
+            mn[j] = v;
+        }
+    }
+    u32 validmask = 0;                                            // bit (7-j): window j is a valid k-mer
+    {
+        u64 b0 = getbad64(p0), b1 = getbad64(p0 + 64);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            u64 x = j ? ((b0 << j) | (b1 >> (64 - j))) : b0;
+            bool ok = ((x >> (64 - k)) == 0) && (tile0 + p0 + j < limit);
+            validmask |= (ok ? 1u : 0u) << (7 - j);
+        }
+    }
+    s_last[t] = ((validmask & 1u) ? mn[7] : SK_NOMIN);
+    __syncthreads();
+    u32 prevmn = t ? s_last[t - 1] : SK_NOMIN;
+    u32 startmask = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        bool v = (validmask >> (7 - j)) & 1u;
+        u32 cur = v ? mn[j] : SK_NOMIN;
+        if (v && cur != prevmn) startmask |= 1u << (7 - j);
+        prevmn = cur;
+    }
+    reinterpret_cast<u8*>(s_start)[(t >> 2) * 4 + (3 - (t & 3))] = (u8)startmask;
+    reinterpret_cast<u8*>(s_brk)[(t >> 2) * 4 + (3 - (t & 3))] = (u8)(startmask | (~validmask & 0xFFu));
+    __syncthreads();
+
+    // ---- 4. split runs longer than maxS, count records, reserve output space -----------------------------------
+    u32 chunkmask = 0;
+    {
+        u32 rel = 0;
+        if ((validmask & 0x80u) && !(startmask & 0x80u)) {       // my first window continues a run: find its start
+            u32 q = p0 - 1;                                       // p0 > 0 here (thread 0 always starts a run)
+            int wi = (int)(q >> 5);
+            u32 bits = s_start[wi] & (0xFFFFFFFFu << (31 - (q & 31)));
+            while (bits == 0) { wi--; bits = s_start[wi]; }
+            u32 rs = (u32)wi * 32 + 31 - (u32)(__ffs((int)bits) - 1);
+            rel = p0 - rs;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            bool v = (validmask >> (7 - j)) & 1u;
+            if ((startmask >> (7 - j)) & 1u) rel = 0;
+            if (v) { if (rel % (u32)maxS == 0) chunkmask |= 1u << (7 - j); rel++; }
+        }
+    }
+    u32 nch = __popc(chunkmask);
+    u32 nval = __popc(validmask);
+    // block exclusive scan of nch
+    u32 inc = nch;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) s_wsum[warp] = inc;
+    u32 wval = __reduce_add_sync(0xFFFFFFFFu, nval);
+    if (lane == 0 && wval) atomicAdd(&s_nvalid, wval);
+    __syncthreads();
+    u32 wpre = 0, btotal = 0;
+#pragma unroll
+    for (int i = 0; i < SK_THREADS / 32; i++) { u32 s = s_wsum[i]; if (i < warp) wpre += s; btotal += s; }
+    u32 myidx = wpre + inc - nch;
+    if (t == 0) {
+        s_goff = atomicAdd(&ctr->nrec, (unsigned long long)btotal);
+        atomicAdd(&ctr->kmers_valid, (unsigned long long)s_nvalid);
+    }
+    __syncthreads();
+    const u64 goff = s_goff;
+    if (goff + btotal > rec_cap) { if (t == 0) atomicExch(&ctr->overflow, 1u); return; }
+
+    // ---- 5. emit records --------------------------------------------------------------------------------------
+    u32 nk_sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (!((chunkmask >> (7 - j)) & 1u)) continue;
+        u32 p = p0 + j;
+        // next break strictly after p (bounded: s_brk is all ones past the tile)
+        u32 q = p + 1; u32 wi = q >> 5;
+        u32 bits = s_brk[wi] & (0xFFFFFFFFu >> (q & 31));
+        u32 nk;
+        {
+            u32 steps = 0;
+            while (bits == 0 && steps < 9) { wi++; bits = s_brk[wi]; steps++; }
+            u32 nb = bits ? (wi * 32 + (u32)__clz((int)bits)) : (p + (u32)maxS);
+            nk = min((u32)maxS, nb - p);
+        }
+        u64 rw[RW];
+#pragma unroll
+        for (int i = 0; i < RW; i++) rw[i] = get64(p + 32 * i);
+        rw[RW - 1] = (rw[RW - 1] & ~0xFFFFULL) | ((u64)nk << 8) | (u64)bank;
+        u64 ri = goff + myidx;
+        if constexpr (RW == 2) {
+            reinterpret_cast<ulonglong2*>(recs)[ri] = make_ulonglong2(rw[0], rw[1]);
+        } else {
+            reinterpret_cast<ulonglong2*>(recs)[2 * ri] = make_ulonglong2(rw[0], rw[1]);
+            reinterpret_cast<ulonglong2*>(recs)[2 * ri + 1] = make_ulonglong2(rw[2], rw[3]);
+        }
+        rec_meta[ri] = mn[j] | (nk << 24);
+        myidx++; nk_sum += nk;
+    }
+    nk_sum = __reduce_add_sync(0xFFFFFFFFu, nk_sum);
+    if (lane == 0 && nk_sum) atomicAdd(&ctr->kmers_in_recs, (unsigned long long)nk_sum);
+}
+
+// ---- K3a: records/k-mers per partition ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_part_hist(const u32* __restrict__ rec_meta, u64 nrec, u32 nparts,
+                                                   unsigned long long* __restrict__ part_recs,
+                                                   unsigned long long* __restrict__ part_kmers)
+{
+    extern __shared__ u32 s_h[];                                  // [2*nparts]
+    for (u32 i = threadIdx.x; i < 2 * nparts; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (u64)gridDim.x * blockDim.x) {
+        u32 me = rec_meta[i];
+        u32 p = partition_of(me & 0xFFFFFFu, nparts);
+        atomicAdd(&s_h[p], 1u);
+        atomicAdd(&s_h[nparts + p], me >> 24);
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < nparts; i += blockDim.x) {
+        if (s_h[i]) { atomicAdd(&part_recs[i], (unsigned long long)s_h[i]); atomicAdd(&part_kmers[i], (unsigned long long)s_h[nparts + i]); }
+    }
+}
+
+// ---- K3b: scatter records into partition order ------------------------------------------------------------------
+// Block-aggregated: local ranks through smem atomics, one global reservation per (block, partition).
+// dst_base[p] = device pointer (local or NVLink peer) where partition p's records start; cursor[p] = records
+// already placed by this rank.
+constexpr int SC_THREADS = 256;
+constexpr int SC_RPT = 8;
+template <int KW>
+__global__ void __launch_bounds__(SC_THREADS) k_part_scatter(const u64* __restrict__ recs, const u32* __restrict__ rec_meta, u64 nrec,
+                                                             u32 nparts, u64* const* __restrict__ dst_base,
+                                                             unsigned long long* __restrict__ cursor)
+{
+    constexpr int RW = 2 * KW;
+    extern __shared__ u32 s_cnt[];                                // [nparts] counts, then [nparts] reserved bases (u64 as 2 u32)
+    unsigned long long* s_base = reinterpret_cast<unsigned long long*>(s_cnt + ((nparts + 1) & ~1u));
+    const u64 tile0 = (u64)blockIdx.x * SC_THREADS * SC_RPT;
+    for (u32 i = threadIdx.x; i < nparts; i += SC_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    u32 part[SC_RPT], rank[SC_RPT];
+#pragma unroll
+    for (int r = 0; r < SC_RPT; r++) {
+        u64 i = tile0 + (u64)r * SC_THREADS + threadIdx.x;
+        part[r] = 0xFFFFFFFFu;
+        if (i < nrec) { part[r] = partition_of(rec_meta[i] & 0xFFFFFFu, nparts); rank[r] = atomicAdd(&s_cnt[part[r]], 1u); }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < nparts; i += SC_THREADS) {
+        u32 c = s_cnt[i];
+        if (c) s_base[i] = atomicAdd(&cursor[i], (unsigned long long)c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SC_RPT; r++) {
+        u64 i = tile0 + (u64)r * SC_THREADS + threadIdx.x;
+        if (part[r] == 0xFFFFFFFFu) continue;
+        u64 d = s_base[part[r]] + rank[r];
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(dst_base[part[r]]);
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
+        if constexpr (RW == 2) dst[d] = src[i];
+        else { dst[2 * d] = src[2 * i]; dst[2 * d + 1] = src[2 * i + 1]; }
+    }
+}
+
+#endif  // __CUDACC__
+}  // namespace dsk

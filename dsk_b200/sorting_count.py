@@ -1,0 +1,192 @@
+"""Host-side mirror of the reference operator for the counting path.
+
+`SortingCountAlgorithm(bank, props)` follows gatb-core's class of the same name
+(G/src/gatb/kmer/impl/SortingCountAlgorithm.hpp:66-192; options :202-236 of the .cpp) closely enough that
+the parity tests read like the reference's own (G/test/unit/src/kmer/TestDSK.cpp): same option names, same
+defaults, same error for an unhandled k, `execute()`, `getInfo()`, `getSolidCounts()`.  All counting is done
+by libdskgpu.so through the C ABI; this file only parses options, reads bank files and hands bytes over.
+"""
+import gzip
+import os
+
+import numpy as np
+
+from .counter import GpuCounter, DskGpuError
+
+# G/src/gatb/tools/misc/impl/StringsRepository.hpp:81-127
+STR_KMER_SIZE = "-kmer-size"
+STR_KMER_ABUNDANCE_MIN = "-abundance-min"
+STR_KMER_ABUNDANCE_MAX = "-abundance-max"
+STR_SOLIDITY_KIND = "-solidity-kind"
+STR_SOLIDITY_CUSTOM = "-solidity-custom"
+STR_HISTO2D = "-histo2D"
+STR_HISTO = "-histo"
+STR_MINIMIZER_SIZE = "-minimizer-size"
+STR_URI_FILE = "-file"
+STR_URI_OUTPUT = "-out"
+
+NT = "ACTG"
+
+
+def getDefaultProperties():
+    """SortingCountAlgorithm::getOptionsParser defaults (SortingCountAlgorithm.cpp:208-231)."""
+    return {STR_KMER_SIZE: 31, STR_KMER_ABUNDANCE_MIN: "2", STR_KMER_ABUNDANCE_MAX: 2147483647,
+            STR_SOLIDITY_KIND: "sum", STR_HISTO2D: 0, STR_HISTO: 0, STR_MINIMIZER_SIZE: 10}
+
+
+class BankStrings:
+    """In-memory bank of sequences (role of gatb::core::bank::BankStrings in the reference's unit tests)."""
+
+    def __init__(self, *seqs):
+        if len(seqs) == 1 and isinstance(seqs[0], (list, tuple)):
+            seqs = seqs[0]
+        self.seqs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+
+
+class BankFile:
+    """A FASTA/FASTQ file, optionally gzipped (Bank::open on a single uri)."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def read(self):
+        with open(self.path, "rb") as f:
+            head = f.read(2)
+        if head == b"\x1f\x8b":
+            with gzip.open(self.path, "rb") as f:
+                return f.read()
+        with open(self.path, "rb") as f:
+            return f.read()
+
+
+class BankBytes:
+    """File image already in memory."""
+
+    def __init__(self, data):
+        self.data = data
+
+    def read(self):
+        return self.data
+
+
+class BankAlbum:
+    """List of banks (comma separated -file list / BankAlbum)."""
+
+    def __init__(self, banks=None):
+        self.banks = list(banks or [])
+
+    def addBank(self, b):
+        self.banks.append(b)
+
+
+def open_bank(uri):
+    """Bank::open(uri) (G/src/gatb/bank/impl/Bank.cpp:143-160): comma separated list -> album."""
+    parts = [p for p in uri.split(",") if p]
+    if len(parts) == 1:
+        return BankFile(parts[0])
+    return BankAlbum([BankFile(p) for p in parts])
+
+
+class SortingCountAlgorithm:
+    def __init__(self, bank, props=None, device=0, **engine_kw):
+        self.props = dict(getDefaultProperties())
+        if props:
+            self.props.update(props)
+        if isinstance(bank, str):
+            bank = open_bank(bank)
+        self.banks = bank.banks if isinstance(bank, BankAlbum) else [bank]
+        self.device = device
+        self.engine_kw = engine_kw
+        self.info = {}
+        self._solid = None
+        self._hist = None
+
+    # -- option parsing (ConfigurationAlgorithm.cpp:195-264, :478-498) -----------------------------------
+    def _configure(self):
+        p = self.props
+        k = int(p[STR_KMER_SIZE])
+        nb = len(self.banks)
+        kind = str(p[STR_SOLIDITY_KIND])
+        histo2d = int(p.get(STR_HISTO2D, 0)) != 0
+        amin_s = str(p[STR_KMER_ABUNDANCE_MIN])
+        if "auto" in amin_s:
+            raise NotImplementedError("-abundance-min auto (cutoff heuristic) is outside the hot-path scope")
+        amin = [int(x) for x in amin_s.split(",")]
+        if len(amin) > nb:
+            raise ValueError("Kmer solidity has more thresholds than banks")
+        amin = amin + [amin[-1]] * (nb - len(amin))
+        if nb == 1:
+            kind = "sum"                                     # ConfigurationAlgorithm.cpp:261-264
+        per_bank = nb > 1 and (kind != "sum" or histo2d)     # SortingCountAlgorithm.cpp:604-620
+        if histo2d and nb < 2:
+            raise ValueError("histo2D requires at least two banks")
+        solid_vec = None
+        if kind == "custom":
+            sv = str(p.get(STR_SOLIDITY_CUSTOM, ""))
+            solid_vec = [int(c) for c in sv] + [0] * (nb - len(sv))
+        return dict(kmer_size=k, abundance_min=amin, abundance_max=int(p[STR_KMER_ABUNDANCE_MAX]), nb_banks=nb,
+                    per_bank_counts=per_bank, solidity_kind=kind, solid_vec=solid_vec, histo2d=histo2d,
+                    minimizer_size=int(p[STR_MINIMIZER_SIZE]))
+
+    def execute(self):
+        cfg = self._configure()
+        cfg.update(self.engine_kw)
+        try:
+            eng = GpuCounter(device=self.device, **cfg)
+        except DskGpuError as e:
+            if e.code == -1 and "unhandled kmer size" in str(e):
+                raise RuntimeError("Failure because of unhandled kmer size %d" % cfg["kmer_size"]) from e
+            raise
+        with eng:
+            for b, bank in enumerate(self.banks):
+                if isinstance(bank, BankStrings):
+                    eng.push_reads(bank.seqs, bank=b)
+                else:
+                    eng.push_bytes(bank.read(), bank=b, last=True)
+            eng.finish()
+            self._solid = eng.solid()
+            self._hist = eng.histogram()
+            st = eng.stats()
+        self.k = cfg["kmer_size"]
+        self.info = {
+            "kmers_nb_valid": st["kmers_nb_valid"], "kmers_nb_distinct": st["kmers_nb_distinct"],
+            "kmers_nb_solid": st["kmers_nb_solid"], "kmers_nb_weak": st["kmers_nb_distinct"] - st["kmers_nb_solid"],
+            "nb_superkmers": st["nb_superkmers"], "nb_partitions": st["nb_partitions"], "seq_number": st["nb_sequences"],
+            "bank_total_nt": st["nb_nucleotides"], "solidity_kind": cfg["solidity_kind"], "engine": st,
+        }
+        return self
+
+    # -- results -------------------------------------------------------------------------------------------
+    def getInfo(self):
+        return self.info
+
+    def getSolidCounts(self):
+        """(keys uint64[n, words], abundance uint32[n]) -- the content of Partition<Count> "dsk/solid"."""
+        return self._solid
+
+    def getHistogram(self):
+        return self._hist
+
+    def solidKmerStrings(self):
+        keys, cnt = self._solid
+        out = []
+        for row, c in zip(keys, cnt):
+            v = 0
+            for w in reversed(row):
+                v = (v << 64) | int(w)
+            out.append(("".join(NT[(v >> (2 * (self.k - 1 - i))) & 3] for i in range(self.k)), int(c)))
+        return out
+
+    def writeHisto(self, path):
+        """`<out>.histo` text (CountProcessorHistogram.hpp:111-142): 10000 lines "i\\tcount"."""
+        h1, _ = self._hist
+        with open(path, "w") as f:
+            for i in range(1, 10001):
+                f.write("%d\t%d\n" % (i, int(h1[i])))
+
+    def writeHisto2D(self, path):
+        """`<out>.histo2D` text: 10001 rows "%5i:\\t" + 11 x "\\t%6lli" (CountProcessorHistogram.hpp:127-142)."""
+        _, h2 = self._hist
+        with open(path, "w") as f:
+            for i in range(10001):
+                f.write("%5d:\t" % i + "".join("\t%6d" % int(h2[j, i]) for j in range(11)) + "\n")

@@ -1,0 +1,181 @@
+/*
+ * dskgpu.h -- C ABI of the B200-native DSK counting hot path (libdskgpu.so).
+ *
+ * This is the drop-in boundary for gatb-core's SortingCountAlgorithm<span>::execute()
+ * (G/src/gatb/kmer/impl/SortingCountAlgorithm.cpp:636-781; G/ = thirdparty/gatb-core/gatb-core/):
+ * everything between "bank bytes in" and "(canonical k-mer, count) per partition + abundance
+ * histogram out".  Nothing like it exists in the reference (pure C++/pthreads, no FFI); each
+ * entry point names the reference code it replaces.  Plain pointers and sizes only, no C++/torch
+ * types, never throws; every call returns 0 or a negative DSKGPU_ERR_* code.
+ *
+ * One context drives one GPU (one process per GPU); multi-GPU runs create one context per rank
+ * and route super-k-mers between ranks with the dskgpu_xchg_* calls.
+ */
+#ifndef DSKGPU_H
+#define DSKGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSKGPU_ABI_VERSION   1
+#define DSKGPU_MAX_BANKS     16
+#define DSKGPU_HISTO_LEN     10001          /* bins 0..10000 (Histogram.hpp:92, length 10000) */
+#define DSKGPU_HISTO2D_DIM2  11             /* bins 0..10   (CountProcessorHistogram.hpp:173-184) */
+#define DSKGPU_MAX_KMER      63             /* KSIZE_LIST "32 64": k<32 -> 64-bit keys, k<64 -> 128-bit */
+
+/* error codes */
+enum {
+    DSKGPU_OK            =  0,
+    DSKGPU_ERR_ARG       = -1,   /* bad argument / unsupported k (Integer.hpp:479 "unhandled kmer size") */
+    DSKGPU_ERR_CUDA      = -2,   /* CUDA runtime failure (see dskgpu_last_error) */
+    DSKGPU_ERR_NOMEM     = -3,
+    DSKGPU_ERR_FORMAT    = -4,   /* input is not a FASTA / 4-line FASTQ stream the device scanner accepts */
+    DSKGPU_ERR_STATE     = -5,   /* call order violated (push after finish, results before finish, ...) */
+    DSKGPU_ERR_NODEVICE  = -6,   /* no CUDA device: there is NO CPU fallback on the counting path */
+    DSKGPU_ERR_OVERFLOW  = -7    /* internal capacity exceeded */
+};
+
+/* -solidity-kind (G/src/gatb/kmer/impl/CountProcessorSolidity.hpp:186-300) */
+enum { DSKGPU_SOLIDITY_SUM = 0, DSKGPU_SOLIDITY_MIN = 1, DSKGPU_SOLIDITY_MAX = 2,
+       DSKGPU_SOLIDITY_ONE = 3, DSKGPU_SOLIDITY_ALL = 4, DSKGPU_SOLIDITY_CUSTOM = 5 };
+
+/* how a partition is counted (SortingCountAlgorithm.cpp:1489-1497 picks vector vs hash) */
+enum { DSKGPU_COUNT_AUTO = 0, DSKGPU_COUNT_SORT = 1 /* PartitionsByVectorCommand */, DSKGPU_COUNT_HASH = 2 /* PartitionsByHashCommand */ };
+
+/* input stream formats understood by the device record scanner (BankFasta.cpp:485-572) */
+enum { DSKGPU_FMT_AUTO = 0, DSKGPU_FMT_FASTA = 1, DSKGPU_FMT_FASTQ = 2, DSKGPU_FMT_LINES = 3 /* one sequence per line */ };
+
+/* push flags */
+enum { DSKGPU_PUSH_LAST = 1 /* last chunk of this bank (file) */ };
+
+typedef struct dskgpu_ctx dskgpu_ctx;
+
+/* mirrors the options SortingCountAlgorithm reads (SortingCountAlgorithm.cpp:202-236) */
+typedef struct dskgpu_config {
+    int32_t  abi_version;                        /* DSKGPU_ABI_VERSION */
+    int32_t  kmer_size;                          /* -kmer-size        (default 31) */
+    int32_t  minimizer_size;                     /* -minimizer-size   (default 10; clipped to k-1, ConfigurationAlgorithm.cpp:249-251) */
+    int32_t  nb_banks;                           /* number of input banks (files of a comma list), 1..DSKGPU_MAX_BANKS */
+    int32_t  per_bank_counts;                    /* 0: banks are summed while counting (default "sum" path);
+                                                    1: keep one count per bank (-histo2D, -solidity-kind != sum) */
+    int32_t  solidity_kind;                      /* DSKGPU_SOLIDITY_* */
+    int64_t  abundance_min[DSKGPU_MAX_BANKS];    /* -abundance-min (one value or one per bank) */
+    int64_t  abundance_max;                      /* -abundance-max   (default 2^31-1) */
+    uint8_t  solid_vec[DSKGPU_MAX_BANKS];        /* -solidity-custom */
+    int32_t  histo2d;                            /* -histo2D */
+    int32_t  device;                             /* CUDA device ordinal */
+    int32_t  count_mode;                         /* DSKGPU_COUNT_* */
+    int32_t  hash_log2_slots;                    /* 0 = auto; size of the L2-resident hash table */
+    int32_t  nb_partitions;                      /* 0 = auto */
+    int32_t  keep_results_on_device;             /* 1: dskgpu_finish does not copy the solid set to the host */
+    void*    stream;                             /* cudaStream_t to run on, NULL = library-owned stream */
+    int32_t  rank, world_size;                   /* multi-GPU: this context owns partitions p with p % world_size == rank */
+    int32_t  push_chunk_bytes;                   /* 0 = default (64 MiB): granularity of the streamed H2D copy + scan */
+    int32_t  reserved[7];
+} dskgpu_config;
+
+/* stats block: the keys of SortingCountAlgorithm::getInfo() (SortingCountAlgorithm.cpp:728-780) */
+typedef struct dskgpu_stats {
+    uint64_t nb_sequences;          /* bank/sequences/seq_number */
+    uint64_t nb_nucleotides;        /* bank/bank_total_nt */
+    uint64_t kmers_nb_valid;        /* bank/kmers/kmers_nb_valid */
+    uint64_t nb_superkmers;         /* stats/temp_files/nb_superkmers */
+    uint64_t kmers_nb_distinct;     /* stats/kmers/kmers_nb_distinct */
+    uint64_t kmers_nb_solid;        /* stats/kmers/kmers_nb_solid */
+    uint64_t nb_partitions;         /* stats/partitions/nb_partitions */
+    uint64_t nb_groups_hash;        /* stats/partitions/kind/hash   */
+    uint64_t nb_groups_sort;        /* stats/partitions/kind/vector */
+    uint64_t superkmer_bytes;       /* stats/temp_files/total_size */
+    uint64_t gpu_launches;          /* kernels launched by this context since create/reset */
+    /* device time per stage, milliseconds (CUDA events on the context stream) */
+    float ms_parse, ms_superk, ms_partition, ms_count, ms_sort, ms_total;
+    float ms_dominant_kernel;       /* summed duration of the dominant counting kernel (hash insert or radix passes) */
+    uint32_t dominant_kernel_launches;
+    uint32_t reserved[7];
+} dskgpu_stats;
+
+/* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */
+void dskgpu_config_default(dskgpu_config* cfg);
+
+/* replaces: SortingCountAlgorithm ctor + configure() (SortingCountAlgorithm.cpp:525-625) */
+int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out);
+
+/* replaces: fillPartitions() for one chunk of one bank (SortingCountAlgorithm.cpp:1216-1349).
+ * `bytes` are raw FASTA/FASTQ file bytes (already gunzipped), any chunking; records may straddle chunks.
+ * The library scans records, 2-bit encodes, builds minimizers and super-k-mers on the device.
+ * Pass DSKGPU_PUSH_LAST with the final chunk of the bank.  Host memory may be pageable or pinned
+ * (dskgpu_host_alloc); pinned memory is copied without an intermediate staging copy. */
+int dskgpu_push_bytes(dskgpu_ctx* ctx, int bank_id, const char* bytes, size_t n, int format, int flags);
+
+/* same, for bytes that already live in device memory (HBM-resident benchmark leg) */
+int dskgpu_push_device_bytes(dskgpu_ctx* ctx, int bank_id, const void* dev_bytes, size_t n, int format, int flags);
+
+/* replaces: IBank::iterator() -> Sequence2SuperKmer (Sequence2SuperKmer.hpp:138-159) for callers that
+ * already hold parsed sequences: `bases` = concatenated sequences, offsets[nreads+1] delimit them. */
+int dskgpu_push_reads(dskgpu_ctx* ctx, int bank_id, const char* bases, const uint64_t* offsets, size_t nreads);
+
+/* replaces: fillSolidKmers() (SortingCountAlgorithm.cpp:1414-1607) + CountProcessor chain
+ * (histogram -> solidity -> dump; CountProcessorChain.hpp:128-134): partitions the super-k-mers,
+ * counts every partition (hash or sort), filters, histograms, sorts the solid set. */
+int dskgpu_finish(dskgpu_ctx* ctx);
+
+/* replaces: Partition<Count>& getSolidCounts() (SortingCountAlgorithm.hpp:66-192) */
+int dskgpu_num_partitions(dskgpu_ctx* ctx);
+/* partition p: *kmers -> n values of `words` little-endian uint64 each (words = 1 for k<32, 2 for k<64,
+ * low word first), ascending; *counts -> n uint32 abundances (Count::abundance, Abundance.hpp:108-125).
+ * Host pointers owned by the context until destroy/reset. */
+int dskgpu_partition(dskgpu_ctx* ctx, int p, const uint64_t** kmers, const uint32_t** counts, uint64_t* n, int* words);
+/* same data, device pointers (valid until destroy/reset) */
+int dskgpu_partition_device(dskgpu_ctx* ctx, int p, const void** d_kmers, const void** d_counts, uint64_t* n, int* words);
+
+/* replaces: Histogram::save / .histo / .histo2D (Histogram.cpp:43-51; CountProcessorHistogram.hpp:104-159).
+ * hist1d[i] = number of distinct k-mers of abundance i, with the reference's quirks (bins 0 and 10000
+ * always 0, uint16 wrap).  hist2d may be NULL; layout hist2d[dim2 * 10001 + dim1]. */
+int dskgpu_histogram(dskgpu_ctx* ctx, uint64_t* hist1d /*[10001]*/, uint64_t* hist2d /*[11*10001] or NULL*/);
+
+int dskgpu_get_stats(dskgpu_ctx* ctx, dskgpu_stats* out);
+
+/* forget all pushed data and results, keep device buffers (next benchmark step / next pass) */
+int dskgpu_reset(dskgpu_ctx* ctx);
+
+void dskgpu_destroy(dskgpu_ctx* ctx);
+
+/* pinned host memory helpers */
+void* dskgpu_host_alloc(size_t n);
+void  dskgpu_host_free(void* p);
+
+const char* dskgpu_strerror(int code);
+const char* dskgpu_last_error(dskgpu_ctx* ctx);     /* detail text of the last failure (ctx may be NULL) */
+int  dskgpu_device_count(void);
+int  dskgpu_abi_version(void);
+
+/* ---- multi-GPU exchange (replaces the SuperKmerBinFiles temp tier, Storage.cpp:310-589) --------------
+ * After all pushes every rank calls xchg_counts (local per-destination record counts), all-gathers them
+ * out of band (torch.distributed / NCCL), and hands the matrix back to xchg_plan.  Each rank then exposes
+ * its receive buffer; with peer pointers set (CUDA IPC) the partition scatter writes straight into the
+ * owners' HBM over NVLink, otherwise ranks exchange the packed send buffer with an NCCL all-to-all. */
+int dskgpu_xchg_counts(dskgpu_ctx* ctx, uint64_t* send_counts /*[world_size]*/);
+int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts /*[world_size*world_size], row = sender*/);
+int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes);
+int dskgpu_xchg_send_buffer(dskgpu_ctx* ctx, void** d_send, size_t* bytes, uint64_t* send_offsets /*[world_size+1] in records*/);
+int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv /*[world_size]*/);
+int dskgpu_xchg_scatter(dskgpu_ctx* ctx);
+int dskgpu_record_bytes(dskgpu_ctx* ctx);
+
+/* ---- host-side self checks of the device bit logic (no GPU needed; used by the CPU test-suite) ------- */
+/* runs the record-scanner state machine sequentially on the host; out gets one byte per emitted code
+ * (0..3 base, 4|code invalid base, 8 separator).  Returns number of codes or <0. */
+int64_t dskgpu_selftest_scan(const char* bytes, size_t n, int format, uint8_t* out, size_t out_cap);
+/* minimizer value of every k-mer window of a code string (host copy of the device function) */
+int dskgpu_selftest_minimizers(const uint8_t* codes, size_t n, int k, int m, uint32_t* out_min, uint8_t* out_valid);
+/* super-k-mer packing round trip: codes -> records -> canonical k-mers (host copy of pack + expand) */
+int64_t dskgpu_selftest_superkmers(const uint8_t* codes, size_t n, int k, int m, uint64_t* out_kmers /*[n*words]*/, size_t cap, uint64_t* n_records);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSKGPU_H */

@@ -1,0 +1,235 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against
+  * the committed outputs of the real reference binary (tests/golden/ref_runs.json, ref_shell_tests.json),
+  * the reference's unit-test literals (ref_unit_vectors.json),
+  * the CPU oracle on seeded synthetic inputs,
+  * size-independent properties at BASELINE.json's full single-GPU size.
+Bit-exact everywhere (integer work): same multiset of (canonical k-mer, abundance), same histogram."""
+import numpy as np
+import pytest
+
+import oracle
+from dsk_b200 import SortingCountAlgorithm, BankBytes, BankStrings, BankAlbum, GpuCounter
+from dsk_b200.synth import reads_fasta, genome_codes, assembly_fasta
+from util import load_json, read_input, digest, sparse_hist, sparse_hist2d, kmer_to_str
+
+pytestmark = pytest.mark.gpu
+
+SHELL = load_json("ref_shell_tests.json")["tests"]
+UNIT = load_json("ref_unit_vectors.json")
+RUNS = load_json("ref_runs.json")["runs"]
+
+
+def run_gpu(files, k, abundance_min=2, histo2d=False, kind=None, abundance_max=None, **engine):
+    banks = BankAlbum([BankBytes(read_input(f)) for f in files]) if len(files) > 1 else BankBytes(read_input(files[0]))
+    props = {"-kmer-size": k, "-abundance-min": str(abundance_min), "-histo2D": int(histo2d)}
+    if kind:
+        props["-solidity-kind"] = kind
+    if abundance_max is not None:
+        props["-abundance-max"] = abundance_max
+    return SortingCountAlgorithm(banks, props, **engine).execute()
+
+
+def check_against_run(sc, t):
+    info = sc.getInfo()
+    assert info["kmers_nb_valid"] == t["kmers_nb_valid"]
+    assert info["kmers_nb_distinct"] == t["kmers_nb_distinct"]
+    assert info["kmers_nb_solid"] == t["nb_solid"]
+    keys, cnt = sc.getSolidCounts()
+    h1, h2 = sc.getHistogram()
+    assert sparse_hist(h1) == t["hist"]
+    hi = keys[:, 1] if keys.shape[1] == 2 else np.zeros(len(keys), np.uint64)
+    dg, pairs = digest(keys[:, 0], hi, cnt, t["k"])
+    assert [list(p) for p in pairs[:3]] == t["first_kmers"]
+    assert dg == t["kmers_sha256"]
+    if t["histo2d"]:
+        assert sparse_hist2d(h2) == t["hist2d"]
+    # ascending order inside the partition, like the reference's dump
+    v = keys[:, 0].astype(object) if keys.shape[1] == 1 else (keys[:, 1].astype(object) << 64) | keys[:, 0].astype(object)
+    assert all(v[i] < v[i + 1] for i in range(len(v) - 1))
+
+
+@pytest.mark.parametrize("t", RUNS, ids=[t["name"] for t in RUNS])
+def test_reference_runs(t):
+    sc = run_gpu(t["files"], t["k"], t["abundance_min"], t["histo2d"], t.get("solidity_kind"), t.get("abundance_max"))
+    check_against_run(sc, t)
+
+
+SUBSET = [t for t in RUNS if t["name"] in ("c1_k31", "c1_k63", "lowcomplexity.fasta_k31", "lowcomplexity.fasta_k63", "reads.fastq_k31",
+                                           "multiline.fasta_k63", "histo2d_k31", "c123_k31_all", "c1_k21", "c1_k32")]
+
+
+@pytest.mark.parametrize("mode", ["sort", "hash"])
+@pytest.mark.parametrize("t", SUBSET, ids=[t["name"] for t in SUBSET])
+def test_forced_count_modes(t, mode):
+    sc = run_gpu(t["files"], t["k"], t["abundance_min"], t["histo2d"], t.get("solidity_kind"), t.get("abundance_max"), count_mode=mode)
+    check_against_run(sc, t)
+    st = sc.getInfo()["engine"]
+    assert (st["nb_groups_sort"] > 0) == (mode == "sort") and (st["nb_groups_hash"] > 0) == (mode == "hash")
+
+
+@pytest.mark.parametrize("t", SUBSET, ids=[t["name"] for t in SUBSET])
+def test_small_table_many_partitions_and_chunked_push(t):
+    # tiny hash table => many partitions/groups and the occupancy picker sending big partitions to the sort path;
+    # 4 KiB push granularity => records straddle every chunk boundary
+    sc = run_gpu(t["files"], t["k"], t["abundance_min"], t["histo2d"], t.get("solidity_kind"), t.get("abundance_max"),
+                 hash_log2_slots=10, push_chunk_bytes=4096)
+    check_against_run(sc, t)
+    assert sc.getInfo()["engine"]["nb_partitions"] > 1
+
+
+@pytest.mark.parametrize("t", SHELL, ids=[t["name"] for t in SHELL])
+def test_shell_goldens(t):
+    sc = run_gpu(t["files"], t["k"], t["abundance_min"])
+    if "hist" in t:
+        assert sparse_hist(sc.getHistogram()[0]) == t["hist"]
+    if "dsk2ascii" in t:
+        assert "".join("%s %d\n" % p for p in sc.solidKmerStrings()) == t["dsk2ascii"]
+
+
+def test_dsk_check1_literals():
+    d = UNIT["DSK_check1"]
+    for c in d["checks"]:
+        sc = SortingCountAlgorithm(BankStrings(d["seqsets"][c["seqs"]]), {"-kmer-size": c["k"], "-abundance-min": str(c["nks"])}).execute()
+        assert sc.getInfo()["kmers_nb_solid"] == c["nb_solid"], c
+
+
+def test_dsk_check2_values():
+    d = UNIT["DSK_check2"]
+    sc = SortingCountAlgorithm(BankStrings(d["seq"]), {"-kmer-size": 31, "-abundance-min": "1"}).execute()
+    keys, cnt = sc.getSolidCounts()
+    lits = {int(x, 16) for x in d["hex_literals"]}
+    vals = {int(v) for v in keys[:, 0]}
+    assert vals == lits - {0x8b0c176c3b43d207}
+    assert sum(vals) % (1 << 64) == 0x8b0c176c3b43d207 and (cnt == 1).all()
+
+
+@pytest.mark.parametrize("name", ["DSK_perBank1", "DSK_perBank2"])
+def test_dsk_perbank_literals(name):
+    d = UNIT[name]
+    for c in d["checks"]:
+        album = BankAlbum([BankStrings(s) for s in d["banks"]])
+        props = {"-kmer-size": c["k"], "-abundance-min": str(c["min"]), "-abundance-max": c["max"], "-solidity-kind": c["kind"]}
+        sc = SortingCountAlgorithm(album, props).execute()
+        assert len(sc.getSolidCounts()[1]) == c["nb_solid"], c
+
+
+def test_unhandled_kmer_size():
+    with pytest.raises(RuntimeError, match="unhandled kmer size 64"):
+        SortingCountAlgorithm(BankStrings("ACGT" * 40), {"-kmer-size": 64}).execute()
+
+
+def test_empty_and_short_inputs():
+    for data in (b"", b">only header\n", b">a\nACGT\n", b"no header at all\n"):
+        sc = SortingCountAlgorithm(BankBytes(data), {"-kmer-size": 31, "-abundance-min": "1"}).execute()
+        assert sc.getInfo()["kmers_nb_valid"] == 0 and len(sc.getSolidCounts()[1]) == 0
+        assert sc.getHistogram()[0].sum() == 0
+
+
+def test_format_error_is_reported():
+    from dsk_b200 import DskGpuError
+    with pytest.raises(DskGpuError) as e:
+        SortingCountAlgorithm(BankBytes(b">a\nACGTACGTACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"),
+                              {"-kmer-size": 11}).execute()
+    assert e.value.code == -4
+
+
+def compare_with_oracle(data_banks, k, engine=None, **kw):
+    ref = oracle.count_files(data_banks, k, abundance_min=kw.get("abundance_min", 2), histo2d=kw.get("histo2d", False),
+                             kind=kw.get("kind", "sum"))
+    props = {"-kmer-size": k, "-abundance-min": str(kw.get("abundance_min", 2)), "-histo2D": int(kw.get("histo2d", False)),
+             "-solidity-kind": kw.get("kind", "sum")}
+    bank = BankAlbum([BankBytes(d) for d in data_banks]) if len(data_banks) > 1 else BankBytes(data_banks[0])
+    sc = SortingCountAlgorithm(bank, props, **(engine or {})).execute()
+    keys, cnt = sc.getSolidCounts()
+    lo, hi, rc = ref.solid_kmers()
+    assert sc.getInfo()["kmers_nb_valid"] == ref.kmers_nb_valid
+    assert sc.getInfo()["kmers_nb_distinct"] == ref.nb_distinct
+    assert len(cnt) == len(rc)
+    assert (keys[:, 0] == lo).all() and (cnt.astype(np.int64) == rc).all()
+    if keys.shape[1] == 2:
+        assert (keys[:, 1] == hi).all()
+    h1, h2 = sc.getHistogram()
+    assert (h1 == ref.hist).all()
+    if kw.get("histo2d"):
+        assert (h2 == ref.hist2d).all()
+    return sc
+
+
+@pytest.mark.parametrize("k", [31, 63, 21, 47])
+def test_synthetic_vs_oracle(k):
+    buf, n, _ = reads_fasta(G=300_000, coverage=40, L=150, err=0.01, seed=100 + k)
+    compare_with_oracle([buf[:n].tobytes()], k)
+
+
+@pytest.mark.parametrize("mode", ["auto", "sort", "hash"])
+def test_synthetic_medium_modes(mode):
+    buf, n, _ = reads_fasta(G=1_000_000, coverage=30, L=150, err=0.01, seed=5)
+    sc = compare_with_oracle([buf[:n].tobytes()], 31, engine=dict(count_mode=mode, hash_log2_slots=18))
+    assert sc.getInfo()["engine"]["nb_partitions"] > 4
+
+
+def test_histo2d_assembly_vs_reads():
+    g = genome_codes(200_000, seed=9)
+    asm = assembly_fasta(g)
+    buf, n, _ = reads_fasta(coverage=20, L=150, err=0.01, seed=9, genome=g)
+    compare_with_oracle([asm, buf[:n].tobytes()], 31, histo2d=True)
+    compare_with_oracle([asm, buf[:n].tobytes()], 63, histo2d=True, engine=dict(count_mode="sort"))
+
+
+def test_push_reads_equals_push_bytes():
+    buf, n, _ = reads_fasta(G=50_000, coverage=10, L=100, err=0.02, seed=3)
+    data = buf[:n].tobytes()
+    seqs = [ln for ln in data.split(b"\n") if ln and not ln.startswith(b">")]
+    a = SortingCountAlgorithm(BankBytes(data), {"-kmer-size": 27}).execute()
+    b = SortingCountAlgorithm(BankStrings(seqs), {"-kmer-size": 27}).execute()
+    assert (a.getSolidCounts()[0] == b.getSolidCounts()[0]).all() and (a.getSolidCounts()[1] == b.getSolidCounts()[1]).all()
+
+
+def test_device_resident_input_and_reset():
+    import torch
+    buf, n, _ = reads_fasta(G=200_000, coverage=30, L=150, err=0.01, seed=11)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], 31, abundance_min=2)
+    d = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    with GpuCounter(kmer_size=31, abundance_min=2, stream=torch.cuda.current_stream().cuda_stream) as eng:
+        for _ in range(3):                                   # reset() must give identical results every step
+            eng.reset()
+            eng.push_device_bytes(d.data_ptr(), n)
+            eng.finish()
+            keys, cnt = eng.solid()
+            lo, hi, rc = ref.solid_kmers()
+            assert (keys[:, 0] == lo).all() and (cnt == rc.astype(np.uint32)).all()
+            assert (eng.histogram()[0] == ref.hist).all()
+        # unaligned device pointer
+        eng.reset()
+        d2 = torch.empty(n + 7, dtype=torch.uint8, device="cuda")
+        d2[3:3 + n] = d
+        eng.push_device_bytes(d2.data_ptr() + 3, n)
+        eng.finish()
+        assert (eng.solid()[1] == rc.astype(np.uint32)).all()
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_full_size_properties(k):
+    """BASELINE.json configs[1]: 5 Mbp genome, 100x, 150 bp, 1 % error -- size-independent invariants."""
+    buf, n, nreads = reads_fasta(G=5_000_000, coverage=100, L=150, err=0.01, seed=42)
+    with GpuCounter(kmer_size=k, abundance_min=2) as eng:
+        eng.push_bytes(buf[:n])
+        eng.finish()
+        st = eng.stats()
+        keys, cnt = eng.solid()
+        h1, _ = eng.histogram()
+    assert st["kmers_nb_valid"] == nreads * (150 - k + 1)               # no N in this set
+    assert st["nb_sequences"] == nreads and st["nb_nucleotides"] == nreads * 150
+    assert int((h1 * np.arange(10001, dtype=np.uint64)).sum()) == st["kmers_nb_valid"]   # checksum of counts (no count >= 10000 here)
+    assert int(h1.sum()) == st["kmers_nb_distinct"]
+    assert int(h1[2:].sum()) == st["kmers_nb_solid"] == len(cnt)
+    assert int(cnt.astype(np.uint64).sum()) == st["kmers_nb_valid"] - int(h1[1])
+    hc = np.bincount(np.minimum(cnt, 10000), minlength=10001).astype(np.uint64)
+    assert (hc[2:10000] == h1[2:10000]).all()
+    if keys.shape[1] == 1:
+        assert (keys[1:, 0] > keys[:-1, 0]).all()
+    else:
+        assert ((keys[1:, 1] > keys[:-1, 1]) | ((keys[1:, 1] == keys[:-1, 1]) & (keys[1:, 0] > keys[:-1, 0]))).all()
+    if k == 31:   # SURVEY.md 6.2 [measured with the reference]: 103 530 226 distinct / 12 960 855 solid for seed 42 -- different generator, same shape
+        assert 0.9e8 < st["kmers_nb_distinct"] < 1.2e8
