@@ -131,38 +131,81 @@ __device__ __forceinline__ u32 table_slot(u64* keys, u32 smask, const Kmer<2>& k
 }
 
 // ---- K4+K7: expand records and count into the table ------------------------------------------------------------
-// one thread per super-k-mer record; rolling forward / reverse-complement k-mers (K/Model.hpp:877-884)
+// Flat k-mer parallelism: a warp stages 32 records in shared memory, builds the (record, offset) owner map of
+// their k-mers, then every lane extracts ONE k-mer per iteration straight from the packed bases (no rolling,
+// no divergence on the super-k-mer length).  Canonical form via bit-reversal (K/Model.hpp:294, :877-884).
+template <int KW> struct InsCfg { static constexpr int MAXNK = 32 * 2 * KW - 8; };   // k-mers per record upper bound
+
+template <int KW>
+__device__ __forceinline__ Kmer<KW> rec_kmer_at(const u64* r, int j, int k)
+{
+    // k-mer starting at base j of the record
+    if constexpr (KW == 1) {
+        const int q = j >> 5, o = j & 31;                      // j >= 32 only happens for very small k
+        u64 a = r[q], b = q ? 0 : r[1];
+        u64 v = o ? ((a << (2 * o)) | (b >> (64 - 2 * o))) : a;
+        Kmer<1> x; x.w[0] = v >> (64 - 2 * k); return x;
+    } else {
+        const int q = j >> 5, o = j & 31;
+        u64 a = r[q], b = (q + 1 < 4) ? r[q + 1] : 0, c = (q + 2 < 4) ? r[q + 2] : 0;
+        u64 sh[2];
+        sh[0] = o ? ((a << (2 * o)) | (b >> (64 - 2 * o))) : a;
+        sh[1] = o ? ((b << (2 * o)) | (c >> (64 - 2 * o))) : b;
+        return rec_first_kmer2(sh, k);
+    }
+}
+
 template <int KW>
 __global__ void __launch_bounds__(256) k_hash_insert(const u64* __restrict__ recs, u64 rec_begin, u64 rec_end, int k,
                                                      u64* keys, u32* counts, u32 smask, int nbanks, Counters* ctr)
 {
     constexpr int RW = 2 * KW;
-    for (u64 i = rec_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < rec_end; i += (u64)gridDim.x * blockDim.x) {
-        u64 r[RW];
-        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
-        if constexpr (RW == 2) { ulonglong2 v = __ldg(src + i); r[0] = v.x; r[1] = v.y; }
-        else { ulonglong2 v = __ldg(src + 2 * i), u = __ldg(src + 2 * i + 1); r[0] = v.x; r[1] = v.y; r[2] = u.x; r[3] = u.y; }
-        const int nk = (int)((r[RW - 1] >> 8) & 0xFFu);
-        const int bank = (nbanks > 1) ? (int)(r[RW - 1] & 0xFFu) : 0;
-        Kmer<KW> f, rc;
-        if constexpr (KW == 1) f = rec_first_kmer1(r, k); else f = rec_first_kmer2(r, k);
-        rc = kmer_revcomp(f, k);
-        for (int j = 0; j < nk; j++) {
-            if (j) kmer_roll(f, rc, rec_base<RW>(r, k - 1 + j), k);
-            Kmer<KW> c = kmer_canonical(f, rc);
+    constexpr int MAXNK = InsCfg<KW>::MAXNK;
+    __shared__ __align__(16) u64 s_rec[8][32 * RW];
+    __shared__ u8 s_owner[8][32 * MAXNK];
+    __shared__ u16 s_off[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 nwarps = (u64)gridDim.x * 8, gwarp = (u64)blockIdx.x * 8 + warp;
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
+    for (u64 base = rec_begin + gwarp * 32; base < rec_end; base += nwarps * 32) {
+        const u64 i = base + lane;
+        u32 nk = 0;
+        if (i < rec_end) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(&s_rec[warp][lane * RW]);
+            if constexpr (RW == 2) { ulonglong2 v = __ldg(src + i); dst[0] = v; nk = (u32)(v.y >> 8) & 0xFFu; }
+            else { ulonglong2 v = __ldg(src + 2 * i), u = __ldg(src + 2 * i + 1); dst[0] = v; dst[1] = u; nk = (u32)(u.y >> 8) & 0xFFu; }
+        }
+        u32 inc = nk;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+        const u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const u32 off = inc - nk;
+        s_off[warp][lane] = (u16)off;
+        for (u32 j = 0; j < nk; j++) s_owner[warp][off + j] = (u8)lane;
+        __syncwarp();
+        for (u32 t = lane; t < total; t += 32) {
+            const u32 r = s_owner[warp][t];
+            const int j = (int)(t - s_off[warp][r]);
+            const u64* rw = &s_rec[warp][r * RW];
+            Kmer<KW> f = rec_kmer_at<KW>(rw, j, k);
+            Kmer<KW> c = kmer_canonical(f, kmer_revcomp(f, k));
+            const int bank = (nbanks > 1) ? (int)(rw[RW - 1] & 0xFFu) : 0;
             u32 slot = table_slot(keys, smask, c);
-            if (slot == 0xFFFFFFFFu) { atomicExch(&ctr->hash_overflow, 1u); return; }
+            if (slot == 0xFFFFFFFFu) { atomicExch(&ctr->hash_overflow, 1u); break; }
             atomicAdd(&counts[(u64)slot * nbanks + bank], 1u);
         }
+        __syncwarp();
     }
 }
 
 // ---- K6 (hash flavour): sweep the table, run the processor chain, reset the slots ---------------------------------
+// each thread owns SV consecutive slots per iteration (32 bytes of keys = one sector)
 template <int KW>
 __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 nslots, SolidityParams sp, int discard,
                                                    u64* out_keys, u32* out_vals, u64 out_cap,
                                                    unsigned long long* g_hist, unsigned long long* g_hist2d, Counters* ctr)
 {
+    constexpr int SV = (KW == 1) ? 4 : 2;
     __shared__ u32 s_hist[HIST_SMEM_BINS];
     __shared__ u32 s_distinct;
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) s_hist[i] = 0;
@@ -170,22 +213,33 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
     __syncthreads();
     const u64 EMPTY = ~0ULL;
     u32 ndist = 0;
-    const u32 nloop = (nslots + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
+    const u32 ngroups = nslots / SV;                               // nslots is a power of two >= 1024
+    const u32 nthreads = blockDim.x * gridDim.x;
+    const u32 nloop = (ngroups + nthreads - 1) / nthreads;
+    ulonglong2* k2 = reinterpret_cast<ulonglong2*>(keys);
     for (u32 it = 0; it < nloop; it++) {
-        u32 slot = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-        bool occ = false; Kmer<KW> key; u32 cv[MAXB];
-        if (slot < nslots) {
-            if constexpr (KW == 1) { key.w[0] = keys[slot]; occ = key.w[0] != EMPTY; }
-            else { ulonglong2 v = reinterpret_cast<ulonglong2*>(keys)[slot]; key.w[0] = v.x; key.w[1] = v.y; occ = !(v.x == EMPTY && v.y == EMPTY); }
+        const u32 g = it * nthreads + blockIdx.x * blockDim.x + threadIdx.x;
+        ulonglong2 v[2];
+        const bool in = g < ngroups;
+        v[0] = in ? k2[2 * (u64)g] : make_ulonglong2(EMPTY, EMPTY);
+        v[1] = in ? k2[2 * (u64)g + 1] : make_ulonglong2(EMPTY, EMPTY);
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < SV; q++) {
+            Kmer<KW> key; bool occ;
+            if constexpr (KW == 1) { key.w[0] = (q & 1) ? v[q >> 1].y : v[q >> 1].x; occ = key.w[0] != EMPTY; }
+            else { key.w[0] = v[q].x; key.w[1] = v[q].y; occ = !(v[q].x == EMPTY && v[q].y == EMPTY); }
+            bool solid = false; int32_t sum = 0;
+            if (occ) {
+                const u64 slot = (u64)g * SV + q;
+                u32 cv[MAXB];
+                for (int b = 0; b < sp.nbanks; b++) { cv[b] = counts[slot * sp.nbanks + b]; counts[slot * sp.nbanks + b] = 0; }
+                any = true;
+                if (!discard) { ndist++; solid = process_counts(cv, sp, s_hist, g_hist, g_hist2d, &sum); }
+            }
+            emit_solid<KW>(solid, key, sum, out_keys, out_vals, out_cap, ctr);
         }
-        bool solid = false; int32_t sum = 0;
-        if (occ) {
-            for (int b = 0; b < sp.nbanks; b++) { cv[b] = counts[(u64)slot * sp.nbanks + b]; counts[(u64)slot * sp.nbanks + b] = 0; }
-            if constexpr (KW == 1) keys[slot] = EMPTY;
-            else reinterpret_cast<ulonglong2*>(keys)[slot] = make_ulonglong2(EMPTY, EMPTY);
-            if (!discard) { ndist++; solid = process_counts(cv, sp, s_hist, g_hist, g_hist2d, &sum); }
-        }
-        emit_solid<KW>(solid, key, sum, out_keys, out_vals, out_cap, ctr);
+        if (any) { k2[2 * (u64)g] = make_ulonglong2(EMPTY, EMPTY); k2[2 * (u64)g + 1] = make_ulonglong2(EMPTY, EMPTY); }
     }
     ndist = __reduce_add_sync(0xFFFFFFFFu, ndist);
     if ((threadIdx.x & 31) == 0 && ndist) atomicAdd(&s_distinct, ndist);

@@ -526,7 +526,7 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
         if ((rc = ensure(ctx, ctx->svals[i], out_cap * 4))) return rc;
     }
     const int mode = ctx->cfg.count_mode;
-    const int log2s = ctx->cfg.hash_log2_slots > 0 ? ctx->cfg.hash_log2_slots : 22;
+    const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 22;
     u64 nslots = (u64)1 << log2s;
     const double load_max = 0.6;
     const u64 sort_cap = (u64)1 << 28;                             // keys per sort-path group
@@ -631,7 +631,7 @@ static int finish_impl(dskgpu_ctx* ctx)
     ctx->st.kmers_nb_valid = nkm; ctx->st.nb_superkmers = nrec; ctx->st.superkmer_bytes = nrec * (u64)ctx->RW * 8;
 
     // ---- partition plan: P partitions of ~ (table capacity / 4) k-mers each --------------------------------
-    const int log2s = ctx->cfg.hash_log2_slots > 0 ? ctx->cfg.hash_log2_slots : 22;
+    const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 22;
     const u64 target = std::max<u64>(((u64)1 << log2s) * 6 / 10 / 4, 4096);
     u32 P = ctx->cfg.nb_partitions > 0 ? (u32)ctx->cfg.nb_partitions : (u32)std::min<u64>(4096, (nkm + target - 1) / target);
     if (P < 1) P = 1;
@@ -770,36 +770,77 @@ int dskgpu_xchg_scatter(dskgpu_ctx* ctx) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exc
 // ---------------------------------------------------------------------------------------------------------------
 // host self checks (same functions the kernels run; no GPU needed)
 // ---------------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+template <int FMT>
+static int64_t selftest_scan_fmt(const u8* raw, u64 lo, u64 hi, uint8_t* out, size_t out_cap)
+{
+    // replays the device algorithm chunk by chunk (masks -> table -> emission masks) and cross-checks every
+    // chunk against the byte-wise reference state machine scan_step(); tables are also composed per tile.
+    int state = (FMT == FMT_FASTA) ? ST_HDR : 0;          // true state (mask path)
+    int state_ref = state;                                  // byte-wise path
+    size_t w = 0; u32 err = 0; int err_ref = 0;
+    const u64 c0 = lo / SCAN_BPT, c1 = (hi + SCAN_BPT - 1) / SCAN_BPT;
+    Tab tile_tab = tab_identity(); int tile_state0 = state; u32 tile_cnt = 0; u64 in_tile = 0;
+    for (u64 ci = c0; ci < c1; ci++) {
+        const u64 a = ci * SCAN_BPT;
+        u32 words[8] = {0, 0, 0, 0, 0, 0, 0, 0}, active = 0;
+        for (int i = 0; i < SCAN_BPT; i++) { u64 x = a + i; bool in = x >= lo && x < hi; u32 c = in ? raw[x] : 0u; words[i >> 2] |= c << (8 * (i & 3)); active |= (in ? 1u : 0u) << i; }
+        const int prev = (a > lo && a <= hi) ? raw[a - 1] : '\n';
+        const u64 last_end = (a + SCAN_BPT < hi) ? a + SCAN_BPT : hi;
+        const int next = (last_end < hi) ? (int)raw[last_end] : -1;
+        const bool prev_nl = prev == '\n', next_flag = (next == '\n') || next < 0;
+        CMasks m; chunk_masks(words, active, m);
+        const Tab t = chunk_table<FMT>(m, prev_nl, next_flag);
+        u32 em, sep, e2;
+        chunk_emit_masks<FMT>(m, prev_nl, next_flag, state, em, sep, e2);
+        err |= e2;
+        // byte-wise reference
+        u8 ref[SCAN_BPT]; int nref = 0; int pv = prev;
+        for (int i = 0; i < SCAN_BPT; i++) {
+            if (!((active >> i) & 1)) continue;
+            const int ch = (words[i >> 2] >> (8 * (i & 3))) & 0xFF;
+            const int nx = (i + 1 < SCAN_BPT && ((active >> (i + 1)) & 1)) ? (int)((words[(i + 1) >> 2] >> (8 * ((i + 1) & 3))) & 0xFF) : next;
+            const int e = scan_step(FMT, state_ref, pv, ch, nx, err_ref);
+            if (e >= 0) ref[nref++] = (u8)e;
+            pv = ch;
+        }
+        // mask path emission
+        int n = 0;
+        for (int i = 0; i < SCAN_BPT; i++) if ((em >> i) & 1u) {
+            const u32 c = (words[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            const u8 code = (u8)(((sep >> i) & 1u) ? (u32)CODE_SEP : encode_fast(c));
+            if (n >= nref || ref[n] != code) return -1000000 - (int64_t)ci;       // emission differs from scan_step
+            if (w < out_cap) out[w] = code;
+            w++; n++;
+        }
+        if (n != nref) return -2000000 - (int64_t)ci;
+        if ((u32)n != tab_count(t, state)) return -3000000 - (int64_t)ci;          // table count differs
+        state = tab_state(t, state);
+        if (state != state_ref) return -4000000 - (int64_t)ci;                      // table state differs
+        // tile-level composition, as the block scan does
+        tile_tab = tab_compose<FMT>(tile_tab, t); tile_cnt += (u32)n; in_tile++;
+        if (in_tile == SCAN_THREADS || ci + 1 == c1) {
+            if (tab_count(tile_tab, tile_state0) != tile_cnt || tab_state(tile_tab, tile_state0) != state) return -5000000 - (int64_t)ci;
+            tile_tab = tab_identity(); tile_state0 = state; tile_cnt = 0; in_tile = 0;
+        }
+    }
+    if (err || err_ref) return ((err != 0) == (err_ref != 0)) ? -(int64_t)(err | (u32)err_ref) : -6000000;
+    return (int64_t)w;
+}
+
+extern "C" {
+
 int64_t dskgpu_selftest_scan(const char* bytes, size_t n, int format, uint8_t* out, size_t out_cap)
 {
-    // emulates the three device passes chunk by chunk: tables -> composition -> emission
     size_t skip = 0; int fmt = format;
     if (fmt != DSKGPU_FMT_LINES) { int det = detect_format(bytes, n, &skip); if (!det) return 0; if (fmt == DSKGPU_FMT_AUTO) fmt = det; }
     const u8* raw = (const u8*)bytes;
-    const u64 lo = skip, hi = n;
-    int state = (fmt == FMT_FASTA) ? ST_HDR : 0;
-    size_t w = 0; int err = 0;
-    const u64 c0 = lo / SCAN_BPT, c1 = (hi + SCAN_BPT - 1) / SCAN_BPT;
-    for (u64 ci = c0; ci < c1; ci++) {
-        Chunk c; c.active = 0; u64 a = ci * SCAN_BPT;
-        for (int i = 0; i < SCAN_BPT; i++) { u64 x = a + i; bool in = x >= lo && x < hi; c.b[i] = in ? raw[x] : 0; c.active |= (in ? 1u : 0u) << i; }
-        c.prev = (a > lo && a <= hi) ? raw[a - 1] : '\n';
-        u64 last_end = (a + SCAN_BPT < hi) ? a + SCAN_BPT : hi;
-        c.next = (last_end < hi) ? (int)raw[last_end] : -1;
-        Tab t = chunk_table(fmt, c);
-        u8 tmp[SCAN_BPT]; u32 ns = 0, nb = 0;
-        int cnt = chunk_emit(fmt, c, state, tmp, err, ns, nb);
-        if ((u32)cnt != tab_count(t, state)) return -1000 - (int64_t)ci;          // table / emission disagreement
-        int st_chk = state;                                                        // state after emission
-        { int s2 = state, e2 = 0, prev = c.prev; for (int i = 0; i < SCAN_BPT; i++) { if (!((c.active >> i) & 1)) continue;
-              int nx = (i + 1 < SCAN_BPT && ((c.active >> (i + 1)) & 1)) ? c.b[i + 1] : c.next; scan_step(fmt, s2, prev, c.b[i], nx, e2); prev = c.b[i]; } st_chk = s2; }
-        // FASTA states are only meaningful modulo "the next byte is a line start"; compare through one more step
-        if (fmt != FMT_FASTA && tab_state(t, state) != st_chk) return -2000 - (int64_t)ci;
-        for (int i = 0; i < cnt; i++) { if (w < out_cap) out[w] = tmp[i]; w++; }
-        state = tab_state(t, state);
+    switch (fmt) {
+    case FMT_FASTA: return selftest_scan_fmt<FMT_FASTA>(raw, skip, n, out, out_cap);
+    case FMT_FASTQ: return selftest_scan_fmt<FMT_FASTQ>(raw, skip, n, out, out_cap);
+    default:        return selftest_scan_fmt<FMT_LINES>(raw, skip, n, out, out_cap);
     }
-    if (err) return -(int64_t)err;
-    return (int64_t)w;
 }
 
 int dskgpu_selftest_minimizers(const uint8_t* codes, size_t n, int k, int m, uint32_t* out_min, uint8_t* out_valid)

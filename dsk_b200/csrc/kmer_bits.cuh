@@ -80,11 +80,28 @@ DSK_HD int scan_step(int fmt, int& state, int prev, int c, int next, int& err)
 // reverse the 32 2-bit groups of a 64-bit word
 DSK_HD u64 rev2_64(u64 x)
 {
+#ifdef __CUDA_ARCH__
+    u64 y = __brevll(x);                                    // bit reversal, then swap the two bits of every pair back
+    return ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);
+#else
     x = ((x >> 2)  & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
     x = ((x >> 4)  & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
     x = ((x >> 8)  & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
     x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
     return (x >> 32) | (x << 32);
+#endif
+}
+DSK_HD u32 rev2_32(u32 x)
+{
+#ifdef __CUDA_ARCH__
+    u32 y = __brev(x);
+    return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+#else
+    x = ((x >> 2)  & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4)  & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8)  & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
 }
 // reverse complement of a k-mer (k <= 32) held in the low 2k bits, first base most significant
 DSK_HD u64 revcomp64(u64 x, int k)
@@ -104,16 +121,15 @@ DSK_HD void revcomp128(u64 lo, u64 hi, int k, u64& rlo, u64& rhi)
     else               { rlo = a >> (sh - 64); rhi = 0; }
 }
 
-// m-mer value used for minimizer selection (the reference's _mmer_lut entry), m <= 16
+// m-mer value used for minimizer selection (the reference's _mmer_lut entry), 2 <= m <= 15, 32-bit arithmetic
 DSK_HD u32 mmer_value(u32 x, int m)
 {
-    const u32 mmask = (m >= 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
-    u32 rc = (u32)(revcomp64((u64)x, m));
+    const u32 mmask = (1u << (2 * m)) - 1u;
+    u32 rc = rev2_32(x ^ 0xAAAAAAAAu) >> (32 - 2 * m);      // complement every base, reverse, drop the padding pairs
     u32 v = rc < x ? rc : x;
     // K/Model.hpp:1220-1251 is_allowed: ban "AA" anywhere except as the first two letters
-    u64 mask_ma1 = 0x5555555555555555ULL & ((1ULL << ((m - 2) * 2)) - 1ULL);
-    u64 a1 = v;
-    a1 = ~(a1 | (a1 >> 2));
+    const u32 mask_ma1 = 0x55555555u & ((1u << ((m - 2) * 2)) - 1u);
+    u32 a1 = ~(v | (v >> 2));
     a1 = ((a1 >> 1) & a1) & mask_ma1;
     return a1 ? mmask : v;
 }

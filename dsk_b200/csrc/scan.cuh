@@ -5,11 +5,12 @@
 // (G/src/gatb/bank/impl/BankFasta.cpp:485-572, G/src/gatb/tools/misc/api/Data.hpp:185), which the reference
 // runs single-threaded under the iterate lock (ICommand.hpp:304-331).
 //
-// Parallelisation: the scanner is a tiny state machine (line type for FASTA, line index mod 4 for FASTQ).
-// Every 32-byte thread chunk is summarised as a transition table  state_in -> (state_out, #codes emitted);
-// tables compose associatively, so a block scan (k_scan_tables), a scan over tiles (k_scan_tiles) and a
-// second block scan (k_scan_emit) give every thread its true input state and output offset.  The same
-// table builder / composer runs on the host in dskgpu_selftest_scan (tests pin it against the oracle).
+// The scanner is a tiny state machine (scan_step in kmer_bits.cuh: line type for FASTA, line index mod 4 for
+// FASTQ).  Every 32-byte thread chunk is turned into bit masks (newline, header start, ...) held in registers;
+// from the masks a transition table  state_in -> (state_out, #codes emitted)  follows in a few bit operations.
+// Tables compose associatively, so a block scan (k_scan_tables), a scan over tiles (k_scan_tiles) and a second
+// block scan (k_scan_emit) give every thread its true input state and output offset.  The mask evaluators are
+// host+device functions; dskgpu_selftest_scan replays them on the host against the byte-wise scan_step.
 #pragma once
 #include "kmer_bits.cuh"
 
@@ -19,88 +20,180 @@ constexpr int SCAN_BPT = 32;                 // bytes per thread
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE = SCAN_BPT * SCAN_THREADS;   // 8192 bytes per tile
 
-// transition table over <=4 states: st = 4 x 2 bits (state_out per state_in), cnt = 4 x u16
+DSK_HD int popc32(u32 x)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+DSK_HD int ctz32(u32 x)      // x != 0
+{
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+DSK_HD int msb32(u32 x)      // x != 0
+{
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+
+// ---- per-chunk bit masks (bit i <-> byte i of the chunk) ---------------------------------------------------
+struct CMasks { u32 nl, gt, plus, at, cr, active; };
+
+DSK_HD u32 bits_below(int b) { return b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u); }     // bits [0, b)
+
+DSK_HD void chunk_masks(const u32* w /*[8]*/, u32 active, CMasks& m)
+{
+    u32 nl = 0, gt = 0, plus = 0, at = 0, cr = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_BPT; i++) {
+        const u32 c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+        nl   |= (c == '\n' ? 1u : 0u) << i;
+        gt   |= (((c == '>') | (c == '@')) ? 1u : 0u) << i;
+        at   |= (c == '@' ? 1u : 0u) << i;
+        plus |= (c == '+' ? 1u : 0u) << i;
+        cr   |= (c == '\r' ? 1u : 0u) << i;
+    }
+    m.nl = nl & active; m.gt = gt & active; m.plus = plus & active; m.at = at & active; m.cr = cr & active; m.active = active;
+}
+
+// CR bytes that are dropped: followed by '\n' or by the end of the stream (BankFasta.cpp:471)
+DSK_HD u32 cr_dropped(const CMasks& m, bool next_is_nl_or_eof)
+{
+    if (m.cr == 0) return 0;
+    u32 follow = (m.nl >> 1);
+    if (m.active && next_is_nl_or_eof) follow |= 1u << msb32(m.active);
+    return m.cr & follow;
+}
+
+// FASTA evaluation for input state `st_in` (ST_SEQ / ST_HDR): emitted-byte mask, separator mask, output state.
+// Line starts: byte after '\n' (prev_nl tells it for byte 0).  A line starting with '>' or '@' is a header
+// (BankFasta.cpp:528); one starting with '+' would switch the reference to FASTQ parsing -> flagged.
+DSK_HD void fasta_eval(const CMasks& m, bool prev_nl, bool next_flag, int st_in, u32& em, u32& sep, int& st_out, u32& err_ls)
+{
+    const u32 ls = ((m.nl << 1) | ((prev_nl && m.active) ? (1u << ctz32(m.active)) : 0u)) & m.active;   // prev_nl applies to the first active byte
+    const u32 hdr_like = ls & (m.gt | m.plus);
+    u32 hm = 0; int cur = st_in; int start = 0; u32 it = ls;
+    while (it) {
+        const int p = ctz32(it);
+        if (cur == ST_HDR) hm |= bits_below(p) & ~bits_below(start);
+        cur = ((hdr_like >> p) & 1) ? ST_HDR : ST_SEQ;
+        start = p; it &= it - 1;
+    }
+    if (cur == ST_HDR) hm |= ~bits_below(start);
+    sep = ls & m.gt;
+    em = (m.active & ~hm & ~m.nl & ~cr_dropped(m, next_flag)) | sep;
+    st_out = cur;
+    err_ls = ls & m.plus;
+}
+
+// FASTQ evaluation for input phase `ph_in` (line index mod 4): sequence lines are the segments of phase 1;
+// their '\n' becomes the record separator.
+DSK_HD void fastq_eval(const CMasks& m, bool prev_nl, bool next_flag, int ph_in, u32& em, u32& sep, int& ph_out, u32& err)
+{
+    const u32 ls = ((m.nl << 1) | ((prev_nl && m.active) ? (1u << ctz32(m.active)) : 0u)) & m.active;   // prev_nl applies to the first active byte
+    u32 seqm = 0; int ph = ph_in; int start = 0; u32 it = m.nl; err = 0;
+    for (;;) {
+        const int p = it ? ctz32(it) : 32;                              // next newline (inclusive end of the segment)
+        const u32 seg = (p >= 31 ? 0xFFFFFFFFu : bits_below(p + 1)) & ~bits_below(start);
+        if (ph == 1) seqm |= seg;
+        const u32 seg_ls = seg & ls;                                    // the segment's first byte if it starts a line
+        if (seg_ls) {
+            if (ph == 0 && !(seg_ls & (m.at | m.nl))) err |= SCAN_ERR_FASTQ_AT;
+            if (ph == 2 && !(seg_ls & m.plus)) err |= SCAN_ERR_FASTQ_PLUS;
+        }
+        if (p >= 32) break;
+        ph = (ph + 1) & 3; start = p + 1; it &= it - 1;
+        if (start >= 32) break;
+    }
+    seqm &= m.active;
+    em = seqm & ~cr_dropped(m, next_flag);
+    sep = em & m.nl;
+    ph_out = ph;
+}
+
+// ---- transition tables ------------------------------------------------------------------------------------------
+// generic form over <= 4 states: st = 4 x 2 bits (state_out per state_in), cnt = 4 x u16 (codes emitted)
 struct Tab { u32 st; u64 cnt; };
 DSK_HD Tab tab_identity() { Tab t; t.st = 0xE4u; t.cnt = 0; return t; }
 DSK_HD int tab_state(const Tab& t, int s) { return (t.st >> (2 * s)) & 3; }
 DSK_HD u32 tab_count(const Tab& t, int s) { return (u32)((t.cnt >> (16 * s)) & 0xFFFFu); }
-// apply f first, then g
+// apply f first, then g.  FASTQ tables are rotations (state_out = state_in + q), FASTA tables have 2 states.
+template <int FMT>
 DSK_HD Tab tab_compose(const Tab& f, const Tab& g)
 {
-    Tab r; r.st = 0; r.cnt = 0;
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-        int fs = tab_state(f, s);
-        r.st |= (u32)tab_state(g, fs) << (2 * s);
-        r.cnt |= (u64)((tab_count(f, s) + tab_count(g, fs)) & 0xFFFFu) << (16 * s);
+    Tab r;
+    if (FMT == FMT_LINES) { r.st = 0xE4u; r.cnt = f.cnt + g.cnt; return r; }
+    if (FMT == FMT_FASTQ) {
+        const u32 qf = f.st & 3u, qg = g.st & 3u, q = (qf + qg) & 3u;       // st of state 0 is the rotation
+        const u64 gc = qf ? ((g.cnt >> (16 * qf)) | (g.cnt << (64 - 16 * qf))) : g.cnt;
+        r.cnt = f.cnt + gc;                                                   // 4 x u16 lanes, no lane overflows (<= 8192)
+        r.st = q | (((q + 1) & 3u) << 2) | (((q + 2) & 3u) << 4) | (((q + 3) & 3u) << 6);
+        return r;
     }
+    // FASTA: states 0 (SEQ) and 1 (HDR)
+    const u32 f0 = f.st & 1u, f1 = (f.st >> 2) & 1u;
+    const u32 g0 = g.st & 1u, g1 = (g.st >> 2) & 1u;
+    const u32 gc0 = (u32)(g.cnt & 0xFFFFu), gc1 = (u32)((g.cnt >> 16) & 0xFFFFu);
+    const u32 r0 = f0 ? g1 : g0, r1 = f1 ? g1 : g0;
+    const u32 c0 = (u32)(f.cnt & 0xFFFFu) + (f0 ? gc1 : gc0), c1 = (u32)((f.cnt >> 16) & 0xFFFFu) + (f1 ? gc1 : gc0);
+    r.st = r0 | (r1 << 2) | (2u << 4) | (3u << 6);
+    r.cnt = (u64)c0 | ((u64)c1 << 16);
     return r;
 }
 
-// bytes of one thread chunk plus its neighbours; inactive bytes (outside the stream window) are skipped
-struct Chunk {
-    u8 b[SCAN_BPT];
-    u32 active;          // bit i: byte i belongs to the stream window
-    int prev, next;      // byte before b[0] / after b[31] as seen by the scanner
-};
-
-// table of one chunk.  One pass, exploiting the structure of each format (see file header).
-DSK_HD Tab chunk_table(int fmt, const Chunk& c)
+template <int FMT>
+DSK_HD Tab chunk_table(const CMasks& m, bool prev_nl, bool next_flag)
 {
     Tab t;
-    if (fmt == FMT_FASTA) {
-        // run from ST_SEQ; both states converge at the first line start inside the chunk
-        int state = ST_SEQ, err = 0; u32 cnt = 0, cnt_prefix = 0; bool had_ls = false;
-        int prev = c.prev;
-        for (int i = 0; i < SCAN_BPT; i++) {
-            if (!((c.active >> i) & 1)) continue;
-            int ch = c.b[i];
-            int nx = (i + 1 < SCAN_BPT && ((c.active >> (i + 1)) & 1)) ? c.b[i + 1] : c.next;
-            if (prev == '\n' && !had_ls) { had_ls = true; cnt_prefix = cnt; }
-            if (scan_step(FMT_FASTA, state, prev, ch, nx, err) >= 0) cnt++;
-            prev = ch;
-        }
-        if (!had_ls) cnt_prefix = cnt;
-        u32 st_hdr = had_ls ? (u32)state : (u32)ST_HDR;
-        t.st = (u32)state | (st_hdr << 2) | (2u << 4) | (3u << 6);
-        t.cnt = (u64)cnt | ((u64)(cnt - cnt_prefix) << 16);
+    if (FMT == FMT_FASTA) {
+        u32 em0, em1, sep, e; int so0, so1;
+        fasta_eval(m, prev_nl, next_flag, ST_SEQ, em0, sep, so0, e);
+        fasta_eval(m, prev_nl, next_flag, ST_HDR, em1, sep, so1, e);
+        t.cnt = (u64)popc32(em0) | ((u64)popc32(em1) << 16);
+        t.st = (u32)so0 | ((u32)so1 << 2) | (2u << 4) | (3u << 6);
         return t;
     }
-    if (fmt == FMT_FASTQ) {
-        // segment q (after q newlines) is the sequence line for start phase s = (1-q)&3
-        u32 cn[4] = {0, 0, 0, 0}; int q = 0;
-        for (int i = 0; i < SCAN_BPT; i++) {
-            if (!((c.active >> i) & 1)) continue;
-            int ch = c.b[i];
-            int nx = (i + 1 < SCAN_BPT && ((c.active >> (i + 1)) & 1)) ? c.b[i + 1] : c.next;
-            int s = (1 - q) & 3;
-            if (ch == '\n') { cn[s]++; q = (q + 1) & 3; }
-            else if (!(ch == '\r' && (nx == '\n' || nx < 0))) cn[s]++;
-        }
+    if (FMT == FMT_FASTQ) {
         t.st = 0; t.cnt = 0;
-        for (int s = 0; s < 4; s++) { t.st |= (u32)((s + q) & 3) << (2 * s); t.cnt |= (u64)cn[s] << (16 * s); }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            u32 em, sep, e; int so;
+            fastq_eval(m, prev_nl, next_flag, s, em, sep, so, e);
+            t.cnt |= (u64)popc32(em) << (16 * s);
+            t.st |= (u32)so << (2 * s);
+        }
         return t;
     }
-    // FMT_LINES: every byte emits exactly one code, single state
-    u32 n = 0;
-    for (int i = 0; i < SCAN_BPT; i++) n += (c.active >> i) & 1;
-    t.st = 0xE4u; t.cnt = (u64)n * 0x0001000100010001ULL;
+    t.cnt = (u64)popc32(m.active);
+    t.st = 0xE4u;
     return t;
 }
 
-// emission of one chunk given its true input state; out[] receives the codes (<= 32). returns count.
-DSK_HD int chunk_emit(int fmt, const Chunk& c, int state, u8* out, int& err, u32& nsep, u32& nbase)
+// masks of the bytes to emit for the true input state
+template <int FMT>
+DSK_HD void chunk_emit_masks(const CMasks& m, bool prev_nl, bool next_flag, int state, u32& em, u32& sep, u32& err)
 {
-    int n = 0, prev = c.prev;
-    for (int i = 0; i < SCAN_BPT; i++) {
-        if (!((c.active >> i) & 1)) continue;
-        int ch = c.b[i];
-        int nx = (i + 1 < SCAN_BPT && ((c.active >> (i + 1)) & 1)) ? c.b[i + 1] : c.next;
-        int e = scan_step(fmt, state, prev, ch, nx, err);
-        if (e >= 0) { out[n++] = (u8)e; if (e == CODE_SEP) nsep++; else nbase++; }
-        prev = ch;
-    }
-    return n;
+    int so;
+    if (FMT == FMT_FASTA) { u32 e; fasta_eval(m, prev_nl, next_flag, state, em, sep, so, e); err = e ? (u32)SCAN_ERR_PLUS_IN_FASTA : 0u; }
+    else if (FMT == FMT_FASTQ) { fastq_eval(m, prev_nl, next_flag, state, em, sep, so, err); }
+    else { em = m.active; sep = m.nl; err = 0; }
+}
+
+// code of byte c (0..3 | 4 when not ACGTacgt)
+DSK_HD u32 encode_fast(u32 c)
+{
+    const u32 u = (c & 0xDFu) - 65u;                               // 'A' -> 0, 'C' -> 2, 'G' -> 6, 'T' -> 19
+    const bool ok = (u < 20u) && ((0x80045u >> u) & 1u);
+    return ((c >> 1) & 3u) | (ok ? 0u : (u32)CODE_INVALID);
 }
 
 // ---- device side ------------------------------------------------------------------------------------------
@@ -122,30 +215,36 @@ struct StreamState {
 struct TileTab { u32 st; u32 cnt[4]; };          // tile-level table (counts fit u32: <= 8192)
 struct TileIn  { u64 base; u32 state; u32 pad; };
 
+// loads the 32 bytes of a thread chunk (absolute byte index a of the 16-byte aligned buffer `raw`); bytes outside
+// the stream window [lo, hi) are inactive.  Also returns the neighbour information the scanner needs.
 __device__ __forceinline__ void load_chunk(const u8* __restrict__ raw, u64 a, u64 lo, u64 hi, const StreamState* ss,
-                                           int next_after, Chunk& c)
+                                           int next_after, u32* w, u32& active, bool& prev_nl, bool& next_flag)
 {
-    c.active = 0;
     if (a >= lo && a + SCAN_BPT <= hi) {
         const uint4* p = reinterpret_cast<const uint4*>(raw + a);
         uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
-        u32 w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-        for (int i = 0; i < SCAN_BPT; i++) c.b[i] = (u8)(w[i >> 2] >> (8 * (i & 3)));
-        c.active = 0xFFFFFFFFu;
+        w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+        active = 0xFFFFFFFFu;
     } else {
+        active = 0;
 #pragma unroll
-        for (int i = 0; i < SCAN_BPT; i++) {
-            u64 x = a + i; bool in = (x >= lo && x < hi);
-            c.b[i] = in ? raw[x] : 0;
-            c.active |= (in ? 1u : 0u) << i;
+        for (int i = 0; i < 8; i++) w[i] = 0;
+        if (a + SCAN_BPT > lo && a < hi) {
+#pragma unroll
+            for (int i = 0; i < SCAN_BPT; i++) {
+                u64 x = a + i; bool in = (x >= lo && x < hi);
+                u32 c = in ? raw[x] : 0u;
+                w[i >> 2] |= c << (8 * (i & 3));
+                active |= (in ? 1u : 0u) << i;
+            }
         }
     }
-    // neighbours
-    if (a > lo && a <= hi) c.prev = raw[a - 1]; else c.prev = ss->prev_byte;
-    // `next` is consulted after the last ACTIVE byte of the chunk
+    int prev = (a > lo && a <= hi) ? (int)raw[a - 1] : ss->prev_byte;
+    prev_nl = (prev == '\n');
+    // byte following the last active byte of this chunk
     u64 last_end = (a + SCAN_BPT < hi) ? a + SCAN_BPT : hi;
-    c.next = (last_end < hi) ? (int)raw[last_end] : (next_after == -2 ? (int)raw[hi] : next_after);   // -2: stream continues in place
+    int next = (last_end < hi) ? (int)raw[last_end] : (next_after == -2 ? (int)raw[hi] : next_after);   // -2: stream continues in place
+    next_flag = (next == '\n') || (next < 0);
 }
 
 __device__ __forceinline__ Tab tab_shfl_up(const Tab& t, int d)
@@ -155,6 +254,7 @@ __device__ __forceinline__ Tab tab_shfl_up(const Tab& t, int d)
 
 // block-wide exclusive scan of tables (compose order = thread order). Returns the exclusive prefix of this
 // thread; *block_total gets the composition of the whole block (valid in all threads).
+template <int FMT>
 __device__ __forceinline__ Tab block_scan_tabs(Tab mine, Tab* s_warp /*[8]*/, Tab* block_total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -162,18 +262,21 @@ __device__ __forceinline__ Tab block_scan_tabs(Tab mine, Tab* s_warp /*[8]*/, Ta
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         Tab o = tab_shfl_up(inc, d);
-        if (lane >= d) inc = tab_compose(o, inc);
+        if (lane >= d) inc = tab_compose<FMT>(o, inc);
     }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    Tab pre = tab_identity();
-    for (int w = 0; w < warp; w++) pre = tab_compose(pre, s_warp[w]);
+    Tab pre = tab_identity(), tot = tab_identity();
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+        Tab x = s_warp[w];
+        if (w < warp) pre = tab_compose<FMT>(pre, x);
+        tot = tab_compose<FMT>(tot, x);
+    }
     Tab exl = tab_shfl_up(inc, 1);
     if (lane == 0) exl = tab_identity();
-    Tab tot = tab_identity();
-    for (int w = 0; w < SCAN_THREADS / 32; w++) tot = tab_compose(tot, s_warp[w]);
     *block_total = tot;
-    return tab_compose(pre, exl);
+    return tab_compose<FMT>(pre, exl);
 }
 
 // pass A: one table per tile
@@ -182,11 +285,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tables(const u8* __restri
                                                                const StreamState* ss, int next_after, TileTab* tabs)
 {
     __shared__ Tab s_warp[SCAN_THREADS / 32];
-    u64 tile = tile_first + blockIdx.x;
-    u64 a = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_BPT;
-    Chunk c; load_chunk(raw, a, lo, hi, ss, next_after, c);
-    Tab mine = chunk_table(FMT, c);
-    Tab tot; block_scan_tabs(mine, s_warp, &tot);
+    const u64 tile = tile_first + blockIdx.x;
+    const u64 a = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_BPT;
+    u32 w[8], active; bool prev_nl, next_flag;
+    load_chunk(raw, a, lo, hi, ss, next_after, w, active, prev_nl, next_flag);
+    CMasks m; chunk_masks(w, active, m);
+    Tab mine = chunk_table<FMT>(m, prev_nl, next_flag);
+    Tab tot; block_scan_tabs<FMT>(mine, s_warp, &tot);
     if (threadIdx.x == 0) {
         TileTab tt; tt.st = tot.st;
         for (int s = 0; s < 4; s++) tt.cnt[s] = tab_count(tot, s);
@@ -209,9 +314,11 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const TileTab* __restrict__
     u32 st[4] = {0, 1, 2, 3}; u32 cn[4] = {0, 0, 0, 0};
     for (u64 i = b; i < e; i++) {
         TileTab tt = tabs[i];
+#pragma unroll
         for (int s = 0; s < 4; s++) { cn[s] += tt.cnt[st[s]]; st[s] = (tt.st >> (2 * st[s])) & 3; }
     }
     s_st[t] = st[0] | (st[1] << 2) | (st[2] << 4) | (st[3] << 6);
+#pragma unroll
     for (int s = 0; s < 4; s++) s_cnt[t][s] = cn[s];
     __syncthreads();
     // phase 2: thread 0 chains the 1024 run tables
@@ -235,36 +342,53 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const TileTab* __restrict__
     }
 }
 
-// pass C: emit codes.  `carry0` = number of codes already at the front of the code buffer.
+// pass C: emit codes into the code buffer behind the carry of the previous chunk
 template <int FMT>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_emit(const u8* __restrict__ raw, u64 lo, u64 hi, u64 tile_first,
                                                              const StreamState* ss_ro, StreamState* ss, int next_after,
                                                              const TileIn* __restrict__ tin, u8* __restrict__ codes)
 {
     __shared__ Tab s_warp[SCAN_THREADS / 32];
-    __shared__ u8 s_out[SCAN_TILE];
+    __shared__ __align__(16) u8 s_out[SCAN_TILE + 32];
     __shared__ u32 s_red[3];
-    u64 tile = tile_first + blockIdx.x;
-    u64 a = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_BPT;
+    const u64 tile = tile_first + blockIdx.x;
+    const u64 a = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_BPT;
     if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
-    Chunk c; load_chunk(raw, a, lo, hi, ss_ro, next_after, c);
-    Tab mine = chunk_table(FMT, c);
-    Tab tot; Tab exl = block_scan_tabs(mine, s_warp, &tot);
-    TileIn ti = tin[blockIdx.x];
-    int state = tab_state(exl, ti.state);
-    u32 off = tab_count(exl, ti.state);
-    u32 tile_cnt = tab_count(tot, ti.state);
-    int err = 0; u32 nsep = 0, nbase = 0;
-    u8 tmp[SCAN_BPT];
-    int n = chunk_emit(FMT, c, state, tmp, err, nsep, nbase);
-    for (int i = 0; i < n; i++) s_out[off + i] = tmp[i];
-    // stats / errors
-    u32 wsep = __reduce_add_sync(0xFFFFFFFFu, nsep), wbase = __reduce_add_sync(0xFFFFFFFFu, nbase);
-    u32 werr = __reduce_or_sync(0xFFFFFFFFu, (u32)err);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_red[0], wsep); atomicAdd(&s_red[1], wbase); atomicOr(&s_red[2], werr); }
-    __syncthreads();
+    u32 w[8], active; bool prev_nl, next_flag;
+    load_chunk(raw, a, lo, hi, ss_ro, next_after, w, active, prev_nl, next_flag);
+    CMasks m; chunk_masks(w, active, m);
+    Tab mine = chunk_table<FMT>(m, prev_nl, next_flag);
+    Tab tot; Tab exl = block_scan_tabs<FMT>(mine, s_warp, &tot);
+    const TileIn ti = tin[blockIdx.x];
+    const int state = tab_state(exl, ti.state);
+    const u32 tile_cnt = tab_count(tot, ti.state);
     u8* dst = codes + ss_ro->carry + ti.base;
-    for (u32 i = threadIdx.x; i < tile_cnt; i += SCAN_THREADS) dst[i] = s_out[i];
+    const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);           // smem mirrors the 16-byte phase of dst
+    u32 off = pad + tab_count(exl, ti.state);
+    u32 em, sep, err;
+    chunk_emit_masks<FMT>(m, prev_nl, next_flag, state, em, sep, err);
+#pragma unroll
+    for (int i = 0; i < SCAN_BPT; i++) {
+        if ((em >> i) & 1u) {
+            const u32 c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            s_out[off++] = (u8)(((sep >> i) & 1u) ? (u32)CODE_SEP : encode_fast(c));
+        }
+    }
+    // stats / errors
+    const u32 nsep = __popc(sep & em), nbase = __popc(em) - nsep;
+    const u32 wsep = __reduce_add_sync(0xFFFFFFFFu, nsep), wbase = __reduce_add_sync(0xFFFFFFFFu, nbase);
+    const u32 werr = __reduce_or_sync(0xFFFFFFFFu, err);
+    if ((threadIdx.x & 31) == 0) { if (wsep) atomicAdd(&s_red[0], wsep); if (wbase) atomicAdd(&s_red[1], wbase); if (werr) atomicOr(&s_red[2], werr); }
+    __syncthreads();
+    // copy out: 16-byte vectors where a whole vector is ours, bytes at the two ragged ends
+    u8* dst0 = dst - pad;
+    const u32 end = pad + tile_cnt;
+    const u32 nvec = (end + 15) / 16;
+    for (u32 q = threadIdx.x; q < nvec; q += SCAN_THREADS) {
+        const u32 b0 = q * 16, b1 = b0 + 16;
+        if (b0 >= pad && b1 <= end) reinterpret_cast<uint4*>(dst0)[q] = reinterpret_cast<const uint4*>(s_out)[q];
+        else for (u32 j = (b0 > pad ? b0 : pad); j < (b1 < end ? b1 : end); j++) dst0[j] = s_out[j];
+    }
     if (threadIdx.x == 0) {
         if (s_red[0]) atomicAdd((unsigned long long*)&ss->nsep, (unsigned long long)s_red[0]);
         if (s_red[1]) atomicAdd((unsigned long long*)&ss->nbase, (unsigned long long)s_red[1]);
@@ -287,7 +411,7 @@ __global__ void k_scan_carry(u8* codes, StreamState* ss, int k)
 // end of a bank: nothing left can form a k-mer; restart the scanner
 __global__ void k_scan_reset_stream(StreamState* ss, int fmt)
 {
-    ss->fsm_state = (fmt == FMT_FASTA) ? ST_HDR : 0;   // FASTA: bytes before the first header are skipped
+    ss->fsm_state = (fmt == FMT_FASTA) ? ST_HDR : 0;
     ss->prev_byte = '\n'; ss->prev_byte_next = '\n';
     ss->carry = 0; ss->total = 0;
 }
