@@ -73,11 +73,12 @@ __device__ __forceinline__ void flush_hist(const u32* s_hist, unsigned long long
 struct AppendSmem { u32 wsum[2][8]; unsigned long long base[2]; };
 
 template <int KW, int MAXN>
-__device__ __forceinline__ void block_append(int n, const Kmer<KW>* k, const int32_t* v, u64* out_keys, u32* out_vals,
-                                             u64 out_cap, Counters* ctr, AppendSmem* sm, int par)
+__device__ __forceinline__ void block_append(u32 mask /*bit i: entry i is valid*/, const Kmer<KW>* k, const int32_t* v, u64* out_keys,
+                                             u32* out_vals, u64 out_cap, Counters* ctr, AppendSmem* sm, int par)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32 inc = (u32)n;
+    const u32 n = (u32)__popc(mask);
+    u32 inc = n;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
     if (lane == 31) sm->wsum[par][warp] = inc;
@@ -88,10 +89,10 @@ __device__ __forceinline__ void block_append(int n, const Kmer<KW>* k, const int
     if (tot == 0) return;                                          // uniform across the block
     if (threadIdx.x == 0) sm->base[par] = atomicAdd(&ctr->solid_n, (unsigned long long)tot);
     __syncthreads();
-    u64 pos = sm->base[par] + wpre + inc - (u32)n;
+    u64 pos = sm->base[par] + wpre + inc - n;
 #pragma unroll
     for (int i = 0; i < MAXN; i++) {
-        if (i < n) {
+        if ((mask >> i) & 1u) {
             if (pos < out_cap) {
 #pragma unroll
                 for (int q = 0; q < KW; q++) out_keys[pos * KW + q] = k[i].w[q];
@@ -110,37 +111,59 @@ __device__ __forceinline__ void cas128(u64* addr, u64 clo, u64 chi, u64 slo, u64
                  : "=l"(olo), "=l"(ohi) : "l"(clo), "l"(chi), "l"(slo), "l"(shi), "l"(addr) : "memory");
 }
 
-// find-or-claim the slot of `key`; returns slot or 0xFFFFFFFF on overflow
+// 32-byte (one L2 sector) load, L2-coherent: LDG.E.ENL2.256 on sm_100
+__device__ __forceinline__ void ld256cg(const u64* p, u64& a, u64& b, u64& c, u64& d)
+{
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+
+// find-or-claim the slot of `key`; returns slot or 0xFFFFFFFF on overflow.
+// Bucketed linear probing: a bucket is one 32-byte sector (4 x 64-bit keys or 2 x 128-bit keys), fetched with a
+// single 256-bit load, so a probe costs one L2 round trip and ~all k-mers resolve in their first bucket.
+// Slots only ever go EMPTY -> key during the insert phase, which makes a stale snapshot safe: a non-empty slot is
+// final, an empty-looking slot is validated by the CAS that claims it (the CAS returns the truth).
 __device__ __forceinline__ u32 table_slot(u64* keys, u32 smask, const Kmer<1>& key)
 {
     const u64 EMPTY = ~0ULL;
-    u32 slot = (u32)kmer_hash(key) & smask;
+    const u32 bmask = smask >> 2;
+    u32 b = (u32)kmer_hash(key) & bmask;
     for (u32 probe = 0; probe < HASH_MAX_PROBE; probe++) {
-        u64 cur = __ldcg(&keys[slot]);
-        if (cur == key.w[0]) return slot;
-        if (cur == EMPTY) {
-            u64 old = atomicCAS((unsigned long long*)&keys[slot], EMPTY, key.w[0]);
-            if (old == EMPTY || old == key.w[0]) return slot;
+        u64 kk[4];
+        ld256cg(keys + 4 * (u64)b, kk[0], kk[1], kk[2], kk[3]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (kk[i] == key.w[0]) return 4 * b + i;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (kk[i] == EMPTY) {
+                u64 old = atomicCAS((unsigned long long*)&keys[4 * (u64)b + i], EMPTY, key.w[0]);
+                if (old == EMPTY || old == key.w[0]) return 4 * b + i;
+            }
         }
-        slot = (slot + 1) & smask;
+        b = (b + 1) & bmask;
     }
     return 0xFFFFFFFFu;
 }
 __device__ __forceinline__ u32 table_slot(u64* keys, u32 smask, const Kmer<2>& key)
 {
     const u64 EMPTY = ~0ULL;
-    u32 slot = (u32)kmer_hash(key) & smask;
+    const u32 bmask = smask >> 1;
+    u32 b = (u32)kmer_hash(key) & bmask;
     for (u32 probe = 0; probe < HASH_MAX_PROBE; probe++) {
-        // a plain 16-byte load may be torn against a concurrent claim; it is only trusted when it shows a
-        // complete foreign key (neither half all-ones), which can never change again
-        ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(keys) + slot);
-        bool foreign = (cur.x != EMPTY) && (cur.y != EMPTY) && !(cur.x == key.w[0] && cur.y == key.w[1]);
-        if (!foreign) {
-            u64 olo, ohi;
-            cas128(keys + 2 * (u64)slot, EMPTY, EMPTY, key.w[0], key.w[1], olo, ohi);
-            if ((olo == EMPTY && ohi == EMPTY) || (olo == key.w[0] && ohi == key.w[1])) return slot;
+        u64 kk[4];
+        ld256cg(keys + 4 * (u64)b, kk[0], kk[1], kk[2], kk[3]);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            // a 16-byte key may be read torn against a concurrent claim; the snapshot is only trusted when it shows
+            // a complete foreign key (neither half all-ones), which can never change again
+            const u64 lo = kk[2 * i], hi = kk[2 * i + 1];
+            const bool foreign = (lo != EMPTY) && (hi != EMPTY) && !(lo == key.w[0] && hi == key.w[1]);
+            if (!foreign) {
+                u64 olo, ohi;
+                cas128(keys + 4 * (u64)b + 2 * i, EMPTY, EMPTY, key.w[0], key.w[1], olo, ohi);
+                if ((olo == EMPTY && ohi == EMPTY) || (olo == key.w[0] && ohi == key.w[1])) return 2 * b + i;
+            }
         }
-        slot = (slot + 1) & smask;
+        b = (b + 1) & bmask;
     }
     return 0xFFFFFFFFu;
 }
@@ -214,13 +237,16 @@ __global__ void __launch_bounds__(256) k_hash_insert(const u64* __restrict__ rec
 }
 
 // ---- K6 (hash flavour): sweep the table, run the processor chain, reset the slots ---------------------------------
-// each thread owns SV consecutive slots per iteration (32 bytes of keys = one sector)
-template <int KW>
+// each thread owns SV consecutive slots per iteration; keys and (single-bank) counts come in as independent
+// 16-byte vector loads so one iteration costs one memory round trip
+template <int KW, bool NB1>
 __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 nslots, SolidityParams sp, int discard,
                                                    u64* out_keys, u32* out_vals, u64 out_cap,
                                                    unsigned long long* g_hist, unsigned long long* g_hist2d, Counters* ctr)
 {
-    constexpr int SV = (KW == 1) ? 4 : 2;
+    constexpr int SV = (KW == 1) ? 8 : 4;                          // slots per thread-iteration
+    constexpr int KV = SV * KW / 2;                                // 16-byte key vectors per iteration (4)
+    constexpr int CV = SV / 4;                                     // 16-byte count vectors (NB1 only)
     __shared__ u32 s_hist[HIST_SMEM_BINS];
     __shared__ u32 s_distinct;
     __shared__ AppendSmem s_app;
@@ -233,32 +259,49 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
     const u32 nthreads = blockDim.x * gridDim.x;
     const u32 nloop = (ngroups + nthreads - 1) / nthreads;
     ulonglong2* k2 = reinterpret_cast<ulonglong2*>(keys);
+    uint4* c4 = reinterpret_cast<uint4*>(counts);
     for (u32 it = 0; it < nloop; it++) {
         const u32 g = it * nthreads + blockIdx.x * blockDim.x + threadIdx.x;
-        ulonglong2 v[2];
         const bool in = g < ngroups;
-        v[0] = in ? k2[2 * (u64)g] : make_ulonglong2(EMPTY, EMPTY);
-        v[1] = in ? k2[2 * (u64)g + 1] : make_ulonglong2(EMPTY, EMPTY);
-        bool any = false;
-        Kmer<KW> sk[SV]; int32_t sv[SV]; int ns = 0;
+        ulonglong2 v[KV]; uint4 cvec[CV > 0 ? CV : 1];
+#pragma unroll
+        for (int q = 0; q < KV; q++) v[q] = in ? k2[(u64)g * KV + q] : make_ulonglong2(EMPTY, EMPTY);
+        if (NB1) {
+#pragma unroll
+            for (int q = 0; q < CV; q++) cvec[q] = in ? c4[(u64)g * CV + q] : make_uint4(0, 0, 0, 0);
+        }
+        u32 occm = 0;
+        Kmer<KW> sk[SV]; int32_t sv[SV]; u32 solidm = 0;
 #pragma unroll
         for (int q = 0; q < SV; q++) {
-            Kmer<KW> key; bool occ;
-            if constexpr (KW == 1) { key.w[0] = (q & 1) ? v[q >> 1].y : v[q >> 1].x; occ = key.w[0] != EMPTY; }
-            else { key.w[0] = v[q].x; key.w[1] = v[q].y; occ = !(v[q].x == EMPTY && v[q].y == EMPTY); }
-            if (occ) {
-                const u64 slot = (u64)g * SV + q;
-                u32 cv[MAXB]; int32_t sum = 0;
-                for (int b = 0; b < sp.nbanks; b++) { cv[b] = counts[slot * sp.nbanks + b]; counts[slot * sp.nbanks + b] = 0; }
-                any = true;
-                if (!discard) {
-                    ndist++;
-                    if (process_counts(cv, sp, s_hist, g_hist, g_hist2d, &sum)) { sk[ns] = key; sv[ns] = sum; ns++; }
-                }
+            if constexpr (KW == 1) { sk[q].w[0] = (q & 1) ? v[q >> 1].y : v[q >> 1].x; if (sk[q].w[0] != EMPTY) occm |= 1u << q; }
+            else { sk[q].w[0] = v[q].x; sk[q].w[1] = v[q].y; if (!(v[q].x == EMPTY && v[q].y == EMPTY)) occm |= 1u << q; }
+            sv[q] = 0;
+        }
+        if (occm) {
+#pragma unroll
+            for (int q = 0; q < KV; q++) k2[(u64)g * KV + q] = make_ulonglong2(EMPTY, EMPTY);
+            if (NB1) {
+#pragma unroll
+                for (int q = 0; q < CV; q++) c4[(u64)g * CV + q] = make_uint4(0, 0, 0, 0);
             }
         }
-        if (any) { k2[2 * (u64)g] = make_ulonglong2(EMPTY, EMPTY); k2[2 * (u64)g + 1] = make_ulonglong2(EMPTY, EMPTY); }
-        block_append<KW, SV>(ns, sk, sv, out_keys, out_vals, out_cap, ctr, &s_app, (int)(it & 1));
+#pragma unroll
+        for (int q = 0; q < SV; q++) {
+            if (!((occm >> q) & 1u)) continue;
+            u32 cv[MAXB];
+            if (NB1) { const uint4 c = cvec[q >> 2]; cv[0] = (q & 3) == 0 ? c.x : (q & 3) == 1 ? c.y : (q & 3) == 2 ? c.z : c.w; }
+            else {
+                const u64 slot = (u64)g * SV + q;
+                for (int b = 0; b < sp.nbanks; b++) { cv[b] = counts[slot * sp.nbanks + b]; counts[slot * sp.nbanks + b] = 0; }
+            }
+            if (!discard) {
+                ndist++;
+                int32_t sum = 0;
+                if (process_counts(cv, sp, s_hist, g_hist, g_hist2d, &sum)) { sv[q] = sum; solidm |= 1u << q; }
+            }
+        }
+        block_append<KW, SV>(solidm, sk, sv, out_keys, out_vals, out_cap, ctr, &s_app, (int)(it & 1));
     }
     ndist = __reduce_add_sync(0xFFFFFFFFu, ndist);
     if ((threadIdx.x & 31) == 0 && ndist) atomicAdd(&s_distinct, ndist);
@@ -335,12 +378,13 @@ __global__ void __launch_bounds__(256) k_rle_emit(const u64* __restrict__ keys, 
     const u64 per_it = (u64)blockDim.x * gridDim.x * RI;
     const u64 nloop = (n + per_it - 1) / per_it;
     for (u64 it = 0; it < nloop; it++) {
-        Kmer<KW> sk[RI]; int32_t sv[RI]; int ns = 0;
+        Kmer<KW> sk[RI]; int32_t sv[RI]; u32 solidm = 0;
 #pragma unroll
         for (int r = 0; r < RI; r++) {
             const u64 i = it * per_it + ((u64)r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
             if (i >= n) continue;
             const Kmer<KW> key = load(i);
+            sk[r] = key; sv[r] = 0;
             const bool head = (i == 0) || !kmer_eq(load(i - 1), key);
             if (!head) continue;
             u64 step = 1, lo = i;                                  // keys[lo] == key ; find last equal
@@ -352,9 +396,9 @@ __global__ void __launch_bounds__(256) k_rle_emit(const u64* __restrict__ keys, 
             if (sp.nbanks == 1) cv[0] = (u32)cnt;
             else { for (int b = 0; b < sp.nbanks; b++) cv[b] = 0; for (u64 j = i; j <= lo; j++) cv[banks[j]]++; }
             ndist++;
-            if (process_counts(cv, sp, s_hist, g_hist, g_hist2d, &sum)) { sk[ns] = key; sv[ns] = sum; ns++; }
+            if (process_counts(cv, sp, s_hist, g_hist, g_hist2d, &sum)) { sv[r] = sum; solidm |= 1u << r; }
         }
-        block_append<KW, RI>(ns, sk, sv, out_keys, out_vals, out_cap, ctr, &s_app, (int)(it & 1));
+        block_append<KW, RI>(solidm, sk, sv, out_keys, out_vals, out_cap, ctr, &s_app, (int)(it & 1));
     }
     ndist = __reduce_add_sync(0xFFFFFFFFu, ndist);
     if ((threadIdx.x & 31) == 0 && ndist) atomicAdd(&s_distinct, ndist);

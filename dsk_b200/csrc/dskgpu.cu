@@ -543,10 +543,16 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
                                                                               (u32)(slots - 1), ctx->NB, ctr); LAUNCHED();
         cudaEventRecord(b, ctx->stream);
         ctx->spans.push_back({a, b, SPAN_DOM});
-        const unsigned gs = (unsigned)std::min<u64>((slots + 255) / 256, 148 * 8);
-        k_hash_scan<KW><<<gs, 256, 0, ctx->stream>>>((u64*)ctx->tkeys.p, (u32*)ctx->tcounts.p, (u32)slots, sp, 0, (u64*)ctx->skeys[0].p,
-                                                     (u32*)ctx->svals[0].p, out_cap, (unsigned long long*)ctx->hist.p,
-                                                     (unsigned long long*)ctx->hist2d.p, ctr); LAUNCHED();
+        const unsigned gs = (unsigned)std::min<u64>((slots / 8 + 255) / 256, 148 * 8);
+        if (ctx->NB == 1)
+            k_hash_scan<KW, true><<<gs, 256, 0, ctx->stream>>>((u64*)ctx->tkeys.p, (u32*)ctx->tcounts.p, (u32)slots, sp, 0, (u64*)ctx->skeys[0].p,
+                                                               (u32*)ctx->svals[0].p, out_cap, (unsigned long long*)ctx->hist.p,
+                                                               (unsigned long long*)ctx->hist2d.p, ctr);
+        else
+            k_hash_scan<KW, false><<<gs, 256, 0, ctx->stream>>>((u64*)ctx->tkeys.p, (u32*)ctx->tcounts.p, (u32)slots, sp, 0, (u64*)ctx->skeys[0].p,
+                                                                (u32*)ctx->svals[0].p, out_cap, (unsigned long long*)ctx->hist.p,
+                                                                (unsigned long long*)ctx->hist2d.p, ctr);
+        LAUNCHED();
         ctx->st.nb_groups_hash++;
         (void)gi; (void)kmers;
         return 0;
