@@ -92,7 +92,7 @@ static int ensure(dskgpu_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false, s
     return 0;
 }
 
-enum { SPAN_PARSE = 0, SPAN_SUPERK = 1, SPAN_PART = 2, SPAN_COUNT = 3, SPAN_SORT = 4, SPAN_DOM = 5, SPAN_TOTAL = 6 };
+enum { SPAN_PARSE = 0, SPAN_SUPERK = 1, SPAN_PART = 2, SPAN_COUNT = 3, SPAN_SORT = 4, SPAN_DOM = 5, SPAN_TOTAL = 6, SPAN_SORTPASS = 7 };
 
 static cudaEvent_t get_event(dskgpu_ctx* ctx)
 {
@@ -459,7 +459,7 @@ static int radix_sort(dskgpu_ctx* ctx, u64* keys[2], u32* vals[2], u64 n, int np
             (const unsigned long long*)ctx->rs_hist.p + (size_t)p * 256, (u32*)ctx->rs_status.p, (u32*)ctx->rs_tilectr.p + p);
         LAUNCHED();
         cudaEventRecord(b, ctx->stream);
-        ctx->spans.push_back({a, b, HAS_VAL ? SPAN_SORT : SPAN_DOM});
+        ctx->spans.push_back({a, b, HAS_VAL ? SPAN_SORTPASS : SPAN_DOM});
         cur ^= 1;
     }
     *result_buf = cur;
@@ -796,7 +796,7 @@ static int64_t selftest_scan_fmt(const u8* raw, u64 lo, u64 hi, uint8_t* out, si
         const u64 last_end = (a + SCAN_BPT < hi) ? a + SCAN_BPT : hi;
         const int next = (last_end < hi) ? (int)raw[last_end] : -1;
         const bool prev_nl = prev == '\n', next_flag = (next == '\n') || next < 0;
-        CMasks m; chunk_masks(words, active, m);
+        CMasks m; chunk_masks(words, active, prev_nl, m);
         const Tab t = chunk_table<FMT>(m, prev_nl, next_flag);
         u32 em, sep, e2;
         chunk_emit_masks<FMT>(m, prev_nl, next_flag, state, em, sep, e2);

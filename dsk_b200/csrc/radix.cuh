@@ -21,7 +21,10 @@ template <int KW> struct RsCfg { static constexpr int ITEMS = (KW == 1) ? 16 : 8
 
 template <int KW> __device__ __forceinline__ u32 rs_digit(const u64* key, int pass)
 {
-    return (u32)(key[pass >> 3] >> ((pass & 7) * 8)) & 0xFFu;
+    // no dynamic indexing: it would push the caller's key registers into local memory
+    u64 w = key[0];
+    if constexpr (KW == 2) w = (pass & 8) ? key[1] : key[0];
+    return (u32)(w >> ((pass & 7) * 8)) & 0xFFu;
 }
 
 // histogram of every digit of every key in one read: hist[pass][256]
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(256) k_rs_scan(unsigned long long* hist)
 }
 
 template <int KW, bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(const u64* __restrict__ in_keys, u64* __restrict__ out_keys,
+__global__ void __launch_bounds__(RS_THREADS, 3) k_rs_onesweep(const u64* __restrict__ in_keys, u64* __restrict__ out_keys,
                                                             const u32* __restrict__ in_vals, u32* __restrict__ out_vals,
                                                             u64 n, int pass, const unsigned long long* __restrict__ gbase /*[256]*/,
                                                             u32* status /*[ntiles][256]*/, u32* tile_counter)
@@ -80,14 +83,13 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(const u64* __restric
     const u32 nvalid = (u32)((n - tile0 < (u64)TILE) ? (n - tile0) : (u64)TILE);
 
     // 1. load (warp-striped) and rank within the warp, stable
-    u64 key[ITEMS][KW]; u32 val[ITEMS]; u32 rd[ITEMS];              // rd = rank | digit << 16
+    u64 key[ITEMS][KW]; u32 rd[ITEMS];                             // rd = rank | digit << 16
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
         u32 li = (u32)warp * 32 * ITEMS + r * 32 + lane;           // index inside the tile
         bool ok = li < nvalid;
 #pragma unroll
         for (int q = 0; q < KW; q++) key[r][q] = ok ? in_keys[(tile0 + li) * KW + q] : ~0ULL;
-        if (HAS_VAL) val[r] = ok ? in_vals[tile0 + li] : 0u;
         u32 d = ok ? rs_digit<KW>(key[r], pass) : 256u;            // padding sorts after everything, never written
         u32 peers = __match_any_sync(0xFFFFFFFFu, d);
         u32 pre = (d < 256u) ? s_wc[warp][d] : 0u;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(const u64* __restric
             u32 idx = s_dstart[d] + s_wc[warp][d] + (rd[r] & 0xFFFFu);
 #pragma unroll
             for (int q = 0; q < KW; q++) s_keys[idx * KW + q] = key[r][q];
-            if (HAS_VAL) s_vals[idx] = val[r];
+            if (HAS_VAL) s_vals[idx] = in_vals[tile0 + (u32)warp * 32 * ITEMS + r * 32 + lane];   // payload fetched late: keeps 16 registers free
         }
     }
     __syncthreads();

@@ -50,19 +50,47 @@ struct CMasks { u32 nl, gt, plus, at, cr, active; };
 
 DSK_HD u32 bits_below(int b) { return b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u); }     // bits [0, b)
 
-DSK_HD void chunk_masks(const u32* w /*[8]*/, u32 active, CMasks& m)
+// 4-bit mask of the bytes of w equal to the byte replicated in pat4 (exact SWAR zero-byte test + multiply gather)
+DSK_HD u32 eqmask4(u32 w, u32 pat4)
 {
-    u32 nl = 0, gt = 0, plus = 0, at = 0, cr = 0;
+    const u32 x = w ^ pat4;
+    const u32 z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;     // 0x80 in every byte of x that is zero
+    return ((z >> 7) * 0x10204080u) >> 28;
+}
+DSK_HD u32 byte_at(const u32* w, int p)                      // byte p of the chunk without dynamic register indexing
+{
+    u32 x = w[0];
 #pragma unroll
-    for (int i = 0; i < SCAN_BPT; i++) {
-        const u32 c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-        nl   |= (c == '\n' ? 1u : 0u) << i;
-        gt   |= (((c == '>') | (c == '@')) ? 1u : 0u) << i;
-        at   |= (c == '@' ? 1u : 0u) << i;
-        plus |= (c == '+' ? 1u : 0u) << i;
-        cr   |= (c == '\r' ? 1u : 0u) << i;
+    for (int i = 1; i < 8; i++) x = ((p >> 2) == i) ? w[i] : x;
+    return (x >> (8 * (p & 3))) & 0xFFu;
+}
+
+// newline / CR masks for all bytes (SWAR); '>', '@', '+' only matter at line starts, so they are looked up there only
+DSK_HD void chunk_masks(const u32* w /*[8]*/, u32 active, bool prev_nl, CMasks& m)
+{
+    u32 nl = 0, cr = 0, anycr = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        nl |= eqmask4(w[i], 0x0A0A0A0Au) << (4 * i);
+        const u32 x = w[i] ^ 0x0D0D0D0Du;
+        anycr |= ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
     }
-    m.nl = nl & active; m.gt = gt & active; m.plus = plus & active; m.at = at & active; m.cr = cr & active; m.active = active;
+    if (anycr) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) cr |= eqmask4(w[i], 0x0D0D0D0Du) << (4 * i);
+    }
+    nl &= active; cr &= active;
+    u32 gt = 0, at = 0, plus = 0;
+    u32 ls = ((nl << 1) | ((prev_nl && active) ? (1u << ctz32(active)) : 0u)) & active;
+    while (ls) {
+        const int p = ctz32(ls);
+        const u32 c = byte_at(w, p);
+        gt   |= (((c == '>') | (c == '@')) ? 1u : 0u) << p;
+        at   |= (c == '@' ? 1u : 0u) << p;
+        plus |= (c == '+' ? 1u : 0u) << p;
+        ls &= ls - 1;
+    }
+    m.nl = nl; m.gt = gt; m.plus = plus; m.at = at; m.cr = cr; m.active = active;     // gt/at/plus: line starts only
 }
 
 // CR bytes that are dropped: followed by '\n' or by the end of the stream (BankFasta.cpp:471)
@@ -289,7 +317,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tables(const u8* __restri
     const u64 a = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_BPT;
     u32 w[8], active; bool prev_nl, next_flag;
     load_chunk(raw, a, lo, hi, ss, next_after, w, active, prev_nl, next_flag);
-    CMasks m; chunk_masks(w, active, m);
+    CMasks m; chunk_masks(w, active, prev_nl, m);
     Tab mine = chunk_table<FMT>(m, prev_nl, next_flag);
     Tab tot; block_scan_tabs<FMT>(mine, s_warp, &tot);
     if (threadIdx.x == 0) {
@@ -356,7 +384,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_emit(const u8* __restrict
     if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
     u32 w[8], active; bool prev_nl, next_flag;
     load_chunk(raw, a, lo, hi, ss_ro, next_after, w, active, prev_nl, next_flag);
-    CMasks m; chunk_masks(w, active, m);
+    CMasks m; chunk_masks(w, active, prev_nl, m);
     Tab mine = chunk_table<FMT>(m, prev_nl, next_flag);
     Tab tot; Tab exl = block_scan_tabs<FMT>(mine, s_warp, &tot);
     const TileIn ti = tin[blockIdx.x];

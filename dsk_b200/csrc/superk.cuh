@@ -65,14 +65,12 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
 
     // ---- 1. load 8 codes per thread, pack to 2 bits + invalid bitmap ---------------------------------
     auto load8 = [&](int ti) {
-        u64 v = *reinterpret_cast<const u64*>(codes + tile0 + 8 * (u64)ti);
-        u32 p16 = 0, b8 = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            u32 c = (u32)(v >> (8 * j)) & 0xFFu;
-            p16 |= (c & 3u) << (14 - 2 * j);
-            b8 |= ((c >> 2) ? 1u : 0u) << (7 - j);
-        }
+        const uint2 v = *reinterpret_cast<const uint2*>(codes + tile0 + 8 * (u64)ti);
+        // SWAR: gather the 2-bit codes / the "not a valid base" flags of 4 bytes with one multiply each
+        auto pack4 = [](u32 w) -> u32 { return ((w & 0x03030303u) * 0x40100401u) >> 24; };               // byte j -> bits 7-2j..6-2j
+        auto bad4 = [](u32 w) -> u32 { u32 nz = ((((w >> 2) & 0x03030303u) + 0x03030303u) >> 2) & 0x01010101u; return (nz * 0x80402010u) >> 28; };
+        const u32 p16 = (pack4(v.x) << 8) | pack4(v.y);
+        const u32 b8 = (bad4(v.x) << 4) | bad4(v.y);
         reinterpret_cast<u16*>(s_pk)[(ti >> 2) * 4 + (3 - (ti & 3))] = (u16)p16;
         reinterpret_cast<u8*>(s_bad)[(ti >> 3) * 8 + (7 - (ti & 7))] = (u8)b8;
     };
@@ -164,20 +162,20 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
     // ---- 4. split runs longer than maxS, count records, reserve output space -----------------------------------
     u32 chunkmask = 0;
     {
-        u32 rel = 0;
+        u32 rel = 0;                                              // index of the window inside its run, modulo maxS
         if ((validmask & 0x80u) && !(startmask & 0x80u)) {       // my first window continues a run: find its start
             u32 q = p0 - 1;                                       // p0 > 0 here (thread 0 always starts a run)
             int wi = (int)(q >> 5);
             u32 bits = s_start[wi] & (0xFFFFFFFFu << (31 - (q & 31)));
             while (bits == 0) { wi--; bits = s_start[wi]; }
             u32 rs = (u32)wi * 32 + 31 - (u32)(__ffs((int)bits) - 1);
-            rel = p0 - rs;
+            rel = (p0 - rs) % (u32)maxS;
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            bool v = (validmask >> (7 - j)) & 1u;
-            if ((startmask >> (7 - j)) & 1u) rel = 0;
-            if (v) { if (rel % (u32)maxS == 0) chunkmask |= 1u << (7 - j); rel++; }
+            const u32 bit = 1u << (7 - j);
+            if (startmask & bit) rel = 0;
+            if (validmask & bit) { if (rel == 0) chunkmask |= bit; rel++; if (rel == (u32)maxS) rel = 0; }
         }
     }
     u32 nch = __popc(chunkmask);
@@ -200,37 +198,39 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
     }
     __syncthreads();
     const u64 goff = s_goff;
-    if (goff + btotal > rec_cap) { if (t == 0) atomicExch(&ctr->overflow, 1u); return; }
+    if (goff + btotal > rec_cap) { if (t == 0) atomicExch(&ctr->overflow, 1u); return; }   // uniform: whole block leaves
 
-    // ---- 5. emit records --------------------------------------------------------------------------------------
-    u32 nk_sum = 0;
+    // ---- 5. emit records: chunk starts are listed in smem, then thread i builds record i (coalesced stores) ------
+    __shared__ u16 s_list[SK_TP];                                 // tile-relative position of every record start
+    u32* s_lmn = s_mv;                                            // its minimizer (s_mv is dead after step 3)
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        if (!((chunkmask >> (7 - j)) & 1u)) continue;
-        u32 p = p0 + j;
+        if ((chunkmask >> (7 - j)) & 1u) { s_list[myidx] = p0 + j; s_lmn[myidx] = mn[j]; myidx++; }
+    }
+    __syncthreads();
+    u32 nk_sum = 0;
+    for (u32 i = t; i < btotal; i += SK_THREADS) {
+        const u32 p = s_list[i];
         // next break strictly after p (bounded: s_brk is all ones past the tile)
         u32 q = p + 1; u32 wi = q >> 5;
         u32 bits = s_brk[wi] & (0xFFFFFFFFu >> (q & 31));
-        u32 nk;
-        {
-            u32 steps = 0;
-            while (bits == 0 && steps < 9) { wi++; bits = s_brk[wi]; steps++; }
-            u32 nb = bits ? (wi * 32 + (u32)__clz((int)bits)) : (p + (u32)maxS);
-            nk = min((u32)maxS, nb - p);
-        }
+        u32 steps = 0;
+        while (bits == 0 && steps < 9) { wi++; bits = s_brk[wi]; steps++; }
+        const u32 nb = bits ? (wi * 32 + (u32)__clz((int)bits)) : (p + (u32)maxS);
+        const u32 nk = min((u32)maxS, nb - p);
         u64 rw[RW];
 #pragma unroll
-        for (int i = 0; i < RW; i++) rw[i] = get64(p + 32 * i);
+        for (int x = 0; x < RW; x++) rw[x] = get64(p + 32 * x);
         rw[RW - 1] = (rw[RW - 1] & ~0xFFFFULL) | ((u64)nk << 8) | (u64)bank;
-        u64 ri = goff + myidx;
+        const u64 ri = goff + i;
         if constexpr (RW == 2) {
             reinterpret_cast<ulonglong2*>(recs)[ri] = make_ulonglong2(rw[0], rw[1]);
         } else {
             reinterpret_cast<ulonglong2*>(recs)[2 * ri] = make_ulonglong2(rw[0], rw[1]);
             reinterpret_cast<ulonglong2*>(recs)[2 * ri + 1] = make_ulonglong2(rw[2], rw[3]);
         }
-        rec_meta[ri] = mn[j] | (nk << 24);
-        myidx++; nk_sum += nk;
+        rec_meta[ri] = s_lmn[i] | (nk << 24);
+        nk_sum += nk;
     }
     nk_sum = __reduce_add_sync(0xFFFFFFFFu, nk_sum);
     if (lane == 0 && nk_sum) atomicAdd(&ctr->kmers_in_recs, (unsigned long long)nk_sum);
