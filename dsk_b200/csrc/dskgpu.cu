@@ -526,7 +526,7 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
         if ((rc = ensure(ctx, ctx->svals[i], out_cap * 4))) return rc;
     }
     const int mode = ctx->cfg.count_mode;
-    const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 22;
+    const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 23;
     u64 nslots = (u64)1 << log2s;
     const double load_max = 0.6;
     const u64 sort_cap = (u64)1 << 28;                             // keys per sort-path group
@@ -637,7 +637,7 @@ static int finish_impl(dskgpu_ctx* ctx)
     ctx->st.kmers_nb_valid = nkm; ctx->st.nb_superkmers = nrec; ctx->st.superkmer_bytes = nrec * (u64)ctx->RW * 8;
 
     // ---- partition plan: P partitions of ~ (table capacity / 4) k-mers each --------------------------------
-    const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 22;
+    const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 23;
     const u64 target = std::max<u64>(((u64)1 << log2s) * 6 / 10 / 4, 4096);
     u32 P = ctx->cfg.nb_partitions > 0 ? (u32)ctx->cfg.nb_partitions : (u32)std::min<u64>(4096, (nkm + target - 1) / target);
     if (P < 1) P = 1;
