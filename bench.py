@@ -239,12 +239,18 @@ def main():
         torch.cuda.synchronize()
 
     eng = GpuCounter(kmer_size=args.kmer_size, abundance_min=2, device=local, stream=stream.cuda_stream, count_mode=args.count_mode,
-                     hash_log2_slots=args.hash_log2_slots, keep_results_on_device=True)
+                     hash_log2_slots=args.hash_log2_slots, keep_results_on_device=True, rank=rank, world_size=world)
+
+    from dsk_b200.distributed import distributed_finish
+    devobj = torch.device("cuda", local)
 
     def step_device():
         eng.reset()
         eng.push_device_bytes(dev.data_ptr(), n, fmt="fasta")
-        eng.finish()
+        if world > 1:
+            distributed_finish(eng, dist, devobj)
+        else:
+            eng.finish()
 
     for _ in range(args.warmup):
         step_device()
@@ -278,13 +284,16 @@ def main():
     e2e = None
     if not args.no_e2e:
         eng2 = GpuCounter(kmer_size=args.kmer_size, abundance_min=2, device=local, stream=stream.cuda_stream, count_mode=args.count_mode,
-                          hash_log2_slots=args.hash_log2_slots, keep_results_on_device=False)
+                          hash_log2_slots=args.hash_log2_slots, keep_results_on_device=False, rank=rank, world_size=world)
         hptr = pinned.data_ptr()
 
         def step_e2e():
             eng2.reset()
             eng2.push_bytes((hptr, n), fmt="fasta")
-            eng2.finish()
+            if world > 1:
+                distributed_finish(eng2, dist, devobj)
+            else:
+                eng2.finish()
             return eng2.stats()
 
         for _ in range(max(1, args.warmup)):

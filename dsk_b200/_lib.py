@@ -46,8 +46,8 @@ SYMBOLS = [
     "dskgpu_finish", "dskgpu_num_partitions", "dskgpu_partition", "dskgpu_partition_device", "dskgpu_histogram",
     "dskgpu_get_stats", "dskgpu_reset", "dskgpu_destroy", "dskgpu_host_alloc", "dskgpu_host_free", "dskgpu_strerror",
     "dskgpu_last_error", "dskgpu_device_count", "dskgpu_abi_version",
-    "dskgpu_xchg_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_send_buffer", "dskgpu_xchg_set_peers",
-    "dskgpu_xchg_scatter", "dskgpu_record_bytes",
+    "dskgpu_xchg_local_totals", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
+    "dskgpu_xchg_open_peer", "dskgpu_xchg_set_peers", "dskgpu_xchg_scatter", "dskgpu_xchg_sync", "dskgpu_xchg_layout", "dskgpu_record_bytes",
     "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers",
 ]
 
@@ -87,12 +87,16 @@ def lib():
     L.dskgpu_strerror.restype = C.c_char_p
     L.dskgpu_last_error.argtypes = [C.c_void_p]
     L.dskgpu_last_error.restype = C.c_char_p
-    L.dskgpu_xchg_counts.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg_local_totals.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
+    L.dskgpu_xchg_part_counts.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, P(C.c_uint32)]
     L.dskgpu_xchg_plan.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_recv_buffer.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_size_t)]
-    L.dskgpu_xchg_send_buffer.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_size_t), C.c_void_p]
+    L.dskgpu_xchg_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg_open_peer.argtypes = [C.c_void_p, C.c_void_p, P(C.c_void_p)]
     L.dskgpu_xchg_set_peers.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_scatter.argtypes = [C.c_void_p]
+    L.dskgpu_xchg_sync.argtypes = [C.c_void_p]
+    L.dskgpu_xchg_layout.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.dskgpu_record_bytes.argtypes = [C.c_void_p]
     L.dskgpu_selftest_scan.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
     L.dskgpu_selftest_scan.restype = C.c_int64

@@ -140,3 +140,55 @@ class GpuCounter:
 
     def __exit__(self, *a):
         self.close()
+
+
+# ---- multi-GPU exchange (include/dskgpu.h "multi-GPU exchange") ----------------------------------------------
+def _xchg_methods():
+    def xchg_local_totals(self):
+        km, nr = C.c_uint64(), C.c_uint64()
+        self._check(self.L.dskgpu_xchg_local_totals(self.h, C.byref(km), C.byref(nr)))
+        return km.value, nr.value
+
+    def xchg_part_counts(self, global_kmers):
+        P = C.c_uint32()
+        self._check(self.L.dskgpu_xchg_part_counts(self.h, global_kmers, None, C.byref(P)))
+        counts = np.zeros(2 * P.value, dtype=np.uint64)
+        self._check(self.L.dskgpu_xchg_part_counts(self.h, global_kmers, counts.ctypes.data, C.byref(P)))
+        return counts
+
+    def xchg_plan(self, all_counts):
+        a = np.ascontiguousarray(all_counts, dtype=np.uint64)
+        self._check(self.L.dskgpu_xchg_plan(self.h, a.ctypes.data))
+
+    def xchg_recv_buffer(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.L.dskgpu_xchg_recv_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def xchg_ipc_handle(self):
+        buf = (C.c_ubyte * 64)()
+        self._check(self.L.dskgpu_xchg_ipc_handle(self.h, buf))
+        return bytes(buf)
+
+    def xchg_open_peer(self, handle):
+        p = C.c_void_p()
+        hb = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self.L.dskgpu_xchg_open_peer(self.h, hb, C.byref(p)))
+        return p.value
+
+    def xchg_set_peers(self, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(x) if x else 0) for x in ptrs])
+        self._check(self.L.dskgpu_xchg_set_peers(self.h, arr))
+
+    def xchg_scatter(self):
+        self._check(self.L.dskgpu_xchg_scatter(self.h))
+
+    def xchg_sync(self):
+        self._check(self.L.dskgpu_xchg_sync(self.h))
+
+    for f in (xchg_local_totals, xchg_part_counts, xchg_plan, xchg_recv_buffer, xchg_ipc_handle, xchg_open_peer, xchg_set_peers,
+              xchg_scatter, xchg_sync):
+        setattr(GpuCounter, f.__name__, f)
+
+
+_xchg_methods()

@@ -63,7 +63,9 @@ struct dskgpu_ctx {
     u32 nparts = 0;
     // multi-GPU
     std::vector<u64> xchg_matrix; std::vector<void*> peer_recv; bool xchg_planned = false; bool xchg_scattered = false;
-    u64 my_nrec_owned = 0; std::vector<u64> part_off_owned;     // offsets of my partitions in my receive buffer
+    u64 my_nrec_owned = 0; std::vector<u64> owned_recs, owned_kmers;   // my partitions in my receive buffer (increasing id)
+    std::vector<void*> ipc_opened;
+    bool totals_done = false; u64 local_nrec = 0, local_nkm = 0;
     DevBuf sendbuf;
     dskgpu_stats st;
     // timing
@@ -200,7 +202,8 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     ctx->state = 0; ctx->cur_bank = -1; ctx->stream_open = false; ctx->pending_cr = 0;
     ctx->nrec_known = 0; ctx->k2_inflight = false; ctx->chunk_parity = 0;
     ctx->n_solid = 0; ctx->results_on_host = false; ctx->nparts = 0;
-    ctx->xchg_planned = false; ctx->xchg_scattered = false;
+    ctx->xchg_planned = false; ctx->xchg_scattered = false; ctx->totals_done = false; ctx->local_nrec = ctx->local_nkm = 0;
+    ctx->peer_recv.clear();
     ctx->ev_used = 0; ctx->spans.clear();
     u64 launches = 0;
     memset(&ctx->st, 0, sizeof ctx->st); ctx->st.gpu_launches = launches;
@@ -216,6 +219,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
                      &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr, &ctx->sendbuf};
     for (DevBuf* b : all) b->release();
+    for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
     if (ctx->ev_k2) cudaEventDestroy(ctx->ev_k2);
@@ -618,11 +622,11 @@ static float span_ms(dskgpu_ctx* ctx, int kind, u32* count = nullptr)
     return tot;
 }
 
-template <int KW>
-static int finish_impl(dskgpu_ctx* ctx)
+// ---- stage 1: close the input, read the totals --------------------------------------------------------------------
+static int stage_totals(dskgpu_ctx* ctx)
 {
+    if (ctx->totals_done) return 0;
     Counters* ctr = (Counters*)ctx->ctr.p;
-    int rc;
     if (ctx->stream_open) close_stream(ctx);
     CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_ss, ctx->ss.p, sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -632,49 +636,79 @@ static int finish_impl(dskgpu_ctx* ctx)
     if (ctx->h_ctr->overflow) FAIL(DSKGPU_ERR_OVERFLOW, "super-k-mer record buffer overflow");
     if (ctx->h_ctr->kmers_valid != ctx->h_ctr->kmers_in_recs)
         FAIL(DSKGPU_ERR_OVERFLOW, "internal: %llu valid k-mers but %llu packed in records", ctx->h_ctr->kmers_valid, ctx->h_ctr->kmers_in_recs);
-    const u64 nrec = ctx->h_ctr->nrec, nkm = ctx->h_ctr->kmers_valid;
+    ctx->local_nrec = ctx->h_ctr->nrec; ctx->local_nkm = ctx->h_ctr->kmers_valid;
     ctx->st.nb_sequences = ctx->h_ss->nsep; ctx->st.nb_nucleotides = ctx->h_ss->nbase;
-    ctx->st.kmers_nb_valid = nkm; ctx->st.nb_superkmers = nrec; ctx->st.superkmer_bytes = nrec * (u64)ctx->RW * 8;
+    ctx->st.kmers_nb_valid = ctx->local_nkm; ctx->st.nb_superkmers = ctx->local_nrec;
+    ctx->st.superkmer_bytes = ctx->local_nrec * (u64)ctx->RW * 8;
+    ctx->totals_done = true;
+    return 0;
+}
 
-    // ---- partition plan: P partitions of ~ (table capacity / 4) k-mers each --------------------------------
+// number of partitions for `nkm` k-mers in the whole job: ~ a quarter of the hash table capacity per partition,
+// a multiple of the world size so that every rank owns the same number (owner(p) = p % world_size)
+static u32 choose_partitions(dskgpu_ctx* ctx, u64 nkm)
+{
     const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 23;
     const u64 target = std::max<u64>(((u64)1 << log2s) * 6 / 10 / 4, 4096);
-    u32 P = ctx->cfg.nb_partitions > 0 ? (u32)ctx->cfg.nb_partitions : (u32)std::min<u64>(4096, (nkm + target - 1) / target);
-    if (P < 1) P = 1;
-    if (P > 4096) P = 4096;
-    ctx->nparts = P; ctx->st.nb_partitions = P;
-    std::vector<u64> prec(P, 0), pkm(P, 0);
-    if (nrec) {
-        SpanGuard g(ctx, SPAN_PART);
-        if ((rc = ensure(ctx, ctx->part_recs, P * 8))) return rc;
-        if ((rc = ensure(ctx, ctx->part_kmers, P * 8))) return rc;
-        if ((rc = ensure(ctx, ctx->cursor, P * 8))) return rc;
-        if ((rc = ensure(ctx, ctx->dstbase, P * 8))) return rc;
-        CK(cudaMemsetAsync(ctx->part_recs.p, 0, P * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctx->part_kmers.p, 0, P * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctx->cursor.p, 0, P * 8, ctx->stream));
-        const unsigned hb = (unsigned)std::min<u64>((nrec + 2047) / 2048, 148 * 8);
-        k_part_hist<<<hb, 256, 2 * P * 4, ctx->stream>>>((const u32*)ctx->meta.p, nrec, P, (unsigned long long*)ctx->part_recs.p,
-                                                        (unsigned long long*)ctx->part_kmers.p); LAUNCHED();
-        CK(cudaMemcpyAsync(prec.data(), ctx->part_recs.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(pkm.data(), ctx->part_kmers.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if ((rc = ensure(ctx, ctx->precs, nrec * (u64)ctx->RW * 8 + 64))) return rc;
-        std::vector<u64*> dst(P);
-        u64 o = 0;
-        for (u32 i = 0; i < P; i++) { dst[i] = (u64*)ctx->precs.p + o * ctx->RW; o += prec[i]; }
-        CK(cudaMemcpyAsync(ctx->dstbase.p, dst.data(), P * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));      // dst is a stack vector
-        const unsigned sb = (unsigned)((nrec + SC_THREADS * SC_RPT - 1) / (SC_THREADS * SC_RPT));
-        const size_t smem = (size_t)((P + 1) & ~1u) * 4 + (size_t)P * 8;
-        k_part_scatter<KW><<<sb, SC_THREADS, smem, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, nrec, P,
-                                                                 (u64* const*)ctx->dstbase.p, (unsigned long long*)ctx->cursor.p); LAUNCHED();
-        CK(cudaGetLastError());
-    }
-    ctx->h_part_recs = prec; ctx->h_part_kmers = pkm;
+    const u32 W = (u32)ctx->cfg.world_size;
+    u64 P = ctx->cfg.nb_partitions > 0 ? (u64)ctx->cfg.nb_partitions : (nkm + target - 1) / target;
+    if (P < W) P = W;
+    P = (P + W - 1) / W * W;
+    const u32 PMAX = 4096 / W * W;
+    if (P > PMAX) P = PMAX;
+    return (u32)P;
+}
 
-    // ---- count -----------------------------------------------------------------------------------------------
-    if (nrec) { if ((rc = count_all<KW>(ctx, (const u64*)ctx->precs.p, prec, pkm, nkm))) return rc; }
+// ---- stage 2: records / k-mers of every partition among MY records -------------------------------------------------
+static int stage_part_hist(dskgpu_ctx* ctx, u32 P)
+{
+    int rc;
+    ctx->nparts = P; ctx->st.nb_partitions = P;
+    ctx->h_part_recs.assign(P, 0); ctx->h_part_kmers.assign(P, 0);
+    if ((rc = ensure(ctx, ctx->part_recs, P * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->part_kmers, P * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->cursor, P * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dstbase, P * 8))) return rc;
+    if (ctx->local_nrec == 0) return 0;
+    SpanGuard g(ctx, SPAN_PART);
+    CK(cudaMemsetAsync(ctx->part_recs.p, 0, P * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->part_kmers.p, 0, P * 8, ctx->stream));
+    const unsigned hb = (unsigned)std::min<u64>((ctx->local_nrec + 2047) / 2048, 148 * 8);
+    k_part_hist<<<hb, 256, 2 * P * 4, ctx->stream>>>((const u32*)ctx->meta.p, ctx->local_nrec, P, (unsigned long long*)ctx->part_recs.p,
+                                                    (unsigned long long*)ctx->part_kmers.p); LAUNCHED();
+    CK(cudaMemcpyAsync(ctx->h_part_recs.data(), ctx->part_recs.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_part_kmers.data(), ctx->part_kmers.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- stage 3: scatter my records to dst[p] (local partition array, or the owners' receive buffers over NVLink) ------
+template <int KW>
+static int stage_scatter(dskgpu_ctx* ctx, const std::vector<u64*>& dst)
+{
+    const u32 P = ctx->nparts;
+    if (ctx->local_nrec == 0) return 0;
+    SpanGuard g(ctx, SPAN_PART);
+    CK(cudaMemsetAsync(ctx->cursor.p, 0, P * 8, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dstbase.p, dst.data(), P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));          // dst may be a temporary
+    const unsigned sb = (unsigned)((ctx->local_nrec + SC_THREADS * SC_RPT - 1) / (SC_THREADS * SC_RPT));
+    const size_t smem = (size_t)((P + 1) & ~1u) * 4 + (size_t)P * 8;
+    k_part_scatter<KW><<<sb, SC_THREADS, smem, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, ctx->local_nrec, P,
+                                                             (u64* const*)ctx->dstbase.p, (unsigned long long*)ctx->cursor.p); LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- stage 4: count the partitions stored contiguously in `recs`, order the solid set, copy results out --------------
+template <int KW>
+static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm)
+{
+    Counters* ctr = (Counters*)ctx->ctr.p;
+    int rc;
+    u64 nrec = 0, nkm = 0;
+    for (size_t i = 0; i < prec.size(); i++) { nrec += prec[i]; nkm += pkm[i]; }
+    if (nrec) { if ((rc = count_all<KW>(ctx, recs, prec, pkm, nkm))) return rc; }
     CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_ctr->hash_overflow) FAIL(DSKGPU_ERR_OVERFLOW, "hash table overflow (distinct k-mer estimate too low)");
@@ -682,7 +716,7 @@ static int finish_impl(dskgpu_ctx* ctx)
     ctx->n_solid = ctx->h_ctr->solid_n;
     ctx->st.kmers_nb_distinct = ctx->h_ctr->distinct_n; ctx->st.kmers_nb_solid = ctx->n_solid;
 
-    // ---- order the solid set (ascending k-mer value, as the reference emits within a partition) ------------------
+    // order the solid set (ascending k-mer value, as the reference emits within a partition)
     ctx->solid_buf = 0;
     if (ctx->n_solid) {
         SpanGuard g(ctx, SPAN_SORT);
@@ -690,7 +724,7 @@ static int finish_impl(dskgpu_ctx* ctx)
         u32* vv[2] = {(u32*)ctx->svals[0].p, (u32*)ctx->svals[1].p};
         if ((rc = radix_sort<KW, true>(ctx, kk, vv, ctx->n_solid, (2 * ctx->k + 7) / 8, &ctx->solid_buf))) return rc;
     }
-    // ---- results to the host ---------------------------------------------------------------------------------------
+    // results to the host
     CK(cudaMemcpyAsync(ctx->h_hist, ctx->hist.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_hist + DSKGPU_HISTO_LEN, ctx->hist2d.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2,
                        cudaMemcpyDeviceToHost, ctx->stream));
@@ -716,13 +750,170 @@ static int finish_impl(dskgpu_ctx* ctx)
     return DSKGPU_OK;
 }
 
+template <int KW>
+static int finish_single(dskgpu_ctx* ctx)
+{
+    int rc;
+    if ((rc = stage_totals(ctx))) return rc;
+    const u32 P = choose_partitions(ctx, ctx->local_nkm);
+    if ((rc = stage_part_hist(ctx, P))) return rc;
+    if ((rc = ensure(ctx, ctx->precs, ctx->local_nrec * (u64)ctx->RW * 8 + 64))) return rc;
+    std::vector<u64*> dst(P);
+    u64 o = 0;
+    for (u32 i = 0; i < P; i++) { dst[i] = (u64*)ctx->precs.p + o * ctx->RW; o += ctx->h_part_recs[i]; }
+    if ((rc = stage_scatter<KW>(ctx, dst))) return rc;
+    return stage_count<KW>(ctx, (const u64*)ctx->precs.p, ctx->h_part_recs, ctx->h_part_kmers);
+}
+
+// multi-GPU: the partitions this rank owns sit in its receive buffer, in increasing partition id
+template <int KW>
+static int finish_owned(dskgpu_ctx* ctx)
+{
+    if (!ctx->xchg_scattered) FAIL(DSKGPU_ERR_STATE, "world_size > 1: run the dskgpu_xchg_* sequence before dskgpu_finish");
+    return stage_count<KW>(ctx, (const u64*)ctx->precs.p, ctx->owned_recs, ctx->owned_kmers);
+}
+
+// layout of rank `owner`'s receive buffer: owned partitions in increasing id, each split by sender rank.
+// all[r*2P + p] = records of partition p held by rank r, all[r*2P + P + p] = their k-mers.
+static void xchg_layout(u32 W, u32 P, const u64* all, u32 owner, u32 sender, std::vector<u64>& off_of_part /*[P] (only owned p filled)*/,
+                        std::vector<u64>* owned_recs, std::vector<u64>* owned_kmers, u64* total_recs)
+{
+    off_of_part.assign(P, 0);
+    if (owned_recs) owned_recs->clear();
+    if (owned_kmers) owned_kmers->clear();
+    u64 o = 0;
+    for (u32 p = owner; p < P; p += W) {
+        u64 before = 0, tot = 0, km = 0;
+        for (u32 r = 0; r < W; r++) { const u64 c = all[(u64)r * 2 * P + p]; if (r < sender) before += c; tot += c; km += all[(u64)r * 2 * P + P + p]; }
+        off_of_part[p] = o + before;
+        if (owned_recs) owned_recs->push_back(tot);
+        if (owned_kmers) owned_kmers->push_back(km);
+        o += tot;
+    }
+    if (total_recs) *total_recs = o;
+}
+
 extern "C" {
 
 int dskgpu_finish(dskgpu_ctx* ctx)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
     if (ctx->state != 0) FAIL(DSKGPU_ERR_STATE, "finish called twice");
-    return ctx->KW == 1 ? finish_impl<1>(ctx) : finish_impl<2>(ctx);
+    if (ctx->cfg.world_size > 1) return ctx->KW == 1 ? finish_owned<1>(ctx) : finish_owned<2>(ctx);
+    return ctx->KW == 1 ? finish_single<1>(ctx) : finish_single<2>(ctx);
+}
+
+// ---- multi-GPU exchange ----------------------------------------------------------------------------------------------
+int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    int rc = stage_totals(ctx); if (rc) return rc;
+    if (kmers) *kmers = ctx->local_nkm; if (records) *records = ctx->local_nrec;
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, uint64_t global_kmers, uint64_t* counts, uint32_t* nparts)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    int rc = stage_totals(ctx); if (rc) return rc;
+    const u32 P = choose_partitions(ctx, global_kmers);
+    if (nparts) *nparts = P;
+    if (!counts) return DSKGPU_OK;                                 // size query
+    if ((rc = stage_part_hist(ctx, P))) return rc;
+    for (u32 p = 0; p < P; p++) { counts[p] = ctx->h_part_recs[p]; counts[P + p] = ctx->h_part_kmers[p]; }
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts)
+{
+    if (!ctx || !all_counts) return DSKGPU_ERR_ARG;
+    if (ctx->nparts == 0) FAIL(DSKGPU_ERR_STATE, "xchg_plan before xchg_part_counts");
+    const u32 W = (u32)ctx->cfg.world_size, P = ctx->nparts;
+    ctx->xchg_matrix.assign(all_counts, all_counts + (size_t)W * 2 * P);
+    std::vector<u64> off; u64 tot = 0;
+    xchg_layout(W, P, all_counts, (u32)ctx->cfg.rank, 0, off, &ctx->owned_recs, &ctx->owned_kmers, &tot);
+    ctx->my_nrec_owned = tot;
+    int rc = ensure(ctx, ctx->precs, tot * (u64)ctx->RW * 8 + 64); if (rc) return rc;
+    ctx->xchg_planned = true;
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    if (!ctx->xchg_planned) FAIL(DSKGPU_ERR_STATE, "xchg_recv_buffer before xchg_plan");
+    if (d_recv) *d_recv = ctx->precs.p; if (bytes) *bytes = (size_t)(ctx->my_nrec_owned * (u64)ctx->RW * 8);
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_ipc_handle(dskgpu_ctx* ctx, void* handle64)
+{
+    if (!ctx || !handle64) return DSKGPU_ERR_ARG;
+    if (!ctx->xchg_planned) FAIL(DSKGPU_ERR_STATE, "xchg_ipc_handle before xchg_plan");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->precs.p));
+    memcpy(handle64, &h, 64);
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_open_peer(dskgpu_ctx* ctx, const void* handle64, void** d_ptr)
+{
+    if (!ctx || !handle64 || !d_ptr) return DSKGPU_ERR_ARG;
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ipc_opened.push_back(*d_ptr);
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv)
+{
+    if (!ctx || !d_peer_recv) return DSKGPU_ERR_ARG;
+    ctx->peer_recv.assign(d_peer_recv, d_peer_recv + ctx->cfg.world_size);
+    ctx->peer_recv[ctx->cfg.rank] = ctx->precs.p;
+    return DSKGPU_OK;
+}
+
+// fused partition scatter + all-to-all: every record is stored straight into its owner's receive buffer
+// (peer pointers: NVLink P2P stores), at offsets every rank derives from the all-gathered count matrix
+int dskgpu_xchg_scatter(dskgpu_ctx* ctx)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    if (!ctx->xchg_planned || ctx->peer_recv.size() != (size_t)ctx->cfg.world_size) FAIL(DSKGPU_ERR_STATE, "xchg_scatter before xchg_plan / xchg_set_peers");
+    const u32 W = (u32)ctx->cfg.world_size, P = ctx->nparts, me = (u32)ctx->cfg.rank;
+    std::vector<u64*> dst(P, nullptr);
+    std::vector<u64> off;
+    for (u32 o = 0; o < W; o++) {
+        xchg_layout(W, P, ctx->xchg_matrix.data(), o, me, off, nullptr, nullptr, nullptr);
+        for (u32 p = o; p < P; p += W) dst[p] = (u64*)ctx->peer_recv[o] + off[p] * ctx->RW;
+    }
+    int rc = ctx->KW == 1 ? stage_scatter<1>(ctx, dst) : stage_scatter<2>(ctx, dst);
+    if (rc) return rc;
+    ctx->xchg_scattered = true;
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_sync(dskgpu_ctx* ctx)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSKGPU_OK;
+}
+
+// host-only: where sender `sender`'s records of every partition land in their owners' receive buffers
+// (offsets in records; used by the exchange itself and by the CPU test-suite)
+int dskgpu_xchg_layout(int world_size, uint32_t nparts, const uint64_t* all_counts, int sender, uint64_t* offsets /*[nparts]*/,
+                       uint64_t* recv_records /*[world_size]*/)
+{
+    if (world_size < 1 || !all_counts || !offsets) return DSKGPU_ERR_ARG;
+    std::vector<u64> off;
+    for (u32 o = 0; o < (u32)world_size; o++) {
+        u64 tot = 0;
+        xchg_layout((u32)world_size, nparts, all_counts, o, (u32)sender, off, nullptr, nullptr, &tot);
+        for (u32 p = o; p < nparts; p += (u32)world_size) offsets[p] = off[p];
+        if (recv_records) recv_records[o] = tot;
+    }
+    return DSKGPU_OK;
 }
 
 int dskgpu_num_partitions(dskgpu_ctx* ctx) { if (!ctx || ctx->state != 1) return DSKGPU_ERR_STATE; return 1; }
@@ -764,14 +955,6 @@ int dskgpu_get_stats(dskgpu_ctx* ctx, dskgpu_stats* out)
 }
 
 int dskgpu_record_bytes(dskgpu_ctx* ctx) { return ctx ? ctx->RW * 8 : DSKGPU_ERR_ARG; }
-
-// multi-GPU exchange: implemented in a later section of this file
-int dskgpu_xchg_counts(dskgpu_ctx* ctx, uint64_t*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
-int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
-int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void**, size_t*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
-int dskgpu_xchg_send_buffer(dskgpu_ctx* ctx, void**, size_t*, uint64_t*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
-int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const*) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
-int dskgpu_xchg_scatter(dskgpu_ctx* ctx) { FAIL(DSKGPU_ERR_STATE, "multi-GPU exchange not available in this build"); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host self checks (same functions the kernels run; no GPU needed)

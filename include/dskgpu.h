@@ -154,16 +154,27 @@ int  dskgpu_device_count(void);
 int  dskgpu_abi_version(void);
 
 /* ---- multi-GPU exchange (replaces the SuperKmerBinFiles temp tier, Storage.cpp:310-589) --------------
- * After all pushes every rank calls xchg_counts (local per-destination record counts), all-gathers them
- * out of band (torch.distributed / NCCL), and hands the matrix back to xchg_plan.  Each rank then exposes
- * its receive buffer; with peer pointers set (CUDA IPC) the partition scatter writes straight into the
- * owners' HBM over NVLink, otherwise ranks exchange the packed send buffer with an NCCL all-to-all. */
-int dskgpu_xchg_counts(dskgpu_ctx* ctx, uint64_t* send_counts /*[world_size]*/);
-int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts /*[world_size*world_size], row = sender*/);
+ * One context per rank (one process per GPU).  Partition p is owned by rank p % world_size.  After all pushes:
+ *   1. xchg_local_totals        -> all-reduce the k-mer totals out of band (torch.distributed / NCCL)
+ *   2. xchg_part_counts         -> per-partition record / k-mer counts of this rank; all-gather them
+ *   3. xchg_plan                -> every rank derives every receive-buffer layout from the gathered matrix and
+ *                                  allocates its own receive buffer (xchg_recv_buffer / xchg_ipc_handle expose it)
+ *   4. xchg_set_peers + xchg_scatter -> ONE kernel scatters this rank's super-k-mer records straight into the
+ *                                  owners' HBM (peer pointers from CUDA IPC: NVLink P2P stores) - the partition
+ *                                  scatter and the all-to-all are the same kernel, there is no send staging
+ *   5. xchg_sync, barrier out of band, then dskgpu_finish counts the owned partitions locally. */
+int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records);
+/* counts[0..P) = records, counts[P..2P) = k-mers of each partition on this rank; pass counts = NULL to query P */
+int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, uint64_t global_kmers, uint64_t* counts, uint32_t* nparts);
+int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts /*[world_size][2*P], row = rank*/);
 int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes);
-int dskgpu_xchg_send_buffer(dskgpu_ctx* ctx, void** d_send, size_t* bytes, uint64_t* send_offsets /*[world_size+1] in records*/);
-int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv /*[world_size]*/);
+int dskgpu_xchg_ipc_handle(dskgpu_ctx* ctx, void* handle64 /*cudaIpcMemHandle_t of the receive buffer*/);
+int dskgpu_xchg_open_peer(dskgpu_ctx* ctx, const void* handle64, void** d_ptr);
+int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv /*[world_size]; own entry ignored*/);
 int dskgpu_xchg_scatter(dskgpu_ctx* ctx);
+int dskgpu_xchg_sync(dskgpu_ctx* ctx);
+/* host-only layout helper: offsets[p] = first record slot of `sender` for partition p inside owner(p)'s buffer */
+int dskgpu_xchg_layout(int world_size, uint32_t nparts, const uint64_t* all_counts, int sender, uint64_t* offsets, uint64_t* recv_records);
 int dskgpu_record_bytes(dskgpu_ctx* ctx);
 
 /* ---- host-side self checks of the device bit logic (no GPU needed; used by the CPU test-suite) ------- */

@@ -233,3 +233,52 @@ def test_full_size_properties(k):
         assert ((keys[1:, 1] > keys[:-1, 1]) | ((keys[1:, 1] == keys[:-1, 1]) & (keys[1:, 0] > keys[:-1, 0]))).all()
     if k == 31:   # SURVEY.md 6.2 [measured with the reference]: 103 530 226 distinct / 12 960 855 solid for seed 42 -- different generator, same shape
         assert 0.9e8 < st["kmers_nb_distinct"] < 1.2e8
+
+
+def split_records(data, parts):
+    """cut a FASTA image into `parts` slices at record boundaries"""
+    cuts = [0]
+    for i in range(1, parts):
+        j = data.find(b"\n>", len(data) * i // parts)
+        cuts.append(len(data) if j < 0 else j + 1)
+    cuts.append(len(data))
+    return [data[cuts[i]:cuts[i + 1]] for i in range(parts)]
+
+
+@pytest.mark.parametrize("W,k,mode", [(2, 31, "auto"), (3, 31, "hash"), (2, 63, "auto"), (4, 31, "sort")])
+def test_multi_rank_exchange_in_process(W, k, mode):
+    """N ranks as N contexts on one GPU: every rank parses a slice, the scatter kernel routes records to the owner
+    of their partition (p % W), every rank counts only what it owns.  Union of the ranks' outputs == oracle."""
+    from dsk_b200.distributed import in_process_finish
+    buf, n, _ = reads_fasta(G=400_000, coverage=30, L=150, err=0.01, seed=77)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], k, abundance_min=2)
+    engines = [GpuCounter(kmer_size=k, abundance_min=2, rank=r, world_size=W, count_mode=mode, hash_log2_slots=16) for r in range(W)]
+    try:
+        for e, piece in zip(engines, split_records(data, W)):
+            e.push_bytes(piece)
+        allc = in_process_finish(engines)
+        P = allc.shape[1] // 2
+        assert P % W == 0 and P >= W
+        keys, cnts, hist, valid, distinct = [], [], np.zeros(10001, np.uint64), 0, 0
+        for r, e in enumerate(engines):
+            kk, cc = e.solid()
+            if kk.shape[1] == 1:
+                assert (kk[1:, 0] > kk[:-1, 0]).all()
+            keys.append(kk); cnts.append(cc)
+            hist += e.histogram()[0]
+            st = e.stats()
+            valid += st["kmers_nb_valid"]; distinct += st["kmers_nb_distinct"]
+            assert st["nb_partitions"] == P
+        keys = np.concatenate(keys); cnts = np.concatenate(cnts)
+        order = np.lexsort((keys[:, 0], keys[:, -1])) if keys.shape[1] == 2 else np.argsort(keys[:, 0], kind="stable")
+        keys, cnts = keys[order], cnts[order]
+        lo, hi, rc = ref.solid_kmers()
+        assert valid == ref.kmers_nb_valid and distinct == ref.nb_distinct
+        assert len(cnts) == len(rc) and (keys[:, 0] == lo).all() and (cnts.astype(np.int64) == rc).all()
+        if keys.shape[1] == 2:
+            assert (keys[:, 1] == hi).all()
+        assert (hist == ref.hist).all()
+    finally:
+        for e in engines:
+            e.close()
