@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# Builds host/_build/dsk_gpu: the reference `dsk` command line with the counting class replaced by the device path.
+# Needs the reference tree (headers) and the out-of-tree reference build that oracle/build_ref.sh makes
+# (libgatbcore.a, libhdf5.a, generated config headers).  The binary is static against those and dynamic against
+# dsk_b200/libdskgpu.so (rpath $ORIGIN/../../dsk_b200), so it travels to the GPU box with the snapshot.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(dirname "$HERE")"
+REF="${REF:-/root/reference}"
+B="${REF_BUILD:-${TMPDIR:-/tmp}/dsk_ref_build}"
+OUT="$HERE/_build"
+if [ ! -d "$REF" ]; then echo "no reference tree at $REF (GPU box uses the prebuilt host/_build/dsk_gpu)"; exit 0; fi
+if [ ! -f "$B/ext/gatb-core/lib/Release/libgatbcore.a" ]; then
+  rm -rf "$ROOT/oracle/_ref/bin/dsk"; "$ROOT/oracle/build_ref.sh" "$REF"
+fi
+G="$REF/thirdparty/gatb-core/gatb-core"
+mkdir -p "$OUT"
+if [ -x "$OUT/dsk_gpu" ] && [ "$OUT/dsk_gpu" -nt "$HERE/GpuSortingCount.hpp" ] && [ "$OUT/dsk_gpu" -nt "$HERE/dsk_gpu_main.cpp" ] \
+   && [ "$OUT/dsk_gpu" -nt "$ROOT/include/dskgpu.h" ]; then echo "host/_build/dsk_gpu up to date"; exit 0; fi
+g++ -std=c++11 -O2 -DNDEBUG -D_FILE_OFFSET_BITS=64 -D_GNU_SOURCE -D_LARGEFILE64_SOURCE -D_LARGEFILE_SOURCE -DINT128_FOUND \
+    -include cstdint -Wno-invalid-offsetof -Wno-format -Wno-unknown-pragmas \
+    -I"$B/ext/gatb-core/include" -I"$B/ext/gatb-core/include/Release" -I"$G/src" -I"$G/thirdparty" \
+    -I"$B/ext/gatb-core/thirdparty/hdf5/src" -I"$G/thirdparty/hdf5/src" \
+    "$HERE/dsk_gpu_main.cpp" -o "$OUT/dsk_gpu" \
+    -L"$B/ext/gatb-core/lib/Release" -lgatbcore -lhdf5 -L"$ROOT/dsk_b200" -ldskgpu \
+    -Wl,-rpath,'$ORIGIN/../../dsk_b200' -ldl -lpthread -lz
+echo "built $OUT/dsk_gpu"

@@ -1,0 +1,129 @@
+"""Drop-in test of the C++ host side (-m gpu): `host/_build/dsk_gpu` is the reference `dsk` command line with the counting
+class replaced by the device path (host/GpuSortingCount.hpp over include/dskgpu.h).  Its HDF5 output is read back by the
+UNMODIFIED reference readers `dsk2ascii` and `gatb-h5dump` (oracle/_ref/bin, the checker) and compared with
+  * the committed outputs of the real reference (tests/golden/ref_runs.json), and
+  * the reference `dsk` binary run side by side on the same input, when it is available on the box.
+This is the shape of the reference's own end-to-end tests (R/scripts/simple_test.sh:35-135)."""
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+from util import load_json, INPUTS, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DSK_GPU = os.path.join(ROOT, "host", "_build", "dsk_gpu")
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+RUNS = load_json("ref_runs.json")["runs"]
+SHELL = load_json("ref_shell_tests.json")["tests"]
+
+need_bins = pytest.mark.skipif(not (os.path.exists(DSK_GPU) and os.path.exists(os.path.join(REFBIN, "dsk2ascii"))),
+                               reason="host/_build/dsk_gpu or oracle/_ref/bin readers not built (python __graft_entry__.py)")
+
+
+def run(cmd, cwd):
+    p = subprocess.run(cmd, cwd=cwd, capture_output=True, text=True)
+    assert p.returncode == 0, "%s\n%s\n%s" % (" ".join(cmd), p.stdout[-2000:], p.stderr[-2000:])
+    return p.stdout
+
+
+def dsk_args(t, out):
+    a = ["-file", ",".join(os.path.join(INPUTS, f) for f in t["files"]), "-kmer-size", str(t["k"]), "-abundance-min", str(t["abundance_min"]),
+         "-out", out, "-histo", "1", "-verbose", "0"]
+    if t.get("histo2d"):
+        a += ["-histo2D", "1"]
+    if t.get("solidity_kind"):
+        a += ["-solidity-kind", t["solidity_kind"]]
+    if t.get("abundance_max") is not None:
+        a += ["-abundance-max", str(t["abundance_max"])]
+    return a
+
+
+def read_back(h5, tmp):
+    """what the reference's readers see in an output file"""
+    txt = os.path.join(tmp, os.path.basename(h5) + ".txt")
+    run([os.path.join(REFBIN, "dsk2ascii"), "-file", h5, "-out", txt, "-verbose", "0"], tmp)
+    lines = sorted(open(txt, "rb").read().splitlines())
+    histo = run([os.path.join(REFBIN, "gatb-h5dump"), "-y", "-d", "histogram/histogram", h5], tmp)
+    histo = "\n".join(ln for ln in histo.splitlines() if not ln.startswith("HDF5 "))      # first line names the file
+    header = run([os.path.join(REFBIN, "gatb-h5dump"), "-H", h5], tmp)
+    return lines, histo, header
+
+
+CLI_RUNS = [t for t in RUNS if t["name"] in ("c1_k31", "c1_k63", "c1_k31_min3_max20", "c1234_k31", "longread_k63", "reads.fastq_k31", "multiline.fasta_k31",
+                                            "weird.fasta_k31", "histo2d_k31", "histo2d_c123_k31", "c123_k31_min", "c123_k31_one", "c123_k31_all")]
+
+
+@need_bins
+@pytest.mark.parametrize("t", CLI_RUNS, ids=[t["name"] for t in CLI_RUNS])
+def test_cli_against_committed_reference_outputs(t, tmp_path):
+    tmp = str(tmp_path)
+    out = os.path.join(tmp, "gpu_out")
+    run([DSK_GPU] + dsk_args(t, out), tmp)
+    lines, histo, header = read_back(out + ".h5", tmp)
+    assert len(lines) == t["nb_solid"]
+    m = hashlib.sha256()
+    for ln in lines:
+        m.update(ln + b"\n")
+    assert m.hexdigest() == t["kmers_sha256"]
+    # <out>.histo text: 10000 lines "i\tcount" (CountProcessorHistogram.hpp:111-142)
+    rows = open(out + ".histo").read().splitlines()
+    assert len(rows) == 10000
+    got = {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])}
+    assert got == t["hist"]
+    # layout names the readers rely on
+    for name in ('GROUP "dsk"', 'GROUP "solid"', 'DATASET "0"', 'GROUP "histogram"', 'DATASET "histogram"', 'DATASET "cutoff"',
+                 'DATASET "nbsolidsforcutoff"', 'GROUP "minimizers"', 'DATASET "minimRepart"', 'GROUP "configuration"',
+                 'ATTRIBUTE "kmer_size"', 'ATTRIBUTE "nb_partitions"', 'ATTRIBUTE "xml"'):
+        assert name in header, name
+    if t.get("histo2d"):
+        assert len(open(out + ".histo2D").read().splitlines()) == 10001
+
+
+@need_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFBIN, "dsk")), reason="reference dsk binary not on this box")
+@pytest.mark.parametrize("name", ["c1_k31", "c1_k63", "histo2d_c123_k31", "reads.fastq_k31"])
+def test_cli_side_by_side_with_reference_binary(name, tmp_path):
+    t = [r for r in RUNS if r["name"] == name][0]
+    tmp = str(tmp_path)
+    a, b = os.path.join(tmp, "gpu_out"), os.path.join(tmp, "ref_out")
+    run([DSK_GPU] + dsk_args(t, a), tmp)
+    run([os.path.join(REFBIN, "dsk")] + dsk_args(t, b) + ["-out-tmp", tmp], tmp)
+    la, ha, hda = read_back(a + ".h5", tmp)
+    lb, hb, hdb = read_back(b + ".h5", tmp)
+    assert la == lb                                          # dsk2ascii | sort
+    assert ha == hb                                          # gatb-h5dump -y -d histogram/histogram
+    assert open(a + ".histo", "rb").read() == open(b + ".histo", "rb").read()
+    if t.get("histo2d"):
+        assert open(a + ".histo2D", "rb").read() == open(b + ".histo2D", "rb").read()
+    # same dataset types: the compound {value, abundance} of dsk/solid/0 and {index, abundance} of the histogram
+
+    def types(h):
+        return sorted(set(ln.strip() for ln in h.splitlines() if "H5T_" in ln))
+    assert types(hda) == types(hdb)
+
+
+@need_bins
+def test_cli_shell_goldens(tmp_path):
+    """R/scripts/simple_test.sh: histogram dumps and dsk2ascii text"""
+    tmp = str(tmp_path)
+    for t in SHELL:
+        out = os.path.join(tmp, "o_" + t["name"])
+        run([DSK_GPU] + dsk_args(t, out), tmp)
+        if "dsk2ascii" in t:
+            txt = out + ".txt"
+            run([os.path.join(REFBIN, "dsk2ascii"), "-file", out + ".h5", "-out", txt, "-verbose", "0"], tmp)
+            assert open(txt).read() == t["dsk2ascii"]
+        if "hist" in t:
+            rows = open(out + ".histo").read().splitlines()
+            assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]
+
+
+@need_bins
+def test_cli_unhandled_kmer_size(tmp_path):
+    p = subprocess.run([DSK_GPU, "-file", os.path.join(INPUTS, "shortread.fasta"), "-kmer-size", "64", "-out", str(tmp_path / "x")],
+                       cwd=str(tmp_path), capture_output=True, text=True)
+    assert p.returncode != 0 and "unhandled kmer size 64" in (p.stdout + p.stderr)
