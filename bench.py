@@ -334,7 +334,7 @@ def main():
             "clocks": clocks,
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_hash_insert" if st["nb_groups_hash"] else "k_rs_onesweep", "launches": int(dom_n), "avg_launch_ms": 1e3 * dom_avg_s,
+                         "kernel": "k_count_smem" if st["nb_parts_smem"] else ("k_hash_insert" if st["nb_groups_hash"] else "k_rs_onesweep"), "launches": int(dom_n), "avg_launch_ms": 1e3 * dom_avg_s,
                          "peak_source": peak_src, "algorithmic_bytes_per_kmer": ab["S2_expand"] + ab["S3_sort"]},
             "pipeline_roofline": {"A_k_bytes_per_kmer": A, "achieved": value / world * A, "peak": peak, "unit": "GB/s", "frac": value / world * A / peak,
                                   "note": "whole step per GPU against SURVEY 8(d) A(k); the hash path moves fewer HBM bytes than A(k) assumes"},

@@ -4,11 +4,12 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(PKG, "libdskgpu.so")
+SO = os.environ.get("DSKGPU_LIB") or os.path.join(PKG, "libdskgpu.so")      # DSKGPU_LIB: tuning builds under variants/
 
 MAX_BANKS = 16
 HISTO_LEN = 10001
 HISTO2D_DIM2 = 11
+NBINS = 131072
 
 ERR_NODEVICE = -6
 
@@ -21,7 +22,7 @@ class Config(C.Structure):
         ("solid_vec", C.c_uint8 * MAX_BANKS),
         ("histo2d", C.c_int32), ("device", C.c_int32), ("count_mode", C.c_int32), ("hash_log2_slots", C.c_int32),
         ("nb_partitions", C.c_int32), ("keep_results_on_device", C.c_int32),
-        ("stream", C.c_void_p), ("rank", C.c_int32), ("world_size", C.c_int32), ("push_chunk_bytes", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("stream", C.c_void_p), ("rank", C.c_int32), ("world_size", C.c_int32), ("push_chunk_bytes", C.c_int32), ("smem_table_slots", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -33,7 +34,8 @@ class Stats(C.Structure):
         ("superkmer_bytes", C.c_uint64), ("gpu_launches", C.c_uint64),
         ("ms_parse", C.c_float), ("ms_superk", C.c_float), ("ms_partition", C.c_float), ("ms_count", C.c_float),
         ("ms_sort", C.c_float), ("ms_total", C.c_float), ("ms_dominant_kernel", C.c_float),
-        ("dominant_kernel_launches", C.c_uint32), ("reserved", C.c_uint32 * 7),
+        ("dominant_kernel_launches", C.c_uint32), ("nb_parts_smem", C.c_uint32), ("nb_smem_splits", C.c_uint32),
+        ("smem_table_slots", C.c_uint32), ("reserved", C.c_uint32 * 4),
     ]
 
     def as_dict(self):
@@ -46,7 +48,7 @@ SYMBOLS = [
     "dskgpu_finish", "dskgpu_num_partitions", "dskgpu_partition", "dskgpu_partition_device", "dskgpu_histogram",
     "dskgpu_get_stats", "dskgpu_reset", "dskgpu_destroy", "dskgpu_host_alloc", "dskgpu_host_free", "dskgpu_strerror",
     "dskgpu_last_error", "dskgpu_device_count", "dskgpu_abi_version",
-    "dskgpu_xchg_local_totals", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
+    "dskgpu_xchg_local_totals", "dskgpu_xchg_bin_hist", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
     "dskgpu_xchg_open_peer", "dskgpu_xchg_set_peers", "dskgpu_xchg_scatter", "dskgpu_xchg_sync", "dskgpu_xchg_layout", "dskgpu_record_bytes",
     "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers",
 ]
@@ -88,7 +90,8 @@ def lib():
     L.dskgpu_last_error.argtypes = [C.c_void_p]
     L.dskgpu_last_error.restype = C.c_char_p
     L.dskgpu_xchg_local_totals.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
-    L.dskgpu_xchg_part_counts.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, P(C.c_uint32)]
+    L.dskgpu_xchg_bin_hist.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg_part_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_uint32)]
     L.dskgpu_xchg_plan.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_recv_buffer.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_size_t)]
     L.dskgpu_xchg_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]

@@ -7,7 +7,7 @@ from . import _lib
 
 FMT = {"auto": 0, "fasta": 1, "fastq": 2, "lines": 3}
 SOLIDITY = {"sum": 0, "min": 1, "max": 2, "one": 3, "all": 4, "custom": 5}
-COUNT_MODE = {"auto": 0, "sort": 1, "vector": 1, "hash": 2}
+COUNT_MODE = {"auto": 0, "sort": 1, "vector": 1, "hash": 2, "smem": 3}
 
 
 class DskGpuError(RuntimeError):
@@ -21,7 +21,8 @@ class GpuCounter:
 
     def __init__(self, kmer_size=31, abundance_min=2, abundance_max=2**31 - 1, nb_banks=1, per_bank_counts=False,
                  solidity_kind="sum", solid_vec=None, histo2d=False, minimizer_size=10, device=0, count_mode="auto",
-                 hash_log2_slots=0, nb_partitions=0, keep_results_on_device=False, stream=None, rank=0, world_size=1, push_chunk_bytes=0):
+                 hash_log2_slots=0, nb_partitions=0, keep_results_on_device=False, stream=None, rank=0, world_size=1, push_chunk_bytes=0,
+                 smem_table_slots=0):
         self.L = _lib.lib()
         cfg = _lib.Config()
         self.L.dskgpu_config_default(C.byref(cfg))
@@ -47,6 +48,7 @@ class GpuCounter:
         cfg.stream = stream
         cfg.rank, cfg.world_size = rank, world_size
         cfg.push_chunk_bytes = push_chunk_bytes
+        cfg.smem_table_slots = smem_table_slots
         self.cfg = cfg
         self.k = kmer_size
         self.h = C.c_void_p()
@@ -149,11 +151,17 @@ def _xchg_methods():
         self._check(self.L.dskgpu_xchg_local_totals(self.h, C.byref(km), C.byref(nr)))
         return km.value, nr.value
 
-    def xchg_part_counts(self, global_kmers):
+    def xchg_bin_hist(self):
+        h = np.zeros(2 * _lib.NBINS, dtype=np.uint64)
+        self._check(self.L.dskgpu_xchg_bin_hist(self.h, h.ctypes.data))
+        return h
+
+    def xchg_part_counts(self, global_hist):
+        gh = np.ascontiguousarray(global_hist, dtype=np.uint64)
         P = C.c_uint32()
-        self._check(self.L.dskgpu_xchg_part_counts(self.h, global_kmers, None, C.byref(P)))
+        self._check(self.L.dskgpu_xchg_part_counts(self.h, gh.ctypes.data, None, C.byref(P)))
         counts = np.zeros(2 * P.value, dtype=np.uint64)
-        self._check(self.L.dskgpu_xchg_part_counts(self.h, global_kmers, counts.ctypes.data, C.byref(P)))
+        self._check(self.L.dskgpu_xchg_part_counts(self.h, gh.ctypes.data, counts.ctypes.data, C.byref(P)))
         return counts
 
     def xchg_plan(self, all_counts):
@@ -186,7 +194,7 @@ def _xchg_methods():
     def xchg_sync(self):
         self._check(self.L.dskgpu_xchg_sync(self.h))
 
-    for f in (xchg_local_totals, xchg_part_counts, xchg_plan, xchg_recv_buffer, xchg_ipc_handle, xchg_open_peer, xchg_set_peers,
+    for f in (xchg_local_totals, xchg_bin_hist, xchg_part_counts, xchg_plan, xchg_recv_buffer, xchg_ipc_handle, xchg_open_peer, xchg_set_peers,
               xchg_scatter, xchg_sync):
         setattr(GpuCounter, f.__name__, f)
 

@@ -20,6 +20,7 @@
 #include "scan.cuh"
 #include "superk.cuh"
 #include "count.cuh"
+#include "count_smem.cuh"
 #include "radix.cuh"
 
 using namespace dsk;
@@ -42,7 +43,7 @@ struct dskgpu_ctx {
     DevBuf ss, ctr, hist, hist2d, raw[2], codes, tabs, tin;
     DevBuf recs, meta;                               // staging records (input order)
     DevBuf precs;                                    // partitioned records
-    DevBuf part_recs, part_kmers, cursor, dstbase, gflags;
+    DevBuf cursor, dstbase, bin_hist, bin2part, jobs, work_ctr;
     DevBuf tkeys, tcounts;                           // hash table
     DevBuf skeys[2], svals[2];                       // solid (k-mer, abundance) ping-pong
     DevBuf keys[2], banks[2];                        // sort path ping-pong
@@ -59,8 +60,12 @@ struct dskgpu_ctx {
     size_t push_chunk = (size_t)64 << 20;
     // results
     u64 n_solid = 0; int solid_buf = 0; bool results_on_host = false;
-    std::vector<u64> h_part_recs, h_part_kmers;
+    std::vector<u64> h_part_recs, h_part_kmers;      // this rank's records / k-mers of every partition
+    std::vector<u64> g_part_kmers;                   // whole-job k-mers of every partition
+    std::vector<u32> h_bin2part;
+    unsigned long long* h_bin_hist = nullptr;        // pinned [2][NBINS]
     u32 nparts = 0;
+    u32 smem_cap = 0; int num_sms = 148;
     // multi-GPU
     std::vector<u64> xchg_matrix; std::vector<void*> peer_recv; bool xchg_planned = false; bool xchg_scattered = false;
     u64 my_nrec_owned = 0; std::vector<u64> owned_recs, owned_kmers;   // my partitions in my receive buffer (increasing id)
@@ -174,7 +179,10 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     CK(cudaMallocHost((void**)&ctx->h_ss, sizeof(StreamState)));
     CK(cudaMallocHost((void**)&ctx->h_nrec_probe, 64));
     CK(cudaMallocHost((void**)&ctx->h_hist, sizeof(unsigned long long) * (DSKGPU_HISTO_LEN * (1 + DSKGPU_HISTO2D_DIM2))));
+    CK(cudaMallocHost((void**)&ctx->h_bin_hist, sizeof(unsigned long long) * 2 * NBINS));
     int rc;
+    if ((rc = ensure(ctx, ctx->bin_hist, sizeof(unsigned long long) * 2 * NBINS))) return rc;
+    if ((rc = ensure(ctx, ctx->work_ctr, 64))) return rc;
     if ((rc = ensure(ctx, ctx->ss, sizeof(StreamState)))) return rc;
     if ((rc = ensure(ctx, ctx->ctr, sizeof(Counters)))) return rc;
     if ((rc = ensure(ctx, ctx->hist, sizeof(unsigned long long) * DSKGPU_HISTO_LEN))) return rc;
@@ -185,6 +193,29 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     CK(cudaFuncSetAttribute(k_rs_onesweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CK(cudaFuncSetAttribute(k_rs_onesweep<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
     CK(cudaFuncSetAttribute(k_rs_onesweep<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    // shared-memory counting path: CS_CTAS_PER_SM CTAs share the SM's shared memory; each table takes what is left of its share
+    {
+        int max_optin = 0, per_sm = 0, nsm = 0, reserved = 0;
+        CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+        CK(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
+        CK(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, cfg->device));
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device));
+        ctx->num_sms = nsm > 0 ? nsm : 148;
+        cudaFuncAttributes fa;
+        if (ctx->KW == 1) CK(cudaFuncGetAttributes(&fa, k_count_smem<1>)); else CK(cudaFuncGetAttributes(&fa, k_count_smem<2>));
+        size_t avail = std::min<size_t>((size_t)max_optin, (size_t)per_sm / CS_CTAS_PER_SM - (size_t)reserved) - fa.sharedSizeBytes;
+        const size_t fixed = ctx->KW == 1 ? cs_smem_bytes<1>(0) : cs_smem_bytes<2>(0);
+        u32 cap = avail > fixed ? (u32)((avail - fixed) / (size_t)(8 * ctx->KW + 4)) : 0;
+        cap = cap / 1024 * 1024;
+        if (cap > 16384u) cap = 16384u;                            // the sweep keeps one solid bit per slot of a thread in 32 bits
+        if (cfg->smem_table_slots > 0) cap = std::min<u32>(cap, std::max<u32>(64u, (u32)cfg->smem_table_slots / 4 * 4));
+        ctx->smem_cap = cap;
+        const size_t dyn = ctx->KW == 1 ? cs_smem_bytes<1>(cap) : cs_smem_bytes<2>(cap);
+        if (ctx->KW == 1) { CK(cudaFuncSetAttribute(k_count_smem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                            CK(cudaFuncSetAttribute(k_count_smem<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); }
+        else { CK(cudaFuncSetAttribute(k_count_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+               CK(cudaFuncSetAttribute(k_count_smem<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); }
+    }
     *out = ctx;
     int r = dskgpu_reset(ctx);
     if (r) { *out = nullptr; return r; }
@@ -199,6 +230,7 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     CK(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
     CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
     CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
+    CK(cudaMemsetAsync(ctx->bin_hist.p, 0, sizeof(unsigned long long) * 2 * NBINS, ctx->stream));
     ctx->state = 0; ctx->cur_bank = -1; ctx->stream_open = false; ctx->pending_cr = 0;
     ctx->nrec_known = 0; ctx->k2_inflight = false; ctx->chunk_parity = 0;
     ctx->n_solid = 0; ctx->results_on_host = false; ctx->nparts = 0;
@@ -215,7 +247,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
-                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->part_recs, &ctx->part_kmers, &ctx->cursor, &ctx->dstbase, &ctx->gflags,
+                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->dstbase, &ctx->bin_hist, &ctx->bin2part, &ctx->jobs, &ctx->work_ctr,
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
                      &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr, &ctx->sendbuf};
     for (DevBuf* b : all) b->release();
@@ -227,6 +259,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (ctx->h_ss) cudaFreeHost(ctx->h_ss);
     if (ctx->h_nrec_probe) cudaFreeHost(ctx->h_nrec_probe);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
+    if (ctx->h_bin_hist) cudaFreeHost(ctx->h_bin_hist);
     if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
     if (ctx->h_svals) cudaFreeHost(ctx->h_svals);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -295,8 +328,8 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
         SpanGuard g(ctx, SPAN_SUPERK);
         const unsigned gk = (unsigned)((n + 64 + SK_TP - 1) / SK_TP);
         const int bank = ctx->NB > 1 ? ctx->cur_bank : 0;
-        if (ctx->KW == 1) k_superkmers<1><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p);
-        else              k_superkmers<2><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p);
+        if (ctx->KW == 1) k_superkmers<1><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p);
+        else              k_superkmers<2><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p);
         LAUNCHED();
         k_scan_carry<<<1, 64, 0, ctx->stream>>>((u8*)ctx->codes.p, ss, ctx->k); LAUNCHED();
     }
@@ -511,7 +544,7 @@ static int count_by_sort(dskgpu_ctx* ctx, const u64* recs, u64 rb, u64 re, u64 n
 }
 
 template <int KW>
-static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm, u64 total_kmers)
+static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm, u64 out_cap)
 {
     // prec/pkm: records / k-mers of each partition, stored contiguously in `recs` in this order
     const size_t np = prec.size();
@@ -520,15 +553,6 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
     Counters* ctr = (Counters*)ctx->ctr.p;
     const SolidityParams sp = make_sp(ctx);
     int rc;
-    // capacity of the solid set: every solid k-mer holds at least min(abundance_min) occurrences
-    long long amin = ctx->cfg.abundance_min[0];
-    for (int b = 1; b < ctx->NB; b++) amin = std::min<long long>(amin, ctx->cfg.abundance_min[b]);
-    if (amin < 1 || sp.kind == DSKGPU_SOLIDITY_CUSTOM) amin = 1;
-    const u64 out_cap = total_kmers / (u64)amin + 1024;
-    for (int i = 0; i < 2; i++) {
-        if ((rc = ensure(ctx, ctx->skeys[i], out_cap * KW * 8))) return rc;
-        if ((rc = ensure(ctx, ctx->svals[i], out_cap * 4))) return rc;
-    }
     const int mode = ctx->cfg.count_mode;
     const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 23;
     u64 nslots = (u64)1 << log2s;
@@ -570,7 +594,6 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
         return 0;
     };
 
-    SpanGuard g(ctx, SPAN_COUNT);
     if (mode == DSKGPU_COUNT_SORT) {
         size_t p = 0;
         while (p < np) {
@@ -644,41 +667,65 @@ static int stage_totals(dskgpu_ctx* ctx)
     return 0;
 }
 
-// number of partitions for `nkm` k-mers in the whole job: ~ a quarter of the hash table capacity per partition,
-// a multiple of the world size so that every rank owns the same number (owner(p) = p % world_size)
-static u32 choose_partitions(dskgpu_ctx* ctx, u64 nkm)
+// ---- stage 2: plan the partitions from the whole-job bin histogram ---------------------------------------------------
+static int fetch_local_bin_hist(dskgpu_ctx* ctx)
 {
-    const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 23;
-    const u64 target = std::max<u64>(((u64)1 << log2s) * 6 / 10 / 4, 4096);
-    const u32 W = (u32)ctx->cfg.world_size;
-    u64 P = ctx->cfg.nb_partitions > 0 ? (u64)ctx->cfg.nb_partitions : (nkm + target - 1) / target;
-    if (P < W) P = W;
-    P = (P + W - 1) / W * W;
-    const u32 PMAX = 4096 / W * W;
-    if (P > PMAX) P = PMAX;
-    return (u32)P;
+    CK(cudaMemcpyAsync(ctx->h_bin_hist, ctx->bin_hist.p, sizeof(unsigned long long) * 2 * NBINS, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
-// ---- stage 2: records / k-mers of every partition among MY records -------------------------------------------------
-static int stage_part_hist(dskgpu_ctx* ctx, u32 P)
+static bool use_smem_path(const dskgpu_ctx* ctx)
 {
-    int rc;
+    const int mode = ctx->cfg.count_mode;
+    return ctx->NB == 1 && (mode == DSKGPU_COUNT_AUTO || mode == DSKGPU_COUNT_SMEM) && ctx->smem_cap >= 64;
+}
+
+// k-mers a partition should hold.  Shared-memory path: 2 x the table slots (a 100x / 30x read set has 3-4 occurrences
+// per distinct k-mer, so the table ends up 50-65 % full; sparser data overflows and is split in two passes by the kernel;
+// measured on C2: 125 % -> 4.36 ms, 175 % -> 4.03 ms, 250 % -> 4.03 ms per 400 M k-mers).
+// Global-table path: a quarter of the table capacity, so that groups of partitions can be sized to the measured occupancy.
+static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers)
+{
+    if (ctx->cfg.nb_partitions > 0) return std::max<u64>(1, (global_kmers + ctx->cfg.nb_partitions - 1) / (u64)ctx->cfg.nb_partitions);
+    if (use_smem_path(ctx)) {
+        const char* e = getenv("DSKGPU_SMEM_T_PCT");                 // tuning knob: partition size in % of the table slots
+        const u64 pct = e ? (u64)std::max(10, atoi(e)) : 200;
+        return std::max<u64>(64, (u64)ctx->smem_cap * pct / 100);
+    }
+    const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 23;
+    return std::max<u64>(((u64)1 << log2s) * 6 / 10 / 4, 4096);
+}
+
+// greedy packing of consecutive bins (the role of Repartitor::computeDistrib, K/PartiInfo.cpp:48-106, on exact counts);
+// every rank derives the same plan from the same global histogram.  P is padded to a multiple of the world size.
+static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh /*[2*NBINS] whole job*/)
+{
+    u64 total = 0;
+    for (u32 b = 0; b < NBINS; b++) total += gh[NBINS + b];
+    const u64 T = plan_target_kmers(ctx, total);
+    ctx->h_bin2part.assign(NBINS, 0);
+    u32 P = 0; u64 acc = 0;
+    for (u32 b = 0; b < NBINS; b++) {
+        const u64 km = gh[NBINS + b];
+        if (acc > 0 && acc + km > T) { P++; acc = 0; }
+        ctx->h_bin2part[b] = P; acc += km;
+    }
+    P += 1;
+    const u32 W = (u32)ctx->cfg.world_size;
+    P = (P + W - 1) / W * W;
     ctx->nparts = P; ctx->st.nb_partitions = P;
-    ctx->h_part_recs.assign(P, 0); ctx->h_part_kmers.assign(P, 0);
-    if ((rc = ensure(ctx, ctx->part_recs, P * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->part_kmers, P * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->cursor, P * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->dstbase, P * 8))) return rc;
-    if (ctx->local_nrec == 0) return 0;
-    SpanGuard g(ctx, SPAN_PART);
-    CK(cudaMemsetAsync(ctx->part_recs.p, 0, P * 8, ctx->stream));
-    CK(cudaMemsetAsync(ctx->part_kmers.p, 0, P * 8, ctx->stream));
-    const unsigned hb = (unsigned)std::min<u64>((ctx->local_nrec + 2047) / 2048, 148 * 8);
-    k_part_hist<<<hb, 256, 2 * P * 4, ctx->stream>>>((const u32*)ctx->meta.p, ctx->local_nrec, P, (unsigned long long*)ctx->part_recs.p,
-                                                    (unsigned long long*)ctx->part_kmers.p); LAUNCHED();
-    CK(cudaMemcpyAsync(ctx->h_part_recs.data(), ctx->part_recs.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_part_kmers.data(), ctx->part_kmers.p, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->g_part_kmers.assign(P, 0); ctx->h_part_recs.assign(P, 0); ctx->h_part_kmers.assign(P, 0);
+    for (u32 b = 0; b < NBINS; b++) {
+        const u32 p = ctx->h_bin2part[b];
+        ctx->g_part_kmers[p] += gh[NBINS + b];
+        ctx->h_part_recs[p] += ctx->h_bin_hist[b];
+        ctx->h_part_kmers[p] += ctx->h_bin_hist[NBINS + b];
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->cursor, (size_t)P * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dstbase, (size_t)P * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->bin2part, (size_t)NBINS * 4))) return rc;
     return 0;
 }
 
@@ -689,13 +736,14 @@ static int stage_scatter(dskgpu_ctx* ctx, const std::vector<u64*>& dst)
     const u32 P = ctx->nparts;
     if (ctx->local_nrec == 0) return 0;
     SpanGuard g(ctx, SPAN_PART);
-    CK(cudaMemsetAsync(ctx->cursor.p, 0, P * 8, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dstbase.p, dst.data(), P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)P * 8, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dstbase.p, dst.data(), (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->bin2part.p, ctx->h_bin2part.data(), (size_t)NBINS * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));          // dst may be a temporary
-    const unsigned sb = (unsigned)((ctx->local_nrec + SC_THREADS * SC_RPT - 1) / (SC_THREADS * SC_RPT));
-    const size_t smem = (size_t)((P + 1) & ~1u) * 4 + (size_t)P * 8;
-    k_part_scatter<KW><<<sb, SC_THREADS, smem, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, ctx->local_nrec, P,
-                                                             (u64* const*)ctx->dstbase.p, (unsigned long long*)ctx->cursor.p); LAUNCHED();
+    const unsigned sb = (unsigned)std::min<u64>((ctx->local_nrec + SC_THREADS - 1) / SC_THREADS, (u64)ctx->num_sms * 32);
+    k_part_scatter<KW><<<sb, SC_THREADS, 0, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, ctx->local_nrec,
+                                                          (const u32*)ctx->bin2part.p, (u64* const*)ctx->dstbase.p,
+                                                          (unsigned long long*)ctx->cursor.p); LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -706,15 +754,71 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
 {
     Counters* ctr = (Counters*)ctx->ctr.p;
     int rc;
+    const size_t np = prec.size();
     u64 nrec = 0, nkm = 0;
-    for (size_t i = 0; i < prec.size(); i++) { nrec += prec[i]; nkm += pkm[i]; }
-    if (nrec) { if ((rc = count_all<KW>(ctx, recs, prec, pkm, nkm))) return rc; }
+    for (size_t i = 0; i < np; i++) { nrec += prec[i]; nkm += pkm[i]; }
+    ctx->st.smem_table_slots = ctx->smem_cap;
+    if (nrec) {
+        // capacity of the solid set: every solid k-mer holds at least min(abundance_min) occurrences
+        long long amin = ctx->cfg.abundance_min[0];
+        for (int b = 1; b < ctx->NB; b++) amin = std::min<long long>(amin, ctx->cfg.abundance_min[b]);
+        if (amin < 1 || ctx->cfg.solidity_kind == DSKGPU_SOLIDITY_CUSTOM) amin = 1;
+        const u64 out_cap = nkm / (u64)amin + 1024;
+        for (int i = 0; i < 2; i++) {
+            if ((rc = ensure(ctx, ctx->skeys[i], out_cap * KW * 8))) return rc;
+            if ((rc = ensure(ctx, ctx->svals[i], out_cap * 4))) return rc;
+        }
+        // occupancy picks the path of every partition (K/SortingCountAlgorithm.cpp:1489-1497): shared-memory table when the
+        // partition is within reach of a few split passes, else the global paths
+        const bool smem = use_smem_path(ctx);
+        const u64 smem_max = (u64)ctx->smem_cap * 16;
+        std::vector<SmemJob> jobs;
+        std::vector<u64> off(np + 1, 0);
+        std::vector<char> big(np, 0);
+        for (size_t i = 0; i < np; i++) {
+            off[i + 1] = off[i] + prec[i];
+            if (prec[i] == 0) continue;
+            if (smem && pkm[i] <= smem_max && prec[i] < 0xFFFFFFFFull) { SmemJob j; j.rec_begin = off[i]; j.nrec = (unsigned)prec[i]; j.pad = 0; jobs.push_back(j); }
+            else big[i] = 1;
+        }
+        SpanGuard g(ctx, SPAN_COUNT);
+        if (!jobs.empty()) {
+            std::sort(jobs.begin(), jobs.end(), [](const SmemJob& a, const SmemJob& b) { return a.nrec > b.nrec; });   // longest first
+            if ((rc = ensure(ctx, ctx->jobs, jobs.size() * sizeof(SmemJob)))) return rc;
+            CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), jobs.size() * sizeof(SmemJob), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));      // jobs is a temporary
+            const unsigned grid = (unsigned)std::min<size_t>(jobs.size(), (size_t)ctx->num_sms * CS_CTAS_PER_SM);
+            const size_t dyn = KW == 1 ? cs_smem_bytes<1>(ctx->smem_cap) : cs_smem_bytes<2>(ctx->smem_cap);
+            cudaEvent_t a = get_event(ctx), b = get_event(ctx);
+            cudaEventRecord(a, ctx->stream);
+            k_count_smem<KW><<<grid, CS_THREADS, dyn, ctx->stream>>>(recs, (const SmemJob*)ctx->jobs.p, (u32)jobs.size(), ctx->k, ctx->smem_cap,
+                                                                   (long long)ctx->cfg.abundance_min[0], (long long)ctx->cfg.abundance_max,
+                                                                   (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
+                                                                   (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p); LAUNCHED();
+            cudaEventRecord(b, ctx->stream);
+            ctx->spans.push_back({a, b, SPAN_DOM});
+            ctx->st.nb_parts_smem = (u32)jobs.size();
+            CK(cudaGetLastError());
+        }
+        // maximal runs of consecutive big partitions go through the global hash / sort paths
+        for (size_t i = 0; i < np;) {
+            if (!big[i]) { i++; continue; }
+            size_t j = i; u64 km = 0;
+            std::vector<u64> rp, rk;
+            while (j < np && (big[j] || prec[j] == 0)) { rp.push_back(prec[j]); rk.push_back(pkm[j]); km += pkm[j]; j++; }
+            if ((rc = count_all<KW>(ctx, recs + off[i] * (u64)ctx->RW, rp, rk, out_cap))) return rc;
+            i = j;
+        }
+    }
     CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_ctr->hash_overflow) FAIL(DSKGPU_ERR_OVERFLOW, "hash table overflow (distinct k-mer estimate too low)");
+    if (ctx->h_ctr->smem_failed) FAIL(DSKGPU_ERR_OVERFLOW, "shared-memory table overflow at the deepest split (%u passes)", ctx->h_ctr->smem_failed);
     if (ctx->h_ctr->overflow) FAIL(DSKGPU_ERR_OVERFLOW, "solid k-mer buffer overflow");
     ctx->n_solid = ctx->h_ctr->solid_n;
     ctx->st.kmers_nb_distinct = ctx->h_ctr->distinct_n; ctx->st.kmers_nb_solid = ctx->n_solid;
+    ctx->st.nb_smem_splits = ctx->h_ctr->smem_splits;
 
     // order the solid set (ascending k-mer value, as the reference emits within a partition)
     ctx->solid_buf = 0;
@@ -755,8 +859,9 @@ static int finish_single(dskgpu_ctx* ctx)
 {
     int rc;
     if ((rc = stage_totals(ctx))) return rc;
-    const u32 P = choose_partitions(ctx, ctx->local_nkm);
-    if ((rc = stage_part_hist(ctx, P))) return rc;
+    if ((rc = fetch_local_bin_hist(ctx))) return rc;
+    if ((rc = plan_partitions(ctx, ctx->h_bin_hist))) return rc;
+    const u32 P = ctx->nparts;
     if ((rc = ensure(ctx, ctx->precs, ctx->local_nrec * (u64)ctx->RW * 8 + 64))) return rc;
     std::vector<u64*> dst(P);
     u64 o = 0;
@@ -812,14 +917,24 @@ int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records
     return DSKGPU_OK;
 }
 
-int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, uint64_t global_kmers, uint64_t* counts, uint32_t* nparts)
+int dskgpu_xchg_bin_hist(dskgpu_ctx* ctx, uint64_t* hist)
 {
-    if (!ctx) return DSKGPU_ERR_ARG;
+    if (!ctx || !hist) return DSKGPU_ERR_ARG;
     int rc = stage_totals(ctx); if (rc) return rc;
-    const u32 P = choose_partitions(ctx, global_kmers);
+    if ((rc = fetch_local_bin_hist(ctx))) return rc;
+    memcpy(hist, ctx->h_bin_hist, sizeof(uint64_t) * 2 * NBINS);
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, const uint64_t* global_hist, uint64_t* counts, uint32_t* nparts)
+{
+    if (!ctx || !global_hist) return DSKGPU_ERR_ARG;
+    int rc = stage_totals(ctx); if (rc) return rc;
+    if ((rc = fetch_local_bin_hist(ctx))) return rc;
+    if ((rc = plan_partitions(ctx, (const unsigned long long*)global_hist))) return rc;
+    const u32 P = ctx->nparts;
     if (nparts) *nparts = P;
     if (!counts) return DSKGPU_OK;                                 // size query
-    if ((rc = stage_part_hist(ctx, P))) return rc;
     for (u32 p = 0; p < P; p++) { counts[p] = ctx->h_part_recs[p]; counts[P + p] = ctx->h_part_kmers[p]; }
     return DSKGPU_OK;
 }

@@ -134,13 +134,17 @@ DSK_HD u32 mmer_value(u32 x, int m)
     return a1 ? mmask : v;
 }
 
-// minimizer -> partition (the role of Repartitor::operator(), K/PartiInfo.hpp:323; any deterministic
-// map is legal -- SURVEY.md appendix C).  Multiplicative hash + range reduction, no table.
-DSK_HD u32 partition_of(u32 minimizer, u32 nparts)
+// minimizer -> bin (the role of Repartitor::operator(), K/PartiInfo.hpp:323; any deterministic map is legal --
+// SURVEY.md appendix C).  Records are histogrammed into NBINS fine bins while they are produced; at finish the
+// host packs consecutive bins into partitions of the size the counting kernel wants (balanced on exact counts,
+// the job the reference gives to its sampled LPT table, K/PartiInfo.cpp:48-106).
+constexpr int NBINS_LOG2 = 17;
+constexpr u32 NBINS = 1u << NBINS_LOG2;
+DSK_HD u32 bin_of(u32 minimizer)
 {
     u32 h = minimizer * 0x9E3779B1u;
     h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
-    return (u32)(((u64)h * (u64)nparts) >> 32);
+    return h >> (32 - NBINS_LOG2);
 }
 
 // 64-bit finalizer (murmur3 fmix64) for hash-table slots

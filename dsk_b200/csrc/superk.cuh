@@ -32,6 +32,8 @@ struct Counters {
     unsigned int overflow;            // record buffer overflow
     unsigned int hash_overflow;
     unsigned long long expand_cursor; // sort path: keys written
+    unsigned int smem_splits;         // shared-memory path: table overflows answered by splitting a pass in two
+    unsigned int smem_failed;         // shared-memory path: passes that still overflowed at the deepest split
 };
 
 #ifdef __CUDACC__
@@ -41,7 +43,8 @@ __device__ __forceinline__ u32 sk_pidx(u32 p) { return p + (p >> 3); }     // pa
 template <int KW>
 __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict__ codes, const StreamState* __restrict__ ss,
                                                            int k, int m, int bank, u64* __restrict__ recs,
-                                                           u32* __restrict__ rec_meta, u64 rec_cap, Counters* ctr)
+                                                           u32* __restrict__ rec_meta, u64 rec_cap, Counters* ctr,
+                                                           unsigned long long* __restrict__ bin_hist /*[2][NBINS] records, k-mers*/)
 {
     constexpr int RW = 2 * KW;
     __shared__ u64 s_pk[SK_TP / 32 + 8];                         // 2-bit bases, MSB first, 32 per word
@@ -229,72 +232,38 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
             reinterpret_cast<ulonglong2*>(recs)[2 * ri] = make_ulonglong2(rw[0], rw[1]);
             reinterpret_cast<ulonglong2*>(recs)[2 * ri + 1] = make_ulonglong2(rw[2], rw[3]);
         }
-        rec_meta[ri] = s_lmn[i] | (nk << 24);
+        // fine histogram of the bins while the records are produced (fire-and-forget REDs under an ALU-bound kernel)
+        const u32 bin = bin_of(s_lmn[i]);
+        rec_meta[ri] = bin | (nk << 24);
+        atomicAdd(&bin_hist[bin], 1ULL);
+        atomicAdd(&bin_hist[NBINS + bin], (unsigned long long)nk);
         nk_sum += nk;
     }
     nk_sum = __reduce_add_sync(0xFFFFFFFFu, nk_sum);
     if (lane == 0 && nk_sum) atomicAdd(&ctr->kmers_in_recs, (unsigned long long)nk_sum);
 }
 
-// ---- K3a: records/k-mers per partition ------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_part_hist(const u32* __restrict__ rec_meta, u64 nrec, u32 nparts,
-                                                   unsigned long long* __restrict__ part_recs,
-                                                   unsigned long long* __restrict__ part_kmers)
-{
-    extern __shared__ u32 s_h[];                                  // [2*nparts]
-    for (u32 i = threadIdx.x; i < 2 * nparts; i += blockDim.x) s_h[i] = 0;
-    __syncthreads();
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (u64)gridDim.x * blockDim.x) {
-        u32 me = rec_meta[i];
-        u32 p = partition_of(me & 0xFFFFFFu, nparts);
-        atomicAdd(&s_h[p], 1u);
-        atomicAdd(&s_h[nparts + p], me >> 24);
-    }
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < nparts; i += blockDim.x) {
-        if (s_h[i]) { atomicAdd(&part_recs[i], (unsigned long long)s_h[i]); atomicAdd(&part_kmers[i], (unsigned long long)s_h[nparts + i]); }
-    }
-}
-
-// ---- K3b: scatter records into partition order ------------------------------------------------------------------
-// Block-aggregated: local ranks through smem atomics, one global reservation per (block, partition).
-// dst_base[p] = device pointer (local or NVLink peer) where partition p's records start; cursor[p] = records
-// already placed by this rank.
+// ---- K3: scatter records into partition order --------------------------------------------------------------------
+// bin2part[bin] = partition of a bin (planned on the host from the exact bin histogram); dst_base[p] = device
+// pointer (local or NVLink peer) where this rank's records of partition p start; cursor[p] = records already placed.
+// Partitions are small (a few thousand records) and there are tens of thousands of them, so a record takes one
+// L2 atomic on its partition's cursor and one 16/32-byte vector store.
 constexpr int SC_THREADS = 256;
-constexpr int SC_RPT = 8;
 template <int KW>
 __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(const u64* __restrict__ recs, const u32* __restrict__ rec_meta, u64 nrec,
-                                                             u32 nparts, u64* const* __restrict__ dst_base,
+                                                             const u32* __restrict__ bin2part, u64* const* __restrict__ dst_base,
                                                              unsigned long long* __restrict__ cursor)
 {
     constexpr int RW = 2 * KW;
-    extern __shared__ u32 s_cnt[];                                // [nparts] counts, then [nparts] reserved bases (u64 as 2 u32)
-    unsigned long long* s_base = reinterpret_cast<unsigned long long*>(s_cnt + ((nparts + 1) & ~1u));
-    const u64 tile0 = (u64)blockIdx.x * SC_THREADS * SC_RPT;
-    for (u32 i = threadIdx.x; i < nparts; i += SC_THREADS) s_cnt[i] = 0;
-    __syncthreads();
-    u32 part[SC_RPT], rank[SC_RPT];
-#pragma unroll
-    for (int r = 0; r < SC_RPT; r++) {
-        u64 i = tile0 + (u64)r * SC_THREADS + threadIdx.x;
-        part[r] = 0xFFFFFFFFu;
-        if (i < nrec) { part[r] = partition_of(rec_meta[i] & 0xFFFFFFu, nparts); rank[r] = atomicAdd(&s_cnt[part[r]], 1u); }
-    }
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < nparts; i += SC_THREADS) {
-        u32 c = s_cnt[i];
-        if (c) s_base[i] = atomicAdd(&cursor[i], (unsigned long long)c);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < SC_RPT; r++) {
-        u64 i = tile0 + (u64)r * SC_THREADS + threadIdx.x;
-        if (part[r] == 0xFFFFFFFFu) continue;
-        u64 d = s_base[part[r]] + rank[r];
-        ulonglong2* dst = reinterpret_cast<ulonglong2*>(dst_base[part[r]]);
-        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
-        if constexpr (RW == 2) dst[d] = src[i];
-        else { dst[2 * d] = src[2 * i]; dst[2 * d + 1] = src[2 * i + 1]; }
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
+    for (u64 i = (u64)blockIdx.x * SC_THREADS + threadIdx.x; i < nrec; i += (u64)gridDim.x * SC_THREADS) {
+        const u32 p = __ldg(bin2part + (rec_meta[i] & (NBINS - 1)));
+        ulonglong2 a = src[(RW / 2) * i], b;
+        if constexpr (RW == 4) b = src[2 * i + 1];
+        const u64 d = atomicAdd(&cursor[p], 1ULL);
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(dst_base[p]);
+        if constexpr (RW == 2) dst[d] = a;
+        else { dst[2 * d] = a; dst[2 * d + 1] = b; }
     }
 }
 

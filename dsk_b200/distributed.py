@@ -4,7 +4,8 @@ Every rank parses its own slice of the reads; super-k-mer records are routed to 
 (owner(p) = p % world_size) by the partition-scatter kernel itself, which stores straight into the owners' HBM
 through CUDA-IPC peer pointers (NVLink P2P) -- the role the reference gives to its temp files
 (SuperKmerBinFiles, G/src/gatb/tools/storage/impl/Storage.cpp:310-589).  Only tiny metadata crosses
-torch.distributed: the k-mer totals (all-reduce), the per-partition count matrix (all-gather) and the IPC handles.
+torch.distributed: the minimizer-bin histogram (all-reduce, 1 MB), the per-partition count matrix (all-gather) and
+the IPC handles.
 """
 import ctypes as C
 
@@ -40,10 +41,9 @@ def distributed_finish(eng, dist, device):
     """Runs the exchange + local counting on every rank (call after the pushes).  Returns the gathered count matrix."""
     import torch
     W, rank = dist.get_world_size(), dist.get_rank()
-    km, _ = eng.xchg_local_totals()
-    t = torch.tensor([km], dtype=torch.int64, device=device)
-    dist.all_reduce(t)
-    counts = eng.xchg_part_counts(int(t.item()))
+    t = torch.from_numpy(eng.xchg_bin_hist().astype(np.int64)).to(device)      # (records, k-mers) per minimizer bin, 1 MB
+    dist.all_reduce(t)                                                         # every rank plans the same partitions
+    counts = eng.xchg_part_counts(t.cpu().numpy().astype(np.uint64))
     allc = all_gather_counts(dist, counts, device)
     eng.xchg_plan(allc)
     handle = np.frombuffer(eng.xchg_ipc_handle(), dtype=np.uint8).copy()
@@ -74,9 +74,8 @@ def distributed_finish(eng, dist, device):
 def in_process_finish(engines):
     """Same protocol for several contexts living in ONE process (tests: N 'ranks' on one GPU, no IPC needed)."""
     W = len(engines)
-    totals = [e.xchg_local_totals()[0] for e in engines]
-    gk = int(sum(totals))
-    allc = np.stack([e.xchg_part_counts(gk) for e in engines])
+    gh = np.sum([e.xchg_bin_hist() for e in engines], axis=0, dtype=np.uint64)
+    allc = np.stack([e.xchg_part_counts(gh) for e in engines])
     for e in engines:
         e.xchg_plan(allc)
     ptrs = [e.xchg_recv_buffer()[0] for e in engines]

@@ -26,6 +26,7 @@ extern "C" {
 #define DSKGPU_HISTO_LEN     10001          /* bins 0..10000 (Histogram.hpp:92, length 10000) */
 #define DSKGPU_HISTO2D_DIM2  11             /* bins 0..10   (CountProcessorHistogram.hpp:173-184) */
 #define DSKGPU_MAX_KMER      63             /* KSIZE_LIST "32 64": k<32 -> 64-bit keys, k<64 -> 128-bit */
+#define DSKGPU_NBINS         131072         /* fine minimizer bins that are packed into partitions at finish */
 
 /* error codes */
 enum {
@@ -43,8 +44,12 @@ enum {
 enum { DSKGPU_SOLIDITY_SUM = 0, DSKGPU_SOLIDITY_MIN = 1, DSKGPU_SOLIDITY_MAX = 2,
        DSKGPU_SOLIDITY_ONE = 3, DSKGPU_SOLIDITY_ALL = 4, DSKGPU_SOLIDITY_CUSTOM = 5 };
 
-/* how a partition is counted (SortingCountAlgorithm.cpp:1489-1497 picks vector vs hash) */
-enum { DSKGPU_COUNT_AUTO = 0, DSKGPU_COUNT_SORT = 1 /* PartitionsByVectorCommand */, DSKGPU_COUNT_HASH = 2 /* PartitionsByHashCommand */ };
+/* how a partition is counted (SortingCountAlgorithm.cpp:1489-1497 picks vector vs hash by partition occupancy).
+ * AUTO: partitions are sized for the shared-memory hash table of one SM (DSKGPU_COUNT_SMEM); partitions too big for it
+ *       go to the L2-resident global hash table, and those too big for that to the radix-sort path.
+ * SORT / HASH / SMEM force one path (SMEM still hands oversize partitions to HASH). */
+enum { DSKGPU_COUNT_AUTO = 0, DSKGPU_COUNT_SORT = 1 /* PartitionsByVectorCommand */, DSKGPU_COUNT_HASH = 2 /* PartitionsByHashCommand */,
+       DSKGPU_COUNT_SMEM = 3 };
 
 /* input stream formats understood by the device record scanner (BankFasta.cpp:485-572) */
 enum { DSKGPU_FMT_AUTO = 0, DSKGPU_FMT_FASTA = 1, DSKGPU_FMT_FASTQ = 2, DSKGPU_FMT_LINES = 3 /* one sequence per line */ };
@@ -75,7 +80,8 @@ typedef struct dskgpu_config {
     void*    stream;                             /* cudaStream_t to run on, NULL = library-owned stream */
     int32_t  rank, world_size;                   /* multi-GPU: this context owns partitions p with p % world_size == rank */
     int32_t  push_chunk_bytes;                   /* 0 = default (64 MiB): granularity of the streamed H2D copy + scan */
-    int32_t  reserved[7];
+    int32_t  smem_table_slots;                   /* 0 = auto (all the shared memory of an SM); tests shrink it to force splits */
+    int32_t  reserved[6];
 } dskgpu_config;
 
 /* stats block: the keys of SortingCountAlgorithm::getInfo() (SortingCountAlgorithm.cpp:728-780) */
@@ -93,9 +99,12 @@ typedef struct dskgpu_stats {
     uint64_t gpu_launches;          /* kernels launched by this context since create/reset */
     /* device time per stage, milliseconds (CUDA events on the context stream) */
     float ms_parse, ms_superk, ms_partition, ms_count, ms_sort, ms_total;
-    float ms_dominant_kernel;       /* summed duration of the dominant counting kernel (hash insert or radix passes) */
+    float ms_dominant_kernel;       /* summed duration of the dominant counting kernel (smem count, hash insert or radix passes) */
     uint32_t dominant_kernel_launches;
-    uint32_t reserved[7];
+    uint32_t nb_parts_smem;         /* partitions counted in shared memory */
+    uint32_t nb_smem_splits;        /* table overflows answered by splitting a pass */
+    uint32_t smem_table_slots;      /* capacity of the shared-memory table */
+    uint32_t reserved[4];
 } dskgpu_stats;
 
 /* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */
@@ -155,7 +164,8 @@ int  dskgpu_abi_version(void);
 
 /* ---- multi-GPU exchange (replaces the SuperKmerBinFiles temp tier, Storage.cpp:310-589) --------------
  * One context per rank (one process per GPU).  Partition p is owned by rank p % world_size.  After all pushes:
- *   1. xchg_local_totals        -> all-reduce the k-mer totals out of band (torch.distributed / NCCL)
+ *   1. xchg_bin_hist            -> this rank's (records, k-mers) per minimizer bin; all-reduce (sum) it out of band
+ *                                  (torch.distributed / NCCL): every rank then plans the same partitions
  *   2. xchg_part_counts         -> per-partition record / k-mer counts of this rank; all-gather them
  *   3. xchg_plan                -> every rank derives every receive-buffer layout from the gathered matrix and
  *                                  allocates its own receive buffer (xchg_recv_buffer / xchg_ipc_handle expose it)
@@ -164,8 +174,11 @@ int  dskgpu_abi_version(void);
  *                                  scatter and the all-to-all are the same kernel, there is no send staging
  *   5. xchg_sync, barrier out of band, then dskgpu_finish counts the owned partitions locally. */
 int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records);
-/* counts[0..P) = records, counts[P..2P) = k-mers of each partition on this rank; pass counts = NULL to query P */
-int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, uint64_t global_kmers, uint64_t* counts, uint32_t* nparts);
+/* hist[0..NBINS) = records, hist[NBINS..2*NBINS) = k-mers of every bin on this rank */
+int dskgpu_xchg_bin_hist(dskgpu_ctx* ctx, uint64_t* hist /*[2*DSKGPU_NBINS]*/);
+/* plans the partitions from the whole-job histogram (sum over ranks); counts[0..P) = records, counts[P..2P) = k-mers of
+ * each partition on this rank; pass counts = NULL to query P */
+int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, const uint64_t* global_hist /*[2*DSKGPU_NBINS]*/, uint64_t* counts, uint32_t* nparts);
 int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts /*[world_size][2*P], row = rank*/);
 int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes);
 int dskgpu_xchg_ipc_handle(dskgpu_ctx* ctx, void* handle64 /*cudaIpcMemHandle_t of the receive buffer*/);

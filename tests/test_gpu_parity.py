@@ -58,23 +58,48 @@ SUBSET = [t for t in RUNS if t["name"] in ("c1_k31", "c1_k63", "lowcomplexity.fa
                                            "multiline.fasta_k63", "histo2d_k31", "c123_k31_all", "c1_k21", "c1_k32")]
 
 
-@pytest.mark.parametrize("mode", ["sort", "hash"])
+@pytest.mark.parametrize("mode", ["sort", "hash", "smem"])
 @pytest.mark.parametrize("t", SUBSET, ids=[t["name"] for t in SUBSET])
 def test_forced_count_modes(t, mode):
     sc = run_gpu(t["files"], t["k"], t["abundance_min"], t["histo2d"], t.get("solidity_kind"), t.get("abundance_max"), count_mode=mode)
     check_against_run(sc, t)
     st = sc.getInfo()["engine"]
-    assert (st["nb_groups_sort"] > 0) == (mode == "sort") and (st["nb_groups_hash"] > 0) == (mode == "hash")
+    per_bank = len(t["files"]) > 1 and (t["histo2d"] or (t.get("solidity_kind") or "sum") != "sum")
+    if mode == "smem" and not per_bank:
+        # shared-memory tables everywhere except the partitions too big for a few split passes (lowcomplexity: one hot minimizer)
+        assert st["nb_parts_smem"] > 0 and st["nb_groups_sort"] == 0
+    elif mode == "smem":
+        assert st["nb_parts_smem"] == 0 and st["nb_groups_hash"] > 0           # per-bank counts live in the global table
+    else:
+        assert (st["nb_groups_sort"] > 0) == (mode == "sort") and (st["nb_groups_hash"] > 0) == (mode == "hash") and st["nb_parts_smem"] == 0
 
 
 @pytest.mark.parametrize("t", SUBSET, ids=[t["name"] for t in SUBSET])
 def test_small_table_many_partitions_and_chunked_push(t):
-    # tiny hash table => many partitions/groups and the occupancy picker sending big partitions to the sort path;
+    # tiny global hash table => many partitions/groups and the occupancy picker sending big partitions to the sort path;
     # 4 KiB push granularity => records straddle every chunk boundary
     sc = run_gpu(t["files"], t["k"], t["abundance_min"], t["histo2d"], t.get("solidity_kind"), t.get("abundance_max"),
-                 hash_log2_slots=10, push_chunk_bytes=4096)
+                 count_mode="hash", hash_log2_slots=10, push_chunk_bytes=4096)
     check_against_run(sc, t)
     assert sc.getInfo()["engine"]["nb_partitions"] > 1
+
+
+@pytest.mark.parametrize("slots", [64, 256, 2048])
+@pytest.mark.parametrize("t", SUBSET, ids=[t["name"] for t in SUBSET])
+def test_tiny_smem_table_overflow_splits(t, slots):
+    # a shared-memory table far too small for its partitions: the kernel must answer every overflow by splitting the pass
+    # (recursively) and still produce the reference's counts; partitions beyond 16 x slots k-mers go to the global paths
+    sc = run_gpu(t["files"], t["k"], t["abundance_min"], t["histo2d"], t.get("solidity_kind"), t.get("abundance_max"),
+                 count_mode="smem", smem_table_slots=slots, nb_partitions=1000 if slots == 64 else 0)
+    check_against_run(sc, t)
+    st = sc.getInfo()["engine"]
+    per_bank = len(t["files"]) > 1 and (t["histo2d"] or (t.get("solidity_kind") or "sum") != "sum")
+    if not per_bank:
+        assert st["smem_table_slots"] == slots
+        if t["kmers_nb_distinct"] > 20000:                       # (lowcomplexity: a few hot minimizers, all beyond 16 x slots)
+            assert st["nb_parts_smem"] > 0
+            if slots == 64:
+                assert st["nb_smem_splits"] > 0
 
 
 @pytest.mark.parametrize("t", SHELL, ids=[t["name"] for t in SHELL])
@@ -161,7 +186,7 @@ def test_synthetic_vs_oracle(k):
     compare_with_oracle([buf[:n].tobytes()], k)
 
 
-@pytest.mark.parametrize("mode", ["auto", "sort", "hash"])
+@pytest.mark.parametrize("mode", ["auto", "sort", "hash", "smem"])
 def test_synthetic_medium_modes(mode):
     buf, n, _ = reads_fasta(G=1_000_000, coverage=30, L=150, err=0.01, seed=5)
     sc = compare_with_oracle([buf[:n].tobytes()], 31, engine=dict(count_mode=mode, hash_log2_slots=18))
@@ -245,7 +270,7 @@ def split_records(data, parts):
     return [data[cuts[i]:cuts[i + 1]] for i in range(parts)]
 
 
-@pytest.mark.parametrize("W,k,mode", [(2, 31, "auto"), (3, 31, "hash"), (2, 63, "auto"), (4, 31, "sort")])
+@pytest.mark.parametrize("W,k,mode", [(2, 31, "auto"), (3, 31, "hash"), (2, 63, "auto"), (4, 31, "sort"), (3, 63, "smem")])
 def test_multi_rank_exchange_in_process(W, k, mode):
     """N ranks as N contexts on one GPU: every rank parses a slice, the scatter kernel routes records to the owner
     of their partition (p % W), every rank counts only what it owns.  Union of the ranks' outputs == oracle."""
