@@ -9,7 +9,7 @@ SO = os.environ.get("DSKGPU_LIB") or os.path.join(PKG, "libdskgpu.so")      # DS
 MAX_BANKS = 16
 HISTO_LEN = 10001
 HISTO2D_DIM2 = 11
-NBINS = 131072
+NBINS = 65536
 
 ERR_NODEVICE = -6
 

@@ -85,6 +85,18 @@ struct dskgpu_ctx {
 #define FAIL(code, ...) do { char b_[512]; snprintf(b_, sizeof b_, __VA_ARGS__); if (ctx) ctx->err = b_; g_last_error = b_; return (code); } while (0)
 #define LAUNCHED() do { ctx->st.gpu_launches++; } while (0)
 
+// DSKGPU_TRACE=1: host wall-clock of the stages of push / finish on stderr (tuning aid)
+#include <chrono>
+static bool g_trace = getenv("DSKGPU_TRACE") != nullptr;
+static std::chrono::steady_clock::time_point g_t0;
+static void trace(const char* what)
+{
+    if (!g_trace) return;
+    auto now = std::chrono::steady_clock::now();
+    if (!what) { g_t0 = now; return; }
+    fprintf(stderr, "[dskgpu] %-28s +%8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - g_t0).count());
+}
+
 static int ensure(dskgpu_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false, size_t keep_bytes = 0)
 {
     if (bytes <= b.cap) return 0;
@@ -701,27 +713,28 @@ static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers)
 // every rank derives the same plan from the same global histogram.  P is padded to a multiple of the world size.
 static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh /*[2*NBINS] whole job*/)
 {
+    const unsigned long long* gk = gh + NBINS;
+    const unsigned long long* lr = ctx->h_bin_hist; const unsigned long long* lk = ctx->h_bin_hist + NBINS;
     u64 total = 0;
-    for (u32 b = 0; b < NBINS; b++) total += gh[NBINS + b];
+    for (u32 b = 0; b < NBINS; b++) total += gk[b];
     const u64 T = plan_target_kmers(ctx, total);
-    ctx->h_bin2part.assign(NBINS, 0);
-    u32 P = 0; u64 acc = 0;
+    ctx->h_bin2part.resize(NBINS);
+    ctx->g_part_kmers.clear(); ctx->h_part_recs.clear(); ctx->h_part_kmers.clear();
+    u32* b2p = ctx->h_bin2part.data();
+    u32 P = 0; u64 acc = 0, ar = 0, ak = 0;
     for (u32 b = 0; b < NBINS; b++) {
-        const u64 km = gh[NBINS + b];
-        if (acc > 0 && acc + km > T) { P++; acc = 0; }
-        ctx->h_bin2part[b] = P; acc += km;
+        const u64 km = gk[b];
+        if (acc > 0 && acc + km > T) {
+            ctx->g_part_kmers.push_back(acc); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
+            P++; acc = ar = ak = 0;
+        }
+        b2p[b] = P; acc += km; ar += lr[b]; ak += lk[b];
     }
+    ctx->g_part_kmers.push_back(acc); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
     P += 1;
     const u32 W = (u32)ctx->cfg.world_size;
-    P = (P + W - 1) / W * W;
+    while (P % W) { ctx->g_part_kmers.push_back(0); ctx->h_part_recs.push_back(0); ctx->h_part_kmers.push_back(0); P++; }
     ctx->nparts = P; ctx->st.nb_partitions = P;
-    ctx->g_part_kmers.assign(P, 0); ctx->h_part_recs.assign(P, 0); ctx->h_part_kmers.assign(P, 0);
-    for (u32 b = 0; b < NBINS; b++) {
-        const u32 p = ctx->h_bin2part[b];
-        ctx->g_part_kmers[p] += gh[NBINS + b];
-        ctx->h_part_recs[p] += ctx->h_bin_hist[b];
-        ctx->h_part_kmers[p] += ctx->h_bin_hist[NBINS + b];
-    }
     int rc;
     if ((rc = ensure(ctx, ctx->cursor, (size_t)P * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dstbase, (size_t)P * 8))) return rc;
@@ -781,6 +794,7 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
             if (smem && pkm[i] <= smem_max && prec[i] < 0xFFFFFFFFull) { SmemJob j; j.rec_begin = off[i]; j.nrec = (unsigned)prec[i]; j.pad = 0; jobs.push_back(j); }
             else big[i] = 1;
         }
+        trace("jobs built");
         SpanGuard g(ctx, SPAN_COUNT);
         if (!jobs.empty()) {
             std::sort(jobs.begin(), jobs.end(), [](const SmemJob& a, const SmemJob& b) { return a.nrec > b.nrec; });   // longest first
@@ -800,6 +814,7 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
             ctx->spans.push_back({a, b, SPAN_DOM});
             ctx->st.nb_parts_smem = (u32)jobs.size();
             CK(cudaGetLastError());
+            trace("count kernel launched");
         }
         // maximal runs of consecutive big partitions go through the global hash / sort paths
         for (size_t i = 0; i < np;) {
@@ -813,6 +828,7 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
     }
     CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    trace("count done (sync)");
     if (ctx->h_ctr->hash_overflow) FAIL(DSKGPU_ERR_OVERFLOW, "hash table overflow (distinct k-mer estimate too low)");
     if (ctx->h_ctr->smem_failed) FAIL(DSKGPU_ERR_OVERFLOW, "shared-memory table overflow at the deepest split (%u passes)", ctx->h_ctr->smem_failed);
     if (ctx->h_ctr->overflow) FAIL(DSKGPU_ERR_OVERFLOW, "solid k-mer buffer overflow");
@@ -858,16 +874,23 @@ template <int KW>
 static int finish_single(dskgpu_ctx* ctx)
 {
     int rc;
+    trace(nullptr);
     if ((rc = stage_totals(ctx))) return rc;
+    trace("totals (push kernels done)");
     if ((rc = fetch_local_bin_hist(ctx))) return rc;
+    trace("bin hist d2h");
     if ((rc = plan_partitions(ctx, ctx->h_bin_hist))) return rc;
+    trace("plan");
     const u32 P = ctx->nparts;
     if ((rc = ensure(ctx, ctx->precs, ctx->local_nrec * (u64)ctx->RW * 8 + 64))) return rc;
     std::vector<u64*> dst(P);
     u64 o = 0;
     for (u32 i = 0; i < P; i++) { dst[i] = (u64*)ctx->precs.p + o * ctx->RW; o += ctx->h_part_recs[i]; }
     if ((rc = stage_scatter<KW>(ctx, dst))) return rc;
-    return stage_count<KW>(ctx, (const u64*)ctx->precs.p, ctx->h_part_recs, ctx->h_part_kmers);
+    trace("scatter launched");
+    rc = stage_count<KW>(ctx, (const u64*)ctx->precs.p, ctx->h_part_recs, ctx->h_part_kmers);
+    trace("finish done");
+    return rc;
 }
 
 // multi-GPU: the partitions this rank owns sit in its receive buffer, in increasing partition id
@@ -1109,14 +1132,19 @@ static int64_t selftest_scan_fmt(const u8* raw, u64 lo, u64 hi, uint8_t* out, si
             if (e >= 0) ref[nref++] = (u8)e;
             pv = ch;
         }
-        // mask path emission
+        // mask path emission, through the same word-level compaction the kernel runs (word_codes: SWAR encode + byte permute)
         int n = 0;
-        for (int i = 0; i < SCAN_BPT; i++) if ((em >> i) & 1u) {
-            const u32 c = (words[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            const u8 code = (u8)(((sep >> i) & 1u) ? (u32)CODE_SEP : encode_fast(c));
-            if (n >= nref || ref[n] != code) return -1000000 - (int64_t)ci;       // emission differs from scan_step
-            if (w < out_cap) out[w] = code;
-            w++; n++;
+        for (int wi = 0; wi < 8; wi++) {
+            const u32 nib = (em >> (4 * wi)) & 0xFu;
+            if (!nib) continue;
+            const u32 packed = word_codes(words[wi], nib, (sep >> (4 * wi)) & 0xFu);
+            if (popc32(nib) < 4 && (packed >> (8 * popc32(nib)))) return -7000000 - (int64_t)ci;   // kernel ORs the words together
+            for (int j = 0; j < popc32(nib); j++) {
+                const u8 code = (u8)(packed >> (8 * j));
+                if (n >= nref || ref[n] != code) return -1000000 - (int64_t)ci;       // emission differs from scan_step
+                if (w < out_cap) out[w] = code;
+                w++; n++;
+            }
         }
         if (n != nref) return -2000000 - (int64_t)ci;
         if ((u32)n != tab_count(t, state)) return -3000000 - (int64_t)ci;          // table count differs

@@ -138,7 +138,7 @@ DSK_HD u32 mmer_value(u32 x, int m)
 // SURVEY.md appendix C).  Records are histogrammed into NBINS fine bins while they are produced; at finish the
 // host packs consecutive bins into partitions of the size the counting kernel wants (balanced on exact counts,
 // the job the reference gives to its sampled LPT table, K/PartiInfo.cpp:48-106).
-constexpr int NBINS_LOG2 = 17;
+constexpr int NBINS_LOG2 = 16;
 constexpr u32 NBINS = 1u << NBINS_LOG2;
 DSK_HD u32 bin_of(u32 minimizer)
 {

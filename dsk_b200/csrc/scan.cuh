@@ -224,6 +224,53 @@ DSK_HD u32 encode_fast(u32 c)
     return ((c >> 1) & 3u) | (ok ? 0u : (u32)CODE_INVALID);
 }
 
+// codes of 4 bytes at once: (c >> 1) & 3 per byte, | 4 in the bytes that are not one of ACGTacgt
+DSK_HD u32 encode4(u32 w)
+{
+    const u32 codes = (w >> 1) & 0x03030303u;
+    // expected upper-case letter of each code (A C T G for 0..3): bytes of 0x47544341 selected by the codes
+    u32 exp;
+#ifdef __CUDA_ARCH__
+    const u32 t = (codes | (codes >> 4)) & 0x00330033u;             // codes of bytes 0,1 / 2,3 as nibbles
+    exp = __byte_perm(0x47544341u, 0u, (t | (t >> 8)) & 0x3333u);
+#else
+    exp = 0;
+    for (int j = 0; j < 4; j++) exp |= ((0x47544341u >> (8 * ((codes >> (8 * j)) & 3u))) & 0xFFu) << (8 * j);
+#endif
+    const u32 x = (w & 0xDFDFDFDFu) ^ exp;                          // zero byte <=> valid base
+    const u32 nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+    return codes | (nz >> 5);
+}
+// byte-permute selector that moves the bytes whose bit is set in `nib` to the low end, in order
+DSK_HD u32 compact_sel(u32 nib)
+{
+    u32 sel = 0, pos = 0;
+#pragma unroll
+    for (u32 j = 0; j < 4; j++) { if ((nib >> j) & 1u) { sel |= j << (4 * pos); pos++; } }
+    return sel;
+}
+// host + device byte permute (low 4 selector nibbles, selecting among the 4 bytes of a)
+DSK_HD u32 perm4(u32 a, u32 sel)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, 0u, sel);
+#else
+    u32 r = 0;
+    for (int j = 0; j < 4; j++) r |= ((a >> (8 * ((sel >> (4 * j)) & 3u))) & 0xFFu) << (8 * j);
+    return r;
+#endif
+}
+
+// the emitted codes of one 4-byte word, packed to the low end: `nib` = bytes to emit, `sepnib` = those that are separators
+DSK_HD u32 word_codes(u32 w, u32 nib, u32 sepnib)
+{
+    u32 codes = encode4(w);
+    const u32 sm4 = ((sepnib * 0x00204081u) & 0x01010101u) * 0xFFu;        // 0xFF in the separator bytes
+    codes = (codes & ~sm4) | (0x08080808u & sm4);
+    if (nib == 0xFu) return codes;
+    return perm4(codes, compact_sel(nib)) & ((1u << (8 * popc32(nib))) - 1u);      // bytes beyond the emitted ones must be zero: callers OR them
+}
+
 // ---- device side ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
@@ -327,15 +374,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tables(const u8* __restri
     }
 }
 
-// pass B: chain the tile tables (single block of 1024 threads, each owning a contiguous run of tiles)
+// pass B: chain the tile tables (single block of 1024 threads, each owning a contiguous run of tiles; the 1024 run
+// tables are chained by a block-wide scan -- tables compose associatively)
+struct RunTab { u32 st; u32 cnt[4]; };          // st: 4 x 2 bits state_out per state_in; cnt: codes emitted per state_in (no overflow: u32 per chunk)
+__device__ __forceinline__ RunTab run_compose(const RunTab& f, const RunTab& g)   // f first, then g
+{
+    RunTab r; r.st = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const u32 m = (f.st >> (2 * s)) & 3u;
+        // no dynamic indexing of g.cnt (would go to local memory)
+        const u32 gc = m == 0 ? g.cnt[0] : m == 1 ? g.cnt[1] : m == 2 ? g.cnt[2] : g.cnt[3];
+        r.cnt[s] = f.cnt[s] + gc;
+        r.st |= ((g.st >> (2 * m)) & 3u) << (2 * s);
+    }
+    return r;
+}
+__device__ __forceinline__ RunTab run_shfl_up(const RunTab& t, int d)
+{
+    RunTab o; o.st = __shfl_up_sync(0xFFFFFFFFu, t.st, d);
+#pragma unroll
+    for (int s = 0; s < 4; s++) o.cnt[s] = __shfl_up_sync(0xFFFFFFFFu, t.cnt[s], d);
+    return o;
+}
+
 __global__ void __launch_bounds__(1024) k_scan_tiles(const TileTab* __restrict__ tabs, u64 ntiles, TileIn* tin, StreamState* ss,
                                                      const u8* raw, u64 lo, u64 hi)
 {
-    __shared__ u32 s_st[1024];
-    __shared__ u32 s_cnt[1024][4];
-    __shared__ u64 s_base[1024];
-    __shared__ u32 s_in[1024];
-    const int t = threadIdx.x;
+    __shared__ RunTab s_warp[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     u64 per = (ntiles + 1023) / 1024;
     u64 b = (u64)t * per, e = b + per; if (e > ntiles) e = ntiles; if (b > ntiles) b = ntiles;
     // phase 1: table of my run, for all 4 start states
@@ -343,30 +410,47 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const TileTab* __restrict__
     for (u64 i = b; i < e; i++) {
         TileTab tt = tabs[i];
 #pragma unroll
-        for (int s = 0; s < 4; s++) { cn[s] += tt.cnt[st[s]]; st[s] = (tt.st >> (2 * st[s])) & 3; }
-    }
-    s_st[t] = st[0] | (st[1] << 2) | (st[2] << 4) | (st[3] << 6);
-#pragma unroll
-    for (int s = 0; s < 4; s++) s_cnt[t][s] = cn[s];
-    __syncthreads();
-    // phase 2: thread 0 chains the 1024 run tables
-    if (t == 0) {
-        u32 s = ss->fsm_state; u64 base = 0;
-        for (int i = 0; i < 1024; i++) {
-            s_in[i] = s; s_base[i] = base;
-            base += s_cnt[i][s]; s = (s_st[i] >> (2 * s)) & 3;
+        for (int s = 0; s < 4; s++) {
+            const u32 m = st[s];
+            cn[s] += m == 0 ? tt.cnt[0] : m == 1 ? tt.cnt[1] : m == 2 ? tt.cnt[2] : tt.cnt[3];
+            st[s] = (tt.st >> (2 * m)) & 3;
         }
-        ss->fsm_state = s;
-        ss->total = ss->carry + base;
-        ss->prev_byte_next = (hi > lo) ? (int)raw[hi - 1] : ss->prev_byte;
+    }
+    RunTab mine; mine.st = st[0] | (st[1] << 2) | (st[2] << 4) | (st[3] << 6);
+#pragma unroll
+    for (int s = 0; s < 4; s++) mine.cnt[s] = cn[s];
+    // phase 2: inclusive scan of the run tables (warp shuffles, then the 32 warp totals)
+    RunTab inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { RunTab o = run_shfl_up(inc, d); if (lane >= d) inc = run_compose(o, inc); }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        RunTab w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { RunTab o = run_shfl_up(w, d); if (lane >= d) w = run_compose(o, w); }
+        s_warp[lane] = w;                                        // inclusive over warps
     }
     __syncthreads();
+    RunTab exl = run_shfl_up(inc, 1);                            // exclusive within the warp
+    if (lane == 0) { exl.st = 0xE4u; exl.cnt[0] = exl.cnt[1] = exl.cnt[2] = exl.cnt[3] = 0; }
+    if (warp > 0) exl = run_compose(s_warp[warp - 1], exl);
+    // my true start state and output base
+    const u32 s0 = ss->fsm_state;
+    u32 s = (exl.st >> (2 * s0)) & 3;
+    u64 base = s0 == 0 ? exl.cnt[0] : s0 == 1 ? exl.cnt[1] : s0 == 2 ? exl.cnt[2] : exl.cnt[3];
     // phase 3: replay my run with the true start state
-    u32 s = s_in[t]; u64 base = s_base[t];
     for (u64 i = b; i < e; i++) {
         TileTab tt = tabs[i];
         TileIn ti; ti.base = base; ti.state = s; ti.pad = 0; tin[i] = ti;
-        base += tt.cnt[s]; s = (tt.st >> (2 * s)) & 3;
+        base += s == 0 ? tt.cnt[0] : s == 1 ? tt.cnt[1] : s == 2 ? tt.cnt[2] : tt.cnt[3];
+        s = (tt.st >> (2 * s)) & 3;
+    }
+    __syncthreads();                                             // everybody has read ss->fsm_state
+    if (t == 1023) {
+        ss->fsm_state = s;
+        ss->total = ss->carry + base;
+        ss->prev_byte_next = (hi > lo) ? (int)raw[hi - 1] : ss->prev_byte;
     }
 }
 
@@ -395,12 +479,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_emit(const u8* __restrict
     u32 off = pad + tab_count(exl, ti.state);
     u32 em, sep, err;
     chunk_emit_masks<FMT>(m, prev_nl, next_flag, state, em, sep, err);
+    // compaction, a 4-byte word at a time: SWAR encode, byte-permute the emitted bytes to the front, append to a 64-bit
+    // accumulator; whole aligned words go out with one 32-bit store, only the ragged head / tail bytes are stored singly
+    {
+        u32* s_out32 = reinterpret_cast<u32*>(s_out);
+        const u32 head = off & 3u;                                 // bytes of the first aligned word that belong to my predecessor
+        u32 wpos = off >> 2;
+        u64 acc = 0; u32 fill = head; bool first = head != 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_BPT; i++) {
-        if ((em >> i) & 1u) {
-            const u32 c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            s_out[off++] = (u8)(((sep >> i) & 1u) ? (u32)CODE_SEP : encode_fast(c));
+        for (int i = 0; i < 8; i++) {
+            const u32 nib = (em >> (4 * i)) & 0xFu;
+            if (nib == 0) continue;
+            const u32 packed = word_codes(w[i], nib, (sep >> (4 * i)) & 0xFu);
+            acc |= (u64)packed << (8 * fill);
+            fill += (u32)__popc(nib);
+            if (fill >= 4) {
+                const u32 word = (u32)acc;
+                if (first) {                                       // bytes head..3 are mine
+                    for (u32 j = head; j < 4; j++) s_out[4 * wpos + j] = (u8)(word >> (8 * j));
+                    first = false;
+                } else s_out32[wpos] = word;
+                wpos++; acc >>= 32; fill -= 4;
+            }
         }
+        // tail: bytes [first ? head : 0, fill) of the last word
+        for (u32 j = first ? head : 0u; j < fill; j++) s_out[4 * wpos + j] = (u8)((u32)acc >> (8 * j));
     }
     // stats / errors
     const u32 nsep = __popc(sep & em), nbase = __popc(em) - nsep;

@@ -26,7 +26,7 @@ extern "C" {
 #define DSKGPU_HISTO_LEN     10001          /* bins 0..10000 (Histogram.hpp:92, length 10000) */
 #define DSKGPU_HISTO2D_DIM2  11             /* bins 0..10   (CountProcessorHistogram.hpp:173-184) */
 #define DSKGPU_MAX_KMER      63             /* KSIZE_LIST "32 64": k<32 -> 64-bit keys, k<64 -> 128-bit */
-#define DSKGPU_NBINS         131072         /* fine minimizer bins that are packed into partitions at finish */
+#define DSKGPU_NBINS         65536          /* fine minimizer bins that are packed into partitions at finish */
 
 /* error codes */
 enum {
