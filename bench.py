@@ -50,6 +50,19 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, args):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json, written by
+    tools/ncu_summary.py); only valid for the workload the capture was taken on (the default one)."""
+    default = (args.kmer_size == 31 and args.genome == 5_000_000 and args.coverage == 100 and args.read_len == 150)
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not default or not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get(kernel)
+    if not d or "dram__bytes_read.sum" not in d:
+        return None
+    return d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -324,6 +337,7 @@ def main():
         dom_bytes_per_launch = (ab["S2_expand"] + ab["S3_sort"]) * kmers * args.steps / max(1, dom_n)
         dom_avg_s = dom_ms / 1e3 / max(1, dom_n)
         achieved = dom_bytes_per_launch / dom_avg_s / 1e9 if dom_avg_s > 0 else 0.0
+        dom_kernel = "k_count_smem" if st["nb_parts_smem"] else ("k_hash_insert" if st["nb_groups_hash"] else "k_rs_onesweep")
         line = {
             "metric": "Gk-mers/s counted", "value": value, "unit": "Gk-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if args.kmer_size < 32 else "u128",
@@ -333,8 +347,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms": stage,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_count_smem" if st["nb_parts_smem"] else ("k_hash_insert" if st["nb_groups_hash"] else "k_rs_onesweep"), "launches": int(dom_n), "avg_launch_ms": 1e3 * dom_avg_s,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom_kernel, args),
+                         "kernel": dom_kernel, "launches": int(dom_n), "avg_launch_ms": 1e3 * dom_avg_s,
                          "peak_source": peak_src, "algorithmic_bytes_per_kmer": ab["S2_expand"] + ab["S3_sort"]},
             "pipeline_roofline": {"A_k_bytes_per_kmer": A, "achieved": value / world * A, "peak": peak, "unit": "GB/s", "frac": value / world * A / peak,
                                   "note": "whole step per GPU against SURVEY 8(d) A(k); the hash path moves fewer HBM bytes than A(k) assumes"},

@@ -63,3 +63,24 @@ with open(os.path.join(dst, "%s_ncu_full_summary.txt" % tag), "w") as out:
                 out.write("   %-90s %s %s\n" % (k, vals[i], units[i]))
         out.write("\n")
 print(open(os.path.join(dst, "%s_ncu_full_summary.txt" % tag)).read())
+
+# 3. DRAM traffic per launch of every captured kernel -> profiles/ncu_traffic.json (bench.py's roofline.traffic reads it;
+#    valid for the default bench workload the captures are taken on: C2, k=31)
+import json
+import re
+tj = os.path.join(dst, "ncu_traffic.json")
+traffic = json.load(open(tj)) if os.path.exists(tj) else {}
+cur = None
+MUL = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+for ln in open(os.path.join(dst, "%s_ncu_full_summary.txt" % tag)):
+    m = re.match(r"== prof_(\w+)\.ncu-rep", ln)
+    if m:
+        cur = m.group(1); traffic[cur] = {"tag": tag, "workload": "bench.py default (C2, k=31)"}
+        continue
+    f = ln.split()
+    if cur and len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
+        if f[0].startswith("dram"):
+            traffic[cur][f[0]] = float(f[1]) * MUL.get(f[2], 1)
+        else:
+            traffic[cur]["ncu_duration"] = "%s %s" % (f[1], f[2])
+json.dump(traffic, open(tj, "w"), indent=1, sort_keys=True)
