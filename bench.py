@@ -190,10 +190,13 @@ def main():
     ap.add_argument("--hash-log2-slots", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--device-synth", action="store_true", help="draw the read set on the device (3 Gbp-class workloads)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
-    workload = "synthetic %.0f Mbp genome, %dx %dbp reads, %.0f%% error, k=%d (BASELINE.json configs[1])" % (
+    workload = "synthetic %.0f Mbp genome, %dx %dbp reads, %.0f%% error, k=%d" % (
         args.genome / 1e6, args.coverage, args.read_len, args.err * 100, args.kmer_size)
+    if (args.genome, args.coverage, args.read_len, args.kmer_size) == (5_000_000, 100, 150, 31):
+        workload += " (BASELINE.json configs[1])"
 
     import torch
     if args.impl == "reference":
@@ -241,9 +244,19 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    pinned, n, nreads = make_workload(args, rank, world)
-    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
-    dev.copy_(pinned[:n], non_blocking=False)
+    if args.device_synth:
+        from dsk_b200.synth import reads_fasta_device
+        dev, nreads = reads_fasta_device(args.genome, args.coverage, args.read_len, args.err, seed=args.seed + 1000 * rank, device="cuda")
+        n = dev.numel()
+        pinned = None
+        if not (args.no_e2e and args.no_cpu_baseline):
+            pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            pinned.copy_(dev)
+        torch.cuda.empty_cache()
+    else:
+        pinned, n, nreads = make_workload(args, rank, world)
+        dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+        dev.copy_(pinned[:n], non_blocking=False)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -357,7 +370,7 @@ def main():
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(args, pinned, n)
+                line["cpu_baseline"] = cpu_baseline(args, pinned, n, sample_frac=min(1.0, 6e8 / max(1, n)))
             except Exception as ex:  # never lose the GPU line to a baseline hiccup
                 line["cpu_baseline"] = {"value": None, "unit": "Gk-mers/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % ex}
         print(json.dumps(line))

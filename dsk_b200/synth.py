@@ -80,3 +80,38 @@ def assembly_fasta(g, width=70, name=b"contig"):
     body[:, width] = 10
     tail = letters[nfull * width:].tobytes()
     return b">" + name + b"\n" + body.tobytes() + (tail + b"\n" if tail else b"")
+
+
+def reads_fasta_device(G, coverage=30, L=150, err=0.01, seed=42, device="cuda", batch=1 << 21):
+    """Same read model generated on the device with torch (benchmark plumbing for read sets too big to draw with numpy
+    in reasonable time: the 3 Gbp-class configurations).  Fixed-width headers ">r%09d" so that every record has the same
+    size and a batch is one 2-D tensor.  Returns (uint8 cuda tensor of FASTA bytes, nreads).  Not bit-identical to
+    reads_fasta() (different PRNG); parity at this scale is checked through size-independent properties."""
+    import torch
+    gen = torch.Generator(device=device); gen.manual_seed(seed)
+    g = torch.randint(0, 4, (G,), dtype=torch.uint8, device=device, generator=gen)
+    n = int(G * coverage // L)
+    W = 2 + 9 + 1 + L + 1
+    out = torch.empty(n * W, dtype=torch.uint8, device=device)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    ar = torch.arange(L, device=device, dtype=torch.int64)
+    pow10 = torch.tensor([10 ** (8 - j) for j in range(9)], device=device, dtype=torch.int64)
+    for b in range(0, n, batch):
+        m = min(batch, n - b)
+        starts = torch.randint(0, G - L + 1, (m,), device=device, generator=gen)
+        codes = g[starts[:, None] + ar[None, :]]
+        if err > 0:
+            mask = torch.rand((m, L), device=device, generator=gen) < err
+            shift = torch.randint(1, 4, (m, L), dtype=torch.uint8, device=device, generator=gen)
+            codes = torch.where(mask, (codes + shift) & 3, codes)
+        strand = torch.randint(0, 2, (m,), device=device, generator=gen).bool()
+        codes = torch.where(strand[:, None], 3 - codes.flip(1), codes)
+        blk = out[b * W:(b + m) * W].view(m, W)
+        blk[:, 0] = ord(">"); blk[:, 1] = ord("r")
+        ids = torch.arange(b, b + m, device=device, dtype=torch.int64)
+        blk[:, 2:11] = (48 + (ids[:, None] // pow10[None, :]) % 10).to(torch.uint8)
+        blk[:, 11] = 10
+        blk[:, 12:12 + L] = acgt[codes.long()]
+        blk[:, 12 + L] = 10
+        del codes, starts
+    return out, n
