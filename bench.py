@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--hash-log2-slots", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--histo2d", action="store_true", help="BASELINE.json configs[4]: bank 0 = the genome as an assembly, bank 1 = the reads, -histo2D 1")
     ap.add_argument("--device-synth", action="store_true", help="draw the read set on the device (3 Gbp-class workloads)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -197,6 +198,9 @@ def main():
         args.genome / 1e6, args.coverage, args.read_len, args.err * 100, args.kmer_size)
     if (args.genome, args.coverage, args.read_len, args.kmer_size) == (5_000_000, 100, 150, 31):
         workload += " (BASELINE.json configs[1])"
+    if args.histo2d:
+        workload = "-histo2D: %.0f Mbp assembly (bank 0) + %dx %dbp reads, %.0f%% error (bank 1), k=%d (BASELINE.json configs[4] shape)" % (
+            args.genome / 1e6, args.coverage, args.read_len, args.err * 100, args.kmer_size)
 
     import torch
     if args.impl == "reference":
@@ -244,9 +248,14 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev_asm = None
     if args.device_synth:
-        from dsk_b200.synth import reads_fasta_device
-        dev, nreads = reads_fasta_device(args.genome, args.coverage, args.read_len, args.err, seed=args.seed + 1000 * rank, device="cuda")
+        from dsk_b200.synth import reads_fasta_device, genome_device, assembly_fasta_device
+        gdev = genome_device(args.genome, seed=args.seed, device="cuda")
+        dev, nreads = reads_fasta_device(args.genome, args.coverage, args.read_len, args.err, seed=args.seed + 1000 * rank, device="cuda", genome=gdev)
+        if args.histo2d:
+            dev_asm = assembly_fasta_device(gdev)
+        del gdev
         n = dev.numel()
         pinned = None
         if not (args.no_e2e and args.no_cpu_baseline):
@@ -257,6 +266,15 @@ def main():
         pinned, n, nreads = make_workload(args, rank, world)
         dev = torch.empty(n, dtype=torch.uint8, device="cuda")
         dev.copy_(pinned[:n], non_blocking=False)
+        if args.histo2d:
+            from dsk_b200.synth import genome_codes, assembly_fasta
+            asm = assembly_fasta(genome_codes(args.genome, seed=args.seed))
+            dev_asm = torch.frombuffer(bytearray(asm), dtype=torch.uint8).cuda()
+    h_asm = None
+    if dev_asm is not None and not args.no_e2e:
+        h_asm = torch.empty(dev_asm.numel(), dtype=torch.uint8, pin_memory=True); h_asm.copy_(dev_asm)
+    bank_kw = dict(nb_banks=2, per_bank_counts=True, histo2d=True) if args.histo2d else {}
+    rb = 1 if args.histo2d else 0                      # bank id of the reads
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -265,14 +283,16 @@ def main():
         torch.cuda.synchronize()
 
     eng = GpuCounter(kmer_size=args.kmer_size, abundance_min=2, device=local, stream=stream.cuda_stream, count_mode=args.count_mode,
-                     hash_log2_slots=args.hash_log2_slots, keep_results_on_device=True, rank=rank, world_size=world)
+                     hash_log2_slots=args.hash_log2_slots, keep_results_on_device=True, rank=rank, world_size=world, **bank_kw)
 
     from dsk_b200.distributed import distributed_finish
     devobj = torch.device("cuda", local)
 
     def step_device():
         eng.reset()
-        eng.push_device_bytes(dev.data_ptr(), n, fmt="fasta")
+        if dev_asm is not None and rank == 0:             # the assembly enters the job once
+            eng.push_device_bytes(dev_asm.data_ptr(), dev_asm.numel(), bank=0, fmt="fasta")
+        eng.push_device_bytes(dev.data_ptr(), n, bank=rb, fmt="fasta")
         if world > 1:
             distributed_finish(eng, dist, devobj)
         else:
@@ -310,12 +330,14 @@ def main():
     e2e = None
     if not args.no_e2e:
         eng2 = GpuCounter(kmer_size=args.kmer_size, abundance_min=2, device=local, stream=stream.cuda_stream, count_mode=args.count_mode,
-                          hash_log2_slots=args.hash_log2_slots, keep_results_on_device=False, rank=rank, world_size=world)
+                          hash_log2_slots=args.hash_log2_slots, keep_results_on_device=False, rank=rank, world_size=world, **bank_kw)
         hptr = pinned.data_ptr()
 
         def step_e2e():
             eng2.reset()
-            eng2.push_bytes((hptr, n), fmt="fasta")
+            if h_asm is not None and rank == 0:
+                eng2.push_bytes((h_asm.data_ptr(), h_asm.numel()), bank=0, fmt="fasta")
+            eng2.push_bytes((hptr, n), bank=rb, fmt="fasta")
             if world > 1:
                 distributed_finish(eng2, dist, devobj)
             else:
@@ -335,7 +357,7 @@ def main():
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": kmers_all * args.steps / float(tt[0]) / 1e9, "unit": "Gk-mers/s", "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": d2h,
+        e2e = {"value": kmers_all * args.steps / float(tt[0]) / 1e9, "unit": "Gk-mers/s", "h2d_bytes_per_step": int(n) + (h_asm.numel() if h_asm is not None else 0), "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * float(tt[0]) / args.steps}
         eng2.close()
 
@@ -368,7 +390,7 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.histo2d:
             try:
                 line["cpu_baseline"] = cpu_baseline(args, pinned, n, sample_frac=min(1.0, 6e8 / max(1, n)))
             except Exception as ex:  # never lose the GPU line to a baseline hiccup

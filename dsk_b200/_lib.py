@@ -10,6 +10,7 @@ MAX_BANKS = 16
 HISTO_LEN = 10001
 HISTO2D_DIM2 = 11
 NBINS = 65536
+NBINS_MAX = 1 << 20
 
 ERR_NODEVICE = -6
 
@@ -48,7 +49,7 @@ SYMBOLS = [
     "dskgpu_finish", "dskgpu_num_partitions", "dskgpu_partition", "dskgpu_partition_device", "dskgpu_histogram",
     "dskgpu_get_stats", "dskgpu_reset", "dskgpu_destroy", "dskgpu_host_alloc", "dskgpu_host_free", "dskgpu_strerror",
     "dskgpu_last_error", "dskgpu_device_count", "dskgpu_abi_version",
-    "dskgpu_xchg_local_totals", "dskgpu_xchg_bin_hist", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
+    "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_bin_hist", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
     "dskgpu_xchg_open_peer", "dskgpu_xchg_set_peers", "dskgpu_xchg_scatter", "dskgpu_xchg_sync", "dskgpu_xchg_layout", "dskgpu_record_bytes",
     "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers",
 ]
@@ -90,6 +91,8 @@ def lib():
     L.dskgpu_last_error.argtypes = [C.c_void_p]
     L.dskgpu_last_error.restype = C.c_char_p
     L.dskgpu_xchg_local_totals.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
+    L.dskgpu_xchg_prepare.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg_set_global.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int)]
     L.dskgpu_xchg_bin_hist.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_part_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_uint32)]
     L.dskgpu_xchg_plan.argtypes = [C.c_void_p, C.c_void_p]

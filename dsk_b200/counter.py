@@ -151,8 +151,20 @@ def _xchg_methods():
         self._check(self.L.dskgpu_xchg_local_totals(self.h, C.byref(km), C.byref(nr)))
         return km.value, nr.value
 
+    def xchg_prepare(self):
+        v = np.zeros(4, dtype=np.uint64)
+        self._check(self.L.dskgpu_xchg_prepare(self.h, v.ctypes.data))
+        return v
+
+    def xchg_set_global(self, global4):
+        g = np.ascontiguousarray(global4, dtype=np.uint64)
+        lvl = C.c_int()
+        self._check(self.L.dskgpu_xchg_set_global(self.h, g.ctypes.data, C.byref(lvl)))
+        self._bin_level = lvl.value
+        return lvl.value
+
     def xchg_bin_hist(self):
-        h = np.zeros(2 * _lib.NBINS, dtype=np.uint64)
+        h = np.zeros(2 << self._bin_level, dtype=np.uint64)          # xchg_set_global comes first
         self._check(self.L.dskgpu_xchg_bin_hist(self.h, h.ctypes.data))
         return h
 
@@ -194,7 +206,7 @@ def _xchg_methods():
     def xchg_sync(self):
         self._check(self.L.dskgpu_xchg_sync(self.h))
 
-    for f in (xchg_local_totals, xchg_bin_hist, xchg_part_counts, xchg_plan, xchg_recv_buffer, xchg_ipc_handle, xchg_open_peer, xchg_set_peers,
+    for f in (xchg_local_totals, xchg_prepare, xchg_set_global, xchg_bin_hist, xchg_part_counts, xchg_plan, xchg_recv_buffer, xchg_ipc_handle, xchg_open_peer, xchg_set_peers,
               xchg_scatter, xchg_sync):
         setattr(GpuCounter, f.__name__, f)
 

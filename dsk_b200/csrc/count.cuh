@@ -195,10 +195,12 @@ __device__ __forceinline__ Kmer<KW> rec_kmer_at(const u64* r, int j, int k)
 
 template <int KW>
 __global__ void __launch_bounds__(256) k_hash_insert(const u64* __restrict__ recs, u64 rec_begin, u64 rec_end, int k,
-                                                     u64* keys, u32* counts, u32 smask, int nbanks, Counters* ctr)
+                                                     u64* keys, u32* counts, u32 smask, int nbanks, Counters* ctr,
+                                                     const unsigned long long* nrec_dev = nullptr /*optional: record count that lives on the device*/)
 {
     constexpr int RW = 2 * KW;
     constexpr int MAXNK = InsCfg<KW>::MAXNK;
+    if (nrec_dev) { const u64 e = rec_begin + *nrec_dev; if (e < rec_end) rec_end = e; }
     __shared__ __align__(16) u64 s_rec[8][32 * RW];
     __shared__ u8 s_owner[8][32 * MAXNK];
     __shared__ u16 s_off[8][32];
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
                 const u64 slot = (u64)g * SV + q;
                 for (int b = 0; b < sp.nbanks; b++) { cv[b] = counts[slot * sp.nbanks + b]; counts[slot * sp.nbanks + b] = 0; }
             }
+            if (discard == 2) ndist++;                               // density sample: occupied slots are all that matters
             if (!discard) {
                 ndist++;
                 int32_t sum = 0;
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
     if ((threadIdx.x & 31) == 0 && ndist) atomicAdd(&s_distinct, ndist);
     __syncthreads();
     flush_hist(s_hist, g_hist);
-    if (threadIdx.x == 0 && s_distinct) atomicAdd(&ctr->distinct_n, (unsigned long long)s_distinct);
+    if (threadIdx.x == 0 && s_distinct) atomicAdd(discard == 2 ? &ctr->sample_distinct : &ctr->distinct_n, (unsigned long long)s_distinct);
 }
 
 __global__ void k_fill_u64(u64* p, u64 n, u64 v)

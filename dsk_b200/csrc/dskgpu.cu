@@ -43,7 +43,8 @@ struct dskgpu_ctx {
     DevBuf ss, ctr, hist, hist2d, raw[2], codes, tabs, tin;
     DevBuf recs, meta;                               // staging records (input order)
     DevBuf precs;                                    // partitioned records
-    DevBuf cursor, dstbase, bin_hist, bin2part, jobs, work_ctr;
+    DevBuf cursor, dstbase, bin_hist, bin_fold, bin2part, jobs, work_ctr;
+    DevBuf sample_recs, stab_keys, stab_counts;      // density sample: selected records, small hash table
     DevBuf tkeys, tcounts;                           // hash table
     DevBuf skeys[2], svals[2];                       // solid (k-mer, abundance) ping-pong
     DevBuf keys[2], banks[2];                        // sort path ping-pong
@@ -63,7 +64,7 @@ struct dskgpu_ctx {
     std::vector<u64> h_part_recs, h_part_kmers;      // this rank's records / k-mers of every partition
     std::vector<u64> g_part_kmers;                   // whole-job k-mers of every partition
     std::vector<u32> h_bin2part;
-    unsigned long long* h_bin_hist = nullptr;        // pinned [2][NBINS]
+    unsigned long long* h_bin_hist = nullptr;        // pinned [2][1 << bin_level] (room for the finest level)
     u32 nparts = 0;
     u32 smem_cap = 0; int num_sms = 148;
     // multi-GPU
@@ -71,6 +72,10 @@ struct dskgpu_ctx {
     u64 my_nrec_owned = 0; std::vector<u64> owned_recs, owned_kmers;   // my partitions in my receive buffer (increasing id)
     std::vector<void*> ipc_opened;
     bool totals_done = false; u64 local_nrec = 0, local_nkm = 0;
+    u64 bytes_pushed = 0;                            // raw input bytes so far (sizes the density sample before the totals are known)
+    bool sample_queued = false; u64 sample_nkm = 0, sample_distinct = 0;
+    bool global_set = false; u64 g_total_kmers = 0; double density = 1.0; bool density_known = false;
+    int bin_level = NBINS_LOG2; bool hist_fetched = false;
     DevBuf sendbuf;
     dskgpu_stats st;
     // timing
@@ -191,9 +196,10 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     CK(cudaMallocHost((void**)&ctx->h_ss, sizeof(StreamState)));
     CK(cudaMallocHost((void**)&ctx->h_nrec_probe, 64));
     CK(cudaMallocHost((void**)&ctx->h_hist, sizeof(unsigned long long) * (DSKGPU_HISTO_LEN * (1 + DSKGPU_HISTO2D_DIM2))));
-    CK(cudaMallocHost((void**)&ctx->h_bin_hist, sizeof(unsigned long long) * 2 * NBINS));
+    CK(cudaMallocHost((void**)&ctx->h_bin_hist, sizeof(unsigned long long) * 2 * NBINS_FINE));
     int rc;
-    if ((rc = ensure(ctx, ctx->bin_hist, sizeof(unsigned long long) * 2 * NBINS))) return rc;
+    if ((rc = ensure(ctx, ctx->bin_hist, sizeof(unsigned long long) * 2 * NBINS_FINE))) return rc;
+    if ((rc = ensure(ctx, ctx->bin_fold, sizeof(unsigned long long) * 2 * (NBINS_FINE / 2)))) return rc;
     if ((rc = ensure(ctx, ctx->work_ctr, 64))) return rc;
     if ((rc = ensure(ctx, ctx->ss, sizeof(StreamState)))) return rc;
     if ((rc = ensure(ctx, ctx->ctr, sizeof(Counters)))) return rc;
@@ -242,11 +248,13 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     CK(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
     CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
     CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
-    CK(cudaMemsetAsync(ctx->bin_hist.p, 0, sizeof(unsigned long long) * 2 * NBINS, ctx->stream));
+    CK(cudaMemsetAsync(ctx->bin_hist.p, 0, sizeof(unsigned long long) * 2 * NBINS_FINE, ctx->stream));
     ctx->state = 0; ctx->cur_bank = -1; ctx->stream_open = false; ctx->pending_cr = 0;
     ctx->nrec_known = 0; ctx->k2_inflight = false; ctx->chunk_parity = 0;
     ctx->n_solid = 0; ctx->results_on_host = false; ctx->nparts = 0;
     ctx->xchg_planned = false; ctx->xchg_scattered = false; ctx->totals_done = false; ctx->local_nrec = ctx->local_nkm = 0;
+    ctx->bytes_pushed = 0; ctx->sample_queued = false; ctx->sample_nkm = ctx->sample_distinct = 0;
+    ctx->global_set = false; ctx->g_total_kmers = 0; ctx->density = 1.0; ctx->density_known = false; ctx->bin_level = NBINS_LOG2; ctx->hist_fetched = false;
     ctx->peer_recv.clear();
     ctx->ev_used = 0; ctx->spans.clear();
     u64 launches = 0;
@@ -259,7 +267,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
-                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->dstbase, &ctx->bin_hist, &ctx->bin2part, &ctx->jobs, &ctx->work_ctr,
+                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->dstbase, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->bin2part, &ctx->jobs, &ctx->work_ctr,
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
                      &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr, &ctx->sendbuf};
     for (DevBuf* b : all) b->release();
@@ -300,6 +308,7 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
     if (hi <= lo) return 0;
     const int fmt = ctx->cur_fmt;
     const u64 n = hi - lo;
+    ctx->bytes_pushed += n;
     const u64 tile_first = lo / SCAN_TILE;
     const u64 ntiles = (hi + SCAN_TILE - 1) / SCAN_TILE - tile_first;
     int rc;
@@ -622,7 +631,9 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
     u64 max_part = 0; for (size_t i = 0; i < np; i++) max_part = std::max(max_part, pkm[i]);
     if (mode == DSKGPU_COUNT_HASH) { while ((double)nslots * load_max < (double)max_part && nslots < ((u64)1 << 31)) nslots <<= 1; }
     if ((rc = init_table(nslots))) return rc;
+    // distinct / total: from the density sample when there is one, else measured on a first group sized for r = 1
     double r = 1.0; bool have_r = false;
+    if (ctx->density_known) { r = std::min(1.0, std::max(0.02, ctx->density * 1.3 + 0.01)); have_r = true; }
     size_t p = 0; int gi = 0;
     while (p < np) {
         const double capk = (double)nslots * load_max / r;
@@ -657,12 +668,69 @@ static float span_ms(dskgpu_ctx* ctx, int kind, u32* count = nullptr)
     return tot;
 }
 
+// ---- density sample: distinct / total k-mers of the job, estimated on whole bins ---------------------------------------
+// The records of the fine bins below a threshold (about SAMPLE_KMERS k-mers) are copied out, counted in a small hash
+// table and only the number of occupied slots is kept.  Every occurrence of a k-mer lies in the same bin, so the ratio is
+// unbiased for the job; it sizes the partitions (shared-memory table load) and the groups of the global hash path, the
+// job the reference gives to its sampling pass (K/RepartitionAlgorithm.cpp:395-492, K/ConfigurationAlgorithm.cpp:245-467).
+constexpr u64 SAMPLE_KMERS = 512 * 1024;
+constexpr u64 SAMPLE_KM_CAP = 1u << 20;
+constexpr u32 SAMPLE_SLOTS = 1u << 21;
+
+template <int KW>
+static int queue_sample(dskgpu_ctx* ctx)
+{
+    if (ctx->sample_queued) return 0;
+    ctx->sample_queued = true;
+    if (ctx->recs.p == nullptr || ctx->bytes_pushed == 0) return 0;
+    int rc;
+    if ((rc = ensure(ctx, ctx->sample_recs, SAMPLE_KM_CAP * (u64)ctx->RW * 8))) return rc;
+    if (ctx->stab_keys.p == nullptr) {
+        if ((rc = ensure(ctx, ctx->stab_keys, (size_t)SAMPLE_SLOTS * KW * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->stab_counts, (size_t)SAMPLE_SLOTS * 4))) return rc;
+        k_fill_u64<<<148 * 4, 256, 0, ctx->stream>>>((u64*)ctx->stab_keys.p, (u64)SAMPLE_SLOTS * KW, ~0ULL); LAUNCHED();
+        CK(cudaMemsetAsync(ctx->stab_counts.p, 0, (size_t)SAMPLE_SLOTS * 4, ctx->stream));
+    }
+    Counters* ctr = (Counters*)ctx->ctr.p;
+    // the exact k-mer total is still on the device: size the sample from the bytes pushed (~0.7 k-mers per FASTA byte)
+    const double est = std::max(1.0, (double)ctx->bytes_pushed * 0.7);
+    double f = (double)SAMPLE_KMERS / est;
+    u32 thresh = f >= 1.0 ? NBINS_FINE : (u32)std::max(1.0, f * (double)NBINS_FINE + 0.5);
+    k_sample_select<KW><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, &ctr->nrec, thresh,
+                                                                    (u64*)ctx->sample_recs.p, SAMPLE_KM_CAP, ctr); LAUNCHED();
+    k_hash_insert<KW><<<ctx->num_sms * 2, 256, 0, ctx->stream>>>((const u64*)ctx->sample_recs.p, 0, SAMPLE_KM_CAP, ctx->k, (u64*)ctx->stab_keys.p,
+                                                                  (u32*)ctx->stab_counts.p, SAMPLE_SLOTS - 1, 1, ctr, &ctr->sample_nrec); LAUNCHED();
+    SolidityParams sp; memset(&sp, 0, sizeof sp); sp.nbanks = 1;
+    k_hash_scan<KW, true><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((u64*)ctx->stab_keys.p, (u32*)ctx->stab_counts.p, SAMPLE_SLOTS, sp, 2, nullptr, nullptr, 0,
+                                                                      (unsigned long long*)ctx->hist.p, (unsigned long long*)ctx->hist2d.p, ctr); LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static bool use_smem_path(const dskgpu_ctx* ctx);
+static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers);
+
+// whole-job figures every rank plans from: k-mer total and density sample.  Picks the bin level.
+static void set_global(dskgpu_ctx* ctx, u64 g_kmers, u64 g_sample_kmers, u64 g_sample_distinct)
+{
+    ctx->g_total_kmers = g_kmers;
+    ctx->density_known = g_sample_kmers >= 4096;
+    ctx->density = ctx->density_known ? std::min(1.0, std::max(0.01, (double)g_sample_distinct / (double)g_sample_kmers)) : 1.0;
+    const u64 T = plan_target_kmers(ctx, g_kmers);
+    // bins of the chosen level should average a quarter of a partition, so that packing consecutive bins balances well
+    int L = NBINS_LOG2;
+    while (L < NBINS_FINE_LOG2 && ((u64)1 << L) * (T / 4 + 1) < g_kmers) L++;
+    ctx->bin_level = L;
+    ctx->global_set = true; ctx->hist_fetched = false;
+}
+
 // ---- stage 1: close the input, read the totals --------------------------------------------------------------------
 static int stage_totals(dskgpu_ctx* ctx)
 {
     if (ctx->totals_done) return 0;
     Counters* ctr = (Counters*)ctx->ctr.p;
     if (ctx->stream_open) close_stream(ctx);
+    { int rc = ctx->KW == 1 ? queue_sample<1>(ctx) : queue_sample<2>(ctx); if (rc) return rc; }
     CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_ss, ctx->ss.p, sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -672,6 +740,7 @@ static int stage_totals(dskgpu_ctx* ctx)
     if (ctx->h_ctr->kmers_valid != ctx->h_ctr->kmers_in_recs)
         FAIL(DSKGPU_ERR_OVERFLOW, "internal: %llu valid k-mers but %llu packed in records", ctx->h_ctr->kmers_valid, ctx->h_ctr->kmers_in_recs);
     ctx->local_nrec = ctx->h_ctr->nrec; ctx->local_nkm = ctx->h_ctr->kmers_valid;
+    ctx->sample_nkm = ctx->h_ctr->sample_nkm; ctx->sample_distinct = ctx->h_ctr->sample_distinct;
     ctx->st.nb_sequences = ctx->h_ss->nsep; ctx->st.nb_nucleotides = ctx->h_ss->nbase;
     ctx->st.kmers_nb_valid = ctx->local_nkm; ctx->st.nb_superkmers = ctx->local_nrec;
     ctx->st.superkmer_bytes = ctx->local_nrec * (u64)ctx->RW * 8;
@@ -682,8 +751,18 @@ static int stage_totals(dskgpu_ctx* ctx)
 // ---- stage 2: plan the partitions from the whole-job bin histogram ---------------------------------------------------
 static int fetch_local_bin_hist(dskgpu_ctx* ctx)
 {
-    CK(cudaMemcpyAsync(ctx->h_bin_hist, ctx->bin_hist.p, sizeof(unsigned long long) * 2 * NBINS, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->hist_fetched) return 0;
+    if (!ctx->global_set) set_global(ctx, ctx->local_nkm, ctx->sample_nkm, ctx->sample_distinct);
+    const int shift = NBINS_FINE_LOG2 - ctx->bin_level;
+    const u32 nb = 1u << ctx->bin_level;
+    const void* src = ctx->bin_hist.p;
+    if (shift) {
+        k_fold_bins<<<(2 * nb + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, shift, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
+        src = ctx->bin_fold.p;
+    }
+    CK(cudaMemcpyAsync(ctx->h_bin_hist, src, sizeof(unsigned long long) * 2 * nb, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hist_fetched = true;
     return 0;
 }
 
@@ -693,17 +772,19 @@ static bool use_smem_path(const dskgpu_ctx* ctx)
     return ctx->NB == 1 && (mode == DSKGPU_COUNT_AUTO || mode == DSKGPU_COUNT_SMEM) && ctx->smem_cap >= 64;
 }
 
-// k-mers a partition should hold.  Shared-memory path: 2 x the table slots (a 100x / 30x read set has 3-4 occurrences
-// per distinct k-mer, so the table ends up 50-65 % full; sparser data overflows and is split in two passes by the kernel;
-// measured on C2: 125 % -> 4.36 ms, 175 % -> 4.03 ms, 250 % -> 4.03 ms per 400 M k-mers).
+// k-mers a partition should hold.  Shared-memory path: what fills the table to ~52 % given the sampled density
+// (distinct / total k-mers: 0.26 for 100x reads at k=31, 0.47 at k=63, 0.43 for 30x reads).
 // Global-table path: a quarter of the table capacity, so that groups of partitions can be sized to the measured occupancy.
 static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers)
 {
     if (ctx->cfg.nb_partitions > 0) return std::max<u64>(1, (global_kmers + ctx->cfg.nb_partitions - 1) / (u64)ctx->cfg.nb_partitions);
     if (use_smem_path(ctx)) {
-        const char* e = getenv("DSKGPU_SMEM_T_PCT");                 // tuning knob: partition size in % of the table slots
-        const u64 pct = e ? (u64)std::max(10, atoi(e)) : 200;
-        return std::max<u64>(64, (u64)ctx->smem_cap * pct / 100);
+        // table load after the last insert = T * density / slots: 52 % is the measured optimum (C2: density 0.26, T = 200 % of
+        // the slots -> 4.03 ms; 125 % -> 4.36 ms; beyond 65 % overflows (= split passes) appear)
+        const char* e = getenv("DSKGPU_SMEM_LOAD_PCT");
+        const double load = (e ? (double)std::max(5, atoi(e)) : 52.0) / 100.0;
+        const double t = (double)ctx->smem_cap * load / ctx->density;
+        return (u64)std::min(std::max(t, 64.0), (double)ctx->smem_cap * 4.0);
     }
     const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 23;
     return std::max<u64>(((u64)1 << log2s) * 6 / 10 / 4, 4096);
@@ -711,18 +792,19 @@ static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers)
 
 // greedy packing of consecutive bins (the role of Repartitor::computeDistrib, K/PartiInfo.cpp:48-106, on exact counts);
 // every rank derives the same plan from the same global histogram.  P is padded to a multiple of the world size.
-static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh /*[2*NBINS] whole job*/)
+static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh /*[2 << bin_level] whole job*/)
 {
-    const unsigned long long* gk = gh + NBINS;
-    const unsigned long long* lr = ctx->h_bin_hist; const unsigned long long* lk = ctx->h_bin_hist + NBINS;
+    const u32 NB_ = 1u << ctx->bin_level;
+    const unsigned long long* gk = gh + NB_;
+    const unsigned long long* lr = ctx->h_bin_hist; const unsigned long long* lk = ctx->h_bin_hist + NB_;
     u64 total = 0;
-    for (u32 b = 0; b < NBINS; b++) total += gk[b];
+    for (u32 b = 0; b < NB_; b++) total += gk[b];
     const u64 T = plan_target_kmers(ctx, total);
-    ctx->h_bin2part.resize(NBINS);
+    ctx->h_bin2part.resize(NB_);
     ctx->g_part_kmers.clear(); ctx->h_part_recs.clear(); ctx->h_part_kmers.clear();
     u32* b2p = ctx->h_bin2part.data();
     u32 P = 0; u64 acc = 0, ar = 0, ak = 0;
-    for (u32 b = 0; b < NBINS; b++) {
+    for (u32 b = 0; b < NB_; b++) {
         const u64 km = gk[b];
         if (acc > 0 && acc + km > T) {
             ctx->g_part_kmers.push_back(acc); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
@@ -738,7 +820,7 @@ static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh /*[2*NB
     int rc;
     if ((rc = ensure(ctx, ctx->cursor, (size_t)P * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dstbase, (size_t)P * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->bin2part, (size_t)NBINS * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->bin2part, (size_t)NB_ * 4))) return rc;
     return 0;
 }
 
@@ -751,11 +833,11 @@ static int stage_scatter(dskgpu_ctx* ctx, const std::vector<u64*>& dst)
     SpanGuard g(ctx, SPAN_PART);
     CK(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)P * 8, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dstbase.p, dst.data(), (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->bin2part.p, ctx->h_bin2part.data(), (size_t)NBINS * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->bin2part.p, ctx->h_bin2part.data(), ctx->h_bin2part.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));          // dst may be a temporary
     const unsigned sb = (unsigned)std::min<u64>((ctx->local_nrec + SC_THREADS - 1) / SC_THREADS, (u64)ctx->num_sms * 32);
     k_part_scatter<KW><<<sb, SC_THREADS, 0, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, ctx->local_nrec,
-                                                          (const u32*)ctx->bin2part.p, (u64* const*)ctx->dstbase.p,
+                                                          (const u32*)ctx->bin2part.p, NBINS_FINE_LOG2 - ctx->bin_level, (u64* const*)ctx->dstbase.p,
                                                           (unsigned long long*)ctx->cursor.p); LAUNCHED();
     CK(cudaGetLastError());
     return 0;
@@ -784,7 +866,11 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
         // occupancy picks the path of every partition (K/SortingCountAlgorithm.cpp:1489-1497): shared-memory table when the
         // partition is within reach of a few split passes, else the global paths
         const bool smem = use_smem_path(ctx);
-        const u64 smem_max = (u64)ctx->smem_cap * 16;
+        // forced SMEM mode keeps everything within reach of four split levels; AUTO keeps what is expected to fit the table
+        // without a split (85 % full at the sampled density) and gives the rest to the global paths, which cost about two
+        // clean shared-memory passes -- less than one split
+        const u64 smem_max = ctx->cfg.count_mode == DSKGPU_COUNT_SMEM ? (u64)ctx->smem_cap * 16
+                           : (u64)std::max((double)ctx->smem_cap, (double)ctx->smem_cap * 0.85 / ctx->density);
         std::vector<SmemJob> jobs;
         std::vector<u64> off(np + 1, 0);
         std::vector<char> big(np, 0);
@@ -940,12 +1026,30 @@ int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records
     return DSKGPU_OK;
 }
 
+int dskgpu_xchg_prepare(dskgpu_ctx* ctx, uint64_t* local4)
+{
+    if (!ctx || !local4) return DSKGPU_ERR_ARG;
+    int rc = stage_totals(ctx); if (rc) return rc;
+    local4[0] = ctx->local_nkm; local4[1] = ctx->local_nrec; local4[2] = ctx->sample_nkm; local4[3] = ctx->sample_distinct;
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_set_global(dskgpu_ctx* ctx, const uint64_t* global4, int* log2_bins)
+{
+    if (!ctx || !global4) return DSKGPU_ERR_ARG;
+    if (!ctx->totals_done) FAIL(DSKGPU_ERR_STATE, "xchg_set_global before xchg_prepare");
+    set_global(ctx, global4[0], global4[2], global4[3]);
+    if (log2_bins) *log2_bins = ctx->bin_level;
+    return DSKGPU_OK;
+}
+
 int dskgpu_xchg_bin_hist(dskgpu_ctx* ctx, uint64_t* hist)
 {
     if (!ctx || !hist) return DSKGPU_ERR_ARG;
     int rc = stage_totals(ctx); if (rc) return rc;
+    if (!ctx->global_set) FAIL(DSKGPU_ERR_STATE, "xchg_bin_hist before xchg_set_global (the ranks must agree on the bin level)");
     if ((rc = fetch_local_bin_hist(ctx))) return rc;
-    memcpy(hist, ctx->h_bin_hist, sizeof(uint64_t) * 2 * NBINS);
+    memcpy(hist, ctx->h_bin_hist, sizeof(uint64_t) * ((size_t)2 << ctx->bin_level));
     return DSKGPU_OK;
 }
 

@@ -34,6 +34,9 @@ struct Counters {
     unsigned long long expand_cursor; // sort path: keys written
     unsigned int smem_splits;         // shared-memory path: table overflows answered by splitting a pass in two
     unsigned int smem_failed;         // shared-memory path: passes that still overflowed at the deepest split
+    unsigned long long sample_nrec;   // density sample: records / k-mers selected, distinct k-mers found among them
+    unsigned long long sample_nkm;
+    unsigned long long sample_distinct;
 };
 
 #ifdef __CUDACC__
@@ -44,7 +47,7 @@ template <int KW>
 __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict__ codes, const StreamState* __restrict__ ss,
                                                            int k, int m, int bank, u64* __restrict__ recs,
                                                            u32* __restrict__ rec_meta, u64 rec_cap, Counters* ctr,
-                                                           unsigned long long* __restrict__ bin_hist /*[2][NBINS] records, k-mers*/)
+                                                           unsigned long long* __restrict__ bin_hist /*[2][NBINS_FINE] records, k-mers*/)
 {
     constexpr int RW = 2 * KW;
     __shared__ u64 s_pk[SK_TP / 32 + 8];                         // 2-bit bases, MSB first, 32 per word
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
         const u32 bin = bin_of(s_lmn[i]);
         rec_meta[ri] = bin | (nk << 24);
         atomicAdd(&bin_hist[bin], 1ULL);
-        atomicAdd(&bin_hist[NBINS + bin], (unsigned long long)nk);
+        atomicAdd(&bin_hist[NBINS_FINE + bin], (unsigned long long)nk);
         nk_sum += nk;
     }
     nk_sum = __reduce_add_sync(0xFFFFFFFFu, nk_sum);
@@ -244,26 +247,61 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
 }
 
 // ---- K3: scatter records into partition order --------------------------------------------------------------------
-// bin2part[bin] = partition of a bin (planned on the host from the exact bin histogram); dst_base[p] = device
+// bin2part[bin >> bin_shift] = partition of a bin of the planned level (planned on the host from the exact bin histogram);
+// dst_base[p] = device
 // pointer (local or NVLink peer) where this rank's records of partition p start; cursor[p] = records already placed.
 // Partitions are small (a few thousand records) and there are tens of thousands of them, so a record takes one
 // L2 atomic on its partition's cursor and one 16/32-byte vector store.
 constexpr int SC_THREADS = 256;
 template <int KW>
 __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(const u64* __restrict__ recs, const u32* __restrict__ rec_meta, u64 nrec,
-                                                             const u32* __restrict__ bin2part, u64* const* __restrict__ dst_base,
+                                                             const u32* __restrict__ bin2part, int bin_shift, u64* const* __restrict__ dst_base,
                                                              unsigned long long* __restrict__ cursor)
 {
     constexpr int RW = 2 * KW;
     const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
     for (u64 i = (u64)blockIdx.x * SC_THREADS + threadIdx.x; i < nrec; i += (u64)gridDim.x * SC_THREADS) {
-        const u32 p = __ldg(bin2part + (rec_meta[i] & (NBINS - 1)));
+        const u32 p = __ldg(bin2part + ((rec_meta[i] & (NBINS_FINE - 1)) >> bin_shift));
         ulonglong2 a = src[(RW / 2) * i], b;
         if constexpr (RW == 4) b = src[2 * i + 1];
         const u64 d = atomicAdd(&cursor[p], 1ULL);
         ulonglong2* dst = reinterpret_cast<ulonglong2*>(dst_base[p]);
         if constexpr (RW == 2) dst[d] = a;
         else { dst[2 * d] = a; dst[2 * d + 1] = b; }
+    }
+}
+
+// fine bin histogram [2][NBINS_FINE] -> level histogram [2][NBINS_FINE >> shift]
+__global__ void k_fold_bins(const unsigned long long* __restrict__ fine, int shift, unsigned long long* __restrict__ out)
+{
+    const u32 nb = NBINS_FINE >> shift, per = 1u << shift;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * nb; i += gridDim.x * blockDim.x) {
+        const u32 half = i >= nb ? 1u : 0u, b = i - half * nb;
+        const unsigned long long* src = fine + (size_t)half * NBINS_FINE + ((size_t)b << shift);
+        unsigned long long acc = 0;
+        for (u32 j = 0; j < per; j++) acc += src[j];
+        out[i] = acc;
+    }
+}
+
+// density sample: the records of the fine bins below `thresh` are copied out (all occurrences of a k-mer share their
+// bin, so distinct / total of the sample estimates distinct / total of the job)
+template <int KW>
+__global__ void __launch_bounds__(256) k_sample_select(const u64* __restrict__ recs, const u32* __restrict__ rec_meta, const unsigned long long* nrec_dev,
+                                                       u32 thresh, u64* __restrict__ out, u64 km_cap, Counters* ctr)
+{
+    constexpr int RW = 2 * KW;
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(out);
+    const u64 nrec = *nrec_dev;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (u64)gridDim.x * blockDim.x) {
+        const u32 mt = rec_meta[i];
+        if ((mt & (NBINS_FINE - 1)) >= thresh) continue;
+        const unsigned long long nk = mt >> 24;
+        if (atomicAdd(&ctr->sample_nkm, nk) + nk > km_cap) { atomicAdd(&ctr->sample_nkm, ~nk + 1ULL); continue; }   // sample full (a record holds >= 1 k-mer,
+        const u64 d = atomicAdd(&ctr->sample_nrec, 1ULL);                                                              //  so records <= km_cap as well)
+#pragma unroll
+        for (int q = 0; q < RW / 2; q++) dst[(RW / 2) * d + q] = src[(RW / 2) * i + q];
     }
 }
 

@@ -4,7 +4,7 @@ Every rank parses its own slice of the reads; super-k-mer records are routed to 
 (owner(p) = p % world_size) by the partition-scatter kernel itself, which stores straight into the owners' HBM
 through CUDA-IPC peer pointers (NVLink P2P) -- the role the reference gives to its temp files
 (SuperKmerBinFiles, G/src/gatb/tools/storage/impl/Storage.cpp:310-589).  Only tiny metadata crosses
-torch.distributed: the minimizer-bin histogram (all-reduce, 1 MB), the per-partition count matrix (all-gather) and
+torch.distributed: four job totals and the minimizer-bin histogram (all-reduce, 1-16 MB), the per-partition count matrix (all-gather) and
 the IPC handles.
 """
 import ctypes as C
@@ -41,6 +41,9 @@ def distributed_finish(eng, dist, device):
     """Runs the exchange + local counting on every rank (call after the pushes).  Returns the gathered count matrix."""
     import torch
     W, rank = dist.get_world_size(), dist.get_rank()
+    g4 = torch.from_numpy(eng.xchg_prepare().astype(np.int64)).to(device)     # k-mers, records, density sample (k-mers, distinct)
+    dist.all_reduce(g4)                                                       # every rank picks the same bin level / partition size
+    eng.xchg_set_global(g4.cpu().numpy().astype(np.uint64))
     t = torch.from_numpy(eng.xchg_bin_hist().astype(np.int64)).to(device)      # (records, k-mers) per minimizer bin, 1 MB
     dist.all_reduce(t)                                                         # every rank plans the same partitions
     counts = eng.xchg_part_counts(t.cpu().numpy().astype(np.uint64))
@@ -74,6 +77,9 @@ def distributed_finish(eng, dist, device):
 def in_process_finish(engines):
     """Same protocol for several contexts living in ONE process (tests: N 'ranks' on one GPU, no IPC needed)."""
     W = len(engines)
+    g4 = np.sum([e.xchg_prepare() for e in engines], axis=0, dtype=np.uint64)
+    for e in engines:
+        e.xchg_set_global(g4)
     gh = np.sum([e.xchg_bin_hist() for e in engines], axis=0, dtype=np.uint64)
     allc = np.stack([e.xchg_part_counts(gh) for e in engines])
     for e in engines:

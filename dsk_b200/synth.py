@@ -82,14 +82,35 @@ def assembly_fasta(g, width=70, name=b"contig"):
     return b">" + name + b"\n" + body.tobytes() + (tail + b"\n" if tail else b"")
 
 
-def reads_fasta_device(G, coverage=30, L=150, err=0.01, seed=42, device="cuda", batch=1 << 21):
+def genome_device(G, seed=42, device="cuda"):
+    import torch
+    gen = torch.Generator(device=device); gen.manual_seed(seed)
+    return torch.randint(0, 4, (G,), dtype=torch.uint8, device=device, generator=gen)
+
+
+def assembly_fasta_device(g, width=70):
+    """the genome as one multi-line FASTA record, built on the device (bank 0 of the -histo2D configuration)"""
+    import torch
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=g.device)
+    head = torch.tensor(list(b">contig\n"), dtype=torch.uint8, device=g.device)
+    nfull = g.numel() // width
+    body = torch.empty((nfull, width + 1), dtype=torch.uint8, device=g.device)
+    body[:, :width] = acgt[g[:nfull * width].long()].view(nfull, width)
+    body[:, width] = 10
+    tail = acgt[g[nfull * width:].long()]
+    nl = torch.tensor([10], dtype=torch.uint8, device=g.device)
+    return torch.cat([head, body.view(-1)] + ([tail, nl] if tail.numel() else []))
+
+
+def reads_fasta_device(G, coverage=30, L=150, err=0.01, seed=42, device="cuda", batch=1 << 21, genome=None):
     """Same read model generated on the device with torch (benchmark plumbing for read sets too big to draw with numpy
     in reasonable time: the 3 Gbp-class configurations).  Fixed-width headers ">r%09d" so that every record has the same
     size and a batch is one 2-D tensor.  Returns (uint8 cuda tensor of FASTA bytes, nreads).  Not bit-identical to
     reads_fasta() (different PRNG); parity at this scale is checked through size-independent properties."""
     import torch
-    gen = torch.Generator(device=device); gen.manual_seed(seed)
-    g = torch.randint(0, 4, (G,), dtype=torch.uint8, device=device, generator=gen)
+    gen = torch.Generator(device=device); gen.manual_seed(seed + 1)
+    g = genome if genome is not None else genome_device(G, seed, device)
+    G = g.numel()
     n = int(G * coverage // L)
     W = 2 + 9 + 1 + L + 1
     out = torch.empty(n * W, dtype=torch.uint8, device=device)

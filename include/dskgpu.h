@@ -26,7 +26,8 @@ extern "C" {
 #define DSKGPU_HISTO_LEN     10001          /* bins 0..10000 (Histogram.hpp:92, length 10000) */
 #define DSKGPU_HISTO2D_DIM2  11             /* bins 0..10   (CountProcessorHistogram.hpp:173-184) */
 #define DSKGPU_MAX_KMER      63             /* KSIZE_LIST "32 64": k<32 -> 64-bit keys, k<64 -> 128-bit */
-#define DSKGPU_NBINS         65536          /* fine minimizer bins that are packed into partitions at finish */
+#define DSKGPU_NBINS         65536          /* minimizer bins packed into partitions at finish: the coarsest level ... */
+#define DSKGPU_NBINS_MAX     (1u << 20)     /* ... and the finest (multi-G k-mer jobs); the level is picked from the job size */
 
 /* error codes */
 enum {
@@ -164,6 +165,9 @@ int  dskgpu_abi_version(void);
 
 /* ---- multi-GPU exchange (replaces the SuperKmerBinFiles temp tier, Storage.cpp:310-589) --------------
  * One context per rank (one process per GPU).  Partition p is owned by rank p % world_size.  After all pushes:
+ *   0. xchg_prepare             -> this rank's {k-mers, records, density-sample k-mers, density-sample distinct}; all-reduce
+ *                                  (sum) the four numbers out of band, hand the sums to xchg_set_global: every rank then
+ *                                  agrees on the bin level (2^16 .. 2^20 bins) and on the partition size
  *   1. xchg_bin_hist            -> this rank's (records, k-mers) per minimizer bin; all-reduce (sum) it out of band
  *                                  (torch.distributed / NCCL): every rank then plans the same partitions
  *   2. xchg_part_counts         -> per-partition record / k-mer counts of this rank; all-gather them
@@ -174,11 +178,13 @@ int  dskgpu_abi_version(void);
  *                                  scatter and the all-to-all are the same kernel, there is no send staging
  *   5. xchg_sync, barrier out of band, then dskgpu_finish counts the owned partitions locally. */
 int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records);
-/* hist[0..NBINS) = records, hist[NBINS..2*NBINS) = k-mers of every bin on this rank */
-int dskgpu_xchg_bin_hist(dskgpu_ctx* ctx, uint64_t* hist /*[2*DSKGPU_NBINS]*/);
+int dskgpu_xchg_prepare(dskgpu_ctx* ctx, uint64_t* local4 /*[4]*/);
+int dskgpu_xchg_set_global(dskgpu_ctx* ctx, const uint64_t* global4 /*[4] sums over ranks*/, int* log2_bins /*out: B = 1 << *log2_bins*/);
+/* hist[0..B) = records, hist[B..2*B) = k-mers of every bin on this rank */
+int dskgpu_xchg_bin_hist(dskgpu_ctx* ctx, uint64_t* hist /*[2*B]*/);
 /* plans the partitions from the whole-job histogram (sum over ranks); counts[0..P) = records, counts[P..2P) = k-mers of
  * each partition on this rank; pass counts = NULL to query P */
-int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, const uint64_t* global_hist /*[2*DSKGPU_NBINS]*/, uint64_t* counts, uint32_t* nparts);
+int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, const uint64_t* global_hist /*[2*B]*/, uint64_t* counts, uint32_t* nparts);
 int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts /*[world_size][2*P], row = rank*/);
 int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes);
 int dskgpu_xchg_ipc_handle(dskgpu_ctx* ctx, void* handle64 /*cudaIpcMemHandle_t of the receive buffer*/);

@@ -13,3 +13,4 @@ DSKGPU_TRACE=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baselin
 timeout 600 python bench.py --steps 5 --warmup 3 --kmer-size 63 > "$OUT/bench_k63.json" 2> "$OUT/bench_k63.err"; tail -c 3000 "$OUT/bench_k63.json"
 timeout 600 python bench.py --steps 3 --warmup 3 --genome 125000000 --coverage 30 --device-synth --no-e2e --no-cpu-baseline > "$OUT/bench_g125m.json" 2> "$OUT/bench_g125m.err"; tail -c 3000 "$OUT/bench_g125m.json"; tail -5 "$OUT/bench_g125m.err"
 timeout 600 python bench.py --steps 3 --warmup 3 --genome 125000000 --coverage 30 --device-synth --no-e2e --no-cpu-baseline --kmer-size 63 > "$OUT/bench_g125m_k63.json" 2> "$OUT/bench_g125m_k63.err"; tail -c 3000 "$OUT/bench_g125m_k63.json"; tail -5 "$OUT/bench_g125m_k63.err"
+timeout 900 python bench.py --steps 2 --warmup 2 --histo2d --genome 100000000 --coverage 50 --device-synth --no-e2e > "$OUT/bench_c5_histo2d.json" 2> "$OUT/bench_c5_histo2d.err"; tail -c 2500 "$OUT/bench_c5_histo2d.json"; tail -5 "$OUT/bench_c5_histo2d.err"
