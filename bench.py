@@ -377,7 +377,8 @@ def main():
             "metric": "Gk-mers/s counted", "value": value, "unit": "Gk-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if args.kmer_size < 32 else "u128",
             "data": "synthetic",
-            "config": {"workload": workload, "kmers_per_step_per_gpu": int(kmers), "input_bytes_per_gpu": int(n), "count_mode": args.count_mode,
+            "config": {"workload": workload, "kmers_per_step_per_gpu": int(kmers), "input_bytes_per_gpu": int(n), "count_mode": args.count_mode, "sampled_density": st["density_ppm"] / 1e6, "log2_bins": st["log2_bins"], "partitions": int(st["nb_partitions"]),
+                       "smem_partitions": int(st["nb_parts_smem"]), "smem_splits": int(st["nb_smem_splits"]),
                        "l2_policy": "inputs (%.0f MB) larger than the 126 MB L2; no flush" % (n / 1e6), "parallelism": "1 rank per GPU, partitions sharded by id"},
             "gpu_launches": int(launches),
             "clocks": clocks,

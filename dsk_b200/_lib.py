@@ -23,7 +23,7 @@ class Config(C.Structure):
         ("solid_vec", C.c_uint8 * MAX_BANKS),
         ("histo2d", C.c_int32), ("device", C.c_int32), ("count_mode", C.c_int32), ("hash_log2_slots", C.c_int32),
         ("nb_partitions", C.c_int32), ("keep_results_on_device", C.c_int32),
-        ("stream", C.c_void_p), ("rank", C.c_int32), ("world_size", C.c_int32), ("push_chunk_bytes", C.c_int32), ("smem_table_slots", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("stream", C.c_void_p), ("rank", C.c_int32), ("world_size", C.c_int32), ("push_chunk_bytes", C.c_int32), ("smem_table_slots", C.c_int32), ("bank_histograms", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -36,7 +36,7 @@ class Stats(C.Structure):
         ("ms_parse", C.c_float), ("ms_superk", C.c_float), ("ms_partition", C.c_float), ("ms_count", C.c_float),
         ("ms_sort", C.c_float), ("ms_total", C.c_float), ("ms_dominant_kernel", C.c_float),
         ("dominant_kernel_launches", C.c_uint32), ("nb_parts_smem", C.c_uint32), ("nb_smem_splits", C.c_uint32),
-        ("smem_table_slots", C.c_uint32), ("reserved", C.c_uint32 * 4),
+        ("smem_table_slots", C.c_uint32), ("density_ppm", C.c_uint32), ("log2_bins", C.c_uint32), ("reserved", C.c_uint32 * 2),
     ]
 
     def as_dict(self):
@@ -47,6 +47,7 @@ class Stats(C.Structure):
 SYMBOLS = [
     "dskgpu_config_default", "dskgpu_create", "dskgpu_push_bytes", "dskgpu_push_device_bytes", "dskgpu_push_reads",
     "dskgpu_finish", "dskgpu_num_partitions", "dskgpu_partition", "dskgpu_partition_device", "dskgpu_histogram",
+    "dskgpu_recount", "dskgpu_bank_histograms",
     "dskgpu_get_stats", "dskgpu_reset", "dskgpu_destroy", "dskgpu_host_alloc", "dskgpu_host_free", "dskgpu_strerror",
     "dskgpu_last_error", "dskgpu_device_count", "dskgpu_abi_version",
     "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_bin_hist", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
@@ -79,6 +80,8 @@ def lib():
     L.dskgpu_partition_device.argtypes = [C.c_void_p, C.c_int, P(C.c_void_p), P(C.c_void_p), P(C.c_uint64), P(C.c_int)]
     L.dskgpu_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.dskgpu_get_stats.argtypes = [C.c_void_p, P(Stats)]
+    L.dskgpu_recount.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_bank_histograms.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_reset.argtypes = [C.c_void_p]
     L.dskgpu_destroy.argtypes = [C.c_void_p]
     L.dskgpu_destroy.restype = None

@@ -22,7 +22,7 @@ class GpuCounter:
     def __init__(self, kmer_size=31, abundance_min=2, abundance_max=2**31 - 1, nb_banks=1, per_bank_counts=False,
                  solidity_kind="sum", solid_vec=None, histo2d=False, minimizer_size=10, device=0, count_mode="auto",
                  hash_log2_slots=0, nb_partitions=0, keep_results_on_device=False, stream=None, rank=0, world_size=1, push_chunk_bytes=0,
-                 smem_table_slots=0):
+                 smem_table_slots=0, bank_histograms=False):
         self.L = _lib.lib()
         cfg = _lib.Config()
         self.L.dskgpu_config_default(C.byref(cfg))
@@ -49,6 +49,7 @@ class GpuCounter:
         cfg.rank, cfg.world_size = rank, world_size
         cfg.push_chunk_bytes = push_chunk_bytes
         cfg.smem_table_slots = smem_table_slots
+        cfg.bank_histograms = int(bank_histograms)
         self.cfg = cfg
         self.k = kmer_size
         self.h = C.c_void_p()
@@ -91,6 +92,17 @@ class GpuCounter:
 
     def reset(self):
         self._check(self.L.dskgpu_reset(self.h))
+
+    def recount(self, abundance_min):
+        """second pass of -abundance-min auto: same partitions (still in HBM), new thresholds"""
+        a = list(abundance_min) + [abundance_min[-1]] * (_lib.MAX_BANKS - len(abundance_min))
+        arr = (C.c_int64 * _lib.MAX_BANKS)(*a)
+        self._check(self.L.dskgpu_recount(self.h, arr))
+
+    def bank_histograms(self):
+        h = np.zeros((max(1, self.cfg.nb_banks if self.cfg.per_bank_counts else 1), _lib.HISTO_LEN), np.uint64)
+        self._check(self.L.dskgpu_bank_histograms(self.h, h.ctypes.data))
+        return h
 
     # -- results ------------------------------------------------------------------------------------
     def solid(self):

@@ -26,6 +26,7 @@ struct SolidityParams {
     long long amin[MAXB];
     long long amax;
     unsigned char solid_vec[MAXB];
+    unsigned long long* bank_hist; // optional [nbanks][10001]: histogram of every bank's own count (CountProcessorCutoff with N banks)
 };
 
 #ifdef __CUDACC__
@@ -45,6 +46,9 @@ __device__ __forceinline__ bool process_counts(const u32* cv, const SolidityPara
     *sum_out = sum;
     u32 bin = histo_bin(sum);
     if (bin) { if (bin < HIST_SMEM_BINS) atomicAdd(&s_hist[bin], 1u); else atomicAdd(&g_hist[bin], 1ULL); }
+    if (sp.bank_hist) {                                              // CountProcessorCutoff.hpp:113-116: bank i sees count[i]
+        for (int b = 0; b < nb; b++) { const u32 bb = histo_bin((int32_t)cv[b]); if (bb) atomicAdd(&sp.bank_hist[(size_t)b * 10001u + bb], 1ULL); }
+    }
     if (sp.histo2d) {
         u32 i1 = (u32)(sum - (int32_t)cv[0]) & 0xFFFFu, i2 = cv[0] & 0xFFFFu;
         if (i1 >= 10000u) i1 = 10000u;

@@ -39,7 +39,10 @@ constexpr int CS_MAX_SPLIT = 10;               // up to 1024 sub-passes before t
 constexpr int CS_Q = 4;                        // k-mers per work item
 constexpr int CS_QCAP = 64;                    // retry queue entries per warp
 
-struct SmemJob { unsigned long long rec_begin; unsigned int nrec; unsigned int pad; };
+// split0: the job starts as 2^split0 sub-passes (the host knows the partition's k-mers and the sampled density, so a
+// partition that cannot fit the table is never tried in one pass first)
+struct SmemJob { unsigned long long rec_begin; unsigned int nrec; unsigned int split0; };
+constexpr int CS_MAX_SPLIT0 = 4;
 
 // bytes of dynamic shared memory for a table of `cap` slots (host + device agree through this one function):
 // table keys + counts, record staging [warps][32][RW], retry queue [warps][QCAP] keys + slots
@@ -170,9 +173,12 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
         const u32 nrec = jobs[job].nrec, nchunks = (nrec + CS_CHUNK - 1) / CS_CHUNK;
 
         // depth-first over (split level, residue) work items; uniform across the CTA
-        u32 stack[CS_MAX_SPLIT + 2];
+        u32 stack[CS_MAX_SPLIT + 2 + (1 << CS_MAX_SPLIT0)];
         int sp = 0;
-        stack[sp++] = 0;
+        {
+            const u32 l0 = min(jobs[job].split0, (u32)CS_MAX_SPLIT0);
+            for (u32 r = (1u << l0); r-- > 0;) stack[sp++] = (l0 << 16) | r;
+        }
         while (sp > 0) {
             const u32 item = stack[--sp];
             const u32 lvl = item >> 16, res = item & 0xFFFFu, smask = (1u << lvl) - 1u;

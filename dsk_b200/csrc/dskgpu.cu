@@ -40,7 +40,7 @@ struct dskgpu_ctx {
     int state = 0;                                   // 0 accepting pushes, 1 finished
     std::string err;
     // device state
-    DevBuf ss, ctr, hist, hist2d, raw[2], codes, tabs, tin;
+    DevBuf ss, ctr, hist, hist2d, bank_hist, raw[2], codes, tabs, tin;
     DevBuf recs, meta;                               // staging records (input order)
     DevBuf precs;                                    // partitioned records
     DevBuf cursor, dstbase, bin_hist, bin_fold, bin2part, jobs, work_ctr;
@@ -205,6 +205,7 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     if ((rc = ensure(ctx, ctx->ctr, sizeof(Counters)))) return rc;
     if ((rc = ensure(ctx, ctx->hist, sizeof(unsigned long long) * DSKGPU_HISTO_LEN))) return rc;
     if ((rc = ensure(ctx, ctx->hist2d, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2))) return rc;
+    if (ctx->NB > 1 && cfg->bank_histograms && (rc = ensure(ctx, ctx->bank_hist, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * (size_t)ctx->NB))) return rc;
     // dynamic shared memory opt-in for the one-sweep kernels
     const int smem1 = RsCfg<1>::TILE * 8 + RsCfg<1>::TILE * 4, smem2 = RsCfg<2>::TILE * 16 + RsCfg<2>::TILE * 4;
     CK(cudaFuncSetAttribute(k_rs_onesweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
@@ -248,6 +249,7 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     CK(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
     CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
     CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
+    if (ctx->bank_hist.p) CK(cudaMemsetAsync(ctx->bank_hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * (size_t)ctx->NB, ctx->stream));
     CK(cudaMemsetAsync(ctx->bin_hist.p, 0, sizeof(unsigned long long) * 2 * NBINS_FINE, ctx->stream));
     ctx->state = 0; ctx->cur_bank = -1; ctx->stream_open = false; ctx->pending_cr = 0;
     ctx->nrec_known = 0; ctx->k2_inflight = false; ctx->chunk_parity = 0;
@@ -266,7 +268,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
 {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
+    DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->bank_hist, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
                      &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->dstbase, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->bin2part, &ctx->jobs, &ctx->work_ctr,
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
                      &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr, &ctx->sendbuf};
@@ -531,6 +533,7 @@ static SolidityParams make_sp(dskgpu_ctx* ctx)
     sp.kind = ctx->cfg.solidity_kind; sp.nbanks = ctx->NB; sp.histo2d = ctx->cfg.histo2d;
     for (int i = 0; i < MAXB; i++) { sp.amin[i] = ctx->cfg.abundance_min[i]; sp.solid_vec[i] = ctx->cfg.solid_vec[i]; }
     sp.amax = ctx->cfg.abundance_max;
+    sp.bank_hist = (ctx->NB > 1 && ctx->bank_hist.p) ? (unsigned long long*)ctx->bank_hist.p : nullptr;
     if (sp.nbanks == 1) sp.kind = DSKGPU_SOLIDITY_SUM;          // ConfigurationAlgorithm.cpp:261-264
     return sp;
 }
@@ -630,6 +633,12 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
     // on the first group (sized for the worst case r = 1).
     u64 max_part = 0; for (size_t i = 0; i < np; i++) max_part = std::max(max_part, pkm[i]);
     if (mode == DSKGPU_COUNT_HASH) { while ((double)nslots * load_max < (double)max_part && nslots < ((u64)1 << 31)) nslots <<= 1; }
+    if (ctx->cfg.hash_log2_slots <= 0) {
+        // a call that covers little (a few heavy partitions next to the shared-memory path) gets a table to match:
+        // initialising and sweeping 2^23 slots would cost more than the counting itself
+        u64 tot = 0; for (size_t i = 0; i < np; i++) tot += pkm[i];
+        while (nslots > ((u64)1 << 16) && (double)(nslots >> 1) * load_max >= (double)tot) nslots >>= 1;
+    }
     if ((rc = init_table(nslots))) return rc;
     // distinct / total: from the density sample when there is one, else measured on a first group sized for r = 1
     double r = 1.0; bool have_r = false;
@@ -853,6 +862,7 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
     u64 nrec = 0, nkm = 0;
     for (size_t i = 0; i < np; i++) { nrec += prec[i]; nkm += pkm[i]; }
     ctx->st.smem_table_slots = ctx->smem_cap;
+    ctx->st.density_ppm = ctx->density_known ? (u32)(ctx->density * 1e6) : 0u; ctx->st.log2_bins = (u32)ctx->bin_level;
     if (nrec) {
         // capacity of the solid set: every solid k-mer holds at least min(abundance_min) occurrences
         long long amin = ctx->cfg.abundance_min[0];
@@ -866,24 +876,30 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
         // occupancy picks the path of every partition (K/SortingCountAlgorithm.cpp:1489-1497): shared-memory table when the
         // partition is within reach of a few split passes, else the global paths
         const bool smem = use_smem_path(ctx);
-        // forced SMEM mode keeps everything within reach of four split levels; AUTO keeps what is expected to fit the table
-        // without a split (85 % full at the sampled density) and gives the rest to the global paths, which cost about two
-        // clean shared-memory passes -- less than one split
-        const u64 smem_max = ctx->cfg.count_mode == DSKGPU_COUNT_SMEM ? (u64)ctx->smem_cap * 16
-                           : (u64)std::max((double)ctx->smem_cap, (double)ctx->smem_cap * 0.85 / ctx->density);
+        // a partition expected to fill the table beyond 75 % (k-mers x sampled density) starts as 2^split0 sub-passes over
+        // hash residues; beyond 16 sub-passes it goes to the global paths.  Forced SMEM mode (tests) starts everything in one
+        // pass and lets the kernel discover the splits.
+        const bool presplit = ctx->cfg.count_mode != DSKGPU_COUNT_SMEM;
+        const double fit = std::max(64.0, (double)ctx->smem_cap * 0.75 / ctx->density);     // k-mers one pass can take
+        const u64 smem_max = presplit ? (u64)(fit * (double)(1 << CS_MAX_SPLIT0)) : (u64)ctx->smem_cap * 16;
         std::vector<SmemJob> jobs;
         std::vector<u64> off(np + 1, 0);
         std::vector<char> big(np, 0);
         for (size_t i = 0; i < np; i++) {
             off[i + 1] = off[i] + prec[i];
             if (prec[i] == 0) continue;
-            if (smem && pkm[i] <= smem_max && prec[i] < 0xFFFFFFFFull) { SmemJob j; j.rec_begin = off[i]; j.nrec = (unsigned)prec[i]; j.pad = 0; jobs.push_back(j); }
+            if (smem && pkm[i] <= smem_max && prec[i] < 0xFFFFFFFFull) {
+                SmemJob j; j.rec_begin = off[i]; j.nrec = (unsigned)prec[i]; j.split0 = 0;
+                if (presplit) while (j.split0 < (unsigned)CS_MAX_SPLIT0 && (double)pkm[i] > fit * (double)(1u << j.split0)) j.split0++;
+                jobs.push_back(j);
+            }
             else big[i] = 1;
         }
         trace("jobs built");
         SpanGuard g(ctx, SPAN_COUNT);
         if (!jobs.empty()) {
-            std::sort(jobs.begin(), jobs.end(), [](const SmemJob& a, const SmemJob& b) { return a.nrec > b.nrec; });   // longest first
+            std::sort(jobs.begin(), jobs.end(), [](const SmemJob& a, const SmemJob& b) {                               // longest first
+                return ((u64)a.nrec << a.split0) > ((u64)b.nrec << b.split0); });
             if ((rc = ensure(ctx, ctx->jobs, jobs.size() * sizeof(SmemJob)))) return rc;
             CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), jobs.size() * sizeof(SmemJob), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
@@ -1155,6 +1171,38 @@ int dskgpu_xchg_layout(int world_size, uint32_t nparts, const uint64_t* all_coun
         for (u32 p = o; p < nparts; p += (u32)world_size) offsets[p] = off[p];
         if (recv_records) recv_records[o] = tot;
     }
+    return DSKGPU_OK;
+}
+
+// second pass of "-abundance-min auto": the partitioned records are still in HBM, only the counting stage runs again
+int dskgpu_recount(dskgpu_ctx* ctx, const int64_t* abundance_min)
+{
+    if (!ctx || !abundance_min) return DSKGPU_ERR_ARG;
+    if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "recount before finish");
+    for (int b = 0; b < DSKGPU_MAX_BANKS; b++) ctx->cfg.abundance_min[b] = abundance_min[b < ctx->cfg.nb_banks ? b : ctx->cfg.nb_banks - 1];
+    Counters* ctr = (Counters*)ctx->ctr.p;
+    CK(cudaMemsetAsync(&ctr->solid_n, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(&ctr->distinct_n, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(&ctr->smem_splits, 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
+    if (ctx->bank_hist.p) CK(cudaMemsetAsync(ctx->bank_hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * (size_t)ctx->NB, ctx->stream));
+    ctx->state = 0; ctx->n_solid = 0; ctx->results_on_host = false;
+    ctx->st.nb_groups_hash = ctx->st.nb_groups_sort = 0;
+    const bool owned = ctx->cfg.world_size > 1;
+    const std::vector<u64>& pr = owned ? ctx->owned_recs : ctx->h_part_recs;
+    const std::vector<u64>& pk = owned ? ctx->owned_kmers : ctx->h_part_kmers;
+    return ctx->KW == 1 ? stage_count<1>(ctx, (const u64*)ctx->precs.p, pr, pk) : stage_count<2>(ctx, (const u64*)ctx->precs.p, pr, pk);
+}
+
+int dskgpu_bank_histograms(dskgpu_ctx* ctx, uint64_t* hist)
+{
+    if (!ctx || !hist) return DSKGPU_ERR_ARG;
+    if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "histograms requested before finish");
+    if (ctx->NB == 1) { memcpy(hist, ctx->h_hist, sizeof(uint64_t) * DSKGPU_HISTO_LEN); return DSKGPU_OK; }
+    if (!ctx->bank_hist.p) FAIL(DSKGPU_ERR_STATE, "per-bank histograms were not requested (cfg.bank_histograms)");
+    CK(cudaMemcpyAsync(hist, ctx->bank_hist.p, sizeof(uint64_t) * DSKGPU_HISTO_LEN * (size_t)ctx->NB, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return DSKGPU_OK;
 }
 

@@ -82,7 +82,10 @@ typedef struct dskgpu_config {
     int32_t  rank, world_size;                   /* multi-GPU: this context owns partitions p with p % world_size == rank */
     int32_t  push_chunk_bytes;                   /* 0 = default (64 MiB): granularity of the streamed H2D copy + scan */
     int32_t  smem_table_slots;                   /* 0 = auto (all the shared memory of an SM); tests shrink it to force splits */
-    int32_t  reserved[6];
+    int32_t  bank_histograms;                    /* 1: also keep one abundance histogram per bank (dskgpu_bank_histograms; the first
+                                                    pass of -abundance-min auto with -solidity-kind one/all/custom).  Global atomics
+                                                    per distinct k-mer: leave 0 unless those cutoffs are needed */
+    int32_t  reserved[5];
 } dskgpu_config;
 
 /* stats block: the keys of SortingCountAlgorithm::getInfo() (SortingCountAlgorithm.cpp:728-780) */
@@ -105,7 +108,9 @@ typedef struct dskgpu_stats {
     uint32_t nb_parts_smem;         /* partitions counted in shared memory */
     uint32_t nb_smem_splits;        /* table overflows answered by splitting a pass */
     uint32_t smem_table_slots;      /* capacity of the shared-memory table */
-    uint32_t reserved[4];
+    uint32_t density_ppm;           /* sampled distinct / total k-mers x 1e6 (0 = sample too small) */
+    uint32_t log2_bins;             /* minimizer-bin level the partitions were packed from (16..20) */
+    uint32_t reserved[2];
 } dskgpu_stats;
 
 /* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */
@@ -146,6 +151,17 @@ int dskgpu_partition_device(dskgpu_ctx* ctx, int p, const void** d_kmers, const 
  * hist1d[i] = number of distinct k-mers of abundance i, with the reference's quirks (bins 0 and 10000
  * always 0, uint16 wrap).  hist2d may be NULL; layout hist2d[dim2 * 10001 + dim1]. */
 int dskgpu_histogram(dskgpu_ctx* ctx, uint64_t* hist1d /*[10001]*/, uint64_t* hist2d /*[11*10001] or NULL*/);
+
+/* replaces: the second fillSolidKmers pass of "-abundance-min auto" (SortingCountAlgorithm.cpp:1393-1402 run once per
+ * processor of getDefaultProcessorVector, :454-514; thresholds updated by CountProcessorCustomProxy::endPass, :419-444).
+ * Call after dskgpu_finish: counts the partitions again -- the super-k-mer records are still in HBM -- with new
+ * abundance_min[nb_banks]; results, histograms and stats are replaced. */
+int dskgpu_recount(dskgpu_ctx* ctx, const int64_t* abundance_min);
+/* replaces: the per-bank histograms of CountProcessorCutoff (CountProcessorCutoff.hpp:101-116), from which the reference
+ * derives one cutoff per bank for -solidity-kind one/all/custom.  hist[b * 10001 + i] = distinct k-mers whose count in
+ * bank b is i (same quirks as dskgpu_histogram); needs cfg.bank_histograms = 1.  With summed banks (per_bank_counts = 0)
+ * this is the 1-D histogram. */
+int dskgpu_bank_histograms(dskgpu_ctx* ctx, uint64_t* hist /*[nb_banks * 10001]*/);
 
 int dskgpu_get_stats(dskgpu_ctx* ctx, dskgpu_stats* out);
 
