@@ -52,6 +52,7 @@ SYMBOLS = [
     "dskgpu_last_error", "dskgpu_device_count", "dskgpu_abi_version",
     "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_bin_hist", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
     "dskgpu_xchg_open_peer", "dskgpu_xchg_set_peers", "dskgpu_xchg_scatter", "dskgpu_xchg_sync", "dskgpu_xchg_layout", "dskgpu_record_bytes",
+    "dskgpu_xchg2_hist", "dskgpu_xchg2_plan", "dskgpu_xchg2_ensure_recv", "dskgpu_xchg2_scatter",
     "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers",
 ]
 
@@ -105,6 +106,10 @@ def lib():
     L.dskgpu_xchg_set_peers.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_scatter.argtypes = [C.c_void_p]
     L.dskgpu_xchg_sync.argtypes = [C.c_void_p]
+    L.dskgpu_xchg2_hist.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg2_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_uint32)]
+    L.dskgpu_xchg2_ensure_recv.argtypes = [C.c_void_p, C.c_uint64]
+    L.dskgpu_xchg2_scatter.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_layout.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.dskgpu_record_bytes.argtypes = [C.c_void_p]
     L.dskgpu_selftest_scan.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]

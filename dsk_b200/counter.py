@@ -46,6 +46,7 @@ class GpuCounter:
         cfg.nb_partitions = nb_partitions
         cfg.keep_results_on_device = int(keep_results_on_device)
         cfg.stream = stream
+        self.stream = stream
         cfg.rank, cfg.world_size = rank, world_size
         cfg.push_chunk_bytes = push_chunk_bytes
         cfg.smem_table_slots = smem_table_slots
@@ -217,6 +218,27 @@ def _xchg_methods():
 
     def xchg_sync(self):
         self._check(self.L.dskgpu_xchg_sync(self.h))
+
+    def xchg2_hist(self, d_out):
+        """copies this rank's bin histogram ([2 << level] u64) into the caller's device buffer (stream-ordered)"""
+        self._check(self.L.dskgpu_xchg2_hist(self.h, C.c_void_p(d_out)))
+
+    def xchg2_plan(self, d_global_hist):
+        """-> (local records per partition [P], records every rank receives [W])"""
+        P = C.c_uint32()
+        need = np.zeros(self.cfg.world_size, dtype=np.uint64)
+        cnt = np.zeros((1 << self._bin_level) + self.cfg.world_size, dtype=np.uint64)      # P <= bins (+ padding to the world size)
+        self._check(self.L.dskgpu_xchg2_plan(self.h, C.c_void_p(d_global_hist), cnt.ctypes.data, need.ctypes.data, C.byref(P)))
+        return cnt[:P.value], need
+
+    def xchg2_ensure_recv(self, capacity_records):
+        self._check(self.L.dskgpu_xchg2_ensure_recv(self.h, int(capacity_records)))
+
+    def xchg2_scatter(self, d_matrix):
+        self._check(self.L.dskgpu_xchg2_scatter(self.h, C.c_void_p(d_matrix)))
+
+    for f in (xchg2_hist, xchg2_plan, xchg2_ensure_recv, xchg2_scatter):
+        setattr(GpuCounter, f.__name__, f)
 
     for f in (xchg_local_totals, xchg_prepare, xchg_set_global, xchg_bin_hist, xchg_part_counts, xchg_plan, xchg_recv_buffer, xchg_ipc_handle, xchg_open_peer, xchg_set_peers,
               xchg_scatter, xchg_sync):

@@ -77,6 +77,12 @@ struct dskgpu_ctx {
     bool global_set = false; u64 g_total_kmers = 0; double density = 1.0; bool density_known = false;
     int bin_level = NBINS_LOG2; bool hist_fetched = false;
     DevBuf sendbuf;
+    // exchange v2 (bulk segments): records in local partition order, per-partition offsets on the device, pinned global histogram
+    DevBuf lrecs, xoff, xpeers;
+    unsigned long long* h_ghist = nullptr;
+    std::vector<u64> g_part_recs;                    // whole-job records of every partition
+    std::vector<u64> x_need;                         // records every rank receives
+    u64 recv_cap_recs = 0;
     dskgpu_stats st;
     // timing
     std::vector<cudaEvent_t> evpool; size_t ev_used = 0;
@@ -271,7 +277,8 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->bank_hist, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
                      &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->dstbase, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->bin2part, &ctx->jobs, &ctx->work_ctr,
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
-                     &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr, &ctx->sendbuf};
+                     &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr, &ctx->sendbuf,
+                     &ctx->lrecs, &ctx->xoff, &ctx->xpeers};
     for (DevBuf* b : all) b->release();
     for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -282,6 +289,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (ctx->h_nrec_probe) cudaFreeHost(ctx->h_nrec_probe);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
     if (ctx->h_bin_hist) cudaFreeHost(ctx->h_bin_hist);
+    if (ctx->h_ghist) cudaFreeHost(ctx->h_ghist);
     if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
     if (ctx->h_svals) cudaFreeHost(ctx->h_svals);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -810,21 +818,21 @@ static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh /*[2 <<
     for (u32 b = 0; b < NB_; b++) total += gk[b];
     const u64 T = plan_target_kmers(ctx, total);
     ctx->h_bin2part.resize(NB_);
-    ctx->g_part_kmers.clear(); ctx->h_part_recs.clear(); ctx->h_part_kmers.clear();
+    ctx->g_part_kmers.clear(); ctx->g_part_recs.clear(); ctx->h_part_recs.clear(); ctx->h_part_kmers.clear();
     u32* b2p = ctx->h_bin2part.data();
-    u32 P = 0; u64 acc = 0, ar = 0, ak = 0;
+    u32 P = 0; u64 acc = 0, gr = 0, ar = 0, ak = 0;
     for (u32 b = 0; b < NB_; b++) {
         const u64 km = gk[b];
         if (acc > 0 && acc + km > T) {
-            ctx->g_part_kmers.push_back(acc); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
-            P++; acc = ar = ak = 0;
+            ctx->g_part_kmers.push_back(acc); ctx->g_part_recs.push_back(gr); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
+            P++; acc = gr = ar = ak = 0;
         }
-        b2p[b] = P; acc += km; ar += lr[b]; ak += lk[b];
+        b2p[b] = P; acc += km; gr += gh[b]; ar += lr[b]; ak += lk[b];
     }
-    ctx->g_part_kmers.push_back(acc); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
+    ctx->g_part_kmers.push_back(acc); ctx->g_part_recs.push_back(gr); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
     P += 1;
     const u32 W = (u32)ctx->cfg.world_size;
-    while (P % W) { ctx->g_part_kmers.push_back(0); ctx->h_part_recs.push_back(0); ctx->h_part_kmers.push_back(0); P++; }
+    while (P % W) { ctx->g_part_kmers.push_back(0); ctx->g_part_recs.push_back(0); ctx->h_part_recs.push_back(0); ctx->h_part_kmers.push_back(0); P++; }
     ctx->nparts = P; ctx->st.nb_partitions = P;
     int rc;
     if ((rc = ensure(ctx, ctx->cursor, (size_t)P * 8))) return rc;
@@ -1147,6 +1155,86 @@ int dskgpu_xchg_scatter(dskgpu_ctx* ctx)
     }
     int rc = ctx->KW == 1 ? stage_scatter<1>(ctx, dst) : stage_scatter<2>(ctx, dst);
     if (rc) return rc;
+    ctx->xchg_scattered = true;
+    return DSKGPU_OK;
+}
+
+// ---- exchange v2: metadata stays on the device, records travel as whole partition segments ---------------------------
+// The per-record peer stores of xchg_scatter cross NVLink as isolated 16-byte writes; here the records are first scattered
+// into partition order in local HBM (the single-GPU kernel) and every (partition, sender) segment -- ~17 KB on C2 -- is
+// then copied to its owner's receive buffer with coalesced 16-byte vector stores.  The bin histogram is all-reduced and
+// the per-partition counts are all-gathered by the caller on DEVICE buffers (NCCL), so no metadata crosses the host twice.
+int dskgpu_xchg2_hist(dskgpu_ctx* ctx, void* d_out)
+{
+    if (!ctx || !d_out) return DSKGPU_ERR_ARG;
+    int rc = stage_totals(ctx); if (rc) return rc;
+    if (!ctx->global_set) FAIL(DSKGPU_ERR_STATE, "xchg2_hist before xchg_set_global (the ranks must agree on the bin level)");
+    if ((rc = fetch_local_bin_hist(ctx))) return rc;
+    const void* src = ctx->bin_level == NBINS_FINE_LOG2 ? ctx->bin_hist.p : ctx->bin_fold.p;
+    CK(cudaMemcpyAsync(d_out, src, sizeof(unsigned long long) * ((size_t)2 << ctx->bin_level), cudaMemcpyDeviceToDevice, ctx->stream));
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist, uint64_t* local_counts, uint64_t* need_records, uint32_t* nparts)
+{
+    if (!ctx || !d_global_hist) return DSKGPU_ERR_ARG;
+    if (!ctx->hist_fetched) FAIL(DSKGPU_ERR_STATE, "xchg2_plan before xchg2_hist");
+    const u32 W = (u32)ctx->cfg.world_size, me = (u32)ctx->cfg.rank;
+    if (ctx->nparts == 0) {
+        if (!ctx->h_ghist) CK(cudaMallocHost((void**)&ctx->h_ghist, sizeof(unsigned long long) * 2 * NBINS_FINE));
+        CK(cudaMemcpyAsync(ctx->h_ghist, d_global_hist, sizeof(unsigned long long) * ((size_t)2 << ctx->bin_level), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        int rc = plan_partitions(ctx, ctx->h_ghist); if (rc) return rc;
+        const u32 P = ctx->nparts;
+        // receive-buffer layout: owned partitions in increasing id; x_need[r] = records rank r receives
+        ctx->x_need.assign(W, 0);
+        std::vector<u64> hoff((size_t)2 * P + 1, 0);               // [0..P] local prefix, [P+1..2P] base of p in its owner's buffer
+        for (u32 p = 0; p < P; p++) { hoff[p + 1] = hoff[p] + ctx->h_part_recs[p]; hoff[P + 1 + p] = ctx->x_need[p % W]; ctx->x_need[p % W] += ctx->g_part_recs[p]; }
+        ctx->owned_recs.clear(); ctx->owned_kmers.clear();
+        for (u32 p = me; p < P; p += W) { ctx->owned_recs.push_back(ctx->g_part_recs[p]); ctx->owned_kmers.push_back(ctx->g_part_kmers[p]); }
+        ctx->my_nrec_owned = ctx->x_need[me];
+        if ((rc = ensure(ctx, ctx->xoff, hoff.size() * 8))) return rc;
+        CK(cudaMemcpyAsync(ctx->xoff.p, hoff.data(), hoff.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));                    // hoff is a temporary
+    }
+    const u32 P = ctx->nparts;
+    if (nparts) *nparts = P;
+    if (local_counts) for (u32 p = 0; p < P; p++) local_counts[p] = ctx->h_part_recs[p];
+    if (need_records) for (u32 r = 0; r < W; r++) need_records[r] = ctx->x_need[r];
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg2_ensure_recv(dskgpu_ctx* ctx, uint64_t capacity_records)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    if (ctx->nparts == 0) FAIL(DSKGPU_ERR_STATE, "xchg2_ensure_recv before xchg2_plan");
+    const u64 want = std::max<u64>(capacity_records, ctx->my_nrec_owned);
+    int rc = ensure(ctx, ctx->precs, want * (u64)ctx->RW * 8 + 64); if (rc) return rc;
+    ctx->xchg_planned = true;
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg2_scatter(dskgpu_ctx* ctx, const void* d_matrix)
+{
+    if (!ctx || !d_matrix) return DSKGPU_ERR_ARG;
+    if (!ctx->xchg_planned || ctx->peer_recv.size() != (size_t)ctx->cfg.world_size) FAIL(DSKGPU_ERR_STATE, "xchg2_scatter before xchg2_ensure_recv / xchg_set_peers");
+    const u32 W = (u32)ctx->cfg.world_size, P = ctx->nparts, me = (u32)ctx->cfg.rank;
+    if (ctx->precs.cap < ctx->my_nrec_owned * (u64)ctx->RW * 8) FAIL(DSKGPU_ERR_STATE, "receive buffer smaller than the planned layout");
+    int rc;
+    if ((rc = ensure(ctx, ctx->lrecs, ctx->local_nrec * (u64)ctx->RW * 8 + 64))) return rc;
+    if ((rc = ensure(ctx, ctx->xpeers, (size_t)W * 8))) return rc;
+    std::vector<u64*> dst(P);
+    { u64 o = 0; for (u32 p = 0; p < P; p++) { dst[p] = (u64*)ctx->lrecs.p + o * ctx->RW; o += ctx->h_part_recs[p]; } }
+    rc = ctx->KW == 1 ? stage_scatter<1>(ctx, dst) : stage_scatter<2>(ctx, dst);
+    if (rc) return rc;
+    if (ctx->local_nrec) {
+        SpanGuard g(ctx, SPAN_PART);
+        CK(cudaMemcpyAsync(ctx->xpeers.p, ctx->peer_recv.data(), (size_t)W * 8, cudaMemcpyHostToDevice, ctx->stream));
+        const unsigned grid = (unsigned)std::min<u32>(P, (u32)ctx->num_sms * 8);
+        k_xchg_copy<<<grid, 256, 0, ctx->stream>>>((const ulonglong2*)ctx->lrecs.p, (const u64*)ctx->xoff.p, (const u64*)d_matrix,
+                                                   (ulonglong2* const*)ctx->xpeers.p, W, me, P, (u32)ctx->RW / 2); LAUNCHED();
+        CK(cudaGetLastError());
+    }
     ctx->xchg_scattered = true;
     return DSKGPU_OK;
 }

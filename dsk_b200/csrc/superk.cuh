@@ -284,6 +284,25 @@ __global__ void k_fold_bins(const unsigned long long* __restrict__ fine, int shi
     }
 }
 
+// exchange v2: this rank's segment of every partition (contiguous in `lrecs`) goes to the partition owner's receive buffer.
+// xoff[0..P] = local prefix (records), xoff[P+1+p] = first record of partition p in its owner's buffer; matrix[s*P + p] =
+// records of partition p held by rank s (all-gathered on the device); senders are laid out in rank order inside a partition.
+// One CTA per segment, 16-byte vector loads / stores: NVLink sees long contiguous writes instead of isolated records.
+__global__ void __launch_bounds__(256) k_xchg_copy(const ulonglong2* __restrict__ lrecs, const u64* __restrict__ xoff, const u64* __restrict__ matrix,
+                                                   ulonglong2* const* __restrict__ peers, u32 W, u32 me, u32 P, u32 v_per_rec)
+{
+    for (u32 p = blockIdx.x; p < P; p += gridDim.x) {
+        const u64 b = xoff[p], n = xoff[p + 1] - b;
+        if (n == 0) continue;
+        u64 before = xoff[P + 1 + p];
+        for (u32 s = 0; s < me; s++) before += matrix[(u64)s * P + p];
+        const ulonglong2* src = lrecs + b * v_per_rec;
+        ulonglong2* dst = peers[p % W] + before * v_per_rec;
+        const u64 nv = n * v_per_rec;
+        for (u64 i = threadIdx.x; i < nv; i += 256) dst[i] = src[i];
+    }
+}
+
 // density sample: the records of the fine bins below `thresh` are copied out (all occurrences of a k-mer share their
 // bin, so distinct / total of the sample estimates distinct / total of the job)
 template <int KW>

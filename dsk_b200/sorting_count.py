@@ -12,6 +12,7 @@ import os
 import numpy as np
 
 from .counter import GpuCounter, DskGpuError
+from .histogram import compute_threshold, auto_thresholds, MIN_AUTO_THRESHOLD
 
 # G/src/gatb/tools/misc/impl/StringsRepository.hpp:81-127
 STR_KMER_SIZE = "-kmer-size"
@@ -109,9 +110,7 @@ class SortingCountAlgorithm:
         kind = str(p[STR_SOLIDITY_KIND])
         histo2d = int(p.get(STR_HISTO2D, 0)) != 0
         amin_s = str(p[STR_KMER_ABUNDANCE_MIN])
-        if "auto" in amin_s:
-            raise NotImplementedError("-abundance-min auto (cutoff heuristic) is outside the hot-path scope")
-        amin = [int(x) for x in amin_s.split(",")]
+        amin = [-1 if x == "auto" else int(x) for x in amin_s.split(",")]      # ConfigurationAlgorithm.cpp:478-498
         if len(amin) > nb:
             raise ValueError("Kmer solidity has more thresholds than banks")
         amin = amin + [amin[-1]] * (nb - len(amin))
@@ -124,13 +123,21 @@ class SortingCountAlgorithm:
         if kind == "custom":
             sv = str(p.get(STR_SOLIDITY_CUSTOM, ""))
             solid_vec = [int(c) for c in sv] + [0] * (nb - len(sv))
+        # "auto" anywhere: a first count pass builds the histogram(s) the cutoffs come from -- one histogram of the sum
+        # for sum/min/max, one per bank for one/all/custom (SortingCountAlgorithm.cpp:455-514)
+        self._auto = -1 in amin
+        self._auto_per_bank = self._auto and nb > 1 and kind in ("one", "all", "custom")
         return dict(kmer_size=k, abundance_min=amin, abundance_max=int(p[STR_KMER_ABUNDANCE_MAX]), nb_banks=nb,
                     per_bank_counts=per_bank, solidity_kind=kind, solid_vec=solid_vec, histo2d=histo2d,
-                    minimizer_size=int(p[STR_MINIMIZER_SIZE]))
+                    minimizer_size=int(p[STR_MINIMIZER_SIZE]), bank_histograms=self._auto_per_bank)
 
     def execute(self):
         cfg = self._configure()
         cfg.update(self.engine_kw)
+        user_amin = list(cfg["abundance_min"])
+        if self._auto:
+            # pass 1 (the cutoff processor) dumps nothing: no abundance reaches this threshold
+            cfg["abundance_min"] = [2**31 - 1] * len(user_amin)
         try:
             eng = GpuCounter(device=self.device, **cfg)
         except DskGpuError as e:
@@ -144,6 +151,11 @@ class SortingCountAlgorithm:
                 else:
                     eng.push_bytes(bank.read(), bank=b, last=True)
             eng.finish()
+            self.cutoffs = None
+            if self._auto:
+                hs = eng.bank_histograms() if self._auto_per_bank else [eng.histogram()[0]]
+                self.cutoffs = [compute_threshold(h, MIN_AUTO_THRESHOLD)[0] for h in hs]
+                eng.recount(auto_thresholds(user_amin, self.cutoffs))          # pass 2: the dsk processor chain
             self._solid = eng.solid()
             self._hist = eng.histogram()
             st = eng.stats()
@@ -153,6 +165,7 @@ class SortingCountAlgorithm:
             "kmers_nb_solid": st["kmers_nb_solid"], "kmers_nb_weak": st["kmers_nb_distinct"] - st["kmers_nb_solid"],
             "nb_superkmers": st["nb_superkmers"], "nb_partitions": st["nb_partitions"], "seq_number": st["nb_sequences"],
             "bank_total_nt": st["nb_nucleotides"], "solidity_kind": cfg["solidity_kind"], "engine": st,
+            "cutoffs_auto": self.cutoffs,
         }
         return self
 

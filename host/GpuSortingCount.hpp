@@ -15,6 +15,7 @@
 #include <gatb/kmer/impl/CountProcessorHistogram.hpp>
 #include <zlib.h>
 
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -81,6 +82,7 @@ public:
         {
             TIME_INFO(getTimeInfo(), "fill_solid_kmers");         // K/SortingCountAlgorithm.cpp:1391
             check(dskgpu_finish(_ctx), _ctx, "dskgpu_finish");
+            if (_autoCutoff) executeAutoCutoff();
         }
         writeResults();
     }
@@ -97,6 +99,9 @@ private:
     dskgpu_stats      _st;
     std::string       _histoName, _histo2DName;
     bool              _autoCutoff;
+    bool              _autoPerBank;
+    std::vector<long long> _userAbundanceMin;      // -1 = auto
+    std::vector<CountNumber> _cutoffs;
 
     // ---- configure(): K/SortingCountAlgorithm.cpp:525-625 -------------------------------------------------------
     void configure()
@@ -168,13 +173,20 @@ private:
         c.per_bank_counts = (c.nb_banks > 1 && (kind != DSKGPU_SOLIDITY_SUM || histo2D)) ? 1 : 0;
         c.histo2d = histo2D ? 1 : 0;
         _autoCutoff = false;
+        _userAbundanceMin.clear();
         for (size_t i = 0; i < (size_t)DSKGPU_MAX_BANKS; i++) {
             const size_t j = i < _config._abundance.size() ? i : _config._abundance.size() - 1;
             long long lo = _config._abundance.empty() ? 2 : (long long)_config._abundance[j].getBegin();
-            if (lo < 0) { _autoCutoff = true; lo = 1; }
+            if (lo < 0) { _autoCutoff = true; lo = -1; }
+            _userAbundanceMin.push_back(lo);
             c.abundance_min[i] = lo;
         }
-        if (_autoCutoff) throw Exception("-abundance-min auto needs the two-pass cutoff chain (SURVEY.md 8(f)-3): not on the device path yet");
+        // "auto" anywhere: the reference runs the partitions through a cutoff processor first, then through the dsk
+        // chain (K/SortingCountAlgorithm.cpp:455-514).  Here: pass 1 dumps nothing (no abundance reaches the threshold)
+        // and leaves the histogram(s); executeAutoCutoff() turns them into thresholds and counts again from HBM.
+        _autoPerBank = _autoCutoff && c.nb_banks > 1 && (kind == DSKGPU_SOLIDITY_ONE || kind == DSKGPU_SOLIDITY_ALL || kind == DSKGPU_SOLIDITY_CUSTOM);
+        if (_autoCutoff) for (size_t i = 0; i < (size_t)DSKGPU_MAX_BANKS; i++) c.abundance_min[i] = 2147483647LL;
+        c.bank_histograms = _autoPerBank ? 1 : 0;
         c.abundance_max = _config._abundance.empty() ? 2147483647LL : (long long)_config._abundance[0].getEnd();
         for (size_t i = 0; i < (size_t)DSKGPU_MAX_BANKS; i++) c.solid_vec[i] = (i < _config._solidVec.size()) ? (_config._solidVec[i] ? 1 : 0) : 1;
         const char* dev = getenv("DSKGPU_DEVICE");
@@ -255,6 +267,30 @@ private:
         dskgpu_host_free(buf[0]); dskgpu_host_free(buf[1]);
     }
 
+    // ---- -abundance-min auto: CountProcessorCutoff::endPass + CountProcessorSolidityInfo::setAbundanceMin ----------------
+    // (K/CountProcessorCutoff.hpp:86-124, K/CountProcessorSolidity.hpp:45-66); the heuristic itself is the reference's own
+    // Histogram::compute_threshold, run on the device histogram(s)
+    void executeAutoCutoff()
+    {
+        const size_t nbHist = _autoPerBank ? (size_t)_config._nb_banks : 1;
+        std::vector<uint64_t> hs(nbHist * (size_t)DSKGPU_HISTO_LEN);
+        if (_autoPerBank) check(dskgpu_bank_histograms(_ctx, hs.data()), _ctx, "dskgpu_bank_histograms");
+        else              check(dskgpu_histogram(_ctx, hs.data(), 0), _ctx, "dskgpu_histogram");
+        _cutoffs.clear();
+        for (size_t b = 0; b < nbHist; b++) {
+            Histogram H(10000);
+            for (size_t i = 0; i <= 10000; i++) H.get((u_int16_t)i) = hs[b * DSKGPU_HISTO_LEN + i];
+            H.compute_threshold(3);
+            _cutoffs.push_back((CountNumber)H.get_solid_cutoff());
+        }
+        const size_t nbThr = std::max<size_t>(1, _config._abundance.size());
+        if (_cutoffs.size() > nbThr) throw Exception("Unable to set abundance min values (%d values for %d banks)", (int)_cutoffs.size(), (int)nbThr);
+        int64_t amin[DSKGPU_MAX_BANKS];
+        for (size_t i = 0; i < _cutoffs.size(); i++) amin[i] = _userAbundanceMin[i] == -1 ? (int64_t)_cutoffs[i] : (int64_t)_userAbundanceMin[i];
+        for (size_t i = _cutoffs.size(); i < (size_t)DSKGPU_MAX_BANKS; i++) amin[i] = amin[_cutoffs.size() - 1];
+        check(dskgpu_recount(_ctx, amin), _ctx, "dskgpu_recount");
+    }
+
     // ---- results: CountProcessorDump / CountProcessorHistogram roles, in bulk ---------------------------------------
     void writeResults()
     {
@@ -333,6 +369,11 @@ private:
         getInfo()->add(3, "nb_superkmers", "%lld", (long long)_st.nb_superkmers);
         getInfo()->add(3, "avg_superk_length", "%.2f", _st.nb_superkmers ? (double)_st.kmers_nb_valid / (double)_st.nb_superkmers : 0.0);
         getInfo()->add(3, "total_size_(MB)", "%lld", (long long)(_st.superkmer_bytes >> 20));
+        if (_autoCutoff) {                                        // CountProcessorCutoff::getProperties (K/CountProcessorCutoff.hpp:128-137)
+            std::stringstream ss; for (size_t i = 0; i < _cutoffs.size(); i++) ss << _cutoffs[i] << " ";
+            getInfo()->add(2, "cutoffs_auto");
+            getInfo()->add(3, "values", "%s", ss.str().c_str());
+        }
         getInfo()->add(2, ph.getProperties());
         getInfo()->add(2, "kmers");
         getInfo()->add(3, "solidity_kind", "%s", toString(_config._solidityKind).c_str());

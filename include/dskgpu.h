@@ -208,6 +208,24 @@ int dskgpu_xchg_open_peer(dskgpu_ctx* ctx, const void* handle64, void** d_ptr);
 int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv /*[world_size]; own entry ignored*/);
 int dskgpu_xchg_scatter(dskgpu_ctx* ctx);
 int dskgpu_xchg_sync(dskgpu_ctx* ctx);
+/* ---- exchange v2 (what dsk_b200.distributed.distributed_finish uses): same ownership and receive-buffer layout, but
+ * the metadata stays on the device and the records cross NVLink as whole (partition, sender) segments:
+ *   xchg_prepare / xchg_set_global as above;
+ *   xchg2_hist        copies this rank's bin histogram [2*B] into a DEVICE buffer of the caller, who all-reduces it in
+ *                     place (NCCL);
+ *   xchg2_plan        reads the all-reduced histogram, plans the partitions; local_counts[P] = this rank's records per
+ *                     partition (the caller all-gathers them into a DEVICE matrix [world_size][P]); need_records[r] =
+ *                     records rank r receives (every rank computes the same numbers, so every rank knows when a peer
+ *                     has to grow its receive buffer and the IPC handles must be exchanged again);
+ *   xchg2_ensure_recv sizes the receive buffer (capacity >= own need), then xchg_ipc_handle / open_peer / set_peers;
+ *   xchg2_scatter     scatters the records into partition order in local HBM, then ONE kernel copies every segment into
+ *                     its owner's receive buffer through the peer pointers (coalesced 16-byte stores over NVLink);
+ *   xchg_sync, barrier, dskgpu_finish. */
+int dskgpu_xchg2_hist(dskgpu_ctx* ctx, void* d_hist_out /*device, [2*B] u64*/);
+int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist /*device, [2*B] u64*/, uint64_t* local_counts /*[P] or NULL*/,
+                      uint64_t* need_records /*[world_size] or NULL*/, uint32_t* nparts);
+int dskgpu_xchg2_ensure_recv(dskgpu_ctx* ctx, uint64_t capacity_records);
+int dskgpu_xchg2_scatter(dskgpu_ctx* ctx, const void* d_matrix /*device, [world_size][P] u64*/);
 /* host-only layout helper: offsets[p] = first record slot of `sender` for partition p inside owner(p)'s buffer */
 int dskgpu_xchg_layout(int world_size, uint32_t nparts, const uint64_t* all_counts, int sender, uint64_t* offsets, uint64_t* recv_records);
 int dskgpu_record_bytes(dskgpu_ctx* ctx);

@@ -3,5 +3,5 @@
 Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs.
 The product package (dsk_b200) never imports this module.
 """
-from .pyoracle import (Oracle, OracleResult, count_files, kmers_of, parse_stats, mmer_lut,
+from .pyoracle import (Oracle, OracleResult, count_files, histogram_threshold, kmers_of, parse_stats, mmer_lut,
                        ref_available, run_reference, read_maybe_gz, ORACLE_DIR)

@@ -74,6 +74,7 @@ class OracleResult:
     solid: np.ndarray        # bool  [ndistinct]
     hist: np.ndarray         # uint64[10001]  (index = abundance; bins 0 and 10000 are always 0)
     hist2d: np.ndarray       # uint64[11, 10001]  ([dim2, dim1])
+    cutoffs: object = None   # -abundance-min auto: the cutoffs of the first pass
 
     @property
     def nb_distinct(self):
@@ -142,12 +143,79 @@ class Oracle:
             self.L.orc_destroy(self.h)
 
 
+def histogram_threshold(hist, min_auto_threshold=3, length=10000):
+    """Histogram::compute_threshold (G/src/gatb/tools/misc/impl/Histogram.cpp:61-190) restated: smoothed histogram
+    (u64 casts of 0.6/0.4 and 0.2/0.6/0.2 double mixes), first increase, highest smoothed bin after it, lowest smoothed
+    bin between the two = cutoff, capped at the first abundance whose cumulated volume reaches 25 %, floored at
+    `min_auto_threshold`.  Returns (cutoff, nbsolids)."""
+    H = [int(x) for x in hist[:length + 1]]
+    S = [0] * (length + 1)
+    S[1] = int(0.6 * float(H[1]) + 0.4 * float(H[2]))                       # :68
+    total = H[1] + H[length] * length                                      # :69,:98
+    inc_at = peak_at = -1
+    peak = 0
+    for i in range(2, length):                                             # :78-96
+        total += H[i] * i
+        S[i] = int(0.2 * float(H[i - 1]) + 0.6 * float(H[i]) + 0.2 * float(H[i + 1]))
+        if inc_at == -1 and S[i - 1] < S[i]:
+            inc_at = i - 1
+        if inc_at > 0 and S[i] > peak:
+            peak, peak_at = S[i], i
+    if inc_at == -1:                                                       # :101-105
+        return min_auto_threshold, 0
+    cut, low = 0, 10000000000
+    for i in range(inc_at, peak_at + 1):                                   # :115-122
+        if S[i] < low:
+            low, cut = S[i], i
+    cap, gone = 0, 0
+    for i in range(length + 1):                                            # :130-142
+        gone += H[i] * i
+        if float(gone) / float(total) >= 0.25:
+            cap = i + 1
+            break
+    cut = max(min(cut, cap), min_auto_threshold)                           # :144-148
+    return cut, int(sum(H[cut:length + 1]))
+
+
+def _bank_histogram(counts_b):
+    """CountProcessorHistogram on one bank's counts: u16 truncation, clamp, bins 1..9999 survive (Histogram.hpp:92,221)."""
+    idx = (counts_b.astype(np.int64) & 0xFFFF)
+    idx = np.minimum(idx, 10000)
+    h = np.bincount(idx, minlength=10001).astype(np.uint64)
+    h[0] = 0
+    h[10000] = 0
+    return h
+
+
 def count_files(banks, k, m=0, **kw):
-    """banks: list of byte strings (one file image per bank)."""
-    o = Oracle(k, len(banks), m)
-    for b, data in enumerate(banks):
-        o.add_file_bytes(data, b)
-    return o.finish(**kw)
+    """banks: list of byte strings (one file image per bank).  abundance_min may hold -1 entries ("auto"): the cutoffs
+    are then computed first, as the reference's cutoff pass does (SortingCountAlgorithm.cpp:455-514,
+    CountProcessorCutoff.hpp:86-124, CountProcessorSolidity.hpp:45-66); the result carries them in `.cutoffs`."""
+    def run(**kw2):
+        o = Oracle(k, len(banks), m)
+        for b, data in enumerate(banks):
+            o.add_file_bytes(data, b)
+        return o.finish(**kw2)
+    amin = kw.get("abundance_min", 2)
+    if isinstance(amin, int):
+        amin = [amin] * len(banks)
+    amin = list(amin) + [amin[-1]] * (len(banks) - len(amin))
+    if -1 not in amin:
+        res = run(**kw)
+        res.cutoffs = None
+        return res
+    kind = kw.get("kind", "sum") if len(banks) > 1 else "sum"
+    first = run(**dict(kw, abundance_min=[2**31 - 1] * len(banks)))
+    if kind in ("sum", "min", "max"):
+        hs = [first.hist]                                                  # histogram of the sum over all banks
+    else:
+        hs = [_bank_histogram(first.counts[:, b]) for b in range(len(banks))]
+    cutoffs = [histogram_threshold(h, 3)[0] for h in hs]
+    new = [c if a == -1 else a for a, c in zip(amin, cutoffs)]
+    new = new + [new[-1]] * (len(amin) - len(new))
+    res = run(**dict(kw, abundance_min=new))
+    res.cutoffs = cutoffs
+    return res
 
 
 def kmers_of(seq, k, m=0, forward=False):

@@ -11,6 +11,7 @@ What it writes
                            G/test/unit/src/kmer/TestDSK.cpp and TestKmer.cpp
   ref_runs.json            outputs of the real reference `dsk` on every input (solid k-mer digest,
                            counts, sparse histogram, stats) -- the "outputs of the reference run here" pin
+  ref_runs_auto.json       same for `-abundance-min auto` (cutoffs of the first pass + the solid set they select)
 """
 import gzip
 import hashlib
@@ -292,9 +293,49 @@ def ref_runs(synth):
               open(os.path.join(HERE, "ref_runs.json"), "w"), indent=1)
 
 
+def auto_cutoffs_of(stats):
+    """`cutoffs_auto / values` of the -verbose 1 stats block (CountProcessorCutoff::getProperties)"""
+    lines = stats.replace("\r", "\n").splitlines()
+    for i, ln in enumerate(lines):
+        if "cutoffs_auto" in ln:
+            return [int(x) for x in lines[i + 1].split(":", 1)[1].split()]
+    return None
+
+
+def ref_runs_auto():
+    """-abundance-min auto: the reference's two-pass cutoff chain on committed inputs"""
+    assert ref_available(), "build the reference first: oracle/build_ref.sh"
+    c1 = "read50x_ref10K_e001.fasta.gz"
+    cases = [("auto_c1_k31", [c1], 31, "auto", None), ("auto_c1_k63", [c1], 63, "auto", None),
+             ("auto_c1_k15", [c1], 15, "auto", None), ("auto_c1_k11", [c1], 11, "auto", None),
+             ("auto_asmreads_k21", ["asm_reads.fasta"], 21, "auto", None),
+             ("auto_lowcomplexity_k31", ["lowcomplexity.fasta"], 31, "auto", None),
+             ("auto_c123_k31_sum", ["c1.fasta.gz", "c2.fasta.gz", "c3.fasta.gz"], 31, "auto", None),
+             ("auto_c123_k31_all", ["c1.fasta.gz", "c2.fasta.gz", "c3.fasta.gz"], 31, "auto", "all"),
+             ("auto_c123_k15_one", ["c1.fasta.gz", "c2.fasta.gz", "c3.fasta.gz"], 15, "auto", "one"),
+             ("auto_c123_k15_mixed_all", ["c1.fasta.gz", "c2.fasta.gz", "c3.fasta.gz"], 15, "2,auto", "all"),
+             ("auto_c123_k21_max", ["c1.fasta.gz", "c2.fasta.gz", "c3.fasta.gz"], 21, "auto", "max"),
+             ("auto_asm_reads_k21_one", ["assembly.fasta", "asm_reads.fasta"], 21, "auto,auto", "one")]
+    runs = []
+    for name, files, k, amin, kind in cases:
+        r = run_reference([os.path.join(INP, f) for f in files], k, abundance_min=amin, histo=True, nb_cores=2, solidity_kind=kind)
+        ent = {"name": name, "files": files, "k": k, "abundance_min": amin, "solidity_kind": kind or "sum",
+               "cutoffs": auto_cutoffs_of(r["stats"]), "nb_solid": len(r["kmers"]), "kmers_sha256": kmer_digest(r["kmers"]),
+               "sum_counts": int(sum(c for _, c in r["kmers"])), "hist": sparse(r["hist"]),
+               "kmers_nb_solid": int(stat_value(r["stats"], "kmers_nb_solid") or 0)}
+        runs.append(ent)
+        print(name, ent["cutoffs"], ent["nb_solid"], flush=True)
+    json.dump({"source": "oracle/_ref/bin/dsk -abundance-min auto (unmodified reference)", "runs": runs},
+              open(os.path.join(HERE, "ref_runs_auto.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if "--auto-only" in sys.argv:
+        ref_runs_auto()
+        sys.exit(0)
     shell_tests()
     unit_vectors()
     if "--units-only" not in sys.argv:
         s = synth_inputs()
         ref_runs(s)
+        ref_runs_auto()

@@ -127,3 +127,27 @@ def test_cli_unhandled_kmer_size(tmp_path):
     p = subprocess.run([DSK_GPU, "-file", os.path.join(INPUTS, "shortread.fasta"), "-kmer-size", "64", "-out", str(tmp_path / "x")],
                        cwd=str(tmp_path), capture_output=True, text=True)
     assert p.returncode != 0 and "unhandled kmer size 64" in (p.stdout + p.stderr)
+
+
+AUTO = load_json("ref_runs_auto.json")["runs"]
+
+
+@need_bins
+@pytest.mark.parametrize("t", AUTO, ids=[t["name"] for t in AUTO])
+def test_cli_abundance_min_auto(t, tmp_path):
+    """-abundance-min auto through the command line: cutoffs of the first pass and the solid set they select"""
+    tmp = str(tmp_path)
+    out = os.path.join(tmp, "gpu_out")
+    a = dsk_args(t, out)
+    a[a.index("-verbose") + 1] = "1"
+    stats = run([DSK_GPU] + a, tmp).replace("\r", "\n").splitlines()
+    i = [j for j, ln in enumerate(stats) if "cutoffs_auto" in ln][0]
+    assert [int(x) for x in stats[i + 1].split(":", 1)[1].split()] == t["cutoffs"]
+    lines, _, _ = read_back(out + ".h5", tmp)
+    assert len(lines) == t["nb_solid"]
+    m = hashlib.sha256()
+    for ln in lines:
+        m.update(ln + b"\n")
+    assert m.hexdigest() == t["kmers_sha256"]
+    rows = open(out + ".histo").read().splitlines()
+    assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]

@@ -270,11 +270,12 @@ def split_records(data, parts):
     return [data[cuts[i]:cuts[i + 1]] for i in range(parts)]
 
 
+@pytest.mark.parametrize("proto", ["v1", "v2"])
 @pytest.mark.parametrize("W,k,mode", [(2, 31, "auto"), (3, 31, "hash"), (2, 63, "auto"), (4, 31, "sort"), (3, 63, "smem")])
-def test_multi_rank_exchange_in_process(W, k, mode):
+def test_multi_rank_exchange_in_process(W, k, mode, proto):
     """N ranks as N contexts on one GPU: every rank parses a slice, the scatter kernel routes records to the owner
     of their partition (p % W), every rank counts only what it owns.  Union of the ranks' outputs == oracle."""
-    from dsk_b200.distributed import in_process_finish
+    from dsk_b200.distributed import in_process_finish, in_process_finish_v2
     buf, n, _ = reads_fasta(G=400_000, coverage=30, L=150, err=0.01, seed=77)
     data = buf[:n].tobytes()
     ref = oracle.count_files([data], k, abundance_min=2)
@@ -282,8 +283,12 @@ def test_multi_rank_exchange_in_process(W, k, mode):
     try:
         for e, piece in zip(engines, split_records(data, W)):
             e.push_bytes(piece)
-        allc = in_process_finish(engines)
-        P = allc.shape[1] // 2
+        if proto == "v1":                 # per-record peer stores, host-side metadata
+            P = in_process_finish(engines).shape[1] // 2
+        else:                             # bulk partition segments, device-side metadata (what distributed_finish runs)
+            M = in_process_finish_v2(engines)
+            P = M.shape[1]
+            assert int(M.sum()) == sum(e.stats()["nb_superkmers"] for e in engines)
         assert P % W == 0 and P >= W
         keys, cnts, hist, valid, distinct = [], [], np.zeros(10001, np.uint64), 0, 0
         for r, e in enumerate(engines):
@@ -307,3 +312,33 @@ def test_multi_rank_exchange_in_process(W, k, mode):
     finally:
         for e in engines:
             e.close()
+
+
+# ---------------------------------------------------------------- -abundance-min auto
+AUTO = load_json("ref_runs_auto.json")["runs"]
+
+
+@pytest.mark.parametrize("t", AUTO, ids=[t["name"] for t in AUTO])
+def test_reference_auto_cutoff_runs(t):
+    """two count passes over the partitions held in HBM: cutoff histogram(s) -> thresholds -> recount"""
+    sc = run_gpu(t["files"], t["k"], t["abundance_min"], kind=t["solidity_kind"])
+    assert sc.getInfo()["cutoffs_auto"] == t["cutoffs"]
+    assert sc.getInfo()["kmers_nb_solid"] == t["nb_solid"]
+    keys, cnt = sc.getSolidCounts()
+    h1, _ = sc.getHistogram()
+    assert sparse_hist(h1) == t["hist"]
+    hi = keys[:, 1] if keys.shape[1] == 2 else np.zeros(len(keys), np.uint64)
+    dg, _ = digest(keys[:, 0], hi, cnt, t["k"])
+    assert dg == t["kmers_sha256"]
+
+
+def test_auto_cutoff_synthetic_vs_oracle():
+    buf, n, _ = reads_fasta(G=200_000, coverage=40, L=150, err=0.01, seed=5)
+    data = buf[:n].tobytes()
+    for k in (21, 31):
+        ref = oracle.count_files([data], k, abundance_min=-1)
+        sc = SortingCountAlgorithm(BankBytes(data), {"-kmer-size": k, "-abundance-min": "auto"}).execute()
+        assert sc.getInfo()["cutoffs_auto"] == ref.cutoffs
+        keys, cnt = sc.getSolidCounts()
+        lo, _, rc = ref.solid_kmers()
+        assert len(cnt) == len(rc) and (keys[:, 0] == lo).all() and (cnt.astype(np.int64) == rc).all()

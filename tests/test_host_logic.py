@@ -147,3 +147,41 @@ def test_superkmer_pack_expand_roundtrip(L, k):
     else:
         assert (got[:, 0] == lo[valid]).all() and (got[:, 1] == hi[valid]).all()
     assert 0 < nrec.value <= n
+
+
+# ---------------------------------------------------------------- -abundance-min auto: host-side cutoff heuristic
+def test_compute_threshold_matches_reference_cutoffs():
+    """the product's restatement of Histogram::compute_threshold on the histograms of real reference runs"""
+    import json
+    from dsk_b200.histogram import compute_threshold, auto_thresholds
+    runs = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_runs_auto.json")))["runs"]
+    seen = set()
+    for t in runs:
+        if t["solidity_kind"] not in ("sum", "min", "max") or len(t["files"]) > 1 and t["solidity_kind"] != "sum":
+            continue                                  # the committed histogram is the histogram of the sum
+        h = np.zeros(10001, np.uint64)
+        for i, v in t["hist"].items():
+            h[int(i)] = v
+        assert compute_threshold(h, 3)[0] == t["cutoffs"][0], t["name"]
+        seen.add(t["cutoffs"][0])
+    assert len(seen) >= 4                             # 3 (the floor) and real valleys
+    assert auto_thresholds([-1, 4, -1], [7, 9]) == [7, 4, 4]          # CountProcessorSolidity.hpp:45-66
+    assert auto_thresholds([-1], [5]) == [5]
+    with pytest.raises(ValueError):
+        auto_thresholds([-1], [3, 3])
+
+
+def test_compute_threshold_agrees_with_oracle_restatement_on_random_histograms():
+    import oracle
+    from dsk_b200.histogram import compute_threshold
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        h = np.zeros(10001, np.uint64)
+        n = int(rng.integers(3, 200))
+        peak = int(rng.integers(2, n))
+        x = np.arange(1, n + 1)
+        shape = rng.integers(1, 10**6) * np.exp(-x / rng.uniform(0.5, 3)) + rng.integers(0, 10**5) * np.exp(-((x - peak) ** 2) / (2 * rng.uniform(1, 30) ** 2))
+        h[1:n + 1] = (shape * rng.uniform(0.7, 1.3, n)).astype(np.uint64)
+        a = compute_threshold(h, 3)
+        b = oracle.histogram_threshold(h, 3)
+        assert (a[0], a[1]) == b, trial

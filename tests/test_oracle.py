@@ -153,3 +153,22 @@ def test_survey_md5_anchor():
         _, pairs = digest(lo, hi, cnt, k)
         txt = "".join("%s %d\n" % p for p in pairs)
         assert hashlib.md5(txt.encode()).hexdigest() == md5
+
+
+# ---------------------------------------------------------------- -abundance-min auto (two-pass cutoff chain)
+AUTO = load_json("ref_runs_auto.json")["runs"]
+
+
+def _amin_list(s):
+    return [-1 if x == "auto" else int(x) for x in str(s).split(",")]
+
+
+@pytest.mark.parametrize("t", AUTO, ids=[t["name"] for t in AUTO])
+def test_reference_auto_cutoff_runs(t):
+    r = run_oracle(t["files"], t["k"], abundance_min=_amin_list(t["abundance_min"]), kind=t["solidity_kind"])
+    assert r.cutoffs == t["cutoffs"]
+    assert r.nb_solid == t["nb_solid"] == t["kmers_nb_solid"]
+    assert sparse_hist(r.hist) == t["hist"]
+    lo, hi, cnt = r.solid_kmers()
+    dg, _ = digest(lo, hi, cnt, t["k"])
+    assert dg == t["kmers_sha256"]
