@@ -726,6 +726,7 @@ static int queue_sample(dskgpu_ctx* ctx)
 
 static bool use_smem_path(const dskgpu_ctx* ctx);
 static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers);
+constexpr int SMEM_MAX_SPLIT0_DEFAULT = 1;
 
 // whole-job figures every rank plans from: k-mer total and density sample.  Picks the bin level.
 static void set_global(dskgpu_ctx* ctx, u64 g_kmers, u64 g_sample_kmers, u64 g_sample_distinct)
@@ -789,6 +790,25 @@ static bool use_smem_path(const dskgpu_ctx* ctx)
     return ctx->NB == 1 && (mode == DSKGPU_COUNT_AUTO || mode == DSKGPU_COUNT_SMEM) && ctx->smem_cap >= 64;
 }
 
+// Shared-memory path limits.  One pass over a partition takes `fit` k-mers (table filled to 75 % at the sampled density);
+// a bigger partition starts pre-split into 2^split0 hash-residue sub-passes.  Every sub-pass re-reads the records and
+// re-extracts every k-mer (~47 % of a full pass), so beyond 2^max_split0 sub-passes the L2-resident global table -- one
+// pass whatever the size -- is the cheaper path.  The size of a partition is bounded below by its heaviest minimizer
+// (9e-5 of the job at k=31, m=10): multi-G k-mer jobs and multi-GPU jobs are where this matters.
+static int smem_max_split0(const dskgpu_ctx*)
+{
+    static const int v = [] { const char* e = getenv("DSKGPU_SMEM_MAX_SPLIT0"); int x = e ? atoi(e) : SMEM_MAX_SPLIT0_DEFAULT;
+                              return std::min(std::max(x, 0), (int)CS_MAX_SPLIT0); }();
+    return v;
+}
+static double smem_fit_kmers(const dskgpu_ctx* ctx) { return std::max(64.0, (double)ctx->smem_cap * 0.75 / ctx->density); }
+static u64 smem_max_kmers(const dskgpu_ctx* ctx)
+{
+    // forced SMEM mode (tests) starts everything in one pass and lets the kernel discover the splits
+    if (ctx->cfg.count_mode == DSKGPU_COUNT_SMEM) return (u64)ctx->smem_cap * 16;
+    return (u64)(smem_fit_kmers(ctx) * (double)(1 << smem_max_split0(ctx)));
+}
+
 // k-mers a partition should hold.  Shared-memory path: what fills the table to ~52 % given the sampled density
 // (distinct / total k-mers: 0.26 for 100x reads at k=31, 0.47 at k=63, 0.43 for 30x reads).
 // Global-table path: a quarter of the table capacity, so that groups of partitions can be sized to the measured occupancy.
@@ -831,6 +851,25 @@ static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh /*[2 <<
     }
     ctx->g_part_kmers.push_back(acc); ctx->g_part_recs.push_back(gr); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
     P += 1;
+    if (use_smem_path(ctx) && ctx->cfg.count_mode == DSKGPU_COUNT_AUTO) {
+        // partitions beyond the reach of the shared-memory path are renumbered to the end (heaviest first, so that
+        // p % world_size spreads them evenly): the global-table path then sees one contiguous run of records on every
+        // rank instead of many short ones.  Every rank derives the same order from the same whole-job histogram.
+        const u64 lim = smem_max_kmers(ctx);
+        std::vector<u32> heavy;
+        for (u32 p = 0; p < P; p++) if (ctx->g_part_kmers[p] > lim) heavy.push_back(p);
+        if (!heavy.empty() && heavy.size() < P) {
+            std::stable_sort(heavy.begin(), heavy.end(), [&](u32 a, u32 b) { return ctx->g_part_kmers[a] > ctx->g_part_kmers[b]; });
+            std::vector<u32> newid(P); std::vector<char> is_heavy(P, 0);
+            for (u32 h : heavy) is_heavy[h] = 1;
+            u32 nid = 0;
+            for (u32 p = 0; p < P; p++) if (!is_heavy[p]) newid[p] = nid++;
+            for (u32 h : heavy) newid[h] = nid++;
+            auto permute = [&](std::vector<u64>& v) { std::vector<u64> t(P); for (u32 p = 0; p < P; p++) t[newid[p]] = v[p]; v.swap(t); };
+            permute(ctx->g_part_kmers); permute(ctx->g_part_recs); permute(ctx->h_part_recs); permute(ctx->h_part_kmers);
+            for (u32 b = 0; b < NB_; b++) b2p[b] = newid[b2p[b]];
+        }
+    }
     const u32 W = (u32)ctx->cfg.world_size;
     while (P % W) { ctx->g_part_kmers.push_back(0); ctx->g_part_recs.push_back(0); ctx->h_part_recs.push_back(0); ctx->h_part_kmers.push_back(0); P++; }
     ctx->nparts = P; ctx->st.nb_partitions = P;
@@ -888,8 +927,9 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
         // hash residues; beyond 16 sub-passes it goes to the global paths.  Forced SMEM mode (tests) starts everything in one
         // pass and lets the kernel discover the splits.
         const bool presplit = ctx->cfg.count_mode != DSKGPU_COUNT_SMEM;
-        const double fit = std::max(64.0, (double)ctx->smem_cap * 0.75 / ctx->density);     // k-mers one pass can take
-        const u64 smem_max = presplit ? (u64)(fit * (double)(1 << CS_MAX_SPLIT0)) : (u64)ctx->smem_cap * 16;
+        const double fit = smem_fit_kmers(ctx);                                             // k-mers one pass can take
+        const u64 smem_max = smem_max_kmers(ctx);
+        const unsigned max_split0 = (unsigned)smem_max_split0(ctx);
         std::vector<SmemJob> jobs;
         std::vector<u64> off(np + 1, 0);
         std::vector<char> big(np, 0);
@@ -898,7 +938,7 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
             if (prec[i] == 0) continue;
             if (smem && pkm[i] <= smem_max && prec[i] < 0xFFFFFFFFull) {
                 SmemJob j; j.rec_begin = off[i]; j.nrec = (unsigned)prec[i]; j.split0 = 0;
-                if (presplit) while (j.split0 < (unsigned)CS_MAX_SPLIT0 && (double)pkm[i] > fit * (double)(1u << j.split0)) j.split0++;
+                if (presplit) while (j.split0 < max_split0 && (double)pkm[i] > fit * (double)(1u << j.split0)) j.split0++;
                 jobs.push_back(j);
             }
             else big[i] = 1;

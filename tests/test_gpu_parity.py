@@ -193,6 +193,16 @@ def test_synthetic_medium_modes(mode):
     assert sc.getInfo()["engine"]["nb_partitions"] > 4
 
 
+@pytest.mark.parametrize("k", [31, 63])
+def test_auto_mixed_shared_memory_and_global_table(k):
+    # a shared-memory table far smaller than the heavy minimizer bins, in AUTO mode: the partitions beyond two sub-passes
+    # are renumbered to the end and counted by the global table, the others by the shared-memory path, in the same job
+    buf, n, _ = reads_fasta(G=1_000_000, coverage=30, L=150, err=0.01, seed=11)
+    sc = compare_with_oracle([buf[:n].tobytes()], k, engine=dict(count_mode="auto", smem_table_slots=256, hash_log2_slots=18))
+    st = sc.getInfo()["engine"]
+    assert st["nb_parts_smem"] > 0 and st["nb_groups_hash"] > 0 and st["smem_table_slots"] == 256
+
+
 def test_histo2d_assembly_vs_reads():
     g = genome_codes(200_000, seed=9)
     asm = assembly_fasta(g)
@@ -271,7 +281,7 @@ def split_records(data, parts):
 
 
 @pytest.mark.parametrize("proto", ["v1", "v2"])
-@pytest.mark.parametrize("W,k,mode", [(2, 31, "auto"), (3, 31, "hash"), (2, 63, "auto"), (4, 31, "sort"), (3, 63, "smem")])
+@pytest.mark.parametrize("W,k,mode", [(2, 31, "auto"), (3, 31, "hash"), (2, 63, "auto"), (4, 31, "sort"), (3, 63, "smem"), (3, 31, "auto-tiny")])
 def test_multi_rank_exchange_in_process(W, k, mode, proto):
     """N ranks as N contexts on one GPU: every rank parses a slice, the scatter kernel routes records to the owner
     of their partition (p % W), every rank counts only what it owns.  Union of the ranks' outputs == oracle."""
@@ -279,7 +289,10 @@ def test_multi_rank_exchange_in_process(W, k, mode, proto):
     buf, n, _ = reads_fasta(G=400_000, coverage=30, L=150, err=0.01, seed=77)
     data = buf[:n].tobytes()
     ref = oracle.count_files([data], k, abundance_min=2)
-    engines = [GpuCounter(kmer_size=k, abundance_min=2, rank=r, world_size=W, count_mode=mode, hash_log2_slots=16) for r in range(W)]
+    extra = {}
+    if mode == "auto-tiny":               # heavy partitions (global table) and light ones (shared memory) on every rank
+        mode, extra = "auto", dict(smem_table_slots=256)
+    engines = [GpuCounter(kmer_size=k, abundance_min=2, rank=r, world_size=W, count_mode=mode, hash_log2_slots=16, **extra) for r in range(W)]
     try:
         for e, piece in zip(engines, split_records(data, W)):
             e.push_bytes(piece)
@@ -300,6 +313,8 @@ def test_multi_rank_exchange_in_process(W, k, mode, proto):
             st = e.stats()
             valid += st["kmers_nb_valid"]; distinct += st["kmers_nb_distinct"]
             assert st["nb_partitions"] == P
+            if extra:
+                assert st["nb_parts_smem"] > 0 and st["nb_groups_hash"] > 0
         keys = np.concatenate(keys); cnts = np.concatenate(cnts)
         order = np.lexsort((keys[:, 0], keys[:, -1])) if keys.shape[1] == 2 else np.argsort(keys[:, 0], kind="stable")
         keys, cnts = keys[order], cnts[order]
