@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Multi-process, multi-GPU parity check of the exchange + counting path (run under torchrun on a box with >= 2 GPUs):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py
+
+Every rank parses its slice of one seeded read set, `distributed_finish` routes the super-k-mer records to the rank
+owning their partition over NVLink (CUDA-IPC peer pointers) and every rank counts what it owns.  Rank 0 gathers the
+ranks' solid sets + histograms and compares their union with the CPU oracle on the whole read set (bit-exact).
+Test infrastructure: the oracle is the checker here, never on the product path.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def split_records(data, parts):
+    cuts = [0]
+    for i in range(1, parts):
+        j = data.find(b"\n>", len(data) * i // parts)
+        cuts.append(len(data) if j < 0 else j + 1)
+    cuts.append(len(data))
+    return [data[cuts[i]:cuts[i + 1]] for i in range(parts)]
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from dsk_b200 import GpuCounter
+    from dsk_b200.distributed import distributed_finish
+    from dsk_b200.synth import reads_fasta
+    rank = int(os.environ.get("RANK", 0)); W = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    cases = [(31, "auto", 400_000, 30, {}), (63, "auto", 400_000, 30, {}), (31, "hash", 300_000, 20, dict(hash_log2_slots=16)),
+             (31, "sort", 300_000, 20, {}), (31, "auto", 300_000, 30, dict(smem_table_slots=256, hash_log2_slots=16)),
+             (31, "auto", 4_000_000, 40, {})]
+    for k, mode, G, cov, extra in cases:
+        buf, n, _ = reads_fasta(G=G, coverage=cov, L=150, err=0.01, seed=1234 + k)
+        data = buf[:n].tobytes()
+        piece = split_records(data, W)[rank]
+        eng = GpuCounter(kmer_size=k, abundance_min=2, device=local, rank=rank, world_size=W, count_mode=mode,
+                         stream=torch.cuda.current_stream().cuda_stream, **extra)
+        for rep in range(2):                      # second round re-uses receive buffers + peer handles (no IPC re-open)
+            eng.reset()
+            eng.push_bytes(piece)
+            distributed_finish(eng, dist, dev)
+            kk, cc = eng.solid()
+            h1 = eng.histogram()[0]
+            st = eng.stats()
+            mine = (kk, cc, h1, st["kmers_nb_valid"], st["kmers_nb_distinct"], st["nb_partitions"])
+            allr = [None] * W
+            dist.all_gather_object(allr, mine)
+            if rank == 0:
+                ref = oracle.count_files([data], k, abundance_min=2)
+                keys = np.concatenate([a[0] for a in allr]); cnts = np.concatenate([a[1] for a in allr])
+                hist = np.sum([a[2] for a in allr], axis=0, dtype=np.uint64)
+                valid = sum(a[3] for a in allr); distinct = sum(a[4] for a in allr)
+                order = np.lexsort((keys[:, 0], keys[:, -1])) if keys.shape[1] == 2 else np.argsort(keys[:, 0], kind="stable")
+                keys, cnts = keys[order], cnts[order]
+                lo, hi, rc = ref.solid_kmers()
+                good = (valid == ref.kmers_nb_valid and distinct == ref.nb_distinct and len(cnts) == len(rc)
+                        and (keys[:, 0] == lo).all() and (cnts.astype(np.int64) == rc).all() and (hist == ref.hist).all()
+                        and (keys.shape[1] == 1 or (keys[:, 1] == hi).all()))
+                ok = ok and bool(good)
+                print("mgpu_check W=%d k=%d mode=%s G=%d rep=%d: %s  (valid %d, distinct %d, solid %d, partitions %d, per-rank solid %s)" % (
+                    W, k, mode, G, rep, "OK" if good else "MISMATCH", valid, distinct, len(cnts), allr[0][5], [len(a[1]) for a in allr]), flush=True)
+        eng.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("mgpu_check:", "ALL OK" if ok else "FAILED", flush=True)
+    return 0 if int(flag[0]) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
