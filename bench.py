@@ -64,10 +64,46 @@ def ncu_traffic(kernel, args):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: an NVML polling thread (every ~2 ms, so even a
+    60 ms region yields tens of samples); `nvidia-smi -lms 100` only as the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        import threading
+        self.p = None; self.f = None; self.samples = []; self.reasons = set(); self.max_mhz = None; self.power = []
+        self._stop = threading.Event(); self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for bit, nm in names.items():
+                            if r & bit:
+                                self.reasons.add(nm)
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -77,6 +113,16 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self._stop.set(); self.thread.join(timeout=2)
+            sm = sorted(self.samples)
+            if sm:
+                out.update(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], samples=len(sm), source="nvml, 2 ms polling over the timed region")
+            if self.power:
+                out["power_w_max"] = max(self.power)
+            out["sm_max_mhz"] = self.max_mhz
+            out["reasons"] = sorted(self.reasons)
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -100,6 +146,7 @@ class ClockSampler:
             sm.sort()
             out["sm_mhz"] = sm[len(sm) // 2]
             out["samples"] = len(sm)
+            out["source"] = "nvidia-smi -lms 100"
         out["reasons"] = sorted(reasons)
         return out
 
@@ -275,7 +322,10 @@ def main():
         h_asm = torch.empty(dev_asm.numel(), dtype=torch.uint8, pin_memory=True); h_asm.copy_(dev_asm)
     bank_kw = dict(nb_banks=2, per_bank_counts=True, histo2d=True) if args.histo2d else {}
     rb = 1 if args.histo2d else 0                      # bank id of the reads
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream carries everything: the library's kernels, torch's copies and the NCCL metadata
+    # collectives are ordered on it without host syncs, and the CUDA events below are recorded on the launching stream
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
 
     def barrier():
         if world > 1:
@@ -317,13 +367,24 @@ def main():
     clocks = sampler.stop() if sampler else None
     st = eng.stats()
     kmers = st["kmers_nb_valid"]
+    # size-independent invariant of the last timed step (after the clock stopped): every valid k-mer parsed by some rank
+    # was counted by the rank owning its partition, i.e. sum_i i * histogram[i] over all ranks == valid k-mers over all
+    # ranks (holds while no abundance reaches 10 000, Histogram.hpp:92,221 -- true for the synthetic read sets here)
+    import numpy as np
+    h1 = eng.histogram()[0]
+    mass = int((h1.astype(np.uint64) * np.arange(h1.size, dtype=np.uint64)).sum())
     t = torch.tensor([ms, float(kmers)], dtype=torch.float64, device="cuda")
+    chk = torch.tensor([mass, int(kmers), int(st["kmers_nb_distinct"]), int(st["kmers_nb_solid"])], dtype=torch.int64, device="cuda")
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
         ms_all, kmers_all = float(tmax[0]), float(tsum[1])
     else:
         ms_all, kmers_all = ms, float(kmers)
+    chk = [int(x) for x in chk.cpu()]
+    checks = {"histogram_mass": chk[0], "valid_kmers": chk[1], "distinct_kmers": chk[2], "solid_kmers": chk[3],
+              "every_valid_kmer_counted": (chk[0] == chk[1]) if not args.histo2d else None}
     value = kmers_all * args.steps / (ms_all / 1e3) / 1e9
 
     # ---- e2e leg: host buffers in, host results out ------------------------------------------------------
@@ -383,6 +444,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms": stage,
+            "checks": checks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom_kernel, args),
                          "kernel": dom_kernel, "launches": int(dom_n), "avg_launch_ms": 1e3 * dom_avg_s,
                          "peak_source": peak_src, "algorithmic_bytes_per_kmer": ab["S2_expand"] + ab["S3_sort"]},

@@ -62,7 +62,9 @@ def distributed_finish(eng, dist, device):
 
     W, rank = dist.get_world_size(), dist.get_rank()
     cur = torch.cuda.current_stream(device)
-    same_stream = eng.stream is not None and int(eng.stream) == int(cur.cuda_stream)
+    # cfg.stream == NULL (also what torch reports for the legacy default stream) means a library-OWNED non-blocking
+    # stream: it is never "the same stream" as torch's, so the two sides must be ordered by explicit syncs.
+    same_stream = bool(eng.stream) and int(eng.stream) == int(cur.cuda_stream)
 
     def to_torch():          # work queued by the library must be visible to torch's stream
         if not same_stream:

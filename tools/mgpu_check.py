@@ -39,19 +39,33 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
+    import faulthandler
+    import time
+    t_start = time.time()
+
+    def progress(msg):                               # every rank, so a hang can be localised from the log
+        sys.stderr.write("[rank %d +%6.1fs] %s\n" % (rank, time.time() - t_start, msg)); sys.stderr.flush()
     cases = [(31, "auto", 400_000, 30, {}), (63, "auto", 400_000, 30, {}), (31, "hash", 300_000, 20, dict(hash_log2_slots=16)),
              (31, "sort", 300_000, 20, {}), (31, "auto", 300_000, 30, dict(smem_table_slots=256, hash_log2_slots=16)),
-             (31, "auto", 4_000_000, 40, {})]
-    for k, mode, G, cov, extra in cases:
+             (31, "auto", 2_000_000, 30, {}), (63, "auto", 1_000_000, 30, {})]
+    shared = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(shared)
+    for ci, (k, mode, G, cov, extra) in enumerate(cases):
         buf, n, _ = reads_fasta(G=G, coverage=cov, L=150, err=0.01, seed=1234 + k)
         data = buf[:n].tobytes()
         piece = split_records(data, W)[rank]
+        ref = oracle.count_files([data], k, abundance_min=2) if rank == 0 else None
+        faulthandler.dump_traceback_later(120, exit=True)      # a stuck exchange ends the run with stacks instead of burning the box
+        # odd cases run on a library-owned stream (explicit host syncs order it against torch's NCCL work), even cases on
+        # one shared torch stream (what bench.py does)
         eng = GpuCounter(kmer_size=k, abundance_min=2, device=local, rank=rank, world_size=W, count_mode=mode,
-                         stream=torch.cuda.current_stream().cuda_stream, **extra)
-        for rep in range(2):                      # second round re-uses receive buffers + peer handles (no IPC re-open)
+                         stream=(shared.cuda_stream if ci % 2 == 0 else None), **extra)
+        for rep in range(3):                      # second round re-uses receive buffers + peer handles (no IPC re-open)
+            progress("case %d k=%d %s rep %d: push" % (ci, k, mode, rep))
             eng.reset()
             eng.push_bytes(piece)
             distributed_finish(eng, dist, dev)
+            progress("case %d rep %d: finished, %d partitions" % (ci, rep, eng.stats()["nb_partitions"]))
             kk, cc = eng.solid()
             h1 = eng.histogram()[0]
             st = eng.stats()
@@ -59,7 +73,6 @@ def main():
             allr = [None] * W
             dist.all_gather_object(allr, mine)
             if rank == 0:
-                ref = oracle.count_files([data], k, abundance_min=2)
                 keys = np.concatenate([a[0] for a in allr]); cnts = np.concatenate([a[1] for a in allr])
                 hist = np.sum([a[2] for a in allr], axis=0, dtype=np.uint64)
                 valid = sum(a[3] for a in allr); distinct = sum(a[4] for a in allr)
@@ -72,6 +85,7 @@ def main():
                 ok = ok and bool(good)
                 print("mgpu_check W=%d k=%d mode=%s G=%d rep=%d: %s  (valid %d, distinct %d, solid %d, partitions %d, per-rank solid %s)" % (
                     W, k, mode, G, rep, "OK" if good else "MISMATCH", valid, distinct, len(cnts), allr[0][5], [len(a[1]) for a in allr]), flush=True)
+        faulthandler.cancel_dump_traceback_later()
         eng.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
