@@ -66,6 +66,39 @@ __device__ __forceinline__ bool process_counts(const u32* cv, const SolidityPara
     }
 }
 
+// The same chain without its side effects: returns solidity, the abundance to dump, the 1-D histogram bin (0 = not
+// recorded) and the flat 2-D bin (i1 + 10001 * i2, or ~0u without -histo2D).  The caller applies the histogram updates
+// (count_smem.cuh aggregates them per warp: three quarters of the distinct k-mers of a read set land in ONE bin).
+constexpr u32 H2_NONE = 0xFFFFFFFFu;
+__device__ __forceinline__ bool eval_counts(const u32* cv, const SolidityParams& sp, int32_t* sum_out, u32* bin1, u32* bin2)
+{
+    const int nb = sp.nbanks;
+    int32_t sum = 0;
+    if (nb == 1) sum = (int32_t)cv[0];
+    else for (int b = 0; b < nb; b++) if (sp.kind != 5 || sp.solid_vec[b]) sum += (int32_t)cv[b];   // CountProcessorChain.hpp:158-169
+    *sum_out = sum;
+    *bin1 = histo_bin(sum);
+    *bin2 = H2_NONE;
+    if (sp.bank_hist) {                                              // CountProcessorCutoff.hpp:113-116: bank i sees count[i]
+        for (int b = 0; b < nb; b++) { const u32 bb = histo_bin((int32_t)cv[b]); if (bb) atomicAdd(&sp.bank_hist[(size_t)b * 10001u + bb], 1ULL); }
+    }
+    if (sp.histo2d) {                                                // Histogram.hpp:92-98 inc2D, clamps of SURVEY 8(a)-13(v)
+        u32 i1 = (u32)(sum - (int32_t)cv[0]) & 0xFFFFu, i2 = cv[0] & 0xFFFFu;
+        if (i1 >= 10000u) i1 = 10000u;
+        if (i2 >= 10u) i2 = 10u;
+        *bin2 = i1 + 10001u * i2;
+    }
+    auto inr = [&](long long x, long long lo) { return lo <= x && x <= sp.amax; };
+    switch (sp.kind) {
+    case 0: return inr(sum, sp.amin[0]);
+    case 1: { u32 v = cv[0]; for (int b = 1; b < nb; b++) v = min(v, cv[b]); return inr(v, sp.amin[0]); }
+    case 2: { u32 v = cv[0]; for (int b = 1; b < nb; b++) v = max(v, cv[b]); return inr(v, sp.amin[0]); }
+    case 3: { for (int b = 0; b < nb; b++) if (inr(cv[b], sp.amin[b])) return true; return false; }
+    case 4: { for (int b = 0; b < nb; b++) if (!inr(cv[b], sp.amin[b])) return false; return true; }
+    default: { for (int b = 0; b < nb; b++) { bool in = inr(cv[b], sp.amin[b]); if (sp.solid_vec[b] != in) return false; } return true; }
+    }
+}
+
 __device__ __forceinline__ void flush_hist(const u32* s_hist, unsigned long long* g_hist)
 {
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) { u32 v = s_hist[i]; if (v) atomicAdd(&g_hist[i], (unsigned long long)v); }

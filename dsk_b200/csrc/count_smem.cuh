@@ -46,10 +46,13 @@ constexpr int CS_MAX_SPLIT0 = 4;
 
 // bytes of dynamic shared memory for a table of `cap` slots (host + device agree through this one function):
 // table keys + counts, record staging [warps][32][RW], retry queue [warps][QCAP] keys + slots
-template <int KW> DSK_HD size_t cs_smem_bytes(u32 cap)
+// nb = counts kept per slot (1, or one per bank when the processors need per-bank counts: -histo2D, solidity kinds)
+template <int KW> DSK_HD size_t cs_smem_bytes(u32 cap, int nb = 1)
 {
-    return (size_t)cap * (8 * KW + 4) + (size_t)CS_WARPS * 32 * 2 * KW * 8 + (size_t)CS_WARPS * CS_QCAP * (8 * KW + 4);
+    return (size_t)cap * (8 * KW + 4 * nb) + (size_t)CS_WARPS * 32 * 2 * KW * 8 + (size_t)CS_WARPS * CS_QCAP * (8 * KW + 4);
 }
+constexpr int CS_H2_I1 = 64;                   // -histo2D: bins (i1 < 64, any i2) are accumulated in shared memory
+constexpr int CS_MAX_BANKS = 4;                // per-bank counts beyond this go to the global-table path
 
 #ifdef __CUDACC__
 
@@ -113,20 +116,26 @@ __device__ __forceinline__ u64 cs_window(const u64* r, int p)
     return o ? ((a << (2 * o)) | (b >> (64 - 2 * o))) : a;
 }
 
-template <int KW>
+// MB = false: one count per k-mer (banks summed), solidity = abundance range [amin, amax] -- the dsk default.
+// MB = true : `nb` counts per slot (the record's bank byte picks the column); the sweep runs the whole CountProcessor
+//             chain of count.cuh (`process_counts`: per-bank solidity kinds, -histo2D, per-bank histograms) on them.
+template <int KW, bool MB>
 __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const u64* __restrict__ recs, const SmemJob* __restrict__ jobs, u32 njobs,
                                                               int k, u32 cap, long long amin, long long amax,
                                                               u64* __restrict__ out_keys, u32* __restrict__ out_vals, u64 out_cap,
-                                                              unsigned long long* __restrict__ g_hist, Counters* ctr, u32* work_counter)
+                                                              unsigned long long* __restrict__ g_hist, Counters* ctr, u32* work_counter,
+                                                              int nb_arg, const SolidityParams spar, unsigned long long* __restrict__ g_hist2d)
 {
     constexpr int RW = 2 * KW;
+    const u32 nb = MB ? (u32)nb_arg : 1u;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     u64* s_keys = reinterpret_cast<u64*>(s_dyn);                                   // [cap][KW]
-    u32* s_counts = reinterpret_cast<u32*>(s_dyn + (size_t)cap * 8 * KW);          // [cap]
-    u64* s_rec = reinterpret_cast<u64*>(s_dyn + (size_t)cap * (8 * KW + 4));       // [CS_WARPS][32][RW]   (cap % 4 == 0 keeps it 16-byte aligned)
+    u32* s_counts = reinterpret_cast<u32*>(s_dyn + (size_t)cap * 8 * KW);          // [cap][nb]
+    u64* s_rec = reinterpret_cast<u64*>(s_dyn + (size_t)cap * (8 * KW + 4 * nb));  // [CS_WARPS][32][RW]   (cap % 4 == 0 keeps it 16-byte aligned)
     u64* s_qkey = s_rec + (size_t)CS_WARPS * 32 * RW;                              // [CS_WARPS][CS_QCAP][KW]
     u32* s_qslot = reinterpret_cast<u32*>(s_qkey + (size_t)CS_WARPS * CS_QCAP * KW);   // [CS_WARPS][CS_QCAP]
     __shared__ u32 s_hist[HIST_SMEM_BINS];
+    __shared__ u32 s_h2[MB ? 11 * CS_H2_I1 : 1];                                   // -histo2D bins with dim-1 index < CS_H2_I1, all 11 dim-2 rows
     __shared__ u32 s_wsum[CS_WARPS];
     __shared__ u32 s_job, s_flag, s_chunk;
     __shared__ unsigned long long s_base;
@@ -135,8 +144,9 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
     const u32 lt_mask = (1u << lane) - 1u;
     const u64 EMPTY = ~0ULL;
     for (u32 i = t; i < cap * KW; i += CS_THREADS) s_keys[i] = EMPTY;
-    for (u32 i = t; i < cap; i += CS_THREADS) s_counts[i] = 0;
+    for (u32 i = t; i < cap * nb; i += CS_THREADS) s_counts[i] = 0;
     for (int i = t; i < HIST_SMEM_BINS; i += CS_THREADS) s_hist[i] = 0;
+    if constexpr (MB) for (int i = t; i < 11 * CS_H2_I1; i += CS_THREADS) s_h2[i] = 0;
     if (t == 0) s_flag = 0;
     u32 n1 = 0, n2 = 0, ndist = 0, nsplit = 0;
     u64* my_rec = s_rec + (size_t)warp * 32 * RW;
@@ -154,10 +164,11 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 Kmer<KW> key;
 #pragma unroll
                 for (int q = 0; q < KW; q++) key.w[q] = my_qkey[idx * KW + q];
-                u32 slot = my_qslot[idx];
+                u32 slot = my_qslot[idx], bank = 0;
+                if constexpr (MB) { bank = slot >> 16; slot &= 0xFFFFu; }             // cap <= 16384
                 bool ok = false;
                 for (int p = 0; p < CS_MAXPROBE && !ok; p++) { ok = cs_probe(keys_a, slot, key); if (!ok) slot = (slot + 1 == cap) ? 0u : slot + 1; }
-                if (ok) cs_inc32(counts_a + slot * 4u); else s_flag = 1u;
+                if (ok) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u); else s_flag = 1u;
             }
         }
         __syncwarp();
@@ -217,6 +228,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                     const u32 ex_r = __shfl_sync(0xFFFFFFFFu, exc, r & 31);
                     const u32 nk_r = __shfl_sync(0xFFFFFFFFu, nk, r & 31);
                     int cnt = 0, j0 = 0;
+                    u32 bank = 0;
                     u64 rw[RW];
                     Kmer<KW> f, rc;
                     u64 nextb = 0;
@@ -226,6 +238,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                         const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(my_rec + r * RW);
                         const ulonglong2 a = rp[0]; rw[0] = a.x; rw[1] = a.y;
                         if constexpr (RW == 4) { const ulonglong2 b = rp[1]; rw[2] = b.x; rw[3] = b.y; }
+                        if constexpr (MB) bank = (u32)rw[RW - 1] & 0xFFu;
                         if constexpr (KW == 1) f.w[0] = cs_window<RW>(rw, j0) >> (64 - 2 * k);
                         else { const u64 hw[2] = {cs_window<RW>(rw, j0), cs_window<RW>(rw, j0 + 32)}; f = rec_first_kmer2(hw, k); }
                         rc = kmer_revcomp(f, k);
@@ -246,13 +259,13 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                             }
                         }
                         const u32 pm = __ballot_sync(0xFFFFFFFFu, pending);         // (also the reconvergence point of the probes)
-                        if (found) cs_inc32(counts_a + slot * 4u);
+                        if (found) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u);
                         if (pm) {
                             if (pending) {
                                 const u32 pos = qn + (u32)__popc(pm & lt_mask);
 #pragma unroll
                                 for (int q = 0; q < KW; q++) my_qkey[pos * KW + q] = c.w[q];
-                                my_qslot[pos] = slot;
+                                my_qslot[pos] = MB ? (slot | (bank << 16)) : slot;
                             }
                             qn += (u32)__popc(pm);
                             if (qn > CS_QCAP - 32) { drain(qn); qn = 0; }
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
             if (overflowed) {
                 // clear, then split this item in two (or give up: reported, never silent)
                 for (u32 i = t; i < cap * KW; i += CS_THREADS) s_keys[i] = EMPTY;
-                for (u32 i = t; i < cap; i += CS_THREADS) s_counts[i] = 0;
+                for (u32 i = t; i < cap * nb; i += CS_THREADS) s_counts[i] = 0;
                 if (t == 0) s_flag = 0;
                 if (lvl >= (u32)CS_MAX_SPLIT) { if (t == 0) atomicAdd(&ctr->smem_failed, 1u); }
                 else { stack[sp++] = ((lvl + 1) << 16) | (res + (1u << lvl)); stack[sp++] = ((lvl + 1) << 16) | res; nsplit++; }
@@ -280,6 +293,36 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
             // a slot is occupied iff its count is non-zero (a claim is always followed by its increment), so the scan reads
             // only the counts, four per 16-byte load; keys are read for the solid slots alone.  cap % (4 * CS_THREADS) == 0.
             u32 solidm = 0;                                                        // bit (4 * v + q): slot 4 * (v * CS_THREADS + t) + q
+            if constexpr (MB) {
+                // per-bank counts: thread t owns slots t, t + CS_THREADS, ... (bit v of solidm: slot v * CS_THREADS + t); the
+                // abundance to dump (CountProcessorDump: Count(kmer, sum)) replaces the bank-0 count once the chain has run
+                // Histogram updates are aggregated per warp (match.any on the bin): most distinct k-mers of a read set share one bin.
+                const u32 nv = (cap + CS_THREADS - 1) / CS_THREADS;                // uniform trip count: the warp votes below
+                for (u32 v = 0; v < nv; v++) {
+                    const u32 sl = v * CS_THREADS + (u32)t;
+                    u32 cv[MAXB]; u32 any = 0;
+                    if (sl < cap) for (u32 b = 0; b < nb; b++) { cv[b] = s_counts[sl * nb + b]; any |= cv[b]; }
+                    u32 bin1 = 0, bin2 = H2_NONE;
+                    if (any) {
+                        ndist++;
+                        int32_t sum;
+                        if (eval_counts(cv, spar, &sum, &bin1, &bin2)) solidm |= 1u << v;
+                        s_counts[sl * nb] = (u32)sum;
+                    }
+                    const u32 p1 = __match_any_sync(0xFFFFFFFFu, bin1);
+                    if (bin1 && lane == __ffs((int)p1) - 1) {
+                        const u32 c = (u32)__popc(p1);
+                        if (bin1 < HIST_SMEM_BINS) atomicAdd(&s_hist[bin1], c); else atomicAdd(&g_hist[bin1], (unsigned long long)c);
+                    }
+                    if (spar.histo2d) {
+                        const u32 p2 = __match_any_sync(0xFFFFFFFFu, bin2);
+                        if (bin2 != H2_NONE && lane == __ffs((int)p2) - 1) {
+                            const u32 c = (u32)__popc(p2), i2 = bin2 / 10001u, i1 = bin2 - i2 * 10001u;
+                            if (i1 < CS_H2_I1) atomicAdd(&s_h2[i2 * CS_H2_I1 + i1], c); else atomicAdd(&g_hist2d[bin2], (unsigned long long)c);
+                        }
+                    }
+                }
+            } else
             {
                 const uint4* c4 = reinterpret_cast<const uint4*>(s_counts);
                 int v = 0;
@@ -315,15 +358,22 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 u32 m = solidm;
                 while (m) {
                     const int b = __ffs((int)m) - 1; m &= m - 1;
-                    const u32 slot = 4u * ((u32)(b >> 2) * CS_THREADS + (u32)t) + (u32)(b & 3);
+                    const u32 slot = MB ? (u32)b * CS_THREADS + (u32)t : 4u * ((u32)(b >> 2) * CS_THREADS + (u32)t) + (u32)(b & 3);
                     if (pos < out_cap) {
 #pragma unroll
                         for (int q = 0; q < KW; q++) out_keys[pos * KW + q] = s_keys[slot * KW + q];
-                        out_vals[pos] = s_counts[slot];
+                        out_vals[pos] = s_counts[MB ? slot * nb : slot];
                     } else atomicExch(&ctr->overflow, 2u);
                     pos++;
                 }
             }
+            if constexpr (MB) {
+                for (u32 sl = t; sl < cap; sl += CS_THREADS) {
+#pragma unroll
+                    for (int q = 0; q < KW; q++) s_keys[sl * KW + q] = EMPTY;
+                    for (u32 b = 0; b < nb; b++) s_counts[sl * nb + b] = 0;
+                }
+            } else
             {
                 // every thread clears exactly the slot groups it scanned (nobody else reads or writes them in this phase)
                 ulonglong2* k2 = reinterpret_cast<ulonglong2*>(s_keys);
@@ -347,6 +397,13 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
     }
     __syncthreads();
     flush_hist(s_hist, g_hist);
+    if constexpr (MB) {
+        if (spar.histo2d)
+            for (int i = t; i < 11 * CS_H2_I1; i += CS_THREADS) {
+                const u32 c = s_h2[i];
+                if (c) atomicAdd(&g_hist2d[(u32)(i % CS_H2_I1) + 10001u * (u32)(i / CS_H2_I1)], (unsigned long long)c);
+            }
+    }
     if (t == 0 && nsplit) atomicAdd(&ctr->smem_splits, nsplit);
 }
 

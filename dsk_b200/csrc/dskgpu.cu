@@ -226,20 +226,23 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
         CK(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, cfg->device));
         CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device));
         ctx->num_sms = nsm > 0 ? nsm : 148;
+        // the kernel variant this context will launch: 64/128-bit keys x (one summed count | one count per bank)
+        const bool mb = ctx->NB > 1;
+        const void* fn = ctx->KW == 1 ? (mb ? (const void*)k_count_smem<1, true> : (const void*)k_count_smem<1, false>)
+                                      : (mb ? (const void*)k_count_smem<2, true> : (const void*)k_count_smem<2, false>);
         cudaFuncAttributes fa;
-        if (ctx->KW == 1) CK(cudaFuncGetAttributes(&fa, k_count_smem<1>)); else CK(cudaFuncGetAttributes(&fa, k_count_smem<2>));
+        CK(cudaFuncGetAttributes(&fa, fn));
         size_t avail = std::min<size_t>((size_t)max_optin, (size_t)per_sm / CS_CTAS_PER_SM - (size_t)reserved) - fa.sharedSizeBytes;
         const size_t fixed = ctx->KW == 1 ? cs_smem_bytes<1>(0) : cs_smem_bytes<2>(0);
-        u32 cap = avail > fixed ? (u32)((avail - fixed) / (size_t)(8 * ctx->KW + 4)) : 0;
+        u32 cap = avail > fixed ? (u32)((avail - fixed) / (size_t)(8 * ctx->KW + 4 * ctx->NB)) : 0;
         cap = cap / 1024 * 1024;
         if (cap > 16384u) cap = 16384u;                            // the sweep keeps one solid bit per slot of a thread in 32 bits
         if (cfg->smem_table_slots > 0) cap = std::min<u32>(cap, std::max<u32>(64u, (u32)cfg->smem_table_slots / 4 * 4));
+        if (ctx->NB > CS_MAX_BANKS) cap = 0;                       // many banks: the global-table path
         ctx->smem_cap = cap;
-        const size_t dyn = ctx->KW == 1 ? cs_smem_bytes<1>(cap) : cs_smem_bytes<2>(cap);
-        if (ctx->KW == 1) { CK(cudaFuncSetAttribute(k_count_smem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                            CK(cudaFuncSetAttribute(k_count_smem<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); }
-        else { CK(cudaFuncSetAttribute(k_count_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-               CK(cudaFuncSetAttribute(k_count_smem<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); }
+        const size_t dyn = ctx->KW == 1 ? cs_smem_bytes<1>(cap, ctx->NB) : cs_smem_bytes<2>(cap, ctx->NB);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     *out = ctx;
     int r = dskgpu_reset(ctx);
@@ -787,7 +790,7 @@ static int fetch_local_bin_hist(dskgpu_ctx* ctx)
 static bool use_smem_path(const dskgpu_ctx* ctx)
 {
     const int mode = ctx->cfg.count_mode;
-    return ctx->NB == 1 && (mode == DSKGPU_COUNT_AUTO || mode == DSKGPU_COUNT_SMEM) && ctx->smem_cap >= 64;
+    return ctx->NB <= CS_MAX_BANKS && (mode == DSKGPU_COUNT_AUTO || mode == DSKGPU_COUNT_SMEM) && ctx->smem_cap >= 64;
 }
 
 // Shared-memory path limits.  One pass over a partition takes `fit` k-mers (table filled to 75 % at the sampled density);
@@ -953,13 +956,21 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
             CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));      // jobs is a temporary
             const unsigned grid = (unsigned)std::min<size_t>(jobs.size(), (size_t)ctx->num_sms * CS_CTAS_PER_SM);
-            const size_t dyn = KW == 1 ? cs_smem_bytes<1>(ctx->smem_cap) : cs_smem_bytes<2>(ctx->smem_cap);
+            const size_t dyn = cs_smem_bytes<KW>(ctx->smem_cap, ctx->NB);
             cudaEvent_t a = get_event(ctx), b = get_event(ctx);
             cudaEventRecord(a, ctx->stream);
-            k_count_smem<KW><<<grid, CS_THREADS, dyn, ctx->stream>>>(recs, (const SmemJob*)ctx->jobs.p, (u32)jobs.size(), ctx->k, ctx->smem_cap,
+            if (ctx->NB == 1)
+                k_count_smem<KW, false><<<grid, CS_THREADS, dyn, ctx->stream>>>(recs, (const SmemJob*)ctx->jobs.p, (u32)jobs.size(), ctx->k, ctx->smem_cap,
                                                                    (long long)ctx->cfg.abundance_min[0], (long long)ctx->cfg.abundance_max,
                                                                    (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
-                                                                   (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p); LAUNCHED();
+                                                                   (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p, 1, SolidityParams(), nullptr);
+            else
+                k_count_smem<KW, true><<<grid, CS_THREADS, dyn, ctx->stream>>>(recs, (const SmemJob*)ctx->jobs.p, (u32)jobs.size(), ctx->k, ctx->smem_cap,
+                                                                   (long long)ctx->cfg.abundance_min[0], (long long)ctx->cfg.abundance_max,
+                                                                   (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
+                                                                   (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p, ctx->NB, make_sp(ctx),
+                                                                   (unsigned long long*)ctx->hist2d.p);
+            LAUNCHED();
             cudaEventRecord(b, ctx->stream);
             ctx->spans.push_back({a, b, SPAN_DOM});
             ctx->st.nb_parts_smem = (u32)jobs.size();

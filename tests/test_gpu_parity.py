@@ -64,12 +64,10 @@ def test_forced_count_modes(t, mode):
     sc = run_gpu(t["files"], t["k"], t["abundance_min"], t["histo2d"], t.get("solidity_kind"), t.get("abundance_max"), count_mode=mode)
     check_against_run(sc, t)
     st = sc.getInfo()["engine"]
-    per_bank = len(t["files"]) > 1 and (t["histo2d"] or (t.get("solidity_kind") or "sum") != "sum")
-    if mode == "smem" and not per_bank:
-        # shared-memory tables everywhere except the partitions too big for a few split passes (lowcomplexity: one hot minimizer)
+    if mode == "smem":
+        # shared-memory tables everywhere except the partitions too big for a few split passes (lowcomplexity: one hot minimizer);
+        # per-bank counts (-histo2D, solidity kinds over several banks) use the multi-count variant of the same kernel
         assert st["nb_parts_smem"] > 0 and st["nb_groups_sort"] == 0
-    elif mode == "smem":
-        assert st["nb_parts_smem"] == 0 and st["nb_groups_hash"] > 0           # per-bank counts live in the global table
     else:
         assert (st["nb_groups_sort"] > 0) == (mode == "sort") and (st["nb_groups_hash"] > 0) == (mode == "hash") and st["nb_parts_smem"] == 0
 
@@ -93,13 +91,11 @@ def test_tiny_smem_table_overflow_splits(t, slots):
                  count_mode="smem", smem_table_slots=slots, nb_partitions=1000 if slots == 64 else 0)
     check_against_run(sc, t)
     st = sc.getInfo()["engine"]
-    per_bank = len(t["files"]) > 1 and (t["histo2d"] or (t.get("solidity_kind") or "sum") != "sum")
-    if not per_bank:
-        assert st["smem_table_slots"] == slots
-        if t["kmers_nb_distinct"] > 20000:                       # (lowcomplexity: a few hot minimizers, all beyond 16 x slots)
-            assert st["nb_parts_smem"] > 0
-            if slots == 64:
-                assert st["nb_smem_splits"] > 0
+    assert st["smem_table_slots"] == slots
+    if t["kmers_nb_distinct"] > 20000:                       # (lowcomplexity: a few hot minimizers, all beyond 16 x slots)
+        assert st["nb_parts_smem"] > 0
+        if slots == 64:
+            assert st["nb_smem_splits"] > 0
 
 
 @pytest.mark.parametrize("t", SHELL, ids=[t["name"] for t in SHELL])
@@ -209,6 +205,12 @@ def test_histo2d_assembly_vs_reads():
     buf, n, _ = reads_fasta(coverage=20, L=150, err=0.01, seed=9, genome=g)
     compare_with_oracle([asm, buf[:n].tobytes()], 31, histo2d=True)
     compare_with_oracle([asm, buf[:n].tobytes()], 63, histo2d=True, engine=dict(count_mode="sort"))
+    # per-bank counts in the shared-memory tables (two counts per slot), with and without overflow splits, 64- and 128-bit keys
+    for k, eng in ((31, dict(count_mode="smem")), (63, dict(count_mode="smem")), (31, dict(count_mode="smem", smem_table_slots=256)),
+                   (63, dict(count_mode="auto", smem_table_slots=512, hash_log2_slots=16)), (31, dict(count_mode="hash"))):
+        sc = compare_with_oracle([asm, buf[:n].tobytes()], k, histo2d=True, engine=eng)
+        st = sc.getInfo()["engine"]
+        assert (st["nb_parts_smem"] > 0) == (eng["count_mode"] != "hash")
 
 
 def test_push_reads_equals_push_bytes():
