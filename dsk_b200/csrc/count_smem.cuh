@@ -51,7 +51,7 @@ template <int KW> DSK_HD size_t cs_smem_bytes(u32 cap, int nb = 1)
 {
     return (size_t)cap * (8 * KW + 4 * nb) + (size_t)CS_WARPS * 32 * 2 * KW * 8 + (size_t)CS_WARPS * CS_QCAP * (8 * KW + 4);
 }
-constexpr int CS_H2_I1 = 64;                   // -histo2D: bins (i1 < 64, any i2) are accumulated in shared memory
+constexpr int CS_H2_I1 = H2_SMEM_I1;           // -histo2D: bins (i1 < 64, any i2) are accumulated in shared memory
 constexpr int CS_MAX_BANKS = 4;                // per-bank counts beyond this go to the global-table path
 
 #ifdef __CUDACC__
