@@ -239,6 +239,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--histo2d", action="store_true", help="BASELINE.json configs[4]: bank 0 = the genome as an assembly, bank 1 = the reads, -histo2D 1")
     ap.add_argument("--device-synth", action="store_true", help="draw the read set on the device (3 Gbp-class workloads)")
+    ap.add_argument("--minimizer-size", type=int, default=0, help="0 = what the host adapters do: dskgpu_suggest_minimizer_size(k-mers of the whole job)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     workload = "synthetic %.0f Mbp genome, %dx %dbp reads, %.0f%% error, k=%d" % (
@@ -332,6 +333,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # minimizer length from the k-mers of the WHOLE job (all ranks), like host/GpuSortingCount.hpp does from the bank estimate
+    from dsk_b200 import _lib as _dsklib
+    job_kmers = world * (int(args.genome * args.coverage // args.read_len) * max(0, args.read_len - args.kmer_size + 1) + (args.genome if args.histo2d else 0))
+    msize = args.minimizer_size or _dsklib.lib().dskgpu_suggest_minimizer_size(job_kmers, args.kmer_size)
+    bank_kw["minimizer_size"] = msize
     eng = GpuCounter(kmer_size=args.kmer_size, abundance_min=2, device=local, stream=stream.cuda_stream, count_mode=args.count_mode,
                      hash_log2_slots=args.hash_log2_slots, keep_results_on_device=True, rank=rank, world_size=world, **bank_kw)
 
@@ -438,7 +444,7 @@ def main():
             "metric": "Gk-mers/s counted", "value": value, "unit": "Gk-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if args.kmer_size < 32 else "u128",
             "data": "synthetic",
-            "config": {"workload": workload, "kmers_per_step_per_gpu": int(kmers), "input_bytes_per_gpu": int(n), "count_mode": args.count_mode, "sampled_density": st["density_ppm"] / 1e6, "log2_bins": st["log2_bins"], "partitions": int(st["nb_partitions"]),
+            "config": {"workload": workload, "kmers_per_step_per_gpu": int(kmers), "input_bytes_per_gpu": int(n), "count_mode": args.count_mode, "minimizer_size": msize, "sampled_density": st["density_ppm"] / 1e6, "log2_bins": st["log2_bins"], "partitions": int(st["nb_partitions"]),
                        "smem_partitions": int(st["nb_parts_smem"]), "smem_splits": int(st["nb_smem_splits"]),
                        "l2_policy": "inputs (%.0f MB) larger than the 126 MB L2; no flush" % (n / 1e6), "parallelism": "1 rank per GPU, partitions sharded by id"},
             "gpu_launches": int(launches),

@@ -36,7 +36,7 @@ class Stats(C.Structure):
         ("ms_parse", C.c_float), ("ms_superk", C.c_float), ("ms_partition", C.c_float), ("ms_count", C.c_float),
         ("ms_sort", C.c_float), ("ms_total", C.c_float), ("ms_dominant_kernel", C.c_float),
         ("dominant_kernel_launches", C.c_uint32), ("nb_parts_smem", C.c_uint32), ("nb_smem_splits", C.c_uint32),
-        ("smem_table_slots", C.c_uint32), ("density_ppm", C.c_uint32), ("log2_bins", C.c_uint32), ("reserved", C.c_uint32 * 2),
+        ("smem_table_slots", C.c_uint32), ("density_ppm", C.c_uint32), ("log2_bins", C.c_uint32), ("nb_groups_bucket", C.c_uint32), ("reserved", C.c_uint32 * 1),
     ]
 
     def as_dict(self):
@@ -53,7 +53,7 @@ SYMBOLS = [
     "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_bin_hist", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
     "dskgpu_xchg_open_peer", "dskgpu_xchg_set_peers", "dskgpu_xchg_scatter", "dskgpu_xchg_sync", "dskgpu_xchg_layout", "dskgpu_record_bytes",
     "dskgpu_xchg2_hist", "dskgpu_xchg2_plan", "dskgpu_xchg2_ensure_recv", "dskgpu_xchg2_scatter",
-    "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers",
+    "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers", "dskgpu_suggest_minimizer_size",
 ]
 
 _LIB = None
@@ -117,5 +117,6 @@ def lib():
     L.dskgpu_selftest_minimizers.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.dskgpu_selftest_superkmers.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, P(C.c_uint64)]
     L.dskgpu_selftest_superkmers.restype = C.c_int64
+    L.dskgpu_suggest_minimizer_size.argtypes = [C.c_uint64, C.c_int]
     _LIB = L
     return L

@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
     __syncthreads();
     const u64 EMPTY = ~0ULL;
     u32 ndist = 0;
+    unsigned long long sumsq = 0;
     const u32 ngroups = nslots / SV;                               // nslots is a power of two >= 1024
     const u32 nthreads = blockDim.x * gridDim.x;
     const u32 nloop = (ngroups + nthreads - 1) / nthreads;
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
                 const u64 slot = (u64)g * SV + q;
                 for (int b = 0; b < sp.nbanks; b++) { cv[b] = counts[slot * sp.nbanks + b]; counts[slot * sp.nbanks + b] = 0; }
             }
-            if (discard == 2) ndist++;                               // density sample: occupied slots are all that matters
+            if (discard == 2) { ndist++; sumsq += (unsigned long long)cv[0] * cv[0]; }   // density sample: occupied slots + multiplicities
             if (!discard) {
                 ndist++;
                 int32_t sum = 0;
@@ -364,6 +365,10 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
     flush_hist(s_hist, g_hist);
     if (!NB1 && sp.histo2d) flush_hist2d(s_h2, g_hist2d);
     if (threadIdx.x == 0 && s_distinct) atomicAdd(discard == 2 ? &ctr->sample_distinct : &ctr->distinct_n, (unsigned long long)s_distinct);
+    if (discard == 2) {
+        for (int d = 16; d; d >>= 1) sumsq += __shfl_xor_sync(0xFFFFFFFFu, sumsq, d);
+        if ((threadIdx.x & 31) == 0 && sumsq) atomicAdd(&ctr->sample_sumsq, sumsq);
+    }
 }
 
 __global__ void k_fill_u64(u64* p, u64 n, u64 v)
@@ -409,6 +414,68 @@ __global__ void __launch_bounds__(256) k_expand_keys(const u64* __restrict__ rec
             for (int q = 0; q < KW; q++) out_keys[(pos + j) * KW + q] = c.w[q];
             if (nbanks > 1) out_bank[pos + j] = bank;
         }
+    }
+}
+
+// ---- heavy minimizer bins: expand records into hash buckets of flat keys ------------------------------------------------
+// A partition is bounded below by its heaviest minimizer bin (9e-5 of the job at k=31, m=10): in multi-G k-mer jobs most
+// bins outgrow a shared-memory table.  Those partitions are expanded into canonical k-mers (what ReadSuperKCommand does,
+// K/PartitionsCommand.cpp:944-1128) and every k-mer is appended to the slab of bucket = hash(k-mer) * S >> 32: equal
+// k-mers meet in one bucket, a bucket holds what one shared-memory table takes, and the buckets are then counted by
+// k_count_smem<KW, MB, true> straight from the flat keys.  Extra HBM traffic: one key written + read per k-mer (16 B at
+// k <= 31) instead of the global table's random L2 atomics.  With per-bank counts the bank id rides in the two spare top
+// bits of the key (2k <= 62 resp. 126 bits are used, nb <= 4).
+__device__ __forceinline__ u32 bucket_hash(u32 h)      // independent of the bits that pick the slot (top) and the sub-pass (8..)
+{
+    h = (h ^ (h >> 16)) * 0xC2B2AE3Du; h = (h ^ (h >> 13)) * 0x27D4EB2Fu; return h ^ (h >> 16);
+}
+
+template <int KW> __device__ __forceinline__ u32 cs_hash_of(const Kmer<KW>& a);   // count_smem.cuh
+
+template <int KW>
+__global__ void __launch_bounds__(256) k_expand_bucket(const u64* __restrict__ recs, u64 rec_begin, u64 rec_end, int k, int nbanks,
+                                                       u32 nbuckets, u32 slab, u64* __restrict__ out_keys, u32* __restrict__ cursors, Counters* ctr)
+{
+    constexpr int RW = 2 * KW;
+    constexpr int MAXNK = InsCfg<KW>::MAXNK;
+    __shared__ __align__(16) u64 s_rec[8][32 * RW];
+    __shared__ u8 s_owner[8][32 * MAXNK];
+    __shared__ u16 s_off[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 nwarps = (u64)gridDim.x * 8, gwarp = (u64)blockIdx.x * 8 + warp;
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
+    for (u64 base = rec_begin + gwarp * 32; base < rec_end; base += nwarps * 32) {
+        const u64 i = base + lane;
+        u32 nk = 0;
+        if (i < rec_end) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(&s_rec[warp][lane * RW]);
+            if constexpr (RW == 2) { ulonglong2 v = __ldg(src + i); dst[0] = v; nk = (u32)(v.y >> 8) & 0xFFu; }
+            else { ulonglong2 v = __ldg(src + 2 * i), u = __ldg(src + 2 * i + 1); dst[0] = v; dst[1] = u; nk = (u32)(u.y >> 8) & 0xFFu; }
+        }
+        u32 inc = nk;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+        const u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const u32 off = inc - nk;
+        s_off[warp][lane] = (u16)off;
+        for (u32 j = 0; j < nk; j++) s_owner[warp][off + j] = (u8)lane;
+        __syncwarp();
+        for (u32 t = lane; t < total; t += 32) {
+            const u32 r = s_owner[warp][t];
+            const int j = (int)(t - s_off[warp][r]);
+            const u64* rw = &s_rec[warp][r * RW];
+            Kmer<KW> f = rec_kmer_at<KW>(rw, j, k);
+            Kmer<KW> c = kmer_canonical(f, kmer_revcomp(f, k));
+            const u32 b = __umulhi(bucket_hash(cs_hash_of<KW>(c)), nbuckets);
+            const u32 pos = atomicAdd(&cursors[b], 1u);
+            if (pos < slab) {
+                if (nbanks > 1) c.w[KW - 1] |= (u64)(rw[RW - 1] & 3u) << 62;
+                u64* o = out_keys + ((u64)b * slab + pos) * KW;
+                if constexpr (KW == 1) o[0] = c.w[0];
+                else *reinterpret_cast<ulonglong2*>(o) = make_ulonglong2(c.w[0], c.w[1]);
+            } else atomicExch(&ctr->bucket_overflow, 1u);
+        }
+        __syncwarp();
     }
 }
 

@@ -70,6 +70,8 @@ __device__ __forceinline__ u32 cs_hash(const Kmer<2>& a)
     return (x ^ (x >> 15)) * 0x85EBCA77u;
 }
 
+template <int KW> __device__ __forceinline__ u32 cs_hash_of(const Kmer<KW>& a) { return cs_hash(a); }
+
 // explicit shared-space accesses on 32-bit addresses (generic pointers make the compiler rebuild the window base at
 // every access site)
 __device__ __forceinline__ u32 cs_saddr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -119,12 +121,16 @@ __device__ __forceinline__ u64 cs_window(const u64* r, int p)
 // MB = false: one count per k-mer (banks summed), solidity = abundance range [amin, amax] -- the dsk default.
 // MB = true : `nb` counts per slot (the record's bank byte picks the column); the sweep runs the whole CountProcessor
 //             chain of count.cuh (`process_counts`: per-bank solidity kinds, -histo2D, per-bank histograms) on them.
-template <int KW, bool MB>
+// KEYS = false: a job is a partition of super-k-mer records (jobs[]).
+// KEYS = true : a job is a hash bucket of flat canonical k-mers written by k_expand_bucket (count.cuh): job j reads
+//               min(bucket_n[j], slab) keys at recs + j * slab * KW; `jobs` is unused.
+template <int KW, bool MB, bool KEYS = false>
 __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const u64* __restrict__ recs, const SmemJob* __restrict__ jobs, u32 njobs,
                                                               int k, u32 cap, long long amin, long long amax,
                                                               u64* __restrict__ out_keys, u32* __restrict__ out_vals, u64 out_cap,
                                                               unsigned long long* __restrict__ g_hist, Counters* ctr, u32* work_counter,
-                                                              int nb_arg, const SolidityParams spar, unsigned long long* __restrict__ g_hist2d)
+                                                              int nb_arg, const SolidityParams spar, unsigned long long* __restrict__ g_hist2d,
+                                                              const u32* __restrict__ bucket_n = nullptr, u32 slab = 0)
 {
     constexpr int RW = 2 * KW;
     const u32 nb = MB ? (u32)nb_arg : 1u;
@@ -180,14 +186,14 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
         __syncthreads();
         const u32 job = s_job;
         if (job >= njobs) break;
-        const u64 rb = jobs[job].rec_begin;
-        const u32 nrec = jobs[job].nrec, nchunks = (nrec + CS_CHUNK - 1) / CS_CHUNK;
+        const u64 rb = KEYS ? (u64)job * slab : jobs[job].rec_begin;
+        const u32 nrec = KEYS ? min(bucket_n[job], slab) : jobs[job].nrec, nchunks = (nrec + CS_CHUNK - 1) / CS_CHUNK;
 
         // depth-first over (split level, residue) work items; uniform across the CTA
         u32 stack[CS_MAX_SPLIT + 2 + (1 << CS_MAX_SPLIT0)];
         int sp = 0;
         {
-            const u32 l0 = min(jobs[job].split0, (u32)CS_MAX_SPLIT0);
+            const u32 l0 = KEYS ? 0u : min(jobs[job].split0, (u32)CS_MAX_SPLIT0);
             for (u32 r = (1u << l0); r-- > 0;) stack[sp++] = (l0 << 16) | r;
         }
         while (sp > 0) {
@@ -196,9 +202,29 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
             if (t == 0) s_chunk = CS_WARPS;                                        // chunks beyond the first one per warp are dealt dynamically
             __syncthreads();
 
+            // ---- insert: flat keys (one per thread and iteration; the probe loop runs to the end, loads stay <= 52 %) ---------
+            if constexpr (KEYS) {
+                const u64* kp = recs + rb * KW;
+                for (u32 i0 = 0; i0 < nrec; i0 += CS_THREADS) {
+                    if (*reinterpret_cast<volatile u32*>(&s_flag)) break;
+                    const u32 i = i0 + (u32)t;
+                    if (i >= nrec) continue;
+                    Kmer<KW> c;
+                    if constexpr (KW == 1) c.w[0] = __ldg(kp + i);
+                    else { const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(kp) + i); c.w[0] = v.x; c.w[1] = v.y; }
+                    u32 bank = 0;
+                    if constexpr (MB) { bank = (u32)(c.w[KW - 1] >> 62); c.w[KW - 1] &= ~(3ULL << 62); }
+                    const u32 h = cs_hash(c);
+                    if (((h >> 8) & smask) != res) continue;
+                    u32 slot = __umulhi(h, cap);
+                    bool ok = false;
+                    for (int p = 0; p < CS_MAXPROBE && !ok; p++) { ok = cs_probe(keys_a, slot, c); if (!ok) slot = (slot + 1 == cap) ? 0u : slot + 1; }
+                    if (ok) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u); else s_flag = 1u;
+                }
+            }
             // ---- insert: warps expand chunks of 32 records -----------------------------------------------------------
             u32 qn = 0;
-            for (u32 chunk = warp; chunk < nchunks;) {
+            for (u32 chunk = warp; !KEYS && chunk < nchunks;) {
                 if (*reinterpret_cast<volatile u32*>(&s_flag)) break;              // somebody overflowed: the pass is void
                 const u32 ri = chunk * CS_CHUNK + lane;
                 u32 nk = 0;

@@ -73,12 +73,12 @@ struct dskgpu_ctx {
     std::vector<void*> ipc_opened;
     bool totals_done = false; u64 local_nrec = 0, local_nkm = 0;
     u64 bytes_pushed = 0;                            // raw input bytes so far (sizes the density sample before the totals are known)
-    bool sample_queued = false; u64 sample_nkm = 0, sample_distinct = 0;
+    bool sample_queued = false; u64 sample_nkm = 0, sample_distinct = 0; double sample_wmult = 0.0;   // wmult: occurrence-weighted multiplicity (this rank's sample)
     bool global_set = false; u64 g_total_kmers = 0; double density = 1.0; bool density_known = false;
     int bin_level = NBINS_LOG2; bool hist_fetched = false;
     DevBuf sendbuf;
     // exchange v2 (bulk segments): records in local partition order, per-partition offsets on the device, pinned global histogram
-    DevBuf lrecs, xoff, xpeers;
+    DevBuf lrecs, xoff, xpeers, bcur;
     unsigned long long* h_ghist = nullptr;
     std::vector<u64> g_part_recs;                    // whole-job records of every partition
     std::vector<u64> x_need;                         // records every rank receives
@@ -182,7 +182,7 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     ctx->k = cfg->kmer_size;
     int m = cfg->minimizer_size > 0 ? cfg->minimizer_size : 10;
     if (m > ctx->k - 1) m = ctx->k - 1;              // ConfigurationAlgorithm.cpp:249-251
-    if (m > 12) m = 12;                              // meta word packs the minimizer in 24 bits
+    if (m > DSKGPU_MAX_MINIMIZER) m = DSKGPU_MAX_MINIMIZER;   // m-mer values are 32-bit (kmer_bits.cuh: mmer_value)
     if (m < 2) m = 2;
     if (m > ctx->k) m = ctx->k;
     ctx->m = m;
@@ -243,11 +243,34 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
         const size_t dyn = ctx->KW == 1 ? cs_smem_bytes<1>(cap, ctx->NB) : cs_smem_bytes<2>(cap, ctx->NB);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        // the flat-key variant (heavy partitions) shares the table geometry
+        const void* fk = ctx->KW == 1 ? (mb ? (const void*)k_count_smem<1, true, true> : (const void*)k_count_smem<1, false, true>)
+                                      : (mb ? (const void*)k_count_smem<2, true, true> : (const void*)k_count_smem<2, false, true>);
+        cudaFuncAttributes fb;
+        CK(cudaFuncGetAttributes(&fb, fk));
+        if (fb.sharedSizeBytes > fa.sharedSizeBytes) FAIL(DSKGPU_ERR_CUDA, "internal: key variant of k_count_smem needs more static shared memory");
+        CK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        CK(cudaFuncSetAttribute(fk, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     *out = ctx;
     int r = dskgpu_reset(ctx);
     if (r) { *out = nullptr; return r; }
     return DSKGPU_OK;
+}
+
+// The partition of a k-mer is a pure function of its minimizer, so a partition can never be lighter than its heaviest
+// minimizer bin: ~9e-5 of the job at m = 10 (k = 31), about 16 times less for every two more letters.  A shared-memory
+// table takes ~30 K k-mers, so the minimizer length has to grow with the job to keep the bins inside its reach -- the
+// role ConfigurationAlgorithm (K/ConfigurationAlgorithm.cpp:245-467) gives to nb_partitions, which it derives from the
+// estimated volume.  The choice only moves k-mers between partitions: unobservable in the results.
+int dskgpu_suggest_minimizer_size(uint64_t expected_kmers, int kmer_size)
+{
+    int m = 10;                                        // the reference's default (-minimizer-size)
+    if (expected_kmers > 600ull * 1000 * 1000) m = 12;
+    if (expected_kmers > 12ull * 1000 * 1000 * 1000) m = 14;
+    if (m > kmer_size - 1) m = kmer_size - 1;
+    if (m < 2) m = 2;
+    return m;
 }
 
 int dskgpu_reset(dskgpu_ctx* ctx)
@@ -264,7 +287,7 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     ctx->nrec_known = 0; ctx->k2_inflight = false; ctx->chunk_parity = 0;
     ctx->n_solid = 0; ctx->results_on_host = false; ctx->nparts = 0;
     ctx->xchg_planned = false; ctx->xchg_scattered = false; ctx->totals_done = false; ctx->local_nrec = ctx->local_nkm = 0;
-    ctx->bytes_pushed = 0; ctx->sample_queued = false; ctx->sample_nkm = ctx->sample_distinct = 0;
+    ctx->bytes_pushed = 0; ctx->sample_queued = false; ctx->sample_nkm = ctx->sample_distinct = 0; ctx->sample_wmult = 0.0;
     ctx->global_set = false; ctx->g_total_kmers = 0; ctx->density = 1.0; ctx->density_known = false; ctx->bin_level = NBINS_LOG2; ctx->hist_fetched = false;
     ctx->peer_recv.clear();
     ctx->ev_used = 0; ctx->spans.clear();
@@ -281,7 +304,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
                      &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->dstbase, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->bin2part, &ctx->jobs, &ctx->work_ctr,
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
                      &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr, &ctx->sendbuf,
-                     &ctx->lrecs, &ctx->xoff, &ctx->xpeers};
+                     &ctx->lrecs, &ctx->xoff, &ctx->xpeers, &ctx->bcur};
     for (DevBuf* b : all) b->release();
     for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -762,6 +785,7 @@ static int stage_totals(dskgpu_ctx* ctx)
         FAIL(DSKGPU_ERR_OVERFLOW, "internal: %llu valid k-mers but %llu packed in records", ctx->h_ctr->kmers_valid, ctx->h_ctr->kmers_in_recs);
     ctx->local_nrec = ctx->h_ctr->nrec; ctx->local_nkm = ctx->h_ctr->kmers_valid;
     ctx->sample_nkm = ctx->h_ctr->sample_nkm; ctx->sample_distinct = ctx->h_ctr->sample_distinct;
+    ctx->sample_wmult = ctx->sample_nkm >= 4096 ? (double)ctx->h_ctr->sample_sumsq / (double)ctx->sample_nkm : 0.0;
     ctx->st.nb_sequences = ctx->h_ss->nsep; ctx->st.nb_nucleotides = ctx->h_ss->nbase;
     ctx->st.kmers_nb_valid = ctx->local_nkm; ctx->st.nb_superkmers = ctx->local_nrec;
     ctx->st.superkmer_bytes = ctx->local_nrec * (u64)ctx->RW * 8;
@@ -902,6 +926,93 @@ static int stage_scatter(dskgpu_ctx* ctx, const std::vector<u64*>& dst)
     return 0;
 }
 
+// ---- heavy partitions: hash-bucketed flat keys, counted in shared memory ---------------------------------------------
+// prec/pkm: records / k-mers of the partitions of one contiguous run starting at `recs`.  Groups of consecutive partitions
+// (<= BUCKET_GROUP_KMERS k-mers) are expanded into S = k-mers / T hash buckets with fixed-size slabs (uniform hashing: the
+// slab is the mean + 15 % + 6 sigma), then counted bucket by bucket by k_count_smem<KW, MB, true>.  A slab can only
+// overflow when a single k-mer has a huge multiplicity (low-complexity input): that group falls back to the global table.
+constexpr u64 BUCKET_GROUP_KMERS = (u64)1 << 27;
+
+template <int KW>
+static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm, u64 out_cap);
+
+template <int KW>
+static int count_by_buckets(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm, u64 out_cap)
+{
+    Counters* ctr = (Counters*)ctx->ctr.p;
+    const size_t np = prec.size();
+    // k-mers per bucket: what fills the shared-memory table to ~52 % at the sampled density (same rule as the partitions)
+    const u64 T = (u64)std::min(std::max((double)ctx->smem_cap * 0.52 / ctx->density, 64.0), (double)ctx->smem_cap * 4.0);
+    int rc;
+    size_t p = 0; u64 roff = 0;
+    while (p < np) {
+        size_t q = p; u64 km = 0, nr = 0;
+        while (q < np && (q == p || km + pkm[q] <= BUCKET_GROUP_KMERS)) { km += pkm[q]; nr += prec[q]; q++; }
+        if (km == 0) { p = q; roff += nr; continue; }
+        const u64 S64 = std::max<u64>(1, (km + T - 1) / T);
+        // slab = mean + 8 sigma.  Equal k-mers share a bucket, so a bucket's load is a compound Poisson: its variance is
+        // mean x (occurrence-weighted multiplicity of a k-mer), measured on the density sample (x 1.5: hot minimizer bins
+        // are more repetitive than the average bin); without a sample, a generous 256.
+        const double mean = (double)km / (double)S64;
+        const double wm = ctx->sample_wmult > 0.0 ? std::max(1.0, ctx->sample_wmult * 1.5) : 256.0;
+        const u64 slab64 = (u64)std::max(mean * 1.25, mean + 8.0 * std::sqrt(mean * wm)) + 64;
+        bool fallback = S64 > 0x7FFFFFFFull || slab64 > 0x7FFFFFFFull;
+        if (!fallback) {
+            const u32 S = (u32)S64, slab = (u32)slab64;
+            if ((rc = ensure(ctx, ctx->keys[0], (u64)S * slab * KW * 8 + 64))) return rc;
+            if ((rc = ensure(ctx, ctx->bcur, (size_t)S * 4))) return rc;
+            CK(cudaMemsetAsync(ctx->bcur.p, 0, (size_t)S * 4, ctx->stream));
+            const unsigned gb = (unsigned)std::min<u64>((nr + 255) / 256, (u64)ctx->num_sms * 8);
+            k_expand_bucket<KW><<<gb ? gb : 1, 256, 0, ctx->stream>>>(recs + roff * (u64)ctx->RW, 0, nr, ctx->k, ctx->NB, S, slab, (u64*)ctx->keys[0].p,
+                                                                     (u32*)ctx->bcur.p, ctr); LAUNCHED();
+            CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->h_ctr->bucket_overflow) { fallback = true; CK(cudaMemsetAsync(&ctr->bucket_overflow, 0, sizeof(unsigned int), ctx->stream)); }
+            else {
+                CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
+                const unsigned grid = (unsigned)std::min<u64>(S, (u64)ctx->num_sms * CS_CTAS_PER_SM);
+                const size_t dyn = cs_smem_bytes<KW>(ctx->smem_cap, ctx->NB);
+                cudaEvent_t a = get_event(ctx), b = get_event(ctx);
+                cudaEventRecord(a, ctx->stream);
+                if (ctx->NB == 1)
+                    k_count_smem<KW, false, true><<<grid, CS_THREADS, dyn, ctx->stream>>>((const u64*)ctx->keys[0].p, nullptr, S, ctx->k, ctx->smem_cap,
+                        (long long)ctx->cfg.abundance_min[0], (long long)ctx->cfg.abundance_max, (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
+                        (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p, 1, SolidityParams(), nullptr, (const u32*)ctx->bcur.p, slab);
+                else
+                    k_count_smem<KW, true, true><<<grid, CS_THREADS, dyn, ctx->stream>>>((const u64*)ctx->keys[0].p, nullptr, S, ctx->k, ctx->smem_cap,
+                        (long long)ctx->cfg.abundance_min[0], (long long)ctx->cfg.abundance_max, (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
+                        (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p, ctx->NB, make_sp(ctx), (unsigned long long*)ctx->hist2d.p,
+                        (const u32*)ctx->bcur.p, slab);
+                LAUNCHED();
+                cudaEventRecord(b, ctx->stream);
+                ctx->spans.push_back({a, b, SPAN_DOM});
+                ctx->st.nb_groups_bucket++;
+                CK(cudaGetLastError());
+            }
+        }
+        if (fallback) {
+            std::vector<u64> rp(prec.begin() + p, prec.begin() + q), rk(pkm.begin() + p, pkm.begin() + q);
+            if ((rc = count_all<KW>(ctx, recs + roff * (u64)ctx->RW, rp, rk, out_cap))) return rc;
+        }
+        roff += nr; p = q;
+    }
+    return 0;
+}
+
+// Which path takes the heavy partitions (measured on B200, profiles/r01u-r01v): with one count per k-mer the L2-resident
+// global table wins (3 G k-mer job: count stage 65 ms against 116 ms -- k_expand_bucket's per-k-mer cursor atomics and
+// scattered stores run at 25 G k-mers/s); with per-bank counts the key buckets win (-histo2D, 4.1 G k-mers: 169 ms against
+// 267 ms).  DSKGPU_HEAVY_PATH=bucket|table overrides.  The first answer to heavy bins is a longer minimizer
+// (dskgpu_suggest_minimizer_size): both paths are what is left for low-complexity input.
+static bool heavy_by_buckets(const dskgpu_ctx* ctx)
+{
+    if (!(ctx->cfg.count_mode == DSKGPU_COUNT_AUTO && use_smem_path(ctx))) return false;
+    const char* e = getenv("DSKGPU_HEAVY_PATH");
+    if (e && strcmp(e, "table") == 0) return false;
+    if (e && strcmp(e, "bucket") == 0) return true;
+    return ctx->NB > 1;
+}
+
 // ---- stage 4: count the partitions stored contiguously in `recs`, order the solid set, copy results out --------------
 template <int KW>
 static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm)
@@ -983,7 +1094,9 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
             size_t j = i; u64 km = 0;
             std::vector<u64> rp, rk;
             while (j < np && (big[j] || prec[j] == 0)) { rp.push_back(prec[j]); rk.push_back(pkm[j]); km += pkm[j]; j++; }
-            if ((rc = count_all<KW>(ctx, recs + off[i] * (u64)ctx->RW, rp, rk, out_cap))) return rc;
+            if (heavy_by_buckets(ctx)) rc = count_by_buckets<KW>(ctx, recs + off[i] * (u64)ctx->RW, rp, rk, out_cap);
+            else rc = count_all<KW>(ctx, recs + off[i] * (u64)ctx->RW, rp, rk, out_cap);
+            if (rc) return rc;
             i = j;
         }
     }

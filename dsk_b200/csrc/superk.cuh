@@ -37,6 +37,9 @@ struct Counters {
     unsigned long long sample_nrec;   // density sample: records / k-mers selected, distinct k-mers found among them
     unsigned long long sample_nkm;
     unsigned long long sample_distinct;
+    unsigned int bucket_overflow;     // key-bucket path: a hash bucket outgrew its slab (one k-mer with a huge multiplicity)
+    unsigned int pad0;
+    unsigned long long sample_sumsq;  // density sample: sum of count^2 over its distinct k-mers (occurrence-weighted multiplicity)
 };
 
 #ifdef __CUDACC__

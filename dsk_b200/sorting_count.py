@@ -11,6 +11,7 @@ import os
 
 import numpy as np
 
+from . import _lib
 from .counter import GpuCounter, DskGpuError
 from .histogram import compute_threshold, auto_thresholds, MIN_AUTO_THRESHOLD
 
@@ -133,6 +134,17 @@ class SortingCountAlgorithm:
 
     def execute(self):
         cfg = self._configure()
+        if cfg["minimizer_size"] == 10:
+            # reference default: sized from the estimated volume (~0.7 k-mers per input byte), as host/GpuSortingCount.hpp does
+            nbytes = 0
+            for bank in self.banks:
+                if isinstance(bank, BankStrings):
+                    nbytes += sum(len(x) for x in bank.seqs)
+                elif isinstance(bank, BankBytes):
+                    nbytes += len(bank.data)
+                elif os.path.exists(bank.path):
+                    nbytes += os.path.getsize(bank.path) * (4 if bank.path.endswith(".gz") else 1)
+            cfg["minimizer_size"] = _lib.lib().dskgpu_suggest_minimizer_size(int(0.7 * nbytes), cfg["kmer_size"])
         cfg.update(self.engine_kw)
         user_amin = list(cfg["abundance_min"])
         if self._auto:

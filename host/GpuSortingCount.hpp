@@ -154,7 +154,10 @@ private:
         dskgpu_config c;
         dskgpu_config_default(&c);
         c.kmer_size = (int32_t)_config._kmerSize;
+        // -minimizer-size left at the reference default: sized from the estimated volume, the way ConfigurationAlgorithm
+        // sizes nb_partitions (bins must shrink as the job grows; which partition a k-mer lands in is unobservable)
         c.minimizer_size = (int32_t)in->getInt(STR_MINIMIZER_SIZE);
+        if (c.minimizer_size == 10) c.minimizer_size = dskgpu_suggest_minimizer_size((uint64_t)_config._kmersNb, c.kmer_size);
         c.nb_banks = (int32_t)_config._nb_banks;
         if (c.nb_banks > DSKGPU_MAX_BANKS) throw Exception("at most %d banks are supported by the device path", DSKGPU_MAX_BANKS);
         // kind of the FILTER: created from -solidity-kind before -histo2D forces the counting path to per-bank

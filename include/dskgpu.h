@@ -25,6 +25,7 @@ extern "C" {
 #define DSKGPU_MAX_BANKS     16
 #define DSKGPU_HISTO_LEN     10001          /* bins 0..10000 (Histogram.hpp:92, length 10000) */
 #define DSKGPU_HISTO2D_DIM2  11             /* bins 0..10   (CountProcessorHistogram.hpp:173-184) */
+#define DSKGPU_MAX_MINIMIZER 14             /* -minimizer-size is clipped to this (32-bit m-mer arithmetic) */
 #define DSKGPU_MAX_KMER      63             /* KSIZE_LIST "32 64": k<32 -> 64-bit keys, k<64 -> 128-bit */
 #define DSKGPU_NBINS         65536          /* minimizer bins packed into partitions at finish: the coarsest level ... */
 #define DSKGPU_NBINS_MAX     (1u << 20)     /* ... and the finest (multi-G k-mer jobs); the level is picked from the job size */
@@ -110,11 +111,19 @@ typedef struct dskgpu_stats {
     uint32_t smem_table_slots;      /* capacity of the shared-memory table */
     uint32_t density_ppm;           /* sampled distinct / total k-mers x 1e6 (0 = sample too small) */
     uint32_t log2_bins;             /* minimizer-bin level the partitions were packed from (16..20) */
-    uint32_t reserved[2];
+    uint32_t nb_groups_bucket;      /* heavy partitions: groups expanded into hash buckets of flat keys, counted in shared memory */
+    uint32_t reserved[1];
 } dskgpu_stats;
 
 /* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */
 void dskgpu_config_default(dskgpu_config* cfg);
+
+/* replaces: the part of ConfigurationAlgorithm::execute (ConfigurationAlgorithm.cpp:245-467) that sizes the partitioning
+ * from the estimated volume.  Returns the minimizer length to put in cfg->minimizer_size for a job of `expected_kmers`
+ * k-mers over ALL ranks (10 up to 0.6 G k-mers, 12 up to 12 G, 14 beyond; clipped to kmer_size-1): a partition cannot be
+ * lighter than its heaviest minimizer bin, so the bins must shrink as the job grows to stay inside a shared-memory table.
+ * Which partition a k-mer lands in is unobservable in the results.  Host-only, no device needed. */
+int dskgpu_suggest_minimizer_size(uint64_t expected_kmers, int kmer_size);
 
 /* replaces: SortingCountAlgorithm ctor + configure() (SortingCountAlgorithm.cpp:525-625) */
 int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out);

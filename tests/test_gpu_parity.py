@@ -182,6 +182,20 @@ def test_synthetic_vs_oracle(k):
     compare_with_oracle([buf[:n].tobytes()], k)
 
 
+@pytest.mark.parametrize("k,m", [(31, 8), (31, 12), (31, 14), (63, 12), (63, 14), (21, 13)])
+def test_minimizer_sizes(k, m):
+    # -minimizer-size only moves k-mers between partitions: same counts whatever m (big jobs run with m = 12 / 14)
+    buf, n, _ = reads_fasta(G=300_000, coverage=30, L=150, err=0.01, seed=300 + m)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], k, abundance_min=2)
+    sc = SortingCountAlgorithm(BankBytes(data), {"-kmer-size": k, "-abundance-min": "2", "-minimizer-size": m}).execute()
+    keys, cnt = sc.getSolidCounts()
+    lo, hi, rc = ref.solid_kmers()
+    assert sc.getInfo()["kmers_nb_valid"] == ref.kmers_nb_valid and sc.getInfo()["kmers_nb_distinct"] == ref.nb_distinct
+    assert len(cnt) == len(rc) and (keys[:, 0] == lo).all() and (cnt.astype(np.int64) == rc).all()
+    assert (sc.getHistogram()[0] == ref.hist).all()
+
+
 @pytest.mark.parametrize("mode", ["auto", "sort", "hash", "smem"])
 def test_synthetic_medium_modes(mode):
     buf, n, _ = reads_fasta(G=1_000_000, coverage=30, L=150, err=0.01, seed=5)
@@ -189,14 +203,40 @@ def test_synthetic_medium_modes(mode):
     assert sc.getInfo()["engine"]["nb_partitions"] > 4
 
 
+@pytest.mark.parametrize("heavy", ["bucket", "table"])
 @pytest.mark.parametrize("k", [31, 63])
-def test_auto_mixed_shared_memory_and_global_table(k):
+def test_auto_mixed_shared_memory_and_heavy_partitions(k, heavy, monkeypatch):
     # a shared-memory table far smaller than the heavy minimizer bins, in AUTO mode: the partitions beyond two sub-passes
-    # are renumbered to the end and counted by the global table, the others by the shared-memory path, in the same job
+    # are renumbered to the end and expanded into hash buckets of flat keys counted in shared memory (default) or counted
+    # by the global table (DSKGPU_HEAVY_PATH=table), the others by the shared-memory path, in the same job
+    monkeypatch.setenv("DSKGPU_HEAVY_PATH", heavy)
     buf, n, _ = reads_fasta(G=1_000_000, coverage=30, L=150, err=0.01, seed=11)
     sc = compare_with_oracle([buf[:n].tobytes()], k, engine=dict(count_mode="auto", smem_table_slots=256, hash_log2_slots=18))
     st = sc.getInfo()["engine"]
-    assert st["nb_parts_smem"] > 0 and st["nb_groups_hash"] > 0 and st["smem_table_slots"] == 256
+    assert st["nb_parts_smem"] > 0 and st["smem_table_slots"] == 256
+    assert (st["nb_groups_bucket"] > 0) == (heavy == "bucket") and (st["nb_groups_hash"] > 0) == (heavy == "table")
+
+
+def test_heavy_bucket_overflow_falls_back_to_the_table(monkeypatch):
+    # one k-mer with a huge multiplicity (poly-A reads) outgrows any hash-bucket slab: that group must fall back to the
+    # global table, never lose counts
+    monkeypatch.setenv("DSKGPU_HEAVY_PATH", "bucket")
+    buf, n, _ = reads_fasta(G=200_000, coverage=20, L=150, err=0.01, seed=21)
+    data = buf[:n].tobytes() + b"".join(b">p%d\n%s\n" % (i, b"A" * 150) for i in range(3000))
+    sc = compare_with_oracle([data], 31, engine=dict(count_mode="auto", smem_table_slots=256, hash_log2_slots=16))
+    st = sc.getInfo()["engine"]
+    assert st["nb_groups_hash"] > 0
+
+
+def test_heavy_buckets_with_per_bank_counts():
+    # -histo2D + heavy partitions: the bank id rides in the two spare top bits of the flat keys
+    g = genome_codes(300_000, seed=19)
+    asm = assembly_fasta(g)
+    buf, n, _ = reads_fasta(coverage=25, L=150, err=0.01, seed=19, genome=g)
+    for k in (31, 63, 21):
+        sc = compare_with_oracle([asm, buf[:n].tobytes()], k, histo2d=True, engine=dict(count_mode="auto", smem_table_slots=256, hash_log2_slots=16))
+        st = sc.getInfo()["engine"]
+        assert st["nb_groups_bucket"] > 0 and st["nb_parts_smem"] > 0
 
 
 def test_histo2d_assembly_vs_reads():
@@ -316,7 +356,7 @@ def test_multi_rank_exchange_in_process(W, k, mode, proto):
             valid += st["kmers_nb_valid"]; distinct += st["kmers_nb_distinct"]
             assert st["nb_partitions"] == P
             if extra:
-                assert st["nb_parts_smem"] > 0 and st["nb_groups_hash"] > 0
+                assert st["nb_parts_smem"] > 0 and st["nb_groups_hash"] + st["nb_groups_bucket"] > 0
         keys = np.concatenate(keys); cnts = np.concatenate(cnts)
         order = np.lexsort((keys[:, 0], keys[:, -1])) if keys.shape[1] == 2 else np.argsort(keys[:, 0], kind="stable")
         keys, cnts = keys[order], cnts[order]
