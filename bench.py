@@ -242,6 +242,7 @@ def main():
     ap.add_argument("--minimizer-size", type=int, default=0, help="0 = what the host adapters do: dskgpu_suggest_minimizer_size(k-mers of the whole job)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")          # stdout carries the JSON line and nothing else
     workload = "synthetic %.0f Mbp genome, %dx %dbp reads, %.0f%% error, k=%d" % (
         args.genome / 1e6, args.coverage, args.read_len, args.err * 100, args.kmer_size)
     if (args.genome, args.coverage, args.read_len, args.kmer_size) == (5_000_000, 100, 150, 31):
