@@ -242,7 +242,10 @@ def main():
     ap.add_argument("--minimizer-size", type=int, default=0, help="0 = what the host adapters do: dskgpu_suggest_minimizer_size(k-mers of the whole job)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")          # stdout carries the JSON line and nothing else
+    # stdout carries the JSON line and nothing else: whatever libraries print (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     workload = "synthetic %.0f Mbp genome, %dx %dbp reads, %.0f%% error, k=%d" % (
         args.genome / 1e6, args.coverage, args.read_len, args.err * 100, args.kmer_size)
     if (args.genome, args.coverage, args.read_len, args.kmer_size) == (5_000_000, 100, 150, 31):
@@ -288,7 +291,7 @@ def main():
                 "config": {"workload": workload, "kmers_per_step": vals[0][0] if vals else 0},
                 "cpu_baseline": {"value": val, "unit": "Gk-mers/s", "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": val, "unit": "Gk-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out); json_out.flush()
         return 0
 
     # ------------------------------------------------------------------------------------------ our arm
@@ -360,12 +363,13 @@ def main():
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0; dom_ms = 0.0; dom_n = 0; stage = {}
+    launches = 0; dom_ms = 0.0; dom_n = 0; stage = {}; x_ms = 0.0; x_bytes = 0
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
         st = eng.stats()
         launches += st["gpu_launches"]; dom_ms += st["ms_dominant_kernel"]; dom_n += st["dominant_kernel_launches"]
+        x_ms += st["ms_exchange"]; x_bytes += st["exchange_bytes_out"]
         for kk in ("ms_parse", "ms_superk", "ms_partition", "ms_count", "ms_sort"):
             stage[kk] = stage.get(kk, 0.0) + st[kk] / args.steps
     e1.record(stream)
@@ -389,6 +393,13 @@ def main():
         ms_all, kmers_all = float(tmax[0]), float(tsum[1])
     else:
         ms_all, kmers_all = ms, float(kmers)
+    xt = torch.tensor([x_ms, float(x_bytes)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        xmax = xt.clone(); dist.all_reduce(xmax, op=dist.ReduceOp.MAX)
+        xsum = xt.clone(); dist.all_reduce(xsum, op=dist.ReduceOp.SUM)
+        x_ms_max, x_bytes_all = float(xmax[0]), float(xsum[1])
+    else:
+        x_ms_max, x_bytes_all = 0.0, 0.0
     chk = [int(x) for x in chk.cpu()]
     checks = {"histogram_mass": chk[0], "valid_kmers": chk[1], "distinct_kmers": chk[2], "solid_kmers": chk[3],
               "every_valid_kmer_counted": (chk[0] == chk[1]) if not args.histo2d else None}
@@ -456,8 +467,17 @@ def main():
                          "kernel": dom_kernel, "launches": int(dom_n), "avg_launch_ms": 1e3 * dom_avg_s,
                          "peak_source": peak_src, "algorithmic_bytes_per_kmer": ab["S2_expand"] + ab["S3_sort"]},
             "pipeline_roofline": {"A_k_bytes_per_kmer": A, "achieved": value / world * A, "peak": peak, "unit": "GB/s", "frac": value / world * A / peak,
+                                  "peak_nominal": 8000.0, "frac_nominal": value / world * A / 8000.0,
                                   "note": "whole step per GPU against SURVEY 8(d) A(k); the hash path moves fewer HBM bytes than A(k) assumes"},
         }
+        if world > 1:
+            # records stored into other ranks' HBM by k_xchg_copy (summed over ranks and steps) / the slowest rank's
+            # summed copy-kernel time (CUDA events on the context stream), per GPU, against 900 GB/s per direction
+            per_gpu = (x_bytes_all / world) / (x_ms_max / 1e3) / 1e9 if x_ms_max > 0 else 0.0
+            line["nvlink"] = {"exchanged_bytes_per_step": x_bytes_all / args.steps, "ms_exchange_per_step": x_ms_max / args.steps,
+                              "achieved": per_gpu, "peak": 900.0, "unit": "GB/s per GPU, one direction", "frac": per_gpu / 900.0,
+                              "share_of_step": (x_ms_max / args.steps) / (ms_all / args.steps),
+                              "note": "the copy kernel also moves each rank's own partitions (1/N of the records) HBM->HBM inside the same launch"}
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline and not args.histo2d:
@@ -465,7 +485,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(args, pinned, n, sample_frac=min(1.0, 6e8 / max(1, n)))
             except Exception as ex:  # never lose the GPU line to a baseline hiccup
                 line["cpu_baseline"] = {"value": None, "unit": "Gk-mers/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % ex}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out); json_out.flush()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -37,10 +37,11 @@ class Stats(C.Structure):
         ("ms_sort", C.c_float), ("ms_total", C.c_float), ("ms_dominant_kernel", C.c_float),
         ("dominant_kernel_launches", C.c_uint32), ("nb_parts_smem", C.c_uint32), ("nb_smem_splits", C.c_uint32),
         ("smem_table_slots", C.c_uint32), ("density_ppm", C.c_uint32), ("log2_bins", C.c_uint32), ("nb_groups_bucket", C.c_uint32), ("reserved", C.c_uint32 * 1),
+        ("exchange_bytes_out", C.c_uint64), ("ms_exchange", C.c_float), ("reserved2", C.c_uint32),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
 
 
 # every symbol include/dskgpu.h declares (tests check the library exports all of them)

@@ -79,6 +79,7 @@ struct dskgpu_ctx {
     DevBuf sendbuf;
     // exchange v2 (bulk segments): records in local partition order, per-partition offsets on the device, pinned global histogram
     DevBuf lrecs, xoff, xpeers, bcur;
+    u64 xchg_bytes_out = 0;
     unsigned long long* h_ghist = nullptr;
     std::vector<u64> g_part_recs;                    // whole-job records of every partition
     std::vector<u64> x_need;                         // records every rank receives
@@ -122,7 +123,7 @@ static int ensure(dskgpu_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false, s
     return 0;
 }
 
-enum { SPAN_PARSE = 0, SPAN_SUPERK = 1, SPAN_PART = 2, SPAN_COUNT = 3, SPAN_SORT = 4, SPAN_DOM = 5, SPAN_TOTAL = 6, SPAN_SORTPASS = 7 };
+enum { SPAN_PARSE = 0, SPAN_SUPERK = 1, SPAN_PART = 2, SPAN_COUNT = 3, SPAN_SORT = 4, SPAN_DOM = 5, SPAN_TOTAL = 6, SPAN_SORTPASS = 7, SPAN_XCHG = 8 };
 
 static cudaEvent_t get_event(dskgpu_ctx* ctx)
 {
@@ -286,7 +287,7 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     ctx->state = 0; ctx->cur_bank = -1; ctx->stream_open = false; ctx->pending_cr = 0;
     ctx->nrec_known = 0; ctx->k2_inflight = false; ctx->chunk_parity = 0;
     ctx->n_solid = 0; ctx->results_on_host = false; ctx->nparts = 0;
-    ctx->xchg_planned = false; ctx->xchg_scattered = false; ctx->totals_done = false; ctx->local_nrec = ctx->local_nkm = 0;
+    ctx->xchg_planned = false; ctx->xchg_scattered = false; ctx->xchg_bytes_out = 0; ctx->totals_done = false; ctx->local_nrec = ctx->local_nkm = 0;
     ctx->bytes_pushed = 0; ctx->sample_queued = false; ctx->sample_nkm = ctx->sample_distinct = 0; ctx->sample_wmult = 0.0;
     ctx->global_set = false; ctx->g_total_kmers = 0; ctx->density = 1.0; ctx->density_known = false; ctx->bin_level = NBINS_LOG2; ctx->hist_fetched = false;
     ctx->peer_recv.clear();
@@ -1139,6 +1140,7 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
     ctx->st.ms_partition = span_ms(ctx, SPAN_PART); ctx->st.ms_count = span_ms(ctx, SPAN_COUNT);
     ctx->st.ms_sort = span_ms(ctx, SPAN_SORT);
     ctx->st.ms_dominant_kernel = span_ms(ctx, SPAN_DOM, &ctx->st.dominant_kernel_launches);
+    ctx->st.ms_exchange = span_ms(ctx, SPAN_XCHG); ctx->st.exchange_bytes_out = ctx->xchg_bytes_out;
     ctx->st.ms_total = ctx->st.ms_parse + ctx->st.ms_superk + ctx->st.ms_partition + ctx->st.ms_count + ctx->st.ms_sort;
     ctx->state = 1;
     return DSKGPU_OK;
@@ -1395,9 +1397,17 @@ int dskgpu_xchg2_scatter(dskgpu_ctx* ctx, const void* d_matrix)
         SpanGuard g(ctx, SPAN_PART);
         CK(cudaMemcpyAsync(ctx->xpeers.p, ctx->peer_recv.data(), (size_t)W * 8, cudaMemcpyHostToDevice, ctx->stream));
         const unsigned grid = (unsigned)std::min<u32>(P, (u32)ctx->num_sms * 8);
+        cudaEvent_t xa = get_event(ctx), xb = get_event(ctx);
+        cudaEventRecord(xa, ctx->stream);
         k_xchg_copy<<<grid, 256, 0, ctx->stream>>>((const ulonglong2*)ctx->lrecs.p, (const u64*)ctx->xoff.p, (const u64*)d_matrix,
                                                    (ulonglong2* const*)ctx->xpeers.p, W, me, P, (u32)ctx->RW / 2); LAUNCHED();
+        cudaEventRecord(xb, ctx->stream);
+        ctx->spans.push_back({xa, xb, SPAN_XCHG});
         CK(cudaGetLastError());
+        // bytes this rank stores into OTHER ranks' HBM (NVLink); its own partitions are a local copy
+        u64 remote = 0;
+        for (u32 p = 0; p < P; p++) if (p % W != me) remote += ctx->h_part_recs[p];
+        ctx->xchg_bytes_out = remote * (u64)ctx->RW * 8;
     }
     ctx->xchg_scattered = true;
     return DSKGPU_OK;

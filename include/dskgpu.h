@@ -113,6 +113,10 @@ typedef struct dskgpu_stats {
     uint32_t log2_bins;             /* minimizer-bin level the partitions were packed from (16..20) */
     uint32_t nb_groups_bucket;      /* heavy partitions: groups expanded into hash buckets of flat keys, counted in shared memory */
     uint32_t reserved[1];
+    /* multi-GPU exchange (this rank): bytes stored into other ranks' HBM over NVLink, duration of the segment-copy kernel */
+    uint64_t exchange_bytes_out;
+    float    ms_exchange;
+    uint32_t reserved2;
 } dskgpu_stats;
 
 /* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */
