@@ -48,6 +48,8 @@ def main():
     cases = [(31, "auto", 400_000, 30, {}), (63, "auto", 400_000, 30, {}), (31, "hash", 300_000, 20, dict(hash_log2_slots=16)),
              (31, "sort", 300_000, 20, {}), (31, "auto", 300_000, 30, dict(smem_table_slots=256, hash_log2_slots=16)),
              (31, "auto", 2_000_000, 30, {}), (63, "auto", 1_000_000, 30, {})]
+    if os.environ.get("MGPU_SHORT"):               # N >= 4 boxes are charged N x: one case per path
+        cases = [cases[0], cases[1], cases[4], cases[5]]
     shared = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(shared)
     for ci, (k, mode, G, cov, extra) in enumerate(cases):
@@ -60,7 +62,7 @@ def main():
         # one shared torch stream (what bench.py does)
         eng = GpuCounter(kmer_size=k, abundance_min=2, device=local, rank=rank, world_size=W, count_mode=mode,
                          stream=(shared.cuda_stream if ci % 2 == 0 else None), **extra)
-        for rep in range(3):                      # second round re-uses receive buffers + peer handles (no IPC re-open)
+        for rep in range(2 if os.environ.get("MGPU_SHORT") else 3):                      # second round re-uses receive buffers + peer handles (no IPC re-open)
             progress("case %d k=%d %s rep %d: push" % (ci, k, mode, rep))
             eng.reset()
             eng.push_bytes(piece)
