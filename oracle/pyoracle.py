@@ -11,18 +11,25 @@ import numpy as np
 
 ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_LIB_WIDE = None
 
 KINDS = {"sum": 0, "min": 1, "max": 2, "one": 3, "all": 4, "custom": 5}
 
 
-def _lib():
-    global _LIB
-    if _LIB is not None:
+def _lib(k=31):
+    """liboracle.so (128-bit keys, k <= 63: the pinned restatement of KSIZE_LIST "32 64") or, for k >= 64,
+    liboracle_wide.so (same source built with -DORC_WIDE: 256-bit keys, spans 96 and 128)."""
+    global _LIB, _LIB_WIDE
+    wide = k >= 64
+    if not wide and _LIB is not None:
         return _LIB
-    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    if wide and _LIB_WIDE is not None:
+        return _LIB_WIDE
+    name = "liboracle_wide.so" if wide else "liboracle.so"
+    so = os.path.join(ORACLE_DIR, name)
     src = os.path.join(ORACLE_DIR, "dsk_oracle.c")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "liboracle.so"])
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", name])
     L = C.CDLL(so)
     L.orc_create.restype = C.c_void_p
     L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -34,17 +41,23 @@ def _lib():
         f = getattr(L, "orc_" + name)
         f.restype = C.c_uint64
         f.argtypes = [C.c_void_p]
-    for name in ("keys_lo", "keys_hi", "counts", "sums", "solid", "hist", "hist2d"):
+    for name in ("keys_lo", "keys_hi", "keys_w2", "keys_w3", "counts", "sums", "solid", "hist", "hist2d"):
         f = getattr(L, "orc_" + name)
         f.restype = C.c_void_p
         f.argtypes = [C.c_void_p]
     L.orc_kmers_of.restype = C.c_int
     L.orc_kmers_of.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+    L.orc_kmers_of4.restype = C.c_int
+    L.orc_kmers_of4.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+    L.orc_max_k.restype = C.c_int
     L.orc_parse_stats.restype = C.c_uint64
     L.orc_parse_stats.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t]
     L.orc_mmer_lut.restype = C.c_uint32
     L.orc_mmer_lut.argtypes = [C.c_uint32, C.c_int]
-    _LIB = L
+    if wide:
+        _LIB_WIDE = L
+    else:
+        _LIB = L
     return L
 
 
@@ -69,6 +82,8 @@ class OracleResult:
     nb_superkmers: int
     keys_lo: np.ndarray      # distinct canonical k-mers, ascending (low 64 bits)
     keys_hi: np.ndarray      # high 64 bits (all zero for k<=32)
+    keys_w2: np.ndarray      # bits 128..191 (k >= 65, wide build; zeros otherwise)
+    keys_w3: np.ndarray      # bits 192..255 (k >= 97)
     counts: np.ndarray       # int32 [ndistinct, nbanks]
     sums: np.ndarray         # int32 [ndistinct]
     solid: np.ndarray        # bool  [ndistinct]
@@ -88,6 +103,11 @@ class OracleResult:
         s = self.solid
         return self.keys_lo[s], self.keys_hi[s], self.sums[s]
 
+    def solid_kmer_words(self):
+        """(uint64[n, 4] value words, least significant first; int32[n] abundance) of the solid k-mers, ascending"""
+        s = self.solid
+        return np.stack([self.keys_lo[s], self.keys_hi[s], self.keys_w2[s], self.keys_w3[s]], axis=1), self.sums[s]
+
 
 def _np_from(ptr, dtype, n):
     if n == 0:
@@ -100,7 +120,9 @@ class Oracle:
     """Accumulate sequences/files per bank, then finish() -> OracleResult."""
 
     def __init__(self, k, nbanks=1, m=0):
-        self.L = _lib()
+        self.L = _lib(k)
+        if k > self.L.orc_max_k():
+            raise ValueError("oracle built for k <= %d" % self.L.orc_max_k())
         self.k, self.nbanks = k, nbanks
         self.h = self.L.orc_create(k, nbanks, m)
 
@@ -128,6 +150,8 @@ class Oracle:
             nb_seq=L.orc_nb_seq(h), nb_nt=L.orc_nb_nt(h), nb_superkmers=L.orc_nb_superkmers(h),
             keys_lo=_np_from(L.orc_keys_lo(h), np.uint64, nd),
             keys_hi=_np_from(L.orc_keys_hi(h), np.uint64, nd),
+            keys_w2=_np_from(L.orc_keys_w2(h), np.uint64, nd),
+            keys_w3=_np_from(L.orc_keys_w3(h), np.uint64, nd),
             counts=_np_from(L.orc_counts(h), np.int32, nd * nb).reshape(nd, nb),
             sums=_np_from(L.orc_sums(h), np.int32, nd),
             solid=_np_from(L.orc_solid(h), np.uint8, nd).astype(bool),
@@ -224,10 +248,23 @@ def kmers_of(seq, k, m=0, forward=False):
     n = max(0, len(seq) - k + 1)
     lo = np.zeros(n, np.uint64); hi = np.zeros(n, np.uint64)
     valid = np.zeros(n, np.uint8); mn = np.zeros(n, np.uint32); mp = np.zeros(n, np.int32)
-    got = _lib().orc_kmers_of(seq, len(seq), k, m, int(forward), lo.ctypes.data, hi.ctypes.data,
-                              valid.ctypes.data, mn.ctypes.data, mp.ctypes.data)
+    got = _lib(k).orc_kmers_of(seq, len(seq), k, m, int(forward), lo.ctypes.data, hi.ctypes.data,
+                               valid.ctypes.data, mn.ctypes.data, mp.ctypes.data)
     assert got == n
     return lo, hi, valid.astype(bool), mn, mp
+
+
+def kmers_of_words(seq, k, m=0, forward=False):
+    """k-mer values as uint64[n, 4] (least significant word first), validity, minimizers (k up to 127)"""
+    if isinstance(seq, str):
+        seq = seq.encode()
+    n = max(0, len(seq) - k + 1)
+    w = [np.zeros(n, np.uint64) for _ in range(4)]
+    valid = np.zeros(n, np.uint8); mn = np.zeros(n, np.uint32); mp = np.zeros(n, np.int32)
+    got = _lib(k).orc_kmers_of4(seq, len(seq), k, m, int(forward), w[0].ctypes.data, w[1].ctypes.data, w[2].ctypes.data,
+                                w[3].ctypes.data, valid.ctypes.data, mn.ctypes.data, mp.ctypes.data)
+    assert got == n
+    return np.stack(w, axis=1), valid.astype(bool), mn, mp
 
 
 def parse_stats(data):
@@ -247,8 +284,13 @@ def mmer_lut(x, m):
 # ------------------------------------------------------------------------------------------------
 # the real reference (oracle/_ref/bin/{dsk,dsk2ascii,gatb-h5dump}), when it was built
 # ------------------------------------------------------------------------------------------------
-def _ref_bin(name):
-    return os.path.join(ORACLE_DIR, "_ref", "bin", name)
+def _ref_bin(name, wide=False):
+    """oracle/_ref/bin (KSIZE_LIST "32 64") or oracle/_ref/wide/bin (KSIZE_LIST "32 64 96 128", golden generation only)"""
+    return os.path.join(ORACLE_DIR, "_ref", "wide", "bin", name) if wide else os.path.join(ORACLE_DIR, "_ref", "bin", name)
+
+
+def ref_wide_available():
+    return all(os.access(_ref_bin(n, True), os.X_OK) for n in ("dsk", "dsk2ascii"))
 
 
 def ref_available():
@@ -256,13 +298,13 @@ def ref_available():
 
 
 def run_reference(files, k, abundance_min=2, histo=True, histo2d=False, nb_cores=0, extra=(), workdir=None,
-                  want_kmers=True, solidity_kind=None, abundance_max=None):
+                  want_kmers=True, solidity_kind=None, abundance_max=None, wide=False):
     """Runs the reference `dsk` on `files` (list of paths; comma-joined like the CLI) and returns
     dict(kmers=[(str,count)...] sorted, hist=np.uint64[10001], hist2d=..., stats=str, seconds=float)."""
     import time
     tmp = workdir or tempfile.mkdtemp(prefix="dskref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     out = os.path.join(tmp, "ref")
-    cmd = [_ref_bin("dsk"), "-file", ",".join(files), "-kmer-size", str(k), "-abundance-min", str(abundance_min),
+    cmd = [_ref_bin("dsk", wide), "-file", ",".join(files), "-kmer-size", str(k), "-abundance-min", str(abundance_min),
            "-out", out, "-out-tmp", tmp, "-out-dir", tmp, "-verbose", "1", "-nb-cores", str(nb_cores)]
     if histo:
         cmd += ["-histo", "1"]
@@ -293,7 +335,7 @@ def run_reference(files, k, abundance_min=2, histo=True, histo2d=False, nb_cores
         res["hist2d"] = np.array(rows, dtype=np.uint64).T   # -> [dim2(11), dim1(10001)]
     if want_kmers:
         txt = os.path.join(tmp, "ref.txt")
-        q = subprocess.run([_ref_bin("dsk2ascii"), "-file", out + ".h5", "-out", txt], cwd=tmp, capture_output=True, text=True)
+        q = subprocess.run([_ref_bin("dsk2ascii", wide), "-file", out + ".h5", "-out", txt], cwd=tmp, capture_output=True, text=True)
         if q.returncode != 0:
             raise RuntimeError("dsk2ascii failed: " + q.stderr[-2000:])
         km = []

@@ -74,3 +74,28 @@ def read_input(name):
     if head == b"\x1f\x8b":
         return gzip.open(p, "rb").read()
     return open(p, "rb").read()
+
+
+def kmer_words_to_strings(words, k):
+    """uint64[n, W] value words (least significant first, W up to 4) -> list of k-mer strings"""
+    words = np.asarray(words, dtype=np.uint64)
+    n = len(words)
+    if n == 0:
+        return []
+    out = np.empty((n, k), dtype=np.uint8)
+    lut = np.frombuffer(NT.encode(), dtype=np.uint8)
+    for i in range(k):
+        sh = 2 * (k - 1 - i)
+        c = (words[:, sh // 64] >> np.uint64(sh % 64)) & np.uint64(3)
+        out[:, i] = lut[c.astype(np.int64)]
+    return [row.tobytes().decode() for row in out]
+
+
+def digest_words(words, counts, k):
+    """sha256 over 'KMER count\\n' lines sorted in C locale, for keys given as 64-bit words (any span)"""
+    strs = kmer_words_to_strings(words, k)
+    pairs = sorted(zip(strs, (int(c) for c in counts)))
+    m = hashlib.sha256()
+    for s, c in pairs:
+        m.update(("%s %d\n" % (s, c)).encode())
+    return m.hexdigest(), pairs
