@@ -21,6 +21,7 @@
 #include "superk.cuh"
 #include "count.cuh"
 #include "count_smem.cuh"
+#include "kmer_wide.cuh"
 #include "radix.cuh"
 
 using namespace dsk;
@@ -1637,6 +1638,48 @@ int64_t dskgpu_selftest_superkmers(const uint8_t* codes, size_t n, int k, int m,
     }
     if (n_records) *n_records = nrec;
     return (int64_t)w;
+}
+
+// host model of the wide spans (kmer_wide.cuh, k <= 127): canonical k-mers of a code stream computed two ways -- rolling
+// (kmern_roll) and by extraction from a packed record (recn_kmer_at + kmern_revcomp) -- which must agree; returns the number
+// of windows, or -1 - p at the first window p where the two disagree.  out_words: [n-k+1][4], out_valid: [n-k+1].
+int64_t dskgpu_selftest_wide_kmers(const uint8_t* codes, size_t n, int k, uint64_t* out_words, uint8_t* out_valid)
+{
+    if (k < 2 || k > 127 || n < (size_t)k) return 0;
+    const size_t npos = n - k + 1;
+    auto run = [&](auto tag) -> int64_t {
+        constexpr int KW = decltype(tag)::value, RW = 2 * KW;
+        const int cap_bases = 32 * RW - 8;                                   // bases a record of RW words can hold
+        Kmer<KW> f, rc;
+        for (int i = 0; i < KW; i++) { f.w[i] = 0; rc.w[i] = 0; }
+        for (size_t i = 0; i < n; i++) {
+            kmern_roll<KW>(f, rc, codes[i] & 3, k);
+            if (i + 1 < (size_t)k) continue;
+            const size_t p = i + 1 - k;
+            bool ok = true;
+            for (int j = 0; j < k; j++) if (codes[p + j] >> 2) ok = false;
+            const Kmer<KW> c = kmern_canonical<KW>(f, rc);
+            for (int q = 0; q < 4; q++) out_words[4 * p + q] = q < KW ? c.w[q] : 0;
+            out_valid[p] = ok;
+            // second way: a record that starts a few bases before p (so that the extraction offset varies)
+            const size_t back = std::min<size_t>(p, (size_t)(p % 7));
+            const size_t r0 = p - back;
+            const size_t nb = std::min<size_t>((size_t)cap_bases, n - r0);
+            if (back + (size_t)k > nb) continue;
+            u64 r[RW];
+            for (int q = 0; q < RW; q++) r[q] = 0;
+            for (size_t b = 0; b < nb; b++) r[b >> 5] |= (u64)(codes[r0 + b] & 3) << (62 - 2 * (b & 31));
+            r[RW - 1] &= ~0xFFFFULL;                                         // the [nk:8][bank:8] field
+            const Kmer<KW> g = recn_kmer_at<KW, RW>(r, (int)back, k);
+            const Kmer<KW> c2 = kmern_canonical<KW>(g, kmern_revcomp<KW>(g, k));
+            if (!kmern_eq<KW>(g, f) || !kmern_eq<KW>(c2, c)) return -1 - (int64_t)p;
+        }
+        return (int64_t)npos;
+    };
+    if (k < 32) return run(std::integral_constant<int, 1>());
+    if (k < 64) return run(std::integral_constant<int, 2>());
+    if (k < 96) return run(std::integral_constant<int, 3>());
+    return run(std::integral_constant<int, 4>());
 }
 
 }  // extern "C"

@@ -251,6 +251,9 @@ int64_t dskgpu_selftest_scan(const char* bytes, size_t n, int format, uint8_t* o
 int dskgpu_selftest_minimizers(const uint8_t* codes, size_t n, int k, int m, uint32_t* out_min, uint8_t* out_valid);
 /* super-k-mer packing round trip: codes -> records -> canonical k-mers (host copy of pack + expand) */
 int64_t dskgpu_selftest_superkmers(const uint8_t* codes, size_t n, int k, int m, uint64_t* out_kmers /*[n*words]*/, size_t cap, uint64_t* n_records);
+/* wide spans groundwork (k <= 127, dsk_b200/csrc/kmer_wide.cuh; the counting path itself still rejects k >= 64): canonical
+ * k-mers of a code stream as 4 words each, computed by rolling and by extraction from a packed record (must agree) */
+int64_t dskgpu_selftest_wide_kmers(const uint8_t* codes, size_t n, int k, uint64_t* out_words /*[n-k+1][4]*/, uint8_t* out_valid);
 
 #ifdef __cplusplus
 }

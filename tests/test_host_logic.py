@@ -193,3 +193,20 @@ def test_suggested_minimizer_size_grows_with_the_job(L):
     assert f(0, 31) == 10 and f(400_000_000, 31) == 10 and f(800_000_000, 31) == 12 and f(3_000_000_000, 31) == 12
     assert f(72_000_000_000, 31) == 14 and f(72_000_000_000, 63) == 14
     assert f(72_000_000_000, 11) == 10 and f(10, 5) == 4                      # clipped to k-1 (ConfigurationAlgorithm.cpp:249-251)
+
+
+@pytest.mark.parametrize("k", [5, 31, 32, 33, 63, 64, 65, 71, 95, 96, 97, 111, 127])
+def test_wide_kmer_logic_matches_the_wide_oracle(L, k):
+    # dsk_b200/csrc/kmer_wide.cuh (N-word roll / revcomp / extraction from a packed record), host-compiled, against the
+    # oracle (wide build for k >= 64, pinned against the reference built with KSIZE_LIST "32 64 96 128")
+    rng = np.random.default_rng(1000 + k)
+    seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 700).tobytes())
+    seq = seq[:300] + b"N" + seq[301:500] + b"GGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGG" + seq[500:]
+    codes = encode(seq)
+    n = len(seq) - k + 1
+    words = np.zeros((n, 4), np.uint64); valid = np.zeros(n, np.uint8)
+    got = L.dskgpu_selftest_wide_kmers(codes.ctypes.data, codes.size, k, words.ctypes.data, valid.ctypes.data)
+    assert got == n, "rolling and record extraction disagree at window %d" % (-1 - got)
+    ow, ovalid, _, _ = oracle.kmers_of_words(seq, k)
+    assert (valid.astype(bool) == ovalid).all()
+    assert (words[ovalid] == ow[ovalid]).all()
