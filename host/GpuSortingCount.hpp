@@ -44,6 +44,15 @@ inline void check(int rc, dskgpu_ctx* ctx, const char* what)
     throw Exception("%s: %s (%s)", what, dskgpu_strerror(rc), detail ? detail : "");
 }
 
+/** Thrown instead of Exception when the device record scanner rejects the input layout (DSKGPU_ERR_FORMAT): the adapter
+ *  answers by feeding the same banks through the reference's own parser (IBank::iterator), see execute(). */
+struct FormatRejected { std::string what; };
+inline void checkFormat(int rc, dskgpu_ctx* ctx, const char* what)
+{
+    if (rc == DSKGPU_ERR_FORMAT) { FormatRejected e; const char* d = dskgpu_last_error(ctx); e.what = d ? d : ""; throw e; }
+    check(rc, ctx, what);
+}
+
 template <size_t span = KMER_DEFAULT_SPAN>
 class GpuSortingCount : public Algorithm
 {
@@ -75,14 +84,27 @@ public:
     void execute()
     {
         configure();
-        {
-            TIME_INFO(getTimeInfo(), "fill_partitions");          // same labels as K/SortingCountAlgorithm.cpp:1218
-            feedBanks();
-        }
-        {
-            TIME_INFO(getTimeInfo(), "fill_solid_kmers");         // K/SortingCountAlgorithm.cpp:1391
-            check(dskgpu_finish(_ctx), _ctx, "dskgpu_finish");
-            if (_autoCutoff) executeAutoCutoff();
+        // The device scanner takes what dsk is fed in practice: FASTA (single- or multi-line) and 4-line FASTQ, plain or
+        // gzip.  Whatever else BankFasta accepts (multi-line FASTQ, '+' lines inside FASTA, ...; BankFasta.cpp:485-572) is
+        // rejected by the scanner, never mis-parsed; the same banks then go through the reference's own parser, sequence by
+        // sequence (IBank::iterator -> dskgpu_push_reads), and the counting path is unchanged.
+        for (int attempt = 0; ; attempt++) {
+            try {
+                {
+                    TIME_INFO(getTimeInfo(), "fill_partitions");          // same labels as K/SortingCountAlgorithm.cpp:1218
+                    feedBanks();
+                }
+                {
+                    TIME_INFO(getTimeInfo(), "fill_solid_kmers");         // K/SortingCountAlgorithm.cpp:1391
+                    checkFormat(dskgpu_finish(_ctx), _ctx, "dskgpu_finish");
+                    if (_autoCutoff) executeAutoCutoff();
+                }
+                break;
+            } catch (FormatRejected& e) {
+                if (attempt > 0 || _viaIterator) throw Exception("dskgpu: input rejected by the record scanner (%s)", e.what.c_str());
+                _viaIterator = true;
+                check(dskgpu_reset(_ctx), _ctx, "dskgpu_reset");
+            }
         }
         writeResults();
     }
@@ -94,6 +116,7 @@ private:
     void setStorage(Storage* storage) { SP_SETATTR(storage); }
 
     Configuration     _config;
+    bool              _viaIterator = false;        // second attempt: banks parsed by the reference's own reader
     dskgpu_ctx*       _ctx;
     Partition<Count>* _solidCounts;
     dskgpu_stats      _st;
@@ -216,7 +239,8 @@ private:
             int r2 = (n == cap) ? gzread(f, buf[par ^ 1], (unsigned)cap) : 0;
             if (r2 < 0) { gzclose(f); throw Exception("read error on %s", path.c_str()); }
             const bool last = (r2 == 0);
-            check(dskgpu_push_bytes(_ctx, bankId, buf[par], n, DSKGPU_FMT_AUTO, last ? DSKGPU_PUSH_LAST : 0), _ctx, "dskgpu_push_bytes");
+            const int rc = dskgpu_push_bytes(_ctx, bankId, buf[par], n, DSKGPU_FMT_AUTO, last ? DSKGPU_PUSH_LAST : 0);
+            if (rc != DSKGPU_OK) { gzclose(f); checkFormat(rc, _ctx, "dskgpu_push_bytes"); }
             if (last) break;
             par ^= 1; n = (size_t)r2;
         }
@@ -262,7 +286,7 @@ private:
                 collectLeaves(composite ? top[t] : _bank, leaves);
                 for (size_t i = 0; i < leaves.size(); i++) {
                     const std::string id = leaves[i]->getId();
-                    if (isRegularFile(id)) feedFile((int)t, id, buf, cap);
+                    if (!_viaIterator && isRegularFile(id)) feedFile((int)t, id, buf, cap);
                     else feedSequences((int)t, leaves[i]);
                 }
             }
