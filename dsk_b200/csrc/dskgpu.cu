@@ -858,7 +858,7 @@ static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers)
 
 // greedy packing of consecutive bins (the role of Repartitor::computeDistrib, K/PartiInfo.cpp:48-106, on exact counts);
 // every rank derives the same plan from the same global histogram.  P is padded to a multiple of the world size.
-static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh /*[2 << bin_level] whole job*/)
+static void plan_partitions_host(dskgpu_ctx* ctx, const unsigned long long* gh /*[2 << bin_level] whole job*/)
 {
     const u32 NB_ = 1u << ctx->bin_level;
     const unsigned long long* gk = gh + NB_;
@@ -902,6 +902,13 @@ static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh /*[2 <<
     const u32 W = (u32)ctx->cfg.world_size;
     while (P % W) { ctx->g_part_kmers.push_back(0); ctx->g_part_recs.push_back(0); ctx->h_part_recs.push_back(0); ctx->h_part_kmers.push_back(0); P++; }
     ctx->nparts = P; ctx->st.nb_partitions = P;
+}
+
+// the plan (host only, above) + the device tables the scatter needs
+static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh)
+{
+    plan_partitions_host(ctx, gh);
+    const u32 P = ctx->nparts, NB_ = 1u << ctx->bin_level;
     int rc;
     if ((rc = ensure(ctx, ctx->cursor, (size_t)P * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dstbase, (size_t)P * 8))) return rc;
@@ -1638,6 +1645,34 @@ int64_t dskgpu_selftest_superkmers(const uint8_t* codes, size_t n, int k, int m,
     }
     if (n_records) *n_records = nrec;
     return (int64_t)w;
+}
+
+// host-only run of the partition planner (plan_partitions_host): what every rank derives from the all-reduced bin
+// histogram.  global_hist / local_hist: [2 << level] (records per bin, then k-mers per bin).  Outputs: bin2part[1 << level],
+// and per partition (capacity max_parts) the whole-job k-mers and this rank's records.  Returns the number of partitions
+// (a multiple of world_size), or -1 when max_parts is too small.  No device is touched.
+int64_t dskgpu_selftest_plan(int level, const uint64_t* global_hist, const uint64_t* local_hist, int world_size, int nb_counts,
+                             uint32_t smem_slots, double density, int count_mode, int forced_nb_partitions,
+                             uint32_t* bin2part, uint64_t* part_kmers, uint64_t* part_local_recs, size_t max_parts)
+{
+    if (level < NBINS_LOG2 || level > NBINS_FINE_LOG2 || !global_hist || !local_hist || world_size < 1) return DSKGPU_ERR_ARG;
+    dskgpu_ctx* ctx = new dskgpu_ctx();
+    dskgpu_config_default(&ctx->cfg);
+    ctx->cfg.world_size = world_size; ctx->cfg.count_mode = count_mode; ctx->cfg.nb_partitions = forced_nb_partitions;
+    ctx->NB = nb_counts; ctx->smem_cap = smem_slots; ctx->density = density; ctx->density_known = true; ctx->bin_level = level;
+    std::vector<unsigned long long> lh(local_hist, local_hist + ((size_t)2 << level));
+    ctx->h_bin_hist = lh.data();
+    plan_partitions_host(ctx, (const unsigned long long*)global_hist);
+    const u32 P = ctx->nparts;
+    int64_t ret = (int64_t)P;
+    if (P > max_parts) ret = -1;
+    else {
+        for (u32 b = 0; b < (1u << level); b++) bin2part[b] = ctx->h_bin2part[b];
+        for (u32 p = 0; p < P; p++) { part_kmers[p] = ctx->g_part_kmers[p]; part_local_recs[p] = ctx->h_part_recs[p]; }
+    }
+    ctx->h_bin_hist = nullptr;
+    delete ctx;
+    return ret;
 }
 
 // host model of the wide spans (kmer_wide.cuh, k <= 127): canonical k-mers of a code stream computed two ways -- rolling

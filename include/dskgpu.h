@@ -251,6 +251,11 @@ int64_t dskgpu_selftest_scan(const char* bytes, size_t n, int format, uint8_t* o
 int dskgpu_selftest_minimizers(const uint8_t* codes, size_t n, int k, int m, uint32_t* out_min, uint8_t* out_valid);
 /* super-k-mer packing round trip: codes -> records -> canonical k-mers (host copy of pack + expand) */
 int64_t dskgpu_selftest_superkmers(const uint8_t* codes, size_t n, int k, int m, uint64_t* out_kmers /*[n*words]*/, size_t cap, uint64_t* n_records);
+/* the partition planner on the host alone (what every rank derives from the all-reduced minimizer-bin histogram):
+ * hist arrays are [2 << level] = records per bin, then k-mers per bin; returns the number of partitions */
+int64_t dskgpu_selftest_plan(int level, const uint64_t* global_hist, const uint64_t* local_hist, int world_size, int nb_counts,
+                             uint32_t smem_slots, double density, int count_mode, int forced_nb_partitions,
+                             uint32_t* bin2part, uint64_t* part_kmers, uint64_t* part_local_recs, size_t max_parts);
 /* wide spans groundwork (k <= 127, dsk_b200/csrc/kmer_wide.cuh; the counting path itself still rejects k >= 64): canonical
  * k-mers of a code stream as 4 words each, computed by rolling and by extraction from a packed record (must agree) */
 int64_t dskgpu_selftest_wide_kmers(const uint8_t* codes, size_t n, int k, uint64_t* out_words /*[n-k+1][4]*/, uint8_t* out_valid);

@@ -210,3 +210,63 @@ def test_wide_kmer_logic_matches_the_wide_oracle(L, k):
     ow, ovalid, _, _ = oracle.kmers_of_words(seq, k)
     assert (valid.astype(bool) == ovalid).all()
     assert (words[ovalid] == ow[ovalid]).all()
+
+
+def _plan(L, level, gh, lh, world, nb_counts=1, slots=15360, density=0.26, mode=0, forced=0):
+    nb = 1 << level
+    b2p = np.zeros(nb, np.uint32); pk = np.zeros(nb + world, np.uint64); pr = np.zeros(nb + world, np.uint64)
+    P = L.dskgpu_selftest_plan(level, gh.ctypes.data, lh.ctypes.data, world, nb_counts, slots, density, mode, forced,
+                               b2p.ctypes.data, pk.ctypes.data, pr.ctypes.data, pk.size)
+    assert P > 0
+    return int(P), b2p, pk[:P], pr[:P]
+
+
+@pytest.mark.parametrize("world,level", [(1, 16), (2, 17), (4, 18), (8, 16)])
+def test_partition_planner_invariants_and_rank_agreement(L, world, level):
+    # what every rank derives from the all-reduced minimizer-bin histogram (plan_partitions_host): skewed bins (a few
+    # hot minimizers), ranks holding different shares of every bin
+    rng = np.random.default_rng(level * 10 + world)
+    nb = 1 << level
+    km = (rng.pareto(1.3, nb) * 3000).astype(np.uint64) + rng.integers(0, 2000, nb).astype(np.uint64)
+    km[rng.integers(0, nb, 5)] += np.uint64(2_000_000)                 # hot bins far beyond one shared-memory table
+    km[rng.integers(0, nb, 50)] = 0                                    # and empty ones
+    rec = (km // np.uint64(11)) + (km > 0).astype(np.uint64)
+    share = rng.dirichlet(np.ones(world), nb)                          # every rank's share of every bin
+    lrec = np.floor(share * rec[:, None]).astype(np.uint64)
+    lrec[:, 0] += rec - lrec.sum(1)
+    lkm = np.floor(share * km[:, None]).astype(np.uint64)
+    lkm[:, 0] += km - lkm.sum(1)
+    gh = np.concatenate([rec, km]).astype(np.uint64)
+    slots, density = 15360, 0.26
+    T = slots * 0.52 / density
+    plans = []
+    for r in range(world):
+        lh = np.concatenate([lrec[:, r], lkm[:, r]]).astype(np.uint64)
+        plans.append(_plan(L, level, gh, lh, world, slots=slots, density=density))
+    P, b2p, pk, _ = plans[0]
+    assert P % world == 0
+    for Pr, b2, pkr, _ in plans[1:]:                                   # same plan on every rank
+        assert Pr == P and (b2 == b2p).all() and (pkr == pk).all()
+    assert b2p.max() < P and int(pk.sum()) == int(km.sum())
+    assert (np.bincount(b2p, weights=km.astype(np.float64), minlength=P).astype(np.uint64) == pk).all()
+    # the ranks' local records of a partition add up to the whole-job records of its bins
+    tot_local = np.sum([p[3] for p in plans], axis=0)
+    assert (tot_local == np.bincount(b2p, weights=rec.astype(np.float64), minlength=P).astype(np.uint64)).all()
+    # a partition is at most T k-mers unless it is a single bin (a bin cannot be split: the minimizer decides the partition)
+    nbins_of = np.bincount(b2p, minlength=P)
+    assert ((pk <= T + 1) | (nbins_of == 1)).all()
+    # partitions beyond the reach of the shared-memory path (AUTO mode) are numbered after all the others, heaviest first
+    lim = slots * 0.75 / density * 2                                   # fit x 2^max_split0 (default 1)
+    heavy = np.nonzero(pk > lim)[0]
+    assert len(heavy) >= 5
+    nonempty_light = np.nonzero((pk <= lim) & (pk > 0))[0]
+    assert heavy.min() > nonempty_light.max()
+    assert (np.diff(pk[heavy].astype(np.int64)) <= 0).all()
+
+
+def test_partition_planner_forced_partition_count(L):
+    nb = 1 << 16
+    km = np.full(nb, 1000, np.uint64); rec = np.full(nb, 90, np.uint64)
+    gh = np.concatenate([rec, km])
+    P, b2p, pk, pr = _plan(L, 16, gh, gh, 1, mode=2, forced=64)      # hash mode, -nb-partitions style override
+    assert P == 64 and (pk == 1024 * 1000).all() and (np.diff(b2p.astype(np.int64)) >= 0).all() and int(pr.sum()) == int(rec.sum())
