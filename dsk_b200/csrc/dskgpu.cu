@@ -1663,6 +1663,13 @@ int64_t dskgpu_selftest_plan(int level, const uint64_t* global_hist, const uint6
     std::vector<unsigned long long> lh(local_hist, local_hist + ((size_t)2 << level));
     ctx->h_bin_hist = lh.data();
     plan_partitions_host(ctx, (const unsigned long long*)global_hist);
+    if (getenv("DSKGPU_PLAN_TIMING")) {                                   // warm re-runs on the same context, as in a job loop
+        for (int i = 0; i < 3; i++) {
+            const auto t0 = std::chrono::steady_clock::now();
+            plan_partitions_host(ctx, (const unsigned long long*)global_hist);
+            fprintf(stderr, "[plan] level %d: %.3f ms\n", level, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+    }
     const u32 P = ctx->nparts;
     int64_t ret = (int64_t)P;
     if (P > max_parts) ret = -1;
