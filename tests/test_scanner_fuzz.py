@@ -112,3 +112,40 @@ def test_odd_fasta_is_rejected_or_parsed_like_the_reference(L, data):
 @given(data=fastq4())
 def test_four_line_fastq_is_never_rejected_and_parsed_like_the_reference(L, data):
     check(L, data, must_accept=True, fastq=True)
+
+
+# ---------------------------------------------------------------- super-k-mer records: pack -> expand round trip
+@st.composite
+def sequence_k_m(draw):
+    k = draw(st.integers(3, 63))
+    m = draw(st.integers(2, min(14, k - 1)))
+    pieces = draw(st.lists(st.one_of(
+        st.text(alphabet="ACGT", min_size=1, max_size=120),                         # random stretch
+        st.sampled_from(["A", "C", "G", "T", "AC", "ACG", "AAT"]).flatmap(          # low complexity: one hot minimizer,
+            lambda u: st.integers(5, 150).map(lambda r: u * r)),                    # runs longer than a record can hold
+        st.sampled_from(["N", "n", "R", "NN"])), min_size=1, max_size=12))           # invalid bases
+    return k, m, "".join(pieces).encode()
+
+
+@settings(max_examples=400, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(kms=sequence_k_m())
+def test_superkmer_records_hold_exactly_the_valid_kmers(L, kms):
+    """host copy of K2 + K4 (split at minimizer changes / invalid windows / record capacity, pack MSB first, expand by
+    rolling): the canonical k-mers that come back are the oracle's valid k-mers, in order, whatever k, m and the content"""
+    import ctypes as C
+    k, m, seq = kms
+    if len(seq) < k:
+        return
+    codes = encode(seq)
+    words = 1 if k < 32 else 2
+    cap = len(seq)
+    out = np.zeros(cap * words, np.uint64)
+    nrec = C.c_uint64()
+    n = L.dskgpu_selftest_superkmers(codes.ctypes.data, codes.size, k, m, out.ctypes.data, cap, C.byref(nrec))
+    lo, hi, valid, _, _ = oracle.kmers_of(seq, k)
+    assert n == int(valid.sum())
+    got = out[: n * words].reshape(n, words)
+    assert (got[:, 0] == lo[valid]).all()
+    if words == 2:
+        assert (got[:, 1] == hi[valid]).all()
+    assert (nrec.value > 0) == (n > 0) and nrec.value <= max(n, 0)
