@@ -54,7 +54,7 @@ SYMBOLS = [
     "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_bin_hist", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
     "dskgpu_xchg_open_peer", "dskgpu_xchg_set_peers", "dskgpu_xchg_scatter", "dskgpu_xchg_sync", "dskgpu_xchg_layout", "dskgpu_record_bytes",
     "dskgpu_xchg2_hist", "dskgpu_xchg2_plan", "dskgpu_xchg2_ensure_recv", "dskgpu_xchg2_scatter",
-    "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers", "dskgpu_suggest_minimizer_size", "dskgpu_selftest_wide_kmers", "dskgpu_selftest_plan",
+    "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers", "dskgpu_suggest_minimizer_size", "dskgpu_selftest_wide_kmers", "dskgpu_selftest_plan", "dskgpu_selftest_wide_superkmers",
 ]
 
 _LIB = None
@@ -124,5 +124,7 @@ def lib():
     L.dskgpu_selftest_plan.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_double, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.dskgpu_selftest_plan.restype = C.c_int64
+    L.dskgpu_selftest_wide_superkmers.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, P(C.c_uint64)]
+    L.dskgpu_selftest_wide_superkmers.restype = C.c_int64
     _LIB = L
     return L

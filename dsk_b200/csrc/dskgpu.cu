@@ -1647,6 +1647,47 @@ int64_t dskgpu_selftest_superkmers(const uint8_t* codes, size_t n, int k, int m,
     return (int64_t)w;
 }
 
+// the same round trip with the N-word logic of kmer_wide.cuh (k <= 127: records of 2*KW words, KW = 1..4): split at
+// minimizer changes / invalid windows / record capacity, pack MSB first with the [nk:8][bank:8] field in the last word,
+// expand by extraction of the first k-mer + rolling.  out_kmers: 4 words per k-mer.
+int64_t dskgpu_selftest_wide_superkmers(const uint8_t* codes, size_t n, int k, int m, uint64_t* out_kmers, size_t cap, uint64_t* n_records)
+{
+    if (k < 2 || k > 127) return DSKGPU_ERR_ARG;
+    if (n < (size_t)k) { if (n_records) *n_records = 0; return 0; }
+    const size_t npos = n - k + 1;
+    std::vector<u32> mn(npos); std::vector<u8> valid(npos);
+    dskgpu_selftest_minimizers(codes, n, k, m, mn.data(), valid.data());
+    auto run = [&](auto tag) -> int64_t {
+        constexpr int KW = decltype(tag)::value, RW = 2 * KW;
+        const int maxS = rec_max_kmers(KW, k);
+        size_t w = 0; u64 nrec = 0, p = 0;
+        while (p < npos) {
+            if (!valid[p]) { p++; continue; }
+            size_t q = p; while (q < npos && valid[q] && mn[q] == mn[p] && (q - p) < (size_t)maxS) q++;
+            const int nk = (int)(q - p);
+            u64 r[RW];
+            for (int i = 0; i < RW; i++) r[i] = 0;
+            for (int i = 0; i < k - 1 + nk; i++) r[i >> 5] |= (u64)(codes[p + i] & 3) << (62 - 2 * (i & 31));
+            if ((k - 1 + nk) > rec_capacity_bases(KW)) return -2;                     // would overwrite the nk/bank field
+            r[RW - 1] = (r[RW - 1] & ~0xFFFFULL) | ((u64)nk << 8);
+            Kmer<KW> f = recn_kmer_at<KW, RW>(r, 0, k), rc = kmern_revcomp<KW>(f, k);
+            for (int j = 0; j < nk; j++) {
+                if (j) kmern_roll<KW>(f, rc, rec_base<RW>(r, k - 1 + j), k);
+                const Kmer<KW> c = kmern_canonical<KW>(f, rc);
+                if (w < cap) for (int x = 0; x < 4; x++) out_kmers[4 * w + x] = x < KW ? c.w[x] : 0;
+                w++;
+            }
+            nrec++; p = q;
+        }
+        if (n_records) *n_records = nrec;
+        return (int64_t)w;
+    };
+    if (k < 32) return run(std::integral_constant<int, 1>());
+    if (k < 64) return run(std::integral_constant<int, 2>());
+    if (k < 96) return run(std::integral_constant<int, 3>());
+    return run(std::integral_constant<int, 4>());
+}
+
 // host-only run of the partition planner (plan_partitions_host): what every rank derives from the all-reduced bin
 // histogram.  global_hist / local_hist: [2 << level] (records per bin, then k-mers per bin).  Outputs: bin2part[1 << level],
 // and per partition (capacity max_parts) the whole-job k-mers and this rank's records.  Returns the number of partitions

@@ -260,6 +260,9 @@ int64_t dskgpu_selftest_plan(int level, const uint64_t* global_hist, const uint6
  * k-mers of a code stream as 4 words each, computed by rolling and by extraction from a packed record (must agree) */
 int64_t dskgpu_selftest_wide_kmers(const uint8_t* codes, size_t n, int k, uint64_t* out_words /*[n-k+1][4]*/, uint8_t* out_valid);
 
+/* super-k-mer record round trip with the N-word logic (k <= 127, records of 2, 4, 6 or 8 words); 4 words per k-mer out */
+int64_t dskgpu_selftest_wide_superkmers(const uint8_t* codes, size_t n, int k, int m, uint64_t* out_kmers /*[cap][4]*/, size_t cap, uint64_t* n_records);
+
 #ifdef __cplusplus
 }
 #endif

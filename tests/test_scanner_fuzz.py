@@ -149,3 +149,33 @@ def test_superkmer_records_hold_exactly_the_valid_kmers(L, kms):
     if words == 2:
         assert (got[:, 1] == hi[valid]).all()
     assert (nrec.value > 0) == (n > 0) and nrec.value <= max(n, 0)
+
+
+@st.composite
+def wide_sequence_k_m(draw):
+    k = draw(st.integers(3, 127))
+    m = draw(st.integers(2, min(14, k - 1)))
+    pieces = draw(st.lists(st.one_of(
+        st.text(alphabet="ACGT", min_size=1, max_size=200),
+        st.sampled_from(["A", "G", "T", "AC", "GGT"]).flatmap(lambda u: st.integers(5, 300).map(lambda r: u * r)),
+        st.sampled_from(["N", "n", "NN"])), min_size=1, max_size=10))
+    return k, m, "".join(pieces).encode()
+
+
+@settings(max_examples=400, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(kms=wide_sequence_k_m())
+def test_wide_superkmer_records_hold_exactly_the_valid_kmers(L, kms):
+    """the same round trip through the N-word logic (kmer_wide.cuh: records of 2/4/6/8 words, k up to 127) -- groundwork for
+    the spans 96 and 128; the checker is the oracle (wide build for k >= 64, pinned against the 4-span reference)"""
+    import ctypes as C
+    k, m, seq = kms
+    if len(seq) < k:
+        return
+    codes = encode(seq)
+    cap = len(seq)
+    out = np.zeros((cap, 4), np.uint64)
+    nrec = C.c_uint64()
+    n = L.dskgpu_selftest_wide_superkmers(codes.ctypes.data, codes.size, k, m, out.ctypes.data, cap, C.byref(nrec))
+    words, valid, _, _ = oracle.kmers_of_words(seq, k)
+    assert n == int(valid.sum())
+    assert (out[:n] == words[valid]).all()
