@@ -270,3 +270,30 @@ def test_partition_planner_forced_partition_count(L):
     gh = np.concatenate([rec, km])
     P, b2p, pk, pr = _plan(L, 16, gh, gh, 1, mode=2, forced=64)      # hash mode, -nb-partitions style override
     assert P == 64 and (pk == 1024 * 1000).all() and (np.diff(b2p.astype(np.int64)) >= 0).all() and int(pr.sum()) == int(rec.sum())
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    # the counting path is CUDA-only: without libdskgpu.so the binding raises, it never falls back to anything
+    monkeypatch.setattr(_lib, "SO", str(tmp_path / "libdskgpu.so"))
+    monkeypatch.setattr(_lib, "_LIB", None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_product_package_never_imports_the_oracle():
+    # the oracle is test infrastructure: nothing under dsk_b200/ (nor the C++ host, nor the C ABI) may reference it
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for sub in ("dsk_b200", "host", "include"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            if "_build" in dirpath or "__pycache__" in dirpath:
+                continue
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".sh")):
+                    continue
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r'(^\s*(import|from)\s+oracle\b)|(#include\s+[<"][^>"]*oracle)|(-loracle)|((dlopen|CDLL)\([^)]*oracle)', txt, re.M):
+                    offenders.append(os.path.join(sub, f))
+    assert offenders == []
