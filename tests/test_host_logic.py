@@ -297,3 +297,25 @@ def test_product_package_never_imports_the_oracle():
                 if re.search(r'(^\s*(import|from)\s+oracle\b)|(#include\s+[<"][^>"]*oracle)|(-loracle)|((dlopen|CDLL)\([^)]*oracle)', txt, re.M):
                     offenders.append(os.path.join(sub, f))
     assert offenders == []
+
+
+@pytest.mark.parametrize("world,level,slots,density", [(1, 16, 15360, 0.26), (2, 17, 15360, 0.3), (8, 18, 11264, 0.45), (3, 16, 256, 0.3)])
+def test_parallel_planner_prototype_equals_the_host_planner(L, world, level, slots, density):
+    # tools/plan_parallel_proto.py: prefix sums + one binary search per bin + pointer doubling give, bit for bit, the plan
+    # of the sequential greedy packing in dskgpu.cu (the device-side planner of round 2 is a transcription of the prototype)
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from plan_parallel_proto import plan_parallel
+    rng = np.random.default_rng(level + world)
+    nb = 1 << level
+    km = (rng.pareto(1.3, nb) * 3000).astype(np.uint64) + rng.integers(0, 2000, nb).astype(np.uint64)
+    km[rng.integers(0, nb, 6)] += np.uint64(2_500_000)
+    km[rng.integers(0, nb, 3000)] = 0                                    # runs of empty bins, also at partition starts
+    km[:5] = 0
+    rec = (km // np.uint64(11)) + (km > 0).astype(np.uint64)
+    gh = np.concatenate([rec, km]).astype(np.uint64)
+    P, b2p, pk, _ = _plan(L, level, gh, gh, world, slots=slots, density=density)
+    T = int(min(max(slots * 0.52 / density, 64.0), slots * 4.0))
+    lim = int(max(64.0, slots * 0.75 / density) * 2)                      # fit x 2^max_split0 (default 1)
+    b2, pk2 = plan_parallel(km, T, lim, world)
+    assert pk2.size == P and (pk2 == pk).all() and (b2 == b2p).all()
