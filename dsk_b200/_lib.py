@@ -23,7 +23,8 @@ class Config(C.Structure):
         ("solid_vec", C.c_uint8 * MAX_BANKS),
         ("histo2d", C.c_int32), ("device", C.c_int32), ("count_mode", C.c_int32), ("hash_log2_slots", C.c_int32),
         ("nb_partitions", C.c_int32), ("keep_results_on_device", C.c_int32),
-        ("stream", C.c_void_p), ("rank", C.c_int32), ("world_size", C.c_int32), ("push_chunk_bytes", C.c_int32), ("smem_table_slots", C.c_int32), ("bank_histograms", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("stream", C.c_void_p), ("rank", C.c_int32), ("world_size", C.c_int32), ("push_chunk_bytes", C.c_int32), ("smem_table_slots", C.c_int32), ("bank_histograms", C.c_int32),
+        ("nb_passes", C.c_int32), ("pass_id", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -36,8 +37,8 @@ class Stats(C.Structure):
         ("ms_parse", C.c_float), ("ms_superk", C.c_float), ("ms_partition", C.c_float), ("ms_count", C.c_float),
         ("ms_sort", C.c_float), ("ms_total", C.c_float), ("ms_dominant_kernel", C.c_float),
         ("dominant_kernel_launches", C.c_uint32), ("nb_parts_smem", C.c_uint32), ("nb_smem_splits", C.c_uint32),
-        ("smem_table_slots", C.c_uint32), ("density_ppm", C.c_uint32), ("log2_bins", C.c_uint32), ("nb_groups_bucket", C.c_uint32), ("reserved", C.c_uint32 * 1),
-        ("exchange_bytes_out", C.c_uint64), ("ms_exchange", C.c_float), ("reserved2", C.c_uint32),
+        ("smem_table_slots", C.c_uint32), ("density_ppm", C.c_uint32), ("log2_bins", C.c_uint32), ("nb_groups_bucket", C.c_uint32), ("nb_hash_regroups", C.c_uint32),
+        ("exchange_bytes_out", C.c_uint64), ("ms_exchange", C.c_float), ("nb_solid_regrows", C.c_uint32), ("kmers_in_pass", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -53,6 +54,7 @@ SYMBOLS = [
     "dskgpu_last_error", "dskgpu_device_count", "dskgpu_abi_version",
     "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_bin_hist", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
     "dskgpu_xchg_open_peer", "dskgpu_xchg_set_peers", "dskgpu_xchg_scatter", "dskgpu_xchg_sync", "dskgpu_xchg_layout", "dskgpu_record_bytes",
+    "dskgpu_set_pass", "dskgpu_push_sync", "dskgpu_suggest_nb_passes", "dskgpu_xchg_close_peer", "dskgpu_multi_finish",
     "dskgpu_xchg2_hist", "dskgpu_xchg2_plan", "dskgpu_xchg2_ensure_recv", "dskgpu_xchg2_scatter",
     "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers", "dskgpu_suggest_minimizer_size", "dskgpu_selftest_wide_kmers", "dskgpu_selftest_plan", "dskgpu_selftest_wide_superkmers",
 ]
@@ -77,6 +79,11 @@ def lib():
     L.dskgpu_push_device_bytes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
     L.dskgpu_push_reads.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
     L.dskgpu_finish.argtypes = [C.c_void_p]
+    L.dskgpu_set_pass.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.dskgpu_push_sync.argtypes = [C.c_void_p]
+    L.dskgpu_suggest_nb_passes.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int]
+    L.dskgpu_xchg_close_peer.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_multi_finish.argtypes = [C.c_void_p, C.c_int]
     L.dskgpu_num_partitions.argtypes = [C.c_void_p]
     L.dskgpu_partition.argtypes = [C.c_void_p, C.c_int, P(C.c_void_p), P(C.c_void_p), P(C.c_uint64), P(C.c_int)]
     L.dskgpu_partition_device.argtypes = [C.c_void_p, C.c_int, P(C.c_void_p), P(C.c_void_p), P(C.c_uint64), P(C.c_int)]

@@ -22,7 +22,7 @@ class GpuCounter:
     def __init__(self, kmer_size=31, abundance_min=2, abundance_max=2**31 - 1, nb_banks=1, per_bank_counts=False,
                  solidity_kind="sum", solid_vec=None, histo2d=False, minimizer_size=10, device=0, count_mode="auto",
                  hash_log2_slots=0, nb_partitions=0, keep_results_on_device=False, stream=None, rank=0, world_size=1, push_chunk_bytes=0,
-                 smem_table_slots=0, bank_histograms=False):
+                 smem_table_slots=0, bank_histograms=False, nb_passes=1, pass_id=0):
         self.L = _lib.lib()
         cfg = _lib.Config()
         self.L.dskgpu_config_default(C.byref(cfg))
@@ -51,6 +51,7 @@ class GpuCounter:
         cfg.push_chunk_bytes = push_chunk_bytes
         cfg.smem_table_slots = smem_table_slots
         cfg.bank_histograms = int(bank_histograms)
+        cfg.nb_passes, cfg.pass_id = nb_passes, pass_id
         self.cfg = cfg
         self.k = kmer_size
         self.h = C.c_void_p()
@@ -93,6 +94,14 @@ class GpuCounter:
 
     def reset(self):
         self._check(self.L.dskgpu_reset(self.h))
+
+    def set_pass(self, pass_id, nb_passes):
+        """the next pushes keep the super-k-mers of pass `pass_id` of `nb_passes` (call on a fresh / reset context)"""
+        self._check(self.L.dskgpu_set_pass(self.h, pass_id, nb_passes))
+
+    def push_sync(self):
+        """every host buffer handed to push_bytes has been copied to the device"""
+        self._check(self.L.dskgpu_push_sync(self.h))
 
     def recount(self, abundance_min):
         """second pass of -abundance-min auto: same partitions (still in HBM), new thresholds"""
@@ -155,6 +164,16 @@ class GpuCounter:
 
     def __exit__(self, *a):
         self.close()
+
+
+def multi_finish(engines):
+    """dskgpu_multi_finish: exchange + counting for several contexts (ranks 0..n-1) living in this process"""
+    L = _lib.lib()
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    rc = L.dskgpu_multi_finish(arr, len(engines))
+    if rc != 0:
+        msgs = [(L.dskgpu_last_error(e.h) or b"").decode() for e in engines]
+        raise DskGpuError(rc, "; ".join(m for m in msgs if m) or L.dskgpu_strerror(rc).decode())
 
 
 # ---- multi-GPU exchange (include/dskgpu.h "multi-GPU exchange") ----------------------------------------------

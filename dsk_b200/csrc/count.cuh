@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
     if (threadIdx.x == 0) s_distinct = 0;
     __syncthreads();
     const u64 EMPTY = ~0ULL;
-    u32 ndist = 0;
+    u32 ndist = 0, nsamp_solid = 0;
     unsigned long long sumsq = 0;
     const u32 ngroups = nslots / SV;                               // nslots is a power of two >= 1024
     const u32 nthreads = blockDim.x * gridDim.x;
@@ -350,7 +350,10 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
                 const u64 slot = (u64)g * SV + q;
                 for (int b = 0; b < sp.nbanks; b++) { cv[b] = counts[slot * sp.nbanks + b]; counts[slot * sp.nbanks + b] = 0; }
             }
-            if (discard == 2) { ndist++; sumsq += (unsigned long long)cv[0] * cv[0]; }   // density sample: occupied slots + multiplicities
+            if (discard == 2) {                                    // density sample: occupied slots, multiplicities, share reaching the threshold
+                ndist++; sumsq += (unsigned long long)cv[0] * cv[0];
+                if ((long long)cv[0] >= sp.amin[0] && (long long)cv[0] <= sp.amax) nsamp_solid++;
+            }
             if (!discard) {
                 ndist++;
                 int32_t sum = 0;
@@ -368,6 +371,8 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
     if (discard == 2) {
         for (int d = 16; d; d >>= 1) sumsq += __shfl_xor_sync(0xFFFFFFFFu, sumsq, d);
         if ((threadIdx.x & 31) == 0 && sumsq) atomicAdd(&ctr->sample_sumsq, sumsq);
+        nsamp_solid = __reduce_add_sync(0xFFFFFFFFu, nsamp_solid);
+        if ((threadIdx.x & 31) == 0 && nsamp_solid) atomicAdd(&ctr->sample_solid, (unsigned long long)nsamp_solid);
     }
 }
 

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,7 @@ struct DevBuf {
 struct dskgpu_ctx {
     dskgpu_config cfg;
     int k = 0, m = 0, KW = 1, RW = 2, NB = 1;         // NB = counts kept per k-mer
+    int nb_passes = 1, pass_id = 0;                  // this context keeps the super-k-mers whose minimizer bin % nb_passes == pass_id
     cudaStream_t stream = nullptr; bool own_stream = false;
     cudaStream_t copy_stream = nullptr;
     int state = 0;                                   // 0 accepting pushes, 1 finished
@@ -61,7 +63,7 @@ struct dskgpu_ctx {
     u64 rec_cap = 0; u64 nrec_known = 0; int chunk_parity = 0; bool k2_inflight = false;
     size_t push_chunk = (size_t)64 << 20;
     // results
-    u64 n_solid = 0; int solid_buf = 0; bool results_on_host = false;
+    u64 n_solid = 0; int solid_buf = 0; bool results_on_host = false; u64 solid_cap = 0;
     std::vector<u64> h_part_recs, h_part_kmers;      // this rank's records / k-mers of every partition
     std::vector<u64> g_part_kmers;                   // whole-job k-mers of every partition
     std::vector<u32> h_bin2part;
@@ -72,7 +74,9 @@ struct dskgpu_ctx {
     std::vector<u64> xchg_matrix; std::vector<void*> peer_recv; bool xchg_planned = false; bool xchg_scattered = false;
     u64 my_nrec_owned = 0; std::vector<u64> owned_recs, owned_kmers;   // my partitions in my receive buffer (increasing id)
     std::vector<void*> ipc_opened;
-    bool totals_done = false; u64 local_nrec = 0, local_nkm = 0;
+    bool totals_done = false; u64 local_nrec = 0, local_nkm = 0;     // records / k-mers this context holds (this pass)
+    u64 bank_nkm = 0;                                // valid k-mers of everything pushed (all passes)
+    u64 sample_solid = 0;
     u64 bytes_pushed = 0;                            // raw input bytes so far (sizes the density sample before the totals are known)
     bool sample_queued = false; u64 sample_nkm = 0, sample_distinct = 0; double sample_wmult = 0.0;   // wmult: occurrence-weighted multiplicity (this rank's sample)
     bool global_set = false; u64 g_total_kmers = 0; double density = 1.0; bool density_known = false;
@@ -97,6 +101,9 @@ struct dskgpu_ctx {
     if (ctx) ctx->err = b_; g_last_error = b_; return DSKGPU_ERR_CUDA; } } while (0)
 #define FAIL(code, ...) do { char b_[512]; snprintf(b_, sizeof b_, __VA_ARGS__); if (ctx) ctx->err = b_; g_last_error = b_; return (code); } while (0)
 #define LAUNCHED() do { ctx->st.gpu_launches++; } while (0)
+// every ABI entry point runs on the context's device, whatever the caller's current device is (several contexts, one per
+// GPU, can live in one process: host/GpuSortingCount.hpp with DSKGPU_DEVICES, dskgpu_multi_finish)
+static inline void use_device(const dskgpu_ctx* ctx) { int d = -1; if (cudaGetDevice(&d) != cudaSuccess || d != ctx->cfg.device) cudaSetDevice(ctx->cfg.device); }
 
 // DSKGPU_TRACE=1: host wall-clock of the stages of push / finish on stderr (tuning aid)
 #include <chrono>
@@ -192,6 +199,9 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     ctx->RW = 2 * ctx->KW;
     ctx->NB = (cfg->per_bank_counts && cfg->nb_banks > 1) ? cfg->nb_banks : 1;
     if (cfg->push_chunk_bytes > 0) ctx->push_chunk = (size_t)std::max(cfg->push_chunk_bytes, 64);
+    ctx->nb_passes = cfg->nb_passes > 1 ? cfg->nb_passes : 1;
+    ctx->pass_id = cfg->nb_passes > 1 ? cfg->pass_id : 0;
+    if (ctx->pass_id < 0 || ctx->pass_id >= ctx->nb_passes) { delete ctx; ctx = nullptr; FAIL(DSKGPU_ERR_ARG, "pass_id %d outside [0, nb_passes = %d)", cfg->pass_id, cfg->nb_passes); }
     memset(&ctx->st, 0, sizeof ctx->st);
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) { delete ctx; ctx = nullptr; FAIL(DSKGPU_ERR_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(e)); }
@@ -278,6 +288,7 @@ int dskgpu_suggest_minimizer_size(uint64_t expected_kmers, int kmer_size)
 int dskgpu_reset(dskgpu_ctx* ctx)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemsetAsync(ctx->ss.p, 0, sizeof(StreamState), ctx->stream));
     CK(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
@@ -387,8 +398,8 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
         SpanGuard g(ctx, SPAN_SUPERK);
         const unsigned gk = (unsigned)((n + 64 + SK_TP - 1) / SK_TP);
         const int bank = ctx->NB > 1 ? ctx->cur_bank : 0;
-        if (ctx->KW == 1) k_superkmers<1><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p);
-        else              k_superkmers<2><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p);
+        if (ctx->KW == 1) k_superkmers<1><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p, (u32)ctx->nb_passes, (u32)ctx->pass_id);
+        else              k_superkmers<2><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p, (u32)ctx->nb_passes, (u32)ctx->pass_id);
         LAUNCHED();
         k_scan_carry<<<1, 64, 0, ctx->stream>>>((u8*)ctx->codes.p, ss, ctx->k); LAUNCHED();
     }
@@ -414,6 +425,7 @@ extern "C" {
 int dskgpu_push_bytes(dskgpu_ctx* ctx, int bank_id, const char* bytes, size_t n, int format, int flags)
 {
     if (!ctx || (!bytes && n)) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->state != 0) FAIL(DSKGPU_ERR_STATE, "push after finish");
     const bool last = flags & DSKGPU_PUSH_LAST;
     size_t skip = 0;
@@ -465,6 +477,7 @@ int dskgpu_push_bytes(dskgpu_ctx* ctx, int bank_id, const char* bytes, size_t n,
 int dskgpu_push_device_bytes(dskgpu_ctx* ctx, int bank_id, const void* dev_bytes, size_t n, int format, int flags)
 {
     if (!ctx || (!dev_bytes && n)) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->state != 0) FAIL(DSKGPU_ERR_STATE, "push after finish");
     const bool last = flags & DSKGPU_PUSH_LAST;
     const u8* p = (const u8*)dev_bytes;
@@ -507,6 +520,7 @@ int dskgpu_push_device_bytes(dskgpu_ctx* ctx, int bank_id, const void* dev_bytes
 int dskgpu_push_reads(dskgpu_ctx* ctx, int bank_id, const char* bases, const uint64_t* offsets, size_t nreads)
 {
     if (!ctx || !bases || !offsets) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     // one sequence per line: the separator is inserted on the host while staging
     size_t total = (size_t)(offsets[nreads] - offsets[0]) + nreads;
     char* tmp = (char*)dskgpu_host_alloc(total ? total : 1);
@@ -619,10 +633,18 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
     const double load_max = 0.6;
     const u64 sort_cap = (u64)1 << 28;                             // keys per sort-path group
 
-    auto run_hash = [&](size_t pb, size_t pe, u64 kmers, u64 slots, int gi) -> int {
+    auto init_table = [&](u64 slots) -> int {
         int rc2;
         if ((rc2 = ensure(ctx, ctx->tkeys, slots * KW * 8))) return rc2;
         if ((rc2 = ensure(ctx, ctx->tcounts, slots * 4 * (u64)ctx->NB))) return rc2;
+        k_fill_u64<<<148 * 4, 256, 0, ctx->stream>>>((u64*)ctx->tkeys.p, slots * KW, ~0ULL); LAUNCHED();
+        CK(cudaMemsetAsync(ctx->tcounts.p, 0, slots * 4 * (u64)ctx->NB, ctx->stream));
+        return 0;
+    };
+    // one group of consecutive partitions [pb, pe) through the table.  `checked`: the group was sized from an ESTIMATE of
+    // distinct / total, so the insert is followed by a look at the overflow flag before the sweep; *overflowed tells the
+    // caller to redo the group at the worst-case ratio (the table has been cleared again)
+    auto run_hash = [&](size_t pb, size_t pe, u64 slots, bool checked, bool* overflowed) -> int {
         const u64 rb = off[pb], re = off[pe];
         const unsigned gi_blocks = (unsigned)std::min<u64>((re - rb + 255) / 256, 148 * 8);
         cudaEvent_t a = get_event(ctx), b = get_event(ctx);
@@ -631,6 +653,17 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
                                                                               (u32)(slots - 1), ctx->NB, ctr); LAUNCHED();
         cudaEventRecord(b, ctx->stream);
         ctx->spans.push_back({a, b, SPAN_DOM});
+        if (overflowed) *overflowed = false;
+        if (checked) {
+            CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->h_ctr->hash_overflow) {
+                CK(cudaMemsetAsync(&ctr->hash_overflow, 0, sizeof(unsigned int), ctx->stream));
+                int rc2 = init_table(slots); if (rc2) return rc2;
+                *overflowed = true;
+                return 0;
+            }
+        }
         const unsigned gs = (unsigned)std::min<u64>((slots / 8 + 255) / 256, 148 * 8);
         if (ctx->NB == 1)
             k_hash_scan<KW, true><<<gs, 256, 0, ctx->stream>>>((u64*)ctx->tkeys.p, (u32*)ctx->tcounts.p, (u32)slots, sp, 0, (u64*)ctx->skeys[0].p,
@@ -642,15 +675,6 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
                                                                 (unsigned long long*)ctx->hist2d.p, ctr);
         LAUNCHED();
         ctx->st.nb_groups_hash++;
-        (void)gi; (void)kmers;
-        return 0;
-    };
-    auto init_table = [&](u64 slots) -> int {
-        int rc2;
-        if ((rc2 = ensure(ctx, ctx->tkeys, slots * KW * 8))) return rc2;
-        if ((rc2 = ensure(ctx, ctx->tcounts, slots * 4 * (u64)ctx->NB))) return rc2;
-        k_fill_u64<<<148 * 4, 256, 0, ctx->stream>>>((u64*)ctx->tkeys.p, slots * KW, ~0ULL); LAUNCHED();
-        CK(cudaMemsetAsync(ctx->tcounts.p, 0, slots * 4 * (u64)ctx->NB, ctx->stream));
         return 0;
     };
 
@@ -665,8 +689,10 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
         return 0;
     }
     // hash (forced) or auto.  The table is sized once; groups of consecutive partitions are sized so that the
-    // estimated number of distinct k-mers stays under load_max * nslots.  The distinct/total ratio r is measured
-    // on the first group (sized for the worst case r = 1).
+    // estimated number of distinct k-mers stays under load_max * nslots.  The distinct/total ratio r comes from the
+    // density sample (or is measured on a first group sized for the worst case r = 1).  It is an estimate: a group whose
+    // k-mers are less repetitive than the job's average (hot low-complexity bins) can outgrow the table -- that group is
+    // then redone in sub-groups sized for r = 1, which cannot overflow (never an error, as in the reference).
     u64 max_part = 0; for (size_t i = 0; i < np; i++) max_part = std::max(max_part, pkm[i]);
     if (mode == DSKGPU_COUNT_HASH) { while ((double)nslots * load_max < (double)max_part && nslots < ((u64)1 << 31)) nslots <<= 1; }
     if (ctx->cfg.hash_log2_slots <= 0) {
@@ -676,31 +702,39 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
         while (nslots > ((u64)1 << 16) && (double)(nslots >> 1) * load_max >= (double)tot) nslots >>= 1;
     }
     if ((rc = init_table(nslots))) return rc;
-    // distinct / total: from the density sample when there is one, else measured on a first group sized for r = 1
     double r = 1.0; bool have_r = false;
     if (ctx->density_known) { r = std::min(1.0, std::max(0.02, ctx->density * 1.3 + 0.01)); have_r = true; }
-    size_t p = 0; int gi = 0;
-    while (p < np) {
-        const double capk = (double)nslots * load_max / r;
-        size_t q = p; u64 km = 0;
-        while (q < np && km + pkm[q] <= (u64)capk) { km += pkm[q]; q++; }
-        if (q == p) {
-            // a single partition exceeds the table: occupancy picks the sort path
-            if ((rc = count_by_sort<KW>(ctx, recs, off[p], off[p + 1], pkm[p], out_cap))) return rc;
-            p++; continue;
+    if (const char* e = getenv("DSKGPU_TEST_HASH_RATIO")) { r = std::min(1.0, std::max(0.001, atof(e))); have_r = true; }   // test hook: a wrong estimate
+    // partitions [pb, pe) in groups sized for the ratio rr; a single partition beyond the table goes to the sort path
+    std::function<int(size_t, size_t, double)> run_range = [&](size_t pb, size_t pe, double rr) -> int {
+        size_t p = pb;
+        while (p < pe) {
+            const double capk = (double)nslots * load_max / rr;
+            size_t q = p; u64 km = 0;
+            while (q < pe && km + pkm[q] <= (u64)capk) { km += pkm[q]; q++; }
+            if (q == p) {                                                  // occupancy picks the sort path
+                int rc2 = count_by_sort<KW>(ctx, recs, off[p], off[p + 1], pkm[p], out_cap); if (rc2) return rc2;
+                p++; continue;
+            }
+            if (km == 0) { p = q; continue; }
+            const bool calibrate = !have_r;
+            u64 d0 = 0;
+            if (calibrate) { CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); d0 = ctx->h_ctr->distinct_n; }
+            bool ovf = false;
+            int rc2 = run_hash(p, q, nslots, rr < 1.0, &ovf); if (rc2) return rc2;
+            if (ovf) { ctx->st.nb_hash_regroups++; rc2 = run_range(p, q, 1.0); if (rc2) return rc2; p = q; continue; }
+            if (calibrate) {
+                CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
+                if (ctx->h_ctr->hash_overflow) FAIL(DSKGPU_ERR_OVERFLOW, "hash table overflow in a group sized for distinct = total (internal)");
+                const double dr = (double)(ctx->h_ctr->distinct_n - d0) / (double)km;
+                r = std::min(1.0, std::max(0.02, dr * 1.3 + 0.01)); have_r = true;
+                rr = r;
+            }
+            p = q;
         }
-        if (km == 0) { p = q; continue; }
-        u64 d0 = 0;
-        if (!have_r) { CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); d0 = ctx->h_ctr->distinct_n; }
-        if ((rc = run_hash(p, q, km, nslots, gi++))) return rc;
-        if (!have_r) {
-            CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
-            if (ctx->h_ctr->hash_overflow) FAIL(DSKGPU_ERR_OVERFLOW, "hash table overflow in the calibration group");
-            double dr = (double)(ctx->h_ctr->distinct_n - d0) / (double)km;
-            r = std::min(1.0, std::max(0.02, dr * 1.3 + 0.01)); have_r = true;
-        }
-        p = q;
-    }
+        return 0;
+    };
+    if ((rc = run_range(0, np, r))) return rc;
     CK(cudaGetLastError());
     return 0;
 }
@@ -746,6 +780,11 @@ static int queue_sample(dskgpu_ctx* ctx)
     k_hash_insert<KW><<<ctx->num_sms * 2, 256, 0, ctx->stream>>>((const u64*)ctx->sample_recs.p, 0, SAMPLE_KM_CAP, ctx->k, (u64*)ctx->stab_keys.p,
                                                                   (u32*)ctx->stab_counts.p, SAMPLE_SLOTS - 1, 1, ctr, &ctr->sample_nrec); LAUNCHED();
     SolidityParams sp; memset(&sp, 0, sizeof sp); sp.nbanks = 1;
+    // share of the sampled distinct k-mers whose summed count reaches the smallest threshold: sizes the solid-set buffers
+    sp.amin[0] = ctx->cfg.abundance_min[0]; sp.amax = ctx->cfg.abundance_max;
+    for (int b = 1; b < ctx->cfg.nb_banks; b++) sp.amin[0] = std::min<long long>(sp.amin[0], ctx->cfg.abundance_min[b]);
+    if (ctx->cfg.solidity_kind == DSKGPU_SOLIDITY_CUSTOM) sp.amin[0] = 1;
+    if (ctx->NB > 1) sp.amax = 0x7FFFFFFFFFFFFFFFLL;                    // per-bank ranges: the summed count only bounds from below
     k_hash_scan<KW, true><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((u64*)ctx->stab_keys.p, (u32*)ctx->stab_counts.p, SAMPLE_SLOTS, sp, 2, nullptr, nullptr, 0,
                                                                       (unsigned long long*)ctx->hist.p, (unsigned long long*)ctx->hist2d.p, ctr); LAUNCHED();
     CK(cudaGetLastError());
@@ -783,13 +822,14 @@ static int stage_totals(dskgpu_ctx* ctx)
     ctx->k2_inflight = false;
     if (ctx->h_ss->err) FAIL(DSKGPU_ERR_FORMAT, "device record scanner rejected the input (flags 0x%x): not plain FASTA / 4-line FASTQ", ctx->h_ss->err);
     if (ctx->h_ctr->overflow) FAIL(DSKGPU_ERR_OVERFLOW, "super-k-mer record buffer overflow");
-    if (ctx->h_ctr->kmers_valid != ctx->h_ctr->kmers_in_recs)
-        FAIL(DSKGPU_ERR_OVERFLOW, "internal: %llu valid k-mers but %llu packed in records", ctx->h_ctr->kmers_valid, ctx->h_ctr->kmers_in_recs);
-    ctx->local_nrec = ctx->h_ctr->nrec; ctx->local_nkm = ctx->h_ctr->kmers_valid;
+    if (ctx->h_ctr->kmers_pass != ctx->h_ctr->kmers_in_recs)
+        FAIL(DSKGPU_ERR_OVERFLOW, "internal: %llu valid k-mers in this pass but %llu packed in records", ctx->h_ctr->kmers_pass, ctx->h_ctr->kmers_in_recs);
+    ctx->local_nrec = ctx->h_ctr->nrec; ctx->local_nkm = ctx->h_ctr->kmers_pass; ctx->bank_nkm = ctx->h_ctr->kmers_valid;
+    ctx->sample_solid = ctx->h_ctr->sample_solid;
     ctx->sample_nkm = ctx->h_ctr->sample_nkm; ctx->sample_distinct = ctx->h_ctr->sample_distinct;
     ctx->sample_wmult = ctx->sample_nkm >= 4096 ? (double)ctx->h_ctr->sample_sumsq / (double)ctx->sample_nkm : 0.0;
     ctx->st.nb_sequences = ctx->h_ss->nsep; ctx->st.nb_nucleotides = ctx->h_ss->nbase;
-    ctx->st.kmers_nb_valid = ctx->local_nkm; ctx->st.nb_superkmers = ctx->local_nrec;
+    ctx->st.kmers_nb_valid = ctx->bank_nkm; ctx->st.kmers_in_pass = ctx->local_nkm; ctx->st.nb_superkmers = ctx->local_nrec;
     ctx->st.superkmer_bytes = ctx->local_nrec * (u64)ctx->RW * 8;
     ctx->totals_done = true;
     return 0;
@@ -1024,9 +1064,10 @@ static bool heavy_by_buckets(const dskgpu_ctx* ctx)
 
 // ---- stage 4: count the partitions stored contiguously in `recs`, order the solid set, copy results out --------------
 template <int KW>
-static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm)
+static int stage_count_once(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm, u64 cap_request, u64* need_cap)
 {
     Counters* ctr = (Counters*)ctx->ctr.p;
+    *need_cap = 0;
     int rc;
     const size_t np = prec.size();
     u64 nrec = 0, nkm = 0;
@@ -1034,11 +1075,24 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
     ctx->st.smem_table_slots = ctx->smem_cap;
     ctx->st.density_ppm = ctx->density_known ? (u32)(ctx->density * 1e6) : 0u; ctx->st.log2_bins = (u32)ctx->bin_level;
     if (nrec) {
-        // capacity of the solid set: every solid k-mer holds at least min(abundance_min) occurrences
+        // Capacity of the solid set.  Worst case: every solid k-mer holds at least min(abundance_min) occurrences -- 108 GB of
+        // ping-pong buffers for a 9 G k-mer job whose solid set is 5 GB.  Big jobs therefore start from an ESTIMATE (share of
+        // the sampled distinct k-mers that reach the threshold, with margin); the kernels keep counting past the capacity, so
+        // an overflowing pass still reports the exact size and the counting stage is redone once at that size (stage_count).
         long long amin = ctx->cfg.abundance_min[0];
         for (int b = 1; b < ctx->NB; b++) amin = std::min<long long>(amin, ctx->cfg.abundance_min[b]);
         if (amin < 1 || ctx->cfg.solidity_kind == DSKGPU_SOLIDITY_CUSTOM) amin = 1;
-        const u64 out_cap = nkm / (u64)amin + 1024;
+        const u64 worst = nkm / (u64)amin + 1024;
+        u64 out_cap = worst;
+        if (cap_request) out_cap = std::min(worst, cap_request);
+        else if (worst * (u64)(KW * 8 + 4) * 2 > ((u64)256 << 20)) {
+            double share = 0.08;                                                   // of the k-mers counted here
+            if (ctx->cfg.world_size == 1 && ctx->sample_nkm >= 4096) share = 1.5 * (double)ctx->sample_solid / (double)ctx->sample_nkm + 0.01;
+            const u64 have = std::min<u64>(ctx->skeys[0].cap / (KW * 8), std::min<u64>(ctx->skeys[1].cap / (KW * 8), std::min<u64>(ctx->svals[0].cap / 4, ctx->svals[1].cap / 4)));
+            out_cap = std::min(worst, std::max(have, (u64)((double)nkm * share) + ((u64)1 << 20)));
+        }
+        if (const char* e = getenv("DSKGPU_TEST_SOLID_CAP")) { if (!cap_request) out_cap = std::min(worst, (u64)std::max(1LL, atoll(e))); }   // test hook: a wrong estimate
+        ctx->solid_cap = out_cap;
         for (int i = 0; i < 2; i++) {
             if ((rc = ensure(ctx, ctx->skeys[i], out_cap * KW * 8))) return rc;
             if ((rc = ensure(ctx, ctx->svals[i], out_cap * 4))) return rc;
@@ -1114,7 +1168,11 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
     trace("count done (sync)");
     if (ctx->h_ctr->hash_overflow) FAIL(DSKGPU_ERR_OVERFLOW, "hash table overflow (distinct k-mer estimate too low)");
     if (ctx->h_ctr->smem_failed) FAIL(DSKGPU_ERR_OVERFLOW, "shared-memory table overflow at the deepest split (%u passes)", ctx->h_ctr->smem_failed);
-    if (ctx->h_ctr->overflow) FAIL(DSKGPU_ERR_OVERFLOW, "solid k-mer buffer overflow");
+    if (ctx->h_ctr->overflow) {                                    // the cursor kept counting: solid_n is the exact size needed
+        if (ctx->h_ctr->solid_n <= ctx->solid_cap) FAIL(DSKGPU_ERR_OVERFLOW, "solid k-mer buffer overflow (internal)");
+        *need_cap = ctx->h_ctr->solid_n + 1024;
+        return DSKGPU_OK;
+    }
     ctx->n_solid = ctx->h_ctr->solid_n;
     ctx->st.kmers_nb_distinct = ctx->h_ctr->distinct_n; ctx->st.kmers_nb_solid = ctx->n_solid;
     ctx->st.nb_smem_splits = ctx->h_ctr->smem_splits;
@@ -1151,6 +1209,42 @@ static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>&
     ctx->st.ms_exchange = span_ms(ctx, SPAN_XCHG); ctx->st.exchange_bytes_out = ctx->xchg_bytes_out;
     ctx->st.ms_total = ctx->st.ms_parse + ctx->st.ms_superk + ctx->st.ms_partition + ctx->st.ms_count + ctx->st.ms_sort;
     ctx->state = 1;
+    return DSKGPU_OK;
+}
+
+// clears what a counting pass accumulates (solid cursor, distinct counter, histograms, split/overflow flags, the spans of
+// the counting stage) so that the stage can run again from the partitioned records still in HBM
+static int reset_count_state(dskgpu_ctx* ctx)
+{
+    Counters* ctr = (Counters*)ctx->ctr.p;
+    CK(cudaMemsetAsync(&ctr->solid_n, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(&ctr->distinct_n, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(&ctr->smem_splits, 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(&ctr->overflow, 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
+    if (ctx->bank_hist.p) CK(cudaMemsetAsync(ctx->bank_hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * (size_t)ctx->NB, ctx->stream));
+    ctx->n_solid = 0; ctx->results_on_host = false;
+    ctx->st.nb_groups_hash = ctx->st.nb_groups_sort = 0; ctx->st.nb_groups_bucket = 0; ctx->st.nb_hash_regroups = 0;
+    // timing spans of the counting stage belong to the pass that produced the results
+    std::vector<dskgpu_ctx::Span> keep;
+    for (auto& sp : ctx->spans) if (sp.kind != SPAN_COUNT && sp.kind != SPAN_SORT && sp.kind != SPAN_DOM && sp.kind != SPAN_SORTPASS) keep.push_back(sp);
+    ctx->spans.swap(keep);
+    return 0;
+}
+
+template <int KW>
+static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm, u64 cap_request = 0)
+{
+    u64 need = 0;
+    int rc = stage_count_once<KW>(ctx, recs, prec, pkm, cap_request, &need);
+    if (rc || !need) return rc;
+    // the estimate was too small: once more at the exact size (the records are still in HBM)
+    if ((rc = reset_count_state(ctx))) return rc;
+    ctx->st.nb_solid_regrows++;
+    rc = stage_count_once<KW>(ctx, recs, prec, pkm, need, &need);
+    if (rc) return rc;
+    if (need) FAIL(DSKGPU_ERR_OVERFLOW, "solid k-mer buffer overflow after the exact-size pass (internal)");
     return DSKGPU_OK;
 }
 
@@ -1210,6 +1304,7 @@ extern "C" {
 int dskgpu_finish(dskgpu_ctx* ctx)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->state != 0) FAIL(DSKGPU_ERR_STATE, "finish called twice");
     if (ctx->cfg.world_size > 1) return ctx->KW == 1 ? finish_owned<1>(ctx) : finish_owned<2>(ctx);
     return ctx->KW == 1 ? finish_single<1>(ctx) : finish_single<2>(ctx);
@@ -1219,6 +1314,7 @@ int dskgpu_finish(dskgpu_ctx* ctx)
 int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     int rc = stage_totals(ctx); if (rc) return rc;
     if (kmers) *kmers = ctx->local_nkm; if (records) *records = ctx->local_nrec;
     return DSKGPU_OK;
@@ -1227,6 +1323,7 @@ int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records
 int dskgpu_xchg_prepare(dskgpu_ctx* ctx, uint64_t* local4)
 {
     if (!ctx || !local4) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     int rc = stage_totals(ctx); if (rc) return rc;
     local4[0] = ctx->local_nkm; local4[1] = ctx->local_nrec; local4[2] = ctx->sample_nkm; local4[3] = ctx->sample_distinct;
     return DSKGPU_OK;
@@ -1235,6 +1332,7 @@ int dskgpu_xchg_prepare(dskgpu_ctx* ctx, uint64_t* local4)
 int dskgpu_xchg_set_global(dskgpu_ctx* ctx, const uint64_t* global4, int* log2_bins)
 {
     if (!ctx || !global4) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (!ctx->totals_done) FAIL(DSKGPU_ERR_STATE, "xchg_set_global before xchg_prepare");
     set_global(ctx, global4[0], global4[2], global4[3]);
     if (log2_bins) *log2_bins = ctx->bin_level;
@@ -1244,6 +1342,7 @@ int dskgpu_xchg_set_global(dskgpu_ctx* ctx, const uint64_t* global4, int* log2_b
 int dskgpu_xchg_bin_hist(dskgpu_ctx* ctx, uint64_t* hist)
 {
     if (!ctx || !hist) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     int rc = stage_totals(ctx); if (rc) return rc;
     if (!ctx->global_set) FAIL(DSKGPU_ERR_STATE, "xchg_bin_hist before xchg_set_global (the ranks must agree on the bin level)");
     if ((rc = fetch_local_bin_hist(ctx))) return rc;
@@ -1254,6 +1353,7 @@ int dskgpu_xchg_bin_hist(dskgpu_ctx* ctx, uint64_t* hist)
 int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, const uint64_t* global_hist, uint64_t* counts, uint32_t* nparts)
 {
     if (!ctx || !global_hist) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     int rc = stage_totals(ctx); if (rc) return rc;
     if ((rc = fetch_local_bin_hist(ctx))) return rc;
     if ((rc = plan_partitions(ctx, (const unsigned long long*)global_hist))) return rc;
@@ -1267,6 +1367,7 @@ int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, const uint64_t* global_hist, uint64
 int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts)
 {
     if (!ctx || !all_counts) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->nparts == 0) FAIL(DSKGPU_ERR_STATE, "xchg_plan before xchg_part_counts");
     const u32 W = (u32)ctx->cfg.world_size, P = ctx->nparts;
     ctx->xchg_matrix.assign(all_counts, all_counts + (size_t)W * 2 * P);
@@ -1281,6 +1382,7 @@ int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts)
 int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (!ctx->xchg_planned) FAIL(DSKGPU_ERR_STATE, "xchg_recv_buffer before xchg_plan");
     if (d_recv) *d_recv = ctx->precs.p; if (bytes) *bytes = (size_t)(ctx->my_nrec_owned * (u64)ctx->RW * 8);
     return DSKGPU_OK;
@@ -1289,6 +1391,7 @@ int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes)
 int dskgpu_xchg_ipc_handle(dskgpu_ctx* ctx, void* handle64)
 {
     if (!ctx || !handle64) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (!ctx->xchg_planned) FAIL(DSKGPU_ERR_STATE, "xchg_ipc_handle before xchg_plan");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t h;
@@ -1300,6 +1403,7 @@ int dskgpu_xchg_ipc_handle(dskgpu_ctx* ctx, void* handle64)
 int dskgpu_xchg_open_peer(dskgpu_ctx* ctx, const void* handle64, void** d_ptr)
 {
     if (!ctx || !handle64 || !d_ptr) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
     CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->ipc_opened.push_back(*d_ptr);
@@ -1309,6 +1413,7 @@ int dskgpu_xchg_open_peer(dskgpu_ctx* ctx, const void* handle64, void** d_ptr)
 int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv)
 {
     if (!ctx || !d_peer_recv) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     ctx->peer_recv.assign(d_peer_recv, d_peer_recv + ctx->cfg.world_size);
     ctx->peer_recv[ctx->cfg.rank] = ctx->precs.p;
     return DSKGPU_OK;
@@ -1319,6 +1424,7 @@ int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv)
 int dskgpu_xchg_scatter(dskgpu_ctx* ctx)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (!ctx->xchg_planned || ctx->peer_recv.size() != (size_t)ctx->cfg.world_size) FAIL(DSKGPU_ERR_STATE, "xchg_scatter before xchg_plan / xchg_set_peers");
     const u32 W = (u32)ctx->cfg.world_size, P = ctx->nparts, me = (u32)ctx->cfg.rank;
     std::vector<u64*> dst(P, nullptr);
@@ -1341,6 +1447,7 @@ int dskgpu_xchg_scatter(dskgpu_ctx* ctx)
 int dskgpu_xchg2_hist(dskgpu_ctx* ctx, void* d_out)
 {
     if (!ctx || !d_out) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     int rc = stage_totals(ctx); if (rc) return rc;
     if (!ctx->global_set) FAIL(DSKGPU_ERR_STATE, "xchg2_hist before xchg_set_global (the ranks must agree on the bin level)");
     if ((rc = fetch_local_bin_hist(ctx))) return rc;
@@ -1352,6 +1459,7 @@ int dskgpu_xchg2_hist(dskgpu_ctx* ctx, void* d_out)
 int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist, uint64_t* local_counts, uint64_t* need_records, uint32_t* nparts)
 {
     if (!ctx || !d_global_hist) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (!ctx->hist_fetched) FAIL(DSKGPU_ERR_STATE, "xchg2_plan before xchg2_hist");
     const u32 W = (u32)ctx->cfg.world_size, me = (u32)ctx->cfg.rank;
     if (ctx->nparts == 0) {
@@ -1381,6 +1489,7 @@ int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist, uint64_t* loca
 int dskgpu_xchg2_ensure_recv(dskgpu_ctx* ctx, uint64_t capacity_records)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->nparts == 0) FAIL(DSKGPU_ERR_STATE, "xchg2_ensure_recv before xchg2_plan");
     const u64 want = std::max<u64>(capacity_records, ctx->my_nrec_owned);
     int rc = ensure(ctx, ctx->precs, want * (u64)ctx->RW * 8 + 64); if (rc) return rc;
@@ -1391,6 +1500,7 @@ int dskgpu_xchg2_ensure_recv(dskgpu_ctx* ctx, uint64_t capacity_records)
 int dskgpu_xchg2_scatter(dskgpu_ctx* ctx, const void* d_matrix)
 {
     if (!ctx || !d_matrix) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (!ctx->xchg_planned || ctx->peer_recv.size() != (size_t)ctx->cfg.world_size) FAIL(DSKGPU_ERR_STATE, "xchg2_scatter before xchg2_ensure_recv / xchg_set_peers");
     const u32 W = (u32)ctx->cfg.world_size, P = ctx->nparts, me = (u32)ctx->cfg.rank;
     if (ctx->precs.cap < ctx->my_nrec_owned * (u64)ctx->RW * 8) FAIL(DSKGPU_ERR_STATE, "receive buffer smaller than the planned layout");
@@ -1421,10 +1531,124 @@ int dskgpu_xchg2_scatter(dskgpu_ctx* ctx, const void* d_matrix)
     return DSKGPU_OK;
 }
 
+int dskgpu_xchg_close_peer(dskgpu_ctx* ctx, void* d_ptr)
+{
+    if (!ctx || !d_ptr) return DSKGPU_ERR_ARG;
+    use_device(ctx);
+    for (size_t i = 0; i < ctx->ipc_opened.size(); i++)
+        if (ctx->ipc_opened[i] == d_ptr) {
+            CK(cudaStreamSynchronize(ctx->stream));                    // nothing of ours may still be storing through the mapping
+            CK(cudaIpcCloseMemHandle(d_ptr));
+            ctx->ipc_opened.erase(ctx->ipc_opened.begin() + (long)i);
+            return DSKGPU_OK;
+        }
+    FAIL(DSKGPU_ERR_ARG, "xchg_close_peer: pointer was not opened by this context");
+}
+
+int dskgpu_set_pass(dskgpu_ctx* ctx, int pass_id, int nb_passes)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    if (nb_passes < 1 || pass_id < 0 || pass_id >= nb_passes) FAIL(DSKGPU_ERR_ARG, "pass_id %d outside [0, nb_passes = %d)", pass_id, nb_passes);
+    if (ctx->state != 0 || ctx->bytes_pushed != 0) FAIL(DSKGPU_ERR_STATE, "set_pass on a context that holds data (reset it first)");
+    ctx->nb_passes = nb_passes; ctx->pass_id = pass_id;
+    return DSKGPU_OK;
+}
+
+int dskgpu_push_sync(dskgpu_ctx* ctx)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    return DSKGPU_OK;
+}
+
+// Sizing rule behind the pass count (the reference derives nb_passes from the estimated volume against -max-disk,
+// K/ConfigurationAlgorithm.cpp:245-467; here the bound is HBM).  Per k-mer of one pass on one GPU:
+//   records, input order + partition order (+ the receive buffer when the job is sharded) ... (2 | 3) x record bytes / s
+//   record meta (bin | nk) ............................................................... 4 / s
+//   solid-set ping-pong buffers at the default estimate (8 % of the k-mers + margin) ...... 2 x 0.10 x (8 KW + 4)
+// with s = k-mers per record (~ 9 at m = 12..14, the lengths multi-G k-mer jobs get), plus 2 GiB of fixed buffers.
+int dskgpu_suggest_nb_passes(uint64_t expected_kmers, int kmer_size, int world_size, uint64_t hbm_bytes, int device)
+{
+    if (world_size < 1) world_size = 1;
+    if (hbm_bytes == 0) {
+        size_t fr = 0, tot = 0;
+        int cur = -1; cudaGetDevice(&cur);
+        if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+        if (cur >= 0 && cur != device) cudaSetDevice(cur);
+        hbm_bytes = fr;
+    }
+    const int KW = kmer_size < 32 ? 1 : 2;
+    const double s = kmer_size < 32 ? 9.0 : 18.0;
+    const double per_kmer = ((world_size > 1 ? 3.0 : 2.0) * 16.0 * KW + 4.0) / s + 2.0 * 0.10 * (8.0 * KW + 4.0);
+    const double fixed = 2.0 * 1024 * 1024 * 1024;
+    const double budget = (double)hbm_bytes * 0.90 - fixed;
+    if (budget <= 0) return 1 << 10;
+    const double need = (double)expected_kmers / world_size * per_kmer;
+    int passes = (int)(need / budget) + 1;
+    return passes < 1 ? 1 : passes;
+}
+
 int dskgpu_xchg_sync(dskgpu_ctx* ctx)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
+    return DSKGPU_OK;
+}
+
+// ---- several contexts (ranks) in one process: the exchange protocol with host-side sums in place of the collectives ------
+}  // extern "C"
+#include <thread>
+extern "C" {
+
+int dskgpu_multi_finish(dskgpu_ctx* const* ctxs, int n)
+{
+    dskgpu_ctx* ctx = (ctxs && n > 0) ? ctxs[0] : nullptr;
+    if (!ctx) return DSKGPU_ERR_ARG;
+    for (int r = 0; r < n; r++) {
+        if (!ctxs[r]) return DSKGPU_ERR_ARG;
+        if (ctxs[r]->cfg.world_size != n || ctxs[r]->cfg.rank != r) FAIL(DSKGPU_ERR_ARG, "multi_finish: ctxs[%d] must have rank %d of world_size %d", r, r, n);
+        if (ctxs[r]->KW != ctx->KW || ctxs[r]->k != ctx->k || ctxs[r]->m != ctx->m) FAIL(DSKGPU_ERR_ARG, "multi_finish: contexts differ in k / minimizer size");
+    }
+    if (n == 1) return dskgpu_finish(ctx);
+    int rc;
+    // peer access between the distinct devices (both directions; contexts sharing a device need nothing)
+    for (int a = 0; a < n; a++) for (int b = 0; b < n; b++) {
+        const int da = ctxs[a]->cfg.device, db = ctxs[b]->cfg.device;
+        if (da == db) continue;
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, da, db));
+        if (!can) FAIL(DSKGPU_ERR_CUDA, "multi_finish: device %d cannot access device %d (no P2P path)", da, db);
+        CK(cudaSetDevice(da));
+        cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError(); else CK(e);
+    }
+    // 1. job totals (k-mers, records, density sample) -> the same bin level and partition size everywhere
+    uint64_t g4[4] = {0, 0, 0, 0};
+    for (int r = 0; r < n; r++) { uint64_t l4[4]; if ((rc = dskgpu_xchg_prepare(ctxs[r], l4))) return rc; for (int i = 0; i < 4; i++) g4[i] += l4[i]; }
+    int level = 0;
+    for (int r = 0; r < n; r++) { int lv = 0; if ((rc = dskgpu_xchg_set_global(ctxs[r], g4, &lv))) return rc; if (r && lv != level) FAIL(DSKGPU_ERR_STATE, "multi_finish: ranks disagree on the bin level"); level = lv; }
+    // 2. whole-job bin histogram (host sum of the ranks' pinned copies)
+    const size_t nh = (size_t)2 << level;
+    std::vector<uint64_t> gh(nh, 0), lh(nh);
+    for (int r = 0; r < n; r++) { if ((rc = dskgpu_xchg_bin_hist(ctxs[r], lh.data()))) return rc; for (size_t i = 0; i < nh; i++) gh[i] += lh[i]; }
+    // 3. every rank plans the same partitions; the per-partition counts of all ranks form the layout matrix
+    uint32_t P = 0;
+    if ((rc = dskgpu_xchg_part_counts(ctxs[0], gh.data(), nullptr, &P))) return rc;
+    std::vector<uint64_t> all((size_t)n * 2 * P);
+    for (int r = 0; r < n; r++) { uint32_t Pr = 0; if ((rc = dskgpu_xchg_part_counts(ctxs[r], gh.data(), all.data() + (size_t)r * 2 * P, &Pr))) return rc; if (Pr != P) FAIL(DSKGPU_ERR_STATE, "multi_finish: ranks disagree on the partition count"); }
+    // 4. receive buffers, peer pointers (same process: plain device pointers), scatter straight into the owners' HBM
+    std::vector<void*> recv(n, nullptr);
+    for (int r = 0; r < n; r++) { if ((rc = dskgpu_xchg_plan(ctxs[r], all.data()))) return rc; size_t nb = 0; if ((rc = dskgpu_xchg_recv_buffer(ctxs[r], &recv[r], &nb))) return rc; }
+    for (int r = 0; r < n; r++) { if ((rc = dskgpu_xchg_set_peers(ctxs[r], recv.data()))) return rc; if ((rc = dskgpu_xchg_scatter(ctxs[r]))) return rc; }
+    for (int r = 0; r < n; r++) if ((rc = dskgpu_xchg_sync(ctxs[r]))) return rc;       // every record has landed before anyone counts
+    // 5. every rank counts what it owns (the stage blocks on its own stream: one host thread per rank)
+    std::vector<int> rcs(n, 0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n; r++) th.emplace_back([&, r] { rcs[r] = dskgpu_finish(ctxs[r]); });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < n; r++) if (rcs[r]) { ctx = ctxs[r]; return rcs[r]; }
     return DSKGPU_OK;
 }
 
@@ -1448,26 +1672,25 @@ int dskgpu_xchg_layout(int world_size, uint32_t nparts, const uint64_t* all_coun
 int dskgpu_recount(dskgpu_ctx* ctx, const int64_t* abundance_min)
 {
     if (!ctx || !abundance_min) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "recount before finish");
     for (int b = 0; b < DSKGPU_MAX_BANKS; b++) ctx->cfg.abundance_min[b] = abundance_min[b < ctx->cfg.nb_banks ? b : ctx->cfg.nb_banks - 1];
-    Counters* ctr = (Counters*)ctx->ctr.p;
-    CK(cudaMemsetAsync(&ctr->solid_n, 0, sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(&ctr->distinct_n, 0, sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(&ctr->smem_splits, 0, sizeof(unsigned int), ctx->stream));
-    CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
-    CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
-    if (ctx->bank_hist.p) CK(cudaMemsetAsync(ctx->bank_hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * (size_t)ctx->NB, ctx->stream));
-    ctx->state = 0; ctx->n_solid = 0; ctx->results_on_host = false;
-    ctx->st.nb_groups_hash = ctx->st.nb_groups_sort = 0;
+    // the solid set is bounded by the distinct k-mers the first pass found (the first pass of -abundance-min auto dumps nothing)
+    const u64 cap_request = ctx->st.kmers_nb_distinct + 1024;
+    int rc = reset_count_state(ctx); if (rc) return rc;
+    ctx->state = 0;
     const bool owned = ctx->cfg.world_size > 1;
     const std::vector<u64>& pr = owned ? ctx->owned_recs : ctx->h_part_recs;
     const std::vector<u64>& pk = owned ? ctx->owned_kmers : ctx->h_part_kmers;
-    return ctx->KW == 1 ? stage_count<1>(ctx, (const u64*)ctx->precs.p, pr, pk) : stage_count<2>(ctx, (const u64*)ctx->precs.p, pr, pk);
+    rc = ctx->KW == 1 ? stage_count<1>(ctx, (const u64*)ctx->precs.p, pr, pk, cap_request) : stage_count<2>(ctx, (const u64*)ctx->precs.p, pr, pk, cap_request);
+    if (rc) ctx->state = 2;                                        // failed: only reset / destroy are valid now
+    return rc;
 }
 
 int dskgpu_bank_histograms(dskgpu_ctx* ctx, uint64_t* hist)
 {
     if (!ctx || !hist) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "histograms requested before finish");
     if (ctx->NB == 1) { memcpy(hist, ctx->h_hist, sizeof(uint64_t) * DSKGPU_HISTO_LEN); return DSKGPU_OK; }
     if (!ctx->bank_hist.p) FAIL(DSKGPU_ERR_STATE, "per-bank histograms were not requested (cfg.bank_histograms)");
@@ -1481,6 +1704,7 @@ int dskgpu_num_partitions(dskgpu_ctx* ctx) { if (!ctx || ctx->state != 1) return
 int dskgpu_partition(dskgpu_ctx* ctx, int p, const uint64_t** kmers, const uint32_t** counts, uint64_t* n, int* words)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "results requested before finish");
     if (p != 0) FAIL(DSKGPU_ERR_ARG, "partition %d out of range", p);
     if (ctx->n_solid && !ctx->results_on_host) FAIL(DSKGPU_ERR_STATE, "results were kept on the device (keep_results_on_device)");
@@ -1491,6 +1715,7 @@ int dskgpu_partition(dskgpu_ctx* ctx, int p, const uint64_t** kmers, const uint3
 int dskgpu_partition_device(dskgpu_ctx* ctx, int p, const void** d_kmers, const void** d_counts, uint64_t* n, int* words)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "results requested before finish");
     if (p != 0) FAIL(DSKGPU_ERR_ARG, "partition %d out of range", p);
     if (d_kmers) *d_kmers = ctx->skeys[ctx->solid_buf].p; if (d_counts) *d_counts = ctx->svals[ctx->solid_buf].p;
@@ -1501,6 +1726,7 @@ int dskgpu_partition_device(dskgpu_ctx* ctx, int p, const void** d_kmers, const 
 int dskgpu_histogram(dskgpu_ctx* ctx, uint64_t* hist1d, uint64_t* hist2d)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
     if (ctx->state != 1) FAIL(DSKGPU_ERR_STATE, "histogram requested before finish");
     if (hist1d) memcpy(hist1d, ctx->h_hist, sizeof(uint64_t) * DSKGPU_HISTO_LEN);
     if (hist2d) memcpy(hist2d, ctx->h_hist + DSKGPU_HISTO_LEN, sizeof(uint64_t) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2);

@@ -40,6 +40,8 @@ struct Counters {
     unsigned int bucket_overflow;     // key-bucket path: a hash bucket outgrew its slab (one k-mer with a huge multiplicity)
     unsigned int pad0;
     unsigned long long sample_sumsq;  // density sample: sum of count^2 over its distinct k-mers (occurrence-weighted multiplicity)
+    unsigned long long kmers_pass;    // valid k-mers whose minimizer belongs to the current pass (== kmers_in_recs)
+    unsigned long long sample_solid;  // density sample: distinct k-mers whose summed count reaches the smallest abundance-min
 };
 
 #ifdef __CUDACC__
@@ -50,7 +52,8 @@ template <int KW>
 __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict__ codes, const StreamState* __restrict__ ss,
                                                            int k, int m, int bank, u64* __restrict__ recs,
                                                            u32* __restrict__ rec_meta, u64 rec_cap, Counters* ctr,
-                                                           unsigned long long* __restrict__ bin_hist /*[2][NBINS_FINE] records, k-mers*/)
+                                                           unsigned long long* __restrict__ bin_hist /*[2][NBINS_FINE] records, k-mers*/,
+                                                           u32 nb_passes, u32 pass_id)
 {
     constexpr int RW = 2 * KW;
     __shared__ u64 s_pk[SK_TP / 32 + 8];                         // 2-bit bases, MSB first, 32 per word
@@ -169,6 +172,14 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
     __syncthreads();
 
     // ---- 4. split runs longer than maxS, count records, reserve output space -----------------------------------
+    // pass filter (the reference's `minimizer % nbPass == pass`, K/SortingCountAlgorithm.cpp:1086, on the fine bin of the
+    // minimizer): windows of other passes are valid k-mers of the bank but produce no record in this pass
+    u32 passmask = 0xFFu;
+    if (nb_passes > 1) {
+        passmask = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (((validmask >> (7 - j)) & 1u) && bin_of(mn[j]) % nb_passes == pass_id) passmask |= 1u << (7 - j);
+    }
     u32 chunkmask = 0;
     {
         u32 rel = 0;                                              // index of the window inside its run, modulo maxS
@@ -187,15 +198,16 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
             if (validmask & bit) { if (rel == 0) chunkmask |= bit; rel++; if (rel == (u32)maxS) rel = 0; }
         }
     }
+    chunkmask &= passmask;
     u32 nch = __popc(chunkmask);
-    u32 nval = __popc(validmask);
+    u32 nval = __popc(validmask) | ((u32)__popc(validmask & passmask) << 16);   // all valid windows | those of this pass
     // block exclusive scan of nch
     u32 inc = nch;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
     if (lane == 31) s_wsum[warp] = inc;
-    u32 wval = __reduce_add_sync(0xFFFFFFFFu, nval);
-    if (lane == 0 && wval) atomicAdd(&s_nvalid, wval);
+    u32 wval = __reduce_add_sync(0xFFFFFFFFu, nval);                          // two 16-bit lanes: <= 256 per warp each
+    if (lane == 0 && wval) atomicAdd(&s_nvalid, wval);                        // <= 2048 per block each
     __syncthreads();
     u32 wpre = 0, btotal = 0;
 #pragma unroll
@@ -203,7 +215,8 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
     u32 myidx = wpre + inc - nch;
     if (t == 0) {
         s_goff = atomicAdd(&ctr->nrec, (unsigned long long)btotal);
-        atomicAdd(&ctr->kmers_valid, (unsigned long long)s_nvalid);
+        atomicAdd(&ctr->kmers_valid, (unsigned long long)(s_nvalid & 0xFFFFu));
+        atomicAdd(&ctr->kmers_pass, (unsigned long long)(s_nvalid >> 16));
     }
     __syncthreads();
     const u64 goff = s_goff;

@@ -156,21 +156,53 @@ class SortingCountAlgorithm:
             if e.code == -1 and "unhandled kmer size" in str(e):
                 raise RuntimeError("Failure because of unhandled kmer size %d" % cfg["kmer_size"]) from e
             raise
-        with eng:
+        # pass loop of SortingCountAlgorithm::execute (SortingCountAlgorithm.cpp:678-689): with nb_passes > 1 the banks are
+        # pushed once per pass and every pass keeps its own share of the minimizers; the results of the passes are disjoint
+        nb_passes = max(1, int(cfg.get("nb_passes", 1) or 1))
+
+        def feed(eng):
             for b, bank in enumerate(self.banks):
                 if isinstance(bank, BankStrings):
                     eng.push_reads(bank.seqs, bank=b)
                 else:
                     eng.push_bytes(bank.read(), bank=b, last=True)
-            eng.finish()
+
+        with eng:
             self.cutoffs = None
-            if self._auto:
-                hs = eng.bank_histograms() if self._auto_per_bank else [eng.histogram()[0]]
+            solids, st = [], None
+            h1 = np.zeros(_lib.HISTO_LEN, np.uint64); h2 = np.zeros((_lib.HISTO2D_DIM2, _lib.HISTO_LEN), np.uint64)
+            new_amin = None
+            if self._auto and nb_passes > 1:
+                # the cutoffs come from the histogram(s) of the WHOLE job: one round of passes for them, one for the dump
+                hs = None
+                for ps in range(nb_passes):
+                    eng.reset(); eng.set_pass(ps, nb_passes); feed(eng); eng.finish()
+                    h = eng.bank_histograms() if self._auto_per_bank else eng.histogram()[0][None, :]
+                    hs = h.copy() if hs is None else hs + h
                 self.cutoffs = [compute_threshold(h, MIN_AUTO_THRESHOLD)[0] for h in hs]
-                eng.recount(auto_thresholds(user_amin, self.cutoffs))          # pass 2: the dsk processor chain
-            self._solid = eng.solid()
-            self._hist = eng.histogram()
-            st = eng.stats()
+                new_amin = auto_thresholds(user_amin, self.cutoffs)
+            for ps in range(nb_passes):
+                if nb_passes > 1:
+                    eng.reset(); eng.set_pass(ps, nb_passes)
+                feed(eng)
+                eng.finish()
+                if self._auto and nb_passes == 1:
+                    hs = eng.bank_histograms() if self._auto_per_bank else [eng.histogram()[0]]
+                    self.cutoffs = [compute_threshold(h, MIN_AUTO_THRESHOLD)[0] for h in hs]
+                    eng.recount(auto_thresholds(user_amin, self.cutoffs))          # pass 2: the dsk processor chain
+                elif new_amin is not None:
+                    eng.recount(new_amin)
+                solids.append(eng.solid())
+                a, b2 = eng.histogram(); h1 += a; h2 += b2
+                s1 = eng.stats()
+                if st is None:
+                    st = s1
+                else:
+                    for key in ("kmers_nb_distinct", "kmers_nb_solid", "nb_superkmers", "nb_partitions", "gpu_launches", "kmers_in_pass",
+                                "nb_parts_smem", "nb_smem_splits", "nb_groups_hash", "nb_groups_sort", "nb_groups_bucket"):
+                        st[key] += s1[key]
+            self._solid = (np.concatenate([x[0] for x in solids]), np.concatenate([x[1] for x in solids])) if len(solids) > 1 else solids[0]
+            self._hist = (h1, h2)
         self.k = cfg["kmer_size"]
         self.info = {
             "kmers_nb_valid": st["kmers_nb_valid"], "kmers_nb_distinct": st["kmers_nb_distinct"],

@@ -102,7 +102,7 @@ def assembly_fasta_device(g, width=70):
     return torch.cat([head, body.view(-1)] + ([tail, nl] if tail.numel() else []))
 
 
-def reads_fasta_device(G, coverage=30, L=150, err=0.01, seed=42, device="cuda", batch=1 << 21, genome=None):
+def reads_fasta_device(G, coverage=30, L=150, err=0.01, seed=42, device="cuda", batch=1 << 21, genome=None, nreads=None):
     """Same read model generated on the device with torch (benchmark plumbing for read sets too big to draw with numpy
     in reasonable time: the 3 Gbp-class configurations).  Fixed-width headers ">r%09d" so that every record has the same
     size and a batch is one 2-D tensor.  Returns (uint8 cuda tensor of FASTA bytes, nreads).  Not bit-identical to
@@ -111,7 +111,7 @@ def reads_fasta_device(G, coverage=30, L=150, err=0.01, seed=42, device="cuda", 
     gen = torch.Generator(device=device); gen.manual_seed(seed + 1)
     g = genome if genome is not None else genome_device(G, seed, device)
     G = g.numel()
-    n = int(G * coverage // L)
+    n = int(G * coverage // L) if nreads is None else int(nreads)      # nreads: this rank's slice of the read set
     W = 2 + 9 + 1 + L + 1
     out = torch.empty(n * W, dtype=torch.uint8, device=device)
     acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)

@@ -5,6 +5,13 @@
 // code; only the counting (fillPartitions + fillSolidKmers + the CountProcessor chain,
 // K/SortingCountAlgorithm.cpp:636-781) is replaced by libdskgpu.so.  No CPU counting fallback exists here.
 //
+// Several GPUs (DSKGPU_DEVICES=all | n | "0,2,5"): ONE process, one context + one reader thread per device.  Plain files are
+// cut into byte ranges at record starts and every device parses its own range; dskgpu_multi_finish routes the super-k-mers to
+// the device owning their partition (peer stores) and every device counts what it owns -- the role the reference gives to
+// its partition files and worker threads.  Jobs whose records exceed HBM run as several passes over the input
+// (DSKGPU_NB_PASSES or dskgpu_suggest_nb_passes; the reference's pass loop, K/SortingCountAlgorithm.cpp:678-689).
+// Output collections: dsk/solid/<pass * nb_devices + device>, k-mers ascending inside each one.
+//
 // Output contract, all written through gatb-core's Storage:
 //   configuration.xml, minimizers/minimRepart, dsk/solid/<p> (+ attrs nb_partitions, kmer_size), dsk.xml,
 //   histogram/{histogram,cutoff,nbsolidsforcutoff}, <out>.histo / <out>.histo2D text files.
@@ -14,9 +21,13 @@
 #include <gatb/kmer/impl/ConfigurationAlgorithm.hpp>
 #include <gatb/kmer/impl/CountProcessorHistogram.hpp>
 #include <zlib.h>
+#include <fcntl.h>
+#include <unistd.h>
 
+#include <algorithm>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../include/dskgpu.h"
@@ -62,14 +73,15 @@ public:
 
     /** Same meaning as SortingCountAlgorithm(IBank*, IProperties*) (K/SortingCountAlgorithm.cpp:119-133). */
     GpuSortingCount(IBank* bank, IProperties* params)
-        : Algorithm("dsk", -1, params), _bank(0), _storage(0), _ctx(0), _solidCounts(0)
+        : Algorithm("dsk", -1, params), _bank(0), _storage(0), _ctx(0), _solidCounts(0), _nbPasses(1)
     {
         setBank(bank);
+        memset(&_st, 0, sizeof _st);
     }
 
     ~GpuSortingCount()
     {
-        if (_ctx) dskgpu_destroy(_ctx);
+        for (size_t i = 0; i < _ctxs.size(); i++) if (_ctxs[i]) dskgpu_destroy(_ctxs[i]);
         setBank(0);
         setStorage(0);
     }
@@ -90,20 +102,12 @@ public:
         // sequence (IBank::iterator -> dskgpu_push_reads), and the counting path is unchanged.
         for (int attempt = 0; ; attempt++) {
             try {
-                {
-                    TIME_INFO(getTimeInfo(), "fill_partitions");          // same labels as K/SortingCountAlgorithm.cpp:1218
-                    feedBanks();
-                }
-                {
-                    TIME_INFO(getTimeInfo(), "fill_solid_kmers");         // K/SortingCountAlgorithm.cpp:1391
-                    checkFormat(dskgpu_finish(_ctx), _ctx, "dskgpu_finish");
-                    if (_autoCutoff) executeAutoCutoff();
-                }
+                runAllPasses();
                 break;
             } catch (FormatRejected& e) {
                 if (attempt > 0 || _viaIterator) throw Exception("dskgpu: input rejected by the record scanner (%s)", e.what.c_str());
                 _viaIterator = true;
-                check(dskgpu_reset(_ctx), _ctx, "dskgpu_reset");
+                for (size_t r = 0; r < _ctxs.size(); r++) check(dskgpu_reset(_ctxs[r]), _ctxs[r], "dskgpu_reset");
             }
         }
         writeResults();
@@ -117,9 +121,13 @@ private:
 
     Configuration     _config;
     bool              _viaIterator = false;        // second attempt: banks parsed by the reference's own reader
-    dskgpu_ctx*       _ctx;
+    dskgpu_ctx*       _ctx;                        // context of rank 0 (== _ctxs[0])
+    std::vector<dskgpu_ctx*> _ctxs;                // one context per device (rank r = _ctxs[r])
+    int               _nbPasses;
     Partition<Count>* _solidCounts;
-    dskgpu_stats      _st;
+    dskgpu_stats      _st;                         // summed over the devices and the passes
+    std::vector<uint64_t> _h1, _h2;                // histograms summed over the devices and the passes
+    u_int64_t         _nbSolidWritten;
     std::string       _histoName, _histo2DName;
     bool              _autoCutoff;
     bool              _autoPerBank;
@@ -148,7 +156,8 @@ private:
         ConfigurationAlgorithm<span> configAlgo(_bank, in);
         configAlgo.execute();
         _config = configAlgo.getConfiguration();
-        // passes / partitions are a property of the device path: no disk tier, one ordered output collection
+        // passes / partitions are a property of the device path (set below, once the devices are known): no disk tier, one
+        // ordered output collection per device and pass
         _config._nb_passes = 1;
         _config._nb_partitions = 1;
         _storage->getGroup(configAlgo.getName()).setProperty("xml", std::string("\n") + configAlgo.getInfo()->getXML());
@@ -215,39 +224,114 @@ private:
         c.bank_histograms = _autoPerBank ? 1 : 0;
         c.abundance_max = _config._abundance.empty() ? 2147483647LL : (long long)_config._abundance[0].getEnd();
         for (size_t i = 0; i < (size_t)DSKGPU_MAX_BANKS; i++) c.solid_vec[i] = (i < _config._solidVec.size()) ? (_config._solidVec[i] ? 1 : 0) : 1;
-        const char* dev = getenv("DSKGPU_DEVICE");
-        c.device = dev ? atoi(dev) : 0;
-        check(dskgpu_create(&c, &_ctx), 0, "dskgpu_create");
+        // devices: DSKGPU_DEVICES = "all" | a count | a comma list of ordinals; default one device (DSKGPU_DEVICE, 0)
+        std::vector<int> devs;
+        const char* dl = getenv("DSKGPU_DEVICES");
+        if (dl && *dl) {
+            const std::string v(dl);
+            const int avail = dskgpu_device_count();
+            if (v == "all") { for (int i = 0; i < avail; i++) devs.push_back(i); }
+            else if (v.find(',') != std::string::npos) { std::stringstream ss(v); std::string tok; while (std::getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(atoi(tok.c_str())); }
+            else { const int n = atoi(v.c_str()); for (int i = 0; i < n; i++) devs.push_back(i); }
+        }
+        if (devs.empty()) { const char* dev = getenv("DSKGPU_DEVICE"); devs.push_back(dev ? atoi(dev) : 0); }
+        const int W = (int)devs.size();
+        // passes: the reference sizes them from the estimated volume against -max-disk (K/ConfigurationAlgorithm.cpp:245-467);
+        // here the bound is what one pass keeps in HBM per device
+        const char* np = getenv("DSKGPU_NB_PASSES");
+        _nbPasses = np ? std::max(1, atoi(np)) : dskgpu_suggest_nb_passes((uint64_t)_config._kmersNb, c.kmer_size, W, 0, devs[0]);
+        _config._nb_passes = (size_t)_nbPasses;
+        _config._nb_partitions = (size_t)W;                        // output collections per pass: one per device, k-mers ascending
+        c.world_size = W;
+        c.nb_passes = _nbPasses; c.pass_id = 0;
+        _ctxs.assign((size_t)W, (dskgpu_ctx*)0);
+        for (int r = 0; r < W; r++) {
+            c.rank = r; c.device = devs[(size_t)r];
+            check(dskgpu_create(&c, &_ctxs[(size_t)r]), 0, "dskgpu_create");
+        }
+        _ctx = _ctxs[0];
     }
 
-    // ---- fillPartitions(): K/SortingCountAlgorithm.cpp:1216-1349, replaced by streaming file bytes to the device ----
+    // ---- fillPartitions(): K/SortingCountAlgorithm.cpp:1216-1349, replaced by streaming file bytes to the devices ----
     static bool isRegularFile(const std::string& p) { return !p.empty() && System::file().doesExist(p) && System::file().getSize(p) > 0; }
 
-    void feedFile(int bankId, const std::string& path, char* buf[2], size_t cap)
+    /** What one reader thread feeds to its device: a byte range of a plain file, a whole (gzip) file, or a bank to iterate. */
+    struct FeedTask { int bank; std::string path; uint64_t begin, end; bool whole; IBank* leaf; };
+    /** An exception crossing a thread boundary (threads must not leak C++ exceptions). */
+    struct ThreadError { bool failed, format; std::string what; ThreadError() : failed(false), format(false) {} };
+
+    static bool isGzip(const std::string& path)
     {
-        // zlib reads plain and gzip files alike (what BankFasta does, G/src/gatb/bank/impl/BankFasta.cpp:391-396)
-        gzFile f = gzopen(path.c_str(), "rb");
-        if (!f) throw Exception("unable to open file %s", path.c_str());
-        gzbuffer(f, 1 << 20);
-        int par = 0;
-        size_t n = 0;
-        int r = gzread(f, buf[par], (unsigned)cap);
-        if (r < 0) { gzclose(f); throw Exception("read error on %s", path.c_str()); }
-        n = (size_t)r;
-        for (;;) {
-            // read the next block before pushing this one, so the last block is known to be the last
-            int r2 = (n == cap) ? gzread(f, buf[par ^ 1], (unsigned)cap) : 0;
-            if (r2 < 0) { gzclose(f); throw Exception("read error on %s", path.c_str()); }
-            const bool last = (r2 == 0);
-            const int rc = dskgpu_push_bytes(_ctx, bankId, buf[par], n, DSKGPU_FMT_AUTO, last ? DSKGPU_PUSH_LAST : 0);
-            if (rc != DSKGPU_OK) { gzclose(f); checkFormat(rc, _ctx, "dskgpu_push_bytes"); }
-            if (last) break;
-            par ^= 1; n = (size_t)r2;
-        }
-        gzclose(f);
+        unsigned char h[2] = {0, 0};
+        FILE* f = fopen(path.c_str(), "rb"); if (!f) return false;
+        const size_t n = fread(h, 1, 2, f); fclose(f);
+        return n == 2 && h[0] == 0x1f && h[1] == 0x8b;
     }
 
-    void feedSequences(int bankId, IBank* b)
+    /** First record start at or after `pos` in a plain FASTA / 4-line FASTQ file (returns `size` when there is none).
+     *  FASTA: a line starting with '>'.  FASTQ: a line starting with '@' whose second next line starts with '+' (a quality
+     *  line may start with '@', but then the line two below is a sequence line, which never starts with '+'). */
+    static uint64_t nextRecordStart(int fd, uint64_t pos, uint64_t size, char first)
+    {
+        if (pos == 0) return 0;
+        const size_t W = (size_t)4 << 20;
+        std::vector<char> buf(W);
+        uint64_t at = pos - 1;                                     // include the byte before: a record start follows a '\n'
+        while (at < size) {
+            const ssize_t n = pread(fd, buf.data(), W, (off_t)at);
+            if (n <= 1) break;
+            for (ssize_t i = 0; i + 1 < n; i++) {
+                if (buf[(size_t)i] != '\n' || buf[(size_t)i + 1] != first) continue;
+                if (first == '>') return at + (uint64_t)i + 1;
+                // FASTQ: check the '+' line two below (inside this window; a window that ends first is retried from here)
+                ssize_t e1 = i + 1; while (e1 < n && buf[(size_t)e1] != '\n') e1++;
+                ssize_t e2 = e1 + 1; while (e2 < n && buf[(size_t)e2] != '\n') e2++;
+                if (e2 + 1 >= n) { if (at + (uint64_t)n >= size) return size; goto refill; }
+                if (buf[(size_t)e2 + 1] == '+') return at + (uint64_t)i + 1;
+                continue;
+            refill:
+                at += i > 0 ? (uint64_t)i : (uint64_t)n - 1; goto next_window;        // (a record longer than the window cannot be a read)
+            }
+            at += (uint64_t)n - 1;
+        next_window:;
+        }
+        return size;
+    }
+
+    /** Streams bytes [begin, end) of a plain file (or a whole gzip file through zlib, BankFasta.cpp:391-396) into one context.
+     *  Two pinned buffers: the file read of block i+1 overlaps the device work on block i; dskgpu_push_sync guarantees the H2D
+     *  copy out of a buffer has completed before that buffer is written again (push_bytes only QUEUES the copy). */
+    static void feedRange(dskgpu_ctx* ctx, const FeedTask& t, char* buf[2], size_t cap)
+    {
+        gzFile gz = 0; int fd = -1;
+        if (t.whole) { gz = gzopen(t.path.c_str(), "rb"); if (!gz) throw Exception("unable to open file %s", t.path.c_str()); gzbuffer(gz, 1 << 20); }
+        else { fd = open(t.path.c_str(), O_RDONLY); if (fd < 0) throw Exception("unable to open file %s", t.path.c_str()); }
+        uint64_t pos = t.begin;
+        struct Closer { gzFile g; int f; ~Closer() { if (g) gzclose(g); if (f >= 0) close(f); } } closer = {gz, fd};
+        (void)closer;
+        auto readBlock = [&](char* dst) -> size_t {
+            if (gz) { const int r = gzread(gz, dst, (unsigned)cap); if (r < 0) throw Exception("read error on %s", t.path.c_str()); return (size_t)r; }
+            size_t got = 0;
+            const size_t want = (size_t)std::min<uint64_t>(cap, t.end - pos);
+            while (got < want) { const ssize_t r = pread(fd, dst + got, want - got, (off_t)(pos + got)); if (r < 0) throw Exception("read error on %s", t.path.c_str()); if (r == 0) break; got += (size_t)r; }
+            pos += got;
+            return got;
+        };
+        int par = 0;
+        size_t n = readBlock(buf[par]);
+        for (;;) {
+            // read the next block before pushing this one, so the last block is known to be the last
+            size_t n2 = 0;
+            if (n == cap) { checkFormat(dskgpu_push_sync(ctx), ctx, "dskgpu_push_sync"); n2 = readBlock(buf[par ^ 1]); }
+            const bool last = (n2 == 0);
+            checkFormat(dskgpu_push_bytes(ctx, t.bank, buf[par], n, DSKGPU_FMT_AUTO, last ? DSKGPU_PUSH_LAST : 0), ctx, "dskgpu_push_bytes");
+            if (last) break;
+            par ^= 1; n = n2;
+        }
+        checkFormat(dskgpu_push_sync(ctx), ctx, "dskgpu_push_sync");       // the buffers are about to be freed / reused
+    }
+
+    static void feedSequences(dskgpu_ctx* ctx, int bankId, IBank* b)
     {
         // non-file banks (BankStrings, BankRandom, ...): IBank::iterator() -> concatenated sequences
         std::vector<char> bases; std::vector<uint64_t> offs(1, 0);
@@ -257,11 +341,11 @@ private:
             bases.insert(bases.end(), s.getDataBuffer(), s.getDataBuffer() + s.getDataSize());
             offs.push_back(bases.size());
             if (bases.size() > ((size_t)256 << 20)) {
-                check(dskgpu_push_reads(_ctx, bankId, bases.data(), offs.data(), offs.size() - 1), _ctx, "dskgpu_push_reads");
+                check(dskgpu_push_reads(ctx, bankId, bases.data(), offs.data(), offs.size() - 1), ctx, "dskgpu_push_reads");
                 bases.clear(); offs.assign(1, 0);
             }
         }
-        if (offs.size() > 1) check(dskgpu_push_reads(_ctx, bankId, bases.data(), offs.data(), offs.size() - 1), _ctx, "dskgpu_push_reads");
+        if (offs.size() > 1) check(dskgpu_push_reads(ctx, bankId, bases.data(), offs.data(), offs.size() - 1), ctx, "dskgpu_push_reads");
     }
 
     void collectLeaves(IBank* b, std::vector<IBank*>& out)
@@ -272,37 +356,169 @@ private:
         for (size_t i = 0; i < sub.size(); i++) collectLeaves(sub[i], out);
     }
 
+    /** Splits the banks into per-device task lists and runs one reader thread per device. */
     void feedBanks()
     {
-        const size_t cap = (size_t)64 << 20;
-        char* buf[2] = {(char*)dskgpu_host_alloc(cap), (char*)dskgpu_host_alloc(cap)};
-        if (!buf[0] || !buf[1]) throw Exception("pinned staging allocation failed");
-        try {
-            // bank id = index in the top-level composition, as the reference's per-bank counts (getCompositionNb)
-            const std::vector<IBank*> top = _bank->getBanks();
-            const bool composite = _config._nb_banks > 1 && top.size() == _config._nb_banks;
-            for (size_t t = 0; t < (composite ? top.size() : 1); t++) {
-                std::vector<IBank*> leaves;
-                collectLeaves(composite ? top[t] : _bank, leaves);
-                for (size_t i = 0; i < leaves.size(); i++) {
-                    const std::string id = leaves[i]->getId();
-                    if (!_viaIterator && isRegularFile(id)) feedFile((int)t, id, buf, cap);
-                    else feedSequences((int)t, leaves[i]);
+        const size_t W = _ctxs.size();
+        std::vector<std::vector<FeedTask> > tasks(W);
+        size_t rr = 0;                                             // round robin for inputs that cannot be cut into ranges
+        // bank id = index in the top-level composition, as the reference's per-bank counts (getCompositionNb)
+        const std::vector<IBank*> top = _bank->getBanks();
+        const bool composite = _config._nb_banks > 1 && top.size() == _config._nb_banks;
+        for (size_t t = 0; t < (composite ? top.size() : 1); t++) {
+            std::vector<IBank*> leaves;
+            collectLeaves(composite ? top[t] : _bank, leaves);
+            for (size_t i = 0; i < leaves.size(); i++) {
+                const std::string id = leaves[i]->getId();
+                FeedTask ft; ft.bank = (int)t; ft.path = id; ft.begin = 0; ft.end = 0; ft.whole = true; ft.leaf = leaves[i];
+                if (_viaIterator || !isRegularFile(id)) { ft.path.clear(); tasks[rr++ % W].push_back(ft); continue; }
+                const uint64_t size = (uint64_t)System::file().getSize(id);
+                char first = 0;
+                static const uint64_t splitMin = getenv("DSKGPU_SPLIT_MIN_BYTES") ? (uint64_t)atoll(getenv("DSKGPU_SPLIT_MIN_BYTES")) : ((uint64_t)8 << 20);
+                if (W > 1 && size >= splitMin && !isGzip(id)) {
+                    FILE* f = fopen(id.c_str(), "rb");
+                    if (f) { int ch; while ((ch = fgetc(f)) != EOF) if (ch == '>' || ch == '@') { first = (char)ch; break; } fclose(f); }
+                }
+                if (!first) { tasks[rr++ % W].push_back(ft); continue; }       // gzip / small / unknown: one device parses it whole
+                const int fd = open(id.c_str(), O_RDONLY);
+                if (fd < 0) throw Exception("unable to open file %s", id.c_str());
+                std::vector<uint64_t> cut(W + 1, size);
+                cut[0] = 0;
+                for (size_t r = 1; r < W; r++) cut[r] = std::max(cut[r - 1], nextRecordStart(fd, size / W * r, size, first));
+                close(fd);
+                for (size_t r = 0; r < W; r++) {
+                    if (cut[r + 1] <= cut[r]) continue;
+                    ft.whole = false; ft.begin = cut[r]; ft.end = cut[r + 1];
+                    tasks[r].push_back(ft);
                 }
             }
-        } catch (...) { dskgpu_host_free(buf[0]); dskgpu_host_free(buf[1]); throw; }
-        dskgpu_host_free(buf[0]); dskgpu_host_free(buf[1]);
+        }
+        const size_t cap = (size_t)64 << 20;
+        std::vector<ThreadError> errs(W);
+        auto worker = [&](size_t r) {
+            char* buf[2] = {(char*)dskgpu_host_alloc(cap), (char*)dskgpu_host_alloc(cap)};
+            try {
+                if (!buf[0] || !buf[1]) throw Exception("pinned staging allocation failed");
+                for (size_t i = 0; i < tasks[r].size(); i++) {
+                    const FeedTask& ft = tasks[r][i];
+                    if (ft.path.empty()) feedSequences(_ctxs[r], ft.bank, ft.leaf);
+                    else feedRange(_ctxs[r], ft, buf, cap);
+                }
+            }
+            catch (FormatRejected& e) { errs[r].failed = true; errs[r].format = true; errs[r].what = e.what; }
+            catch (Exception& e) { errs[r].failed = true; errs[r].what = e.getMessage(); }
+            catch (std::exception& e) { errs[r].failed = true; errs[r].what = e.what(); }
+            dskgpu_host_free(buf[0]); dskgpu_host_free(buf[1]);
+        };
+        if (W == 1) worker(0);
+        else {
+            std::vector<std::thread> th;
+            for (size_t r = 0; r < W; r++) th.push_back(std::thread(worker, r));
+            for (size_t r = 0; r < W; r++) th[r].join();
+        }
+        for (size_t r = 0; r < W; r++) if (errs[r].failed && errs[r].format) { FormatRejected e; e.what = errs[r].what; throw e; }
+        for (size_t r = 0; r < W; r++) if (errs[r].failed) throw Exception("%s", errs[r].what.c_str());
+    }
+
+    /** exchange + counting on every device (dskgpu_finish for one, dskgpu_multi_finish for several) */
+    void finishAll()
+    {
+        if (_ctxs.size() == 1) { checkFormat(dskgpu_finish(_ctx), _ctx, "dskgpu_finish"); return; }
+        const int rc = dskgpu_multi_finish(_ctxs.data(), (int)_ctxs.size());
+        if (rc != DSKGPU_OK) {
+            dskgpu_ctx* bad = _ctx;
+            for (size_t r = 0; r < _ctxs.size(); r++) { const char* d = dskgpu_last_error(_ctxs[r]); if (d && *d) { bad = _ctxs[r]; break; } }
+            checkFormat(rc, bad, "dskgpu_multi_finish");
+        }
+    }
+
+    void recountAll(const int64_t* amin)
+    {
+        const size_t W = _ctxs.size();
+        std::vector<int> rcs(W, 0);
+        if (W == 1) rcs[0] = dskgpu_recount(_ctx, amin);
+        else {
+            std::vector<std::thread> th;
+            for (size_t r = 0; r < W; r++) th.push_back(std::thread([&, r] { rcs[r] = dskgpu_recount(_ctxs[r], amin); }));
+            for (size_t r = 0; r < W; r++) th[r].join();
+        }
+        for (size_t r = 0; r < W; r++) check(rcs[r], _ctxs[r], "dskgpu_recount");
+    }
+
+    /** histograms of the job so far (this pass): summed over the devices */
+    void sumHistograms(std::vector<uint64_t>& hs /*[nbHist][10001]*/, size_t nbHist, bool perBank)
+    {
+        std::vector<uint64_t> one(nbHist * (size_t)DSKGPU_HISTO_LEN);
+        for (size_t r = 0; r < _ctxs.size(); r++) {
+            if (perBank) check(dskgpu_bank_histograms(_ctxs[r], one.data()), _ctxs[r], "dskgpu_bank_histograms");
+            else         check(dskgpu_histogram(_ctxs[r], one.data(), 0), _ctxs[r], "dskgpu_histogram");
+            for (size_t i = 0; i < one.size(); i++) hs[i] += one[i];
+        }
+    }
+
+    /** The pass loop of SortingCountAlgorithm::execute (K/SortingCountAlgorithm.cpp:678-689): every pass pushes the banks
+     *  again and keeps its share of the minimizers.  "-abundance-min auto" needs the histogram of the WHOLE job before
+     *  anything is dumped: with one pass the partitions are counted again from HBM (dskgpu_recount); with several, a first
+     *  round of passes produces the histogram(s) and a second one dumps. */
+    void runAllPasses()
+    {
+        const size_t W = _ctxs.size();
+        const size_t nbHist = _autoPerBank ? (size_t)_config._nb_banks : 1;
+        _h1.assign(DSKGPU_HISTO_LEN, 0); _h2.assign((size_t)DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, 0);
+        memset(&_st, 0, sizeof _st); _nbSolidWritten = 0;
+        Group& dsk = _storage->getGroup("dsk");
+        _solidCounts = &dsk.template getPartition<Count>("solid", W * (size_t)_nbPasses);
+        int64_t amin[DSKGPU_MAX_BANKS];
+        bool haveThresholds = false;
+        if (_autoCutoff && _nbPasses > 1) {
+            std::vector<uint64_t> hs(nbHist * (size_t)DSKGPU_HISTO_LEN, 0);
+            for (int pass = 0; pass < _nbPasses; pass++) {
+                TIME_INFO(getTimeInfo(), "cutoff_passes");
+                beginPass(pass);
+                feedBanks();
+                finishAll();
+                sumHistograms(hs, nbHist, _autoPerBank);
+            }
+            thresholdsFrom(hs, nbHist, amin);
+            haveThresholds = true;
+        }
+        for (int pass = 0; pass < _nbPasses; pass++) {
+            if (_nbPasses > 1) beginPass(pass);
+            {
+                TIME_INFO(getTimeInfo(), "fill_partitions");          // same labels as K/SortingCountAlgorithm.cpp:1218
+                feedBanks();
+            }
+            {
+                TIME_INFO(getTimeInfo(), "fill_solid_kmers");         // K/SortingCountAlgorithm.cpp:1391
+                finishAll();
+                if (_autoCutoff) {
+                    if (!haveThresholds) {
+                        std::vector<uint64_t> hs(nbHist * (size_t)DSKGPU_HISTO_LEN, 0);
+                        sumHistograms(hs, nbHist, _autoPerBank);
+                        thresholdsFrom(hs, nbHist, amin);
+                    }
+                    recountAll(amin);
+                }
+            }
+            TIME_INFO(getTimeInfo(), "dump");
+            collectPass(pass);
+        }
+        _solidCounts->flush();
+    }
+
+    void beginPass(int pass)
+    {
+        for (size_t r = 0; r < _ctxs.size(); r++) {
+            check(dskgpu_reset(_ctxs[r]), _ctxs[r], "dskgpu_reset");
+            check(dskgpu_set_pass(_ctxs[r], pass, _nbPasses), _ctxs[r], "dskgpu_set_pass");
+        }
     }
 
     // ---- -abundance-min auto: CountProcessorCutoff::endPass + CountProcessorSolidityInfo::setAbundanceMin ----------------
     // (K/CountProcessorCutoff.hpp:86-124, K/CountProcessorSolidity.hpp:45-66); the heuristic itself is the reference's own
     // Histogram::compute_threshold, run on the device histogram(s)
-    void executeAutoCutoff()
+    void thresholdsFrom(const std::vector<uint64_t>& hs, size_t nbHist, int64_t* amin /*[DSKGPU_MAX_BANKS]*/)
     {
-        const size_t nbHist = _autoPerBank ? (size_t)_config._nb_banks : 1;
-        std::vector<uint64_t> hs(nbHist * (size_t)DSKGPU_HISTO_LEN);
-        if (_autoPerBank) check(dskgpu_bank_histograms(_ctx, hs.data()), _ctx, "dskgpu_bank_histograms");
-        else              check(dskgpu_histogram(_ctx, hs.data(), 0), _ctx, "dskgpu_histogram");
         _cutoffs.clear();
         for (size_t b = 0; b < nbHist; b++) {
             Histogram H(10000);
@@ -312,17 +528,55 @@ private:
         }
         const size_t nbThr = std::max<size_t>(1, _config._abundance.size());
         if (_cutoffs.size() > nbThr) throw Exception("Unable to set abundance min values (%d values for %d banks)", (int)_cutoffs.size(), (int)nbThr);
-        int64_t amin[DSKGPU_MAX_BANKS];
         for (size_t i = 0; i < _cutoffs.size(); i++) amin[i] = _userAbundanceMin[i] == -1 ? (int64_t)_cutoffs[i] : (int64_t)_userAbundanceMin[i];
         for (size_t i = _cutoffs.size(); i < (size_t)DSKGPU_MAX_BANKS; i++) amin[i] = amin[_cutoffs.size() - 1];
-        check(dskgpu_recount(_ctx, amin), _ctx, "dskgpu_recount");
+    }
+
+    // ---- results of one pass: CountProcessorDump role (K/CountProcessorDump.hpp:85-152), in bulk -----------------------
+    void collectPass(int pass)
+    {
+        const size_t W = _ctxs.size();
+        std::vector<Count> block;
+        std::vector<uint64_t> h1(DSKGPU_HISTO_LEN), h2((size_t)DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2);
+        for (size_t r = 0; r < W; r++) {
+            dskgpu_ctx* ctx = _ctxs[r];
+            const size_t coll = (size_t)pass * W + r;               // CountProcessorDump: partId + passId * nbPartsPerPass
+            const uint64_t* kmers = 0; const uint32_t* counts = 0; uint64_t n = 0; int words = 0;
+            check(dskgpu_partition(ctx, 0, &kmers, &counts, &n, &words), ctx, "dskgpu_partition");
+            const size_t B = 1 << 20;
+            for (uint64_t i = 0; i < n; i += B) {
+                const size_t m = (size_t)std::min<uint64_t>(B, n - i);
+                block.resize(m);
+                for (size_t j = 0; j < m; j++) {
+                    Type v; setValue(v, kmers + (i + j) * words, words);
+                    block[j] = Count(v, (CountNumber)counts[i + j]);
+                }
+                (*_solidCounts)[coll].insert(block.data(), m);
+            }
+            (*_solidCounts)[coll].flush();
+            _nbSolidWritten += n;
+            check(dskgpu_histogram(ctx, h1.data(), h2.data()), ctx, "dskgpu_histogram");
+            for (size_t i = 0; i < h1.size(); i++) _h1[i] += h1[i];
+            for (size_t i = 0; i < h2.size(); i++) _h2[i] += h2[i];
+            dskgpu_stats st;
+            check(dskgpu_get_stats(ctx, &st), ctx, "dskgpu_get_stats");
+            if (pass == 0) {                                         // every pass parses the whole bank: report it once
+                _st.nb_sequences += st.nb_sequences; _st.nb_nucleotides += st.nb_nucleotides; _st.kmers_nb_valid += st.kmers_nb_valid;
+            }
+            _st.nb_superkmers += st.nb_superkmers; _st.superkmer_bytes += st.superkmer_bytes;
+            _st.kmers_nb_distinct += st.kmers_nb_distinct; _st.kmers_nb_solid += st.kmers_nb_solid;
+            if (r == 0) _st.nb_partitions += st.nb_partitions;      // the plan is job-wide: every device reports the same number
+            _st.nb_groups_hash += st.nb_groups_hash; _st.nb_groups_sort += st.nb_groups_sort; _st.gpu_launches += st.gpu_launches;
+            _st.ms_parse = std::max(_st.ms_parse, st.ms_parse); _st.ms_superk = std::max(_st.ms_superk, st.ms_superk);
+            _st.ms_partition = std::max(_st.ms_partition, st.ms_partition); _st.ms_count = std::max(_st.ms_count, st.ms_count);
+            _st.ms_sort = std::max(_st.ms_sort, st.ms_sort);
+        }
     }
 
     // ---- results: CountProcessorDump / CountProcessorHistogram roles, in bulk ---------------------------------------
     void writeResults()
     {
         IProperties* in = getInput();
-        check(dskgpu_get_stats(_ctx, &_st), _ctx, "dskgpu_get_stats");
 
         // minimizers/minimRepart: the blob of Repartitor::save (K/PartiInfo.cpp:271-295) for our map: every minimizer
         // goes to the single output collection 0
@@ -343,36 +597,15 @@ private:
             os.flush();
         }
 
-        // dsk/solid/<p>: CountProcessorDump::begin + bulk Bag<Count>::insert (K/CountProcessorDump.hpp:85-152)
+        // dsk/solid/<p> were written pass by pass (collectPass); attributes as CountProcessorDump::begin leaves them
         Group& dsk = _storage->getGroup("dsk");
-        const int nparts = dskgpu_num_partitions(_ctx);
-        if (nparts < 0) check(nparts, _ctx, "dskgpu_num_partitions");
-        _solidCounts = &dsk.template getPartition<Count>("solid", (size_t)nparts);
+        const int nparts = (int)(_ctxs.size() * (size_t)_nbPasses);
         dsk.addProperty("kmer_size", Stringify::format("%d", (int)_config._kmerSize));
-        u_int64_t nbSolid = 0;
-        std::vector<Count> block;
-        for (int p = 0; p < nparts; p++) {
-            const uint64_t* kmers = 0; const uint32_t* counts = 0; uint64_t n = 0; int words = 0;
-            check(dskgpu_partition(_ctx, p, &kmers, &counts, &n, &words), _ctx, "dskgpu_partition");
-            const size_t B = 1 << 20;
-            for (uint64_t i = 0; i < n; i += B) {
-                const size_t m = (size_t)std::min<uint64_t>(B, n - i);
-                block.resize(m);
-                for (size_t j = 0; j < m; j++) {
-                    Type v; setValue(v, kmers + (i + j) * words, words);
-                    block[j] = Count(v, (CountNumber)counts[i + j]);
-                }
-                (*_solidCounts)[p].insert(block.data(), m);
-            }
-            (*_solidCounts)[p].flush();
-            nbSolid += n;
-        }
-        _solidCounts->flush();
+        const u_int64_t nbSolid = _nbSolidWritten;
 
         // histogram group + text files: the reference's own CountProcessorHistogram::end() on a Histogram object that
         // was filled from the device bins (K/CountProcessorHistogram.hpp:104-159, Histogram.cpp:43-190)
-        std::vector<uint64_t> h1(DSKGPU_HISTO_LEN), h2((size_t)DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2);
-        check(dskgpu_histogram(_ctx, h1.data(), h2.data()), _ctx, "dskgpu_histogram");
+        const std::vector<uint64_t>& h1 = _h1; const std::vector<uint64_t>& h2 = _h2;
         const bool histo2D = !_histo2DName.empty(), histo1D = !_histoName.empty();
         CountProcessorHistogram<span> ph(&_storage->getGroup("histogram"), 10000, in->getInt(STR_KMER_ABUNDANCE_MIN_THRESHOLD),
                                          histo2D, histo1D, _histo2DName, _histoName);
@@ -411,6 +644,8 @@ private:
         getInfo()->add(2, "partitions");
         getInfo()->add(3, "nb_partitions", "%ld", (long)nparts);
         getInfo()->add(3, "nb_items", "%ld", (long)nbSolid);
+        getInfo()->add(3, "nb_passes", "%ld", (long)_nbPasses);
+        getInfo()->add(3, "nb_devices", "%ld", (long)_ctxs.size());
         getInfo()->add(3, "device_partitions", "%ld", (long)_st.nb_partitions);
         getInfo()->add(3, "kind");
         getInfo()->add(4, "vector", "%ld", (long)_st.nb_groups_sort);

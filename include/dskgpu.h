@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DSKGPU_ABI_VERSION   1
+#define DSKGPU_ABI_VERSION   2
 #define DSKGPU_MAX_BANKS     16
 #define DSKGPU_HISTO_LEN     10001          /* bins 0..10000 (Histogram.hpp:92, length 10000) */
 #define DSKGPU_HISTO2D_DIM2  11             /* bins 0..10   (CountProcessorHistogram.hpp:173-184) */
@@ -86,7 +86,11 @@ typedef struct dskgpu_config {
     int32_t  bank_histograms;                    /* 1: also keep one abundance histogram per bank (dskgpu_bank_histograms; the first
                                                     pass of -abundance-min auto with -solidity-kind one/all/custom).  Global atomics
                                                     per distinct k-mer: leave 0 unless those cutoffs are needed */
-    int32_t  reserved[5];
+    int32_t  nb_passes;                          /* 0/1 = one pass.  >1: this context keeps only the super-k-mers whose minimizer bin falls in */
+    int32_t  pass_id;                            /*   pass `pass_id` (the reference's `minimizer % nbPass == pass`, SortingCountAlgorithm.cpp:1086); the
+                                                    caller pushes the whole input once per pass (dskgpu_set_pass + dskgpu_reset in between) and the
+                                                    results of the passes are disjoint: what makes a job whose records exceed HBM fit */
+    int32_t  reserved[3];
 } dskgpu_config;
 
 /* stats block: the keys of SortingCountAlgorithm::getInfo() (SortingCountAlgorithm.cpp:728-780) */
@@ -112,11 +116,12 @@ typedef struct dskgpu_stats {
     uint32_t density_ppm;           /* sampled distinct / total k-mers x 1e6 (0 = sample too small) */
     uint32_t log2_bins;             /* minimizer-bin level the partitions were packed from (16..20) */
     uint32_t nb_groups_bucket;      /* heavy partitions: groups expanded into hash buckets of flat keys, counted in shared memory */
-    uint32_t reserved[1];
+    uint32_t nb_hash_regroups;      /* global-table groups that outgrew the table (sized from an estimate) and were redone at the worst-case size */
     /* multi-GPU exchange (this rank): bytes stored into other ranks' HBM over NVLink, duration of the segment-copy kernel */
     uint64_t exchange_bytes_out;
     float    ms_exchange;
-    uint32_t reserved2;
+    uint32_t nb_solid_regrows;      /* counting stage redone because the solid-set buffers (sized from an estimate) were too small */
+    uint64_t kmers_in_pass;         /* valid k-mers whose minimizer belongs to this context's pass (== kmers_nb_valid with one pass) */
 } dskgpu_stats;
 
 /* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */
@@ -129,8 +134,18 @@ void dskgpu_config_default(dskgpu_config* cfg);
  * Which partition a k-mer lands in is unobservable in the results.  Host-only, no device needed. */
 int dskgpu_suggest_minimizer_size(uint64_t expected_kmers, int kmer_size);
 
+/* replaces: the pass sizing of ConfigurationAlgorithm::execute (ConfigurationAlgorithm.cpp:245-467: nb_passes from the estimated
+ * volume against -max-disk / -max-memory).  Here the bound is HBM: returns how many passes a job of `expected_kmers` k-mers over
+ * `world_size` GPUs needs so that one pass's super-k-mer records (two copies: input order + partition order), the receive
+ * buffer and the solid-set buffers fit in `hbm_bytes` per GPU (0 = ask the device: free memory of `device`).  >= 1. */
+int dskgpu_suggest_nb_passes(uint64_t expected_kmers, int kmer_size, int world_size, uint64_t hbm_bytes, int device);
+
 /* replaces: SortingCountAlgorithm ctor + configure() (SortingCountAlgorithm.cpp:525-625) */
 int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out);
+
+/* replaces: the pass loop of SortingCountAlgorithm::execute (SortingCountAlgorithm.cpp:678-689).  Valid on a context that holds
+ * no pushed data (after create or reset): the next pushes keep the super-k-mers of pass `pass_id` of `nb_passes`. */
+int dskgpu_set_pass(dskgpu_ctx* ctx, int pass_id, int nb_passes);
 
 /* replaces: fillPartitions() for one chunk of one bank (SortingCountAlgorithm.cpp:1216-1349).
  * `bytes` are raw FASTA/FASTQ file bytes (already gunzipped), any chunking; records may straddle chunks.
@@ -138,6 +153,11 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out);
  * Pass DSKGPU_PUSH_LAST with the final chunk of the bank.  Host memory may be pageable or pinned
  * (dskgpu_host_alloc); pinned memory is copied without an intermediate staging copy. */
 int dskgpu_push_bytes(dskgpu_ctx* ctx, int bank_id, const char* bytes, size_t n, int format, int flags);
+
+/* Blocks until every host buffer handed to dskgpu_push_bytes so far has been copied to the device.  push_bytes returns as soon
+ * as the H2D copy is QUEUED: a caller that refills a buffer (double-buffered file reader) must call this first, or not touch
+ * a buffer until two further pushes have returned. */
+int dskgpu_push_sync(dskgpu_ctx* ctx);
 
 /* same, for bytes that already live in device memory (HBM-resident benchmark leg) */
 int dskgpu_push_device_bytes(dskgpu_ctx* ctx, int bank_id, const void* dev_bytes, size_t n, int format, int flags);
@@ -218,6 +238,7 @@ int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts /*[world_size][
 int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes);
 int dskgpu_xchg_ipc_handle(dskgpu_ctx* ctx, void* handle64 /*cudaIpcMemHandle_t of the receive buffer*/);
 int dskgpu_xchg_open_peer(dskgpu_ctx* ctx, const void* handle64, void** d_ptr);
+int dskgpu_xchg_close_peer(dskgpu_ctx* ctx, void* d_ptr /*from xchg_open_peer: unmap a peer buffer that was re-allocated*/);
 int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv /*[world_size]; own entry ignored*/);
 int dskgpu_xchg_scatter(dskgpu_ctx* ctx);
 int dskgpu_xchg_sync(dskgpu_ctx* ctx);
@@ -239,6 +260,13 @@ int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist /*device, [2*B]
                       uint64_t* need_records /*[world_size] or NULL*/, uint32_t* nparts);
 int dskgpu_xchg2_ensure_recv(dskgpu_ctx* ctx, uint64_t capacity_records);
 int dskgpu_xchg2_scatter(dskgpu_ctx* ctx, const void* d_matrix /*device, [world_size][P] u64*/);
+/* ---- several GPUs inside ONE process (what the `dsk_gpu` CLI does with DSKGPU_DEVICES): ctxs[r] is the context of rank r
+ * (cfg.rank = r, cfg.world_size = n, any device each -- peer access is enabled between distinct devices; contexts may also
+ * share a device).  After all pushes (one host thread per context is fine), this runs the whole exchange above with host-side
+ * sums instead of collectives -- totals, bin histogram, plan, receive buffers, peer-pointer scatter -- and then counts the
+ * owned partitions of every context concurrently (one host thread each).  Results are read per context, as after dskgpu_finish. */
+int dskgpu_multi_finish(dskgpu_ctx* const* ctxs, int n);
+
 /* host-only layout helper: offsets[p] = first record slot of `sender` for partition p inside owner(p)'s buffer */
 int dskgpu_xchg_layout(int world_size, uint32_t nparts, const uint64_t* all_counts, int sender, uint64_t* offsets, uint64_t* recv_records);
 int dskgpu_record_bytes(dskgpu_ctx* ctx);

@@ -54,6 +54,9 @@ def _lib(k=31):
     L.orc_parse_stats.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t]
     L.orc_mmer_lut.restype = C.c_uint32
     L.orc_mmer_lut.argtypes = [C.c_uint32, C.c_int]
+    if not wide:
+        L.orc_parse_dump.restype = C.c_int64
+        L.orc_parse_dump.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     if wide:
         _LIB_WIDE = L
     else:
@@ -355,3 +358,16 @@ def stat_value(stats_text, key):
         if s.startswith(key + " ") or s.startswith(key + ":"):
             return s.split(":", 1)[1].strip()
     return None
+
+
+def parse_dump(path, k):
+    """(lo u64[n], hi u64[n], count u32[n]) of a `dsk2ascii` text dump, sorted ascending by k-mer value (k <= 63)."""
+    text = np.fromfile(path, dtype=np.uint8)
+    cap = int(text.size // (k + 3)) + 16
+    lo = np.zeros(cap, np.uint64); hi = np.zeros(cap, np.uint64); cnt = np.zeros(cap, np.uint32)
+    n = _lib(k).orc_parse_dump(text.ctypes.data, text.size, k, lo.ctypes.data, hi.ctypes.data, cnt.ctypes.data, cap)
+    if n < 0 or n > cap:
+        raise RuntimeError("malformed dsk2ascii dump %s (%d)" % (path, n))
+    lo, hi, cnt = lo[:n], hi[:n], cnt[:n]
+    order = np.lexsort((lo, hi)) if k > 32 else np.argsort(lo, kind="stable")
+    return lo[order], hi[order], cnt[order]

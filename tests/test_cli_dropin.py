@@ -151,3 +151,99 @@ def test_cli_abundance_min_auto(t, tmp_path):
     assert m.hexdigest() == t["kmers_sha256"]
     rows = open(out + ".histo").read().splitlines()
     assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]
+
+
+# ---------------------------------------------------------------- several devices / several passes behind the same command line
+def _cli_check(t, tmp, env, extra_names=()):
+    out = os.path.join(tmp, "gpu_out")
+    a = dsk_args(t, out)
+    a[a.index("-verbose") + 1] = "1"
+    p = subprocess.run([DSK_GPU] + a, cwd=tmp, capture_output=True, text=True, env=dict(os.environ, **env))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    lines, histo, header = read_back(out + ".h5", tmp)
+    assert len(lines) == t["nb_solid"]
+    m = hashlib.sha256()
+    for ln in lines:
+        m.update(ln + b"\n")
+    assert m.hexdigest() == t["kmers_sha256"]
+    rows = open(out + ".histo").read().splitlines()
+    assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]
+    for name in extra_names:
+        assert name in header, name
+    return p.stdout.replace("\r", "\n")
+
+
+MULTI = [t for t in RUNS if t["name"] in ("c1_k31", "c1_k63", "reads.fastq_k31", "multiline.fasta_k31", "histo2d_c123_k31", "c123_k31_all", "longread_k63")]
+
+
+@need_bins
+@pytest.mark.parametrize("t", MULTI, ids=[t["name"] for t in MULTI])
+def test_cli_two_contexts_byte_range_slices(t, tmp_path):
+    """DSKGPU_DEVICES with two entries: one process, two contexts (here on the same GPU), each parsing a record-aligned byte
+    range of every plain input file; dskgpu_multi_finish routes the super-k-mers; two output collections dsk/solid/{0,1}"""
+    stats = _cli_check(t, str(tmp_path), {"DSKGPU_DEVICES": "0,0", "DSKGPU_SPLIT_MIN_BYTES": "1000"}, ('DATASET "0"', 'DATASET "1"'))
+    assert "nb_devices" in stats
+
+
+@need_bins
+def test_cli_all_real_devices(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs in the box")
+    for name in ("c1_k31", "c1_k63", "histo2d_c123_k31"):
+        t = [r for r in RUNS if r["name"] == name][0]
+        d = tmp_path / name
+        d.mkdir()
+        _cli_check(t, str(d), {"DSKGPU_DEVICES": "all", "DSKGPU_SPLIT_MIN_BYTES": "1000"}, ('DATASET "1"',))
+
+
+@need_bins
+@pytest.mark.parametrize("name,env", [("c1_k31", {"DSKGPU_NB_PASSES": "3"}), ("c1_k63", {"DSKGPU_NB_PASSES": "2"}),
+                                      ("histo2d_c123_k31", {"DSKGPU_NB_PASSES": "2"}),
+                                      ("c1_k31", {"DSKGPU_NB_PASSES": "2", "DSKGPU_DEVICES": "0,0", "DSKGPU_SPLIT_MIN_BYTES": "1000"})])
+def test_cli_pass_loop(name, env, tmp_path):
+    """several passes over the input (a job whose records exceed HBM): dsk/solid/<pass * devices + device>, same k-mers"""
+    t = [r for r in RUNS if r["name"] == name][0]
+    stats = _cli_check(t, str(tmp_path), env, ('DATASET "1"',))
+    assert "nb_passes" in stats
+
+
+@need_bins
+def test_cli_abundance_min_auto_with_passes_and_devices(tmp_path):
+    for i, env in enumerate(({"DSKGPU_NB_PASSES": "2"}, {"DSKGPU_DEVICES": "0,0", "DSKGPU_SPLIT_MIN_BYTES": "1000"})):
+        t = AUTO[0]
+        d = tmp_path / str(i)
+        d.mkdir()
+        stats = _cli_check(t, str(d), env).splitlines()
+        j = [x for x, ln in enumerate(stats) if "cutoffs_auto" in ln][0]
+        assert [int(x) for x in stats[j + 1].split(":", 1)[1].split()] == t["cutoffs"]
+
+
+@need_bins
+def test_cli_file_larger_than_one_push_block(tmp_path):
+    """a 150 MB FASTA: the reader's double-buffered 64 MiB blocks are reused (dskgpu_push_sync before every refill); the
+    reference binary, when it is on the box, must produce the same dump"""
+    import numpy as np
+    import sys
+    sys.path.insert(0, ROOT)
+    from dsk_b200.synth import reads_fasta
+    buf, n, _ = reads_fasta(G=1_000_000, coverage=140, L=150, err=0.01, seed=5)
+    fa = str(tmp_path / "big.fa")
+    buf[:n].tofile(fa)
+    assert n > (140 << 20)
+    tmp = str(tmp_path)
+    a, b = os.path.join(tmp, "gpu_out"), os.path.join(tmp, "ref_out")
+    args = ["-file", fa, "-kmer-size", "31", "-abundance-min", "3", "-histo", "1", "-verbose", "0"]
+    run([DSK_GPU] + args + ["-out", a], tmp)
+    la, ha, _ = read_back(a + ".h5", tmp)
+    if os.path.exists(os.path.join(REFBIN, "dsk")):
+        run([os.path.join(REFBIN, "dsk")] + args + ["-out", b, "-out-tmp", tmp], tmp)
+        lb, hb, _ = read_back(b + ".h5", tmp)
+        assert la == lb and ha == hb
+        assert open(a + ".histo", "rb").read() == open(b + ".histo", "rb").read()
+    # ... and the same file through two contexts with real byte-range slices
+    c = os.path.join(tmp, "gpu2_out")
+    p = subprocess.run([DSK_GPU] + args + ["-out", c], cwd=tmp, capture_output=True, text=True, env=dict(os.environ, DSKGPU_DEVICES="0,0"))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    lc, hc, _ = read_back(c + ".h5", tmp)
+    assert la == lc and ha == hc

@@ -1,0 +1,181 @@
+"""Parity tests (-m gpu) of what round 2 added to the path: the pass loop (jobs whose records exceed HBM), the solid-set buffers
+sized from an estimate with an exact retry, the global-table groups that outgrow an estimated size, several contexts in one
+process (dskgpu_multi_finish: what the multi-GPU `dsk_gpu` CLI runs), and -- when the box has at least two GPUs -- the real
+multi-process exchange under torchrun.  Bit-exact against the oracle everywhere."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from dsk_b200 import SortingCountAlgorithm, BankBytes, BankAlbum, GpuCounter
+from dsk_b200.counter import multi_finish
+from dsk_b200.synth import reads_fasta, genome_codes, assembly_fasta
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sorted_pairs(keys, cnts):
+    order = np.lexsort((keys[:, 0], keys[:, -1])) if keys.shape[1] == 2 else np.argsort(keys[:, 0], kind="stable")
+    return keys[order], cnts[order]
+
+
+def assert_equals_oracle(keys, cnts, hist, ref, hist2d=None):
+    keys, cnts = sorted_pairs(keys, cnts)
+    lo, hi, rc = ref.solid_kmers()
+    assert len(cnts) == len(rc)
+    assert (keys[:, 0] == lo).all() and (cnts.astype(np.int64) == rc).all()
+    if keys.shape[1] == 2:
+        assert (keys[:, 1] == hi).all()
+    assert (hist == ref.hist).all()
+    if hist2d is not None:
+        assert (hist2d == ref.hist2d).all()
+
+
+def split_records(data, parts):
+    cuts = [0]
+    for i in range(1, parts):
+        j = data.find(b"\n>", len(data) * i // parts)
+        cuts.append(len(data) if j < 0 else j + 1)
+    cuts.append(len(data))
+    return [data[cuts[i]:cuts[i + 1]] for i in range(parts)]
+
+
+# ---------------------------------------------------------------- pass loop (K/SortingCountAlgorithm.cpp:678-689, :1086)
+@pytest.mark.parametrize("k,nb_passes", [(31, 2), (31, 3), (63, 3), (21, 5)])
+def test_pass_loop_union_equals_oracle(k, nb_passes):
+    buf, n, _ = reads_fasta(G=300_000, coverage=30, L=150, err=0.01, seed=900 + k)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], k, abundance_min=2)
+    sc = SortingCountAlgorithm(BankBytes(data), {"-kmer-size": k, "-abundance-min": "2"}, nb_passes=nb_passes).execute()
+    info = sc.getInfo()
+    assert info["kmers_nb_valid"] == ref.kmers_nb_valid                 # every pass sees the whole bank
+    assert info["kmers_nb_distinct"] == ref.nb_distinct                 # ... and counts a disjoint share of it
+    assert info["engine"]["kmers_in_pass"] == ref.kmers_nb_valid        # summed over the passes
+    keys, cnt = sc.getSolidCounts()
+    assert_equals_oracle(keys, cnt, sc.getHistogram()[0], ref)
+
+
+def test_pass_loop_with_histo2d_and_auto_cutoff():
+    g = genome_codes(150_000, seed=29)
+    asm = assembly_fasta(g)
+    buf, n, _ = reads_fasta(coverage=25, L=150, err=0.01, seed=29, genome=g)
+    reads = buf[:n].tobytes()
+    ref = oracle.count_files([asm, reads], 31, abundance_min=2, histo2d=True)
+    sc = SortingCountAlgorithm(BankAlbum([BankBytes(asm), BankBytes(reads)]), {"-kmer-size": 31, "-abundance-min": "2", "-histo2D": 1},
+                               nb_passes=3).execute()
+    keys, cnt = sc.getSolidCounts()
+    h1, h2 = sc.getHistogram()
+    assert_equals_oracle(keys, cnt, h1, ref, h2)
+    # -abundance-min auto: the cutoff comes from the histogram of ALL passes
+    ref = oracle.count_files([reads], 31, abundance_min=-1)
+    sc = SortingCountAlgorithm(BankBytes(reads), {"-kmer-size": 31, "-abundance-min": "auto"}, nb_passes=2).execute()
+    assert sc.getInfo()["cutoffs_auto"] == ref.cutoffs
+    keys, cnt = sc.getSolidCounts()
+    assert_equals_oracle(keys, cnt, sc.getHistogram()[0], ref)
+
+
+def test_set_pass_needs_an_empty_context():
+    from dsk_b200 import DskGpuError
+    buf, n, _ = reads_fasta(G=20_000, coverage=5, L=100, err=0.0, seed=1)
+    with GpuCounter(kmer_size=21) as e:
+        e.set_pass(1, 2)
+        e.push_bytes(buf[:n].tobytes())
+        with pytest.raises(DskGpuError) as ex:
+            e.set_pass(0, 2)
+        assert ex.value.code == -5
+        with pytest.raises(DskGpuError):
+            e.reset(); e.set_pass(2, 2)
+    lib = __import__("dsk_b200")._lib.lib()
+    assert lib.dskgpu_suggest_nb_passes(10**9, 31, 1, 0, 0) == 1
+    assert lib.dskgpu_suggest_nb_passes(72 * 10**9, 31, 1, 180 << 30, 0) >= 2          # BASELINE configs[2] on ONE GPU: passes
+    assert lib.dskgpu_suggest_nb_passes(72 * 10**9, 31, 8, 180 << 30, 0) == 1          # ... on eight: fits
+
+
+# ---------------------------------------------------------------- estimates that turn out wrong are answered, never fatal
+@pytest.mark.parametrize("k,mode", [(31, "auto"), (63, "auto"), (31, "hash"), (31, "sort")])
+def test_solid_buffers_too_small_are_regrown_to_the_exact_size(k, mode, monkeypatch):
+    monkeypatch.setenv("DSKGPU_TEST_SOLID_CAP", "1000")
+    buf, n, _ = reads_fasta(G=200_000, coverage=30, L=150, err=0.01, seed=41)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], k, abundance_min=2)
+    sc = SortingCountAlgorithm(BankBytes(data), {"-kmer-size": k, "-abundance-min": "2"}, count_mode=mode).execute()
+    assert sc.getInfo()["engine"]["nb_solid_regrows"] == 1
+    assert sc.getInfo()["kmers_nb_distinct"] == ref.nb_distinct
+    keys, cnt = sc.getSolidCounts()
+    assert_equals_oracle(keys, cnt, sc.getHistogram()[0], ref)
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_global_table_group_outgrowing_its_estimate_is_regrouped(k, monkeypatch):
+    # groups sized as if 2 % of the k-mers were distinct (they are ~35 %): every group overflows its table and must be redone
+    # in sub-groups sized for distinct = total -- the reference never fails here, neither does this path
+    monkeypatch.setenv("DSKGPU_TEST_HASH_RATIO", "0.02")
+    buf, n, _ = reads_fasta(G=300_000, coverage=30, L=150, err=0.01, seed=43)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], k, abundance_min=2)
+    sc = SortingCountAlgorithm(BankBytes(data), {"-kmer-size": k, "-abundance-min": "2"}, count_mode="hash", hash_log2_slots=15).execute()
+    st = sc.getInfo()["engine"]
+    assert st["nb_hash_regroups"] > 0
+    assert sc.getInfo()["kmers_nb_distinct"] == ref.nb_distinct
+    keys, cnt = sc.getSolidCounts()
+    assert_equals_oracle(keys, cnt, sc.getHistogram()[0], ref)
+
+
+# ---------------------------------------------------------------- several ranks in one process (dskgpu_multi_finish)
+def run_multi(devices, k, data, **kw):
+    W = len(devices)
+    ref = oracle.count_files([data], k, abundance_min=2)
+    engines = [GpuCounter(kmer_size=k, abundance_min=2, rank=r, world_size=W, device=devices[r], **kw) for r in range(W)]
+    try:
+        for e, piece in zip(engines, split_records(data, W)):
+            e.push_bytes(piece)
+        multi_finish(engines)
+        keys, cnts, hist, valid, distinct = [], [], np.zeros(10001, np.uint64), 0, 0
+        for e in engines:
+            kk, cc = e.solid()
+            keys.append(kk); cnts.append(cc)
+            hist += e.histogram()[0]
+            st = e.stats()
+            valid += st["kmers_nb_valid"]; distinct += st["kmers_nb_distinct"]
+        assert valid == ref.kmers_nb_valid and distinct == ref.nb_distinct
+        assert_equals_oracle(np.concatenate(keys), np.concatenate(cnts), hist, ref)
+    finally:
+        for e in engines:
+            e.close()
+
+
+@pytest.mark.parametrize("W,k,mode", [(2, 31, "auto"), (3, 63, "auto"), (4, 31, "hash")])
+def test_multi_finish_contexts_sharing_one_gpu(W, k, mode):
+    buf, n, _ = reads_fasta(G=300_000, coverage=30, L=150, err=0.01, seed=71)
+    run_multi([0] * W, k, buf[:n].tobytes(), count_mode=mode, hash_log2_slots=16)
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_multi_finish_across_real_gpus(k):
+    n = _ngpus()
+    if n < 2:
+        pytest.skip("needs at least two GPUs in the box")
+    buf, nb, _ = reads_fasta(G=1_000_000, coverage=30, L=150, err=0.01, seed=73)
+    run_multi(list(range(min(n, 4))), k, buf[:nb].tobytes())
+
+
+def test_multi_process_exchange_under_torchrun():
+    """tools/mgpu_check.py (one process per GPU, NCCL metadata + CUDA-IPC peer stores; union of the ranks against the oracle)"""
+    n = _ngpus()
+    if n < 2:
+        pytest.skip("needs at least two GPUs in the box")
+    w = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(w), "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(ROOT, "tools", "mgpu_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, MGPU_SHORT="1"))
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "MISMATCH" not in p.stdout

@@ -1,0 +1,26 @@
+#!/usr/bin/env bash
+# One parameterised runner for gpurun calls:  tools/run_gpu.sh <tag> <step> [<step> ...]
+# steps: pytest | bench | bench63 | ref | twin31 | twin63 | sanitize | launches | ncu | cli | big
+set -u
+TAG="${1:-r02}"; shift; OUT=gpurun_out/$TAG; mkdir -p "$OUT"
+for step in "$@"; do
+  case "$step" in
+    pytest)   timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_gpu.log"; tail -5 "$OUT/pytest_gpu.log" ;;
+    bench)    timeout 600 python bench.py > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json"; tail -3 "$OUT/bench_n1.err" ;;
+    benchq)   timeout 600 python bench.py --no-cpu-baseline > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json"; tail -3 "$OUT/bench_n1.err" ;;
+    bench63)  timeout 600 python bench.py --kmer-size 63 --no-cpu-baseline > "$OUT/bench_k63.json" 2> "$OUT/bench_k63.err"; tail -c 2000 "$OUT/bench_k63.json" ;;
+    ref)      timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/bench_reference_arm.json" 2> "$OUT/bench_reference_arm.err"; cat "$OUT/bench_reference_arm.json" ;;
+    twin31)   timeout 900 python tools/twin_check.py --kmer-size 31 > "$OUT/twin_k31.json" 2> "$OUT/twin_k31.err"; cat "$OUT/twin_k31.json"; tail -3 "$OUT/twin_k31.err" ;;
+    twin63)   timeout 900 python tools/twin_check.py --kmer-size 63 > "$OUT/twin_k63.json" 2> "$OUT/twin_k63.err"; cat "$OUT/twin_k63.json"; tail -3 "$OUT/twin_k63.err" ;;
+    sanitize) for tool in memcheck racecheck; do
+                timeout 900 compute-sanitizer --tool $tool --log-file "$OUT/sanitizer_${tool}_smoke.log" python __graft_entry__.py smoke > "$OUT/sanitizer_${tool}_smoke.out" 2>&1
+                echo "$tool smoke exit $?"; tail -3 "$OUT/sanitizer_${tool}_smoke.log"
+                timeout 1200 compute-sanitizer --tool $tool --log-file "$OUT/sanitizer_${tool}_split.log" python -m pytest tests/test_gpu_parity.py -x -q -k "tiny_smem_table_overflow_splits and (c1_k31 or c1_k63 or histo2d_k31) and 64" > "$OUT/sanitizer_${tool}_split.out" 2>&1
+                echo "$tool split exit $?"; tail -3 "$OUT/sanitizer_${tool}_split.log"; tail -2 "$OUT/sanitizer_${tool}_split.out"
+              done ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/launches_bench.log" 2>&1; echo "launches exit $?" ;;
+    ncu)      timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNELS:-k_}" -s "${NCU_SKIP:-60}" -c "${NCU_COUNT:-24}" -f -o "$OUT/ncu_full" python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/ncu_bench.log" 2>&1; echo "ncu exit $?"; ls -la "$OUT" ;;
+    cli)      timeout 900 bash tools/run_cli_check.sh "$OUT" ;;
+    *)        echo "unknown step $step" ;;
+  esac
+done
