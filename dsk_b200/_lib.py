@@ -10,7 +10,7 @@ MAX_BANKS = 16
 HISTO_LEN = 10001
 HISTO2D_DIM2 = 11
 NBINS = 65536
-NBINS_MAX = 1 << 20
+NBINS_MAX = 1 << 22
 
 ERR_NODEVICE = -6
 

@@ -21,6 +21,15 @@
 //
 // A partition whose distinct k-mers overflow the table is not an error: the CTA clears the table and redoes the
 // partition as two sub-passes that each take half of the k-mer hash space (recursively, up to 2^CS_MAX_SPLIT).
+//
+// Record staging (round 2): the records of a job are contiguous in HBM, so ONE elected thread brings them into a
+// shared-memory job buffer with a 1-D bulk copy (cp.async.bulk.shared::cluster.global + mbarrier complete_tx: the TMA
+// unit, no LDG -> register -> STS traffic on the LSU the probes compete for), and the copy for the NEXT job is issued
+// as soon as the last insert of the current one is over, so it lands under the sweep.  The next job id is claimed
+// (global atomic) at the top of the current job.  With the whole job in shared memory the work items are dealt
+// STATICALLY: a block scan over the records' item counts, then every warp takes an equal share of the items --
+// the insert phase no longer ends with most warps waiting at the barrier for the warp that drew the last chunk
+// (18.7 % of the stall samples of the round-1 kernel, profiles/r01y).
 #pragma once
 #include "kmer_bits.cuh"
 #include "superk.cuh"
@@ -47,9 +56,15 @@ constexpr int CS_MAX_SPLIT0 = 4;
 // bytes of dynamic shared memory for a table of `cap` slots (host + device agree through this one function):
 // table keys + counts, record staging [warps][32][RW], retry queue [warps][QCAP] keys + slots
 // nb = counts kept per slot (1, or one per bank when the processors need per-bank counts: -histo2D, solidity kinds)
+// records the shared-memory job buffer holds (a job with more records is streamed through it in slices); sized so that
+// the table and the buffer fill up together at the densities of 30-100x read sets (see stage_count / plan_target_kmers)
+template <int KW> DSK_HD u32 cs_bufrec() { return KW == 1 ? 2368u : 544u; }
 template <int KW> DSK_HD size_t cs_smem_bytes(u32 cap, int nb = 1)
 {
-    return (size_t)cap * (8 * KW + 4 * nb) + (size_t)CS_WARPS * 32 * 2 * KW * 8 + (size_t)CS_WARPS * CS_QCAP * (8 * KW + 4);
+    return (size_t)cap * (8 * KW + 4 * nb)                          // table: keys + counts
+         + (size_t)cs_bufrec<KW>() * (2 * KW * 8 + 2)               // job buffer: records + exclusive item prefix (u16)
+         + (size_t)CS_WARPS * CS_QCAP * (8 * KW + 4)                // retry queues
+         + 16;                                                      // mbarrier
 }
 constexpr int CS_H2_I1 = H2_SMEM_I1;           // -histo2D: bins (i1 < 64, any i2) are accumulated in shared memory
 constexpr int CS_MAX_BANKS = 4;                // per-bank counts beyond this go to the global-table path
@@ -107,6 +122,36 @@ __device__ __forceinline__ bool cs_probe(u32 keys_a, u32 slot, const Kmer<2>& ke
     return (olo == EMPTY && ohi == EMPTY) || (olo == key.w[0] && ohi == key.w[1]);
 }
 
+// the same probe split in two, so that the loads of several k-mers can be in flight together: cs_snap reads the slot,
+// cs_resolve decides from the snapshot (a complete foreign key is final; anything else is decided by the CAS)
+template <int KW> struct CsSnap { u64 w[KW]; };
+__device__ __forceinline__ CsSnap<1> cs_snap1(u32 keys_a, u32 slot) { CsSnap<1> s; s.w[0] = cs_lds64v(keys_a + slot * 8u); return s; }
+__device__ __forceinline__ CsSnap<2> cs_snap2(u32 keys_a, u32 slot)
+{
+    CsSnap<2> s;
+    asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(s.w[0]), "=l"(s.w[1]) : "r"(keys_a + slot * 16u) : "memory");
+    return s;
+}
+__device__ __forceinline__ bool cs_resolve(u32 keys_a, u32 slot, const Kmer<1>& key, const CsSnap<1>& sn)
+{
+    const u64 EMPTY = ~0ULL;
+    if (sn.w[0] == key.w[0]) return true;
+    if (sn.w[0] != EMPTY) return false;
+    const u64 old = cs_cas64(keys_a + slot * 8u, EMPTY, key.w[0]);
+    return old == EMPTY || old == key.w[0];
+}
+__device__ __forceinline__ bool cs_resolve(u32 keys_a, u32 slot, const Kmer<2>& key, const CsSnap<2>& sn)
+{
+    const u64 EMPTY = ~0ULL;
+    if (sn.w[0] == key.w[0] && sn.w[1] == key.w[1]) return true;
+    if (sn.w[0] != EMPTY && sn.w[1] != EMPTY) return false;
+    u64 olo, ohi;
+    asm volatile("{\n\t.reg .b128 c, s, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\t"
+                 "atom.shared.cas.b128 d, [%6], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                 : "=l"(olo), "=l"(ohi) : "l"(EMPTY), "l"(EMPTY), "l"(key.w[0]), "l"(key.w[1]), "r"(keys_a + slot * 16u) : "memory");
+    return (olo == EMPTY && ohi == EMPTY) || (olo == key.w[0] && ohi == key.w[1]);
+}
+
 // 32 bases of a record starting at base p (top bits first); RW words in registers, no dynamic indexing
 template <int RW>
 __device__ __forceinline__ u64 cs_window(const u64* r, int p)
@@ -116,6 +161,29 @@ __device__ __forceinline__ u64 cs_window(const u64* r, int p)
     if constexpr (RW == 2) { a = q ? r[1] : r[0]; b = q ? 0ULL : r[1]; }
     else { a = q == 0 ? r[0] : q == 1 ? r[1] : q == 2 ? r[2] : r[3]; b = q == 0 ? r[1] : q == 1 ? r[2] : q == 2 ? r[3] : 0ULL; }
     return o ? ((a << (2 * o)) | (b >> (64 - 2 * o))) : a;
+}
+
+// ---- mbarrier + 1-D bulk copy (TMA unit) -------------------------------------------------------------------------------
+__device__ __forceinline__ void cs_mbar_init(u32 mbar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// arms the barrier with the byte count of the copy that follows and issues the copy: global -> shared, completion by
+// complete_tx on the mbarrier (16-byte aligned addresses, size a multiple of 16)
+__device__ __forceinline__ void cs_bulk_load(u32 dst, const void* src, u32 bytes, u32 mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void cs_mbar_wait(u32 mbar, u32 parity)
+{
+    u32 ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
 }
 
 // MB = false: one count per k-mer (banks summed), solidity = abundance range [amin, amax] -- the dsk default.
@@ -133,18 +201,23 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                                                               const u32* __restrict__ bucket_n = nullptr, u32 slab = 0)
 {
     constexpr int RW = 2 * KW;
+    constexpr u32 BUFREC = KW == 1 ? 2368u : 544u;                                 // == cs_bufrec<KW>()
+    constexpr u32 RPT = (BUFREC + CS_THREADS - 1) / CS_THREADS;                   // records per thread in the prefix scan
     const u32 nb = MB ? (u32)nb_arg : 1u;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     u64* s_keys = reinterpret_cast<u64*>(s_dyn);                                   // [cap][KW]
     u32* s_counts = reinterpret_cast<u32*>(s_dyn + (size_t)cap * 8 * KW);          // [cap][nb]
-    u64* s_rec = reinterpret_cast<u64*>(s_dyn + (size_t)cap * (8 * KW + 4 * nb));  // [CS_WARPS][32][RW]   (cap % 4 == 0 keeps it 16-byte aligned)
-    u64* s_qkey = s_rec + (size_t)CS_WARPS * 32 * RW;                              // [CS_WARPS][CS_QCAP][KW]
+    u64* s_jrec = reinterpret_cast<u64*>(s_dyn + (size_t)cap * (8 * KW + 4 * nb)); // [BUFREC][RW]   (cap % 4 == 0 keeps it 16-byte aligned)
+    u16* s_pref = reinterpret_cast<u16*>(s_jrec + (size_t)BUFREC * RW);            // [BUFREC] exclusive prefix of the records' work items
+    u64* s_qkey = reinterpret_cast<u64*>(s_pref + BUFREC);                         // [CS_WARPS][CS_QCAP][KW]   (BUFREC % 4 == 0)
     u32* s_qslot = reinterpret_cast<u32*>(s_qkey + (size_t)CS_WARPS * CS_QCAP * KW);   // [CS_WARPS][CS_QCAP]
+    u64* s_mbar = reinterpret_cast<u64*>(s_qslot + (size_t)CS_WARPS * CS_QCAP);
     __shared__ u32 s_hist[HIST_SMEM_BINS];
     __shared__ u32 s_h2[MB ? 11 * CS_H2_I1 : 1];                                   // -histo2D bins with dim-1 index < CS_H2_I1, all 11 dim-2 rows
     __shared__ u32 s_wsum[CS_WARPS];
-    __shared__ u32 s_job, s_flag, s_chunk;
-    __shared__ unsigned long long s_base;
+    __shared__ u32 s_job, s_ovf;                                                   // s_ovf: overflow events so far (only ever incremented)
+    __shared__ unsigned long long s_base, s_drb;                                   // s_drb, s_dnrec, s_dsplit: descriptor of job s_job
+    __shared__ u32 s_dnrec, s_dsplit;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
@@ -153,13 +226,30 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
     for (u32 i = t; i < cap * nb; i += CS_THREADS) s_counts[i] = 0;
     for (int i = t; i < HIST_SMEM_BINS; i += CS_THREADS) s_hist[i] = 0;
     if constexpr (MB) for (int i = t; i < 11 * CS_H2_I1; i += CS_THREADS) s_h2[i] = 0;
-    if (t == 0) s_flag = 0;
-    u32 n1 = 0, n2 = 0, ndist = 0, nsplit = 0;
-    u64* my_rec = s_rec + (size_t)warp * 32 * RW;
+    u32 n1 = 0, n2 = 0, ndist = 0, nsplit = 0, ovf_seen = 0, mb_parity = 0;
     u64* my_qkey = s_qkey + (size_t)warp * CS_QCAP * KW;
     u32* my_qslot = s_qslot + (size_t)warp * CS_QCAP;
-    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
     const u32 keys_a = cs_saddr(s_keys), counts_a = cs_saddr(s_counts);
+    const u32 jrec_a = cs_saddr(s_jrec), mbar_a = cs_saddr(s_mbar);
+    const unsigned char* grec = reinterpret_cast<const unsigned char*>(recs);
+
+    // thread 0: claims a job, publishes its descriptor and starts the bulk copy of its first slice of records
+    auto publish = [&](u32 job) {
+        s_job = job;
+        if (job < njobs) {
+            if constexpr (KEYS) { s_drb = (u64)job * slab; s_dnrec = min(bucket_n[job], slab); s_dsplit = 0; }
+            else {
+                const SmemJob d = jobs[job];
+                s_drb = d.rec_begin; s_dnrec = d.nrec; s_dsplit = min(d.split0, (u32)CS_MAX_SPLIT0);
+                cs_bulk_load(jrec_a, grec + d.rec_begin * (u64)(RW * 8), min(d.nrec, BUFREC) * (u32)(RW * 8), mbar_a);
+            }
+        }
+    };
+    if (t == 0) {
+        s_ovf = 0;
+        if constexpr (!KEYS) cs_mbar_init(mbar_a, 1);
+        publish(atomicAdd(work_counter, 1u));
+    }
 
     // resolve everything in this warp's retry queue (all lanes active, full probe sequences)
     auto drain = [&](u32 qn) {
@@ -174,39 +264,40 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 if constexpr (MB) { bank = slot >> 16; slot &= 0xFFFFu; }             // cap <= 16384
                 bool ok = false;
                 for (int p = 0; p < CS_MAXPROBE && !ok; p++) { ok = cs_probe(keys_a, slot, key); if (!ok) slot = (slot + 1 == cap) ? 0u : slot + 1; }
-                if (ok) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u); else s_flag = 1u;
+                if (ok) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u); else atomicAdd(&s_ovf, 1u);
             }
         }
         __syncwarp();
     };
 
     for (;;) {
-        __syncthreads();                                                           // table clean, s_job free
-        if (t == 0) s_job = atomicAdd(work_counter, 1u);
-        __syncthreads();
+        __syncthreads();                                                           // table clean, descriptor of s_job published
         const u32 job = s_job;
         if (job >= njobs) break;
-        const u64 rb = KEYS ? (u64)job * slab : jobs[job].rec_begin;
-        const u32 nrec = KEYS ? min(bucket_n[job], slab) : jobs[job].nrec, nchunks = (nrec + CS_CHUNK - 1) / CS_CHUNK;
+        const u64 rb = s_drb;
+        const u32 nrec = s_dnrec;
+        const u32 nslices = (nrec + BUFREC - 1) / BUFREC;
+        // the next job is claimed now (thread 0 keeps the ticket in a register: nobody waits for the atomic until the
+        // records of this job are no longer needed)
+        u32 next_job = 0;
+        if (t == 0) next_job = atomicAdd(work_counter, 1u);
+        u32 buf_state = 1;                                                         // 1: slice 0 of this job is on its way (publish); 2: resident; 0: neither
 
         // depth-first over (split level, residue) work items; uniform across the CTA
         u32 stack[CS_MAX_SPLIT + 2 + (1 << CS_MAX_SPLIT0)];
         int sp = 0;
         {
-            const u32 l0 = KEYS ? 0u : min(jobs[job].split0, (u32)CS_MAX_SPLIT0);
+            const u32 l0 = s_dsplit;
             for (u32 r = (1u << l0); r-- > 0;) stack[sp++] = (l0 << 16) | r;
         }
         while (sp > 0) {
             const u32 item = stack[--sp];
             const u32 lvl = item >> 16, res = item & 0xFFFFu, smask = (1u << lvl) - 1u;
-            if (t == 0) s_chunk = CS_WARPS;                                        // chunks beyond the first one per warp are dealt dynamically
-            __syncthreads();
 
             // ---- insert: flat keys (one per thread and iteration; the probe loop runs to the end, loads stay <= 52 %) ---------
             if constexpr (KEYS) {
                 const u64* kp = recs + rb * KW;
                 for (u32 i0 = 0; i0 < nrec; i0 += CS_THREADS) {
-                    if (*reinterpret_cast<volatile u32*>(&s_flag)) break;
                     const u32 i = i0 + (u32)t;
                     if (i >= nrec) continue;
                     Kmer<KW> c;
@@ -219,101 +310,163 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                     u32 slot = __umulhi(h, cap);
                     bool ok = false;
                     for (int p = 0; p < CS_MAXPROBE && !ok; p++) { ok = cs_probe(keys_a, slot, c); if (!ok) slot = (slot + 1 == cap) ? 0u : slot + 1; }
-                    if (ok) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u); else s_flag = 1u;
+                    if (ok) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u); else atomicAdd(&s_ovf, 1u);
                 }
+                __syncthreads();
             }
-            // ---- insert: warps expand chunks of 32 records -----------------------------------------------------------
-            u32 qn = 0;
-            for (u32 chunk = warp; !KEYS && chunk < nchunks;) {
-                if (*reinterpret_cast<volatile u32*>(&s_flag)) break;              // somebody overflowed: the pass is void
-                const u32 ri = chunk * CS_CHUNK + lane;
-                u32 nk = 0;
-                if (lane < CS_CHUNK && ri < nrec) {
-                    const u64 i = rb + ri;
-                    ulonglong2* dst = reinterpret_cast<ulonglong2*>(my_rec + lane * RW);
-                    if constexpr (RW == 2) { const ulonglong2 v = __ldg(src + i); dst[0] = v; nk = (u32)(v.y >> 8) & 0xFFu; }
-                    else { const ulonglong2 v = __ldg(src + 2 * i), u = __ldg(src + 2 * i + 1); dst[0] = v; dst[1] = u; nk = (u32)(u.y >> 8) & 0xFFu; }
+            // ---- insert: super-k-mer records, one slice of <= BUFREC records in the job buffer at a time ----------------------
+            for (u32 sl = 0; !KEYS && sl < nslices; sl++) {
+                const u32 s0 = sl * BUFREC, n = min(BUFREC, nrec - s0);
+                if (!(sl == 0 && buf_state == 2)) {
+                    // (everybody is past the barrier that ended the previous slice: the buffer is free)
+                    if (!(sl == 0 && buf_state == 1) && t == 0) cs_bulk_load(jrec_a, grec + (rb + s0) * (u64)(RW * 8), n * (u32)(RW * 8), mbar_a);
+                    cs_mbar_wait(mbar_a, mb_parity); mb_parity ^= 1u;
                 }
-                // next chunk of this warp (claimed early so the atomic's latency hides under the work)
-                u32 next = 0;
-                if (lane == 0) next = atomicAdd(&s_chunk, 1u);
-                const u32 ni = (nk + CS_Q - 1) / CS_Q;                             // work items of my record
-                u32 inc = ni;
+                buf_state = (nslices == 1) ? 2u : 0u;                              // a one-slice job stays in the buffer for its sub-passes
+
+                // work items of CS_Q k-mers: exclusive prefix over the records of the slice (block scan), then equal shares per warp
+                u32 my_ni[RPT], tsum = 0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
-                const u32 total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-                const u32 exc = inc - ni;
-                next = __shfl_sync(0xFFFFFFFFu, next, 0);
-                __syncwarp();
-                for (u32 t0 = 0; t0 < total; t0 += 32) {
-                    const u32 x = t0 + lane;
-                    // owner record of item x: number of lanes whose inclusive prefix is <= x (binary search by shuffles)
-                    u32 r = 0;
+                for (u32 j = 0; j < RPT; j++) {
+                    const u32 r = (u32)t * RPT + j;
+                    u32 ni = 0;
+                    if (r < n) { const u32 nk = (u32)(s_jrec[(size_t)r * RW + (RW - 1)] >> 8) & 0xFFu; ni = (nk + CS_Q - 1) / CS_Q; }
+                    my_ni[j] = ni; tsum += ni;
+                }
+                u32 tinc = tsum;
 #pragma unroll
-                    for (int step = 16; step; step >>= 1) { const u32 v = __shfl_sync(0xFFFFFFFFu, inc, (r + step - 1) & 31); if (v <= x) r += step; }
-                    const u32 ex_r = __shfl_sync(0xFFFFFFFFu, exc, r & 31);
-                    const u32 nk_r = __shfl_sync(0xFFFFFFFFu, nk, r & 31);
-                    int cnt = 0, j0 = 0;
-                    u32 bank = 0;
-                    u64 rw[RW];
-                    Kmer<KW> f, rc;
-                    u64 nextb = 0;
-                    if (x < total) {
-                        j0 = (int)(x - ex_r) * CS_Q;
-                        cnt = min((int)nk_r - j0, CS_Q);
-                        const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(my_rec + r * RW);
-                        const ulonglong2 a = rp[0]; rw[0] = a.x; rw[1] = a.y;
-                        if constexpr (RW == 4) { const ulonglong2 b = rp[1]; rw[2] = b.x; rw[3] = b.y; }
-                        if constexpr (MB) bank = (u32)rw[RW - 1] & 0xFFu;
-                        if constexpr (KW == 1) f.w[0] = cs_window<RW>(rw, j0) >> (64 - 2 * k);
-                        else { const u64 hw[2] = {cs_window<RW>(rw, j0), cs_window<RW>(rw, j0 + 32)}; f = rec_first_kmer2(hw, k); }
-                        rc = kmer_revcomp(f, k);
-                        nextb = cs_window<RW>(rw, j0 + k);                         // the CS_Q-1 bases that follow the first k-mer
+                for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, tinc, d); if (lane >= d) tinc += o; }
+                if (lane == 31) s_wsum[warp] = tinc;
+                __syncthreads();
+                // prefix over the 32 warp totals: every warp scans them with shuffles (one LDS + 5 steps instead of 32 LDS + adds)
+                u32 wpre, I;
+                {
+                    u32 ws = s_wsum[lane], wi = ws;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += o; }
+                    I = __shfl_sync(0xFFFFFFFFu, wi, 31);
+                    wpre = __shfl_sync(0xFFFFFFFFu, wi - ws, warp);
+                }
+                {
+                    u32 run = wpre + tinc - tsum;
+#pragma unroll
+                    for (u32 j = 0; j < RPT; j++) { const u32 r = (u32)t * RPT + j; if (r < n) s_pref[r] = (u16)run; run += my_ni[j]; }
+                }
+                __syncthreads();
+
+                const u32 lo = (I * (u32)warp) >> 5, hi = (I * (u32)(warp + 1)) >> 5;        // this warp's items
+                u32 qn = 0;
+                if (lo < hi) {
+                    // record owning item `lo`: the largest r with pref[r] <= lo (32-ary search by ballots; pref[0] = 0)
+                    u32 rcur;
+                    {
+                        u32 base = 0, len = n;
+                        while (len > 32) {
+                            const u32 stride = (len + 31) >> 5, off = (u32)lane * stride;
+                            const bool le = off < len && (u32)s_pref[base + off] <= lo;       // true for a prefix of the lanes
+                            const u32 j = (u32)__popc(__ballot_sync(0xFFFFFFFFu, le)) - 1u;
+                            base += j * stride; len = min(stride, len - j * stride);
+                        }
+                        const bool le = (u32)lane < len && (u32)s_pref[base + lane] <= lo;
+                        rcur = base + (u32)__popc(__ballot_sync(0xFFFFFFFFu, le)) - 1u;
                     }
+                    // 32 consecutive items per iteration, whatever records they belong to: 32 items span at most 32 records, so
+                    // the owner of item x is found among the prefixes of records rcur .. rcur + 31 (one value per lane)
+                    for (u32 x0 = lo; x0 < hi; x0 += 32) {
+                        const u32 x = x0 + (u32)lane;
+                        const u32 rl = rcur + (u32)lane;
+                        const u32 pl = rl < n ? (u32)s_pref[rl] : 0xFFFFFFFFu;
+                        u32 ro = 0;                                                    // largest lane l with pref[rcur + l] <= x
 #pragma unroll
-                    for (int u = 0; u < CS_Q; u++) {
-                        bool pending = false, found = false; u32 slot = 0; Kmer<KW> c;
-                        if (u < cnt) {
-                            if (u) { kmer_roll(f, rc, (int)(nextb >> 62), k); nextb <<= 2; }
-                            c = kmer_canonical(f, rc);
-                            const u32 h = cs_hash(c);
-                            if (((h >> 8) & smask) == res) {
-                                slot = __umulhi(h, cap);
-                                found = cs_probe(keys_a, slot, c);
-                                if (!found) { slot = (slot + 1 == cap) ? 0u : slot + 1; found = cs_probe(keys_a, slot, c); }
-                                if (!found) { pending = true; slot = (slot + 1 == cap) ? 0u : slot + 1; }
+                        for (int step = 16; step; step >>= 1) { const u32 v = __shfl_sync(0xFFFFFFFFu, pl, (ro + step) & 31); if (v <= x) ro += step; }
+                        const u32 ex_r = __shfl_sync(0xFFFFFFFFu, pl, ro);
+                        u64 rw[RW];
+                        {
+                            const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(s_jrec + (size_t)(rcur + ro) * RW);
+                            const ulonglong2 a = rp[0]; rw[0] = a.x; rw[1] = a.y;
+                            if constexpr (RW == 4) { const ulonglong2 b = rp[1]; rw[2] = b.x; rw[3] = b.y; }
+                        }
+                        const u32 nk_r = (u32)(rw[RW - 1] >> 8) & 0xFFu;
+                        const int j0 = (int)(x - ex_r) * CS_Q;
+                        const int cnt = x < hi ? min((int)nk_r - j0, CS_Q) : 0;
+                        // record owning the first item of the next iteration (lane 31 knows: its own record, or the one after it)
+                        rcur = __shfl_sync(0xFFFFFFFFu, rcur + ro + ((x + 1u >= ex_r + (nk_r + CS_Q - 1) / CS_Q) ? 1u : 0u), 31);
+                        u32 bank = 0;
+                        Kmer<KW> f, rc;
+                        u64 nextb = 0;
+                        if (cnt > 0) {
+                            if constexpr (MB) bank = (u32)rw[RW - 1] & 0xFFu;
+                            if constexpr (KW == 1) f.w[0] = cs_window<RW>(rw, j0) >> (64 - 2 * k);
+                            else { const u64 hw[2] = {cs_window<RW>(rw, j0), cs_window<RW>(rw, j0 + 32)}; f = rec_first_kmer2(hw, k); }
+                            rc = kmer_revcomp(f, k);
+                            nextb = cs_window<RW>(rw, j0 + k);                         // the CS_Q-1 bases that follow the first k-mer
+                        }
+                        // the CS_Q k-mers of the item: canonical forms, hashes and home slots first, then all the first probes are
+                        // issued together (their shared-memory latencies overlap), then every k-mer is resolved
+                        // (128-bit keys: two at a time, the register budget of a 1024-thread CTA is 64)
+                        constexpr int PH = KW == 1 ? CS_Q : 2;
+#pragma unroll
+                        for (int g = 0; g < CS_Q; g += PH) {
+                            Kmer<KW> cc[PH]; u32 sl0[PH]; u32 actm = 0;
+#pragma unroll
+                            for (int v = 0; v < PH; v++) {
+                                const int u = g + v;
+                                sl0[v] = 0;
+                                if (u < cnt) {
+                                    if (u) { kmer_roll(f, rc, (int)(nextb >> 62), k); nextb <<= 2; }
+                                    cc[v] = kmer_canonical(f, rc);
+                                    const u32 h = cs_hash(cc[v]);
+                                    if (((h >> 8) & smask) == res) { actm |= 1u << v; sl0[v] = __umulhi(h, cap); }
+                                }
+                            }
+                            CsSnap<KW> sn[PH];
+#pragma unroll
+                            for (int v = 0; v < PH; v++) {
+                                if constexpr (KW == 1) sn[v] = cs_snap1(keys_a, sl0[v]); else sn[v] = cs_snap2(keys_a, sl0[v]);   // (slot 0 for the idle ones: harmless)
+                            }
+#pragma unroll
+                            for (int v = 0; v < PH; v++) {
+                                bool pending = false, found = false; u32 slot = sl0[v];
+                                if ((actm >> v) & 1u) {
+                                    found = cs_resolve(keys_a, slot, cc[v], sn[v]);
+                                    if (!found) { slot = (slot + 1 == cap) ? 0u : slot + 1; found = cs_probe(keys_a, slot, cc[v]); }
+                                    if (!found) { pending = true; slot = (slot + 1 == cap) ? 0u : slot + 1; }
+                                }
+                                const u32 pm = __ballot_sync(0xFFFFFFFFu, pending);         // (also the reconvergence point of the probes)
+                                if (found) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u);
+                                if (pm) {
+                                    if (pending) {
+                                        const u32 pos = qn + (u32)__popc(pm & lt_mask);
+#pragma unroll
+                                        for (int q = 0; q < KW; q++) my_qkey[pos * KW + q] = cc[v].w[q];
+                                        my_qslot[pos] = MB ? (slot | (bank << 16)) : slot;
+                                    }
+                                    qn += (u32)__popc(pm);
+                                    if (qn > CS_QCAP - 32) { drain(qn); qn = 0; }
+                                }
                             }
                         }
-                        const u32 pm = __ballot_sync(0xFFFFFFFFu, pending);         // (also the reconvergence point of the probes)
-                        if (found) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u);
-                        if (pm) {
-                            if (pending) {
-                                const u32 pos = qn + (u32)__popc(pm & lt_mask);
-#pragma unroll
-                                for (int q = 0; q < KW; q++) my_qkey[pos * KW + q] = c.w[q];
-                                my_qslot[pos] = MB ? (slot | (bank << 16)) : slot;
-                            }
-                            qn += (u32)__popc(pm);
-                            if (qn > CS_QCAP - 32) { drain(qn); qn = 0; }
-                        }
                     }
                 }
-                __syncwarp();
-                chunk = next;
+                if (qn) drain(qn);
+                __syncthreads();                                                   // inserts of the slice done, job buffer free
             }
-            if (qn) drain(qn);
-            __syncthreads();
-            const u32 overflowed = s_flag;
-            __syncthreads();
+            const u32 ovf_now = *reinterpret_cast<volatile u32*>(&s_ovf);          // stable: nobody inserts until after the next barriers
+            const bool overflowed = ovf_now != ovf_seen;
+            ovf_seen = ovf_now;
             if (overflowed) {
                 // clear, then split this item in two (or give up: reported, never silent)
                 for (u32 i = t; i < cap * KW; i += CS_THREADS) s_keys[i] = EMPTY;
                 for (u32 i = t; i < cap * nb; i += CS_THREADS) s_counts[i] = 0;
-                if (t == 0) s_flag = 0;
                 if (lvl >= (u32)CS_MAX_SPLIT) { if (t == 0) atomicAdd(&ctr->smem_failed, 1u); }
                 else { stack[sp++] = ((lvl + 1) << 16) | (res + (1u << lvl)); stack[sp++] = ((lvl + 1) << 16) | res; nsplit++; }
+                if (KEYS || sp == 0) __syncthreads();                              // (the record path has barriers before its next insert)
+                if (sp == 0 && t == 0) publish(next_job);                          // gave up on the last item: move on
                 continue;
             }
+            // the records of this job are no longer needed after its last work item: the next job's first slice is copied
+            // into the buffer while the table is swept
+            if (sp == 0 && t == 0) publish(next_job);
 
             // ---- sweep: CountProcessor chain over the table, compaction of the solid pairs, clear ---------------------
             // a slot is occupied iff its count is non-zero (a claim is always followed by its increment), so the scan reads
@@ -358,13 +511,11 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const u32 c = cv[q];
-                        if (c == 0u) continue;
-                        ndist++;
-                        if (c == 1u) n1++;
-                        else if (c == 2u) n2++;
-                        else { const u32 bin = histo_bin((int32_t)c); if (bin) { if (bin < HIST_SMEM_BINS) atomicAdd(&s_hist[bin], 1u); else atomicAdd(&g_hist[bin], 1ULL); } }
+                        // counts 0, 1 and 2 -- nine slots out of ten -- are handled without a branch
+                        ndist += (c != 0u) ? 1u : 0u; n1 += (c == 1u) ? 1u : 0u; n2 += (c == 2u) ? 1u : 0u;
+                        if (c > 2u) { const u32 bin = histo_bin((int32_t)c); if (bin) { if (bin < HIST_SMEM_BINS) atomicAdd(&s_hist[bin], 1u); else atomicAdd(&g_hist[bin], 1ULL); } }
                         const long long sum = (long long)(int32_t)c;
-                        if (amin <= sum && sum <= amax) solidm |= 1u << (4 * v + q);
+                        solidm |= (c != 0u && amin <= sum && sum <= amax) ? (1u << (4 * v + q)) : 0u;
                     }
                 }
             }
@@ -374,11 +525,37 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
             for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
             if (lane == 31) s_wsum[warp] = inc;
             __syncthreads();
-            u32 wpre = 0, tot = 0;
+            u32 wpre, tot;
+            {
+                u32 ws = s_wsum[lane], wi = ws;
 #pragma unroll
-            for (int w = 0; w < CS_WARPS; w++) { const u32 x = s_wsum[w]; if (w < warp) wpre += x; tot += x; }
+                for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += o; }
+                tot = __shfl_sync(0xFFFFFFFFu, wi, 31);
+                wpre = __shfl_sync(0xFFFFFFFFu, wi - ws, warp);
+            }
+            // one bump of the global cursor per job; while it is in flight every thread clears the slot groups it scanned that
+            // hold nothing solid (nobody else reads or writes them in this phase)
+            if (tot && t == 0) s_base = atomicAdd(&ctr->solid_n, (unsigned long long)tot);
+            if constexpr (MB) {
+                u32 v = 0;
+                for (u32 sl = t; sl < cap; sl += CS_THREADS, v++) {
+                    if ((solidm >> v) & 1u) continue;
+#pragma unroll
+                    for (int q = 0; q < KW; q++) s_keys[sl * KW + q] = EMPTY;
+                    for (u32 b = 0; b < nb; b++) s_counts[sl * nb + b] = 0;
+                }
+            } else {
+                ulonglong2* k2 = reinterpret_cast<ulonglong2*>(s_keys);
+                uint4* c4 = reinterpret_cast<uint4*>(s_counts);
+                int v = 0;
+                for (u32 g = t; g < cap / 4; g += CS_THREADS, v++) {
+                    if ((solidm >> (4 * v)) & 0xFu) continue;
+#pragma unroll
+                    for (int q = 0; q < 2 * KW; q++) k2[2 * KW * g + q] = make_ulonglong2(EMPTY, EMPTY);
+                    c4[g] = make_uint4(0, 0, 0, 0);
+                }
+            }
             if (tot) {
-                if (t == 0) s_base = atomicAdd(&ctr->solid_n, (unsigned long long)tot);
                 __syncthreads();
                 u64 pos = s_base + wpre + inc - n;
                 u32 m = solidm;
@@ -392,24 +569,29 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                     } else atomicExch(&ctr->overflow, 2u);
                     pos++;
                 }
-            }
-            if constexpr (MB) {
-                for (u32 sl = t; sl < cap; sl += CS_THREADS) {
+                // ... and the groups that held solid slots
+                if constexpr (MB) {
+                    u32 mm = solidm;
+                    while (mm) {
+                        const int b = __ffs((int)mm) - 1; mm &= mm - 1;
+                        const u32 sl = (u32)b * CS_THREADS + (u32)t;
 #pragma unroll
-                    for (int q = 0; q < KW; q++) s_keys[sl * KW + q] = EMPTY;
-                    for (u32 b = 0; b < nb; b++) s_counts[sl * nb + b] = 0;
-                }
-            } else
-            {
-                // every thread clears exactly the slot groups it scanned (nobody else reads or writes them in this phase)
-                ulonglong2* k2 = reinterpret_cast<ulonglong2*>(s_keys);
-                uint4* c4 = reinterpret_cast<uint4*>(s_counts);
-                for (u32 g = t; g < cap / 4; g += CS_THREADS) {
+                        for (int q = 0; q < KW; q++) s_keys[sl * KW + q] = EMPTY;
+                        for (u32 bb = 0; bb < nb; bb++) s_counts[sl * nb + bb] = 0;
+                    }
+                } else {
+                    ulonglong2* k2 = reinterpret_cast<ulonglong2*>(s_keys);
+                    uint4* c4 = reinterpret_cast<uint4*>(s_counts);
+                    int v = 0;
+                    for (u32 g = t; g < cap / 4; g += CS_THREADS, v++) {
+                        if (!((solidm >> (4 * v)) & 0xFu)) continue;
 #pragma unroll
-                    for (int q = 0; q < 2 * KW; q++) k2[2 * KW * g + q] = make_ulonglong2(EMPTY, EMPTY);
-                    c4[g] = make_uint4(0, 0, 0, 0);
+                        for (int q = 0; q < 2 * KW; q++) k2[2 * KW * g + q] = make_ulonglong2(EMPTY, EMPTY);
+                        c4[g] = make_uint4(0, 0, 0, 0);
+                    }
                 }
             }
+            if (sp > 0) __syncthreads();                                           // table clean before the next sub-pass inserts (KEYS path; cheap otherwise)
         }
     }
 

@@ -79,7 +79,7 @@ struct dskgpu_ctx {
     u64 sample_solid = 0;
     u64 bytes_pushed = 0;                            // raw input bytes so far (sizes the density sample before the totals are known)
     bool sample_queued = false; u64 sample_nkm = 0, sample_distinct = 0; double sample_wmult = 0.0;   // wmult: occurrence-weighted multiplicity (this rank's sample)
-    bool global_set = false; u64 g_total_kmers = 0; double density = 1.0; bool density_known = false;
+    bool global_set = false; u64 g_total_kmers = 0, g_total_recs = 0; double density = 1.0; bool density_known = false;
     int bin_level = NBINS_LOG2; bool hist_fetched = false;
     DevBuf sendbuf;
     // exchange v2 (bulk segments): records in local partition order, per-partition offsets on the device, pinned global histogram
@@ -90,6 +90,11 @@ struct dskgpu_ctx {
     std::vector<u64> x_need;                         // records every rank receives
     u64 recv_cap_recs = 0;
     dskgpu_stats st;
+    // pinned staging for the per-finish tables that go to the device (a cudaMemcpyAsync from pageable memory is a synchronous,
+    // staged copy; with ~1 M partitions these tables are 8-16 MB each)
+    struct HostBuf { void* p = nullptr; size_t cap = 0; };
+    HostBuf hb_jobs, hb_dst, hb_off;
+    std::vector<u64> v_off; std::vector<char> v_big; std::vector<SmemJob> v_jobs, v_jobs2;
     // timing
     std::vector<cudaEvent_t> evpool; size_t ev_used = 0;
     struct Span { cudaEvent_t a, b; int kind; };
@@ -115,6 +120,19 @@ static void trace(const char* what)
     auto now = std::chrono::steady_clock::now();
     if (!what) { g_t0 = now; return; }
     fprintf(stderr, "[dskgpu] %-28s +%8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - g_t0).count());
+}
+
+static int ensure_host(dskgpu_ctx* ctx, dskgpu_ctx::HostBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    CK(cudaStreamSynchronize(ctx->stream));                         // a copy out of the old buffer may still be queued
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr; b.cap = 0;
+    const size_t ncap = (bytes + bytes / 2 + 4095) & ~(size_t)4095;
+    cudaError_t e = cudaMallocHost(&b.p, ncap);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); b.p = nullptr; FAIL(DSKGPU_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", ncap, cudaGetErrorString(e)); }
+    b.cap = ncap;
+    return 0;
 }
 
 static int ensure(dskgpu_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false, size_t keep_bytes = 0)
@@ -331,6 +349,9 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (ctx->h_ghist) cudaFreeHost(ctx->h_ghist);
     if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
     if (ctx->h_svals) cudaFreeHost(ctx->h_svals);
+    if (ctx->hb_jobs.p) cudaFreeHost(ctx->hb_jobs.p);
+    if (ctx->hb_dst.p) cudaFreeHost(ctx->hb_dst.p);
+    if (ctx->hb_off.p) cudaFreeHost(ctx->hb_off.p);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -796,9 +817,9 @@ static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers);
 constexpr int SMEM_MAX_SPLIT0_DEFAULT = 1;
 
 // whole-job figures every rank plans from: k-mer total and density sample.  Picks the bin level.
-static void set_global(dskgpu_ctx* ctx, u64 g_kmers, u64 g_sample_kmers, u64 g_sample_distinct)
+static void set_global(dskgpu_ctx* ctx, u64 g_kmers, u64 g_recs, u64 g_sample_kmers, u64 g_sample_distinct)
 {
-    ctx->g_total_kmers = g_kmers;
+    ctx->g_total_kmers = g_kmers; ctx->g_total_recs = g_recs;
     ctx->density_known = g_sample_kmers >= 4096;
     ctx->density = ctx->density_known ? std::min(1.0, std::max(0.01, (double)g_sample_distinct / (double)g_sample_kmers)) : 1.0;
     const u64 T = plan_target_kmers(ctx, g_kmers);
@@ -839,7 +860,7 @@ static int stage_totals(dskgpu_ctx* ctx)
 static int fetch_local_bin_hist(dskgpu_ctx* ctx)
 {
     if (ctx->hist_fetched) return 0;
-    if (!ctx->global_set) set_global(ctx, ctx->local_nkm, ctx->sample_nkm, ctx->sample_distinct);
+    if (!ctx->global_set) set_global(ctx, ctx->local_nkm, ctx->local_nrec, ctx->sample_nkm, ctx->sample_distinct);
     const int shift = NBINS_FINE_LOG2 - ctx->bin_level;
     const u32 nb = 1u << ctx->bin_level;
     const void* src = ctx->bin_hist.p;
@@ -889,8 +910,14 @@ static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers)
         // the slots -> 4.03 ms; 125 % -> 4.36 ms; beyond 65 % overflows (= split passes) appear)
         const char* e = getenv("DSKGPU_SMEM_LOAD_PCT");
         const double load = (e ? (double)std::max(5, atoi(e)) : 52.0) / 100.0;
-        const double t = (double)ctx->smem_cap * load / ctx->density;
-        return (u64)std::min(std::max(t, 64.0), (double)ctx->smem_cap * 4.0);
+        double t = std::min((double)ctx->smem_cap * load / ctx->density, (double)ctx->smem_cap * 4.0);
+        // ... and whose records fit the shared-memory job buffer in one slice (cs_bufrec): the whole job is then staged by one
+        // bulk copy that runs under the previous job's sweep
+        if (ctx->g_total_recs > 0 && ctx->cfg.count_mode == DSKGPU_COUNT_AUTO && ctx->cfg.smem_table_slots <= 0) {
+            const double avg_nk = (double)ctx->g_total_kmers / (double)ctx->g_total_recs;
+            t = std::min(t, (double)(ctx->KW == 1 ? cs_bufrec<1>() : cs_bufrec<2>()) * avg_nk * 0.93);
+        }
+        return (u64)std::max(t, 64.0);
     }
     const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 23;
     return std::max<u64>(((u64)1 << log2s) * 6 / 10 / 4, 4096);
@@ -964,9 +991,11 @@ static int stage_scatter(dskgpu_ctx* ctx, const std::vector<u64*>& dst)
     if (ctx->local_nrec == 0) return 0;
     SpanGuard g(ctx, SPAN_PART);
     CK(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)P * 8, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dstbase.p, dst.data(), (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->bin2part.p, ctx->h_bin2part.data(), ctx->h_bin2part.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));          // dst may be a temporary
+    { int rc = ensure_host(ctx, ctx->hb_dst, (size_t)P * 8 + ctx->h_bin2part.size() * 4); if (rc) return rc; }
+    memcpy(ctx->hb_dst.p, dst.data(), (size_t)P * 8);
+    memcpy((char*)ctx->hb_dst.p + (size_t)P * 8, ctx->h_bin2part.data(), ctx->h_bin2part.size() * 4);
+    CK(cudaMemcpyAsync(ctx->dstbase.p, ctx->hb_dst.p, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->bin2part.p, (char*)ctx->hb_dst.p + (size_t)P * 8, ctx->h_bin2part.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     const unsigned sb = (unsigned)std::min<u64>((ctx->local_nrec + SC_THREADS - 1) / SC_THREADS, (u64)ctx->num_sms * 32);
     k_part_scatter<KW><<<sb, SC_THREADS, 0, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, ctx->local_nrec,
                                                           (const u32*)ctx->bin2part.p, NBINS_FINE_LOG2 - ctx->bin_level, (u64* const*)ctx->dstbase.p,
@@ -1107,9 +1136,9 @@ static int stage_count_once(dskgpu_ctx* ctx, const u64* recs, const std::vector<
         const double fit = smem_fit_kmers(ctx);                                             // k-mers one pass can take
         const u64 smem_max = smem_max_kmers(ctx);
         const unsigned max_split0 = (unsigned)smem_max_split0(ctx);
-        std::vector<SmemJob> jobs;
-        std::vector<u64> off(np + 1, 0);
-        std::vector<char> big(np, 0);
+        std::vector<SmemJob>& jobs = ctx->v_jobs; jobs.clear();
+        std::vector<u64>& off = ctx->v_off; off.assign(np + 1, 0);
+        std::vector<char>& big = ctx->v_big; big.assign(np, 0);
         for (size_t i = 0; i < np; i++) {
             off[i + 1] = off[i] + prec[i];
             if (prec[i] == 0) continue;
@@ -1123,12 +1152,21 @@ static int stage_count_once(dskgpu_ctx* ctx, const u64* recs, const std::vector<
         trace("jobs built");
         SpanGuard g(ctx, SPAN_COUNT);
         if (!jobs.empty()) {
-            std::sort(jobs.begin(), jobs.end(), [](const SmemJob& a, const SmemJob& b) {                               // longest first
-                return ((u64)a.nrec << a.split0) > ((u64)b.nrec << b.split0); });
+            // longest first (the CTAs pull jobs off a queue: the tail of the launch is one job long).  A full sort is what a few
+            // thousand jobs get; beyond that the host cost of sorting ~1 M jobs (tens of ms) exceeds anything the order can
+            // win, and the pre-split jobs -- the long ones -- simply go first, the rest in partition order.
+            if (jobs.size() <= 65536)
+                std::sort(jobs.begin(), jobs.end(), [](const SmemJob& a, const SmemJob& b) { return ((u64)a.nrec << a.split0) > ((u64)b.nrec << b.split0); });
+            else {
+                std::vector<SmemJob>& t = ctx->v_jobs2; t.clear(); t.reserve(jobs.size());
+                for (int s0 = (int)max_split0; s0 >= 0; s0--) for (const SmemJob& j : jobs) if ((int)j.split0 == s0) t.push_back(j);
+                jobs.swap(t);
+            }
             if ((rc = ensure(ctx, ctx->jobs, jobs.size() * sizeof(SmemJob)))) return rc;
-            CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), jobs.size() * sizeof(SmemJob), cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = ensure_host(ctx, ctx->hb_jobs, jobs.size() * sizeof(SmemJob)))) return rc;
+            memcpy(ctx->hb_jobs.p, jobs.data(), jobs.size() * sizeof(SmemJob));
+            CK(cudaMemcpyAsync(ctx->jobs.p, ctx->hb_jobs.p, jobs.size() * sizeof(SmemJob), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));      // jobs is a temporary
             const unsigned grid = (unsigned)std::min<size_t>(jobs.size(), (size_t)ctx->num_sms * CS_CTAS_PER_SM);
             const size_t dyn = cs_smem_bytes<KW>(ctx->smem_cap, ctx->NB);
             cudaEvent_t a = get_event(ctx), b = get_event(ctx);
@@ -1334,7 +1372,7 @@ int dskgpu_xchg_set_global(dskgpu_ctx* ctx, const uint64_t* global4, int* log2_b
     if (!ctx || !global4) return DSKGPU_ERR_ARG;
     use_device(ctx);
     if (!ctx->totals_done) FAIL(DSKGPU_ERR_STATE, "xchg_set_global before xchg_prepare");
-    set_global(ctx, global4[0], global4[2], global4[3]);
+    set_global(ctx, global4[0], global4[1], global4[2], global4[3]);
     if (log2_bins) *log2_bins = ctx->bin_level;
     return DSKGPU_OK;
 }
@@ -1476,8 +1514,9 @@ int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist, uint64_t* loca
         for (u32 p = me; p < P; p += W) { ctx->owned_recs.push_back(ctx->g_part_recs[p]); ctx->owned_kmers.push_back(ctx->g_part_kmers[p]); }
         ctx->my_nrec_owned = ctx->x_need[me];
         if ((rc = ensure(ctx, ctx->xoff, hoff.size() * 8))) return rc;
-        CK(cudaMemcpyAsync(ctx->xoff.p, hoff.data(), hoff.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));                    // hoff is a temporary
+        if ((rc = ensure_host(ctx, ctx->hb_off, hoff.size() * 8))) return rc;
+        memcpy(ctx->hb_off.p, hoff.data(), hoff.size() * 8);
+        CK(cudaMemcpyAsync(ctx->xoff.p, ctx->hb_off.p, hoff.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
     const u32 P = ctx->nparts;
     if (nparts) *nparts = P;

@@ -136,11 +136,11 @@ DSK_HD u32 mmer_value(u32 x, int m)
 
 // minimizer -> bin (the role of Repartitor::operator(), K/PartiInfo.hpp:323; any deterministic map is legal --
 // SURVEY.md appendix C).  Records are histogrammed into 2^NBINS_FINE_LOG2 fine bins while they are produced.  At finish
-// the histogram is folded to the level the job needs (2^16 bins for the 400 M k-mer configuration, up to 2^20 for
+// the histogram is folded to the level the job needs (2^16 bins for the 400 M k-mer configuration, up to 2^22 for
 // multi-G k-mer jobs: level = what keeps the average bin well under one shared-memory table) and the host packs
 // consecutive bins of that level into partitions of the size the counting kernel wants (balanced on exact counts,
 // the job the reference gives to its sampled LPT table, K/PartiInfo.cpp:48-106).
-constexpr int NBINS_FINE_LOG2 = 20;
+constexpr int NBINS_FINE_LOG2 = 22;
 constexpr u32 NBINS_FINE = 1u << NBINS_FINE_LOG2;
 constexpr int NBINS_LOG2 = 16;                               // coarsest level (DSKGPU_NBINS)
 constexpr u32 NBINS = 1u << NBINS_LOG2;

@@ -28,7 +28,7 @@ extern "C" {
 #define DSKGPU_MAX_MINIMIZER 14             /* -minimizer-size is clipped to this (32-bit m-mer arithmetic) */
 #define DSKGPU_MAX_KMER      63             /* KSIZE_LIST "32 64": k<32 -> 64-bit keys, k<64 -> 128-bit */
 #define DSKGPU_NBINS         65536          /* minimizer bins packed into partitions at finish: the coarsest level ... */
-#define DSKGPU_NBINS_MAX     (1u << 20)     /* ... and the finest (multi-G k-mer jobs); the level is picked from the job size */
+#define DSKGPU_NBINS_MAX     (1u << 22)     /* ... and the finest (multi-G k-mer jobs); the level is picked from the job size */
 
 /* error codes */
 enum {
@@ -216,7 +216,7 @@ int  dskgpu_abi_version(void);
  * One context per rank (one process per GPU).  Partition p is owned by rank p % world_size.  After all pushes:
  *   0. xchg_prepare             -> this rank's {k-mers, records, density-sample k-mers, density-sample distinct}; all-reduce
  *                                  (sum) the four numbers out of band, hand the sums to xchg_set_global: every rank then
- *                                  agrees on the bin level (2^16 .. 2^20 bins) and on the partition size
+ *                                  agrees on the bin level (2^16 .. 2^22 bins) and on the partition size
  *   1. xchg_bin_hist            -> this rank's (records, k-mers) per minimizer bin; all-reduce (sum) it out of band
  *                                  (torch.distributed / NCCL): every rank then plans the same partitions
  *   2. xchg_part_counts         -> per-partition record / k-mer counts of this rank; all-gather them

@@ -6,6 +6,7 @@ TAG="${1:-r02}"; shift; OUT=gpurun_out/$TAG; mkdir -p "$OUT"
 for step in "$@"; do
   case "$step" in
     pynew)    timeout 1500 python -m pytest tests/test_gpu_round2.py tests/test_cli_dropin.py -x -q > "$OUT/pytest_new.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_new.log"; tail -15 "$OUT/pytest_new.log" ;;
+    pycount)  timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "reference_runs or tiny_smem or synthetic or histo2d or heavy or multi_rank or forced or regrown or pass_loop" > "$OUT/pytest_count.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_count.log"; tail -4 "$OUT/pytest_count.log" ;;
     pytest)   timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_gpu.log"; tail -5 "$OUT/pytest_gpu.log" ;;
     bench)    timeout 600 python bench.py > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json"; tail -3 "$OUT/bench_n1.err" ;;
     benchq)   timeout 600 python bench.py --no-cpu-baseline > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json"; tail -3 "$OUT/bench_n1.err" ;;
