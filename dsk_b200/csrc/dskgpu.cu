@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dskgpu.h"
@@ -112,6 +113,7 @@ static inline void use_device(const dskgpu_ctx* ctx) { int d = -1; if (cudaGetDe
 
 // DSKGPU_TRACE=1: host wall-clock of the stages of push / finish on stderr (tuning aid)
 #include <chrono>
+#include <unistd.h>
 static bool g_trace = getenv("DSKGPU_TRACE") != nullptr;
 static std::chrono::steady_clock::time_point g_t0;
 static void trace(const char* what)
@@ -119,7 +121,7 @@ static void trace(const char* what)
     if (!g_trace) return;
     auto now = std::chrono::steady_clock::now();
     if (!what) { g_t0 = now; return; }
-    fprintf(stderr, "[dskgpu] %-28s +%8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - g_t0).count());
+    fprintf(stderr, "[dskgpu pid %d] %-48s +%8.3f ms\n", (int)getpid(), what, std::chrono::duration<double, std::milli>(now - g_t0).count());
 }
 
 static int ensure_host(dskgpu_ctx* ctx, dskgpu_ctx::HostBuf& b, size_t bytes)
@@ -934,19 +936,30 @@ static void plan_partitions_host(dskgpu_ctx* ctx, const unsigned long long* gh /
     for (u32 b = 0; b < NB_; b++) total += gk[b];
     const u64 T = plan_target_kmers(ctx, total);
     ctx->h_bin2part.resize(NB_);
-    ctx->g_part_kmers.clear(); ctx->g_part_recs.clear(); ctx->h_part_recs.clear(); ctx->h_part_kmers.clear();
     u32* b2p = ctx->h_bin2part.data();
-    u32 P = 0; u64 acc = 0, gr = 0, ar = 0, ak = 0;
-    for (u32 b = 0; b < NB_; b++) {
-        const u64 km = gk[b];
-        if (acc > 0 && acc + km > T) {
-            ctx->g_part_kmers.push_back(acc); ctx->g_part_recs.push_back(gr); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
-            P++; acc = gr = ar = ak = 0;
+    // two passes (the plan of a 72 G k-mer job packs 4 M bins into ~4 M partitions: no push_back growth, no re-reads):
+    // 1. bin -> partition (the greedy rule: a partition is closed when the next bin would take it beyond T)
+    u32 P = 0;
+    {
+        u64 acc = 0;
+        for (u32 b = 0; b < NB_; b++) {
+            const u64 km = gk[b];
+            if (acc > 0 && acc + km > T) { P++; acc = 0; }
+            b2p[b] = P; acc += km;
         }
-        b2p[b] = P; acc += km; gr += gh[b]; ar += lr[b]; ak += lk[b];
+        P += 1;
     }
-    ctx->g_part_kmers.push_back(acc); ctx->g_part_recs.push_back(gr); ctx->h_part_recs.push_back(ar); ctx->h_part_kmers.push_back(ak);
-    P += 1;
+    // 2. per-partition sums, written by index
+    ctx->g_part_kmers.assign(P, 0); ctx->g_part_recs.assign(P, 0); ctx->h_part_recs.assign(P, 0); ctx->h_part_kmers.assign(P, 0);
+    {
+        u64* pgk = ctx->g_part_kmers.data(); u64* pgr = ctx->g_part_recs.data(); u64* plr = ctx->h_part_recs.data(); u64* plk = ctx->h_part_kmers.data();
+        auto fold = [&](const unsigned long long* src, u64* dst) { for (u32 b = 0; b < NB_; b++) dst[b2p[b]] += src[b]; };
+        if (NB_ >= (1u << 19)) {                               // one host thread per array (memory-bound, no sharing between them)
+            std::thread t1(fold, gk, pgk), t2(fold, gh, pgr), t3(fold, lr, plr);
+            fold(lk, plk);
+            t1.join(); t2.join(); t3.join();
+        } else { fold(gk, pgk); fold(gh, pgr); fold(lr, plr); fold(lk, plk); }
+    }
     if (use_smem_path(ctx) && ctx->cfg.count_mode == DSKGPU_COUNT_AUTO) {
         // partitions beyond the reach of the shared-memory path are renumbered to the end (heaviest first, so that
         // p % world_size spreads them evenly): the global-table path then sees one contiguous run of records on every
@@ -1501,10 +1514,13 @@ int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist, uint64_t* loca
     if (!ctx->hist_fetched) FAIL(DSKGPU_ERR_STATE, "xchg2_plan before xchg2_hist");
     const u32 W = (u32)ctx->cfg.world_size, me = (u32)ctx->cfg.rank;
     if (ctx->nparts == 0) {
+        trace(nullptr);
         if (!ctx->h_ghist) CK(cudaMallocHost((void**)&ctx->h_ghist, sizeof(unsigned long long) * 2 * NBINS_FINE));
         CK(cudaMemcpyAsync(ctx->h_ghist, d_global_hist, sizeof(unsigned long long) * ((size_t)2 << ctx->bin_level), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        trace("xchg2_plan: global hist on host (all-reduce done)");
         int rc = plan_partitions(ctx, ctx->h_ghist); if (rc) return rc;
+        trace("xchg2_plan: planned");
         const u32 P = ctx->nparts;
         // receive-buffer layout: owned partitions in increasing id; x_need[r] = records rank r receives
         ctx->x_need.assign(W, 0);
@@ -1517,6 +1533,7 @@ int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist, uint64_t* loca
         if ((rc = ensure_host(ctx, ctx->hb_off, hoff.size() * 8))) return rc;
         memcpy(ctx->hb_off.p, hoff.data(), hoff.size() * 8);
         CK(cudaMemcpyAsync(ctx->xoff.p, ctx->hb_off.p, hoff.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        trace("xchg2_plan: layout tables queued");
     }
     const u32 P = ctx->nparts;
     if (nparts) *nparts = P;

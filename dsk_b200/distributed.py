@@ -53,7 +53,7 @@ def distributed_finish(eng, dist, device):
     import sys
     import time
     import torch
-    tr = os.environ.get("DSKGPU_TRACE_XCHG") and dist.get_rank() == 0
+    tr = os.environ.get("DSKGPU_TRACE_XCHG") and (dist.get_rank() == 0 or os.environ.get("DSKGPU_TRACE_XCHG") == "all")
     marks = [("start", time.perf_counter())]
 
     def mark(name):
@@ -119,7 +119,7 @@ def distributed_finish(eng, dist, device):
     mark("finish (count + order)")
     if tr:
         for (_, a), (name, b) in zip(marks, marks[1:]):
-            sys.stderr.write("[xchg] %-32s +%8.3f ms\n" % (name, 1e3 * (b - a)))
+            sys.stderr.write("[xchg r%d] %-32s +%8.3f ms\n" % (dist.get_rank(), name, 1e3 * (b - a)))
     return M
 
 
