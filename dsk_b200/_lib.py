@@ -52,10 +52,10 @@ SYMBOLS = [
     "dskgpu_recount", "dskgpu_bank_histograms",
     "dskgpu_get_stats", "dskgpu_reset", "dskgpu_destroy", "dskgpu_host_alloc", "dskgpu_host_free", "dskgpu_strerror",
     "dskgpu_last_error", "dskgpu_device_count", "dskgpu_abi_version",
-    "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_bin_hist", "dskgpu_xchg_part_counts", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
+    "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_hist", "dskgpu_xchg_counts", "dskgpu_xchg_ensure_recv", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
     "dskgpu_xchg_open_peer", "dskgpu_xchg_set_peers", "dskgpu_xchg_scatter", "dskgpu_xchg_sync", "dskgpu_xchg_layout", "dskgpu_record_bytes",
     "dskgpu_set_pass", "dskgpu_push_sync", "dskgpu_suggest_nb_passes", "dskgpu_xchg_close_peer", "dskgpu_multi_finish",
-    "dskgpu_xchg2_hist", "dskgpu_xchg2_plan", "dskgpu_xchg2_ensure_recv", "dskgpu_xchg2_scatter",
+    "dskgpu_debug_plan",
     "dskgpu_selftest_scan", "dskgpu_selftest_minimizers", "dskgpu_selftest_superkmers", "dskgpu_suggest_minimizer_size", "dskgpu_selftest_wide_kmers", "dskgpu_selftest_plan", "dskgpu_selftest_wide_superkmers",
 ]
 
@@ -105,19 +105,18 @@ def lib():
     L.dskgpu_xchg_local_totals.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     L.dskgpu_xchg_prepare.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_set_global.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int)]
-    L.dskgpu_xchg_bin_hist.argtypes = [C.c_void_p, C.c_void_p]
-    L.dskgpu_xchg_part_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_uint32)]
-    L.dskgpu_xchg_plan.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg_hist.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg_plan.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint32), P(C.c_uint32), C.c_void_p]
+    L.dskgpu_xchg_counts.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg_ensure_recv.argtypes = [C.c_void_p, C.c_uint64]
+    L.dskgpu_debug_plan.argtypes = [C.c_void_p, P(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.dskgpu_debug_plan.restype = C.c_int64
     L.dskgpu_xchg_recv_buffer.argtypes = [C.c_void_p, P(C.c_void_p), P(C.c_size_t)]
     L.dskgpu_xchg_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_open_peer.argtypes = [C.c_void_p, C.c_void_p, P(C.c_void_p)]
     L.dskgpu_xchg_set_peers.argtypes = [C.c_void_p, C.c_void_p]
-    L.dskgpu_xchg_scatter.argtypes = [C.c_void_p]
+    L.dskgpu_xchg_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_sync.argtypes = [C.c_void_p]
-    L.dskgpu_xchg2_hist.argtypes = [C.c_void_p, C.c_void_p]
-    L.dskgpu_xchg2_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_uint32)]
-    L.dskgpu_xchg2_ensure_recv.argtypes = [C.c_void_p, C.c_uint64]
-    L.dskgpu_xchg2_scatter.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_layout.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.dskgpu_record_bytes.argtypes = [C.c_void_p]
     L.dskgpu_selftest_scan.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]

@@ -195,27 +195,28 @@ def _xchg_methods():
         self._bin_level = lvl.value
         return lvl.value
 
-    def xchg_bin_hist(self):
-        h = np.zeros(2 << self._bin_level, dtype=np.uint64)          # xchg_set_global comes first
-        self._check(self.L.dskgpu_xchg_bin_hist(self.h, h.ctypes.data))
-        return h
+    def xchg_hist(self, d_out):
+        """this rank's bin histogram [2 << level] u64 -> device buffer of the caller (all-reduce it in place)"""
+        self._check(self.L.dskgpu_xchg_hist(self.h, C.c_void_p(d_out)))
 
-    def xchg_part_counts(self, global_hist):
-        gh = np.ascontiguousarray(global_hist, dtype=np.uint64)
-        P = C.c_uint32()
-        self._check(self.L.dskgpu_xchg_part_counts(self.h, gh.ctypes.data, None, C.byref(P)))
-        counts = np.zeros(2 * P.value, dtype=np.uint64)
-        self._check(self.L.dskgpu_xchg_part_counts(self.h, gh.ctypes.data, counts.ctypes.data, C.byref(P)))
-        return counts
+    def xchg_plan(self, d_global_hist):
+        """device planner; returns (P, PW, need_records[W])"""
+        P, PW = C.c_uint32(), C.c_uint32()
+        need = np.zeros(self.cfg.world_size, dtype=np.uint64)
+        self._check(self.L.dskgpu_xchg_plan(self.h, C.c_void_p(d_global_hist), C.byref(P), C.byref(PW), need.ctypes.data))
+        return P.value, PW.value, need
 
-    def xchg_plan(self, all_counts):
-        a = np.ascontiguousarray(all_counts, dtype=np.uint64)
-        self._check(self.L.dskgpu_xchg_plan(self.h, a.ctypes.data))
+    def xchg_counts(self, d_out):
+        """[W][PW] records per partition grouped by owner, then [W] chunk sizes -> device buffer of the caller"""
+        self._check(self.L.dskgpu_xchg_counts(self.h, C.c_void_p(d_out)))
+
+    def xchg_ensure_recv(self, capacity_records):
+        self._check(self.L.dskgpu_xchg_ensure_recv(self.h, int(capacity_records)))
 
     def xchg_recv_buffer(self):
         p, n = C.c_void_p(), C.c_size_t()
         self._check(self.L.dskgpu_xchg_recv_buffer(self.h, C.byref(p), C.byref(n)))
-        return p.value or 0, n.value
+        return p.value, n.value
 
     def xchg_ipc_handle(self):
         buf = (C.c_ubyte * 64)()
@@ -228,39 +229,32 @@ def _xchg_methods():
         self._check(self.L.dskgpu_xchg_open_peer(self.h, hb, C.byref(p)))
         return p.value
 
+    def xchg_close_peer(self, ptr):
+        self._check(self.L.dskgpu_xchg_close_peer(self.h, C.c_void_p(ptr)))
+
     def xchg_set_peers(self, ptrs):
-        arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(x) if x else 0) for x in ptrs])
+        arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(p) for p in ptrs])
         self._check(self.L.dskgpu_xchg_set_peers(self.h, arr))
 
-    def xchg_scatter(self):
-        self._check(self.L.dskgpu_xchg_scatter(self.h))
+    def xchg_scatter(self, d_recv_counts, d_send_matrix):
+        self._check(self.L.dskgpu_xchg_scatter(self.h, C.c_void_p(d_recv_counts), C.c_void_p(d_send_matrix)))
 
     def xchg_sync(self):
         self._check(self.L.dskgpu_xchg_sync(self.h))
 
-    def xchg2_hist(self, d_out):
-        """copies this rank's bin histogram ([2 << level] u64) into the caller's device buffer (stream-ordered)"""
-        self._check(self.L.dskgpu_xchg2_hist(self.h, C.c_void_p(d_out)))
+    def debug_plan(self):
+        """the plan the DEVICE derived: (level, bin2part, part_kmers, part_recs, part_local_recs)"""
+        lvl = C.c_int()
+        cap = (1 << 22) + 16
+        pk = np.zeros(cap, np.uint64); pr = np.zeros(cap, np.uint64); pl = np.zeros(cap, np.uint64)
+        b2p = np.zeros(1 << 22, np.uint32)
+        P = self.L.dskgpu_debug_plan(self.h, C.byref(lvl), b2p.ctypes.data, pk.ctypes.data, pr.ctypes.data, pl.ctypes.data, cap)
+        if P < 0:
+            self._check(int(P))
+        return lvl.value, b2p[:1 << lvl.value].copy(), pk[:P].copy(), pr[:P].copy(), pl[:P].copy()
 
-    def xchg2_plan(self, d_global_hist):
-        """-> (local records per partition [P], records every rank receives [W])"""
-        P = C.c_uint32()
-        need = np.zeros(self.cfg.world_size, dtype=np.uint64)
-        cnt = np.zeros((1 << self._bin_level) + self.cfg.world_size, dtype=np.uint64)      # P <= bins (+ padding to the world size)
-        self._check(self.L.dskgpu_xchg2_plan(self.h, C.c_void_p(d_global_hist), cnt.ctypes.data, need.ctypes.data, C.byref(P)))
-        return cnt[:P.value], need
-
-    def xchg2_ensure_recv(self, capacity_records):
-        self._check(self.L.dskgpu_xchg2_ensure_recv(self.h, int(capacity_records)))
-
-    def xchg2_scatter(self, d_matrix):
-        self._check(self.L.dskgpu_xchg2_scatter(self.h, C.c_void_p(d_matrix)))
-
-    for f in (xchg2_hist, xchg2_plan, xchg2_ensure_recv, xchg2_scatter):
-        setattr(GpuCounter, f.__name__, f)
-
-    for f in (xchg_local_totals, xchg_prepare, xchg_set_global, xchg_bin_hist, xchg_part_counts, xchg_plan, xchg_recv_buffer, xchg_ipc_handle, xchg_open_peer, xchg_set_peers,
-              xchg_scatter, xchg_sync):
+    for f in (xchg_local_totals, xchg_prepare, xchg_set_global, xchg_hist, xchg_plan, xchg_counts, xchg_ensure_recv, xchg_recv_buffer, xchg_ipc_handle,
+              xchg_open_peer, xchg_close_peer, xchg_set_peers, xchg_scatter, xchg_sync, debug_plan):
         setattr(GpuCounter, f.__name__, f)
 
 

@@ -34,6 +34,7 @@
 #include "kmer_bits.cuh"
 #include "superk.cuh"
 #include "count.cuh"
+#include "plan.cuh"
 
 namespace dsk {
 
@@ -48,9 +49,13 @@ constexpr int CS_MAX_SPLIT = 10;               // up to 1024 sub-passes before t
 constexpr int CS_Q = 4;                        // k-mers per work item
 constexpr int CS_QCAP = 64;                    // retry queue entries per warp
 
-// split0: the job starts as 2^split0 sub-passes (the host knows the partition's k-mers and the sampled density, so a
-// partition that cannot fit the table is never tried in one pass first)
-struct SmemJob { unsigned long long rec_begin; unsigned int nrec; unsigned int split0; };
+// A job is one owned partition: job j of this rank is the partition at position qbase + j of the q-ordered tables
+// (plan.cuh).  Its records are W segments, one per rank that parsed reads (segment s of job j = X[s * PW + j + 1] -
+// X[s * PW + j] records at tab->segptr[s] + X[s * PW + j] * record bytes: the sender-major receive layout; W = 1 on one GPU).
+// Nothing about the jobs is built on the host: the kernel reads the planner's device tables.
+// The job starts as 2^split0 sub-passes, derived from the partition's whole-job k-mers (gk_q) and `fit`, the k-mers one pass
+// takes at the sampled density -- a partition that cannot fit the table is never tried in one pass first.
+struct CsSegs { const XchgTab* tab; const u64* X; const u64* gk_q; u32 W, PW, qbase; float fit; u32 max_split0; };
 constexpr int CS_MAX_SPLIT0 = 4;
 
 // bytes of dynamic shared memory for a table of `cap` slots (host + device agree through this one function):
@@ -169,13 +174,17 @@ __device__ __forceinline__ void cs_mbar_init(u32 mbar, u32 count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// arms the barrier with the byte count of the copy that follows and issues the copy: global -> shared, completion by
-// complete_tx on the mbarrier (16-byte aligned addresses, size a multiple of 16)
-__device__ __forceinline__ void cs_bulk_load(u32 dst, const void* src, u32 bytes, u32 mbar)
+// cs_mbar_expect arms the barrier with the byte count of ALL the copies of one slice (one arrival per phase); cs_bulk_copy
+// issues one of them: global -> shared, completion by complete_tx on the mbarrier (16-byte aligned addresses, size a
+// multiple of 16)
+__device__ __forceinline__ void cs_mbar_expect(u32 mbar, u32 bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cs_bulk_copy(u32 dst, u64 src_addr, u32 bytes, u32 mbar)
+{
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+                 :: "r"(dst), "l"(src_addr), "r"(bytes), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void cs_mbar_wait(u32 mbar, u32 parity)
 {
@@ -189,11 +198,11 @@ __device__ __forceinline__ void cs_mbar_wait(u32 mbar, u32 parity)
 // MB = false: one count per k-mer (banks summed), solidity = abundance range [amin, amax] -- the dsk default.
 // MB = true : `nb` counts per slot (the record's bank byte picks the column); the sweep runs the whole CountProcessor
 //             chain of count.cuh (`process_counts`: per-bank solidity kinds, -histo2D, per-bank histograms) on them.
-// KEYS = false: a job is a partition of super-k-mer records (jobs[]).
+// KEYS = false: a job is a partition of super-k-mer records (segs).
 // KEYS = true : a job is a hash bucket of flat canonical k-mers written by k_expand_bucket (count.cuh): job j reads
-//               min(bucket_n[j], slab) keys at recs + j * slab * KW; `jobs` is unused.
+//               min(bucket_n[j], slab) keys at recs + j * slab * KW; `segs` is unused.
 template <int KW, bool MB, bool KEYS = false>
-__global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const u64* __restrict__ recs, const SmemJob* __restrict__ jobs, u32 njobs,
+__global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const u64* __restrict__ recs, const CsSegs segs, u32 njobs,
                                                               int k, u32 cap, long long amin, long long amax,
                                                               u64* __restrict__ out_keys, u32* __restrict__ out_vals, u64 out_cap,
                                                               unsigned long long* __restrict__ g_hist, Counters* ctr, u32* work_counter,
@@ -218,6 +227,8 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
     __shared__ u32 s_job, s_ovf;                                                   // s_ovf: overflow events so far (only ever incremented)
     __shared__ unsigned long long s_base, s_drb;                                   // s_drb, s_dnrec, s_dsplit: descriptor of job s_job
     __shared__ u32 s_dnrec, s_dsplit;
+    __shared__ unsigned long long s_segsrc[PLAN_MAXW];                             // byte address of the job's segment s
+    __shared__ u32 s_segpre[PLAN_MAXW + 1];                                        // records of the segments before s (thread 0 only)
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
@@ -231,17 +242,34 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
     u32* my_qslot = s_qslot + (size_t)warp * CS_QCAP;
     const u32 keys_a = cs_saddr(s_keys), counts_a = cs_saddr(s_counts);
     const u32 jrec_a = cs_saddr(s_jrec), mbar_a = cs_saddr(s_mbar);
-    const unsigned char* grec = reinterpret_cast<const unsigned char*>(recs);
 
+    // thread 0: records [s0, s0 + n) of the published job (its segments taken as one sequence) -> job buffer, one bulk copy
+    // per segment the slice overlaps
+    auto load_slice = [&](u32 s0, u32 n) {
+        cs_mbar_expect(mbar_a, n * (u32)(RW * 8));
+        for (u32 s = 0; s < segs.W; s++) {
+            const u32 lo = max(s0, s_segpre[s]), hi = min(s0 + n, s_segpre[s + 1]);
+            if (lo < hi) cs_bulk_copy(jrec_a + (lo - s0) * (u32)(RW * 8), s_segsrc[s] + (u64)(lo - s_segpre[s]) * (u64)(RW * 8), (hi - lo) * (u32)(RW * 8), mbar_a);
+        }
+    };
     // thread 0: claims a job, publishes its descriptor and starts the bulk copy of its first slice of records
     auto publish = [&](u32 job) {
         s_job = job;
         if (job < njobs) {
             if constexpr (KEYS) { s_drb = (u64)job * slab; s_dnrec = min(bucket_n[job], slab); s_dsplit = 0; }
             else {
-                const SmemJob d = jobs[job];
-                s_drb = d.rec_begin; s_dnrec = d.nrec; s_dsplit = min(d.split0, (u32)CS_MAX_SPLIT0);
-                cs_bulk_load(jrec_a, grec + d.rec_begin * (u64)(RW * 8), min(d.nrec, BUFREC) * (u32)(RW * 8), mbar_a);
+                u32 tot = 0;
+                for (u32 s = 0; s < segs.W; s++) {
+                    const u64 a = segs.X[(u64)s * segs.PW + job], b = segs.X[(u64)s * segs.PW + job + 1];
+                    s_segsrc[s] = segs.tab->segptr[s] + a * (u64)(RW * 8);
+                    s_segpre[s] = tot; tot += (u32)(b - a);
+                }
+                s_segpre[segs.W] = tot;
+                const float km = (float)segs.gk_q[(u64)segs.qbase + job];
+                u32 sp0 = 0;
+                while (sp0 < segs.max_split0 && km > segs.fit * (float)(1u << sp0)) sp0++;
+                s_dnrec = tot; s_dsplit = sp0;
+                if (tot) load_slice(0, min(tot, BUFREC));
             }
         }
     };
@@ -281,6 +309,11 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
         // records of this job are no longer needed)
         u32 next_job = 0;
         if (t == 0) next_job = atomicAdd(work_counter, 1u);
+        if (nrec == 0) {                                                           // an empty partition (uniform branch: nothing was copied, the table is clean)
+            __syncthreads();                                                       // everybody has read the descriptor
+            if (t == 0) publish(next_job);
+            continue;
+        }
         u32 buf_state = 1;                                                         // 1: slice 0 of this job is on its way (publish); 2: resident; 0: neither
 
         // depth-first over (split level, residue) work items; uniform across the CTA
@@ -319,7 +352,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 const u32 s0 = sl * BUFREC, n = min(BUFREC, nrec - s0);
                 if (!(sl == 0 && buf_state == 2)) {
                     // (everybody is past the barrier that ended the previous slice: the buffer is free)
-                    if (!(sl == 0 && buf_state == 1) && t == 0) cs_bulk_load(jrec_a, grec + (rb + s0) * (u64)(RW * 8), n * (u32)(RW * 8), mbar_a);
+                    if (!(sl == 0 && buf_state == 1) && t == 0) { if constexpr (!KEYS) load_slice(s0, n); }
                     cs_mbar_wait(mbar_a, mb_parity); mb_parity ^= 1u;
                 }
                 buf_state = (nslices == 1) ? 2u : 0u;                              // a one-slice job stays in the buffer for its sub-passes

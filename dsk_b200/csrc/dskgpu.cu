@@ -22,6 +22,7 @@
 #include "scan.cuh"
 #include "superk.cuh"
 #include "count.cuh"
+#include "plan.cuh"
 #include "count_smem.cuh"
 #include "kmer_wide.cuh"
 #include "radix.cuh"
@@ -47,7 +48,7 @@ struct dskgpu_ctx {
     DevBuf ss, ctr, hist, hist2d, bank_hist, raw[2], codes, tabs, tin;
     DevBuf recs, meta;                               // staging records (input order)
     DevBuf precs;                                    // partitioned records
-    DevBuf cursor, dstbase, bin_hist, bin_fold, bin2part, jobs, work_ctr;
+    DevBuf cursor, bin_hist, bin_fold, bin2part, work_ctr;
     DevBuf sample_recs, stab_keys, stab_counts;      // density sample: selected records, small hash table
     DevBuf tkeys, tcounts;                           // hash table
     DevBuf skeys[2], svals[2];                       // solid (k-mer, abundance) ping-pong
@@ -65,15 +66,19 @@ struct dskgpu_ctx {
     size_t push_chunk = (size_t)64 << 20;
     // results
     u64 n_solid = 0; int solid_buf = 0; bool results_on_host = false; u64 solid_cap = 0;
-    std::vector<u64> h_part_recs, h_part_kmers;      // this rank's records / k-mers of every partition
-    std::vector<u64> g_part_kmers;                   // whole-job k-mers of every partition
-    std::vector<u32> h_bin2part;
-    unsigned long long* h_bin_hist = nullptr;        // pinned [2][1 << bin_level] (room for the finest level)
     u32 nparts = 0;
     u32 smem_cap = 0; int num_sms = 148;
+    // device-side plan (plan.cuh): scratch of the planner, q-ordered per-partition tables, exchange table
+    DevBuf pl_ex, pl_E, pl_H, pl_bsum, pl_pk, pl_pr, pl_pl, pl_newid, pl_nvals, pl_hdr;
+    DevBuf gk_q, gr_q, lcnt_q, loff, xX, xtab, xS, hoff, hrecs;
+    PlanHdr* h_hdr = nullptr; XchgTab* h_xtab = nullptr;             // pinned mirrors
+    bool planned = false;
+    u32 nl_me = 0, np_me = 0;                        // owned jobs: [0, nl_me) counted in shared memory, [nl_me, np_me) heavy
+    std::vector<u64> heavy_recs, heavy_kmers;        // whole-job records / k-mers of the owned heavy partitions (increasing id)
+    u64* h_heavy = nullptr; size_t h_heavy_cap = 0;  // pinned staging for them
+    const void* rcnt_dev = nullptr;                  // [W][PW] records of my partitions held by every rank (W = 1: lcnt_q)
     // multi-GPU
-    std::vector<u64> xchg_matrix; std::vector<void*> peer_recv; bool xchg_planned = false; bool xchg_scattered = false;
-    u64 my_nrec_owned = 0; std::vector<u64> owned_recs, owned_kmers;   // my partitions in my receive buffer (increasing id)
+    std::vector<void*> peer_recv; bool xchg_planned = false; bool xchg_scattered = false;
     std::vector<void*> ipc_opened;
     bool totals_done = false; u64 local_nrec = 0, local_nkm = 0;     // records / k-mers this context holds (this pass)
     u64 bank_nkm = 0;                                // valid k-mers of everything pushed (all passes)
@@ -82,20 +87,11 @@ struct dskgpu_ctx {
     bool sample_queued = false; u64 sample_nkm = 0, sample_distinct = 0; double sample_wmult = 0.0;   // wmult: occurrence-weighted multiplicity (this rank's sample)
     bool global_set = false; u64 g_total_kmers = 0, g_total_recs = 0; double density = 1.0; bool density_known = false;
     int bin_level = NBINS_LOG2; bool hist_fetched = false;
-    DevBuf sendbuf;
-    // exchange v2 (bulk segments): records in local partition order, per-partition offsets on the device, pinned global histogram
-    DevBuf lrecs, xoff, xpeers, bcur;
+    // records in q order (owner-major partition order): what the counting kernels read on one GPU, what crosses NVLink as
+    // W - 1 contiguous chunks on several (precs is then the receive buffer)
+    DevBuf lrecs, xpeers, bcur, ghist;
     u64 xchg_bytes_out = 0;
-    unsigned long long* h_ghist = nullptr;
-    std::vector<u64> g_part_recs;                    // whole-job records of every partition
-    std::vector<u64> x_need;                         // records every rank receives
-    u64 recv_cap_recs = 0;
     dskgpu_stats st;
-    // pinned staging for the per-finish tables that go to the device (a cudaMemcpyAsync from pageable memory is a synchronous,
-    // staged copy; with ~1 M partitions these tables are 8-16 MB each)
-    struct HostBuf { void* p = nullptr; size_t cap = 0; };
-    HostBuf hb_jobs, hb_dst, hb_off;
-    std::vector<u64> v_off; std::vector<char> v_big; std::vector<SmemJob> v_jobs, v_jobs2;
     // timing
     std::vector<cudaEvent_t> evpool; size_t ev_used = 0;
     struct Span { cudaEvent_t a, b; int kind; };
@@ -122,19 +118,6 @@ static void trace(const char* what)
     auto now = std::chrono::steady_clock::now();
     if (!what) { g_t0 = now; return; }
     fprintf(stderr, "[dskgpu pid %d] %-48s +%8.3f ms\n", (int)getpid(), what, std::chrono::duration<double, std::milli>(now - g_t0).count());
-}
-
-static int ensure_host(dskgpu_ctx* ctx, dskgpu_ctx::HostBuf& b, size_t bytes)
-{
-    if (bytes <= b.cap) return 0;
-    CK(cudaStreamSynchronize(ctx->stream));                         // a copy out of the old buffer may still be queued
-    if (b.p) cudaFreeHost(b.p);
-    b.p = nullptr; b.cap = 0;
-    const size_t ncap = (bytes + bytes / 2 + 4095) & ~(size_t)4095;
-    cudaError_t e = cudaMallocHost(&b.p, ncap);
-    if (e != cudaSuccess) { (void)cudaGetLastError(); b.p = nullptr; FAIL(DSKGPU_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", ncap, cudaGetErrorString(e)); }
-    b.cap = ncap;
-    return 0;
 }
 
 static int ensure(dskgpu_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false, size_t keep_bytes = 0)
@@ -234,7 +217,8 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     CK(cudaMallocHost((void**)&ctx->h_ss, sizeof(StreamState)));
     CK(cudaMallocHost((void**)&ctx->h_nrec_probe, 64));
     CK(cudaMallocHost((void**)&ctx->h_hist, sizeof(unsigned long long) * (DSKGPU_HISTO_LEN * (1 + DSKGPU_HISTO2D_DIM2))));
-    CK(cudaMallocHost((void**)&ctx->h_bin_hist, sizeof(unsigned long long) * 2 * NBINS_FINE));
+    CK(cudaMallocHost((void**)&ctx->h_hdr, sizeof(PlanHdr)));
+    CK(cudaMallocHost((void**)&ctx->h_xtab, sizeof(XchgTab)));
     int rc;
     if ((rc = ensure(ctx, ctx->bin_hist, sizeof(unsigned long long) * 2 * NBINS_FINE))) return rc;
     if ((rc = ensure(ctx, ctx->bin_fold, sizeof(unsigned long long) * 2 * (NBINS_FINE / 2)))) return rc;
@@ -318,7 +302,7 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     CK(cudaMemsetAsync(ctx->bin_hist.p, 0, sizeof(unsigned long long) * 2 * NBINS_FINE, ctx->stream));
     ctx->state = 0; ctx->cur_bank = -1; ctx->stream_open = false; ctx->pending_cr = 0;
     ctx->nrec_known = 0; ctx->k2_inflight = false; ctx->chunk_parity = 0;
-    ctx->n_solid = 0; ctx->results_on_host = false; ctx->nparts = 0;
+    ctx->n_solid = 0; ctx->results_on_host = false; ctx->nparts = 0; ctx->planned = false; ctx->nl_me = ctx->np_me = 0; ctx->heavy_recs.clear(); ctx->heavy_kmers.clear(); ctx->rcnt_dev = nullptr;
     ctx->xchg_planned = false; ctx->xchg_scattered = false; ctx->xchg_bytes_out = 0; ctx->totals_done = false; ctx->local_nrec = ctx->local_nkm = 0;
     ctx->bytes_pushed = 0; ctx->sample_queued = false; ctx->sample_nkm = ctx->sample_distinct = 0; ctx->sample_wmult = 0.0;
     ctx->global_set = false; ctx->g_total_kmers = 0; ctx->density = 1.0; ctx->density_known = false; ctx->bin_level = NBINS_LOG2; ctx->hist_fetched = false;
@@ -334,10 +318,11 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->bank_hist, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
-                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->dstbase, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->bin2part, &ctx->jobs, &ctx->work_ctr,
+                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->bin2part, &ctx->work_ctr,
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
-                     &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr, &ctx->sendbuf,
-                     &ctx->lrecs, &ctx->xoff, &ctx->xpeers, &ctx->bcur};
+                     &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr,
+                     &ctx->lrecs, &ctx->xpeers, &ctx->bcur, &ctx->ghist, &ctx->pl_ex, &ctx->pl_E, &ctx->pl_H, &ctx->pl_bsum, &ctx->pl_pk, &ctx->pl_pr, &ctx->pl_pl,
+                     &ctx->pl_newid, &ctx->pl_nvals, &ctx->pl_hdr, &ctx->gk_q, &ctx->gr_q, &ctx->lcnt_q, &ctx->loff, &ctx->xX, &ctx->xtab, &ctx->xS, &ctx->hoff, &ctx->hrecs};
     for (DevBuf* b : all) b->release();
     for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -347,13 +332,11 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (ctx->h_ss) cudaFreeHost(ctx->h_ss);
     if (ctx->h_nrec_probe) cudaFreeHost(ctx->h_nrec_probe);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
-    if (ctx->h_bin_hist) cudaFreeHost(ctx->h_bin_hist);
-    if (ctx->h_ghist) cudaFreeHost(ctx->h_ghist);
+    if (ctx->h_hdr) cudaFreeHost(ctx->h_hdr);
+    if (ctx->h_xtab) cudaFreeHost(ctx->h_xtab);
+    if (ctx->h_heavy) cudaFreeHost(ctx->h_heavy);
     if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
     if (ctx->h_svals) cudaFreeHost(ctx->h_svals);
-    if (ctx->hb_jobs.p) cudaFreeHost(ctx->hb_jobs.p);
-    if (ctx->hb_dst.p) cudaFreeHost(ctx->hb_dst.p);
-    if (ctx->hb_off.p) cudaFreeHost(ctx->hb_off.p);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -825,9 +808,10 @@ static void set_global(dskgpu_ctx* ctx, u64 g_kmers, u64 g_recs, u64 g_sample_km
     ctx->density_known = g_sample_kmers >= 4096;
     ctx->density = ctx->density_known ? std::min(1.0, std::max(0.01, (double)g_sample_distinct / (double)g_sample_kmers)) : 1.0;
     const u64 T = plan_target_kmers(ctx, g_kmers);
-    // bins of the chosen level should average a quarter of a partition, so that packing consecutive bins balances well
+    // bins of the chosen level should average an eighth of a partition: a partition overshoots the cut by part of its last bin
+    // (plan.cuh), and the planner runs on the device, so a finer level costs microseconds
     int L = NBINS_LOG2;
-    while (L < NBINS_FINE_LOG2 && ((u64)1 << L) * (T / 4 + 1) < g_kmers) L++;
+    while (L < NBINS_FINE_LOG2 && ((u64)1 << L) * (T / 8 + 1) < g_kmers) L++;
     ctx->bin_level = L;
     ctx->global_set = true; ctx->hist_fetched = false;
 }
@@ -858,20 +842,21 @@ static int stage_totals(dskgpu_ctx* ctx)
     return 0;
 }
 
-// ---- stage 2: plan the partitions from the whole-job bin histogram ---------------------------------------------------
-static int fetch_local_bin_hist(dskgpu_ctx* ctx)
+// ---- stage 2: plan the partitions from the whole-job bin histogram (on the device, plan.cuh) ----------------------------
+// this rank's bin histogram at the planning level, on the device: [2 << bin_level] = records per bin, then k-mers per bin
+static int fold_local_hist(dskgpu_ctx* ctx, const void** d_hist)
 {
-    if (ctx->hist_fetched) return 0;
     if (!ctx->global_set) set_global(ctx, ctx->local_nkm, ctx->local_nrec, ctx->sample_nkm, ctx->sample_distinct);
     const int shift = NBINS_FINE_LOG2 - ctx->bin_level;
     const u32 nb = 1u << ctx->bin_level;
-    const void* src = ctx->bin_hist.p;
+    *d_hist = ctx->bin_hist.p;
     if (shift) {
-        k_fold_bins<<<(2 * nb + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, shift, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
-        src = ctx->bin_fold.p;
+        if (!ctx->hist_fetched) {
+            k_fold_bins<<<(2 * nb + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, shift, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
+            CK(cudaGetLastError());
+        }
+        *d_hist = ctx->bin_fold.p;
     }
-    CK(cudaMemcpyAsync(ctx->h_bin_hist, src, sizeof(unsigned long long) * 2 * nb, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     ctx->hist_fetched = true;
     return 0;
 }
@@ -901,8 +886,8 @@ static u64 smem_max_kmers(const dskgpu_ctx* ctx)
     return (u64)(smem_fit_kmers(ctx) * (double)(1 << smem_max_split0(ctx)));
 }
 
-// k-mers a partition should hold.  Shared-memory path: what fills the table to ~52 % given the sampled density
-// (distinct / total k-mers: 0.26 for 100x reads at k=31, 0.47 at k=63, 0.43 for 30x reads).
+// k-mers a partition should hold AT MOST in the common case.  Shared-memory path: what fills the table to ~52 % given the
+// sampled density (distinct / total k-mers: 0.26 for 100x reads at k=31, 0.47 at k=63, 0.43 for 30x reads).
 // Global-table path: a quarter of the table capacity, so that groups of partitions can be sized to the measured occupancy.
 static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers)
 {
@@ -925,94 +910,132 @@ static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers)
     return std::max<u64>(((u64)1 << log2s) * 6 / 10 / 4, 4096);
 }
 
-// greedy packing of consecutive bins (the role of Repartitor::computeDistrib, K/PartiInfo.cpp:48-106, on exact counts);
-// every rank derives the same plan from the same global histogram.  P is padded to a multiple of the world size.
-static void plan_partitions_host(dskgpu_ctx* ctx, const unsigned long long* gh /*[2 << bin_level] whole job*/)
+// The cut rule of plan.cuh gives partitions of T k-mers on average and T + (the last bin) at most; bins average an eighth of
+// a partition (set_global), so cutting at 85 % of the target keeps the common case under it.  A forced partition count
+// (-nb-partitions style) is honoured exactly.
+static PlanParams make_plan_params(const dskgpu_ctx* ctx)
 {
-    const u32 NB_ = 1u << ctx->bin_level;
-    const unsigned long long* gk = gh + NB_;
-    const unsigned long long* lr = ctx->h_bin_hist; const unsigned long long* lk = ctx->h_bin_hist + NB_;
-    u64 total = 0;
-    for (u32 b = 0; b < NB_; b++) total += gk[b];
-    const u64 T = plan_target_kmers(ctx, total);
-    ctx->h_bin2part.resize(NB_);
-    u32* b2p = ctx->h_bin2part.data();
-    // two passes (the plan of a 72 G k-mer job packs 4 M bins into ~4 M partitions: no push_back growth, no re-reads):
-    // 1. bin -> partition (the greedy rule: a partition is closed when the next bin would take it beyond T)
-    u32 P = 0;
-    {
-        u64 acc = 0;
-        for (u32 b = 0; b < NB_; b++) {
-            const u64 km = gk[b];
-            if (acc > 0 && acc + km > T) { P++; acc = 0; }
-            b2p[b] = P; acc += km;
-        }
-        P += 1;
-    }
-    // 2. per-partition sums, written by index
-    ctx->g_part_kmers.assign(P, 0); ctx->g_part_recs.assign(P, 0); ctx->h_part_recs.assign(P, 0); ctx->h_part_kmers.assign(P, 0);
-    {
-        u64* pgk = ctx->g_part_kmers.data(); u64* pgr = ctx->g_part_recs.data(); u64* plr = ctx->h_part_recs.data(); u64* plk = ctx->h_part_kmers.data();
-        auto fold = [&](const unsigned long long* src, u64* dst) { for (u32 b = 0; b < NB_; b++) dst[b2p[b]] += src[b]; };
-        if (NB_ >= (1u << 19)) {                               // one host thread per array (memory-bound, no sharing between them)
-            std::thread t1(fold, gk, pgk), t2(fold, gh, pgr), t3(fold, lr, plr);
-            fold(lk, plk);
-            t1.join(); t2.join(); t3.join();
-        } else { fold(gk, pgk); fold(gh, pgr); fold(lr, plr); fold(lk, plk); }
-    }
-    if (use_smem_path(ctx) && ctx->cfg.count_mode == DSKGPU_COUNT_AUTO) {
-        // partitions beyond the reach of the shared-memory path are renumbered to the end (heaviest first, so that
-        // p % world_size spreads them evenly): the global-table path then sees one contiguous run of records on every
-        // rank instead of many short ones.  Every rank derives the same order from the same whole-job histogram.
-        const u64 lim = smem_max_kmers(ctx);
-        std::vector<u32> heavy;
-        for (u32 p = 0; p < P; p++) if (ctx->g_part_kmers[p] > lim) heavy.push_back(p);
-        if (!heavy.empty() && heavy.size() < P) {
-            std::stable_sort(heavy.begin(), heavy.end(), [&](u32 a, u32 b) { return ctx->g_part_kmers[a] > ctx->g_part_kmers[b]; });
-            std::vector<u32> newid(P); std::vector<char> is_heavy(P, 0);
-            for (u32 h : heavy) is_heavy[h] = 1;
-            u32 nid = 0;
-            for (u32 p = 0; p < P; p++) if (!is_heavy[p]) newid[p] = nid++;
-            for (u32 h : heavy) newid[h] = nid++;
-            auto permute = [&](std::vector<u64>& v) { std::vector<u64> t(P); for (u32 p = 0; p < P; p++) t[newid[p]] = v[p]; v.swap(t); };
-            permute(ctx->g_part_kmers); permute(ctx->g_part_recs); permute(ctx->h_part_recs); permute(ctx->h_part_kmers);
-            for (u32 b = 0; b < NB_; b++) b2p[b] = newid[b2p[b]];
-        }
-    }
-    const u32 W = (u32)ctx->cfg.world_size;
-    while (P % W) { ctx->g_part_kmers.push_back(0); ctx->g_part_recs.push_back(0); ctx->h_part_recs.push_back(0); ctx->h_part_kmers.push_back(0); P++; }
-    ctx->nparts = P; ctx->st.nb_partitions = P;
+    PlanParams pp;
+    const u64 T = plan_target_kmers(ctx, ctx->g_total_kmers);
+    pp.T = ctx->cfg.nb_partitions > 0 ? T : std::max<u64>(1, (u64)((double)T * 0.85));
+    pp.lim = smem_max_kmers(ctx);
+    pp.nbins = 1u << ctx->bin_level;
+    pp.W = (u32)ctx->cfg.world_size; pp.me = (u32)ctx->cfg.rank;
+    pp.smem_ok = use_smem_path(ctx) ? 1u : 0u;
+    return pp;
 }
 
-// the plan (host only, above) + the device tables the scatter needs
-static int plan_partitions(dskgpu_ctx* ctx, const unsigned long long* gh)
+// d_ghist: whole-job histogram (device, [2 << bin_level]; on one GPU the local one).  Leaves on the device: bin2part (bin -> q),
+// gk_q / gr_q / lcnt_q (per partition, q order), loff (exclusive prefix of lcnt_q); on the host: the header and the owned heavy
+// partitions.  One stream sync (two when there are heavy partitions).
+static int plan_device(dskgpu_ctx* ctx, const void* d_ghist)
 {
-    plan_partitions_host(ctx, gh);
-    const u32 P = ctx->nparts, NB_ = 1u << ctx->bin_level;
+    const void* d_lhist = nullptr;
     int rc;
-    if ((rc = ensure(ctx, ctx->cursor, (size_t)P * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->dstbase, (size_t)P * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->bin2part, (size_t)NB_ * 4))) return rc;
+    if ((rc = fold_local_hist(ctx, &d_lhist))) return rc;
+    if (!d_ghist) d_ghist = d_lhist;
+    const PlanParams pp = make_plan_params(ctx);
+    const u32 nb = pp.nbins, W = pp.W, me = pp.me;
+    const u64 qcap = (u64)nb + W;                                        // W * PW <= P + W <= nbins + W
+    if ((rc = ensure(ctx, ctx->pl_ex, (nb + 1) * 8ull))) return rc;
+    if ((rc = ensure(ctx, ctx->pl_E, (nb + 1) * 8ull))) return rc;
+    if ((rc = ensure(ctx, ctx->pl_H, (nb + 1) * 8ull))) return rc;
+    if ((rc = ensure(ctx, ctx->pl_bsum, ps_bsum_bytes(qcap)))) return rc;
+    if ((rc = ensure(ctx, ctx->pl_pk, nb * 8ull * 3))) return rc;         // pk | pr | pl, cleared together
+    if ((rc = ensure(ctx, ctx->pl_newid, nb * 4ull))) return rc;
+    if ((rc = ensure(ctx, ctx->pl_nvals, 64))) return rc;
+    if ((rc = ensure(ctx, ctx->pl_hdr, sizeof(PlanHdr)))) return rc;
+    if ((rc = ensure(ctx, ctx->gk_q, qcap * 8 * 3))) return rc;            // gk_q | gr_q | lcnt_q, cleared together
+    if ((rc = ensure(ctx, ctx->loff, (qcap + 1) * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->bin2part, nb * 4ull))) return rc;
+    cudaStream_t st = ctx->stream;
+    const u64* gh = (const u64*)d_ghist; const u64* lh = (const u64*)d_lhist;
+    u64* ex = (u64*)ctx->pl_ex.p; u64* E = (u64*)ctx->pl_E.p; u64* H = (u64*)ctx->pl_H.p; u64* bsum = (u64*)ctx->pl_bsum.p;
+    unsigned long long* pk = (unsigned long long*)ctx->pl_pk.p; unsigned long long* pr = pk + nb; unsigned long long* pl = pr + nb;
+    u64* gk_q = (u64*)ctx->gk_q.p; u64* gr_q = gk_q + qcap; u64* lcnt_q = gr_q + qcap;
+    u64* nvals = (u64*)ctx->pl_nvals.p; PlanHdr* hdr = (PlanHdr*)ctx->pl_hdr.p;
+    const unsigned gb = (unsigned)std::min<u32>((nb + 255) / 256, (u32)ctx->num_sms * 8);
+    CK(cudaMemsetAsync(pk, 0, nb * 8ull * 3, st));
+    CK(cudaMemsetAsync(gk_q, 0, qcap * 8 * 3, st));
+    CK(cudaMemsetAsync(hdr, 0, sizeof(PlanHdr), st));
+    ctx->st.gpu_launches += ps_scan(st, PsLoad{gh + nb}, nullptr, nb, bsum, ex);                       // k-mer offset of every bin
+    ctx->st.gpu_launches += ps_scan(st, PsCutFlag{ex, pp.T}, nullptr, nb, bsum, E);                    // cuts before every bin
+    k_plan_sums<<<gb, 256, 0, st>>>(gh, lh, ex, E, pp, pk, pr, pl, nvals); LAUNCHED();
+    ctx->st.gpu_launches += ps_scan(st, PsHeavyFlag{(const u64*)pk, (const u64*)pr, pp.lim, pp.smem_ok}, nvals, nb, bsum, H);
+    k_plan_renumber<<<gb, 256, 0, st>>>((const u64*)pk, (const u64*)pr, (const u64*)pl, H, pp, nvals, (u32*)ctx->pl_newid.p, gk_q, gr_q, lcnt_q, hdr); LAUNCHED();
+    k_plan_bin2q<<<gb, 256, 0, st>>>(ex, E, (const u32*)ctx->pl_newid.p, pp, nvals, (u32*)ctx->bin2part.p); LAUNCHED();
+    ctx->st.gpu_launches += ps_scan(st, PsLoad{lcnt_q}, nvals + 1, qcap, bsum, (u64*)ctx->loff.p);     // first record of every partition in q order
+    k_plan_hdr<<<W, 256, 0, st>>>(gk_q, gr_q, (const u64*)ctx->loff.p, hdr); LAUNCHED();
+    CK(cudaMemcpyAsync(ctx->h_hdr, hdr, sizeof(PlanHdr), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    const PlanHdr& h = *ctx->h_hdr;
+    ctx->nparts = h.P; ctx->st.nb_partitions = h.P;
+    ctx->np_me = me < h.P ? (h.P - me + W - 1) / W : 0;
+    ctx->nl_me = me < h.nlight ? (h.nlight - me + W - 1) / W : 0;
+    ctx->heavy_recs.clear(); ctx->heavy_kmers.clear();
+    const u32 nh = ctx->np_me - ctx->nl_me;
+    if (nh) {
+        if ((size_t)nh * 16 > ctx->h_heavy_cap) {
+            if (ctx->h_heavy) cudaFreeHost(ctx->h_heavy);
+            ctx->h_heavy = nullptr; ctx->h_heavy_cap = 0;
+            CK(cudaMallocHost((void**)&ctx->h_heavy, (size_t)nh * 16 + 4096));
+            ctx->h_heavy_cap = (size_t)nh * 16 + 4096;
+        }
+        const u64 q0 = (u64)me * h.PW + ctx->nl_me;
+        CK(cudaMemcpyAsync(ctx->h_heavy, gr_q + q0, (size_t)nh * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_heavy + nh, gk_q + q0, (size_t)nh * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->heavy_recs.assign(ctx->h_heavy, ctx->h_heavy + nh);
+        ctx->heavy_kmers.assign(ctx->h_heavy + nh, ctx->h_heavy + 2 * (size_t)nh);
+    }
+    ctx->planned = true;
     return 0;
 }
 
-// ---- stage 3: scatter my records to dst[p] (local partition array, or the owners' receive buffers over NVLink) ------
+// ---- stage 3: scatter my records into q order (lrecs): owner-major, so every owner's records are one contiguous chunk -------
 template <int KW>
-static int stage_scatter(dskgpu_ctx* ctx, const std::vector<u64*>& dst)
+static int stage_scatter(dskgpu_ctx* ctx)
 {
-    const u32 P = ctx->nparts;
+    const PlanHdr& h = *ctx->h_hdr;
+    int rc;
+    if ((rc = ensure(ctx, ctx->lrecs, ctx->local_nrec * (u64)ctx->RW * 8 + 64))) return rc;
     if (ctx->local_nrec == 0) return 0;
+    const u64 nq = (u64)ctx->cfg.world_size * h.PW;
+    if ((rc = ensure(ctx, ctx->cursor, nq * 8))) return rc;
     SpanGuard g(ctx, SPAN_PART);
-    CK(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)P * 8, ctx->stream));
-    { int rc = ensure_host(ctx, ctx->hb_dst, (size_t)P * 8 + ctx->h_bin2part.size() * 4); if (rc) return rc; }
-    memcpy(ctx->hb_dst.p, dst.data(), (size_t)P * 8);
-    memcpy((char*)ctx->hb_dst.p + (size_t)P * 8, ctx->h_bin2part.data(), ctx->h_bin2part.size() * 4);
-    CK(cudaMemcpyAsync(ctx->dstbase.p, ctx->hb_dst.p, (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->bin2part.p, (char*)ctx->hb_dst.p + (size_t)P * 8, ctx->h_bin2part.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->cursor.p, ctx->loff.p, nq * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     const unsigned sb = (unsigned)std::min<u64>((ctx->local_nrec + SC_THREADS - 1) / SC_THREADS, (u64)ctx->num_sms * 32);
     k_part_scatter<KW><<<sb, SC_THREADS, 0, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, ctx->local_nrec,
-                                                          (const u32*)ctx->bin2part.p, NBINS_FINE_LOG2 - ctx->bin_level, (u64* const*)ctx->dstbase.p,
+                                                          (const u32*)ctx->bin2part.p, NBINS_FINE_LOG2 - ctx->bin_level, (u64*)ctx->lrecs.p,
                                                           (unsigned long long*)ctx->cursor.p); LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// the segment table the counting kernels read (and, on several GPUs, where every chunk goes).  d_rcnt: [W][PW] records of my
+// partitions held by every rank; d_S: [W][W] chunk sizes (records rank s holds for rank o); peers: receive buffers.
+static int stage_bases(dskgpu_ctx* ctx, const void* d_rcnt, const void* d_S)
+{
+    const PlanHdr& h = *ctx->h_hdr;
+    const u32 W = (u32)ctx->cfg.world_size, me = (u32)ctx->cfg.rank;
+    const u64 nq = (u64)W * h.PW;
+    int rc;
+    if ((rc = ensure(ctx, ctx->xtab, sizeof(XchgTab)))) return rc;
+    if ((rc = ensure(ctx, ctx->xpeers, (size_t)PLAN_MAXW * 8))) return rc;
+    const u64* X = (const u64*)ctx->loff.p;
+    if (W > 1) {
+        if ((rc = ensure(ctx, ctx->xX, (nq + 1) * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->pl_bsum, ps_bsum_bytes(nq)))) return rc;
+        ctx->st.gpu_launches += ps_scan(ctx->stream, PsLoad{(const u64*)d_rcnt}, nullptr, nq, (u64*)ctx->pl_bsum.p, (u64*)ctx->xX.p);
+        X = (const u64*)ctx->xX.p;
+        CK(cudaMemcpyAsync(ctx->xpeers.p, ctx->peer_recv.data(), (size_t)W * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->rcnt_dev = X;
+    const u64* S = W > 1 ? (const u64*)d_S : ((const PlanHdr*)ctx->pl_hdr.p)->send_recs;
+    k_xchg_bases<<<1, 32, 0, ctx->stream>>>((const PlanHdr*)ctx->pl_hdr.p, (const u64*)ctx->loff.p, X, S, (const u64*)ctx->xpeers.p,
+                                            (u64)(uintptr_t)ctx->lrecs.p, W, me, (u32)ctx->RW * 8, (XchgTab*)ctx->xtab.p); LAUNCHED();
+    CK(cudaMemcpyAsync(ctx->h_xtab, ctx->xtab.p, sizeof(XchgTab), cudaMemcpyDeviceToHost, ctx->stream));   // read at the next sync (bad flags)
     CK(cudaGetLastError());
     return 0;
 }
@@ -1066,11 +1089,11 @@ static int count_by_buckets(dskgpu_ctx* ctx, const u64* recs, const std::vector<
                 cudaEvent_t a = get_event(ctx), b = get_event(ctx);
                 cudaEventRecord(a, ctx->stream);
                 if (ctx->NB == 1)
-                    k_count_smem<KW, false, true><<<grid, CS_THREADS, dyn, ctx->stream>>>((const u64*)ctx->keys[0].p, nullptr, S, ctx->k, ctx->smem_cap,
+                    k_count_smem<KW, false, true><<<grid, CS_THREADS, dyn, ctx->stream>>>((const u64*)ctx->keys[0].p, CsSegs(), S, ctx->k, ctx->smem_cap,
                         (long long)ctx->cfg.abundance_min[0], (long long)ctx->cfg.abundance_max, (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
                         (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p, 1, SolidityParams(), nullptr, (const u32*)ctx->bcur.p, slab);
                 else
-                    k_count_smem<KW, true, true><<<grid, CS_THREADS, dyn, ctx->stream>>>((const u64*)ctx->keys[0].p, nullptr, S, ctx->k, ctx->smem_cap,
+                    k_count_smem<KW, true, true><<<grid, CS_THREADS, dyn, ctx->stream>>>((const u64*)ctx->keys[0].p, CsSegs(), S, ctx->k, ctx->smem_cap,
                         (long long)ctx->cfg.abundance_min[0], (long long)ctx->cfg.abundance_max, (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
                         (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p, ctx->NB, make_sp(ctx), (unsigned long long*)ctx->hist2d.p,
                         (const u32*)ctx->bcur.p, slab);
@@ -1104,16 +1127,18 @@ static bool heavy_by_buckets(const dskgpu_ctx* ctx)
     return ctx->NB > 1;
 }
 
-// ---- stage 4: count the partitions stored contiguously in `recs`, order the solid set, copy results out --------------
+// ---- stage 4: count the partitions this rank owns, order the solid set, copy results out --------------------------------
+// Light partitions (jobs [0, nl_me) of my chunk of the q-ordered tables) go to the shared-memory kernel, which reads the
+// planner's device tables itself; the owned heavy partitions (host vectors heavy_recs / heavy_kmers) to the host-driven paths.
 template <int KW>
-static int stage_count_once(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm, u64 cap_request, u64* need_cap)
+static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
 {
     Counters* ctr = (Counters*)ctx->ctr.p;
     *need_cap = 0;
     int rc;
-    const size_t np = prec.size();
-    u64 nrec = 0, nkm = 0;
-    for (size_t i = 0; i < np; i++) { nrec += prec[i]; nkm += pkm[i]; }
+    const PlanHdr& h = *ctx->h_hdr;
+    const u32 W = (u32)ctx->cfg.world_size, me = (u32)ctx->cfg.rank;
+    const u64 nrec = h.need_recs[me], nkm = h.need_kmers[me];
     ctx->st.smem_table_slots = ctx->smem_cap;
     ctx->st.density_ppm = ctx->density_known ? (u32)(ctx->density * 1e6) : 0u; ctx->st.log2_bins = (u32)ctx->bin_level;
     if (nrec) {
@@ -1139,58 +1164,29 @@ static int stage_count_once(dskgpu_ctx* ctx, const u64* recs, const std::vector<
             if ((rc = ensure(ctx, ctx->skeys[i], out_cap * KW * 8))) return rc;
             if ((rc = ensure(ctx, ctx->svals[i], out_cap * 4))) return rc;
         }
-        // occupancy picks the path of every partition (K/SortingCountAlgorithm.cpp:1489-1497): shared-memory table when the
-        // partition is within reach of a few split passes, else the global paths
-        const bool smem = use_smem_path(ctx);
-        // a partition expected to fill the table beyond 75 % (k-mers x sampled density) starts as 2^split0 sub-passes over
-        // hash residues; beyond 16 sub-passes it goes to the global paths.  Forced SMEM mode (tests) starts everything in one
-        // pass and lets the kernel discover the splits.
-        const bool presplit = ctx->cfg.count_mode != DSKGPU_COUNT_SMEM;
-        const double fit = smem_fit_kmers(ctx);                                             // k-mers one pass can take
-        const u64 smem_max = smem_max_kmers(ctx);
-        const unsigned max_split0 = (unsigned)smem_max_split0(ctx);
-        std::vector<SmemJob>& jobs = ctx->v_jobs; jobs.clear();
-        std::vector<u64>& off = ctx->v_off; off.assign(np + 1, 0);
-        std::vector<char>& big = ctx->v_big; big.assign(np, 0);
-        for (size_t i = 0; i < np; i++) {
-            off[i + 1] = off[i] + prec[i];
-            if (prec[i] == 0) continue;
-            if (smem && pkm[i] <= smem_max && prec[i] < 0xFFFFFFFFull) {
-                SmemJob j; j.rec_begin = off[i]; j.nrec = (unsigned)prec[i]; j.split0 = 0;
-                if (presplit) while (j.split0 < max_split0 && (double)pkm[i] > fit * (double)(1u << j.split0)) j.split0++;
-                jobs.push_back(j);
-            }
-            else big[i] = 1;
-        }
-        trace("jobs built");
         SpanGuard g(ctx, SPAN_COUNT);
-        if (!jobs.empty()) {
-            // longest first (the CTAs pull jobs off a queue: the tail of the launch is one job long).  A full sort is what a few
-            // thousand jobs get; beyond that the host cost of sorting ~1 M jobs (tens of ms) exceeds anything the order can
-            // win, and the pre-split jobs -- the long ones -- simply go first, the rest in partition order.
-            if (jobs.size() <= 65536)
-                std::sort(jobs.begin(), jobs.end(), [](const SmemJob& a, const SmemJob& b) { return ((u64)a.nrec << a.split0) > ((u64)b.nrec << b.split0); });
-            else {
-                std::vector<SmemJob>& t = ctx->v_jobs2; t.clear(); t.reserve(jobs.size());
-                for (int s0 = (int)max_split0; s0 >= 0; s0--) for (const SmemJob& j : jobs) if ((int)j.split0 == s0) t.push_back(j);
-                jobs.swap(t);
-            }
-            if ((rc = ensure(ctx, ctx->jobs, jobs.size() * sizeof(SmemJob)))) return rc;
-            if ((rc = ensure_host(ctx, ctx->hb_jobs, jobs.size() * sizeof(SmemJob)))) return rc;
-            memcpy(ctx->hb_jobs.p, jobs.data(), jobs.size() * sizeof(SmemJob));
-            CK(cudaMemcpyAsync(ctx->jobs.p, ctx->hb_jobs.p, jobs.size() * sizeof(SmemJob), cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->nl_me) {
+            // occupancy picks the path of every partition (K/SortingCountAlgorithm.cpp:1489-1497): the planner already put
+            // the partitions within reach of a few split passes first.  A partition expected to fill the table beyond 75 %
+            // (k-mers x sampled density) starts as 2^split0 sub-passes over hash residues (computed by the kernel from gk_q);
+            // forced SMEM mode (tests) starts everything in one pass and lets the kernel discover the splits.
+            CsSegs sg;
+            sg.tab = (const XchgTab*)ctx->xtab.p; sg.X = (const u64*)ctx->rcnt_dev; sg.gk_q = (const u64*)ctx->gk_q.p;
+            sg.W = W; sg.PW = h.PW; sg.qbase = me * h.PW;
+            sg.fit = (float)smem_fit_kmers(ctx);
+            sg.max_split0 = ctx->cfg.count_mode != DSKGPU_COUNT_SMEM ? (u32)smem_max_split0(ctx) : 0u;
             CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
-            const unsigned grid = (unsigned)std::min<size_t>(jobs.size(), (size_t)ctx->num_sms * CS_CTAS_PER_SM);
+            const unsigned grid = (unsigned)std::min<size_t>(ctx->nl_me, (size_t)ctx->num_sms * CS_CTAS_PER_SM);
             const size_t dyn = cs_smem_bytes<KW>(ctx->smem_cap, ctx->NB);
             cudaEvent_t a = get_event(ctx), b = get_event(ctx);
             cudaEventRecord(a, ctx->stream);
             if (ctx->NB == 1)
-                k_count_smem<KW, false><<<grid, CS_THREADS, dyn, ctx->stream>>>(recs, (const SmemJob*)ctx->jobs.p, (u32)jobs.size(), ctx->k, ctx->smem_cap,
+                k_count_smem<KW, false><<<grid, CS_THREADS, dyn, ctx->stream>>>(nullptr, sg, ctx->nl_me, ctx->k, ctx->smem_cap,
                                                                    (long long)ctx->cfg.abundance_min[0], (long long)ctx->cfg.abundance_max,
                                                                    (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
                                                                    (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p, 1, SolidityParams(), nullptr);
             else
-                k_count_smem<KW, true><<<grid, CS_THREADS, dyn, ctx->stream>>>(recs, (const SmemJob*)ctx->jobs.p, (u32)jobs.size(), ctx->k, ctx->smem_cap,
+                k_count_smem<KW, true><<<grid, CS_THREADS, dyn, ctx->stream>>>(nullptr, sg, ctx->nl_me, ctx->k, ctx->smem_cap,
                                                                    (long long)ctx->cfg.abundance_min[0], (long long)ctx->cfg.abundance_max,
                                                                    (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
                                                                    (unsigned long long*)ctx->hist.p, ctr, (u32*)ctx->work_ctr.p, ctx->NB, make_sp(ctx),
@@ -1198,25 +1194,41 @@ static int stage_count_once(dskgpu_ctx* ctx, const u64* recs, const std::vector<
             LAUNCHED();
             cudaEventRecord(b, ctx->stream);
             ctx->spans.push_back({a, b, SPAN_DOM});
-            ctx->st.nb_parts_smem = (u32)jobs.size();
+            ctx->st.nb_parts_smem = ctx->nl_me;
             CK(cudaGetLastError());
             trace("count kernel launched");
         }
-        // maximal runs of consecutive big partitions go through the global hash / sort paths
-        for (size_t i = 0; i < np;) {
-            if (!big[i]) { i++; continue; }
-            size_t j = i; u64 km = 0;
-            std::vector<u64> rp, rk;
-            while (j < np && (big[j] || prec[j] == 0)) { rp.push_back(prec[j]); rk.push_back(pkm[j]); km += pkm[j]; j++; }
-            if (heavy_by_buckets(ctx)) rc = count_by_buckets<KW>(ctx, recs + off[i] * (u64)ctx->RW, rp, rk, out_cap);
-            else rc = count_all<KW>(ctx, recs + off[i] * (u64)ctx->RW, rp, rk, out_cap);
-            if (rc) return rc;
-            i = j;
+        // the owned heavy partitions: one contiguous run of records for the global hash / sort / bucket paths.  On one GPU
+        // they already are the tail of lrecs (q order = id order, heavy ids last); on several their W segments are gathered.
+        if (!ctx->heavy_recs.empty()) {
+            u64 hrec = 0;
+            for (u64 r : ctx->heavy_recs) hrec += r;
+            const u64* hp = nullptr;
+            if (W == 1) hp = (const u64*)ctx->lrecs.p + (nrec - hrec) * (u64)ctx->RW;
+            else if (hrec) {
+                const size_t nh = ctx->heavy_recs.size();
+                if ((rc = ensure(ctx, ctx->hrecs, hrec * (u64)ctx->RW * 8 + 64))) return rc;
+                if ((rc = ensure(ctx, ctx->hoff, (nh + 1) * 8))) return rc;
+                u64* ho = ctx->h_heavy;                                           // pinned, >= 2 * nh words: reuse as staging of the prefix
+                { u64 o = 0; for (size_t i = 0; i < nh; i++) { ho[i] = o; o += ctx->heavy_recs[i]; } }
+                CK(cudaMemcpyAsync(ctx->hoff.p, ho, nh * 8, cudaMemcpyHostToDevice, ctx->stream));
+                const unsigned gg = (unsigned)std::min<u64>((u64)nh * W, (u64)ctx->num_sms * 8);
+                k_gather_heavy<<<gg, 256, 0, ctx->stream>>>((const XchgTab*)ctx->xtab.p, (const u64*)ctx->rcnt_dev, h.PW, W, ctx->nl_me, (u32)nh,
+                                                           (const u64*)ctx->hoff.p, (ulonglong2*)ctx->hrecs.p, (u32)ctx->RW / 2); LAUNCHED();
+                CK(cudaStreamSynchronize(ctx->stream));                           // h_heavy is rewritten by the next plan; cheap next to the heavy paths
+                hp = (const u64*)ctx->hrecs.p;
+            }
+            if (hrec) {
+                if (heavy_by_buckets(ctx)) rc = count_by_buckets<KW>(ctx, hp, ctx->heavy_recs, ctx->heavy_kmers, out_cap);
+                else rc = count_all<KW>(ctx, hp, ctx->heavy_recs, ctx->heavy_kmers, out_cap);
+                if (rc) return rc;
+            }
         }
     }
     CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     trace("count done (sync)");
+    if (ctx->h_xtab->bad) FAIL(DSKGPU_ERR_STATE, "exchange layout inconsistent on the device (flags 0x%x): the ranks disagree on the plan or on the record counts", ctx->h_xtab->bad);
     if (ctx->h_ctr->hash_overflow) FAIL(DSKGPU_ERR_OVERFLOW, "hash table overflow (distinct k-mer estimate too low)");
     if (ctx->h_ctr->smem_failed) FAIL(DSKGPU_ERR_OVERFLOW, "shared-memory table overflow at the deepest split (%u passes)", ctx->h_ctr->smem_failed);
     if (ctx->h_ctr->overflow) {                                    // the cursor kept counting: solid_n is the exact size needed
@@ -1285,15 +1297,15 @@ static int reset_count_state(dskgpu_ctx* ctx)
 }
 
 template <int KW>
-static int stage_count(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& prec, const std::vector<u64>& pkm, u64 cap_request = 0)
+static int stage_count(dskgpu_ctx* ctx, u64 cap_request = 0)
 {
     u64 need = 0;
-    int rc = stage_count_once<KW>(ctx, recs, prec, pkm, cap_request, &need);
+    int rc = stage_count_once<KW>(ctx, cap_request, &need);
     if (rc || !need) return rc;
     // the estimate was too small: once more at the exact size (the records are still in HBM)
     if ((rc = reset_count_state(ctx))) return rc;
     ctx->st.nb_solid_regrows++;
-    rc = stage_count_once<KW>(ctx, recs, prec, pkm, need, &need);
+    rc = stage_count_once<KW>(ctx, need, &need);
     if (rc) return rc;
     if (need) FAIL(DSKGPU_ERR_OVERFLOW, "solid k-mer buffer overflow after the exact-size pass (internal)");
     return DSKGPU_OK;
@@ -1306,48 +1318,22 @@ static int finish_single(dskgpu_ctx* ctx)
     trace(nullptr);
     if ((rc = stage_totals(ctx))) return rc;
     trace("totals (push kernels done)");
-    if ((rc = fetch_local_bin_hist(ctx))) return rc;
-    trace("bin hist d2h");
-    if ((rc = plan_partitions(ctx, ctx->h_bin_hist))) return rc;
-    trace("plan");
-    const u32 P = ctx->nparts;
-    if ((rc = ensure(ctx, ctx->precs, ctx->local_nrec * (u64)ctx->RW * 8 + 64))) return rc;
-    std::vector<u64*> dst(P);
-    u64 o = 0;
-    for (u32 i = 0; i < P; i++) { dst[i] = (u64*)ctx->precs.p + o * ctx->RW; o += ctx->h_part_recs[i]; }
-    if ((rc = stage_scatter<KW>(ctx, dst))) return rc;
+    if ((rc = plan_device(ctx, nullptr))) return rc;
+    trace("plan (device) + header");
+    if ((rc = stage_scatter<KW>(ctx))) return rc;
+    if ((rc = stage_bases(ctx, nullptr, nullptr))) return rc;
     trace("scatter launched");
-    rc = stage_count<KW>(ctx, (const u64*)ctx->precs.p, ctx->h_part_recs, ctx->h_part_kmers);
+    rc = stage_count<KW>(ctx);
     trace("finish done");
     return rc;
 }
 
-// multi-GPU: the partitions this rank owns sit in its receive buffer, in increasing partition id
+// multi-GPU: the partitions this rank owns are W segments each -- its own chunk in lrecs, the others' chunks in its receive buffer
 template <int KW>
 static int finish_owned(dskgpu_ctx* ctx)
 {
     if (!ctx->xchg_scattered) FAIL(DSKGPU_ERR_STATE, "world_size > 1: run the dskgpu_xchg_* sequence before dskgpu_finish");
-    return stage_count<KW>(ctx, (const u64*)ctx->precs.p, ctx->owned_recs, ctx->owned_kmers);
-}
-
-// layout of rank `owner`'s receive buffer: owned partitions in increasing id, each split by sender rank.
-// all[r*2P + p] = records of partition p held by rank r, all[r*2P + P + p] = their k-mers.
-static void xchg_layout(u32 W, u32 P, const u64* all, u32 owner, u32 sender, std::vector<u64>& off_of_part /*[P] (only owned p filled)*/,
-                        std::vector<u64>* owned_recs, std::vector<u64>* owned_kmers, u64* total_recs)
-{
-    off_of_part.assign(P, 0);
-    if (owned_recs) owned_recs->clear();
-    if (owned_kmers) owned_kmers->clear();
-    u64 o = 0;
-    for (u32 p = owner; p < P; p += W) {
-        u64 before = 0, tot = 0, km = 0;
-        for (u32 r = 0; r < W; r++) { const u64 c = all[(u64)r * 2 * P + p]; if (r < sender) before += c; tot += c; km += all[(u64)r * 2 * P + P + p]; }
-        off_of_part[p] = o + before;
-        if (owned_recs) owned_recs->push_back(tot);
-        if (owned_kmers) owned_kmers->push_back(km);
-        o += tot;
-    }
-    if (total_recs) *total_recs = o;
+    return stage_count<KW>(ctx);
 }
 
 extern "C" {
@@ -1390,42 +1376,55 @@ int dskgpu_xchg_set_global(dskgpu_ctx* ctx, const uint64_t* global4, int* log2_b
     return DSKGPU_OK;
 }
 
-int dskgpu_xchg_bin_hist(dskgpu_ctx* ctx, uint64_t* hist)
+int dskgpu_xchg_hist(dskgpu_ctx* ctx, void* d_out)
 {
-    if (!ctx || !hist) return DSKGPU_ERR_ARG;
+    if (!ctx || !d_out) return DSKGPU_ERR_ARG;
     use_device(ctx);
     int rc = stage_totals(ctx); if (rc) return rc;
-    if (!ctx->global_set) FAIL(DSKGPU_ERR_STATE, "xchg_bin_hist before xchg_set_global (the ranks must agree on the bin level)");
-    if ((rc = fetch_local_bin_hist(ctx))) return rc;
-    memcpy(hist, ctx->h_bin_hist, sizeof(uint64_t) * ((size_t)2 << ctx->bin_level));
+    if (!ctx->global_set) FAIL(DSKGPU_ERR_STATE, "xchg_hist before xchg_set_global (the ranks must agree on the bin level)");
+    const void* src = nullptr;
+    if ((rc = fold_local_hist(ctx, &src))) return rc;
+    CK(cudaMemcpyAsync(d_out, src, sizeof(unsigned long long) * ((size_t)2 << ctx->bin_level), cudaMemcpyDeviceToDevice, ctx->stream));
     return DSKGPU_OK;
 }
 
-int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, const uint64_t* global_hist, uint64_t* counts, uint32_t* nparts)
+int dskgpu_xchg_plan(dskgpu_ctx* ctx, const void* d_global_hist, uint32_t* nparts, uint32_t* parts_per_rank, uint64_t* need_records)
 {
-    if (!ctx || !global_hist) return DSKGPU_ERR_ARG;
+    if (!ctx || !d_global_hist) return DSKGPU_ERR_ARG;
     use_device(ctx);
-    int rc = stage_totals(ctx); if (rc) return rc;
-    if ((rc = fetch_local_bin_hist(ctx))) return rc;
-    if ((rc = plan_partitions(ctx, (const unsigned long long*)global_hist))) return rc;
-    const u32 P = ctx->nparts;
-    if (nparts) *nparts = P;
-    if (!counts) return DSKGPU_OK;                                 // size query
-    for (u32 p = 0; p < P; p++) { counts[p] = ctx->h_part_recs[p]; counts[P + p] = ctx->h_part_kmers[p]; }
+    if (!ctx->hist_fetched) FAIL(DSKGPU_ERR_STATE, "xchg_plan before xchg_hist");
+    if (ctx->cfg.world_size > PLAN_MAXW) FAIL(DSKGPU_ERR_ARG, "world_size %d beyond the %d ranks of one exchange", ctx->cfg.world_size, PLAN_MAXW);
+    if (!ctx->planned) {
+        trace(nullptr);
+        int rc = plan_device(ctx, d_global_hist); if (rc) return rc;
+        trace("xchg_plan: planned on the device, header read");
+    }
+    if (nparts) *nparts = ctx->h_hdr->P;
+    if (parts_per_rank) *parts_per_rank = ctx->h_hdr->PW;
+    if (need_records) for (int r = 0; r < ctx->cfg.world_size; r++) need_records[r] = ctx->h_hdr->need_recs[r];
     return DSKGPU_OK;
 }
 
-int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts)
+int dskgpu_xchg_counts(dskgpu_ctx* ctx, void* d_out)
 {
-    if (!ctx || !all_counts) return DSKGPU_ERR_ARG;
+    if (!ctx || !d_out) return DSKGPU_ERR_ARG;
     use_device(ctx);
-    if (ctx->nparts == 0) FAIL(DSKGPU_ERR_STATE, "xchg_plan before xchg_part_counts");
-    const u32 W = (u32)ctx->cfg.world_size, P = ctx->nparts;
-    ctx->xchg_matrix.assign(all_counts, all_counts + (size_t)W * 2 * P);
-    std::vector<u64> off; u64 tot = 0;
-    xchg_layout(W, P, all_counts, (u32)ctx->cfg.rank, 0, off, &ctx->owned_recs, &ctx->owned_kmers, &tot);
-    ctx->my_nrec_owned = tot;
-    int rc = ensure(ctx, ctx->precs, tot * (u64)ctx->RW * 8 + 64); if (rc) return rc;
+    if (!ctx->planned) FAIL(DSKGPU_ERR_STATE, "xchg_counts before xchg_plan");
+    const u32 W = (u32)ctx->cfg.world_size;
+    const u64 nq = (u64)W * ctx->h_hdr->PW, qcap = ((u64)1 << ctx->bin_level) + W;
+    const u64* lcnt_q = (const u64*)ctx->gk_q.p + 2 * qcap;
+    CK(cudaMemcpyAsync(d_out, lcnt_q, nq * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((u64*)d_out + nq, ((const PlanHdr*)ctx->pl_hdr.p)->send_recs, (size_t)W * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_ensure_recv(dskgpu_ctx* ctx, uint64_t capacity_records)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
+    if (!ctx->planned) FAIL(DSKGPU_ERR_STATE, "xchg_ensure_recv before xchg_plan");
+    const u64 want = std::max<u64>(capacity_records, ctx->h_hdr->need_recs[ctx->cfg.rank]);
+    int rc = ensure(ctx, ctx->precs, want * (u64)ctx->RW * 8 + 64); if (rc) return rc;
     ctx->xchg_planned = true;
     return DSKGPU_OK;
 }
@@ -1434,8 +1433,8 @@ int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes)
 {
     if (!ctx) return DSKGPU_ERR_ARG;
     use_device(ctx);
-    if (!ctx->xchg_planned) FAIL(DSKGPU_ERR_STATE, "xchg_recv_buffer before xchg_plan");
-    if (d_recv) *d_recv = ctx->precs.p; if (bytes) *bytes = (size_t)(ctx->my_nrec_owned * (u64)ctx->RW * 8);
+    if (!ctx->xchg_planned) FAIL(DSKGPU_ERR_STATE, "xchg_recv_buffer before xchg_ensure_recv");
+    if (d_recv) *d_recv = ctx->precs.p; if (bytes) *bytes = ctx->precs.cap;
     return DSKGPU_OK;
 }
 
@@ -1443,7 +1442,7 @@ int dskgpu_xchg_ipc_handle(dskgpu_ctx* ctx, void* handle64)
 {
     if (!ctx || !handle64) return DSKGPU_ERR_ARG;
     use_device(ctx);
-    if (!ctx->xchg_planned) FAIL(DSKGPU_ERR_STATE, "xchg_ipc_handle before xchg_plan");
+    if (!ctx->xchg_planned) FAIL(DSKGPU_ERR_STATE, "xchg_ipc_handle before xchg_ensure_recv");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, ctx->precs.p));
@@ -1470,119 +1469,33 @@ int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv)
     return DSKGPU_OK;
 }
 
-// fused partition scatter + all-to-all: every record is stored straight into its owner's receive buffer
-// (peer pointers: NVLink P2P stores), at offsets every rank derives from the all-gathered count matrix
-int dskgpu_xchg_scatter(dskgpu_ctx* ctx)
+// Local scatter into owner-major order, then this rank's chunk for every other rank crosses NVLink as ONE contiguous copy
+// per peer (k_xchg_send: peer stores through the CUDA-IPC / peer-access pointers, no NCCL on the data path).  The rank's own
+// chunk is not copied at all: the counting kernel reads it where the scatter put it.
+int dskgpu_xchg_scatter(dskgpu_ctx* ctx, const void* d_recv_counts, const void* d_send_matrix)
 {
-    if (!ctx) return DSKGPU_ERR_ARG;
+    if (!ctx || !d_recv_counts || !d_send_matrix) return DSKGPU_ERR_ARG;
     use_device(ctx);
-    if (!ctx->xchg_planned || ctx->peer_recv.size() != (size_t)ctx->cfg.world_size) FAIL(DSKGPU_ERR_STATE, "xchg_scatter before xchg_plan / xchg_set_peers");
-    const u32 W = (u32)ctx->cfg.world_size, P = ctx->nparts, me = (u32)ctx->cfg.rank;
-    std::vector<u64*> dst(P, nullptr);
-    std::vector<u64> off;
-    for (u32 o = 0; o < W; o++) {
-        xchg_layout(W, P, ctx->xchg_matrix.data(), o, me, off, nullptr, nullptr, nullptr);
-        for (u32 p = o; p < P; p += W) dst[p] = (u64*)ctx->peer_recv[o] + off[p] * ctx->RW;
-    }
-    int rc = ctx->KW == 1 ? stage_scatter<1>(ctx, dst) : stage_scatter<2>(ctx, dst);
-    if (rc) return rc;
-    ctx->xchg_scattered = true;
-    return DSKGPU_OK;
-}
-
-// ---- exchange v2: metadata stays on the device, records travel as whole partition segments ---------------------------
-// The per-record peer stores of xchg_scatter cross NVLink as isolated 16-byte writes; here the records are first scattered
-// into partition order in local HBM (the single-GPU kernel) and every (partition, sender) segment -- ~17 KB on C2 -- is
-// then copied to its owner's receive buffer with coalesced 16-byte vector stores.  The bin histogram is all-reduced and
-// the per-partition counts are all-gathered by the caller on DEVICE buffers (NCCL), so no metadata crosses the host twice.
-int dskgpu_xchg2_hist(dskgpu_ctx* ctx, void* d_out)
-{
-    if (!ctx || !d_out) return DSKGPU_ERR_ARG;
-    use_device(ctx);
-    int rc = stage_totals(ctx); if (rc) return rc;
-    if (!ctx->global_set) FAIL(DSKGPU_ERR_STATE, "xchg2_hist before xchg_set_global (the ranks must agree on the bin level)");
-    if ((rc = fetch_local_bin_hist(ctx))) return rc;
-    const void* src = ctx->bin_level == NBINS_FINE_LOG2 ? ctx->bin_hist.p : ctx->bin_fold.p;
-    CK(cudaMemcpyAsync(d_out, src, sizeof(unsigned long long) * ((size_t)2 << ctx->bin_level), cudaMemcpyDeviceToDevice, ctx->stream));
-    return DSKGPU_OK;
-}
-
-int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist, uint64_t* local_counts, uint64_t* need_records, uint32_t* nparts)
-{
-    if (!ctx || !d_global_hist) return DSKGPU_ERR_ARG;
-    use_device(ctx);
-    if (!ctx->hist_fetched) FAIL(DSKGPU_ERR_STATE, "xchg2_plan before xchg2_hist");
     const u32 W = (u32)ctx->cfg.world_size, me = (u32)ctx->cfg.rank;
-    if (ctx->nparts == 0) {
-        trace(nullptr);
-        if (!ctx->h_ghist) CK(cudaMallocHost((void**)&ctx->h_ghist, sizeof(unsigned long long) * 2 * NBINS_FINE));
-        CK(cudaMemcpyAsync(ctx->h_ghist, d_global_hist, sizeof(unsigned long long) * ((size_t)2 << ctx->bin_level), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        trace("xchg2_plan: global hist on host (all-reduce done)");
-        int rc = plan_partitions(ctx, ctx->h_ghist); if (rc) return rc;
-        trace("xchg2_plan: planned");
-        const u32 P = ctx->nparts;
-        // receive-buffer layout: owned partitions in increasing id; x_need[r] = records rank r receives
-        ctx->x_need.assign(W, 0);
-        std::vector<u64> hoff((size_t)2 * P + 1, 0);               // [0..P] local prefix, [P+1..2P] base of p in its owner's buffer
-        for (u32 p = 0; p < P; p++) { hoff[p + 1] = hoff[p] + ctx->h_part_recs[p]; hoff[P + 1 + p] = ctx->x_need[p % W]; ctx->x_need[p % W] += ctx->g_part_recs[p]; }
-        ctx->owned_recs.clear(); ctx->owned_kmers.clear();
-        for (u32 p = me; p < P; p += W) { ctx->owned_recs.push_back(ctx->g_part_recs[p]); ctx->owned_kmers.push_back(ctx->g_part_kmers[p]); }
-        ctx->my_nrec_owned = ctx->x_need[me];
-        if ((rc = ensure(ctx, ctx->xoff, hoff.size() * 8))) return rc;
-        if ((rc = ensure_host(ctx, ctx->hb_off, hoff.size() * 8))) return rc;
-        memcpy(ctx->hb_off.p, hoff.data(), hoff.size() * 8);
-        CK(cudaMemcpyAsync(ctx->xoff.p, ctx->hb_off.p, hoff.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-        trace("xchg2_plan: layout tables queued");
-    }
-    const u32 P = ctx->nparts;
-    if (nparts) *nparts = P;
-    if (local_counts) for (u32 p = 0; p < P; p++) local_counts[p] = ctx->h_part_recs[p];
-    if (need_records) for (u32 r = 0; r < W; r++) need_records[r] = ctx->x_need[r];
-    return DSKGPU_OK;
-}
-
-int dskgpu_xchg2_ensure_recv(dskgpu_ctx* ctx, uint64_t capacity_records)
-{
-    if (!ctx) return DSKGPU_ERR_ARG;
-    use_device(ctx);
-    if (ctx->nparts == 0) FAIL(DSKGPU_ERR_STATE, "xchg2_ensure_recv before xchg2_plan");
-    const u64 want = std::max<u64>(capacity_records, ctx->my_nrec_owned);
-    int rc = ensure(ctx, ctx->precs, want * (u64)ctx->RW * 8 + 64); if (rc) return rc;
-    ctx->xchg_planned = true;
-    return DSKGPU_OK;
-}
-
-int dskgpu_xchg2_scatter(dskgpu_ctx* ctx, const void* d_matrix)
-{
-    if (!ctx || !d_matrix) return DSKGPU_ERR_ARG;
-    use_device(ctx);
-    if (!ctx->xchg_planned || ctx->peer_recv.size() != (size_t)ctx->cfg.world_size) FAIL(DSKGPU_ERR_STATE, "xchg2_scatter before xchg2_ensure_recv / xchg_set_peers");
-    const u32 W = (u32)ctx->cfg.world_size, P = ctx->nparts, me = (u32)ctx->cfg.rank;
-    if (ctx->precs.cap < ctx->my_nrec_owned * (u64)ctx->RW * 8) FAIL(DSKGPU_ERR_STATE, "receive buffer smaller than the planned layout");
-    int rc;
-    if ((rc = ensure(ctx, ctx->lrecs, ctx->local_nrec * (u64)ctx->RW * 8 + 64))) return rc;
-    if ((rc = ensure(ctx, ctx->xpeers, (size_t)W * 8))) return rc;
-    std::vector<u64*> dst(P);
-    { u64 o = 0; for (u32 p = 0; p < P; p++) { dst[p] = (u64*)ctx->lrecs.p + o * ctx->RW; o += ctx->h_part_recs[p]; } }
-    rc = ctx->KW == 1 ? stage_scatter<1>(ctx, dst) : stage_scatter<2>(ctx, dst);
+    if (W < 2) FAIL(DSKGPU_ERR_STATE, "xchg_scatter needs world_size > 1");
+    if (!ctx->xchg_planned || ctx->peer_recv.size() != (size_t)W) FAIL(DSKGPU_ERR_STATE, "xchg_scatter before xchg_ensure_recv / xchg_set_peers");
+    if (ctx->precs.cap < ctx->h_hdr->need_recs[me] * (u64)ctx->RW * 8) FAIL(DSKGPU_ERR_STATE, "receive buffer smaller than the planned layout");
+    int rc = ctx->KW == 1 ? stage_scatter<1>(ctx) : stage_scatter<2>(ctx);
     if (rc) return rc;
-    if (ctx->local_nrec) {
+    if ((rc = stage_bases(ctx, d_recv_counts, d_send_matrix))) return rc;
+    u64 remote = 0;
+    for (u32 o = 0; o < W; o++) if (o != me) remote += ctx->h_hdr->send_recs[o];
+    if (remote) {
         SpanGuard g(ctx, SPAN_PART);
-        CK(cudaMemcpyAsync(ctx->xpeers.p, ctx->peer_recv.data(), (size_t)W * 8, cudaMemcpyHostToDevice, ctx->stream));
-        const unsigned grid = (unsigned)std::min<u32>(P, (u32)ctx->num_sms * 8);
+        const unsigned per_peer = (unsigned)std::max<u64>(1, std::min<u64>((remote / (W - 1) * (u64)(ctx->RW / 2) + 1023) / 1024, (u64)ctx->num_sms * 8 / (W - 1)));
         cudaEvent_t xa = get_event(ctx), xb = get_event(ctx);
         cudaEventRecord(xa, ctx->stream);
-        k_xchg_copy<<<grid, 256, 0, ctx->stream>>>((const ulonglong2*)ctx->lrecs.p, (const u64*)ctx->xoff.p, (const u64*)d_matrix,
-                                                   (ulonglong2* const*)ctx->xpeers.p, W, me, P, (u32)ctx->RW / 2); LAUNCHED();
+        k_xchg_send<<<per_peer * (W - 1), 256, 0, ctx->stream>>>((const ulonglong2*)ctx->lrecs.p, (const XchgTab*)ctx->xtab.p, W, me, (u32)ctx->RW / 2); LAUNCHED();
         cudaEventRecord(xb, ctx->stream);
         ctx->spans.push_back({xa, xb, SPAN_XCHG});
         CK(cudaGetLastError());
-        // bytes this rank stores into OTHER ranks' HBM (NVLink); its own partitions are a local copy
-        u64 remote = 0;
-        for (u32 p = 0; p < P; p++) if (p % W != me) remote += ctx->h_part_recs[p];
-        ctx->xchg_bytes_out = remote * (u64)ctx->RW * 8;
     }
+    ctx->xchg_bytes_out = remote * (u64)ctx->RW * 8;                 // bytes stored into OTHER ranks' HBM (NVLink)
     ctx->xchg_scattered = true;
     return DSKGPU_OK;
 }
@@ -1662,6 +1575,7 @@ int dskgpu_multi_finish(dskgpu_ctx* const* ctxs, int n)
 {
     dskgpu_ctx* ctx = (ctxs && n > 0) ? ctxs[0] : nullptr;
     if (!ctx) return DSKGPU_ERR_ARG;
+    if (n > PLAN_MAXW) FAIL(DSKGPU_ERR_ARG, "multi_finish: %d contexts beyond the %d ranks of one exchange", n, PLAN_MAXW);
     for (int r = 0; r < n; r++) {
         if (!ctxs[r]) return DSKGPU_ERR_ARG;
         if (ctxs[r]->cfg.world_size != n || ctxs[r]->cfg.rank != r) FAIL(DSKGPU_ERR_ARG, "multi_finish: ctxs[%d] must have rank %d of world_size %d", r, r, n);
@@ -1680,26 +1594,48 @@ int dskgpu_multi_finish(dskgpu_ctx* const* ctxs, int n)
         cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
         if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError(); else CK(e);
     }
+    auto sync_all = [&]() -> int { for (int r = 0; r < n; r++) { ctx = ctxs[r]; use_device(ctx); CK(cudaStreamSynchronize(ctx->stream)); } ctx = ctxs[0]; return 0; };
     // 1. job totals (k-mers, records, density sample) -> the same bin level and partition size everywhere
     uint64_t g4[4] = {0, 0, 0, 0};
     for (int r = 0; r < n; r++) { uint64_t l4[4]; if ((rc = dskgpu_xchg_prepare(ctxs[r], l4))) return rc; for (int i = 0; i < 4; i++) g4[i] += l4[i]; }
     int level = 0;
     for (int r = 0; r < n; r++) { int lv = 0; if ((rc = dskgpu_xchg_set_global(ctxs[r], g4, &lv))) return rc; if (r && lv != level) FAIL(DSKGPU_ERR_STATE, "multi_finish: ranks disagree on the bin level"); level = lv; }
-    // 2. whole-job bin histogram (host sum of the ranks' pinned copies)
-    const size_t nh = (size_t)2 << level;
-    std::vector<uint64_t> gh(nh, 0), lh(nh);
-    for (int r = 0; r < n; r++) { if ((rc = dskgpu_xchg_bin_hist(ctxs[r], lh.data()))) return rc; for (size_t i = 0; i < nh; i++) gh[i] += lh[i]; }
-    // 3. every rank plans the same partitions; the per-partition counts of all ranks form the layout matrix
-    uint32_t P = 0;
-    if ((rc = dskgpu_xchg_part_counts(ctxs[0], gh.data(), nullptr, &P))) return rc;
-    std::vector<uint64_t> all((size_t)n * 2 * P);
-    for (int r = 0; r < n; r++) { uint32_t Pr = 0; if ((rc = dskgpu_xchg_part_counts(ctxs[r], gh.data(), all.data() + (size_t)r * 2 * P, &Pr))) return rc; if (Pr != P) FAIL(DSKGPU_ERR_STATE, "multi_finish: ranks disagree on the partition count"); }
-    // 4. receive buffers, peer pointers (same process: plain device pointers), scatter straight into the owners' HBM
+    // 2. whole-job bin histogram: every device sums the ranks' histograms through peer pointers (the stand-in for the all-reduce)
+    const u64 nh = (u64)2 << level;
+    PtrList lst; memset(&lst, 0, sizeof lst);
+    for (int r = 0; r < n; r++) { ctx = ctxs[r]; use_device(ctx); const void* p = nullptr; if ((rc = fold_local_hist(ctx, &p))) return rc; lst.p[r] = (const u64*)p; }
+    if ((rc = sync_all())) return rc;
+    for (int r = 0; r < n; r++) {
+        ctx = ctxs[r]; use_device(ctx);
+        if ((rc = ensure(ctx, ctx->ghist, nh * 8))) return rc;
+        k_sum_hists<<<(unsigned)std::min<u64>((nh + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(lst, n, nh, (u64*)ctx->ghist.p); LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    // 3. every rank plans the same partitions (on its device)
+    for (int r = 0; r < n; r++) { ctx = ctxs[r]; use_device(ctx); if ((rc = plan_device(ctx, ctx->ghist.p))) return rc; }
+    ctx = ctxs[0];
+    const u32 P = ctx->h_hdr->P, PW = ctx->h_hdr->PW;
+    for (int r = 1; r < n; r++) if (ctxs[r]->h_hdr->P != P || ctxs[r]->h_hdr->nlight != ctx->h_hdr->nlight) FAIL(DSKGPU_ERR_STATE, "multi_finish: ranks disagree on the plan");
+    // 4. per-partition counts to the owners (the stand-in for the all-to-all), chunk sizes to everybody, receive buffers
+    std::vector<u64> S((size_t)n * n);
+    for (int s = 0; s < n; s++) for (int o = 0; o < n; o++) S[(size_t)s * n + o] = ctxs[s]->h_hdr->send_recs[o];
     std::vector<void*> recv(n, nullptr);
-    for (int r = 0; r < n; r++) { if ((rc = dskgpu_xchg_plan(ctxs[r], all.data()))) return rc; size_t nb = 0; if ((rc = dskgpu_xchg_recv_buffer(ctxs[r], &recv[r], &nb))) return rc; }
-    for (int r = 0; r < n; r++) { if ((rc = dskgpu_xchg_set_peers(ctxs[r], recv.data()))) return rc; if ((rc = dskgpu_xchg_scatter(ctxs[r]))) return rc; }
-    for (int r = 0; r < n; r++) if ((rc = dskgpu_xchg_sync(ctxs[r]))) return rc;       // every record has landed before anyone counts
-    // 5. every rank counts what it owns (the stage blocks on its own stream: one host thread per rank)
+    const u64 qcap = ((u64)1 << level) + (u64)n;
+    for (int o = 0; o < n; o++) {
+        ctx = ctxs[o]; use_device(ctx);
+        if ((rc = ensure(ctx, ctx->ghist, std::max<u64>(nh, (u64)n * PW) * 8))) return rc;          // the histogram is dead: reuse as [W][PW] count rows
+        if ((rc = ensure(ctx, ctx->xS, (size_t)n * n * 8))) return rc;
+        for (int s = 0; s < n; s++)
+            CK(cudaMemcpyAsync((u64*)ctx->ghist.p + (u64)s * PW, (const u64*)ctxs[s]->gk_q.p + 2 * qcap + (u64)o * PW, (size_t)PW * 8, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->xS.p, S.data(), S.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));                                                       // S is pageable host memory
+        if ((rc = dskgpu_xchg_ensure_recv(ctx, 0))) return rc;
+        recv[o] = ctx->precs.p;
+    }
+    // 5. scatter + one contiguous copy per peer, straight into the owners' HBM (same process: plain device pointers)
+    for (int r = 0; r < n; r++) { if ((rc = dskgpu_xchg_set_peers(ctxs[r], recv.data()))) return rc; if ((rc = dskgpu_xchg_scatter(ctxs[r], ctxs[r]->ghist.p, ctxs[r]->xS.p))) return rc; }
+    if ((rc = sync_all())) return rc;                                                                 // every record has landed before anyone counts
+    // 6. every rank counts what it owns (the stage blocks on its own stream: one host thread per rank)
     std::vector<int> rcs(n, 0);
     std::vector<std::thread> th;
     for (int r = 0; r < n; r++) th.emplace_back([&, r] { rcs[r] = dskgpu_finish(ctxs[r]); });
@@ -1708,19 +1644,23 @@ int dskgpu_multi_finish(dskgpu_ctx* const* ctxs, int n)
     return DSKGPU_OK;
 }
 
-// host-only: where sender `sender`'s records of every partition land in their owners' receive buffers
-// (offsets in records; used by the exchange itself and by the CPU test-suite)
-int dskgpu_xchg_layout(int world_size, uint32_t nparts, const uint64_t* all_counts, int sender, uint64_t* offsets /*[nparts]*/,
-                       uint64_t* recv_records /*[world_size]*/)
+// host-only mirror of the receive layout of rank `owner` (CPU test-suite): counts[s * W * PW + q] = records rank s holds for
+// the partition at position q of the q-ordered tables.  The receive buffer holds the chunks of the senders s != owner in
+// rank order (the owner's own chunk never moves): region_base[s] = first record of sender s's chunk (region_base[W] = records
+// received); seg_off[s * PW + j] = first record of (sender s, owned job j) -- inside the receive buffer for s != owner,
+// inside the owner's own chunk for s == owner.
+int dskgpu_xchg_layout(int world_size, uint32_t parts_per_rank, const uint64_t* counts, int owner, uint64_t* region_base, uint64_t* seg_off)
 {
-    if (world_size < 1 || !all_counts || !offsets) return DSKGPU_ERR_ARG;
-    std::vector<u64> off;
-    for (u32 o = 0; o < (u32)world_size; o++) {
-        u64 tot = 0;
-        xchg_layout((u32)world_size, nparts, all_counts, o, (u32)sender, off, nullptr, nullptr, &tot);
-        for (u32 p = o; p < nparts; p += (u32)world_size) offsets[p] = off[p];
-        if (recv_records) recv_records[o] = tot;
+    if (world_size < 1 || world_size > PLAN_MAXW || !counts || !region_base || !seg_off || owner < 0 || owner >= world_size) return DSKGPU_ERR_ARG;
+    const u32 W = (u32)world_size, PW = parts_per_rank;
+    u64 base = 0;
+    for (u32 s = 0; s < W; s++) {
+        region_base[s] = base;
+        u64 o = (s == (u32)owner) ? 0 : base;
+        for (u32 j = 0; j < PW; j++) { seg_off[(u64)s * PW + j] = o; o += counts[(u64)s * W * PW + (u64)owner * PW + j]; }
+        if (s != (u32)owner) base = o;
     }
+    region_base[W] = base;
     return DSKGPU_OK;
 }
 
@@ -1735,10 +1675,7 @@ int dskgpu_recount(dskgpu_ctx* ctx, const int64_t* abundance_min)
     const u64 cap_request = ctx->st.kmers_nb_distinct + 1024;
     int rc = reset_count_state(ctx); if (rc) return rc;
     ctx->state = 0;
-    const bool owned = ctx->cfg.world_size > 1;
-    const std::vector<u64>& pr = owned ? ctx->owned_recs : ctx->h_part_recs;
-    const std::vector<u64>& pk = owned ? ctx->owned_kmers : ctx->h_part_kmers;
-    rc = ctx->KW == 1 ? stage_count<1>(ctx, (const u64*)ctx->precs.p, pr, pk, cap_request) : stage_count<2>(ctx, (const u64*)ctx->precs.p, pr, pk, cap_request);
+    rc = ctx->KW == 1 ? stage_count<1>(ctx, cap_request) : stage_count<2>(ctx, cap_request);
     if (rc) ctx->state = 2;                                        // failed: only reset / destroy are valid now
     return rc;
 }
@@ -1970,39 +1907,62 @@ int64_t dskgpu_selftest_wide_superkmers(const uint8_t* codes, size_t n, int k, i
     return run(std::integral_constant<int, 4>());
 }
 
-// host-only run of the partition planner (plan_partitions_host): what every rank derives from the all-reduced bin
-// histogram.  global_hist / local_hist: [2 << level] (records per bin, then k-mers per bin).  Outputs: bin2part[1 << level],
-// and per partition (capacity max_parts) the whole-job k-mers and this rank's records.  Returns the number of partitions
-// (a multiple of world_size), or -1 when max_parts is too small.  No device is touched.
+// host-only run of the partition planner (plan_host, the sequential mirror of the device planner of plan.cuh): what every
+// rank derives from the all-reduced bin histogram.  global_hist / local_hist: [2 << level] (records per bin, then k-mers per
+// bin).  Outputs: bin2part[1 << level] (partition ids: light partitions first, heavy ones after), and per partition (capacity
+// max_parts) the whole-job k-mers and this rank's records.  Returns the number of partitions, or -1 when max_parts is too
+// small.  No device is touched.
 int64_t dskgpu_selftest_plan(int level, const uint64_t* global_hist, const uint64_t* local_hist, int world_size, int nb_counts,
                              uint32_t smem_slots, double density, int count_mode, int forced_nb_partitions,
                              uint32_t* bin2part, uint64_t* part_kmers, uint64_t* part_local_recs, size_t max_parts)
 {
-    if (level < NBINS_LOG2 || level > NBINS_FINE_LOG2 || !global_hist || !local_hist || world_size < 1) return DSKGPU_ERR_ARG;
+    if (level < NBINS_LOG2 || level > NBINS_FINE_LOG2 || !global_hist || !local_hist || world_size < 1 || world_size > PLAN_MAXW) return DSKGPU_ERR_ARG;
     dskgpu_ctx* ctx = new dskgpu_ctx();
     dskgpu_config_default(&ctx->cfg);
     ctx->cfg.world_size = world_size; ctx->cfg.count_mode = count_mode; ctx->cfg.nb_partitions = forced_nb_partitions;
     ctx->NB = nb_counts; ctx->smem_cap = smem_slots; ctx->density = density; ctx->density_known = true; ctx->bin_level = level;
-    std::vector<unsigned long long> lh(local_hist, local_hist + ((size_t)2 << level));
-    ctx->h_bin_hist = lh.data();
-    plan_partitions_host(ctx, (const unsigned long long*)global_hist);
-    if (getenv("DSKGPU_PLAN_TIMING")) {                                   // warm re-runs on the same context, as in a job loop
-        for (int i = 0; i < 3; i++) {
-            const auto t0 = std::chrono::steady_clock::now();
-            plan_partitions_host(ctx, (const unsigned long long*)global_hist);
-            fprintf(stderr, "[plan] level %d: %.3f ms\n", level, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-        }
-    }
-    const u32 P = ctx->nparts;
-    int64_t ret = (int64_t)P;
-    if (P > max_parts) ret = -1;
-    else {
-        for (u32 b = 0; b < (1u << level); b++) bin2part[b] = ctx->h_bin2part[b];
-        for (u32 p = 0; p < P; p++) { part_kmers[p] = ctx->g_part_kmers[p]; part_local_recs[p] = ctx->h_part_recs[p]; }
-    }
-    ctx->h_bin_hist = nullptr;
+    const u32 nb = 1u << level;
+    u64 total = 0;
+    for (u32 b = 0; b < nb; b++) total += global_hist[nb + b];
+    ctx->g_total_kmers = total;
+    const PlanParams pp = make_plan_params(ctx);
+    const u64 qcap = (u64)nb + world_size;
+    std::vector<u32> b2q(nb);
+    std::vector<u64> gk(qcap), gr(qcap), lc(qcap);
+    const PlanHdr h = plan_host(pp, (const u64*)global_hist, (const u64*)local_hist, b2q.data(), gk.data(), gr.data(), lc.data());
     delete ctx;
-    return ret;
+    if (h.P > max_parts) return -1;
+    auto q2p = [&](u32 q) { return (q % h.PW) * (u32)world_size + q / h.PW; };
+    for (u32 b = 0; b < nb; b++) bin2part[b] = q2p(b2q[b]);
+    for (u32 p = 0; p < h.P; p++) { const u32 q = plan_q(p, (u32)world_size, h.PW); part_kmers[p] = gk[q]; part_local_recs[p] = lc[q]; }
+    return (int64_t)h.P;
+}
+
+// the plan a context derived on the DEVICE (after dskgpu_finish / dskgpu_xchg_plan), copied to the host for the tests that
+// compare it with the host mirror: bin2part[1 << level] (partition ids), per partition whole-job k-mers / records and this
+// rank's records.  Returns the number of partitions (capacity max_parts), the level in *level.
+int64_t dskgpu_debug_plan(dskgpu_ctx* ctx, int* level, uint32_t* bin2part, uint64_t* part_kmers, uint64_t* part_recs, uint64_t* part_local_recs, size_t max_parts)
+{
+    if (!ctx) return DSKGPU_ERR_ARG;
+    use_device(ctx);
+    if (!ctx->planned) FAIL(DSKGPU_ERR_STATE, "debug_plan before the plan exists");
+    const PlanHdr& h = *ctx->h_hdr;
+    const u32 W = (u32)ctx->cfg.world_size, nb = 1u << ctx->bin_level;
+    if (level) *level = ctx->bin_level;
+    if (h.P > max_parts) return -1;
+    const u64 qcap = (u64)nb + W, nq = (u64)W * h.PW;
+    std::vector<u32> b2q(nb); std::vector<u64> t(3 * qcap);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(b2q.data(), ctx->bin2part.p, (size_t)nb * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(t.data(), ctx->gk_q.p, 3 * qcap * 8, cudaMemcpyDeviceToHost));
+    (void)nq;
+    auto q2p = [&](u32 q) { return (q % h.PW) * W + q / h.PW; };
+    if (bin2part) for (u32 b = 0; b < nb; b++) bin2part[b] = q2p(b2q[b]);
+    for (u32 p = 0; p < h.P; p++) {
+        const u32 q = plan_q(p, W, h.PW);
+        if (part_kmers) part_kmers[p] = t[q]; if (part_recs) part_recs[p] = t[qcap + q]; if (part_local_recs) part_local_recs[p] = t[2 * qcap + q];
+    }
+    return (int64_t)h.P;
 }
 
 // host model of the wide spans (kmer_wide.cuh, k <= 127): canonical k-mers of a code stream computed two ways -- rolling

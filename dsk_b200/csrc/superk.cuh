@@ -263,25 +263,25 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
 }
 
 // ---- K3: scatter records into partition order --------------------------------------------------------------------
-// bin2part[bin >> bin_shift] = partition of a bin of the planned level (planned on the host from the exact bin histogram);
-// dst_base[p] = device
-// pointer (local or NVLink peer) where this rank's records of partition p start; cursor[p] = records already placed.
-// Partitions are small (a few thousand records) and there are tens of thousands of them, so a record takes one
-// L2 atomic on its partition's cursor and one 16/32-byte vector store.
+// bin2q[bin >> bin_shift] = position of the bin's partition in q order (plan.cuh: owner-major, so that every owner's
+// partitions -- and after this kernel every owner's RECORDS -- are one contiguous chunk); cursor[q] starts at the first
+// record slot of partition q (a copy of the exclusive prefix of this rank's per-partition record counts), so a record takes
+// one L2 atomic that returns its final position and one 16/32-byte vector store.  There are 20 K (C2) to millions of
+// partitions against ~8 K records per CTA, so there is nothing to aggregate per (CTA, partition).
 constexpr int SC_THREADS = 256;
 template <int KW>
 __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(const u64* __restrict__ recs, const u32* __restrict__ rec_meta, u64 nrec,
-                                                             const u32* __restrict__ bin2part, int bin_shift, u64* const* __restrict__ dst_base,
+                                                             const u32* __restrict__ bin2q, int bin_shift, u64* __restrict__ out,
                                                              unsigned long long* __restrict__ cursor)
 {
     constexpr int RW = 2 * KW;
     const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(out);
     for (u64 i = (u64)blockIdx.x * SC_THREADS + threadIdx.x; i < nrec; i += (u64)gridDim.x * SC_THREADS) {
-        const u32 p = __ldg(bin2part + ((rec_meta[i] & (NBINS_FINE - 1)) >> bin_shift));
+        const u32 q = __ldg(bin2q + ((rec_meta[i] & (NBINS_FINE - 1)) >> bin_shift));
         ulonglong2 a = src[(RW / 2) * i], b;
         if constexpr (RW == 4) b = src[2 * i + 1];
-        const u64 d = atomicAdd(&cursor[p], 1ULL);
-        ulonglong2* dst = reinterpret_cast<ulonglong2*>(dst_base[p]);
+        const u64 d = atomicAdd(&cursor[q], 1ULL);
         if constexpr (RW == 2) dst[d] = a;
         else { dst[2 * d] = a; dst[2 * d + 1] = b; }
     }
@@ -297,25 +297,6 @@ __global__ void k_fold_bins(const unsigned long long* __restrict__ fine, int shi
         unsigned long long acc = 0;
         for (u32 j = 0; j < per; j++) acc += src[j];
         out[i] = acc;
-    }
-}
-
-// exchange v2: this rank's segment of every partition (contiguous in `lrecs`) goes to the partition owner's receive buffer.
-// xoff[0..P] = local prefix (records), xoff[P+1+p] = first record of partition p in its owner's buffer; matrix[s*P + p] =
-// records of partition p held by rank s (all-gathered on the device); senders are laid out in rank order inside a partition.
-// One CTA per segment, 16-byte vector loads / stores: NVLink sees long contiguous writes instead of isolated records.
-__global__ void __launch_bounds__(256) k_xchg_copy(const ulonglong2* __restrict__ lrecs, const u64* __restrict__ xoff, const u64* __restrict__ matrix,
-                                                   ulonglong2* const* __restrict__ peers, u32 W, u32 me, u32 P, u32 v_per_rec)
-{
-    for (u32 p = blockIdx.x; p < P; p += gridDim.x) {
-        const u64 b = xoff[p], n = xoff[p + 1] - b;
-        if (n == 0) continue;
-        u64 before = xoff[P + 1 + p];
-        for (u32 s = 0; s < me; s++) before += matrix[(u64)s * P + p];
-        const ulonglong2* src = lrecs + b * v_per_rec;
-        ulonglong2* dst = peers[p % W] + before * v_per_rec;
-        const u64 nv = n * v_per_rec;
-        for (u64 i = threadIdx.x; i < nv; i += 256) dst[i] = src[i];
     }
 }
 

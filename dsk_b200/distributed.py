@@ -1,11 +1,14 @@
 """Multi-GPU orchestration of the counting path: one process per GPU, torch.distributed for the plumbing.
 
 Every rank parses its own slice of the reads; super-k-mer records are routed to the rank owning their partition
-(owner(p) = p % world_size) by the partition-scatter kernel itself, which stores straight into the owners' HBM
-through CUDA-IPC peer pointers (NVLink P2P) -- the role the reference gives to its temp files
-(SuperKmerBinFiles, G/src/gatb/tools/storage/impl/Storage.cpp:310-589).  Only tiny metadata crosses
-torch.distributed: four job totals and the minimizer-bin histogram (all-reduce, 1-16 MB), the per-partition count matrix (all-gather) and
-the IPC handles.
+(owner(p) = p % world_size) -- the role the reference gives to its temp files (SuperKmerBinFiles,
+G/src/gatb/tools/storage/impl/Storage.cpp:310-589).  The partitions are planned ON THE DEVICE by every rank from the
+all-reduced minimizer-bin histogram (dsk_b200/csrc/plan.cuh); the local records are scattered into owner-major partition
+order, so what crosses NVLink is ONE contiguous chunk per (sender, receiver) pair, stored by the library's own copy kernel
+through CUDA-IPC peer pointers (no NCCL on the data path).  torch.distributed only carries metadata, as DEVICE tensors on
+the stream the kernels run on: four job totals and the bin histogram (all-reduce), the per-partition record counts
+(all-to-all of rows), the chunk sizes (all-gather), the IPC handles when a receive buffer had to grow, and a one-element
+all-reduce that orders "every chunk has landed" before the counting kernels without a host-side barrier.
 """
 import ctypes as C
 
@@ -14,16 +17,18 @@ import numpy as np
 from . import _lib
 
 
-def exchange_layout(world_size, all_counts, sender):
-    """offsets[p] of `sender`'s records inside owner(p)'s receive buffer + records each rank receives (host only)."""
-    all_counts = np.ascontiguousarray(all_counts, dtype=np.uint64)
-    P = all_counts.shape[1] // 2
-    off = np.zeros(P, dtype=np.uint64)
-    recv = np.zeros(world_size, dtype=np.uint64)
-    rc = _lib.lib().dskgpu_xchg_layout(world_size, P, all_counts.ctypes.data, sender, off.ctypes.data, recv.ctypes.data)
+def exchange_layout(world_size, parts_per_rank, counts, owner):
+    """host mirror of rank `owner`'s receive layout (dskgpu_xchg_layout): counts[s] = rank s's records per partition in q
+    order ([W][W * PW]).  Returns (region_base[W + 1], seg_off[W][PW])."""
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    W, PW = world_size, parts_per_rank
+    assert counts.shape == (W, W * PW)
+    base = np.zeros(W + 1, dtype=np.uint64)
+    seg = np.zeros((W, PW), dtype=np.uint64)
+    rc = _lib.lib().dskgpu_xchg_layout(W, PW, counts.ctypes.data, owner, base.ctypes.data, seg.ctypes.data)
     if rc != 0:
         raise RuntimeError("dskgpu_xchg_layout failed: %d" % rc)
-    return off, recv
+    return base, seg
 
 
 def all_gather_counts(dist, counts, device=None):
@@ -44,11 +49,8 @@ def _grow_plan(need, announced):
 
 
 def distributed_finish(eng, dist, device):
-    """Runs the exchange + local counting on every rank (call after the pushes).
-
-    Protocol (include/dskgpu.h "exchange v2"): all-reduce of four job totals, all-reduce of the bin histogram and
-    all-gather of the per-partition record counts on DEVICE buffers (NCCL), CUDA-IPC handles only when a receive buffer
-    had to grow, then the records cross NVLink as whole partition segments and every rank counts what it owns."""
+    """Runs the exchange + local counting on every rank (call after the pushes).  Protocol: include/dskgpu.h "multi-GPU
+    exchange".  Host syncs of the step: the totals (push kernels drained), the four summed totals, the plan header."""
     import os
     import sys
     import time
@@ -80,94 +82,52 @@ def distributed_finish(eng, dist, device):
     level = eng.xchg_set_global(g4.cpu().numpy().astype(np.uint64))
     mark("allreduce totals")
     G = torch.empty(2 << level, dtype=torch.int64, device=device)             # (records, k-mers) per minimizer bin
-    eng.xchg2_hist(G.data_ptr())
+    eng.xchg_hist(G.data_ptr())
     to_torch()
     dist.all_reduce(G)                                                         # every rank plans the same partitions
     to_lib()
-    counts, need = eng.xchg2_plan(G.data_ptr())
-    mark("histogram allreduce + plan")
-    mine = torch.from_numpy(counts.view(np.int64)).to(device)
-    M = torch.empty(W * mine.numel(), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(M, mine)                                       # [W][P] on the device; the host never reads it
-    mark("allgather counts (async)")
+    P, PW, need = eng.xchg_plan(G.data_ptr())                                  # device planner; the host reads one header
+    mark("histogram allreduce + device plan")
+    send = torch.empty(W * PW + W, dtype=torch.int64, device=device)
+    eng.xchg_counts(send.data_ptr())
+    to_torch()
+    rows = torch.empty(W * PW, dtype=torch.int64, device=device)               # row s = rank s's records of MY partitions
+    dist.all_to_all_single(rows, send[:W * PW])
+    S = torch.empty(W * W, dtype=torch.int64, device=device)                   # S[s][o] = records rank s holds for rank o
+    dist.all_gather_into_tensor(S, send[W * PW:])
+    mark("count rows all-to-all (async)")
     # receive buffers: handles travel only when somebody has to grow (every rank sees the same `need`)
     st = getattr(eng, "_xchg_state", None)
     if st is None:
         st = eng._xchg_state = {"announced": [0] * W, "ptrs": [0] * W, "handles": [None] * W}
     want = _grow_plan(need, st["announced"])
     if want != st["announced"]:
-        eng.xchg2_ensure_recv(want[rank])
+        eng.xchg_ensure_recv(want[rank])
         handle = np.frombuffer(eng.xchg_ipc_handle(), dtype=np.uint8).copy()
         hs = all_gather_counts(dist, np.frombuffer(handle.tobytes(), dtype=np.uint64), device)      # 8 x u64 per rank
         for r in range(W):
             hb = hs[r].tobytes()
             if r != rank and st["handles"][r] != hb:
+                if st["ptrs"][r]:
+                    eng.xchg_close_peer(st["ptrs"][r])                        # the peer re-allocated: drop the stale mapping
                 st["handles"][r] = hb
                 st["ptrs"][r] = eng.xchg_open_peer(hb)
         st["announced"] = want
     else:
-        eng.xchg2_ensure_recv(want[rank])
+        eng.xchg_ensure_recv(want[rank])
     eng.xchg_set_peers(st["ptrs"])
     mark("receive buffers / handles")
     to_lib()
-    eng.xchg2_scatter(M.data_ptr())
-    eng.xchg_sync()
-    mark("scatter + segment copy")
-    dist.barrier()                       # every rank's records have landed before anyone counts
-    mark("barrier")
+    eng.xchg_scatter(rows.data_ptr(), S.data_ptr())
+    to_torch()
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    dist.all_reduce(flag)                # stream-ordered: completes on a rank only after every rank's copy kernel has finished
+    to_lib()
+    mark("scatter + chunk copies + ordering all-reduce (queued)")
+    eng._xchg_keep = (G, send, rows, S, flag)                                  # alive until the kernels that read them have run
     eng.finish()
     mark("finish (count + order)")
     if tr:
         for (_, a), (name, b) in zip(marks, marks[1:]):
-            sys.stderr.write("[xchg r%d] %-32s +%8.3f ms\n" % (dist.get_rank(), name, 1e3 * (b - a)))
-    return M
-
-
-def in_process_finish(engines):
-    """Same protocol for several contexts living in ONE process (tests: N 'ranks' on one GPU, no IPC needed)."""
-    W = len(engines)
-    g4 = np.sum([e.xchg_prepare() for e in engines], axis=0, dtype=np.uint64)
-    for e in engines:
-        e.xchg_set_global(g4)
-    gh = np.sum([e.xchg_bin_hist() for e in engines], axis=0, dtype=np.uint64)
-    allc = np.stack([e.xchg_part_counts(gh) for e in engines])
-    for e in engines:
-        e.xchg_plan(allc)
-    ptrs = [e.xchg_recv_buffer()[0] for e in engines]
-    for e in engines:
-        e.xchg_set_peers(ptrs)
-        e.xchg_scatter()
-    for e in engines:
-        e.xchg_sync()
-    for e in engines:
-        e.finish()
-    return allc
-
-
-def in_process_finish_v2(engines, device="cuda"):
-    """exchange v2 for several contexts living in ONE process (tests): torch sums / stacks stand in for NCCL."""
-    import torch
-    g4 = np.sum([e.xchg_prepare() for e in engines], axis=0, dtype=np.uint64)
-    levels = [e.xchg_set_global(g4) for e in engines]
-    assert len(set(levels)) == 1
-    hs = [torch.empty(2 << levels[0], dtype=torch.int64, device=device) for _ in engines]
-    for e, h in zip(engines, hs):
-        e.xchg2_hist(h.data_ptr())
-        e.xchg_sync()
-    G = torch.stack(hs).sum(0)
-    torch.cuda.synchronize()
-    plans = [e.xchg2_plan(G.data_ptr()) for e in engines]
-    M = torch.from_numpy(np.stack([c for c, _ in plans]).view(np.int64)).to(device).contiguous()
-    torch.cuda.synchronize()
-    for e, (_, need) in zip(engines, plans):
-        assert (need == plans[0][1]).all()
-        e.xchg2_ensure_recv(int(need[e.cfg.rank]))
-    ptrs = [e.xchg_recv_buffer()[0] for e in engines]
-    for e in engines:
-        e.xchg_set_peers(ptrs)
-        e.xchg2_scatter(M.data_ptr())
-    for e in engines:
-        e.xchg_sync()
-    for e in engines:
-        e.finish()
-    return M.cpu().numpy()
+            sys.stderr.write("[xchg r%d] %-52s +%8.3f ms\n" % (dist.get_rank(), name, 1e3 * (b - a)))
+    return P

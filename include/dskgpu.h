@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DSKGPU_ABI_VERSION   2
+#define DSKGPU_ABI_VERSION   3
 #define DSKGPU_MAX_BANKS     16
 #define DSKGPU_HISTO_LEN     10001          /* bins 0..10000 (Histogram.hpp:92, length 10000) */
 #define DSKGPU_HISTO2D_DIM2  11             /* bins 0..10   (CountProcessorHistogram.hpp:173-184) */
@@ -213,62 +213,57 @@ int  dskgpu_device_count(void);
 int  dskgpu_abi_version(void);
 
 /* ---- multi-GPU exchange (replaces the SuperKmerBinFiles temp tier, Storage.cpp:310-589) --------------
- * One context per rank (one process per GPU).  Partition p is owned by rank p % world_size.  After all pushes:
- *   0. xchg_prepare             -> this rank's {k-mers, records, density-sample k-mers, density-sample distinct}; all-reduce
- *                                  (sum) the four numbers out of band, hand the sums to xchg_set_global: every rank then
- *                                  agrees on the bin level (2^16 .. 2^22 bins) and on the partition size
- *   1. xchg_bin_hist            -> this rank's (records, k-mers) per minimizer bin; all-reduce (sum) it out of band
- *                                  (torch.distributed / NCCL): every rank then plans the same partitions
- *   2. xchg_part_counts         -> per-partition record / k-mer counts of this rank; all-gather them
- *   3. xchg_plan                -> every rank derives every receive-buffer layout from the gathered matrix and
- *                                  allocates its own receive buffer (xchg_recv_buffer / xchg_ipc_handle expose it)
- *   4. xchg_set_peers + xchg_scatter -> ONE kernel scatters this rank's super-k-mer records straight into the
- *                                  owners' HBM (peer pointers from CUDA IPC: NVLink P2P stores) - the partition
- *                                  scatter and the all-to-all are the same kernel, there is no send staging
- *   5. xchg_sync, barrier out of band, then dskgpu_finish counts the owned partitions locally. */
+ * One context per rank (one process per GPU).  Partition p is owned by rank p % world_size (world_size <= 16).  All the
+ * metadata stays on the device: the caller only moves DEVICE buffers between ranks (NCCL through torch.distributed, or peer
+ * copies inside one process) and the host reads one small header.  After all pushes:
+ *   0. xchg_prepare      -> this rank's {k-mers, records, density-sample k-mers, density-sample distinct}; all-reduce (sum) the
+ *                           four numbers, hand the sums to xchg_set_global: every rank then agrees on the bin level
+ *                           (2^16 .. 2^22 bins) and on the partition size
+ *   1. xchg_hist         copies this rank's (records, k-mers) per minimizer bin, [2 * B] u64, into a DEVICE buffer of the
+ *                           caller, who all-reduces it in place
+ *   2. xchg_plan         plans the partitions ON THE DEVICE from the all-reduced histogram (dsk_b200/csrc/plan.cuh); every
+ *                           rank derives the same plan.  Returns P, the partitions per rank PW = ceil(P / W) and
+ *                           need_records[r] = records rank r receives (the same numbers on every rank, so every rank knows
+ *                           when a peer has to grow its receive buffer and the IPC handles must travel again)
+ *   3. xchg_counts       copies [W][PW] u64 = this rank's records of every partition, grouped by owner (row o goes to rank
+ *                           o: an all-to-all of rows), followed by [W] u64 = records this rank holds for each rank (all-gather
+ *                           them into the [W][W] chunk matrix), into a DEVICE buffer of the caller ((W * PW + W) u64)
+ *   4. xchg_ensure_recv  sizes the receive buffer (capacity >= own need), then xchg_ipc_handle / open_peer / set_peers
+ *   5. xchg_scatter      d_recv_counts = [W][PW] rows received in step 3 (row s = rank s's records of MY partitions),
+ *                           d_send_matrix = [W][W] from step 3.  Scatters the local records into owner-major partition order
+ *                           and stores this rank's chunk for every other rank into its receive buffer with ONE contiguous
+ *                           copy per peer (16-byte vector stores through the peer pointers: NVLink P2P, no NCCL on the data
+ *                           path, sender-major receive layout).  A rank's own chunk never moves.
+ *   6. a stream-ordered barrier of the caller (e.g. a one-element all-reduce on the same stream), then dskgpu_finish counts the
+ *      owned partitions: the counting kernel reads every partition as W segments, one per sender. */
 int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records);
 int dskgpu_xchg_prepare(dskgpu_ctx* ctx, uint64_t* local4 /*[4]*/);
 int dskgpu_xchg_set_global(dskgpu_ctx* ctx, const uint64_t* global4 /*[4] sums over ranks*/, int* log2_bins /*out: B = 1 << *log2_bins*/);
-/* hist[0..B) = records, hist[B..2*B) = k-mers of every bin on this rank */
-int dskgpu_xchg_bin_hist(dskgpu_ctx* ctx, uint64_t* hist /*[2*B]*/);
-/* plans the partitions from the whole-job histogram (sum over ranks); counts[0..P) = records, counts[P..2P) = k-mers of
- * each partition on this rank; pass counts = NULL to query P */
-int dskgpu_xchg_part_counts(dskgpu_ctx* ctx, const uint64_t* global_hist /*[2*B]*/, uint64_t* counts, uint32_t* nparts);
-int dskgpu_xchg_plan(dskgpu_ctx* ctx, const uint64_t* all_counts /*[world_size][2*P], row = rank*/);
+int dskgpu_xchg_hist(dskgpu_ctx* ctx, void* d_hist_out /*device, [2*B] u64*/);
+int dskgpu_xchg_plan(dskgpu_ctx* ctx, const void* d_global_hist /*device, [2*B] u64*/, uint32_t* nparts, uint32_t* parts_per_rank,
+                     uint64_t* need_records /*[world_size] or NULL*/);
+int dskgpu_xchg_counts(dskgpu_ctx* ctx, void* d_out /*device, [W*PW + W] u64*/);
+int dskgpu_xchg_ensure_recv(dskgpu_ctx* ctx, uint64_t capacity_records);
 int dskgpu_xchg_recv_buffer(dskgpu_ctx* ctx, void** d_recv, size_t* bytes);
 int dskgpu_xchg_ipc_handle(dskgpu_ctx* ctx, void* handle64 /*cudaIpcMemHandle_t of the receive buffer*/);
 int dskgpu_xchg_open_peer(dskgpu_ctx* ctx, const void* handle64, void** d_ptr);
 int dskgpu_xchg_close_peer(dskgpu_ctx* ctx, void* d_ptr /*from xchg_open_peer: unmap a peer buffer that was re-allocated*/);
 int dskgpu_xchg_set_peers(dskgpu_ctx* ctx, void* const* d_peer_recv /*[world_size]; own entry ignored*/);
-int dskgpu_xchg_scatter(dskgpu_ctx* ctx);
+int dskgpu_xchg_scatter(dskgpu_ctx* ctx, const void* d_recv_counts /*device, [W][PW] u64*/, const void* d_send_matrix /*device, [W][W] u64*/);
 int dskgpu_xchg_sync(dskgpu_ctx* ctx);
-/* ---- exchange v2 (what dsk_b200.distributed.distributed_finish uses): same ownership and receive-buffer layout, but
- * the metadata stays on the device and the records cross NVLink as whole (partition, sender) segments:
- *   xchg_prepare / xchg_set_global as above;
- *   xchg2_hist        copies this rank's bin histogram [2*B] into a DEVICE buffer of the caller, who all-reduces it in
- *                     place (NCCL);
- *   xchg2_plan        reads the all-reduced histogram, plans the partitions; local_counts[P] = this rank's records per
- *                     partition (the caller all-gathers them into a DEVICE matrix [world_size][P]); need_records[r] =
- *                     records rank r receives (every rank computes the same numbers, so every rank knows when a peer
- *                     has to grow its receive buffer and the IPC handles must be exchanged again);
- *   xchg2_ensure_recv sizes the receive buffer (capacity >= own need), then xchg_ipc_handle / open_peer / set_peers;
- *   xchg2_scatter     scatters the records into partition order in local HBM, then ONE kernel copies every segment into
- *                     its owner's receive buffer through the peer pointers (coalesced 16-byte stores over NVLink);
- *   xchg_sync, barrier, dskgpu_finish. */
-int dskgpu_xchg2_hist(dskgpu_ctx* ctx, void* d_hist_out /*device, [2*B] u64*/);
-int dskgpu_xchg2_plan(dskgpu_ctx* ctx, const void* d_global_hist /*device, [2*B] u64*/, uint64_t* local_counts /*[P] or NULL*/,
-                      uint64_t* need_records /*[world_size] or NULL*/, uint32_t* nparts);
-int dskgpu_xchg2_ensure_recv(dskgpu_ctx* ctx, uint64_t capacity_records);
-int dskgpu_xchg2_scatter(dskgpu_ctx* ctx, const void* d_matrix /*device, [world_size][P] u64*/);
 /* ---- several GPUs inside ONE process (what the `dsk_gpu` CLI does with DSKGPU_DEVICES): ctxs[r] is the context of rank r
  * (cfg.rank = r, cfg.world_size = n, any device each -- peer access is enabled between distinct devices; contexts may also
- * share a device).  After all pushes (one host thread per context is fine), this runs the whole exchange above with host-side
- * sums instead of collectives -- totals, bin histogram, plan, receive buffers, peer-pointer scatter -- and then counts the
- * owned partitions of every context concurrently (one host thread each).  Results are read per context, as after dskgpu_finish. */
+ * share a device).  After all pushes (one host thread per context is fine), this runs the whole exchange above with peer
+ * reads / copies in place of the collectives -- totals, bin histogram, device plan, count rows, receive buffers, scatter + one
+ * contiguous peer copy per rank pair -- and then counts the owned partitions of every context concurrently (one host thread
+ * each).  Results are read per context, as after dskgpu_finish. */
 int dskgpu_multi_finish(dskgpu_ctx* const* ctxs, int n);
 
-/* host-only layout helper: offsets[p] = first record slot of `sender` for partition p inside owner(p)'s buffer */
-int dskgpu_xchg_layout(int world_size, uint32_t nparts, const uint64_t* all_counts, int sender, uint64_t* offsets, uint64_t* recv_records);
+/* host-only mirror of rank `owner`'s receive layout (CPU test-suite): counts[s * W * PW + q] = records rank s holds for the
+ * partition at position q = (p % W) * PW + p / W.  region_base[s] = first record of sender s's chunk in the receive buffer
+ * (senders != owner in rank order; region_base[W] = records received); seg_off[s * PW + j] = first record of (sender s, owned
+ * job j), inside the receive buffer for s != owner, inside the owner's own chunk for s == owner. */
+int dskgpu_xchg_layout(int world_size, uint32_t parts_per_rank, const uint64_t* counts, int owner, uint64_t* region_base /*[W+1]*/, uint64_t* seg_off /*[W*PW]*/);
 int dskgpu_record_bytes(dskgpu_ctx* ctx);
 
 /* ---- host-side self checks of the device bit logic (no GPU needed; used by the CPU test-suite) ------- */
@@ -284,6 +279,9 @@ int64_t dskgpu_selftest_superkmers(const uint8_t* codes, size_t n, int k, int m,
 int64_t dskgpu_selftest_plan(int level, const uint64_t* global_hist, const uint64_t* local_hist, int world_size, int nb_counts,
                              uint32_t smem_slots, double density, int count_mode, int forced_nb_partitions,
                              uint32_t* bin2part, uint64_t* part_kmers, uint64_t* part_local_recs, size_t max_parts);
+/* the plan a context derived on the DEVICE (after dskgpu_finish or dskgpu_xchg_plan), for the tests that compare it with the
+ * host mirror above: same outputs (+ whole-job records per partition); returns the number of partitions */
+int64_t dskgpu_debug_plan(dskgpu_ctx* ctx, int* level, uint32_t* bin2part, uint64_t* part_kmers, uint64_t* part_recs, uint64_t* part_local_recs, size_t max_parts);
 /* wide spans groundwork (k <= 127, dsk_b200/csrc/kmer_wide.cuh; the counting path itself still rejects k >= 64): canonical
  * k-mers of a code stream as 4 words each, computed by rolling and by extraction from a packed record (must agree) */
 int64_t dskgpu_selftest_wide_kmers(const uint8_t* codes, size_t n, int k, uint64_t* out_words /*[n-k+1][4]*/, uint8_t* out_valid);

@@ -1,67 +1,94 @@
-"""N>1 host logic on CPU: world_size-2 gloo processes agree on the exchange layout the scatter kernel will use."""
+"""N>1 host logic on CPU: world_size-2 gloo processes agree on the plan and on the sender-major receive layout the exchange
+kernels use (dskgpu_selftest_plan = the sequential mirror of the device planner, dskgpu_xchg_layout = the mirror of
+k_xchg_bases; include/dskgpu.h "multi-GPU exchange")."""
 import os
 import subprocess
 import sys
 
 import numpy as np
 
-from dsk_b200.distributed import exchange_layout
+from dsk_b200.distributed import exchange_layout, _grow_plan
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 WORKER = r'''
 import os, sys
 import numpy as np
+import torch
 import torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from dsk_b200.distributed import exchange_layout, all_gather_counts
+from dsk_b200 import _lib
+from dsk_b200.distributed import exchange_layout, all_gather_counts, _grow_plan
 dist.init_process_group("gloo")
 rank, W = dist.get_rank(), dist.get_world_size()
-P = 12
-rng = np.random.default_rng(100 + rank)
-recs = rng.integers(0, 50, P).astype(np.uint64)
-recs[rank] = 0                                   # an empty partition somewhere
-counts = np.concatenate([recs, recs * 11])
-allc = all_gather_counts(dist, counts)           # [W, 2P] -- identical on every rank
-off, recv = exchange_layout(W, allc, rank)
-# every rank checks the global tiling property with the gathered matrix: for each owner, the slots
-# [off_s[p], off_s[p] + allc[s][p]) over senders s and owned partitions p tile [0, recv[o]) exactly once
+L = _lib.lib()
+level = 16; nb = 1 << level
+rng = np.random.default_rng(100 + rank)                      # every rank holds different records of every bin
+lkm = (rng.pareto(1.3, nb) * 1500).astype(np.uint64)
+lkm[rng.integers(0, nb, 3)] += np.uint64(1_500_000)          # hot minimizers: heavy partitions
+lrec = lkm // np.uint64(11) + (lkm > 0).astype(np.uint64)
+lh = np.concatenate([lrec, lkm])
+g = torch.from_numpy(lh.astype(np.int64)); dist.all_reduce(g)    # the bin histogram all-reduce of the protocol
+gh = g.numpy().astype(np.uint64)
+b2p = np.zeros(nb, np.uint32); pk = np.zeros(nb + W, np.uint64); pl = np.zeros(nb + W, np.uint64)
+P = L.dskgpu_selftest_plan(level, gh.ctypes.data, lh.ctypes.data, W, 1, 15360, 0.26, 0, 0, b2p.ctypes.data, pk.ctypes.data, pl.ctypes.data, pk.size)
+assert P > 0
+PW = (P + W - 1) // W
+# this rank's records per partition in q order (q = (p % W) * PW + p // W): what dskgpu_xchg_counts hands to the all-to-all
+cq = np.zeros(W * PW, np.uint64)
+p = np.arange(P)
+cq[(p % W) * PW + p // W] = pl[:P]
+allc = all_gather_counts(dist, cq)                          # [W][W * PW]; the real protocol moves only row chunks (all-to-all)
+plans = all_gather_counts(dist, np.concatenate([[np.uint64(P)], pk[:P]]))
+assert (plans == plans[0]).all()                            # every rank derived the same plan from the same histogram
+# every rank checks every owner's layout: the segments of the senders != owner tile the receive buffer exactly once, in
+# sender-major order, and the owner's own chunk is addressed from 0
+need = []
 for o in range(W):
-    used = np.zeros(int(recv[o]), dtype=np.int32)
+    base, seg = exchange_layout(W, PW, allc, o)
+    recv = int(base[W])
+    used = np.zeros(recv, np.int32)
     for s in range(W):
-        off_s, recv_s = exchange_layout(W, allc, s)
-        assert (recv_s == recv).all()
-        for p in range(o, P, W):
-            a = int(off_s[p]); used[a:a + int(allc[s][p])] += 1
-    assert (used == 1).all(), (o, used)
-    assert recv[o] == sum(int(allc[s][p]) for s in range(W) for p in range(o, P, W))
-# partitions of one owner appear in increasing id, senders in increasing rank inside a partition
-prev = -1
-for p in range(rank % W, P, W):
-    pass
-out = np.concatenate([off, recv])
-gathered = all_gather_counts(dist, out)
+        cnt = allc[s][o * PW:(o + 1) * PW]
+        if s == o:
+            assert seg[s][0] == 0 and (np.diff(seg[s].astype(np.int64)) == cnt[:-1].astype(np.int64)).all()
+            continue
+        assert int(seg[s][0]) == int(base[s])               # region of sender s starts with its first owned job
+        for j in range(PW):
+            a = int(seg[s][j]); used[a:a + int(cnt[j])] += 1
+        assert int(seg[s][PW - 1]) + int(cnt[PW - 1]) == int(base[s + 1])
+    assert (used == 1).all(), o
+    assert recv == sum(int(allc[s][o * PW:(o + 1) * PW].sum()) for s in range(W) if s != o)
+    need.append(recv)
+# receive-buffer growth is decided from numbers every rank holds
+want = _grow_plan(need, [0] * W)
+assert all(w >= n for w, n in zip(want, need)) and _grow_plan(need, want) == want
 if rank == 0:
-    print("LAYOUT_OK", int(recv.sum()), int(allc[:, :P].sum()))
-    assert recv.sum() == allc[:, :P].sum()
+    print("LAYOUT_OK", P, int(sum(need)), int(allc.sum()))
 dist.destroy_process_group()
 '''
 
 
 def test_layout_single_rank_is_prefix_sum():
-    counts = np.array([[3, 0, 5, 2, 30, 0, 50, 20]], dtype=np.uint64)      # P = 4
-    off, recv = exchange_layout(1, counts, 0)
-    assert list(off) == [0, 3, 3, 8] and list(recv) == [10]
+    counts = np.array([[3, 0, 5, 2]], dtype=np.uint64)                      # W = 1, PW = 4: everything is the own chunk
+    base, seg = exchange_layout(1, 4, counts, 0)
+    assert list(seg[0]) == [0, 3, 3, 8] and list(base) == [0, 0]
 
 
 def test_layout_two_ranks_by_hand():
-    # P = 4, owner(p) = p % 2.  rank0 holds [1,2,3,4] records, rank1 holds [10,20,30,40]
-    allc = np.array([[1, 2, 3, 4, 0, 0, 0, 0], [10, 20, 30, 40, 0, 0, 0, 0]], dtype=np.uint64)
-    off0, recv = exchange_layout(2, allc, 0)
-    off1, _ = exchange_layout(2, allc, 1)
-    # owner 0 receives p0 (1+10) then p2 (3+30); owner 1 receives p1 (2+20) then p3 (4+40)
-    assert list(recv) == [44, 66]
-    assert list(off0) == [0, 0, 11, 22] and list(off1) == [1, 2, 14, 26]
+    # W = 2, PW = 2 (P = 4, owner(p) = p % 2, q order = [p0, p2 | p1, p3]).  rank0 holds [1,3 | 2,4], rank1 holds [10,30 | 20,40]
+    allc = np.array([[1, 3, 2, 4], [10, 30, 20, 40]], dtype=np.uint64)
+    b0, s0 = exchange_layout(2, 2, allc, 0)
+    b1, s1 = exchange_layout(2, 2, allc, 1)
+    # owner 0 receives rank 1's chunk (p0: 10, p2: 30); its own chunk (1, 3) stays local, addressed from 0
+    assert list(b0) == [0, 0, 40] and list(s0[0]) == [0, 1] and list(s0[1]) == [0, 10]
+    # owner 1 receives rank 0's chunk (p1: 2, p3: 4)
+    assert list(b1) == [0, 6, 6] and list(s1[0]) == [0, 2] and list(s1[1]) == [0, 20]
+
+
+def test_grow_plan_is_monotone():
+    assert _grow_plan([10, 20], [0, 0]) == [10 + 2 + 1024, 20 + 5 + 1024]
+    assert _grow_plan([10, 20], [100, 5]) == [100, 20 + 5 + 1024]
 
 
 def test_world_size_2_gloo_agreement(tmp_path):

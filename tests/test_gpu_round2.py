@@ -125,6 +125,48 @@ def test_global_table_group_outgrowing_its_estimate_is_regrouped(k, monkeypatch)
     assert_equals_oracle(keys, cnt, sc.getHistogram()[0], ref)
 
 
+# ---------------------------------------------------------------- the device planner against its host mirror
+@pytest.mark.parametrize("k,slots,mode", [(31, 4096, "auto"), (63, 2048, "auto"), (31, 1024, "auto"), (31, 256, "auto")])
+def test_device_planner_equals_host_mirror(k, slots, mode):
+    """dsk_b200/csrc/plan.cuh: prefix sums + cut flags + renumbering on the device give, bit for bit, the plan of the
+    sequential restatement (plan_host via dskgpu_selftest_plan) on the histogram of a real job"""
+    import torch
+    from dsk_b200 import _lib
+    buf, n, _ = reads_fasta(G=2_000_000, coverage=20, L=150, err=0.01, seed=91)
+    data = bytearray(buf[:n].tobytes())
+    data[1000:1000] = b">low\n" + b"ACAC" * 40000 + b"\n"                       # one hot minimizer: heavy partitions
+    eng = GpuCounter(kmer_size=k, abundance_min=2, smem_table_slots=slots, count_mode=mode, hash_log2_slots=18)
+    try:
+        eng.push_bytes(bytes(data))
+        g4 = eng.xchg_prepare()
+        level = eng.xchg_set_global(g4)
+        G = torch.empty(2 << level, dtype=torch.int64, device="cuda")
+        eng.xchg_hist(G.data_ptr())
+        eng.xchg_sync()
+        P, PW, need = eng.xchg_plan(G.data_ptr())
+        lvl, b2p, pk, pr, pl = eng.debug_plan()
+        assert lvl == level and len(pk) == P and PW == P
+        gh = G.cpu().numpy().astype(np.uint64)
+        density = min(1.0, max(0.01, float(g4[3]) / float(g4[2]))) if g4[2] >= 4096 else 1.0
+        L = _lib.lib()
+        nb = 1 << level
+        hb2p = np.zeros(nb, np.uint32); hpk = np.zeros(nb + 1, np.uint64); hpl = np.zeros(nb + 1, np.uint64)
+        hP = L.dskgpu_selftest_plan(level, gh.ctypes.data, gh.ctypes.data, 1, 1, slots, density, 0, 0,
+                                    hb2p.ctypes.data, hpk.ctypes.data, hpl.ctypes.data, hpk.size)
+        assert hP == P, (hP, P)
+        assert (hb2p == b2p).all() and (hpk[:P] == pk).all() and (hpl[:P] == pl).all() and (pr == pl).all()
+        assert int(need[0]) == int(pr.sum()) == int(g4[1])
+        eng.finish()                                                            # and the job still counts right from that plan
+        ref = oracle.count_files([bytes(data)], k, abundance_min=2)
+        kk, cc = eng.solid()
+        assert_equals_oracle(kk, cc, eng.histogram()[0], ref)
+        if mode == "auto":
+            st = eng.stats()
+            assert st["nb_parts_smem"] > 0 and st["nb_groups_hash"] > 0
+    finally:
+        eng.close()
+
+
 # ---------------------------------------------------------------- several ranks in one process (dskgpu_multi_finish)
 def run_multi(devices, k, data, **kw):
     W = len(devices)

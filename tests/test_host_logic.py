@@ -31,7 +31,7 @@ def test_abi_exports_every_declared_symbol(L):
     assert declared == set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.dskgpu_abi_version() == 2
+    assert L.dskgpu_abi_version() == 3
 
 
 def test_struct_sizes_match(L):
@@ -221,10 +221,10 @@ def _plan(L, level, gh, lh, world, nb_counts=1, slots=15360, density=0.26, mode=
     return int(P), b2p, pk[:P], pr[:P]
 
 
-@pytest.mark.parametrize("world,level", [(1, 16), (2, 17), (4, 18), (8, 16)])
+@pytest.mark.parametrize("world,level", [(1, 16), (2, 17), (4, 18), (8, 16), (5, 16)])
 def test_partition_planner_invariants_and_rank_agreement(L, world, level):
-    # what every rank derives from the all-reduced minimizer-bin histogram (plan_partitions_host): skewed bins (a few
-    # hot minimizers), ranks holding different shares of every bin
+    # what every rank derives from the all-reduced minimizer-bin histogram (plan_host, the sequential mirror of the device
+    # planner in dsk_b200/csrc/plan.cuh): skewed bins (a few hot minimizers), ranks holding different shares of every bin
     rng = np.random.default_rng(level * 10 + world)
     nb = 1 << level
     km = (rng.pareto(1.3, nb) * 3000).astype(np.uint64) + rng.integers(0, 2000, nb).astype(np.uint64)
@@ -238,13 +238,12 @@ def test_partition_planner_invariants_and_rank_agreement(L, world, level):
     lkm[:, 0] += km - lkm.sum(1)
     gh = np.concatenate([rec, km]).astype(np.uint64)
     slots, density = 15360, 0.26
-    T = slots * 0.52 / density
+    T = int(slots * 0.52 / density * 0.85)                             # the cut: 85 % of the target (make_plan_params)
     plans = []
     for r in range(world):
         lh = np.concatenate([lrec[:, r], lkm[:, r]]).astype(np.uint64)
         plans.append(_plan(L, level, gh, lh, world, slots=slots, density=density))
     P, b2p, pk, _ = plans[0]
-    assert P % world == 0
     for Pr, b2, pkr, _ in plans[1:]:                                   # same plan on every rank
         assert Pr == P and (b2 == b2p).all() and (pkr == pk).all()
     assert b2p.max() < P and int(pk.sum()) == int(km.sum())
@@ -252,16 +251,24 @@ def test_partition_planner_invariants_and_rank_agreement(L, world, level):
     # the ranks' local records of a partition add up to the whole-job records of its bins
     tot_local = np.sum([p[3] for p in plans], axis=0)
     assert (tot_local == np.bincount(b2p, weights=rec.astype(np.float64), minlength=P).astype(np.uint64)).all()
-    # a partition is at most T k-mers unless it is a single bin (a bin cannot be split: the minimizer decides the partition)
+    # the cut rule: a partition is the run of bins that START inside one window of T k-mers, so it holds less than T plus its
+    # last bin (a bin cannot be split: the minimizer decides the partition), and no partition is empty of bins
     nbins_of = np.bincount(b2p, minlength=P)
-    assert ((pk <= T + 1) | (nbins_of == 1)).all()
-    # partitions beyond the reach of the shared-memory path (AUTO mode) are numbered after all the others, heaviest first
-    lim = slots * 0.75 / density * 2                                   # fit x 2^max_split0 (default 1)
+    assert (nbins_of > 0).all()
+    last_bin = np.zeros(P, np.uint64)
+    last_bin[b2p] = km                                                 # bins are visited in increasing order: the last one wins
+    assert (pk < np.uint64(T) + last_bin + np.uint64(1)).all()
+    # bins of a partition are consecutive
+    first = np.full(P, nb, np.int64); last = np.zeros(P, np.int64)
+    np.minimum.at(first, b2p, np.arange(nb)); np.maximum.at(last, b2p, np.arange(nb))
+    assert (last - first + 1 == nbins_of).all()
+    # partitions beyond the reach of the shared-memory path (AUTO mode) are numbered after all the others, in bin order
+    lim = int(slots * 0.75 / density * 2)                              # fit x 2^max_split0 (default 1)
     heavy = np.nonzero(pk > lim)[0]
     assert len(heavy) >= 5
-    nonempty_light = np.nonzero((pk <= lim) & (pk > 0))[0]
-    assert heavy.min() > nonempty_light.max()
-    assert (np.diff(pk[heavy].astype(np.int64)) <= 0).all()
+    light = np.nonzero(pk <= lim)[0]
+    assert heavy.min() > light.max()
+    assert (np.diff(first[heavy]) > 0).all() and (np.diff(first[light]) > 0).all()
 
 
 def test_partition_planner_forced_partition_count(L):
@@ -297,25 +304,3 @@ def test_product_package_never_imports_the_oracle():
                 if re.search(r'(^\s*(import|from)\s+oracle\b)|(#include\s+[<"][^>"]*oracle)|(-loracle)|((dlopen|CDLL)\([^)]*oracle)', txt, re.M):
                     offenders.append(os.path.join(sub, f))
     assert offenders == []
-
-
-@pytest.mark.parametrize("world,level,slots,density", [(1, 16, 15360, 0.26), (2, 17, 15360, 0.3), (8, 18, 11264, 0.45), (3, 16, 256, 0.3)])
-def test_parallel_planner_prototype_equals_the_host_planner(L, world, level, slots, density):
-    # tools/plan_parallel_proto.py: prefix sums + one binary search per bin + pointer doubling give, bit for bit, the plan
-    # of the sequential greedy packing in dskgpu.cu (the device-side planner of round 2 is a transcription of the prototype)
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
-    from plan_parallel_proto import plan_parallel
-    rng = np.random.default_rng(level + world)
-    nb = 1 << level
-    km = (rng.pareto(1.3, nb) * 3000).astype(np.uint64) + rng.integers(0, 2000, nb).astype(np.uint64)
-    km[rng.integers(0, nb, 6)] += np.uint64(2_500_000)
-    km[rng.integers(0, nb, 3000)] = 0                                    # runs of empty bins, also at partition starts
-    km[:5] = 0
-    rec = (km // np.uint64(11)) + (km > 0).astype(np.uint64)
-    gh = np.concatenate([rec, km]).astype(np.uint64)
-    P, b2p, pk, _ = _plan(L, level, gh, gh, world, slots=slots, density=density)
-    T = int(min(max(slots * 0.52 / density, 64.0), slots * 4.0))
-    lim = int(max(64.0, slots * 0.75 / density) * 2)                      # fit x 2^max_split0 (default 1)
-    b2, pk2 = plan_parallel(km, T, lim, world)
-    assert pk2.size == P and (pk2 == pk).all() and (b2 == b2p).all()
