@@ -527,15 +527,17 @@ def main():
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0; dom_ms = 0.0; dom_n = 0; stage = {}; x_ms = 0.0; x_bytes = 0
+    launches = 0; dom_ms = 0.0; dom_n = 0; stage = {}; x_ms = 0.0; x_bytes = 0; push_gap = 0.0; heavy_ms = 0.0
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
         st = eng.stats()
         launches += st["gpu_launches"]; dom_ms += st["ms_dominant_kernel"]; dom_n += st["dominant_kernel_launches"]
         x_ms += st["ms_exchange"]; x_bytes += st["exchange_bytes_out"]
-        for kk in ("ms_parse", "ms_superk", "ms_partition", "ms_count", "ms_sort"):
+        for kk in ("ms_parse", "ms_superk", "ms_plan", "ms_partition", "ms_count", "ms_sort"):
             stage[kk] = stage.get(kk, 0.0) + st[kk] / args.steps
+        push_gap += (st["ms_push_wall"] - st["ms_parse"] - st["ms_superk"]) / args.steps
+        heavy_ms += st["ms_count_heavy"] / args.steps
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -664,6 +666,7 @@ def main():
             "clocks": clocks,
             "stage_ms": stage,
             "host_ms_per_step": ms_all / args.steps - sum(stage.values()),
+            "push_gap_ms_per_step": push_gap, "count_heavy_ms_per_step": heavy_ms,
             "checks": checks,
             "roofline": roof,
             "pipeline_roofline": {"A_k_bytes_per_kmer": A, "achieved": value / world * A, "peak": peak, "unit": "GB/s", "frac": value / world * A / peak,
@@ -675,13 +678,15 @@ def main():
             # every kernel of the step: measured DRAM bytes (ncu, one capture at HEAD) / its share of the step / peak
             line["kernels"] = {"source": "profiles/%s" % nk.get("tag"), "per_step": nk.get("kernels")}
         if world > 1:
-            # records stored into other ranks' HBM by k_xchg_copy (summed over ranks and steps) / the slowest rank's
-            # summed copy-kernel time (CUDA events on the context stream), per GPU, against 900 GB/s per direction
+            # records stored into other ranks' HBM by k_xchg_send (summed over ranks and steps) / the slowest rank's
+            # summed copy-kernel time (CUDA events on the context stream), per GPU, against 900 GB/s per direction (nominal) and
+            # the 770 GB/s peer copy B200_PROFILING.md measured on this pool
             per_gpu = (x_bytes_all / world) / (x_ms_max / 1e3) / 1e9 if x_ms_max > 0 else 0.0
             line["nvlink"] = {"exchanged_bytes_per_step": x_bytes_all / args.steps, "ms_exchange_per_step": x_ms_max / args.steps,
                               "achieved": per_gpu, "peak": 900.0, "unit": "GB/s per GPU, one direction", "frac": per_gpu / 900.0,
+                              "peak_measured_peer_copy": 770.0, "frac_of_measured": per_gpu / 770.0,
                               "share_of_step": (x_ms_max / args.steps) / (ms_all / args.steps),
-                              "note": "the copy kernel also moves each rank's own partitions (1/N of the records) HBM->HBM inside the same launch"}
+                              "note": "one contiguous copy per (sender, receiver) pair, 16-byte peer stores; a rank's own partitions never move"}
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline and not args.histo2d:

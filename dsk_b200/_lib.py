@@ -39,6 +39,7 @@ class Stats(C.Structure):
         ("dominant_kernel_launches", C.c_uint32), ("nb_parts_smem", C.c_uint32), ("nb_smem_splits", C.c_uint32),
         ("smem_table_slots", C.c_uint32), ("density_ppm", C.c_uint32), ("log2_bins", C.c_uint32), ("nb_groups_bucket", C.c_uint32), ("nb_hash_regroups", C.c_uint32),
         ("exchange_bytes_out", C.c_uint64), ("ms_exchange", C.c_float), ("nb_solid_regrows", C.c_uint32), ("kmers_in_pass", C.c_uint64),
+        ("ms_plan", C.c_float), ("ms_push_wall", C.c_float), ("hist_rebuilt", C.c_uint32), ("ms_count_heavy", C.c_float),
     ]
 
     def as_dict(self):
@@ -52,7 +53,7 @@ SYMBOLS = [
     "dskgpu_recount", "dskgpu_bank_histograms",
     "dskgpu_get_stats", "dskgpu_reset", "dskgpu_destroy", "dskgpu_host_alloc", "dskgpu_host_free", "dskgpu_strerror",
     "dskgpu_last_error", "dskgpu_device_count", "dskgpu_abi_version",
-    "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_hist", "dskgpu_xchg_counts", "dskgpu_xchg_ensure_recv", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
+    "dskgpu_xchg_local_totals", "dskgpu_xchg_prepare", "dskgpu_xchg_set_global", "dskgpu_xchg_sketch", "dskgpu_xchg_set_sketch", "dskgpu_xchg_hist", "dskgpu_xchg_counts", "dskgpu_xchg_ensure_recv", "dskgpu_xchg_plan", "dskgpu_xchg_recv_buffer", "dskgpu_xchg_ipc_handle",
     "dskgpu_xchg_open_peer", "dskgpu_xchg_set_peers", "dskgpu_xchg_scatter", "dskgpu_xchg_sync", "dskgpu_xchg_layout", "dskgpu_record_bytes",
     "dskgpu_set_pass", "dskgpu_push_sync", "dskgpu_suggest_nb_passes", "dskgpu_xchg_close_peer", "dskgpu_multi_finish",
     "dskgpu_debug_plan",
@@ -106,6 +107,8 @@ def lib():
     L.dskgpu_xchg_prepare.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_set_global.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int)]
     L.dskgpu_xchg_hist.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg_sketch.argtypes = [C.c_void_p, C.c_void_p]
+    L.dskgpu_xchg_set_sketch.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_plan.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint32), P(C.c_uint32), C.c_void_p]
     L.dskgpu_xchg_counts.argtypes = [C.c_void_p, C.c_void_p]
     L.dskgpu_xchg_ensure_recv.argtypes = [C.c_void_p, C.c_uint64]

@@ -195,6 +195,17 @@ def _xchg_methods():
         self._bin_level = lvl.value
         return lvl.value
 
+    def xchg_sketch(self):
+        """HyperLogLog registers of the distinct k-mers of this rank's density sample (merge over ranks with max)"""
+        v = np.zeros(4096, dtype=np.uint32)
+        self._check(self.L.dskgpu_xchg_sketch(self.h, v.ctypes.data))
+        return v
+
+    def xchg_set_sketch(self, merged):
+        m = np.ascontiguousarray(merged, dtype=np.uint32)
+        assert m.size == 4096
+        self._check(self.L.dskgpu_xchg_set_sketch(self.h, m.ctypes.data))
+
     def xchg_hist(self, d_out):
         """this rank's bin histogram [2 << level] u64 -> device buffer of the caller (all-reduce it in place)"""
         self._check(self.L.dskgpu_xchg_hist(self.h, C.c_void_p(d_out)))
@@ -253,7 +264,7 @@ def _xchg_methods():
             self._check(int(P))
         return lvl.value, b2p[:1 << lvl.value].copy(), pk[:P].copy(), pr[:P].copy(), pl[:P].copy()
 
-    for f in (xchg_local_totals, xchg_prepare, xchg_set_global, xchg_hist, xchg_plan, xchg_counts, xchg_ensure_recv, xchg_recv_buffer, xchg_ipc_handle,
+    for f in (xchg_local_totals, xchg_prepare, xchg_set_global, xchg_sketch, xchg_set_sketch, xchg_hist, xchg_plan, xchg_counts, xchg_ensure_recv, xchg_recv_buffer, xchg_ipc_handle,
               xchg_open_peer, xchg_close_peer, xchg_set_peers, xchg_scatter, xchg_sync, debug_plan):
         setattr(GpuCounter, f.__name__, f)
 

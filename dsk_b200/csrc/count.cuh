@@ -11,6 +11,7 @@
 //   Histogram.hpp:92,221 quirks) -> solidity (K/CountProcessorSolidity.hpp:186-300) -> dump of Count(kmer,sum)
 //   (K/CountProcessorDump.hpp:85-152).
 #pragma once
+#include <cmath>
 #include "kmer_bits.cuh"
 #include "superk.cuh"
 
@@ -291,10 +292,24 @@ __global__ void __launch_bounds__(256) k_hash_insert(const u64* __restrict__ rec
 // ---- K6 (hash flavour): sweep the table, run the processor chain, reset the slots ---------------------------------
 // each thread owns SV consecutive slots per iteration; keys and (single-bank) counts come in as independent
 // 16-byte vector loads so one iteration costs one memory round trip
+constexpr int HLL_BITS = 12;
+constexpr u32 HLL_M = 1u << HLL_BITS;
+// cardinality from HyperLogLog registers (host side; 64-bit hashes: no large-range correction; linear counting when sparse)
+inline double hll_estimate(const u32* reg)
+{
+    double z = 0.0; u32 zeros = 0;
+    for (u32 i = 0; i < HLL_M; i++) { z += std::ldexp(1.0, -(int)reg[i]); zeros += reg[i] == 0; }
+    const double m = (double)HLL_M, alpha = 0.7213 / (1.0 + 1.079 / m);
+    double e = alpha * m * m / z;
+    if (e <= 2.5 * m && zeros) e = m * std::log(m / (double)zeros);
+    return e;
+}
+
 template <int KW, bool NB1>
 __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 nslots, SolidityParams sp, int discard,
                                                    u64* out_keys, u32* out_vals, u64 out_cap,
-                                                   unsigned long long* g_hist, unsigned long long* g_hist2d, Counters* ctr)
+                                                   unsigned long long* g_hist, unsigned long long* g_hist2d, Counters* ctr,
+                                                   u32* __restrict__ hll = nullptr /*density sample: HyperLogLog registers [HLL_M] of its distinct k-mers*/)
 {
     constexpr int SV = (KW == 1) ? 8 : 4;                          // slots per thread-iteration
     constexpr int KV = SV * KW / 2;                                // 16-byte key vectors per iteration (4)
@@ -353,6 +368,10 @@ __global__ void __launch_bounds__(256) k_hash_scan(u64* keys, u32* counts, u32 n
             if (discard == 2) {                                    // density sample: occupied slots, multiplicities, share reaching the threshold
                 ndist++; sumsq += (unsigned long long)cv[0] * cv[0];
                 if ((long long)cv[0] >= sp.amin[0] && (long long)cv[0] <= sp.amax) nsamp_solid++;
+                if (hll) {                                         // the ranks of a multi-GPU job merge these (max) to get the distinct k-mers of the UNION of their samples
+                    const u64 h = kmer_hash(sk[q]), w = h << HLL_BITS;
+                    atomicMax(&hll[h >> (64 - HLL_BITS)], w ? (u32)__clzll((long long)w) + 1u : (u32)(64 - HLL_BITS + 1));
+                }
             }
             if (!discard) {
                 ndist++;

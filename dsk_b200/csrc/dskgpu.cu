@@ -49,12 +49,14 @@ struct dskgpu_ctx {
     DevBuf recs, meta;                               // staging records (input order)
     DevBuf precs;                                    // partitioned records
     DevBuf cursor, bin_hist, bin_fold, bin2part, work_ctr;
-    DevBuf sample_recs, stab_keys, stab_counts;      // density sample: selected records, small hash table
+    DevBuf sample_recs, stab_keys, stab_counts, hll; // density sample: selected records, small hash table, HyperLogLog registers of its distinct k-mers
+    u32* h_hll = nullptr; double sketch_distinct = -1.0;   // pinned copy; distinct k-mers of the union of all ranks' samples (merged sketch), < 0 = not given
     DevBuf tkeys, tcounts;                           // hash table
     DevBuf skeys[2], svals[2];                       // solid (k-mer, abundance) ping-pong
     DevBuf keys[2], banks[2];                        // sort path ping-pong
     DevBuf rs_hist, rs_status, rs_tilectr;
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_k2 = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_probe[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_push0 = nullptr, ev_push1 = nullptr; bool push_timed = false;   // first / last push kernel of the job (wall time of the push phase)
     // host pinned mirrors
     Counters* h_ctr = nullptr; StreamState* h_ss = nullptr;
     unsigned long long* h_nrec_probe = nullptr;
@@ -62,7 +64,10 @@ struct dskgpu_ctx {
     unsigned long long* h_hist = nullptr;            // [10001 + 11*10001]
     // stream bookkeeping
     int cur_bank = -1, cur_fmt = 0; bool stream_open = false; int pending_cr = 0;
-    u64 rec_cap = 0; u64 nrec_known = 0; int chunk_parity = 0; bool k2_inflight = false;
+    u64 rec_cap = 0; u64 nrec_known = 0; int chunk_parity = 0;
+    // record-count probes of the chunks in flight (the host stays two chunks ahead of the device instead of draining it per chunk)
+    struct Probe { int slot; u64 bytes; };
+    std::vector<Probe> probes; int probe_slot = 0;
     size_t push_chunk = (size_t)64 << 20;
     // results
     u64 n_solid = 0; int solid_buf = 0; bool results_on_host = false; u64 solid_cap = 0;
@@ -72,7 +77,7 @@ struct dskgpu_ctx {
     DevBuf pl_ex, pl_E, pl_H, pl_bsum, pl_pk, pl_pr, pl_pl, pl_newid, pl_nvals, pl_hdr;
     DevBuf gk_q, gr_q, lcnt_q, loff, xX, xtab, xS, hoff, hrecs;
     PlanHdr* h_hdr = nullptr; XchgTab* h_xtab = nullptr;             // pinned mirrors
-    bool planned = false;
+    bool planned = false, hist_suspect = false;
     u32 nl_me = 0, np_me = 0;                        // owned jobs: [0, nl_me) counted in shared memory, [nl_me, np_me) heavy
     std::vector<u64> heavy_recs, heavy_kmers;        // whole-job records / k-mers of the owned heavy partitions (increasing id)
     u64* h_heavy = nullptr; size_t h_heavy_cap = 0;  // pinned staging for them
@@ -134,7 +139,7 @@ static int ensure(dskgpu_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false, s
     return 0;
 }
 
-enum { SPAN_PARSE = 0, SPAN_SUPERK = 1, SPAN_PART = 2, SPAN_COUNT = 3, SPAN_SORT = 4, SPAN_DOM = 5, SPAN_TOTAL = 6, SPAN_SORTPASS = 7, SPAN_XCHG = 8 };
+enum { SPAN_PARSE = 0, SPAN_SUPERK = 1, SPAN_PART = 2, SPAN_COUNT = 3, SPAN_SORT = 4, SPAN_DOM = 5, SPAN_TOTAL = 6, SPAN_SORTPASS = 7, SPAN_XCHG = 8, SPAN_PLAN = 9, SPAN_HEAVY = 10 };
 
 static cudaEvent_t get_event(dskgpu_ctx* ctx)
 {
@@ -212,17 +217,20 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); }
-    CK(cudaEventCreateWithFlags(&ctx->ev_k2, cudaEventDisableTiming));
+    for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&ctx->ev_probe[i], cudaEventDisableTiming));
+    CK(cudaEventCreate(&ctx->ev_push0)); CK(cudaEventCreate(&ctx->ev_push1));
     CK(cudaMallocHost((void**)&ctx->h_ctr, sizeof(Counters)));
     CK(cudaMallocHost((void**)&ctx->h_ss, sizeof(StreamState)));
     CK(cudaMallocHost((void**)&ctx->h_nrec_probe, 64));
     CK(cudaMallocHost((void**)&ctx->h_hist, sizeof(unsigned long long) * (DSKGPU_HISTO_LEN * (1 + DSKGPU_HISTO2D_DIM2))));
     CK(cudaMallocHost((void**)&ctx->h_hdr, sizeof(PlanHdr)));
+    CK(cudaMallocHost((void**)&ctx->h_hll, sizeof(u32) * HLL_M));
     CK(cudaMallocHost((void**)&ctx->h_xtab, sizeof(XchgTab)));
     int rc;
-    if ((rc = ensure(ctx, ctx->bin_hist, sizeof(unsigned long long) * 2 * NBINS_FINE))) return rc;
-    if ((rc = ensure(ctx, ctx->bin_fold, sizeof(unsigned long long) * 2 * (NBINS_FINE / 2)))) return rc;
+    if ((rc = ensure(ctx, ctx->bin_hist, sizeof(unsigned long long) * NBINS_FINE))) return rc;
+    if ((rc = ensure(ctx, ctx->bin_fold, sizeof(unsigned long long) * 2 * NBINS_FINE))) return rc;
     if ((rc = ensure(ctx, ctx->work_ctr, 64))) return rc;
+    if ((rc = ensure(ctx, ctx->hll, sizeof(u32) * HLL_M))) return rc;
     if ((rc = ensure(ctx, ctx->ss, sizeof(StreamState)))) return rc;
     if ((rc = ensure(ctx, ctx->ctr, sizeof(Counters)))) return rc;
     if ((rc = ensure(ctx, ctx->hist, sizeof(unsigned long long) * DSKGPU_HISTO_LEN))) return rc;
@@ -299,9 +307,11 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
     CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
     if (ctx->bank_hist.p) CK(cudaMemsetAsync(ctx->bank_hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * (size_t)ctx->NB, ctx->stream));
-    CK(cudaMemsetAsync(ctx->bin_hist.p, 0, sizeof(unsigned long long) * 2 * NBINS_FINE, ctx->stream));
+    CK(cudaMemsetAsync(ctx->bin_hist.p, 0, sizeof(unsigned long long) * NBINS_FINE, ctx->stream));
+    CK(cudaMemsetAsync(ctx->hll.p, 0, sizeof(u32) * HLL_M, ctx->stream));
+    ctx->sketch_distinct = -1.0;
     ctx->state = 0; ctx->cur_bank = -1; ctx->stream_open = false; ctx->pending_cr = 0;
-    ctx->nrec_known = 0; ctx->k2_inflight = false; ctx->chunk_parity = 0;
+    ctx->nrec_known = 0; ctx->probes.clear(); ctx->chunk_parity = 0; ctx->push_timed = false;
     ctx->n_solid = 0; ctx->results_on_host = false; ctx->nparts = 0; ctx->planned = false; ctx->nl_me = ctx->np_me = 0; ctx->heavy_recs.clear(); ctx->heavy_kmers.clear(); ctx->rcnt_dev = nullptr;
     ctx->xchg_planned = false; ctx->xchg_scattered = false; ctx->xchg_bytes_out = 0; ctx->totals_done = false; ctx->local_nrec = ctx->local_nkm = 0;
     ctx->bytes_pushed = 0; ctx->sample_queued = false; ctx->sample_nkm = ctx->sample_distinct = 0; ctx->sample_wmult = 0.0;
@@ -318,7 +328,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->bank_hist, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
-                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->bin2part, &ctx->work_ctr,
+                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->hll, &ctx->bin2part, &ctx->work_ctr,
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
                      &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr,
                      &ctx->lrecs, &ctx->xpeers, &ctx->bcur, &ctx->ghist, &ctx->pl_ex, &ctx->pl_E, &ctx->pl_H, &ctx->pl_bsum, &ctx->pl_pk, &ctx->pl_pr, &ctx->pl_pl,
@@ -327,12 +337,15 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); }
-    if (ctx->ev_k2) cudaEventDestroy(ctx->ev_k2);
+    for (int i = 0; i < 4; i++) if (ctx->ev_probe[i]) cudaEventDestroy(ctx->ev_probe[i]);
+    if (ctx->ev_push0) cudaEventDestroy(ctx->ev_push0);
+    if (ctx->ev_push1) cudaEventDestroy(ctx->ev_push1);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->h_ss) cudaFreeHost(ctx->h_ss);
     if (ctx->h_nrec_probe) cudaFreeHost(ctx->h_nrec_probe);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
     if (ctx->h_hdr) cudaFreeHost(ctx->h_hdr);
+    if (ctx->h_hll) cudaFreeHost(ctx->h_hll);
     if (ctx->h_xtab) cudaFreeHost(ctx->h_xtab);
     if (ctx->h_heavy) cudaFreeHost(ctx->h_heavy);
     if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
@@ -371,11 +384,24 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
     if ((rc = ensure(ctx, ctx->tin, ntiles * sizeof(TileIn)))) return rc;
     if ((rc = ensure(ctx, ctx->codes, std::max<u64>(n, 2 * ctx->push_chunk) + 64 + SK_TP + 1024, true, 64))) return rc;
     // record capacity: worst case one record per position of this chunk on top of what is known to be used
-    if (ctx->k2_inflight) {
-        CK(cudaEventSynchronize(ctx->ev_k2));
-        ctx->nrec_known = *ctx->h_nrec_probe; ctx->k2_inflight = false;
-    }
-    const u64 need = ctx->nrec_known + n + 64;
+    // The host may run two chunks ahead of the device: a chunk still in flight is charged at its worst case (one record per
+    // byte) until its probe (the record counter copied out behind its kernels) has landed.
+    auto harvest = [&](bool wait) -> int {
+        while (!ctx->probes.empty()) {
+            const int sl = ctx->probes.front().slot;
+            if (wait) CK(cudaEventSynchronize(ctx->ev_probe[sl]));
+            else { cudaError_t q = cudaEventQuery(ctx->ev_probe[sl]); if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; } CK(q); }
+            ctx->nrec_known = ctx->h_nrec_probe[sl];
+            ctx->probes.erase(ctx->probes.begin());
+            wait = false;                                                 // one blocking wait per call, then whatever else is ready
+        }
+        return 0;
+    };
+    if ((rc = harvest(false))) return rc;
+    while (ctx->probes.size() >= 2) if ((rc = harvest(true))) return rc;
+    auto upper = [&]() { u64 u = ctx->nrec_known + n + 64; for (auto& pr : ctx->probes) u += pr.bytes; return u; };
+    while (upper() > ctx->rec_cap && !ctx->probes.empty()) if ((rc = harvest(true))) return rc;
+    const u64 need = upper();
     if (need > ctx->rec_cap) {
         u64 ncap = std::max(need, ctx->rec_cap + ctx->rec_cap / 2);
         if ((rc = ensure(ctx, ctx->recs, ncap * ctx->RW * 8, true, ctx->nrec_known * ctx->RW * 8))) return rc;
@@ -383,6 +409,7 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
         ctx->rec_cap = std::min<u64>(ctx->recs.cap / (ctx->RW * 8), ctx->meta.cap / 4);
     }
     StreamState* ss = (StreamState*)ctx->ss.p;
+    if (!ctx->push_timed) { CK(cudaEventRecord(ctx->ev_push0, ctx->stream)); ctx->push_timed = true; }
     {
         SpanGuard g(ctx, SPAN_PARSE);
         const unsigned gt = (unsigned)ntiles;
@@ -409,9 +436,13 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
         LAUNCHED();
         k_scan_carry<<<1, 64, 0, ctx->stream>>>((u8*)ctx->codes.p, ss, ctx->k); LAUNCHED();
     }
-    CK(cudaMemcpyAsync(ctx->h_nrec_probe, &((Counters*)ctx->ctr.p)->nrec, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaEventRecord(ctx->ev_k2, ctx->stream));
-    ctx->k2_inflight = true;
+    {
+        const int sl = ctx->probe_slot; ctx->probe_slot = (sl + 1) & 3;
+        CK(cudaMemcpyAsync(ctx->h_nrec_probe + sl, &((Counters*)ctx->ctr.p)->nrec, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_probe[sl], ctx->stream));
+        ctx->probes.push_back({sl, n});
+    }
+    CK(cudaEventRecord(ctx->ev_push1, ctx->stream));
     CK(cudaGetLastError());
     return 0;
 }
@@ -777,6 +808,7 @@ static int queue_sample(dskgpu_ctx* ctx)
         CK(cudaMemsetAsync(ctx->stab_counts.p, 0, (size_t)SAMPLE_SLOTS * 4, ctx->stream));
     }
     Counters* ctr = (Counters*)ctx->ctr.p;
+    SpanGuard g(ctx, SPAN_PLAN);
     // the exact k-mer total is still on the device: size the sample from the bytes pushed (~0.7 k-mers per FASTA byte)
     const double est = std::max(1.0, (double)ctx->bytes_pushed * 0.7);
     double f = (double)SAMPLE_KMERS / est;
@@ -792,7 +824,7 @@ static int queue_sample(dskgpu_ctx* ctx)
     if (ctx->cfg.solidity_kind == DSKGPU_SOLIDITY_CUSTOM) sp.amin[0] = 1;
     if (ctx->NB > 1) sp.amax = 0x7FFFFFFFFFFFFFFFLL;                    // per-bank ranges: the summed count only bounds from below
     k_hash_scan<KW, true><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((u64*)ctx->stab_keys.p, (u32*)ctx->stab_counts.p, SAMPLE_SLOTS, sp, 2, nullptr, nullptr, 0,
-                                                                      (unsigned long long*)ctx->hist.p, (unsigned long long*)ctx->hist2d.p, ctr); LAUNCHED();
+                                                                      (unsigned long long*)ctx->hist.p, (unsigned long long*)ctx->hist2d.p, ctr, (u32*)ctx->hll.p); LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -806,7 +838,11 @@ static void set_global(dskgpu_ctx* ctx, u64 g_kmers, u64 g_recs, u64 g_sample_km
 {
     ctx->g_total_kmers = g_kmers; ctx->g_total_recs = g_recs;
     ctx->density_known = g_sample_kmers >= 4096;
-    ctx->density = ctx->density_known ? std::min(1.0, std::max(0.01, (double)g_sample_distinct / (double)g_sample_kmers)) : 1.0;
+    // several ranks: the distinct k-mers of the UNION of the ranks' samples come from the merged HyperLogLog sketch (a k-mer
+    // sampled by two ranks is one distinct k-mer of the job; summing the ranks' own distinct counts would overstate the density
+    // more and more as the ranks' shares of the coverage shrink)
+    const double g_distinct = ctx->sketch_distinct >= 0.0 ? std::min(ctx->sketch_distinct, (double)g_sample_distinct) : (double)g_sample_distinct;
+    ctx->density = ctx->density_known ? std::min(1.0, std::max(0.01, g_distinct / (double)g_sample_kmers)) : 1.0;
     const u64 T = plan_target_kmers(ctx, g_kmers);
     // bins of the chosen level should average an eighth of a partition: a partition overshoots the cut by part of its last bin
     // (plan.cuh), and the planner runs on the device, so a finer level costs microseconds
@@ -823,16 +859,24 @@ static int stage_totals(dskgpu_ctx* ctx)
     Counters* ctr = (Counters*)ctx->ctr.p;
     if (ctx->stream_open) close_stream(ctx);
     { int rc = ctx->KW == 1 ? queue_sample<1>(ctx) : queue_sample<2>(ctx); if (rc) return rc; }
+    {
+        // packed bin histogram: could a record field have wrapped?  (test hook: a lower limit exercises the exact rebuild)
+        unsigned long long lim = 1ULL << 28;
+        if (const char* e = getenv("DSKGPU_TEST_HIST_LIMIT")) lim = (unsigned long long)std::max(1LL, atoll(e));
+        k_check_bins<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, lim, ctr); LAUNCHED();
+    }
     CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_ss, ctx->ss.p, sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_hll, ctx->hll.p, sizeof(u32) * HLL_M, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->k2_inflight = false;
+    ctx->probes.clear();
     if (ctx->h_ss->err) FAIL(DSKGPU_ERR_FORMAT, "device record scanner rejected the input (flags 0x%x): not plain FASTA / 4-line FASTQ", ctx->h_ss->err);
     if (ctx->h_ctr->overflow) FAIL(DSKGPU_ERR_OVERFLOW, "super-k-mer record buffer overflow");
     if (ctx->h_ctr->kmers_pass != ctx->h_ctr->kmers_in_recs)
         FAIL(DSKGPU_ERR_OVERFLOW, "internal: %llu valid k-mers in this pass but %llu packed in records", ctx->h_ctr->kmers_pass, ctx->h_ctr->kmers_in_recs);
     ctx->local_nrec = ctx->h_ctr->nrec; ctx->local_nkm = ctx->h_ctr->kmers_pass; ctx->bank_nkm = ctx->h_ctr->kmers_valid;
     ctx->sample_solid = ctx->h_ctr->sample_solid;
+    ctx->hist_suspect = ctx->h_ctr->hist_suspect != 0;
     ctx->sample_nkm = ctx->h_ctr->sample_nkm; ctx->sample_distinct = ctx->h_ctr->sample_distinct;
     ctx->sample_wmult = ctx->sample_nkm >= 4096 ? (double)ctx->h_ctr->sample_sumsq / (double)ctx->sample_nkm : 0.0;
     ctx->st.nb_sequences = ctx->h_ss->nsep; ctx->st.nb_nucleotides = ctx->h_ss->nbase;
@@ -849,14 +893,21 @@ static int fold_local_hist(dskgpu_ctx* ctx, const void** d_hist)
     if (!ctx->global_set) set_global(ctx, ctx->local_nkm, ctx->local_nrec, ctx->sample_nkm, ctx->sample_distinct);
     const int shift = NBINS_FINE_LOG2 - ctx->bin_level;
     const u32 nb = 1u << ctx->bin_level;
-    *d_hist = ctx->bin_hist.p;
-    if (shift) {
-        if (!ctx->hist_fetched) {
-            k_fold_bins<<<(2 * nb + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, shift, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
-            CK(cudaGetLastError());
+    if (!ctx->hist_fetched) {
+        if (!ctx->hist_suspect) {
+            k_fold_bins<<<(nb + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, shift, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
+        } else {
+            // a packed record count may have wrapped (one minimizer with hundreds of millions of k-mers): exact rebuild from the meta
+            CK(cudaMemsetAsync(ctx->bin_fold.p, 0, sizeof(unsigned long long) * 2 * nb, ctx->stream));
+            if (ctx->local_nrec) {
+                k_rebuild_hist<<<(unsigned)std::min<u64>((ctx->local_nrec + 255) / 256, (u64)ctx->num_sms * 16), 256, 0, ctx->stream>>>(
+                    (const u32*)ctx->meta.p, ctx->local_nrec, shift, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
+            }
+            ctx->st.hist_rebuilt = 1;
         }
-        *d_hist = ctx->bin_fold.p;
+        CK(cudaGetLastError());
     }
+    *d_hist = ctx->bin_fold.p;
     ctx->hist_fetched = true;
     return 0;
 }
@@ -949,6 +1000,8 @@ static int plan_device(dskgpu_ctx* ctx, const void* d_ghist)
     if ((rc = ensure(ctx, ctx->loff, (qcap + 1) * 8))) return rc;
     if ((rc = ensure(ctx, ctx->bin2part, nb * 4ull))) return rc;
     cudaStream_t st = ctx->stream;
+    cudaEvent_t pa = get_event(ctx), pb = get_event(ctx);
+    cudaEventRecord(pa, st);
     const u64* gh = (const u64*)d_ghist; const u64* lh = (const u64*)d_lhist;
     u64* ex = (u64*)ctx->pl_ex.p; u64* E = (u64*)ctx->pl_E.p; u64* H = (u64*)ctx->pl_H.p; u64* bsum = (u64*)ctx->pl_bsum.p;
     unsigned long long* pk = (unsigned long long*)ctx->pl_pk.p; unsigned long long* pr = pk + nb; unsigned long long* pl = pr + nb;
@@ -967,6 +1020,8 @@ static int plan_device(dskgpu_ctx* ctx, const void* d_ghist)
     ctx->st.gpu_launches += ps_scan(st, PsLoad{lcnt_q}, nvals + 1, qcap, bsum, (u64*)ctx->loff.p);     // first record of every partition in q order
     k_plan_hdr<<<W, 256, 0, st>>>(gk_q, gr_q, (const u64*)ctx->loff.p, hdr); LAUNCHED();
     CK(cudaMemcpyAsync(ctx->h_hdr, hdr, sizeof(PlanHdr), cudaMemcpyDeviceToHost, st));
+    cudaEventRecord(pb, st);
+    ctx->spans.push_back({pa, pb, SPAN_PLAN});
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     const PlanHdr& h = *ctx->h_hdr;
@@ -1201,6 +1256,7 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
         // the owned heavy partitions: one contiguous run of records for the global hash / sort / bucket paths.  On one GPU
         // they already are the tail of lrecs (q order = id order, heavy ids last); on several their W segments are gathered.
         if (!ctx->heavy_recs.empty()) {
+            SpanGuard gh(ctx, SPAN_HEAVY);
             u64 hrec = 0;
             for (u64 r : ctx->heavy_recs) hrec += r;
             const u64* hp = nullptr;
@@ -1270,6 +1326,9 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
     ctx->st.ms_sort = span_ms(ctx, SPAN_SORT);
     ctx->st.ms_dominant_kernel = span_ms(ctx, SPAN_DOM, &ctx->st.dominant_kernel_launches);
     ctx->st.ms_exchange = span_ms(ctx, SPAN_XCHG); ctx->st.exchange_bytes_out = ctx->xchg_bytes_out;
+    ctx->st.ms_plan = span_ms(ctx, SPAN_PLAN); ctx->st.ms_count_heavy = span_ms(ctx, SPAN_HEAVY);
+    ctx->st.ms_push_wall = 0;
+    if (ctx->push_timed) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev_push0, ctx->ev_push1) == cudaSuccess) ctx->st.ms_push_wall = ms; }
     ctx->st.ms_total = ctx->st.ms_parse + ctx->st.ms_superk + ctx->st.ms_partition + ctx->st.ms_count + ctx->st.ms_sort;
     ctx->state = 1;
     return DSKGPU_OK;
@@ -1291,7 +1350,7 @@ static int reset_count_state(dskgpu_ctx* ctx)
     ctx->st.nb_groups_hash = ctx->st.nb_groups_sort = 0; ctx->st.nb_groups_bucket = 0; ctx->st.nb_hash_regroups = 0;
     // timing spans of the counting stage belong to the pass that produced the results
     std::vector<dskgpu_ctx::Span> keep;
-    for (auto& sp : ctx->spans) if (sp.kind != SPAN_COUNT && sp.kind != SPAN_SORT && sp.kind != SPAN_DOM && sp.kind != SPAN_SORTPASS) keep.push_back(sp);
+    for (auto& sp : ctx->spans) if (sp.kind != SPAN_COUNT && sp.kind != SPAN_SORT && sp.kind != SPAN_DOM && sp.kind != SPAN_SORTPASS && sp.kind != SPAN_HEAVY) keep.push_back(sp);
     ctx->spans.swap(keep);
     return 0;
 }
@@ -1363,6 +1422,23 @@ int dskgpu_xchg_prepare(dskgpu_ctx* ctx, uint64_t* local4)
     use_device(ctx);
     int rc = stage_totals(ctx); if (rc) return rc;
     local4[0] = ctx->local_nkm; local4[1] = ctx->local_nrec; local4[2] = ctx->sample_nkm; local4[3] = ctx->sample_distinct;
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_sketch(dskgpu_ctx* ctx, uint32_t* sketch)
+{
+    if (!ctx || !sketch) return DSKGPU_ERR_ARG;
+    use_device(ctx);
+    int rc = stage_totals(ctx); if (rc) return rc;
+    memcpy(sketch, ctx->h_hll, sizeof(u32) * HLL_M);
+    return DSKGPU_OK;
+}
+
+int dskgpu_xchg_set_sketch(dskgpu_ctx* ctx, const uint32_t* merged)
+{
+    if (!ctx || !merged) return DSKGPU_ERR_ARG;
+    if (ctx->global_set) FAIL(DSKGPU_ERR_STATE, "xchg_set_sketch after xchg_set_global");
+    ctx->sketch_distinct = hll_estimate(merged);
     return DSKGPU_OK;
 }
 
@@ -1598,6 +1674,11 @@ int dskgpu_multi_finish(dskgpu_ctx* const* ctxs, int n)
     // 1. job totals (k-mers, records, density sample) -> the same bin level and partition size everywhere
     uint64_t g4[4] = {0, 0, 0, 0};
     for (int r = 0; r < n; r++) { uint64_t l4[4]; if ((rc = dskgpu_xchg_prepare(ctxs[r], l4))) return rc; for (int i = 0; i < 4; i++) g4[i] += l4[i]; }
+    {
+        std::vector<uint32_t> merged(HLL_M, 0), one(HLL_M);
+        for (int r = 0; r < n; r++) { if ((rc = dskgpu_xchg_sketch(ctxs[r], one.data()))) return rc; for (u32 i = 0; i < HLL_M; i++) merged[i] = std::max(merged[i], one[i]); }
+        for (int r = 0; r < n; r++) if ((rc = dskgpu_xchg_set_sketch(ctxs[r], merged.data()))) return rc;
+    }
     int level = 0;
     for (int r = 0; r < n; r++) { int lv = 0; if ((rc = dskgpu_xchg_set_global(ctxs[r], g4, &lv))) return rc; if (r && lv != level) FAIL(DSKGPU_ERR_STATE, "multi_finish: ranks disagree on the bin level"); level = lv; }
     // 2. whole-job bin histogram: every device sums the ranks' histograms through peer pointers (the stand-in for the all-reduce)

@@ -42,7 +42,16 @@ struct Counters {
     unsigned long long sample_sumsq;  // density sample: sum of count^2 over its distinct k-mers (occurrence-weighted multiplicity)
     unsigned long long kmers_pass;    // valid k-mers whose minimizer belongs to the current pass (== kmers_in_recs)
     unsigned long long sample_solid;  // density sample: distinct k-mers whose summed count reaches the smallest abundance-min
+    unsigned int hist_suspect;        // a fine bin holds so many k-mers that its packed record count may have wrapped (k_check_bins)
+    unsigned int pad1;
 };
+
+// fine-bin histogram entry: records in the top 28 bits, k-mers in the low 36 -- ONE 64-bit RED per record instead of two, and
+// half the L2 footprint (32 MB for 2^22 bins).  A record holds at least one k-mer, so a bin whose k-mer field is below 2^28
+// cannot have wrapped its record field; anything else (one minimizer with > 268 M k-mers on one GPU: degenerate input) is
+// flagged by k_check_bins and the histogram is rebuilt exactly from the record meta (k_rebuild_hist).
+constexpr int BINH_KBITS = 36;
+constexpr unsigned long long BINH_KMASK = (1ULL << BINH_KBITS) - 1ULL;
 
 #ifdef __CUDACC__
 
@@ -52,7 +61,7 @@ template <int KW>
 __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict__ codes, const StreamState* __restrict__ ss,
                                                            int k, int m, int bank, u64* __restrict__ recs,
                                                            u32* __restrict__ rec_meta, u64 rec_cap, Counters* ctr,
-                                                           unsigned long long* __restrict__ bin_hist /*[2][NBINS_FINE] records, k-mers*/,
+                                                           unsigned long long* __restrict__ bin_hist /*[NBINS_FINE] packed: records << 36 | k-mers*/,
                                                            u32 nb_passes, u32 pass_id)
 {
     constexpr int RW = 2 * KW;
@@ -254,8 +263,7 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
         // fine histogram of the bins while the records are produced (fire-and-forget REDs under an ALU-bound kernel)
         const u32 bin = bin_of(s_lmn[i]);
         rec_meta[ri] = bin | (nk << 24);
-        atomicAdd(&bin_hist[bin], 1ULL);
-        atomicAdd(&bin_hist[NBINS_FINE + bin], (unsigned long long)nk);
+        atomicAdd(&bin_hist[bin], (1ULL << BINH_KBITS) | (unsigned long long)nk);
         nk_sum += nk;
     }
     nk_sum = __reduce_add_sync(0xFFFFFFFFu, nk_sum);
@@ -287,16 +295,34 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(const u64* __restri
     }
 }
 
-// fine bin histogram [2][NBINS_FINE] -> level histogram [2][NBINS_FINE >> shift]
+// packed fine bin histogram [NBINS_FINE] -> level histogram [2][NBINS_FINE >> shift] (records per bin, then k-mers per bin)
 __global__ void k_fold_bins(const unsigned long long* __restrict__ fine, int shift, unsigned long long* __restrict__ out)
 {
     const u32 nb = NBINS_FINE >> shift, per = 1u << shift;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * nb; i += gridDim.x * blockDim.x) {
-        const u32 half = i >= nb ? 1u : 0u, b = i - half * nb;
-        const unsigned long long* src = fine + (size_t)half * NBINS_FINE + ((size_t)b << shift);
-        unsigned long long acc = 0;
-        for (u32 j = 0; j < per; j++) acc += src[j];
-        out[i] = acc;
+    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+        const unsigned long long* src = fine + ((size_t)b << shift);
+        unsigned long long r = 0, k = 0;
+        for (u32 j = 0; j < per; j++) { const unsigned long long v = src[j]; r += v >> BINH_KBITS; k += v & BINH_KMASK; }
+        out[b] = r; out[nb + b] = k;
+    }
+}
+
+// flags a fine bin whose k-mer field reached `limit` (2^28 in production): its record field may have wrapped
+__global__ void k_check_bins(const unsigned long long* __restrict__ fine, unsigned long long limit, Counters* ctr)
+{
+    bool bad = false;
+    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < NBINS_FINE; b += gridDim.x * blockDim.x) bad |= (fine[b] & BINH_KMASK) >= limit;
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicExch(&ctr->hist_suspect, 1u);
+}
+
+// the exact level histogram from the record meta (bin | nk << 24), for the flagged case: two 64-bit atomics per record
+__global__ void k_rebuild_hist(const u32* __restrict__ rec_meta, u64 nrec, int shift, unsigned long long* __restrict__ out)
+{
+    const u32 nb = NBINS_FINE >> shift;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (u64)gridDim.x * blockDim.x) {
+        const u32 mt = rec_meta[i], b = (mt & (NBINS_FINE - 1)) >> shift;
+        atomicAdd(&out[b], 1ULL);
+        atomicAdd(&out[nb + b], (unsigned long long)(mt >> 24));
     }
 }
 

@@ -78,7 +78,10 @@ def distributed_finish(eng, dist, device):
 
     g4 = torch.from_numpy(eng.xchg_prepare().astype(np.int64)).to(device)     # k-mers, records, density sample (k-mers, distinct)
     mark("prepare (push kernels done)")
+    sk = torch.from_numpy(eng.xchg_sketch().astype(np.int32)).to(device)       # distinct k-mers of the UNION of the ranks' samples
     dist.all_reduce(g4)                                                       # every rank picks the same bin level / partition size
+    dist.all_reduce(sk, op=dist.ReduceOp.MAX)
+    eng.xchg_set_sketch(sk.cpu().numpy().astype(np.uint32))
     level = eng.xchg_set_global(g4.cpu().numpy().astype(np.uint64))
     mark("allreduce totals")
     G = torch.empty(2 << level, dtype=torch.int64, device=device)             # (records, k-mers) per minimizer bin

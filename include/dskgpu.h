@@ -122,6 +122,10 @@ typedef struct dskgpu_stats {
     float    ms_exchange;
     uint32_t nb_solid_regrows;      /* counting stage redone because the solid-set buffers (sized from an estimate) were too small */
     uint64_t kmers_in_pass;         /* valid k-mers whose minimizer belongs to this context's pass (== kmers_nb_valid with one pass) */
+    float    ms_plan;               /* density sample + device planner (scans, renumbering, layout tables) */
+    float    ms_push_wall;          /* first to last kernel of the push phase on the stream (parse + super-k-mers + any gaps between chunks) */
+    uint32_t hist_rebuilt;          /* 1: the packed minimizer-bin histogram could have wrapped and was rebuilt exactly from the records */
+    float    ms_count_heavy;        /* part of ms_count spent on the heavy partitions (gather + global table / sort / bucket paths) */
 } dskgpu_stats;
 
 /* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */
@@ -218,7 +222,9 @@ int  dskgpu_abi_version(void);
  * copies inside one process) and the host reads one small header.  After all pushes:
  *   0. xchg_prepare      -> this rank's {k-mers, records, density-sample k-mers, density-sample distinct}; all-reduce (sum) the
  *                           four numbers, hand the sums to xchg_set_global: every rank then agrees on the bin level
- *                           (2^16 .. 2^22 bins) and on the partition size
+ *                           (2^16 .. 2^22 bins) and on the partition size.  The distinct / total ratio of the JOB needs the
+ *                           distinct k-mers of the UNION of the ranks' samples: xchg_sketch returns HyperLogLog registers of
+ *                           this rank's sample, all-reduce them with MAX and hand them to xchg_set_sketch before xchg_set_global
  *   1. xchg_hist         copies this rank's (records, k-mers) per minimizer bin, [2 * B] u64, into a DEVICE buffer of the
  *                           caller, who all-reduces it in place
  *   2. xchg_plan         plans the partitions ON THE DEVICE from the all-reduced histogram (dsk_b200/csrc/plan.cuh); every
@@ -238,6 +244,9 @@ int  dskgpu_abi_version(void);
  *      owned partitions: the counting kernel reads every partition as W segments, one per sender. */
 int dskgpu_xchg_local_totals(dskgpu_ctx* ctx, uint64_t* kmers, uint64_t* records);
 int dskgpu_xchg_prepare(dskgpu_ctx* ctx, uint64_t* local4 /*[4]*/);
+#define DSKGPU_SKETCH_LEN 4096
+int dskgpu_xchg_sketch(dskgpu_ctx* ctx, uint32_t* sketch /*[DSKGPU_SKETCH_LEN]*/);
+int dskgpu_xchg_set_sketch(dskgpu_ctx* ctx, const uint32_t* merged /*[DSKGPU_SKETCH_LEN], element-wise max over ranks*/);
 int dskgpu_xchg_set_global(dskgpu_ctx* ctx, const uint64_t* global4 /*[4] sums over ranks*/, int* log2_bins /*out: B = 1 << *log2_bins*/);
 int dskgpu_xchg_hist(dskgpu_ctx* ctx, void* d_hist_out /*device, [2*B] u64*/);
 int dskgpu_xchg_plan(dskgpu_ctx* ctx, const void* d_global_hist /*device, [2*B] u64*/, uint32_t* nparts, uint32_t* parts_per_rank,

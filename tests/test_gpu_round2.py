@@ -167,6 +167,28 @@ def test_device_planner_equals_host_mirror(k, slots, mode):
         eng.close()
 
 
+@pytest.mark.parametrize("k", [31, 63])
+def test_packed_bin_histogram_rebuilt_when_it_could_wrap(k, monkeypatch):
+    """the fine-bin histogram packs (records, k-mers) in one word; a bin heavy enough for the record field to wrap is flagged
+    and the histogram is rebuilt exactly from the record meta -- forced here by lowering the limit; same plan, same counts"""
+    buf, n, _ = reads_fasta(G=300_000, coverage=30, L=150, err=0.01, seed=93)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], k, abundance_min=2)
+    plans = []
+    for limit in (None, "50"):
+        if limit:
+            monkeypatch.setenv("DSKGPU_TEST_HIST_LIMIT", limit)
+        with GpuCounter(kmer_size=k, abundance_min=2) as eng:
+            eng.push_bytes(data)
+            eng.finish()
+            st = eng.stats()
+            assert st["hist_rebuilt"] == (1 if limit else 0)
+            kk, cc = eng.solid()
+            assert_equals_oracle(kk, cc, eng.histogram()[0], ref)
+            plans.append(eng.debug_plan())
+    assert all((a == b).all() if hasattr(a, "all") else a == b for a, b in zip(plans[0], plans[1]))
+
+
 # ---------------------------------------------------------------- several ranks in one process (dskgpu_multi_finish)
 def run_multi(devices, k, data, **kw):
     W = len(devices)
