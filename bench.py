@@ -527,7 +527,7 @@ def main():
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0; dom_ms = 0.0; dom_n = 0; stage = {}; x_ms = 0.0; x_bytes = 0; push_gap = 0.0; heavy_ms = 0.0
+    launches = 0; dom_ms = 0.0; dom_n = 0; stage = {}; x_ms = 0.0; x_bytes = 0; push_gap = 0.0; heavy_ms = 0.0; xt_ms = {}
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
@@ -538,6 +538,8 @@ def main():
             stage[kk] = stage.get(kk, 0.0) + st[kk] / args.steps
         push_gap += (st["ms_push_wall"] - st["ms_parse"] - st["ms_superk"]) / args.steps
         heavy_ms += st["ms_count_heavy"] / args.steps
+        for kk, v in getattr(eng, "xchg_times", {}).items():
+            xt_ms[kk] = xt_ms.get(kk, 0.0) + v / args.steps
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -566,6 +568,10 @@ def main():
     else:
         x_ms_max, x_bytes_all = 0.0, 0.0
     chk = [int(x) for x in chk.cpu()]
+    by_rank = None
+    if world > 1:
+        by_rank = [None] * world
+        dist.all_gather_object(by_rank, {"stage_ms": stage, "exchange_meta_ms": xt_ms, "ms": ms / args.steps, "heavy_ms": heavy_ms})
     checks.update({"histogram_mass": chk[0], "valid_kmers": chk[1], "distinct_kmers": chk[2], "solid_kmers": chk[3],
                    "every_valid_kmer_counted": (chk[0] == chk[1]) if not args.histo2d else None})
     value = kmers_all * args.steps / (ms_all / 1e3) / 1e9
@@ -687,6 +693,8 @@ def main():
                               "peak_measured_peer_copy": 770.0, "frac_of_measured": per_gpu / 770.0,
                               "share_of_step": (x_ms_max / args.steps) / (ms_all / args.steps),
                               "note": "one contiguous copy per (sender, receiver) pair, 16-byte peer stores; a rank's own partitions never move"}
+        if by_rank:
+            line["by_rank"] = by_rank
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline and not args.histo2d:

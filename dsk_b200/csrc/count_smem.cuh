@@ -38,8 +38,14 @@
 
 namespace dsk {
 
-constexpr int CS_THREADS = 1024;               // one CTA per SM: the biggest table (measured: 2 x 512 threads with half tables is 25 % slower)
-constexpr int CS_CTAS_PER_SM = 1;
+#ifndef CS_THREADS_N
+#define CS_THREADS_N 1024
+#endif
+#ifndef CS_CTAS_N
+#define CS_CTAS_N 1
+#endif
+constexpr int CS_THREADS = CS_THREADS_N;       // one CTA per SM: the biggest table (measured: 2 x 512 threads with half tables is 25 % slower)
+constexpr int CS_CTAS_PER_SM = CS_CTAS_N;
 #ifndef CS_CHUNK
 #define CS_CHUNK 32                            // records a warp takes at a time (<= 32)
 #endif
@@ -63,7 +69,13 @@ constexpr int CS_MAX_SPLIT0 = 4;
 // nb = counts kept per slot (1, or one per bank when the processors need per-bank counts: -histo2D, solidity kinds)
 // records the shared-memory job buffer holds (a job with more records is streamed through it in slices); sized so that
 // the table and the buffer fill up together at the densities of 30-100x read sets (see stage_count / plan_target_kmers)
-template <int KW> DSK_HD u32 cs_bufrec() { return KW == 1 ? 2368u : 544u; }
+#ifndef CS_BUFREC1
+#define CS_BUFREC1 2368
+#endif
+#ifndef CS_BUFREC2
+#define CS_BUFREC2 544
+#endif
+template <int KW> DSK_HD u32 cs_bufrec() { return KW == 1 ? (u32)CS_BUFREC1 : (u32)CS_BUFREC2; }
 template <int KW> DSK_HD size_t cs_smem_bytes(u32 cap, int nb = 1)
 {
     return (size_t)cap * (8 * KW + 4 * nb)                          // table: keys + counts
@@ -157,6 +169,35 @@ __device__ __forceinline__ bool cs_resolve(u32 keys_a, u32 slot, const Kmer<2>& 
     return (olo == EMPTY && ohi == EMPTY) || (olo == key.w[0] && ohi == key.w[1]);
 }
 
+// snapshot tests: a full match is final (slots only go EMPTY -> key); a complete foreign key is final too
+__device__ __forceinline__ bool cs_match(const Kmer<1>& key, const CsSnap<1>& sn) { return sn.w[0] == key.w[0]; }
+__device__ __forceinline__ bool cs_match(const Kmer<2>& key, const CsSnap<2>& sn) { return sn.w[0] == key.w[0] && sn.w[1] == key.w[1]; }
+__device__ __forceinline__ bool cs_foreign(const Kmer<1>& key, const CsSnap<1>& sn) { return sn.w[0] != ~0ULL && sn.w[0] != key.w[0]; }
+__device__ __forceinline__ bool cs_foreign(const Kmer<2>& key, const CsSnap<2>& sn)
+{
+    return sn.w[0] != ~0ULL && sn.w[1] != ~0ULL && !(sn.w[0] == key.w[0] && sn.w[1] == key.w[1]);
+}
+
+// predicated claim of an (apparently) empty slot: the CAS is issued under a predicate, not behind a branch, so the fast
+// path of the insert stays straight-line.  Returns true when the slot now holds `key` (claimed, or claimed by an equal key).
+__device__ __forceinline__ bool cs_claim_if(bool p, u32 keys_a, u32 slot, const Kmer<1>& key)
+{
+    const u64 EMPTY = ~0ULL;
+    u64 o = 0;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q atom.shared.cas.b64 %0, [%1], %2, %3;\n\t}"
+                 : "+l"(o) : "r"(keys_a + slot * 8u), "l"(EMPTY), "l"(key.w[0]), "r"((u32)p) : "memory");
+    return p && (o == EMPTY || o == key.w[0]);
+}
+__device__ __forceinline__ bool cs_claim_if(bool p, u32 keys_a, u32 slot, const Kmer<2>& key)
+{
+    const u64 EMPTY = ~0ULL;
+    u64 olo = 0, ohi = 0;
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b128 c, s, d;\n\tsetp.ne.u32 q, %7, 0;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\tmov.b128 d, {%0, %1};\n\t"
+                 "@q atom.shared.cas.b128 d, [%6], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                 : "+l"(olo), "+l"(ohi) : "l"(EMPTY), "l"(EMPTY), "l"(key.w[0]), "l"(key.w[1]), "r"(keys_a + slot * 16u), "r"((u32)p) : "memory");
+    return p && ((olo == EMPTY && ohi == EMPTY) || (olo == key.w[0] && ohi == key.w[1]));
+}
+
 // 32 bases of a record starting at base p (top bits first); RW words in registers, no dynamic indexing
 template <int RW>
 __device__ __forceinline__ u64 cs_window(const u64* r, int p)
@@ -210,7 +251,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                                                               const u32* __restrict__ bucket_n = nullptr, u32 slab = 0)
 {
     constexpr int RW = 2 * KW;
-    constexpr u32 BUFREC = KW == 1 ? 2368u : 544u;                                 // == cs_bufrec<KW>()
+    constexpr u32 BUFREC = KW == 1 ? (u32)CS_BUFREC1 : (u32)CS_BUFREC2;            // == cs_bufrec<KW>()
     constexpr u32 RPT = (BUFREC + CS_THREADS - 1) / CS_THREADS;                   // records per thread in the prefix scan
     const u32 nb = MB ? (u32)nb_arg : 1u;
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -238,6 +279,10 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
     for (int i = t; i < HIST_SMEM_BINS; i += CS_THREADS) s_hist[i] = 0;
     if constexpr (MB) for (int i = t; i < 11 * CS_H2_I1; i += CS_THREADS) s_h2[i] = 0;
     u32 n1 = 0, n2 = 0, ndist = 0, nsplit = 0, ovf_seen = 0, mb_parity = 0;
+    // solidity of a summed count c (an int32 >= 1 when the slot is occupied): amin <= c <= amax as one unsigned range test
+    const long long sol_a = amin < 1 ? 1 : amin, sol_b = amax > 0x7FFFFFFFLL ? 0x7FFFFFFFLL : amax;
+    const bool sol_any = sol_b >= sol_a && sol_a <= 0x7FFFFFFFLL;
+    const u32 sol_lo = sol_any ? (u32)sol_a : 0xFFFFFFFFu, sol_span = sol_any ? (u32)(sol_b - sol_a) : 0u;   // (no count is 2^32 - 1)
     u64* my_qkey = s_qkey + (size_t)warp * CS_QCAP * KW;
     u32* my_qslot = s_qslot + (size_t)warp * CS_QCAP;
     const u32 keys_a = cs_saddr(s_keys), counts_a = cs_saddr(s_counts);
@@ -279,23 +324,49 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
         publish(atomicAdd(work_counter, 1u));
     }
 
-    // resolve everything in this warp's retry queue (all lanes active, full probe sequences)
-    auto drain = [&](u32 qn) {
-        __syncwarp();
-        for (u32 b0 = 0; b0 < qn; b0 += 32) {
-            const u32 idx = b0 + lane;
-            if (idx < qn) {
-                Kmer<KW> key;
+    // The insert is a uniform pipeline: the FAST path of a k-mer is straight-line code -- one snapshot of its home slot, a
+    // predicated increment when the slot already holds the key (most k-mers of a 30-100x read set are repeats) -- and every
+    // other k-mer (new key, or home slot taken) goes to a per-warp ring of (key, slot, probes) entries with one ballot.  The
+    // ring is served 32 entries at a time with all lanes active, ONE probe per entry and round (claim by CAS, or step to the
+    // next slot and go back to the ring): no lane ever waits for another lane's probe sequence, and there is no divergent
+    // branch on the path of a k-mer (r02g profile: 45 % of the warp instructions of the previous version were control flow,
+    // 21 of 32 lanes active on average).
+    u32 qh = 0, qc = 0;                                                            // ring head / entries (warp-uniform)
+    auto ring_push = [&](bool put, const Kmer<KW>& key, u32 sw) {
+        const u32 pm = __ballot_sync(0xFFFFFFFFu, put);
+        if (put) {
+            const u32 pos = (qh + qc + (u32)__popc(pm & lt_mask)) & (u32)(CS_QCAP - 1);
 #pragma unroll
-                for (int q = 0; q < KW; q++) key.w[q] = my_qkey[idx * KW + q];
-                u32 slot = my_qslot[idx], bank = 0;
-                if constexpr (MB) { bank = slot >> 16; slot &= 0xFFFFu; }             // cap <= 16384
-                bool ok = false;
-                for (int p = 0; p < CS_MAXPROBE && !ok; p++) { ok = cs_probe(keys_a, slot, key); if (!ok) slot = (slot + 1 == cap) ? 0u : slot + 1; }
-                if (ok) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u); else atomicAdd(&s_ovf, 1u);
+            for (int q = 0; q < KW; q++) my_qkey[pos * KW + q] = key.w[q];
+            my_qslot[pos] = sw;
+        }
+        qc += (u32)__popc(pm);
+    };
+    // one round over (up to) 32 ring entries: entry = key + (slot | bank << 16 | probes << 24)
+    auto ring_serve = [&]() {
+        __syncwarp();
+        const u32 take = min(qc, 32u);
+        const bool on = (u32)lane < take;
+        const u32 idx = (qh + (u32)lane) & (u32)(CS_QCAP - 1);
+        Kmer<KW> key; u32 sw = 0;
+#pragma unroll
+        for (int q = 0; q < KW; q++) key.w[q] = on ? my_qkey[idx * KW + q] : 0ULL;
+        if (on) sw = my_qslot[idx];
+        __syncwarp();                                                              // entries are in registers before the tail is rewritten
+        bool again = false;
+        if (on) {
+            u32 slot = sw & 0xFFFFu;
+            const u32 bank = MB ? ((sw >> 16) & 0xFFu) : 0u;
+            if (cs_probe(keys_a, slot, key)) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u);
+            else {
+                const u32 np = (sw >> 24) + 1u;
+                slot = (slot + 1 == cap) ? 0u : slot + 1;
+                if (np >= (u32)CS_MAXPROBE) atomicAdd(&s_ovf, 1u);
+                else { again = true; sw = slot | (bank << 16) | (np << 24); }
             }
         }
-        __syncwarp();
+        qh = (qh + take) & (u32)(CS_QCAP - 1); qc -= take;
+        ring_push(again, key, sw);
     };
 
     for (;;) {
@@ -374,7 +445,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 // prefix over the 32 warp totals: every warp scans them with shuffles (one LDS + 5 steps instead of 32 LDS + adds)
                 u32 wpre, I;
                 {
-                    u32 ws = s_wsum[lane], wi = ws;
+                    u32 ws = lane < CS_WARPS ? s_wsum[lane] : 0u, wi = ws;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += o; }
                     I = __shfl_sync(0xFFFFFFFFu, wi, 31);
@@ -387,8 +458,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 }
                 __syncthreads();
 
-                const u32 lo = (I * (u32)warp) >> 5, hi = (I * (u32)(warp + 1)) >> 5;        // this warp's items
-                u32 qn = 0;
+                const u32 lo = (I * (u32)warp) / (u32)CS_WARPS, hi = (I * (u32)(warp + 1)) / (u32)CS_WARPS;        // this warp's items
                 if (lo < hi) {
                     // record owning item `lo`: the largest r with pref[r] <= lo (32-ary search by ballots; pref[0] = 0)
                     u32 rcur;
@@ -426,6 +496,8 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                         rcur = __shfl_sync(0xFFFFFFFFu, rcur + ro + ((x + 1u >= ex_r + (nk_r + CS_Q - 1) / CS_Q) ? 1u : 0u), 31);
                         u32 bank = 0;
                         Kmer<KW> f, rc;
+#pragma unroll
+                        for (int q = 0; q < KW; q++) { f.w[q] = 0; rc.w[q] = 0; }
                         u64 nextb = 0;
                         if (cnt > 0) {
                             if constexpr (MB) bank = (u32)rw[RW - 1] & 0xFFu;
@@ -443,14 +515,12 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                             Kmer<KW> cc[PH]; u32 sl0[PH]; u32 actm = 0;
 #pragma unroll
                             for (int v = 0; v < PH; v++) {
-                                const int u = g + v;
-                                sl0[v] = 0;
-                                if (u < cnt) {
-                                    if (u) { kmer_roll(f, rc, (int)(nextb >> 62), k); nextb <<= 2; }
-                                    cc[v] = kmer_canonical(f, rc);
-                                    const u32 h = cs_hash(cc[v]);
-                                    if (((h >> 8) & smask) == res) { actm |= 1u << v; sl0[v] = __umulhi(h, cap); }
-                                }
+                                const int u = g + v;                                   // (straight-line: lanes past their item's end compute on and are masked)
+                                if (u) { kmer_roll(f, rc, (int)(nextb >> 62), k); nextb <<= 2; }
+                                cc[v] = kmer_canonical(f, rc);
+                                const u32 h = cs_hash(cc[v]);
+                                sl0[v] = __umulhi(h, cap);
+                                actm |= (u < cnt && ((h >> 8) & smask) == res) ? (1u << v) : 0u;
                             }
                             CsSnap<KW> sn[PH];
 #pragma unroll
@@ -459,29 +529,21 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                             }
 #pragma unroll
                             for (int v = 0; v < PH; v++) {
-                                bool pending = false, found = false; u32 slot = sl0[v];
-                                if ((actm >> v) & 1u) {
-                                    found = cs_resolve(keys_a, slot, cc[v], sn[v]);
-                                    if (!found) { slot = (slot + 1 == cap) ? 0u : slot + 1; found = cs_probe(keys_a, slot, cc[v]); }
-                                    if (!found) { pending = true; slot = (slot + 1 == cap) ? 0u : slot + 1; }
-                                }
-                                const u32 pm = __ballot_sync(0xFFFFFFFFu, pending);         // (also the reconvergence point of the probes)
-                                if (found) cs_inc32(counts_a + (MB ? slot * nb + bank : slot) * 4u);
-                                if (pm) {
-                                    if (pending) {
-                                        const u32 pos = qn + (u32)__popc(pm & lt_mask);
-#pragma unroll
-                                        for (int q = 0; q < KW; q++) my_qkey[pos * KW + q] = cc[v].w[q];
-                                        my_qslot[pos] = MB ? (slot | (bank << 16)) : slot;
-                                    }
-                                    qn += (u32)__popc(pm);
-                                    if (qn > CS_QCAP - 32) { drain(qn); qn = 0; }
-                                }
+                                const bool act = (actm >> v) & 1u;
+                                bool hit = act && cs_match(cc[v], sn[v]);
+                                // home slot not (completely) taken by another key: claim it -- a predicated CAS, no branch.  The
+                                // CAS tells the truth whatever the snapshot showed; a k-mer goes to the ring only when its home
+                                // slot holds a foreign key (final: slots only go EMPTY -> key), one slot further, one probe done.
+                                hit |= cs_claim_if(act && !hit && !cs_foreign(cc[v], sn[v]), keys_a, sl0[v], cc[v]);
+                                if (hit) cs_inc32(counts_a + (MB ? sl0[v] * nb + bank : sl0[v]) * 4u);
+                                const u32 s1 = (sl0[v] + 1 == cap) ? 0u : sl0[v] + 1;
+                                ring_push(act && !hit, cc[v], s1 | (MB ? (bank << 16) : 0u) | (1u << 24));
+                                while (qc >= 32u) ring_serve();                        // (a round may hand every entry back: the ring must be under 32 before the next push)
                             }
                         }
                     }
                 }
-                if (qn) drain(qn);
+                while (qc) ring_serve();
                 __syncthreads();                                                   // inserts of the slice done, job buffer free
             }
             const u32 ovf_now = *reinterpret_cast<volatile u32*>(&s_ovf);          // stable: nobody inserts until after the next barriers
@@ -547,8 +609,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                         // counts 0, 1 and 2 -- nine slots out of ten -- are handled without a branch
                         ndist += (c != 0u) ? 1u : 0u; n1 += (c == 1u) ? 1u : 0u; n2 += (c == 2u) ? 1u : 0u;
                         if (c > 2u) { const u32 bin = histo_bin((int32_t)c); if (bin) { if (bin < HIST_SMEM_BINS) atomicAdd(&s_hist[bin], 1u); else atomicAdd(&g_hist[bin], 1ULL); } }
-                        const long long sum = (long long)(int32_t)c;
-                        solidm |= (c != 0u && amin <= sum && sum <= amax) ? (1u << (4 * v + q)) : 0u;
+                        solidm |= (c - sol_lo <= sol_span) ? (1u << (4 * v + q)) : 0u;   // amin <= c <= amax, c != 0 (one unsigned range test)
                     }
                 }
             }
@@ -556,19 +617,12 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
             u32 inc = n;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
-            if (lane == 31) s_wsum[warp] = inc;
-            __syncthreads();
-            u32 wpre, tot;
-            {
-                u32 ws = s_wsum[lane], wi = ws;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += o; }
-                tot = __shfl_sync(0xFFFFFFFFu, wi, 31);
-                wpre = __shfl_sync(0xFFFFFFFFu, wi - ws, warp);
-            }
-            // one bump of the global cursor per job; while it is in flight every thread clears the slot groups it scanned that
-            // hold nothing solid (nobody else reads or writes them in this phase)
-            if (tot && t == 0) s_base = atomicAdd(&ctr->solid_n, (unsigned long long)tot);
+            // one bump of the global cursor per WARP and job (no block-wide scan, no barrier: the order of the solid pairs is
+            // settled by the final sort); while it is in flight every thread clears the slot groups it scanned that hold
+            // nothing solid (nobody else reads or writes them in this phase)
+            const u32 tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            unsigned long long wbase = 0;
+            if (tot && lane == 31) wbase = atomicAdd(&ctr->solid_n, (unsigned long long)tot);
             if constexpr (MB) {
                 u32 v = 0;
                 for (u32 sl = t; sl < cap; sl += CS_THREADS, v++) {
@@ -589,8 +643,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 }
             }
             if (tot) {
-                __syncthreads();
-                u64 pos = s_base + wpre + inc - n;
+                u64 pos = __shfl_sync(0xFFFFFFFFu, wbase, 31) + inc - n;
                 u32 m = solidm;
                 while (m) {
                     const int b = __ffs((int)m) - 1; m &= m - 1;

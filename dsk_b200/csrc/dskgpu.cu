@@ -1268,9 +1268,11 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
                 u64* ho = ctx->h_heavy;                                           // pinned, >= 2 * nh words: reuse as staging of the prefix
                 { u64 o = 0; for (size_t i = 0; i < nh; i++) { ho[i] = o; o += ctx->heavy_recs[i]; } }
                 CK(cudaMemcpyAsync(ctx->hoff.p, ho, nh * 8, cudaMemcpyHostToDevice, ctx->stream));
-                const unsigned gg = (unsigned)std::min<u64>((u64)nh * W, (u64)ctx->num_sms * 8);
+                const u32 total_blocks = (u32)ctx->num_sms * 8;
+                const u32 G = (u32)std::max<u64>(1, std::min<u64>(total_blocks, total_blocks / std::max<u64>(1, (u64)nh * W)));
+                const unsigned gg = total_blocks / G * G;
                 k_gather_heavy<<<gg, 256, 0, ctx->stream>>>((const XchgTab*)ctx->xtab.p, (const u64*)ctx->rcnt_dev, h.PW, W, ctx->nl_me, (u32)nh,
-                                                           (const u64*)ctx->hoff.p, (ulonglong2*)ctx->hrecs.p, (u32)ctx->RW / 2); LAUNCHED();
+                                                           (const u64*)ctx->hoff.p, (ulonglong2*)ctx->hrecs.p, (u32)ctx->RW / 2, G); LAUNCHED();
                 CK(cudaStreamSynchronize(ctx->stream));                           // h_heavy is rewritten by the next plan; cheap next to the heavy paths
                 hp = (const u64*)ctx->hrecs.p;
             }

@@ -301,10 +301,14 @@ __global__ void __launch_bounds__(256) k_xchg_send(const ulonglong2* __restrict_
 
 // owned heavy partitions (jobs [j0, j0 + nj) of my chunk): their W segments are gathered into one partition-major buffer
 // for the host-driven paths.  hoff[i] = first record of heavy job i in `out` (host-computed prefix of the whole-job records).
+// The grid is split into groups of G blocks; group g takes the segments w = g, g + ngroups, ... and its G blocks share the
+// vectors of a segment (a single hot minimizer = one partition of millions of records: every block must help copying it).
 __global__ void __launch_bounds__(256) k_gather_heavy(const XchgTab* __restrict__ tab, const u64* __restrict__ X, u32 PW, u32 W, u32 j0, u32 nj,
-                                                      const u64* __restrict__ hoff, ulonglong2* __restrict__ out, u32 v_per_rec)
+                                                      const u64* __restrict__ hoff, ulonglong2* __restrict__ out, u32 v_per_rec, u32 G)
 {
-    for (u32 w = blockIdx.x; w < nj * W; w += gridDim.x) {
+    const u32 ngroups = gridDim.x / G, grp = blockIdx.x / G, sub = blockIdx.x % G;
+    if (grp >= ngroups) return;
+    for (u32 w = grp; w < nj * W; w += ngroups) {
         const u32 i = w / W, s = w % W, j = j0 + i;
         u64 before = 0;
         for (u32 s2 = 0; s2 < s; s2++) before += X[(u64)s2 * PW + j + 1] - X[(u64)s2 * PW + j];
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(256) k_gather_heavy(const XchgTab* __restrict_
         const ulonglong2* src = reinterpret_cast<const ulonglong2*>(tab->segptr[s]) + a * v_per_rec;
         ulonglong2* dst = out + (hoff[i] + before) * v_per_rec;
         const u64 nv = n * v_per_rec;
-        for (u64 x = threadIdx.x; x < nv; x += 256) dst[x] = src[x];
+        for (u64 x = (u64)sub * 256 + threadIdx.x; x < nv; x += (u64)G * 256) dst[x] = src[x];
     }
 }
 

@@ -76,21 +76,32 @@ def distributed_finish(eng, dist, device):
         if not same_stream:
             cur.synchronize()
 
+    evs = []
+
+    def ev(name):            # device-side timeline of the metadata phases (elapsed times read after finish(), which syncs)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(cur)
+        evs.append((name, e))
+
     g4 = torch.from_numpy(eng.xchg_prepare().astype(np.int64)).to(device)     # k-mers, records, density sample (k-mers, distinct)
     mark("prepare (push kernels done)")
+    ev("start")
     sk = torch.from_numpy(eng.xchg_sketch().astype(np.int32)).to(device)       # distinct k-mers of the UNION of the ranks' samples
     dist.all_reduce(g4)                                                       # every rank picks the same bin level / partition size
     dist.all_reduce(sk, op=dist.ReduceOp.MAX)
     eng.xchg_set_sketch(sk.cpu().numpy().astype(np.uint32))
     level = eng.xchg_set_global(g4.cpu().numpy().astype(np.uint64))
     mark("allreduce totals")
+    ev("totals_allreduce")
     G = torch.empty(2 << level, dtype=torch.int64, device=device)             # (records, k-mers) per minimizer bin
     eng.xchg_hist(G.data_ptr())
     to_torch()
     dist.all_reduce(G)                                                         # every rank plans the same partitions
+    ev("hist_allreduce")
     to_lib()
     P, PW, need = eng.xchg_plan(G.data_ptr())                                  # device planner; the host reads one header
     mark("histogram allreduce + device plan")
+    ev("plan")
     send = torch.empty(W * PW + W, dtype=torch.int64, device=device)
     eng.xchg_counts(send.data_ptr())
     to_torch()
@@ -99,6 +110,7 @@ def distributed_finish(eng, dist, device):
     S = torch.empty(W * W, dtype=torch.int64, device=device)                   # S[s][o] = records rank s holds for rank o
     dist.all_gather_into_tensor(S, send[W * PW:])
     mark("count rows all-to-all (async)")
+    ev("rows_alltoall")
     # receive buffers: handles travel only when somebody has to grow (every rank sees the same `need`)
     st = getattr(eng, "_xchg_state", None)
     if st is None:
@@ -123,13 +135,17 @@ def distributed_finish(eng, dist, device):
     to_lib()
     eng.xchg_scatter(rows.data_ptr(), S.data_ptr())
     to_torch()
+    ev("scatter_send")
     flag = torch.zeros(1, dtype=torch.int32, device=device)
     dist.all_reduce(flag)                # stream-ordered: completes on a rank only after every rank's copy kernel has finished
+    ev("ordering_allreduce")
     to_lib()
     mark("scatter + chunk copies + ordering all-reduce (queued)")
     eng._xchg_keep = (G, send, rows, S, flag)                                  # alive until the kernels that read them have run
     eng.finish()
     mark("finish (count + order)")
+    if same_stream:
+        eng.xchg_times = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(evs, evs[1:])}
     if tr:
         for (_, a), (name, b) in zip(marks, marks[1:]):
             sys.stderr.write("[xchg r%d] %-52s +%8.3f ms\n" % (dist.get_rank(), name, 1e3 * (b - a)))
