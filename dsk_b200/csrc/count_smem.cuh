@@ -297,31 +297,49 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
             if (lo < hi) cs_bulk_copy(jrec_a + (lo - s0) * (u32)(RW * 8), s_segsrc[s] + (u64)(lo - s_segpre[s]) * (u64)(RW * 8), (hi - lo) * (u32)(RW * 8), mbar_a);
         }
     };
-    // thread 0: claims a job, publishes its descriptor and starts the bulk copy of its first slice of records
-    auto publish = [&](u32 job) {
-        s_job = job;
+    // WARP 0 (all its lanes): publishes the descriptor of job `job` (held by lane 0) and starts the bulk copies of its first
+    // slice of records.  Lane s looks after segment s -- its bounds, its source address, its copy -- so the W segments of a
+    // multi-GPU job cost one round trip to the tables, not W.
+    auto publish = [&](u32 job_lane0) {
+        const u32 job = __shfl_sync(0xFFFFFFFFu, job_lane0, 0);
+        if (lane == 0) s_job = job;
         if (job < njobs) {
-            if constexpr (KEYS) { s_drb = (u64)job * slab; s_dnrec = min(bucket_n[job], slab); s_dsplit = 0; }
+            if constexpr (KEYS) { if (lane == 0) { s_drb = (u64)job * slab; s_dnrec = min(bucket_n[job], slab); s_dsplit = 0; } }
             else {
-                u32 tot = 0;
-                for (u32 s = 0; s < segs.W; s++) {
-                    const u64 a = segs.X[(u64)s * segs.PW + job], b = segs.X[(u64)s * segs.PW + job + 1];
-                    s_segsrc[s] = segs.tab->segptr[s] + a * (u64)(RW * 8);
-                    s_segpre[s] = tot; tot += (u32)(b - a);
+                const bool mine = (u32)lane < segs.W;
+                u64 a = 0, b = 0, src = 0;
+                if (mine) { a = segs.X[(u64)lane * segs.PW + job]; b = segs.X[(u64)lane * segs.PW + job + 1]; src = segs.tab->segptr[lane] + a * (u64)(RW * 8); }
+                const u32 c = (u32)(b - a);
+                u32 inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+                const u32 pre = inc - c, tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                if (mine) { s_segsrc[lane] = src; s_segpre[lane] = pre; }
+                const u32 n0 = min(tot, BUFREC);
+                if (lane == 0) {
+                    s_segpre[segs.W] = tot;
+                    const float km = (float)segs.gk_q[(u64)segs.qbase + job];
+                    u32 sp0 = 0;
+                    while (sp0 < segs.max_split0 && km > segs.fit * (float)(1u << sp0)) sp0++;
+                    s_dnrec = tot; s_dsplit = sp0;
+                    if (tot) cs_mbar_expect(mbar_a, n0 * (u32)(RW * 8));
                 }
-                s_segpre[segs.W] = tot;
-                const float km = (float)segs.gk_q[(u64)segs.qbase + job];
-                u32 sp0 = 0;
-                while (sp0 < segs.max_split0 && km > segs.fit * (float)(1u << sp0)) sp0++;
-                s_dnrec = tot; s_dsplit = sp0;
-                if (tot) load_slice(0, min(tot, BUFREC));
+                __syncwarp();                                                      // the barrier is armed before any copy can complete on it
+                const u32 hi = min(n0, pre + c);
+                if (mine && pre < hi) cs_bulk_copy(jrec_a + pre * (u32)(RW * 8), src, (hi - pre) * (u32)(RW * 8), mbar_a);
             }
         }
+        __syncwarp();
     };
-    if (t == 0) {
-        s_ovf = 0;
-        if constexpr (!KEYS) cs_mbar_init(mbar_a, 1);
-        publish(atomicAdd(work_counter, 1u));
+    if (warp == 0) {
+        u32 first = 0;
+        if (lane == 0) {
+            s_ovf = 0;
+            if constexpr (!KEYS) cs_mbar_init(mbar_a, 1);
+            first = atomicAdd(work_counter, 1u);
+        }
+        __syncwarp();
+        publish(first);
     }
 
     // The insert is a uniform pipeline: the FAST path of a k-mer is straight-line code -- one snapshot of its home slot, a
@@ -382,7 +400,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
         if (t == 0) next_job = atomicAdd(work_counter, 1u);
         if (nrec == 0) {                                                           // an empty partition (uniform branch: nothing was copied, the table is clean)
             __syncthreads();                                                       // everybody has read the descriptor
-            if (t == 0) publish(next_job);
+            if (warp == 0) publish(next_job);
             continue;
         }
         u32 buf_state = 1;                                                         // 1: slice 0 of this job is on its way (publish); 2: resident; 0: neither
@@ -556,12 +574,12 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 if (lvl >= (u32)CS_MAX_SPLIT) { if (t == 0) atomicAdd(&ctr->smem_failed, 1u); }
                 else { stack[sp++] = ((lvl + 1) << 16) | (res + (1u << lvl)); stack[sp++] = ((lvl + 1) << 16) | res; nsplit++; }
                 if (KEYS || sp == 0) __syncthreads();                              // (the record path has barriers before its next insert)
-                if (sp == 0 && t == 0) publish(next_job);                          // gave up on the last item: move on
+                if (sp == 0 && warp == 0) publish(next_job);                       // gave up on the last item: move on
                 continue;
             }
             // the records of this job are no longer needed after its last work item: the next job's first slice is copied
             // into the buffer while the table is swept
-            if (sp == 0 && t == 0) publish(next_job);
+            if (sp == 0 && warp == 0) publish(next_job);
 
             // ---- sweep: CountProcessor chain over the table, compaction of the solid pairs, clear ---------------------
             // a slot is occupied iff its count is non-zero (a claim is always followed by its increment), so the scan reads

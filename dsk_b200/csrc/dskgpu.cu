@@ -1907,7 +1907,7 @@ int dskgpu_selftest_minimizers(const uint8_t* codes, size_t n, int k, int m, uin
         for (int i = 0; i < k; i++) if (codes[p + i] >> 2) ok = false;
         for (int j = 0; j + m <= k; j++) {
             u32 x = 0; for (int i = 0; i < m; i++) x = (x << 2) | (codes[p + j + i] & 3);
-            u32 v = mmer_value(x, m); if (v < best) best = v;
+            u32 v = mmer_order(x, m); if (v < best) best = v;
         }
         out_min[p] = best; out_valid[p] = ok;
     }

@@ -134,6 +134,21 @@ DSK_HD u32 mmer_value(u32 x, int m)
     return a1 ? mmask : v;
 }
 
+// What the kernels minimise over.  Identical to mmer_value for every allowed m-mer, so a k-mer that has an allowed m-mer gets
+// the reference's minimizer; the banned m-mers, which the reference all maps to ONE default value (mmask), keep their own
+// value above every allowed one.  The k-mers without any allowed m-mer (1e-3 of a random genome at m = 14: 144 M k-mers of
+// a 72 G k-mer job) are then spread over many minimizer bins instead of forming one giant partition on one rank.  Which
+// partition a k-mer lands in is unobservable in the results.
+DSK_HD u32 mmer_order(u32 x, int m)
+{
+    u32 rc = rev2_32(x ^ 0xAAAAAAAAu) >> (32 - 2 * m);
+    u32 v = rc < x ? rc : x;
+    const u32 mask_ma1 = 0x55555555u & ((1u << ((m - 2) * 2)) - 1u);
+    u32 a1 = ~(v | (v >> 2));
+    a1 = ((a1 >> 1) & a1) & mask_ma1;
+    return a1 ? (v | (1u << (2 * m))) : v;                    // m <= 14: 29 bits
+}
+
 // minimizer -> bin (the role of Repartitor::operator(), K/PartiInfo.hpp:323; any deterministic map is legal --
 // SURVEY.md appendix C).  Records are histogrammed into 2^NBINS_FINE_LOG2 fine bins while they are produced.  At finish
 // the histogram is folded to the level the job needs (2^16 bins for the 400 M k-mer configuration, up to 2^22 for

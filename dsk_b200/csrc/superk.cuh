@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             u32 x = (u32)(W >> (64 - 2 * (j + m))) & mmask;
-            s_mv[sk_pidx(p0 + j)] = mmer_value(x, m);
+            s_mv[sk_pidx(p0 + j)] = mmer_order(x, m);
         }
     };
     mvals8(t);

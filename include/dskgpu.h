@@ -279,7 +279,9 @@ int dskgpu_record_bytes(dskgpu_ctx* ctx);
 /* runs the record-scanner state machine sequentially on the host; out gets one byte per emitted code
  * (0..3 base, 4|code invalid base, 8 separator).  Returns number of codes or <0. */
 int64_t dskgpu_selftest_scan(const char* bytes, size_t n, int format, uint8_t* out, size_t out_cap);
-/* minimizer value of every k-mer window of a code string (host copy of the device function) */
+/* minimizer of every k-mer window of a code string (host copy of the device function).  Values below 4^m are the reference's
+ * minimizer (K/Model.hpp:1254-1287); a value with bit 2m set means "no allowed m-mer in this window": the reference uses its
+ * default minimizer (4^m - 1) there, the device keeps the smallest banned m-mer instead so that such k-mers spread over bins */
 int dskgpu_selftest_minimizers(const uint8_t* codes, size_t n, int k, int m, uint32_t* out_min, uint8_t* out_valid);
 /* super-k-mer packing round trip: codes -> records -> canonical k-mers (host copy of pack + expand) */
 int64_t dskgpu_selftest_superkmers(const uint8_t* codes, size_t n, int k, int m, uint64_t* out_kmers /*[n*words]*/, size_t cap, uint64_t* n_records);
