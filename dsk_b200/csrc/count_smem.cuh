@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
     __shared__ u32 s_h2[MB ? 11 * CS_H2_I1 : 1];                                   // -histo2D bins with dim-1 index < CS_H2_I1, all 11 dim-2 rows
     __shared__ u32 s_wsum[CS_WARPS];
     __shared__ u32 s_job, s_ovf;                                                   // s_ovf: overflow events so far (only ever incremented)
-    __shared__ unsigned long long s_base, s_drb;                                   // s_drb, s_dnrec, s_dsplit: descriptor of job s_job
+    __shared__ unsigned long long s_drb;                                           // s_drb, s_dnrec, s_dsplit: descriptor of job s_job
     __shared__ u32 s_dnrec, s_dsplit;
     __shared__ unsigned long long s_segsrc[PLAN_MAXW];                             // byte address of the job's segment s
     __shared__ u32 s_segpre[PLAN_MAXW + 1];                                        // records of the segments before s (thread 0 only)

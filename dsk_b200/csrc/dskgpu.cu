@@ -94,7 +94,8 @@ struct dskgpu_ctx {
     int bin_level = NBINS_LOG2; bool hist_fetched = false;
     // records in q order (owner-major partition order): what the counting kernels read on one GPU, what crosses NVLink as
     // W - 1 contiguous chunks on several (precs is then the receive buffer)
-    DevBuf lrecs, xpeers, bcur, ghist;
+    DevBuf lrecs, xpeers, bcur, ghist, mkeys;
+    void* qrecs = nullptr;                           // the q-ordered records after the scatter (lrecs, or recs after an even number of MSD passes)
     u64 xchg_bytes_out = 0;
     dskgpu_stats st;
     // timing
@@ -331,7 +332,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
                      &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->hll, &ctx->bin2part, &ctx->work_ctr,
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
                      &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr,
-                     &ctx->lrecs, &ctx->xpeers, &ctx->bcur, &ctx->ghist, &ctx->pl_ex, &ctx->pl_E, &ctx->pl_H, &ctx->pl_bsum, &ctx->pl_pk, &ctx->pl_pr, &ctx->pl_pl,
+                     &ctx->lrecs, &ctx->xpeers, &ctx->bcur, &ctx->ghist, &ctx->mkeys, &ctx->pl_ex, &ctx->pl_E, &ctx->pl_H, &ctx->pl_bsum, &ctx->pl_pk, &ctx->pl_pr, &ctx->pl_pl,
                      &ctx->pl_newid, &ctx->pl_nvals, &ctx->pl_hdr, &ctx->gk_q, &ctx->gr_q, &ctx->lcnt_q, &ctx->loff, &ctx->xX, &ctx->xtab, &ctx->xS, &ctx->hoff, &ctx->hrecs};
     for (DevBuf* b : all) b->release();
     for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
@@ -1048,22 +1049,65 @@ static int plan_device(dskgpu_ctx* ctx, const void* d_ghist)
     return 0;
 }
 
-// ---- stage 3: scatter my records into q order (lrecs): owner-major, so every owner's records are one contiguous chunk -------
+// ---- stage 3: scatter my records into q order: owner-major, so every owner's records are one contiguous chunk -------------
+// Up to ~1 M partitions: one pass, one L2 atomic + one 16/32-byte store per record (k_part_scatter).  Beyond (multi-G k-mer
+// jobs on several GPUs): MSD multi-split passes with block-level binning in shared memory (k_msd_pass), ping-ponging between
+// the input-order buffer and lrecs; ctx->qrecs says where the q-ordered records ended up.
+static u64 msd_min_parts(int KW)
+{
+    // measured (profiles/r02v-r02w): 16-byte records -- the passes win from ~10 K partitions on (C2: 0.72 against 0.80 ms;
+    // 563 K partitions: 28.8 against 38.3 ms; 3.3 M partitions on 8 GPUs: 96 ms for the single pass); 32-byte records move
+    // twice the bytes per pass and only win once the single pass has lost its L2 locality
+    const char* e = getenv("DSKGPU_MSD_MIN_PARTS");                       // (read per call: the tests force the multi-pass path on small jobs)
+    return e ? (u64)std::max(1LL, atoll(e)) : (KW == 1 ? (u64)8192 : (u64)1 << 18);
+}
+
 template <int KW>
 static int stage_scatter(dskgpu_ctx* ctx)
 {
     const PlanHdr& h = *ctx->h_hdr;
     int rc;
     if ((rc = ensure(ctx, ctx->lrecs, ctx->local_nrec * (u64)ctx->RW * 8 + 64))) return rc;
+    ctx->qrecs = ctx->lrecs.p;
     if (ctx->local_nrec == 0) return 0;
     const u64 nq = (u64)ctx->cfg.world_size * h.PW;
-    if ((rc = ensure(ctx, ctx->cursor, nq * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->cursor, (nq + 1) * 8))) return rc;
     SpanGuard g(ctx, SPAN_PART);
-    CK(cudaMemcpyAsync(ctx->cursor.p, ctx->loff.p, nq * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    const unsigned sb = (unsigned)std::min<u64>((ctx->local_nrec + SC_THREADS - 1) / SC_THREADS, (u64)ctx->num_sms * 32);
-    k_part_scatter<KW><<<sb, SC_THREADS, 0, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, ctx->local_nrec,
-                                                          (const u32*)ctx->bin2part.p, NBINS_FINE_LOG2 - ctx->bin_level, (u64*)ctx->lrecs.p,
-                                                          (unsigned long long*)ctx->cursor.p); LAUNCHED();
+    const int bin_shift = NBINS_FINE_LOG2 - ctx->bin_level;
+    if (nq < msd_min_parts(KW)) {
+        CK(cudaMemcpyAsync(ctx->cursor.p, ctx->loff.p, nq * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        const unsigned sb = (unsigned)std::min<u64>((ctx->local_nrec + SC_THREADS - 1) / SC_THREADS, (u64)ctx->num_sms * 32);
+        k_part_scatter<KW><<<sb, SC_THREADS, 0, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, ctx->local_nrec,
+                                                              (const u32*)ctx->bin2part.p, bin_shift, (u64*)ctx->lrecs.p,
+                                                              (unsigned long long*)ctx->cursor.p); LAUNCHED();
+        CK(cudaGetLastError());
+        return 0;
+    }
+    int bits = 1; while (((u64)1 << bits) < nq) bits++;
+    const int npass = (bits + 7) / 8, per = (bits + npass - 1) / npass;
+    if ((rc = ensure(ctx, ctx->mkeys, ctx->local_nrec * 4 + 64))) return rc;
+    const unsigned grid = (unsigned)std::min<u64>((ctx->local_nrec + MS_THREADS * (KW == 1 ? 8 : 4) - 1) / (MS_THREADS * (KW == 1 ? 8 : 4)), (u64)ctx->num_sms * 8);
+    u64* rb[2] = {(u64*)ctx->recs.p, (u64*)ctx->lrecs.p};
+    u32* kb[2] = {(u32*)ctx->meta.p, (u32*)ctx->mkeys.p};
+    for (int p = 0; p < npass; p++) {
+        const int shift = per * (npass - 1 - p), parent_shift = per * (npass - p);
+        const bool first = p == 0, last = p == npass - 1;
+        k_msd_cursor<<<(unsigned)std::min<u64>(((nq >> shift) + 256) / 256, (u64)ctx->num_sms * 8), 256, 0, ctx->stream>>>((const u64*)ctx->loff.p, nq, shift, (unsigned long long*)ctx->cursor.p); LAUNCHED();
+        const u64* src = rb[p & 1]; u64* dst = rb[(p + 1) & 1];
+        const u32* sk = kb[p & 1]; u32* dk = kb[(p + 1) & 1];
+        unsigned long long* cur = (unsigned long long*)ctx->cursor.p;
+        const u32* b2q = (const u32*)ctx->bin2part.p;
+#define MSD_LAUNCH(F, L) do { CK(cudaFuncSetAttribute(k_msd_pass<KW, F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms_smem_bytes<KW>())); \
+        k_msd_pass<KW, F, L><<<grid, MS_THREADS, ms_smem_bytes<KW>(), ctx->stream>>>(src, sk, ctx->local_nrec, b2q, bin_shift, shift, parent_shift, cur, dst, dk); } while (0)
+        if (first && last) MSD_LAUNCH(true, true);
+        else if (first) MSD_LAUNCH(true, false);
+        else if (last) MSD_LAUNCH(false, true);
+        else MSD_LAUNCH(false, false);
+#undef MSD_LAUNCH
+        LAUNCHED();
+    }
+    ctx->qrecs = rb[npass & 1];
+    ctx->st.scatter_passes = (u32)npass;
     CK(cudaGetLastError());
     return 0;
 }
@@ -1089,7 +1133,7 @@ static int stage_bases(dskgpu_ctx* ctx, const void* d_rcnt, const void* d_S)
     ctx->rcnt_dev = X;
     const u64* S = W > 1 ? (const u64*)d_S : ((const PlanHdr*)ctx->pl_hdr.p)->send_recs;
     k_xchg_bases<<<1, 32, 0, ctx->stream>>>((const PlanHdr*)ctx->pl_hdr.p, (const u64*)ctx->loff.p, X, S, (const u64*)ctx->xpeers.p,
-                                            (u64)(uintptr_t)ctx->lrecs.p, W, me, (u32)ctx->RW * 8, (XchgTab*)ctx->xtab.p); LAUNCHED();
+                                            (u64)(uintptr_t)ctx->qrecs, W, me, (u32)ctx->RW * 8, (XchgTab*)ctx->xtab.p); LAUNCHED();
     CK(cudaMemcpyAsync(ctx->h_xtab, ctx->xtab.p, sizeof(XchgTab), cudaMemcpyDeviceToHost, ctx->stream));   // read at the next sync (bad flags)
     CK(cudaGetLastError());
     return 0;
@@ -1260,7 +1304,7 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
             u64 hrec = 0;
             for (u64 r : ctx->heavy_recs) hrec += r;
             const u64* hp = nullptr;
-            if (W == 1) hp = (const u64*)ctx->lrecs.p + (nrec - hrec) * (u64)ctx->RW;
+            if (W == 1) hp = (const u64*)ctx->qrecs + (nrec - hrec) * (u64)ctx->RW;
             else if (hrec) {
                 const size_t nh = ctx->heavy_recs.size();
                 if ((rc = ensure(ctx, ctx->hrecs, hrec * (u64)ctx->RW * 8 + 64))) return rc;
@@ -1568,7 +1612,7 @@ int dskgpu_xchg_scatter(dskgpu_ctx* ctx, const void* d_recv_counts, const void* 
         const unsigned per_peer = (unsigned)std::max<u64>(1, std::min<u64>((remote / (W - 1) * (u64)(ctx->RW / 2) + 1023) / 1024, (u64)ctx->num_sms * 8 / (W - 1)));
         cudaEvent_t xa = get_event(ctx), xb = get_event(ctx);
         cudaEventRecord(xa, ctx->stream);
-        k_xchg_send<<<per_peer * (W - 1), 256, 0, ctx->stream>>>((const ulonglong2*)ctx->lrecs.p, (const XchgTab*)ctx->xtab.p, W, me, (u32)ctx->RW / 2); LAUNCHED();
+        k_xchg_send<<<per_peer * (W - 1), 256, 0, ctx->stream>>>((const ulonglong2*)ctx->qrecs, (const XchgTab*)ctx->xtab.p, W, me, (u32)ctx->RW / 2); LAUNCHED();
         cudaEventRecord(xb, ctx->stream);
         ctx->spans.push_back({xa, xb, SPAN_XCHG});
         CK(cudaGetLastError());

@@ -17,7 +17,16 @@ namespace dsk {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr u32 RS_FLAG_AGG = 1u << 30, RS_FLAG_INC = 2u << 30, RS_MASK = (1u << 30) - 1u;
-template <int KW> struct RsCfg { static constexpr int ITEMS = (KW == 1) ? 16 : 8; static constexpr int TILE = RS_THREADS * ITEMS; };
+#ifndef RS_ITEMS1
+#define RS_ITEMS1 12
+#endif
+#ifndef RS_ITEMS2
+#define RS_ITEMS2 6
+#endif
+#ifndef RS_MINB
+#define RS_MINB 4
+#endif
+template <int KW> struct RsCfg { static constexpr int ITEMS = (KW == 1) ? RS_ITEMS1 : RS_ITEMS2; static constexpr int TILE = RS_THREADS * ITEMS; };
 
 template <int KW> __device__ __forceinline__ u32 rs_digit(const u64* key, int pass)
 {
@@ -58,7 +67,7 @@ __global__ void __launch_bounds__(256) k_rs_scan(unsigned long long* hist)
 }
 
 template <int KW, bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS, 3) k_rs_onesweep(const u64* __restrict__ in_keys, u64* __restrict__ out_keys,
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) k_rs_onesweep(const u64* __restrict__ in_keys, u64* __restrict__ out_keys,
                                                             const u32* __restrict__ in_vals, u32* __restrict__ out_vals,
                                                             u64 n, int pass, const unsigned long long* __restrict__ gbase /*[256]*/,
                                                             u32* status /*[ntiles][256]*/, u32* tile_counter)

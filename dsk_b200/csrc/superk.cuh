@@ -295,6 +295,121 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(const u64* __restri
     }
 }
 
+// ---- K3 for jobs with millions of partitions: MSD multi-split with block-level binning in shared memory ------------------
+// The single-pass scatter above pays one L2 atomic and one isolated 16-byte store per record; beyond ~1 M partitions (multi-G
+// k-mer jobs, multi-GPU jobs) the open destinations no longer fit the L2 and it falls to 10 G records/s.  Here the q-ordered
+// layout is reached in ceil(bits / 8) passes, most significant digit first.  In a pass a CTA takes a tile of 2048 records,
+// bins them by `q >> shift` in shared memory (one shared atomic per record gives its rank inside the tile's bin), reserves
+// ONE run per (tile, bin) on the bin's global cursor, and stores the records of a bin next to each other (runs of ~8 records
+// = one 128-byte line when a pass splits 256 ways).  The destination of every bin is known beforehand -- the planner's
+// exclusive prefix `loff` -- so there is no counting pass.  Input of a later pass is grouped by the previous digit, so the
+// bins a tile can meet are the 256 children of at most two parents (512 counters); anything beyond that (tiny jobs) takes the
+// per-record cursor path.
+constexpr int MS_THREADS = 256;
+constexpr u32 MS_CAP = 512;
+
+// cursor[g] = first record slot of group g = q >> shift (groups 0 .. (nq - 1) >> shift)
+__global__ void k_msd_cursor(const u64* __restrict__ loff, u64 nq, int shift, unsigned long long* __restrict__ cursor)
+{
+    const u64 ng = ((nq - 1) >> shift) + 1;
+    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (u64)gridDim.x * blockDim.x) cursor[g] = loff[min(g << shift, nq)];
+}
+
+template <int KW> DSK_HD u32 ms_tile() { return KW == 1 ? 2048u : 1024u; }
+template <int KW> DSK_HD size_t ms_smem_bytes() { return (size_t)ms_tile<KW>() * (KW * 16 + 4) + MS_CAP * (4 + 4 + 8) + 64; }
+
+template <int KW, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(MS_THREADS) k_msd_pass(const u64* __restrict__ src, const u32* __restrict__ src_key /*FIRST: record meta*/, u64 nrec,
+                                                         const u32* __restrict__ bin2q, int bin_shift, int shift, int parent_shift,
+                                                         unsigned long long* __restrict__ cursor, u64* __restrict__ dst, u32* __restrict__ dst_key)
+{
+    constexpr int RPT = KW == 1 ? 8 : 4;
+    constexpr int VPR = KW;                                        // 16-byte vectors per record
+    constexpr u32 TILE = MS_THREADS * RPT;
+    extern __shared__ __align__(16) unsigned char ms_dyn[];
+    ulonglong2* s_rec = reinterpret_cast<ulonglong2*>(ms_dyn);                               // [TILE][VPR] records grouped by bin
+    unsigned long long* s_base = reinterpret_cast<unsigned long long*>(s_rec + (size_t)TILE * VPR);   // [MS_CAP] global slot of the bin's run
+    u32* s_key = reinterpret_cast<u32*>(s_base + MS_CAP);                                    // [TILE]
+    u32* s_cnt = s_key + TILE;                                                               // [MS_CAP]
+    u32* s_off = s_cnt + MS_CAP;                                                             // [MS_CAP] exclusive prefix of s_cnt
+    __shared__ u32 s_g0, s_wsum[MS_THREADS / 32];
+    const ulonglong2* in = reinterpret_cast<const ulonglong2*>(src);
+    ulonglong2* out = reinterpret_cast<ulonglong2*>(dst);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (u64 base = (u64)blockIdx.x * TILE; base < nrec; base += (u64)gridDim.x * TILE) {
+        for (u32 i = t; i < MS_CAP; i += MS_THREADS) s_cnt[i] = 0;
+        u32 q[RPT]; ulonglong2 ra[RPT], rb[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+            const u64 i = base + (u64)j * MS_THREADS + t;
+            q[j] = 0xFFFFFFFFu;
+            if (i < nrec) {
+                q[j] = FIRST ? __ldg(bin2q + ((src_key[i] & (NBINS_FINE - 1)) >> bin_shift)) : src_key[i];
+                ra[j] = in[VPR * i];
+                if constexpr (KW == 2) rb[j] = in[2 * i + 1];
+            }
+        }
+        // bins of this tile start at the first child of the first record's parent (the input is grouped by parent, parents in
+        // increasing order; the first pass has one parent: everything)
+        if (t == 0) s_g0 = FIRST ? 0u : ((q[0] >> parent_shift) << (parent_shift - shift));
+        __syncthreads();
+        const u32 g0 = s_g0;
+        u32 r[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+            r[j] = 0xFFFFFFFFu;
+            if (q[j] != 0xFFFFFFFFu) { const u32 idx = (q[j] >> shift) - g0; if (idx < MS_CAP) r[j] = atomicAdd(&s_cnt[idx], 1u); }
+        }
+        __syncthreads();
+        // exclusive prefix of the bin counts (two bins per thread) + one global reservation per non-empty bin
+        {
+            const u32 c0 = s_cnt[2 * t], c1 = s_cnt[2 * t + 1];
+            u32 inc = c0 + c1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+            if (lane == 31) s_wsum[warp] = inc;
+            if (c0) s_base[2 * t] = atomicAdd(&cursor[g0 + 2 * t], (unsigned long long)c0);
+            if (c1) s_base[2 * t + 1] = atomicAdd(&cursor[g0 + 2 * t + 1], (unsigned long long)c1);
+            __syncthreads();
+            u32 wpre = 0;
+#pragma unroll
+            for (int w = 0; w < MS_THREADS / 32; w++) wpre += w < warp ? s_wsum[w] : 0u;
+            const u32 ex = wpre + inc - (c0 + c1);
+            s_off[2 * t] = ex; s_off[2 * t + 1] = ex + c0;
+        }
+        __syncthreads();
+        u32 staged = 0;
+#pragma unroll
+        for (int w = 0; w < MS_THREADS / 32; w++) staged += s_wsum[w];
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+            if (q[j] == 0xFFFFFFFFu) continue;
+            const u32 g = q[j] >> shift;
+            if (r[j] != 0xFFFFFFFFu) {
+                const u32 p = s_off[g - g0] + r[j];
+                s_rec[(size_t)p * VPR] = ra[j];
+                if constexpr (KW == 2) s_rec[(size_t)p * VPR + 1] = rb[j];
+                s_key[p] = q[j];
+            } else {                                               // a bin outside the window of this tile (tiny jobs): per-record cursor
+                const u64 pos = atomicAdd(&cursor[g], 1ULL);
+                out[VPR * pos] = ra[j];
+                if constexpr (KW == 2) out[2 * pos + 1] = rb[j];
+                if constexpr (!LAST) dst_key[pos] = q[j];
+            }
+        }
+        __syncthreads();
+        // the staged records leave bin by bin: consecutive threads store consecutive 16/32-byte records of a run
+        for (u32 i = t; i < staged; i += MS_THREADS) {
+            const u32 qq = s_key[i], idx = (qq >> shift) - g0;
+            const u64 pos = s_base[idx] + (u64)(i - s_off[idx]);
+            out[VPR * pos] = s_rec[(size_t)i * VPR];
+            if constexpr (KW == 2) out[2 * pos + 1] = s_rec[(size_t)i * VPR + 1];
+            if constexpr (!LAST) dst_key[pos] = qq;
+        }
+        __syncthreads();                                           // staging buffer and counters are reused by the next tile
+    }
+}
+
 // packed fine bin histogram [NBINS_FINE] -> level histogram [2][NBINS_FINE >> shift] (records per bin, then k-mers per bin)
 __global__ void k_fold_bins(const unsigned long long* __restrict__ fine, int shift, unsigned long long* __restrict__ out)
 {

@@ -83,14 +83,25 @@ def distributed_finish(eng, dist, device):
         e.record(cur)
         evs.append((name, e))
 
-    g4 = torch.from_numpy(eng.xchg_prepare().astype(np.int64)).to(device)     # k-mers, records, density sample (k-mers, distinct)
+    # A rank whose input was rejected (or that failed in any other way) must not leave the others waiting in a collective:
+    # its failure travels as a fifth "total" of the first all-reduce, and every rank raises.
+    failure = None
+    try:
+        l4 = eng.xchg_prepare()                                                # k-mers, records, density sample (k-mers, distinct)
+        sk0 = eng.xchg_sketch()                                                # distinct k-mers of the UNION of the ranks' samples
+    except Exception as ex:                                                    # noqa: BLE001 -- re-raised below, on every rank
+        failure, l4, sk0 = ex, np.zeros(4, np.uint64), np.zeros(4096, np.uint32)
+    g4 = torch.from_numpy(np.concatenate([l4.astype(np.int64), [1 if failure else 0]])).to(device)
     mark("prepare (push kernels done)")
     ev("start")
-    sk = torch.from_numpy(eng.xchg_sketch().astype(np.int32)).to(device)       # distinct k-mers of the UNION of the ranks' samples
+    sk = torch.from_numpy(sk0.astype(np.int32)).to(device)
     dist.all_reduce(g4)                                                       # every rank picks the same bin level / partition size
     dist.all_reduce(sk, op=dist.ReduceOp.MAX)
+    g4h = g4.cpu().numpy()
+    if g4h[4]:
+        raise failure if failure is not None else RuntimeError("distributed_finish: %d other rank(s) failed before the exchange" % int(g4h[4]))
     eng.xchg_set_sketch(sk.cpu().numpy().astype(np.uint32))
-    level = eng.xchg_set_global(g4.cpu().numpy().astype(np.uint64))
+    level = eng.xchg_set_global(g4h[:4].astype(np.uint64))
     mark("allreduce totals")
     ev("totals_allreduce")
     G = torch.empty(2 << level, dtype=torch.int64, device=device)             # (records, k-mers) per minimizer bin
@@ -99,7 +110,14 @@ def distributed_finish(eng, dist, device):
     dist.all_reduce(G)                                                         # every rank plans the same partitions
     ev("hist_allreduce")
     to_lib()
-    P, PW, need = eng.xchg_plan(G.data_ptr())                                  # device planner; the host reads one header
+    try:
+        P, PW, need = eng.xchg_plan(G.data_ptr())                              # device planner; the host reads one header
+    except Exception as ex:                                                    # noqa: BLE001
+        failure, P, PW, need = ex, 0, 0, np.zeros(W, np.uint64)
+    okf = torch.tensor([1 if failure else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(okf)                                                       # (out of memory while planning, ...: all ranks leave together)
+    if int(okf.cpu()[0]):
+        raise failure if failure is not None else RuntimeError("distributed_finish: another rank failed while planning")
     mark("histogram allreduce + device plan")
     ev("plan")
     send = torch.empty(W * PW + W, dtype=torch.int64, device=device)

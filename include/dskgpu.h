@@ -125,7 +125,9 @@ typedef struct dskgpu_stats {
     float    ms_plan;               /* density sample + device planner (scans, renumbering, layout tables) */
     float    ms_push_wall;          /* first to last kernel of the push phase on the stream (parse + super-k-mers + any gaps between chunks) */
     uint32_t hist_rebuilt;          /* 1: the packed minimizer-bin histogram could have wrapped and was rebuilt exactly from the records */
+    uint32_t scatter_passes;        /* 0: single-pass partition scatter; n: MSD multi-split passes (jobs with millions of partitions) */
     float    ms_count_heavy;        /* part of ms_count spent on the heavy partitions (gather + global table / sort / bucket paths) */
+    uint32_t reserved1;
 } dskgpu_stats;
 
 /* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */

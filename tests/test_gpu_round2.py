@@ -189,6 +189,29 @@ def test_packed_bin_histogram_rebuilt_when_it_could_wrap(k, monkeypatch):
     assert all((a == b).all() if hasattr(a, "all") else a == b for a, b in zip(plans[0], plans[1]))
 
 
+@pytest.mark.parametrize("k,W,min_parts", [(31, 1, 1), (63, 1, 1), (31, 3, 1), (31, 1, 300), (31, 2, 5000)])
+def test_msd_multi_split_scatter(k, W, min_parts, monkeypatch):
+    """the partition scatter of jobs with millions of partitions (MSD multi-split passes with block-level binning in shared
+    memory), forced on a small job: 1, 2 or 3 passes depending on the partition count, same results"""
+    monkeypatch.setenv("DSKGPU_MSD_MIN_PARTS", str(min_parts))
+    buf, n, _ = reads_fasta(G=500_000, coverage=30, L=150, err=0.01, seed=97)
+    data = bytearray(buf[:n].tobytes())
+    data[500:500] = b">low\n" + b"AC" * 30000 + b"\n"
+    slots = {1: 0, 300: 1024, 5000: 64}[min_parts]                      # 0: ~1 K partitions (2 passes); 1024: ~15 K (2 passes); 64: ~250 K (3 passes)
+    if W == 1:
+        ref = oracle.count_files([bytes(data)], k, abundance_min=2)
+        with GpuCounter(kmer_size=k, abundance_min=2, smem_table_slots=slots) as eng:
+            eng.push_bytes(bytes(data))
+            eng.finish()
+            st = eng.stats()
+            assert st["scatter_passes"] >= (1 if st["nb_partitions"] <= 256 else 2 if st["nb_partitions"] <= 65536 else 3)
+            kk, cc = eng.solid()
+            assert st["kmers_nb_distinct"] == ref.nb_distinct
+            assert_equals_oracle(kk, cc, eng.histogram()[0], ref)
+    else:
+        run_multi([0] * W, k, bytes(data), smem_table_slots=slots)
+
+
 # ---------------------------------------------------------------- several ranks in one process (dskgpu_multi_finish)
 def run_multi(devices, k, data, **kw):
     W = len(devices)

@@ -89,6 +89,33 @@ def main():
                     W, k, mode, G, rep, "OK" if good else "MISMATCH", valid, distinct, len(cnts), allr[0][5], [len(a[1]) for a in allr]), flush=True)
         faulthandler.cancel_dump_traceback_later()
         eng.close()
+    # a rank whose input the device scanner rejects must make EVERY rank raise (nobody is left waiting in a collective),
+    # and the job after it must run normally
+    buf, n, _ = reads_fasta(G=200_000, coverage=10, L=150, err=0.01, seed=99)
+    data = buf[:n].tobytes()
+    piece = split_records(data, W)[rank]
+    eng = GpuCounter(kmer_size=31, abundance_min=2, device=local, rank=rank, world_size=W, stream=shared.cuda_stream)
+    faulthandler.dump_traceback_later(120, exit=True)
+    eng.push_bytes(b"@r1\nACGTACGTACGTACGTACGTACGTACGTACGTACGT\nACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\nIIIIIIII\n" if rank == W - 1 else piece)
+    raised = False
+    try:
+        distributed_finish(eng, dist, dev)
+    except Exception as ex:                          # noqa: BLE001
+        raised = True
+        progress("failure case: raised %s" % str(ex)[:80])
+    eng.reset()
+    eng.push_bytes(piece)
+    distributed_finish(eng, dist, dev)
+    mass = int((eng.histogram()[0].astype(np.uint64) * np.arange(10001, dtype=np.uint64)).sum())
+    t = torch.tensor([1 if raised else 0, mass, int(eng.stats()["kmers_nb_valid"])], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    faulthandler.cancel_dump_traceback_later()
+    eng.close()
+    if rank == 0:
+        good = int(t[0]) == W and int(t[1]) == int(t[2])
+        ok = ok and good
+        print("mgpu_check W=%d failure propagation: %s  (%d of %d ranks raised; the next job counted %d of %d k-mers)" % (
+            W, "OK" if good else "MISMATCH", int(t[0]), W, int(t[1]), int(t[2])), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -7,7 +7,7 @@ for step in "$@"; do
   case "$step" in
     pynew)    timeout 1500 python -m pytest tests/test_gpu_round2.py tests/test_cli_dropin.py -x -q > "$OUT/pytest_new.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_new.log"; tail -15 "$OUT/pytest_new.log" ;;
     pycount)  timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "reference_runs or tiny_smem or synthetic or histo2d or heavy or multi_rank or forced or regrown or pass_loop" > "$OUT/pytest_count.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_count.log"; tail -4 "$OUT/pytest_count.log" ;;
-    pyfast)   timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "device_planner or packed_bin or multi_rank or multi_finish or synthetic_vs_oracle or tiny_smem or heavy or forced or regrown or pass_loop or auto_cutoff" > "$OUT/pytest_fast.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_fast.log"; tail -25 "$OUT/pytest_fast.log" ;;
+    pyfast)   timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "device_planner or packed_bin or msd_multi or multi_rank or multi_finish or synthetic_vs_oracle or tiny_smem or heavy or forced or regrown or pass_loop or auto_cutoff" > "$OUT/pytest_fast.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_fast.log"; tail -25 "$OUT/pytest_fast.log" ;;
     pytest)   timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_gpu.log"; tail -5 "$OUT/pytest_gpu.log" ;;
     bench)    timeout 600 python bench.py > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json"; tail -3 "$OUT/bench_n1.err" ;;
     benchq)   timeout 600 python bench.py --no-cpu-baseline > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json"; tail -3 "$OUT/bench_n1.err" ;;
@@ -24,7 +24,13 @@ for step in "$@"; do
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/launches_bench.log" 2>&1; echo "launches exit $?" ;;
     ncu)      timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNELS:-k_}" -s "${NCU_SKIP:-60}" -c "${NCU_COUNT:-24}" -f -o "$OUT/ncu_full" python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/ncu_bench.log" 2>&1; echo "ncu exit $?"; ls -la "$OUT" ;;
     big)      timeout 900 python bench.py --genome 375000000 --coverage 30 --device-synth --minimizer-size ${BIG_M:-14} --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > "$OUT/bench_big.json" 2> "$OUT/bench_big.err"; cut -c1-2500 "$OUT/bench_big.json"; tail -3 "$OUT/bench_big.err" ;;
+    bigmsd)   DSKGPU_MSD_MIN_PARTS=1 timeout 900 python bench.py --genome 375000000 --coverage 30 --device-synth --minimizer-size ${BIG_M:-14} --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > "$OUT/bench_bigmsd.json" 2> "$OUT/bench_bigmsd.err"; cut -c1-2500 "$OUT/bench_bigmsd.json"; tail -3 "$OUT/bench_bigmsd.err" ;;
     biglaunches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$OUT/launches_big.csv" python bench.py --genome 375000000 --coverage 30 --device-synth --minimizer-size ${BIG_M:-14} --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/launches_big.log" 2>&1; echo "biglaunches exit $?" ;;
+    ncuk)     # one full capture per named kernel (small report): NCU_LIST="k_scan_emit k_superkmers ..."
+              for kn in ${NCU_LIST:-k_scan_tables k_scan_emit k_superkmers k_rs_onesweep k_msd_pass k_count_smem}; do
+                case "$kn" in k_count_smem) sk=1 ;; k_msd_pass) sk=2 ;; k_rs_onesweep) sk=12 ;; *) sk=6 ;; esac   # a launch of the second (timed) step
+                timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$kn" -s "$sk" -c 1 -f -o "$OUT/ncu_$kn" python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/ncu_$kn.log" 2>&1; echo "ncu $kn exit $?"
+              done; ls -la "$OUT" ;;
     cli)      timeout 900 bash tools/run_cli_check.sh "$OUT" ;;
     *)        echo "unknown step $step" ;;
   esac
