@@ -39,7 +39,7 @@ class Stats(C.Structure):
         ("dominant_kernel_launches", C.c_uint32), ("nb_parts_smem", C.c_uint32), ("nb_smem_splits", C.c_uint32),
         ("smem_table_slots", C.c_uint32), ("density_ppm", C.c_uint32), ("log2_bins", C.c_uint32), ("nb_groups_bucket", C.c_uint32), ("nb_hash_regroups", C.c_uint32),
         ("exchange_bytes_out", C.c_uint64), ("ms_exchange", C.c_float), ("nb_solid_regrows", C.c_uint32), ("kmers_in_pass", C.c_uint64),
-        ("ms_plan", C.c_float), ("ms_push_wall", C.c_float), ("hist_rebuilt", C.c_uint32), ("scatter_passes", C.c_uint32), ("ms_count_heavy", C.c_float), ("reserved1", C.c_uint32),
+        ("ms_plan", C.c_float), ("ms_push_wall", C.c_float), ("hist_rebuilt", C.c_uint32), ("scatter_passes", C.c_uint32), ("ms_count_heavy", C.c_float), ("sort_fallbacks", C.c_uint32),
     ]
 
     def as_dict(self):

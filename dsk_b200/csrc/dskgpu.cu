@@ -71,6 +71,7 @@ struct dskgpu_ctx {
     size_t push_chunk = (size_t)64 << 20;
     // results
     u64 n_solid = 0; int solid_buf = 0; bool results_on_host = false; u64 solid_cap = 0;
+    int sort_src = 0; bool sort_fixup = false;       // ordering of the solid set: input buffer of the fix-up pass, whether it ran
     u32 nparts = 0;
     u32 smem_cap = 0; int num_sms = 148;
     // device-side plan (plan.cuh): scratch of the planner, q-ordered per-partition tables, exchange table
@@ -580,9 +581,9 @@ int dskgpu_push_reads(dskgpu_ctx* ctx, int bank_id, const char* bases, const uin
 // finish path
 // ---------------------------------------------------------------------------------------------------------------
 template <int KW, bool HAS_VAL>
-static int radix_sort(dskgpu_ctx* ctx, u64* keys[2], u32* vals[2], u64 n, int npass, int* result_buf)
+static int radix_sort(dskgpu_ctx* ctx, u64* keys[2], u32* vals[2], u64 n, int npass, int* result_buf, int first_pass = 0, int start_buf = 0)
 {
-    *result_buf = 0;
+    *result_buf = start_buf;
     if (n == 0) return 0;
     if (n >= ((u64)1 << 30)) FAIL(DSKGPU_ERR_OVERFLOW, "radix sort of %llu keys exceeds the 2^30 limit of the tile status words", (unsigned long long)n);
     constexpr int TILE = RsCfg<KW>::TILE;
@@ -594,11 +595,11 @@ static int radix_sort(dskgpu_ctx* ctx, u64* keys[2], u32* vals[2], u64 n, int np
     CK(cudaMemsetAsync(ctx->rs_hist.p, 0, (size_t)npass * 256 * 8, ctx->stream));
     CK(cudaMemsetAsync(ctx->rs_tilectr.p, 0, 64 * 4, ctx->stream));
     const unsigned hb = (unsigned)std::min<u64>((n + RS_THREADS * 8 - 1) / (RS_THREADS * 8), 148 * 8);
-    k_rs_hist<KW><<<hb, RS_THREADS, npass * 256 * 4, ctx->stream>>>(keys[0], n, npass, (unsigned long long*)ctx->rs_hist.p); LAUNCHED();
+    k_rs_hist<KW><<<hb, RS_THREADS, npass * 256 * 4, ctx->stream>>>(keys[start_buf], n, npass, (unsigned long long*)ctx->rs_hist.p, first_pass); LAUNCHED();
     k_rs_scan<<<npass, 256, 0, ctx->stream>>>((unsigned long long*)ctx->rs_hist.p); LAUNCHED();
     const int smem = TILE * KW * 8 + (HAS_VAL ? TILE * 4 : 16);
-    int cur = 0;
-    for (int p = 0; p < npass; p++) {
+    int cur = start_buf;
+    for (int p = first_pass; p < npass; p++) {
         CK(cudaMemsetAsync(ctx->rs_status.p, 0, ntiles * 256 * 4, ctx->stream));
         cudaEvent_t a = get_event(ctx), b = get_event(ctx);
         cudaEventRecord(a, ctx->stream);
@@ -611,6 +612,35 @@ static int radix_sort(dskgpu_ctx* ctx, u64* keys[2], u32* vals[2], u64 n, int np
         cur ^= 1;
     }
     *result_buf = cur;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ascending order of the solid set (as the reference emits inside a partition).  Top ceil(log2 n) bits by one-sweep LSD
+// passes, the rest by the neighbourhood fix-up (radix.cuh); `full` (or keys too short to gain anything) = plain LSD sort.
+// ctx->sort_src = the buffer the fix-up read (intact): where a flagged fix-up restarts from.
+template <int KW>
+static int sort_solid(dskgpu_ctx* ctx, bool full, int start_buf)
+{
+    u64* kk[2] = {(u64*)ctx->skeys[0].p, (u64*)ctx->skeys[1].p};
+    u32* vv[2] = {(u32*)ctx->svals[0].p, (u32*)ctx->svals[1].p};
+    const u64 n = ctx->n_solid;
+    const int npass_full = (2 * ctx->k + 7) / 8;
+    int lg = 1; while (((u64)1 << lg) < n) lg++;
+    const int msd = (lg + 7) / 8;
+    ctx->sort_fixup = false;
+    if (full || getenv("DSKGPU_SORT_FULL") || msd + 1 >= npass_full)
+        return radix_sort<KW, true>(ctx, kk, vv, n, npass_full, &ctx->solid_buf, 0, start_buf);
+    int r = start_buf, rc;
+    if ((rc = radix_sort<KW, true>(ctx, kk, vv, n, npass_full, &r, npass_full - msd, start_buf))) return rc;
+    Counters* ctr = (Counters*)ctx->ctr.p;
+    cudaEvent_t a = get_event(ctx), b = get_event(ctx);
+    cudaEventRecord(a, ctx->stream);
+    k_rs_fix<KW><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(kk[r], vv[r], kk[r ^ 1], vv[r ^ 1], n, 8 * (npass_full - msd), &ctr->sort_fallback); LAUNCHED();
+    cudaEventRecord(b, ctx->stream);
+    ctx->spans.push_back({a, b, SPAN_SORTPASS});
+    ctx->sort_src = r; ctx->solid_buf = r ^ 1; ctx->sort_fixup = true;
+    CK(cudaMemcpyAsync(ctx->h_nrec_probe + 7, &ctr->sort_fallback, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaGetLastError());
     return 0;
 }
@@ -1342,31 +1372,40 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
     ctx->st.kmers_nb_distinct = ctx->h_ctr->distinct_n; ctx->st.kmers_nb_solid = ctx->n_solid;
     ctx->st.nb_smem_splits = ctx->h_ctr->smem_splits;
 
-    // order the solid set (ascending k-mer value, as the reference emits within a partition)
+    // order the solid set (ascending k-mer value, as the reference emits within a partition), results to the host
     ctx->solid_buf = 0;
-    if (ctx->n_solid) {
-        SpanGuard g(ctx, SPAN_SORT);
-        u64* kk[2] = {(u64*)ctx->skeys[0].p, (u64*)ctx->skeys[1].p};
-        u32* vv[2] = {(u32*)ctx->svals[0].p, (u32*)ctx->svals[1].p};
-        if ((rc = radix_sort<KW, true>(ctx, kk, vv, ctx->n_solid, (2 * ctx->k + 7) / 8, &ctx->solid_buf))) return rc;
-    }
-    // results to the host
-    CK(cudaMemcpyAsync(ctx->h_hist, ctx->hist.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_hist + DSKGPU_HISTO_LEN, ctx->hist2d.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2,
-                       cudaMemcpyDeviceToHost, ctx->stream));
-    if (!ctx->cfg.keep_results_on_device && ctx->n_solid) {
-        if (ctx->n_solid > ctx->h_solid_cap) {
-            if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
-            if (ctx->h_svals) cudaFreeHost(ctx->h_svals);
-            ctx->h_solid_cap = ctx->n_solid + ctx->n_solid / 4;
-            CK(cudaMallocHost((void**)&ctx->h_skeys, ctx->h_solid_cap * KW * 8));
-            CK(cudaMallocHost((void**)&ctx->h_svals, ctx->h_solid_cap * 4));
+    auto order_and_copy = [&](bool full, int start_buf) -> int {
+        if (ctx->n_solid) {
+            SpanGuard g(ctx, SPAN_SORT);
+            int rc2 = sort_solid<KW>(ctx, full, start_buf); if (rc2) return rc2;
         }
-        CK(cudaMemcpyAsync(ctx->h_skeys, ctx->skeys[ctx->solid_buf].p, ctx->n_solid * KW * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->h_svals, ctx->svals[ctx->solid_buf].p, ctx->n_solid * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->results_on_host = true;
+        CK(cudaMemcpyAsync(ctx->h_hist, ctx->hist.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_hist + DSKGPU_HISTO_LEN, ctx->hist2d.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        if (!ctx->cfg.keep_results_on_device && ctx->n_solid) {
+            if (ctx->n_solid > ctx->h_solid_cap) {
+                if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
+                if (ctx->h_svals) cudaFreeHost(ctx->h_svals);
+                ctx->h_skeys = nullptr; ctx->h_svals = nullptr;
+                ctx->h_solid_cap = ctx->n_solid + ctx->n_solid / 4;
+                CK(cudaMallocHost((void**)&ctx->h_skeys, ctx->h_solid_cap * KW * 8));
+                CK(cudaMallocHost((void**)&ctx->h_svals, ctx->h_solid_cap * 4));
+            }
+            CK(cudaMemcpyAsync(ctx->h_skeys, ctx->skeys[ctx->solid_buf].p, ctx->n_solid * KW * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_svals, ctx->svals[ctx->solid_buf].p, ctx->n_solid * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->results_on_host = true;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    *(volatile unsigned int*)(ctx->h_nrec_probe + 7) = 0;
+    if ((rc = order_and_copy(false, 0))) return rc;
+    if (ctx->sort_fixup && *(volatile unsigned int*)(ctx->h_nrec_probe + 7)) {
+        // a prefix group too long for the neighbourhood fix-up (low-complexity set): plain full-width sort from its intact input
+        CK(cudaMemsetAsync(&ctr->sort_fallback, 0, sizeof(unsigned int), ctx->stream));
+        ctx->st.sort_fallbacks++;
+        if ((rc = order_and_copy(true, ctx->sort_src))) return rc;
     }
-    CK(cudaStreamSynchronize(ctx->stream));
     ctx->st.ms_parse = span_ms(ctx, SPAN_PARSE); ctx->st.ms_superk = span_ms(ctx, SPAN_SUPERK);
     ctx->st.ms_partition = span_ms(ctx, SPAN_PART); ctx->st.ms_count = span_ms(ctx, SPAN_COUNT);
     ctx->st.ms_sort = span_ms(ctx, SPAN_SORT);
@@ -1389,6 +1428,7 @@ static int reset_count_state(dskgpu_ctx* ctx)
     CK(cudaMemsetAsync(&ctr->distinct_n, 0, sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(&ctr->smem_splits, 0, sizeof(unsigned int), ctx->stream));
     CK(cudaMemsetAsync(&ctr->overflow, 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(&ctr->sort_fallback, 0, sizeof(unsigned int), ctx->stream));
     CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
     CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
     if (ctx->bank_hist.p) CK(cudaMemsetAsync(ctx->bank_hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * (size_t)ctx->NB, ctx->stream));

@@ -36,9 +36,9 @@ template <int KW> __device__ __forceinline__ u32 rs_digit(const u64* key, int pa
     return (u32)(w >> ((pass & 7) * 8)) & 0xFFu;
 }
 
-// histogram of every digit of every key in one read: hist[pass][256]
+// histogram of the digits [first, npass) of every key in one read: hist[pass][256]
 template <int KW>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ keys, u64 n, int npass, unsigned long long* __restrict__ hist)
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ keys, u64 n, int npass, unsigned long long* __restrict__ hist, int first = 0)
 {
     extern __shared__ u32 s_h[];                                  // [npass][256]
     for (int i = threadIdx.x; i < npass * 256; i += RS_THREADS) s_h[i] = 0;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64* __restrict__ 
         u64 key[KW];
 #pragma unroll
         for (int q = 0; q < KW; q++) key[q] = keys[i * KW + q];
-        for (int p = 0; p < npass; p++) atomicAdd(&s_h[p * 256 + rs_digit<KW>(key, p)], 1u);
+        for (int p = first; p < npass; p++) atomicAdd(&s_h[p * 256 + rs_digit<KW>(key, p)], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < npass * 256; i += RS_THREADS) { u32 v = s_h[i]; if (v) atomicAdd(&hist[i], (unsigned long long)v); }
@@ -167,6 +167,57 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) k_rs_onesweep(const u64* 
         for (int q = 0; q < KW; q++) out_keys[g * KW + q] = kk[q];
         if (HAS_VAL) out_vals[g] = s_vals[i];
     }
+}
+
+// ---- ordering of the solid set: top digits by LSD passes, the rest by a neighbourhood fix-up ------------------------------
+// The solid k-mers of a read set are n distinct, nearly uniform keys: once they are ordered by their top ceil(log2 n) bits
+// (ceil(log2 n / 8) one-sweep passes instead of 2k/8), the keys that share a prefix are neighbours, groups of one or two
+// (Poisson, mean < 1).  Every thread ranks its key inside its group by scanning the neighbours with the same prefix and
+// stores it at its final position: one more pass instead of four or five (k = 31) or twelve (k = 63).  Keys that do not
+// behave (a group longer than RS_FIX_LIMIT: low-complexity sets, tiny k) raise `*flag`; the caller then runs the plain
+// full-width LSD sort from the same input, which is still intact.
+constexpr u32 RS_FIX_LIMIT = 48;
+template <int KW> __device__ __forceinline__ bool rs_same_prefix(const u64* a, const u64* b, int shift)
+{
+    if constexpr (KW == 1) return ((a[0] ^ b[0]) >> shift) == 0;
+    else return shift >= 64 ? (((a[1] ^ b[1]) >> (shift - 64)) == 0) : (a[1] == b[1] && ((a[0] ^ b[0]) >> shift) == 0);
+}
+template <int KW> __device__ __forceinline__ bool rs_key_less(const u64* a, const u64* b)
+{
+    if constexpr (KW == 1) return a[0] < b[0];
+    else return a[1] < b[1] || (a[1] == b[1] && a[0] < b[0]);
+}
+template <int KW>
+__global__ void __launch_bounds__(256) k_rs_fix(const u64* __restrict__ in_keys, const u32* __restrict__ in_vals, u64* __restrict__ out_keys,
+                                                u32* __restrict__ out_vals, u64 n, int shift, unsigned int* flag)
+{
+    const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    u64 my[KW], o[KW];
+#pragma unroll
+    for (int q = 0; q < KW; q++) my[q] = in_keys[i * KW + q];
+    u32 smaller = 0, left = 0, right = 0;
+    for (u64 j = i; j > 0;) {
+        j--;
+#pragma unroll
+        for (int q = 0; q < KW; q++) o[q] = in_keys[j * KW + q];
+        if (!rs_same_prefix<KW>(my, o, shift)) break;
+        left++;
+        smaller += rs_key_less<KW>(my, o) ? 0u : 1u;              // (an equal key on the left stays on the left)
+        if (left > RS_FIX_LIMIT) { atomicExch(flag, 1u); return; }
+    }
+    for (u64 j = i + 1; j < n; j++) {
+#pragma unroll
+        for (int q = 0; q < KW; q++) o[q] = in_keys[j * KW + q];
+        if (!rs_same_prefix<KW>(my, o, shift)) break;
+        right++;
+        smaller += rs_key_less<KW>(o, my) ? 1u : 0u;
+        if (right > RS_FIX_LIMIT) { atomicExch(flag, 1u); return; }
+    }
+    const u64 pos = i - left + smaller;
+#pragma unroll
+    for (int q = 0; q < KW; q++) out_keys[pos * KW + q] = my[q];
+    out_vals[pos] = in_vals[i];
 }
 
 #endif  // __CUDACC__

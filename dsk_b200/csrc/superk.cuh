@@ -43,7 +43,7 @@ struct Counters {
     unsigned long long kmers_pass;    // valid k-mers whose minimizer belongs to the current pass (== kmers_in_recs)
     unsigned long long sample_solid;  // density sample: distinct k-mers whose summed count reaches the smallest abundance-min
     unsigned int hist_suspect;        // a fine bin holds so many k-mers that its packed record count may have wrapped (k_check_bins)
-    unsigned int pad1;
+    unsigned int sort_fallback;       // ordering of the solid set: a prefix group too long for the neighbourhood fix-up (k_rs_fix)
 };
 
 // fine-bin histogram entry: records in the top 28 bits, k-mers in the low 36 -- ONE 64-bit RED per record instead of two, and

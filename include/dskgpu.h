@@ -127,7 +127,7 @@ typedef struct dskgpu_stats {
     uint32_t hist_rebuilt;          /* 1: the packed minimizer-bin histogram could have wrapped and was rebuilt exactly from the records */
     uint32_t scatter_passes;        /* 0: single-pass partition scatter; n: MSD multi-split passes (jobs with millions of partitions) */
     float    ms_count_heavy;        /* part of ms_count spent on the heavy partitions (gather + global table / sort / bucket paths) */
-    uint32_t reserved1;
+    uint32_t sort_fallbacks;        /* ordering of the solid set: neighbourhood fix-up gave up (long groups of equal prefixes), full-width sort ran */
 } dskgpu_stats;
 
 /* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */

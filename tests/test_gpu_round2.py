@@ -212,6 +212,46 @@ def test_msd_multi_split_scatter(k, W, min_parts, monkeypatch):
         run_multi([0] * W, k, bytes(data), smem_table_slots=slots)
 
 
+@pytest.mark.parametrize("k", [31, 63])
+def test_solid_set_ordering_fixup_and_fallback(k, monkeypatch):
+    """ordering of the solid set: top ceil(log2 n) bits by one-sweep passes + neighbourhood fix-up; a set with long groups of
+    equal prefixes (here 300 solid k-mers that start with the same 10 bases) makes the fix-up give up and the full-width sort
+    run; both must give the ascending order of the plain sort"""
+    rng = np.random.default_rng(5 + k)
+    buf, n, _ = reads_fasta(G=150_000, coverage=20, L=150, err=0.01, seed=11)
+    recs = [buf[:n].tobytes()]
+    for i in range(300):
+        tail = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), k - 10).tobytes())
+        recs.append((b">p%d\n" % i + b"A" * 10 + tail + b"\n") * 3)
+    data = b"".join(recs)
+    ref = oracle.count_files([data], k, abundance_min=2)
+    outs = []
+    for full in (False, True):
+        if full:
+            monkeypatch.setenv("DSKGPU_SORT_FULL", "1")
+        with GpuCounter(kmer_size=k, abundance_min=2) as eng:
+            eng.push_bytes(data)
+            eng.finish()
+            kk, cc = eng.solid()
+            st = eng.stats()
+            assert st["sort_fallbacks"] == (0 if full else 1)
+            assert_equals_oracle(kk, cc, eng.histogram()[0], ref)
+            key = kk[:, 0].astype(object) if kk.shape[1] == 1 else (kk[:, 1].astype(object) << 64) | kk[:, 0].astype(object)
+            assert all(key[i] < key[i + 1] for i in range(len(key) - 1))            # ascending as delivered, not only as a set
+            outs.append((kk.copy(), cc.copy()))
+    assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()
+    monkeypatch.delenv("DSKGPU_SORT_FULL")
+    # the plain case: no fallback, ascending
+    buf, n, _ = reads_fasta(G=400_000, coverage=30, L=150, err=0.01, seed=12)
+    with GpuCounter(kmer_size=k, abundance_min=2) as eng:
+        eng.push_bytes(buf[:n].tobytes())
+        eng.finish()
+        kk, _ = eng.solid()
+        assert eng.stats()["sort_fallbacks"] == 0
+        key = kk[:, 0].astype(object) if kk.shape[1] == 1 else (kk[:, 1].astype(object) << 64) | kk[:, 0].astype(object)
+        assert all(key[i] < key[i + 1] for i in range(len(key) - 1))
+
+
 # ---------------------------------------------------------------- several ranks in one process (dskgpu_multi_finish)
 def run_multi(devices, k, data, **kw):
     W = len(devices)
