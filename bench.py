@@ -646,21 +646,25 @@ def main():
         dom_avg_s = dom_ms / 1e3 / max(1, dom_n)
         nk = ncu_kernels(args)
         kd = (nk or {}).get("kernels", {}).get(dom_kernel)
-        # roofline of the dominant kernel.  Its HBM traffic is what it really moves (records in, solid pairs out: the table
-        # never leaves shared memory), measured by ncu at HEAD; `achieved` divides that by the kernel's live CUDA-event time.
-        # The kernel is bound by SM instruction issue, not by HBM: `binding` carries that counter from the same capture.
+        # roofline of the dominant kernel, honestly: `traffic` = the DRAM bytes it really moves per launch (dram__bytes_read +
+        # write, ncu --set full at HEAD, profiles/ncu_kernels.json), `achieved` = that / its live CUDA-event duration, `frac` =
+        # achieved / measured HBM peak.  The kernel is NOT HBM-bound (its table never leaves shared memory): `binding` carries the
+        # counters that do bind it, from the same capture.  The SURVEY 8(d) figure (k-mers/s x A(k) / peak, a NORMALISED
+        # throughput) stays in normalised_throughput_frac and pipeline_roofline.
         traffic = (kd["dram_bytes_per_launch"] if kd else None)
         achieved = (traffic / dom_avg_s / 1e9) if (traffic and dom_avg_s > 0) else None
         alg_per_launch = (ab["S2_expand"] + ab["S3_sort"] + ab["S4_reduce"]) * kmers * args.steps / max(1, dom_n)
         roof = {"bound": "hbm", "kernel": dom_kernel, "launches": int(dom_n), "avg_launch_ms": 1e3 * dom_avg_s,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src,
+                "note": "frac is the kernel's real share of HBM bandwidth: small BY DESIGN (the count table lives in shared memory; the LSD-sort dataflow "
+                        "A(k) assumes would move algorithmic_bytes_per_launch); what binds the kernel is in `binding`",
                 "algorithmic_bytes_per_launch": alg_per_launch,
-                "algorithmic_note": "what the reference dataflow (expand + LSD radix sort + reduce, SURVEY 8(d) S2+S3+S4) would move for the k-mers of one launch; "
-                                    "this kernel counts in a shared-memory table instead, so traffic << algorithmic bytes and frac is small BY DESIGN",
                 "normalised_throughput_frac": (alg_per_launch / dom_avg_s / 1e9 / peak) if dom_avg_s > 0 else None,
-                "binding": ({"resource": "SM instruction issue", "sm_throughput_pct": kd.get("sm_throughput_pct"), "barrier_stall_per_issue": kd.get("barrier_stall_per_issue"),
-                             "source": "profiles/%s (ncu --set full at HEAD)" % nk.get("tag")} if kd else None)}
+                "binding": ({"resource": "integer ALU pipe / SM issue slots", "alu_pipe_pct_of_peak": kd.get("alu_pipe_pct"),
+                             "issue_active_pct_of_peak": kd.get("issue_active_pct"), "sm_throughput_pct": kd.get("sm_throughput_pct"),
+                             "barrier_stall_per_issue": kd.get("barrier_stall_per_issue"), "frac_of_binding_resource": (kd.get("issue_active_pct") or 0) / 100.0,
+                             "source": "profiles/%s (ncu --set full, one gpurun call at HEAD)" % nk.get("tag")} if kd else None)}
         line = {
             "metric": "Gk-mers/s counted", "value": value, "unit": "Gk-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if args.kmer_size < 32 else "u128",
@@ -681,8 +685,17 @@ def main():
                                   "note": "whole step per GPU against SURVEY 8(d) A(k): a NORMALISED throughput (the path moves far fewer HBM bytes than A(k) assumes), not bandwidth utilisation"},
         }
         if nk:
-            # every kernel of the step: measured DRAM bytes (ncu, one capture at HEAD) / its share of the step / peak
-            line["kernels"] = {"source": "profiles/%s" % nk.get("tag"), "per_step": nk.get("kernels")}
+            # every hot kernel of the step: measured DRAM bytes per launch (one ncu capture at HEAD), their bandwidth over the captured
+            # launch time against the measured peak, the share of the step (launch list of the same call), the binding counter
+            per = {}
+            for kn, v in (nk.get("kernels") or {}).items():
+                t_us = v.get("captured_launch_us") or 0
+                gbs = (v["dram_bytes_per_launch"] / (t_us * 1e-6) / 1e9) if t_us else None
+                per[kn] = {"launches_per_step": v.get("launches_per_step"), "share_of_step_pct": v.get("share_of_step_pct"),
+                           "dram_bytes_per_launch": v.get("dram_bytes_per_launch"), "dram_gbs": gbs, "hbm_frac": (gbs / peak) if gbs else None,
+                           "binding": v.get("binding"), "sm_throughput_pct": v.get("sm_throughput_pct"), "alu_pipe_pct": v.get("alu_pipe_pct"),
+                           "issue_active_pct": v.get("issue_active_pct"), "barrier_stall_per_issue": v.get("barrier_stall_per_issue")}
+            line["kernels"] = {"source": "profiles/%s" % nk.get("tag"), "per_kernel": per}
         if world > 1:
             # records stored into other ranks' HBM by k_xchg_send (summed over ranks and steps) / the slowest rank's
             # summed copy-kernel time (CUDA events on the context stream), per GPU, against 900 GB/s per direction (nominal) and

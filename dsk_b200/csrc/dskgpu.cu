@@ -291,9 +291,19 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
 // estimated volume.  The choice only moves k-mers between partitions: unobservable in the results.
 int dskgpu_suggest_minimizer_size(uint64_t expected_kmers, int kmer_size)
 {
+    // measured on B200 (profiles/r02z*): C2 (400 M k-mers, k = 31): m = 10 -> 10.77 ms/step (21 table splits), 11 -> 10.51,
+    // 12 -> 10.65 (more records); the same reads at k = 63 (293 M k-mers; 128-bit keys: tables of 8 K slots, density 0.48):
+    // m = 10 -> 19.6 ms (15 % of the partitions too heavy for shared memory), 12 -> 13.0, 14 -> 12.7
+    const double n = (double)expected_kmers;
     int m = 10;                                        // the reference's default (-minimizer-size)
-    if (expected_kmers > 600ull * 1000 * 1000) m = 12;
-    if (expected_kmers > 12ull * 1000 * 1000 * 1000) m = 14;
+    if (kmer_size < 32) {
+        if (n > 150e6) m = 11;
+        if (n > 1.5e9) m = 12;
+        if (n > 12e9) m = 14;
+    } else {
+        if (n > 40e6) m = 12;
+        if (n > 150e6) m = 14;
+    }
     if (m > kmer_size - 1) m = kmer_size - 1;
     if (m < 2) m = 2;
     return m;

@@ -135,8 +135,9 @@ void dskgpu_config_default(dskgpu_config* cfg);
 
 /* replaces: the part of ConfigurationAlgorithm::execute (ConfigurationAlgorithm.cpp:245-467) that sizes the partitioning
  * from the estimated volume.  Returns the minimizer length to put in cfg->minimizer_size for a job of `expected_kmers`
- * k-mers over ALL ranks (10 up to 0.6 G k-mers, 12 up to 12 G, 14 beyond; clipped to kmer_size-1): a partition cannot be
- * lighter than its heaviest minimizer bin, so the bins must shrink as the job grows to stay inside a shared-memory table.
+ * k-mers over ALL ranks (k < 32: 10 up to 150 M k-mers, 11 up to 1.5 G, 12 up to 12 G, 14 beyond; k >= 32, whose 128-bit
+ * tables hold fewer k-mers: 10 up to 40 M, 12 up to 150 M, 14 beyond; clipped to kmer_size-1): a partition cannot be lighter
+ * than its heaviest minimizer bin, so the bins must shrink as the job grows to stay inside a shared-memory table.
  * Which partition a k-mer lands in is unobservable in the results.  Host-only, no device needed. */
 int dskgpu_suggest_minimizer_size(uint64_t expected_kmers, int kmer_size);
 

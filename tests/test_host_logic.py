@@ -194,7 +194,8 @@ def test_compute_threshold_agrees_with_oracle_restatement_on_random_histograms()
 def test_suggested_minimizer_size_grows_with_the_job(L):
     # the role of ConfigurationAlgorithm's volume-driven sizing: 10 (reference default) for small jobs, longer for big ones
     f = L.dskgpu_suggest_minimizer_size
-    assert f(0, 31) == 10 and f(400_000_000, 31) == 10 and f(800_000_000, 31) == 12 and f(3_000_000_000, 31) == 12
+    assert f(0, 31) == 10 and f(100_000_000, 31) == 10 and f(400_000_000, 31) == 11 and f(3_000_000_000, 31) == 12
+    assert f(30_000_000, 63) == 10 and f(100_000_000, 63) == 12 and f(293_000_000, 63) == 14
     assert f(72_000_000_000, 31) == 14 and f(72_000_000_000, 63) == 14
     assert f(72_000_000_000, 11) == 10 and f(10, 5) == 4                      # clipped to k-1 (ConfigurationAlgorithm.cpp:249-251)
 
