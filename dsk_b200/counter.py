@@ -256,9 +256,9 @@ def _xchg_methods():
     def debug_plan(self):
         """the plan the DEVICE derived: (level, bin2part, part_kmers, part_recs, part_local_recs)"""
         lvl = C.c_int()
-        cap = (1 << 22) + 16
+        cap = (1 << 24) + 16
         pk = np.zeros(cap, np.uint64); pr = np.zeros(cap, np.uint64); pl = np.zeros(cap, np.uint64)
-        b2p = np.zeros(1 << 22, np.uint32)
+        b2p = np.zeros(1 << 24, np.uint32)
         P = self.L.dskgpu_debug_plan(self.h, C.byref(lvl), b2p.ctypes.data, pk.ctypes.data, pr.ctypes.data, pl.ctypes.data, cap)
         if P < 0:
             self._check(int(P))

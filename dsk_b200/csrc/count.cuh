@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) k_hash_insert(const u64* __restrict__ rec
             const u64* rw = &s_rec[warp][r * RW];
             Kmer<KW> f = rec_kmer_at<KW>(rw, j, k);
             Kmer<KW> c = kmer_canonical(f, kmer_revcomp(f, k));
-            const int bank = (nbanks > 1) ? (int)(rw[RW - 1] & 0xFFu) : 0;
+            const int bank = (nbanks > 1) ? (int)(rw[RW - 1] & 0xFu) : 0;
             u32 slot = table_slot(keys, smask, c);
             if (slot == 0xFFFFFFFFu) { atomicExch(&ctr->hash_overflow, 1u); break; }
             atomicAdd(&counts[(u64)slot * nbanks + bank], 1u);
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256) k_expand_keys(const u64* __restrict__ rec
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (nk == 0) continue;
         u64 pos = base + inc - nk;
-        const u32 bank = (u32)(r[RW - 1] & 0xFFu);
+        const u32 bank = (u32)(r[RW - 1] & 0xFu);
         Kmer<KW> f, rc;
         if constexpr (KW == 1) f = rec_first_kmer1(r, k); else f = rec_first_kmer2(r, k);
         rc = kmer_revcomp(f, k);

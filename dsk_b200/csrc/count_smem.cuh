@@ -79,7 +79,7 @@ template <int KW> DSK_HD u32 cs_bufrec() { return KW == 1 ? (u32)CS_BUFREC1 : (u
 template <int KW> DSK_HD size_t cs_smem_bytes(u32 cap, int nb = 1)
 {
     return (size_t)cap * (8 * KW + 4 * nb)                          // table: keys + counts
-         + (size_t)cs_bufrec<KW>() * (2 * KW * 8 + 2)               // job buffer: records + exclusive item prefix (u16)
+         + (size_t)cs_bufrec<KW>() * (2 * KW * 8 + 4)               // job buffer: records + (item prefix | record index) of the records of the sub-pass
          + (size_t)CS_WARPS * CS_QCAP * (8 * KW + 4)                // retry queues
          + 16;                                                      // mbarrier
 }
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
     u64* s_keys = reinterpret_cast<u64*>(s_dyn);                                   // [cap][KW]
     u32* s_counts = reinterpret_cast<u32*>(s_dyn + (size_t)cap * 8 * KW);          // [cap][nb]
     u64* s_jrec = reinterpret_cast<u64*>(s_dyn + (size_t)cap * (8 * KW + 4 * nb)); // [BUFREC][RW]   (cap % 4 == 0 keeps it 16-byte aligned)
-    u16* s_pref = reinterpret_cast<u16*>(s_jrec + (size_t)BUFREC * RW);            // [BUFREC] exclusive prefix of the records' work items
+    u32* s_pref = reinterpret_cast<u32*>(s_jrec + (size_t)BUFREC * RW);            // [BUFREC] records of the sub-pass, compacted: exclusive item prefix | record << 16
     u64* s_qkey = reinterpret_cast<u64*>(s_pref + BUFREC);                         // [CS_WARPS][CS_QCAP][KW]   (BUFREC % 4 == 0)
     u32* s_qslot = reinterpret_cast<u32*>(s_qkey + (size_t)CS_WARPS * CS_QCAP * KW);   // [CS_WARPS][CS_QCAP]
     u64* s_mbar = reinterpret_cast<u64*>(s_qslot + (size_t)CS_WARPS * CS_QCAP);
@@ -405,16 +405,18 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
         }
         u32 buf_state = 1;                                                         // 1: slice 0 of this job is on its way (publish); 2: resident; 0: neither
 
-        // depth-first over (split level, residue) work items; uniform across the CTA
+        // depth-first over work items (record sub-pass, hash-split level, hash residue); uniform across the CTA.
+        // A job too big for one table starts as 2^split0 RECORD sub-passes: sub-pass rp takes the records whose sub-bin
+        // (4 hash bits of the minimizer, stored in the record) is rp modulo 2^split0 -- every record, hence every k-mer, in exactly
+        // one sub-pass, so the extra passes cost a prefix scan each, not a re-extraction of every k-mer.  A table that still
+        // overflows (one minimizer heavier than a table) splits the k-mer hash space in two, recursively (lvl, res).
         u32 stack[CS_MAX_SPLIT + 2 + (1 << CS_MAX_SPLIT0)];
         int sp = 0;
-        {
-            const u32 l0 = s_dsplit;
-            for (u32 r = (1u << l0); r-- > 0;) stack[sp++] = (l0 << 16) | r;
-        }
+        const u32 rmask = (1u << s_dsplit) - 1u;
+        for (u32 r = rmask + 1u; r-- > 0;) stack[sp++] = r << 24;
         while (sp > 0) {
             const u32 item = stack[--sp];
-            const u32 lvl = item >> 16, res = item & 0xFFFFu, smask = (1u << lvl) - 1u;
+            const u32 rp = item >> 24, lvl = (item >> 16) & 0xFFu, res = item & 0xFFFFu, smask = (1u << lvl) - 1u;
 
             // ---- insert: flat keys (one per thread and iteration; the probe loop runs to the end, loads stay <= 52 %) ---------
             if constexpr (KEYS) {
@@ -447,12 +449,16 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 buf_state = (nslices == 1) ? 2u : 0u;                              // a one-slice job stays in the buffer for its sub-passes
 
                 // work items of CS_Q k-mers: exclusive prefix over the records of the slice (block scan), then equal shares per warp
+                // (one scan for both: items in the low 16 bits -- <= 2368 x 7 --, records of this sub-pass in the high 16)
                 u32 my_ni[RPT], tsum = 0;
 #pragma unroll
                 for (u32 j = 0; j < RPT; j++) {
                     const u32 r = (u32)t * RPT + j;
                     u32 ni = 0;
-                    if (r < n) { const u32 nk = (u32)(s_jrec[(size_t)r * RW + (RW - 1)] >> 8) & 0xFFu; ni = (nk + CS_Q - 1) / CS_Q; }
+                    if (r < n) {
+                        const u32 lw = (u32)s_jrec[(size_t)r * RW + (RW - 1)], nk = (lw >> 8) & 0xFFu;       // [nk:8][sub-bin:4][bank:4]
+                        ni = (((lw >> 4) & rmask) == rp) ? (((nk + CS_Q - 1) / CS_Q) | (1u << 16)) : 0u;       // (rmask <= 15)
+                    }
                     my_ni[j] = ni; tsum += ni;
                 }
                 u32 tinc = tsum;
@@ -469,26 +475,31 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                     I = __shfl_sync(0xFFFFFFFFu, wi, 31);
                     wpre = __shfl_sync(0xFFFFFFFFu, wi - ws, warp);
                 }
+                const u32 nc = I >> 16;                                            // records of this sub-pass (compacted positions 0 .. nc - 1)
+                I &= 0xFFFFu;                                                      // their work items
                 {
                     u32 run = wpre + tinc - tsum;
 #pragma unroll
-                    for (u32 j = 0; j < RPT; j++) { const u32 r = (u32)t * RPT + j; if (r < n) s_pref[r] = (u16)run; run += my_ni[j]; }
+                    for (u32 j = 0; j < RPT; j++) {
+                        if (my_ni[j]) s_pref[run >> 16] = (run & 0xFFFFu) | (((u32)t * RPT + j) << 16);
+                        run += my_ni[j];
+                    }
                 }
                 __syncthreads();
 
                 const u32 lo = (I * (u32)warp) / (u32)CS_WARPS, hi = (I * (u32)(warp + 1)) / (u32)CS_WARPS;        // this warp's items
                 if (lo < hi) {
-                    // record owning item `lo`: the largest r with pref[r] <= lo (32-ary search by ballots; pref[0] = 0)
+                    // (compacted) record owning item `lo`: the largest r with pref[r] <= lo (32-ary search by ballots; pref[0] = 0)
                     u32 rcur;
                     {
-                        u32 base = 0, len = n;
+                        u32 base = 0, len = nc;
                         while (len > 32) {
                             const u32 stride = (len + 31) >> 5, off = (u32)lane * stride;
-                            const bool le = off < len && (u32)s_pref[base + off] <= lo;       // true for a prefix of the lanes
+                            const bool le = off < len && (s_pref[base + off] & 0xFFFFu) <= lo;  // true for a prefix of the lanes
                             const u32 j = (u32)__popc(__ballot_sync(0xFFFFFFFFu, le)) - 1u;
                             base += j * stride; len = min(stride, len - j * stride);
                         }
-                        const bool le = (u32)lane < len && (u32)s_pref[base + lane] <= lo;
+                        const bool le = (u32)lane < len && (s_pref[base + lane] & 0xFFFFu) <= lo;
                         rcur = base + (u32)__popc(__ballot_sync(0xFFFFFFFFu, le)) - 1u;
                     }
                     // 32 consecutive items per iteration, whatever records they belong to: 32 items span at most 32 records, so
@@ -496,14 +507,16 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                     for (u32 x0 = lo; x0 < hi; x0 += 32) {
                         const u32 x = x0 + (u32)lane;
                         const u32 rl = rcur + (u32)lane;
-                        const u32 pl = rl < n ? (u32)s_pref[rl] : 0xFFFFFFFFu;
+                        const u32 el = rl < nc ? s_pref[rl] : 0xFFFFFFFFu;             // (item prefix | record << 16) of compacted record rcur + lane
+                        const u32 pl = rl < nc ? (el & 0xFFFFu) : 0xFFFFFFFFu;
                         u32 ro = 0;                                                    // largest lane l with pref[rcur + l] <= x
 #pragma unroll
                         for (int step = 16; step; step >>= 1) { const u32 v = __shfl_sync(0xFFFFFFFFu, pl, (ro + step) & 31); if (v <= x) ro += step; }
-                        const u32 ex_r = __shfl_sync(0xFFFFFFFFu, pl, ro);
+                        const u32 en = __shfl_sync(0xFFFFFFFFu, el, ro);
+                        const u32 ex_r = en & 0xFFFFu;
                         u64 rw[RW];
                         {
-                            const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(s_jrec + (size_t)(rcur + ro) * RW);
+                            const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(s_jrec + (size_t)min(en >> 16, BUFREC - 1u) * RW);
                             const ulonglong2 a = rp[0]; rw[0] = a.x; rw[1] = a.y;
                             if constexpr (RW == 4) { const ulonglong2 b = rp[1]; rw[2] = b.x; rw[3] = b.y; }
                         }
@@ -518,7 +531,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                         for (int q = 0; q < KW; q++) { f.w[q] = 0; rc.w[q] = 0; }
                         u64 nextb = 0;
                         if (cnt > 0) {
-                            if constexpr (MB) bank = (u32)rw[RW - 1] & 0xFFu;
+                            if constexpr (MB) bank = (u32)rw[RW - 1] & 0xFu;
                             if constexpr (KW == 1) f.w[0] = cs_window<RW>(rw, j0) >> (64 - 2 * k);
                             else { const u64 hw[2] = {cs_window<RW>(rw, j0), cs_window<RW>(rw, j0 + 32)}; f = rec_first_kmer2(hw, k); }
                             rc = kmer_revcomp(f, k);
@@ -572,7 +585,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                 for (u32 i = t; i < cap * KW; i += CS_THREADS) s_keys[i] = EMPTY;
                 for (u32 i = t; i < cap * nb; i += CS_THREADS) s_counts[i] = 0;
                 if (lvl >= (u32)CS_MAX_SPLIT) { if (t == 0) atomicAdd(&ctr->smem_failed, 1u); }
-                else { stack[sp++] = ((lvl + 1) << 16) | (res + (1u << lvl)); stack[sp++] = ((lvl + 1) << 16) | res; nsplit++; }
+                else { stack[sp++] = (rp << 24) | ((lvl + 1) << 16) | (res + (1u << lvl)); stack[sp++] = (rp << 24) | ((lvl + 1) << 16) | res; nsplit++; }
                 if (KEYS || sp == 0) __syncthreads();                              // (the record path has barriers before its next insert)
                 if (sp == 0 && warp == 0) publish(next_job);                       // gave up on the last item: move on
                 continue;

@@ -93,6 +93,7 @@ struct dskgpu_ctx {
     bool sample_queued = false; u64 sample_nkm = 0, sample_distinct = 0; double sample_wmult = 0.0;   // wmult: occurrence-weighted multiplicity (this rank's sample)
     bool global_set = false; u64 g_total_kmers = 0, g_total_recs = 0; double density = 1.0; bool density_known = false;
     int bin_level = NBINS_LOG2; bool hist_fetched = false;
+    int fine_log2 = 22;                              // fine histogram bins (22; 24 with 14-letter minimizers)
     // records in q order (owner-major partition order): what the counting kernels read on one GPU, what crosses NVLink as
     // W - 1 contiguous chunks on several (precs is then the receive buffer)
     DevBuf lrecs, xpeers, bcur, ghist, mkeys;
@@ -229,8 +230,10 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     CK(cudaMallocHost((void**)&ctx->h_hll, sizeof(u32) * HLL_M));
     CK(cudaMallocHost((void**)&ctx->h_xtab, sizeof(XchgTab)));
     int rc;
-    if ((rc = ensure(ctx, ctx->bin_hist, sizeof(unsigned long long) * NBINS_FINE))) return rc;
-    if ((rc = ensure(ctx, ctx->bin_fold, sizeof(unsigned long long) * 2 * NBINS_FINE))) return rc;
+    ctx->fine_log2 = ctx->m >= 14 ? NBINS_FINE_LOG2_MAX : 22;
+    if (const char* e = getenv("DSKGPU_FINE_LOG2")) ctx->fine_log2 = std::min(NBINS_FINE_LOG2_MAX, std::max(NBINS_LOG2, atoi(e)));
+    if ((rc = ensure(ctx, ctx->bin_hist, sizeof(unsigned long long) << ctx->fine_log2))) return rc;
+    if ((rc = ensure(ctx, ctx->bin_fold, (sizeof(unsigned long long) * 2) << ctx->fine_log2))) return rc;
     if ((rc = ensure(ctx, ctx->work_ctr, 64))) return rc;
     if ((rc = ensure(ctx, ctx->hll, sizeof(u32) * HLL_M))) return rc;
     if ((rc = ensure(ctx, ctx->ss, sizeof(StreamState)))) return rc;
@@ -261,7 +264,7 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
         size_t avail = std::min<size_t>((size_t)max_optin, (size_t)per_sm / CS_CTAS_PER_SM - (size_t)reserved) - fa.sharedSizeBytes;
         const size_t fixed = ctx->KW == 1 ? cs_smem_bytes<1>(0) : cs_smem_bytes<2>(0);
         u32 cap = avail > fixed ? (u32)((avail - fixed) / (size_t)(8 * ctx->KW + 4 * ctx->NB)) : 0;
-        cap = cap / 1024 * 1024;
+        cap = cap / 256 * 256;
         if (cap > 16384u) cap = 16384u;                            // the sweep keeps one solid bit per slot of a thread in 32 bits
         if (cfg->smem_table_slots > 0) cap = std::min<u32>(cap, std::max<u32>(64u, (u32)cfg->smem_table_slots / 4 * 4));
         if (ctx->NB > CS_MAX_BANKS) cap = 0;                       // many banks: the global-table path
@@ -319,7 +322,7 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
     CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
     if (ctx->bank_hist.p) CK(cudaMemsetAsync(ctx->bank_hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * (size_t)ctx->NB, ctx->stream));
-    CK(cudaMemsetAsync(ctx->bin_hist.p, 0, sizeof(unsigned long long) * NBINS_FINE, ctx->stream));
+    CK(cudaMemsetAsync(ctx->bin_hist.p, 0, sizeof(unsigned long long) << ctx->fine_log2, ctx->stream));
     CK(cudaMemsetAsync(ctx->hll.p, 0, sizeof(u32) * HLL_M, ctx->stream));
     ctx->sketch_distinct = -1.0;
     ctx->state = 0; ctx->cur_bank = -1; ctx->stream_open = false; ctx->pending_cr = 0;
@@ -443,8 +446,8 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
         SpanGuard g(ctx, SPAN_SUPERK);
         const unsigned gk = (unsigned)((n + 64 + SK_TP - 1) / SK_TP);
         const int bank = ctx->NB > 1 ? ctx->cur_bank : 0;
-        if (ctx->KW == 1) k_superkmers<1><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p, (u32)ctx->nb_passes, (u32)ctx->pass_id);
-        else              k_superkmers<2><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p, (u32)ctx->nb_passes, (u32)ctx->pass_id);
+        if (ctx->KW == 1) k_superkmers<1><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p, (u32)ctx->nb_passes, (u32)ctx->pass_id, META_BIN_BITS - ctx->fine_log2);
+        else              k_superkmers<2><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p, (u32)ctx->nb_passes, (u32)ctx->pass_id, META_BIN_BITS - ctx->fine_log2);
         LAUNCHED();
         k_scan_carry<<<1, 64, 0, ctx->stream>>>((u8*)ctx->codes.p, ss, ctx->k); LAUNCHED();
     }
@@ -853,7 +856,7 @@ static int queue_sample(dskgpu_ctx* ctx)
     // the exact k-mer total is still on the device: size the sample from the bytes pushed (~0.7 k-mers per FASTA byte)
     const double est = std::max(1.0, (double)ctx->bytes_pushed * 0.7);
     double f = (double)SAMPLE_KMERS / est;
-    u32 thresh = f >= 1.0 ? NBINS_FINE : (u32)std::max(1.0, f * (double)NBINS_FINE + 0.5);
+    u32 thresh = f >= 1.0 ? (1u << META_BIN_BITS) : (u32)std::max(1.0, f * (double)(1u << META_BIN_BITS) + 0.5);
     k_sample_select<KW><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((const u64*)ctx->recs.p, (const u32*)ctx->meta.p, &ctr->nrec, thresh,
                                                                     (u64*)ctx->sample_recs.p, SAMPLE_KM_CAP, ctr); LAUNCHED();
     k_hash_insert<KW><<<ctx->num_sms * 2, 256, 0, ctx->stream>>>((const u64*)ctx->sample_recs.p, 0, SAMPLE_KM_CAP, ctx->k, (u64*)ctx->stab_keys.p,
@@ -872,7 +875,7 @@ static int queue_sample(dskgpu_ctx* ctx)
 
 static bool use_smem_path(const dskgpu_ctx* ctx);
 static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers);
-constexpr int SMEM_MAX_SPLIT0_DEFAULT = 1;
+constexpr int SMEM_MAX_SPLIT0_DEFAULT = 4;
 
 // whole-job figures every rank plans from: k-mer total and density sample.  Picks the bin level.
 static void set_global(dskgpu_ctx* ctx, u64 g_kmers, u64 g_recs, u64 g_sample_kmers, u64 g_sample_distinct)
@@ -888,7 +891,7 @@ static void set_global(dskgpu_ctx* ctx, u64 g_kmers, u64 g_recs, u64 g_sample_km
     // bins of the chosen level should average an eighth of a partition: a partition overshoots the cut by part of its last bin
     // (plan.cuh), and the planner runs on the device, so a finer level costs microseconds
     int L = NBINS_LOG2;
-    while (L < NBINS_FINE_LOG2 && ((u64)1 << L) * (T / 8 + 1) < g_kmers) L++;
+    while (L < ctx->fine_log2 && ((u64)1 << L) * (T / 8 + 1) < g_kmers) L++;
     ctx->bin_level = L;
     ctx->global_set = true; ctx->hist_fetched = false;
 }
@@ -904,7 +907,7 @@ static int stage_totals(dskgpu_ctx* ctx)
         // packed bin histogram: could a record field have wrapped?  (test hook: a lower limit exercises the exact rebuild)
         unsigned long long lim = 1ULL << 28;
         if (const char* e = getenv("DSKGPU_TEST_HIST_LIMIT")) lim = (unsigned long long)std::max(1LL, atoll(e));
-        k_check_bins<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, lim, ctr); LAUNCHED();
+        k_check_bins<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, 1u << ctx->fine_log2, lim, ctr); LAUNCHED();
     }
     CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_ss, ctx->ss.p, sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -932,17 +935,17 @@ static int stage_totals(dskgpu_ctx* ctx)
 static int fold_local_hist(dskgpu_ctx* ctx, const void** d_hist)
 {
     if (!ctx->global_set) set_global(ctx, ctx->local_nkm, ctx->local_nrec, ctx->sample_nkm, ctx->sample_distinct);
-    const int shift = NBINS_FINE_LOG2 - ctx->bin_level;
+    const int shift = ctx->fine_log2 - ctx->bin_level;
     const u32 nb = 1u << ctx->bin_level;
     if (!ctx->hist_fetched) {
         if (!ctx->hist_suspect) {
-            k_fold_bins<<<(nb + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, shift, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
+            k_fold_bins<<<(nb + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)ctx->bin_hist.p, 1u << ctx->fine_log2, shift, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
         } else {
             // a packed record count may have wrapped (one minimizer with hundreds of millions of k-mers): exact rebuild from the meta
             CK(cudaMemsetAsync(ctx->bin_fold.p, 0, sizeof(unsigned long long) * 2 * nb, ctx->stream));
             if (ctx->local_nrec) {
                 k_rebuild_hist<<<(unsigned)std::min<u64>((ctx->local_nrec + 255) / 256, (u64)ctx->num_sms * 16), 256, 0, ctx->stream>>>(
-                    (const u32*)ctx->meta.p, ctx->local_nrec, shift, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
+                    (const u32*)ctx->meta.p, ctx->local_nrec, META_BIN_BITS - ctx->bin_level, nb, (unsigned long long*)ctx->bin_fold.p); LAUNCHED();
             }
             ctx->st.hist_rebuilt = 1;
         }
@@ -960,15 +963,17 @@ static bool use_smem_path(const dskgpu_ctx* ctx)
 }
 
 // Shared-memory path limits.  One pass over a partition takes `fit` k-mers (table filled to 75 % at the sampled density);
-// a bigger partition starts pre-split into 2^split0 hash-residue sub-passes.  Every sub-pass re-reads the records and
-// re-extracts every k-mer (~47 % of a full pass), so beyond 2^max_split0 sub-passes the L2-resident global table -- one
-// pass whatever the size -- is the cheaper path.  The size of a partition is bounded below by its heaviest minimizer
-// (9e-5 of the job at k=31, m=10): multi-G k-mer jobs and multi-GPU jobs are where this matters.
+// a bigger partition starts pre-split into 2^split0 RECORD sub-passes over the sub-bins stored in the records (count_smem.cuh):
+// every record is expanded in exactly one sub-pass, so a partition of up to 16 tables costs little more than 16 partitions of
+// one table.  (Round 1 split by k-mer hash residue: every sub-pass re-extracted every k-mer, and beyond two sub-passes the
+// L2-resident global table was the cheaper path -- 48 % of the k-mers of BASELINE configs[3] at 8 GPUs took it,
+// profiles/r03b.)  The size of a partition is bounded below by its heaviest minimizer bin: jobs of tens of G k-mers are
+// where this matters.
 static int smem_max_split0(const dskgpu_ctx*)
 {
-    static const int v = [] { const char* e = getenv("DSKGPU_SMEM_MAX_SPLIT0"); int x = e ? atoi(e) : SMEM_MAX_SPLIT0_DEFAULT;
-                              return std::min(std::max(x, 0), (int)CS_MAX_SPLIT0); }();
-    return v;
+    const char* e = getenv("DSKGPU_SMEM_MAX_SPLIT0");                     // (read per call: the tests lower it to exercise the heavy paths)
+    const int x = e ? atoi(e) : SMEM_MAX_SPLIT0_DEFAULT;
+    return std::min(std::max(x, 0), (int)CS_MAX_SPLIT0);
 }
 static double smem_fit_kmers(const dskgpu_ctx* ctx) { return std::max(64.0, (double)ctx->smem_cap * 0.75 / ctx->density); }
 static u64 smem_max_kmers(const dskgpu_ctx* ctx)
@@ -1113,7 +1118,7 @@ static int stage_scatter(dskgpu_ctx* ctx)
     const u64 nq = (u64)ctx->cfg.world_size * h.PW;
     if ((rc = ensure(ctx, ctx->cursor, (nq + 1) * 8))) return rc;
     SpanGuard g(ctx, SPAN_PART);
-    const int bin_shift = NBINS_FINE_LOG2 - ctx->bin_level;
+    const int bin_shift = META_BIN_BITS - ctx->bin_level;
     if (nq < msd_min_parts(KW)) {
         CK(cudaMemcpyAsync(ctx->cursor.p, ctx->loff.p, nq * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         const unsigned sb = (unsigned)std::min<u64>((ctx->local_nrec + SC_THREADS - 1) / SC_THREADS, (u64)ctx->num_sms * 32);
@@ -1312,7 +1317,7 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
             CsSegs sg;
             sg.tab = (const XchgTab*)ctx->xtab.p; sg.X = (const u64*)ctx->rcnt_dev; sg.gk_q = (const u64*)ctx->gk_q.p;
             sg.W = W; sg.PW = h.PW; sg.qbase = me * h.PW;
-            sg.fit = (float)smem_fit_kmers(ctx);
+            sg.fit = (float)(smem_fit_kmers(ctx) * 0.85);                            // sub-bins are minimizers: sub-passes are not of equal size
             sg.max_split0 = ctx->cfg.count_mode != DSKGPU_COUNT_SMEM ? (u32)smem_max_split0(ctx) : 0u;
             CK(cudaMemsetAsync(ctx->work_ctr.p, 0, 64, ctx->stream));
             const unsigned grid = (unsigned)std::min<size_t>(ctx->nl_me, (size_t)ctx->num_sms * CS_CTAS_PER_SM);
@@ -2093,7 +2098,7 @@ int64_t dskgpu_selftest_plan(int level, const uint64_t* global_hist, const uint6
                              uint32_t smem_slots, double density, int count_mode, int forced_nb_partitions,
                              uint32_t* bin2part, uint64_t* part_kmers, uint64_t* part_local_recs, size_t max_parts)
 {
-    if (level < NBINS_LOG2 || level > NBINS_FINE_LOG2 || !global_hist || !local_hist || world_size < 1 || world_size > PLAN_MAXW) return DSKGPU_ERR_ARG;
+    if (level < NBINS_LOG2 || level > NBINS_FINE_LOG2_MAX || !global_hist || !local_hist || world_size < 1 || world_size > PLAN_MAXW) return DSKGPU_ERR_ARG;
     dskgpu_ctx* ctx = new dskgpu_ctx();
     dskgpu_config_default(&ctx->cfg);
     ctx->cfg.world_size = world_size; ctx->cfg.count_mode = count_mode; ctx->cfg.nb_partitions = forced_nb_partitions;

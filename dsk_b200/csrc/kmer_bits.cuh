@@ -155,15 +155,29 @@ DSK_HD u32 mmer_order(u32 x, int m)
 // multi-G k-mer jobs: level = what keeps the average bin well under one shared-memory table) and the host packs
 // consecutive bins of that level into partitions of the size the counting kernel wants (balanced on exact counts,
 // the job the reference gives to its sampled LPT table, K/PartiInfo.cpp:48-106).
-constexpr int NBINS_FINE_LOG2 = 22;
-constexpr u32 NBINS_FINE = 1u << NBINS_FINE_LOG2;
+// A record carries the top META_BIN_BITS bits of the minimizer hash ("bin24"); the fine histogram has 2^fine_log2 bins
+// (fine bin = bin24 >> (24 - fine_log2)): 2^22 normally, 2^24 for the jobs that run with 14-letter minimizers (tens of G
+// k-mers: at 2^22 bins the AVERAGE bin of a 72 G k-mer job already is a whole shared-memory table, and 3 % of the k=31 /
+// 48 % of the k=63 k-mers of BASELINE configs[2]/[3] at 8 GPUs ended up in partitions too heavy for it, profiles/r03b).
+constexpr int META_BIN_BITS = 24;
+constexpr u32 META_BIN_MASK = (1u << META_BIN_BITS) - 1u;
+constexpr int NBINS_FINE_LOG2_MAX = 24;
 constexpr int NBINS_LOG2 = 16;                               // coarsest level (DSKGPU_NBINS)
 constexpr u32 NBINS = 1u << NBINS_LOG2;
-DSK_HD u32 bin_of(u32 minimizer)
+// 32-bit hash of a minimizer: the top 24 bits are the record's bin ("bin24"), the next 4 its SUB-BIN -- hash bits no
+// partition is built from, stored in the record itself ([nk:8][sub:4][bank:4] in the low 16 bits of its last word): a
+// partition too big for one shared-memory table is counted as 2^s sub-passes that each take the records of their sub-bins,
+// every record in exactly one of them (all occurrences of a k-mer share minimizer, hence sub-bin).
+DSK_HD u32 bin_hash(u32 minimizer)
 {
     u32 h = minimizer * 0x9E3779B1u;
     h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
-    return h >> (32 - NBINS_FINE_LOG2);
+    return h;
+}
+DSK_HD u32 bin_of(u32 minimizer)
+{
+    const u32 h = bin_hash(minimizer);
+    return h >> (32 - META_BIN_BITS);
 }
 
 // 64-bit finalizer (murmur3 fmix64) for hash-table slots

@@ -61,8 +61,8 @@ template <int KW>
 __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict__ codes, const StreamState* __restrict__ ss,
                                                            int k, int m, int bank, u64* __restrict__ recs,
                                                            u32* __restrict__ rec_meta, u64 rec_cap, Counters* ctr,
-                                                           unsigned long long* __restrict__ bin_hist /*[NBINS_FINE] packed: records << 36 | k-mers*/,
-                                                           u32 nb_passes, u32 pass_id)
+                                                           unsigned long long* __restrict__ bin_hist /*[1 << fine_log2] packed: records << 36 | k-mers*/,
+                                                           u32 nb_passes, u32 pass_id, int fine_shift /*24 - fine_log2*/)
 {
     constexpr int RW = 2 * KW;
     __shared__ u64 s_pk[SK_TP / 32 + 8];                         // 2-bit bases, MSB first, 32 per word
@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
         u64 rw[RW];
 #pragma unroll
         for (int x = 0; x < RW; x++) rw[x] = get64(p + 32 * x);
-        rw[RW - 1] = (rw[RW - 1] & ~0xFFFFULL) | ((u64)nk << 8) | (u64)bank;
+        const u32 hmin = bin_hash(s_lmn[i]);
+        rw[RW - 1] = (rw[RW - 1] & ~0xFFFFULL) | ((u64)nk << 8) | (u64)(((hmin >> 4) & 15u) << 4) | (u64)bank;     // [nk:8][sub-bin:4][bank:4]
         const u64 ri = goff + i;
         if constexpr (RW == 2) {
             reinterpret_cast<ulonglong2*>(recs)[ri] = make_ulonglong2(rw[0], rw[1]);
@@ -261,9 +262,9 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
             reinterpret_cast<ulonglong2*>(recs)[2 * ri + 1] = make_ulonglong2(rw[2], rw[3]);
         }
         // fine histogram of the bins while the records are produced (fire-and-forget REDs under an ALU-bound kernel)
-        const u32 bin = bin_of(s_lmn[i]);
+        const u32 bin = hmin >> (32 - META_BIN_BITS);
         rec_meta[ri] = bin | (nk << 24);
-        atomicAdd(&bin_hist[bin], (1ULL << BINH_KBITS) | (unsigned long long)nk);
+        atomicAdd(&bin_hist[bin >> fine_shift], (1ULL << BINH_KBITS) | (unsigned long long)nk);
         nk_sum += nk;
     }
     nk_sum = __reduce_add_sync(0xFFFFFFFFu, nk_sum);
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(const u64* __restri
     const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
     ulonglong2* dst = reinterpret_cast<ulonglong2*>(out);
     for (u64 i = (u64)blockIdx.x * SC_THREADS + threadIdx.x; i < nrec; i += (u64)gridDim.x * SC_THREADS) {
-        const u32 q = __ldg(bin2q + ((rec_meta[i] & (NBINS_FINE - 1)) >> bin_shift));
+        const u32 q = __ldg(bin2q + ((rec_meta[i] & META_BIN_MASK) >> bin_shift));
         ulonglong2 a = src[(RW / 2) * i], b;
         if constexpr (RW == 4) b = src[2 * i + 1];
         const u64 d = atomicAdd(&cursor[q], 1ULL);
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(MS_THREADS) k_msd_pass(const u64* __restrict__
             const u64 i = base + (u64)j * MS_THREADS + t;
             q[j] = 0xFFFFFFFFu;
             if (i < nrec) {
-                q[j] = FIRST ? __ldg(bin2q + ((src_key[i] & (NBINS_FINE - 1)) >> bin_shift)) : src_key[i];
+                q[j] = FIRST ? __ldg(bin2q + ((src_key[i] & META_BIN_MASK) >> bin_shift)) : src_key[i];
                 ra[j] = in[VPR * i];
                 if constexpr (KW == 2) rb[j] = in[2 * i + 1];
             }
@@ -410,10 +411,10 @@ __global__ void __launch_bounds__(MS_THREADS) k_msd_pass(const u64* __restrict__
     }
 }
 
-// packed fine bin histogram [NBINS_FINE] -> level histogram [2][NBINS_FINE >> shift] (records per bin, then k-mers per bin)
-__global__ void k_fold_bins(const unsigned long long* __restrict__ fine, int shift, unsigned long long* __restrict__ out)
+// packed fine bin histogram [nfine] -> level histogram [2][nfine >> shift] (records per bin, then k-mers per bin)
+__global__ void k_fold_bins(const unsigned long long* __restrict__ fine, u32 nfine, int shift, unsigned long long* __restrict__ out)
 {
-    const u32 nb = NBINS_FINE >> shift, per = 1u << shift;
+    const u32 nb = nfine >> shift, per = 1u << shift;
     for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
         const unsigned long long* src = fine + ((size_t)b << shift);
         unsigned long long r = 0, k = 0;
@@ -423,19 +424,19 @@ __global__ void k_fold_bins(const unsigned long long* __restrict__ fine, int shi
 }
 
 // flags a fine bin whose k-mer field reached `limit` (2^28 in production): its record field may have wrapped
-__global__ void k_check_bins(const unsigned long long* __restrict__ fine, unsigned long long limit, Counters* ctr)
+__global__ void k_check_bins(const unsigned long long* __restrict__ fine, u32 nfine, unsigned long long limit, Counters* ctr)
 {
     bool bad = false;
-    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < NBINS_FINE; b += gridDim.x * blockDim.x) bad |= (fine[b] & BINH_KMASK) >= limit;
+    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < nfine; b += gridDim.x * blockDim.x) bad |= (fine[b] & BINH_KMASK) >= limit;
     if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicExch(&ctr->hist_suspect, 1u);
 }
 
-// the exact level histogram from the record meta (bin | nk << 24), for the flagged case: two 64-bit atomics per record
-__global__ void k_rebuild_hist(const u32* __restrict__ rec_meta, u64 nrec, int shift, unsigned long long* __restrict__ out)
+// the exact level histogram from the record meta (bin24 | nk << 24), for the flagged case: two 64-bit atomics per record
+// (shift = 24 - level, nb = bins of the level)
+__global__ void k_rebuild_hist(const u32* __restrict__ rec_meta, u64 nrec, int shift, u32 nb, unsigned long long* __restrict__ out)
 {
-    const u32 nb = NBINS_FINE >> shift;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (u64)gridDim.x * blockDim.x) {
-        const u32 mt = rec_meta[i], b = (mt & (NBINS_FINE - 1)) >> shift;
+        const u32 mt = rec_meta[i], b = (mt & META_BIN_MASK) >> shift;
         atomicAdd(&out[b], 1ULL);
         atomicAdd(&out[nb + b], (unsigned long long)(mt >> 24));
     }
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(256) k_sample_select(const u64* __restrict__ r
     const u64 nrec = *nrec_dev;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (u64)gridDim.x * blockDim.x) {
         const u32 mt = rec_meta[i];
-        if ((mt & (NBINS_FINE - 1)) >= thresh) continue;
+        if ((mt & META_BIN_MASK) >= thresh) continue;
         const unsigned long long nk = mt >> 24;
         if (atomicAdd(&ctr->sample_nkm, nk) + nk > km_cap) { atomicAdd(&ctr->sample_nkm, ~nk + 1ULL); continue; }   // sample full (a record holds >= 1 k-mer,
         const u64 d = atomicAdd(&ctr->sample_nrec, 1ULL);                                                              //  so records <= km_cap as well)

@@ -210,6 +210,7 @@ def test_auto_mixed_shared_memory_and_heavy_partitions(k, heavy, monkeypatch):
     # are renumbered to the end and expanded into hash buckets of flat keys counted in shared memory (default) or counted
     # by the global table (DSKGPU_HEAVY_PATH=table), the others by the shared-memory path, in the same job
     monkeypatch.setenv("DSKGPU_HEAVY_PATH", heavy)
+    monkeypatch.setenv("DSKGPU_SMEM_MAX_SPLIT0", "1")                     # (default 4: up to 16 record sub-passes stay in shared memory)
     buf, n, _ = reads_fasta(G=1_000_000, coverage=30, L=150, err=0.01, seed=11)
     sc = compare_with_oracle([buf[:n].tobytes()], k, engine=dict(count_mode="auto", smem_table_slots=256, hash_log2_slots=18))
     st = sc.getInfo()["engine"]
@@ -221,6 +222,7 @@ def test_heavy_bucket_overflow_falls_back_to_the_table(monkeypatch):
     # one k-mer with a huge multiplicity (poly-A reads) outgrows any hash-bucket slab: that group must fall back to the
     # global table, never lose counts
     monkeypatch.setenv("DSKGPU_HEAVY_PATH", "bucket")
+    monkeypatch.setenv("DSKGPU_SMEM_MAX_SPLIT0", "1")
     buf, n, _ = reads_fasta(G=200_000, coverage=20, L=150, err=0.01, seed=21)
     data = buf[:n].tobytes() + b"".join(b">p%d\n%s\n" % (i, b"A" * 150) for i in range(3000))
     sc = compare_with_oracle([data], 31, engine=dict(count_mode="auto", smem_table_slots=256, hash_log2_slots=16))
@@ -228,8 +230,9 @@ def test_heavy_bucket_overflow_falls_back_to_the_table(monkeypatch):
     assert st["nb_groups_hash"] > 0
 
 
-def test_heavy_buckets_with_per_bank_counts():
+def test_heavy_buckets_with_per_bank_counts(monkeypatch):
     # -histo2D + heavy partitions: the bank id rides in the two spare top bits of the flat keys
+    monkeypatch.setenv("DSKGPU_SMEM_MAX_SPLIT0", "1")
     g = genome_codes(300_000, seed=19)
     asm = assembly_fasta(g)
     buf, n, _ = reads_fasta(coverage=25, L=150, err=0.01, seed=19, genome=g)
@@ -324,7 +327,7 @@ def split_records(data, parts):
 
 @pytest.mark.parametrize("W,k,mode", [(2, 31, "auto"), (3, 31, "hash"), (2, 63, "auto"), (4, 31, "sort"), (3, 63, "smem"), (3, 31, "auto-tiny"), (5, 31, "auto-tiny"),
                                       (8, 31, "auto")])
-def test_multi_rank_exchange_in_process(W, k, mode):
+def test_multi_rank_exchange_in_process(W, k, mode, monkeypatch):
     """N ranks as N contexts on one GPU: every rank parses a slice and plans the same partitions on the device, scatters its
     records into owner-major order, one contiguous copy per (sender, owner) pair moves them (sender-major receive layout), every
     rank counts only what it owns, each partition as W segments.  Union of the ranks' outputs == oracle."""
@@ -335,6 +338,7 @@ def test_multi_rank_exchange_in_process(W, k, mode):
     extra = {}
     if mode == "auto-tiny":               # heavy partitions (global table) and light ones (shared memory) on every rank
         mode, extra = "auto", dict(smem_table_slots=256)
+        monkeypatch.setenv("DSKGPU_SMEM_MAX_SPLIT0", "1")
     engines = [GpuCounter(kmer_size=k, abundance_min=2, rank=r, world_size=W, count_mode=mode, hash_log2_slots=16, **extra) for r in range(W)]
     try:
         for e, piece in zip(engines, split_records(data, W)):

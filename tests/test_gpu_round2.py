@@ -127,11 +127,12 @@ def test_global_table_group_outgrowing_its_estimate_is_regrouped(k, monkeypatch)
 
 # ---------------------------------------------------------------- the device planner against its host mirror
 @pytest.mark.parametrize("k,slots,mode", [(31, 4096, "auto"), (63, 2048, "auto"), (31, 1024, "auto"), (31, 256, "auto")])
-def test_device_planner_equals_host_mirror(k, slots, mode):
+def test_device_planner_equals_host_mirror(k, slots, mode, monkeypatch):
     """dsk_b200/csrc/plan.cuh: prefix sums + cut flags + renumbering on the device give, bit for bit, the plan of the
     sequential restatement (plan_host via dskgpu_selftest_plan) on the histogram of a real job"""
     import torch
     from dsk_b200 import _lib
+    monkeypatch.setenv("DSKGPU_SMEM_MAX_SPLIT0", "1")                     # heavy partitions exist at every table size of the test
     buf, n, _ = reads_fasta(G=2_000_000, coverage=20, L=150, err=0.01, seed=91)
     data = bytearray(buf[:n].tobytes())
     data[1000:1000] = b">low\n" + b"ACAC" * 40000 + b"\n"                       # one hot minimizer: heavy partitions
@@ -187,6 +188,58 @@ def test_packed_bin_histogram_rebuilt_when_it_could_wrap(k, monkeypatch):
             assert_equals_oracle(kk, cc, eng.histogram()[0], ref)
             plans.append(eng.debug_plan())
     assert all((a == b).all() if hasattr(a, "all") else a == b for a, b in zip(plans[0], plans[1]))
+
+
+@pytest.mark.parametrize("k,slots", [(31, 512), (63, 512), (31, 256), (21, 1024)])
+def test_record_sub_passes_keep_big_partitions_in_shared_memory(k, slots):
+    """a partition of up to 16 tables is counted in shared memory as record sub-passes over the sub-bins stored in the records
+    (every record expanded in exactly one sub-pass); with a tiny table most partitions of this job are such partitions"""
+    g = genome_codes(600_000, seed=23)
+    buf, n, _ = reads_fasta(coverage=30, L=150, err=0.01, seed=23, genome=g)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], k, abundance_min=2)
+    with GpuCounter(kmer_size=k, abundance_min=2, smem_table_slots=slots, nb_partitions=64) as eng:      # 64 partitions of ~270 K k-mers: far beyond one table
+        eng.push_bytes(data)
+        eng.finish()
+        st = eng.stats()
+        kk, cc = eng.solid()
+        assert st["kmers_nb_distinct"] == ref.nb_distinct
+        assert_equals_oracle(kk, cc, eng.histogram()[0], ref)
+    with GpuCounter(kmer_size=k, abundance_min=2, smem_table_slots=slots) as eng:                         # planned sizes: partitions of up to 16 tables stay in shared memory
+        eng.push_bytes(data)
+        eng.finish()
+        st = eng.stats()
+        assert st["nb_parts_smem"] == st["nb_partitions"] and st["nb_groups_hash"] == 0 and st["nb_groups_sort"] == 0
+        kk, cc = eng.solid()
+        assert_equals_oracle(kk, cc, eng.histogram()[0], ref)
+    # two banks, per-bank counts: the bank nibble shares the byte with the sub-bin
+    asm = assembly_fasta(g)
+    sc = SortingCountAlgorithm(BankAlbum([BankBytes(asm), BankBytes(data)]), {"-kmer-size": k, "-abundance-min": "2", "-histo2D": 1}, smem_table_slots=slots).execute()
+    ref2 = oracle.count_files([asm, data], k, abundance_min=2, histo2d=True)
+    keys, cnt = sc.getSolidCounts()
+    h1, h2 = sc.getHistogram()
+    assert_equals_oracle(keys, cnt, h1, ref2, h2)
+
+
+@pytest.mark.parametrize("k,fine,limit", [(31, 24, None), (63, 24, None), (31, 18, None), (31, 24, "40")])
+def test_fine_histogram_levels(k, fine, limit, monkeypatch):
+    """the fine minimizer-bin histogram has 2^22 bins, or 2^24 for the jobs that run with 14-letter minimizers (forced here on a
+    small job, also together with the exact-rebuild path); coarser and finer levels give the same results"""
+    monkeypatch.setenv("DSKGPU_FINE_LOG2", str(fine))
+    if limit:
+        monkeypatch.setenv("DSKGPU_TEST_HIST_LIMIT", limit)
+    buf, n, _ = reads_fasta(G=300_000, coverage=30, L=150, err=0.01, seed=95)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], k, abundance_min=2)
+    with GpuCounter(kmer_size=k, abundance_min=2, minimizer_size=14 if fine == 24 else 10, smem_table_slots=1024) as eng:
+        eng.push_bytes(data)
+        eng.finish()
+        st = eng.stats()
+        assert st["hist_rebuilt"] == (1 if limit else 0)
+        kk, cc = eng.solid()
+        assert st["kmers_nb_distinct"] == ref.nb_distinct
+        assert_equals_oracle(kk, cc, eng.histogram()[0], ref)
+    run_multi([0, 0, 0], k, data, minimizer_size=14 if fine == 24 else 10)
 
 
 @pytest.mark.parametrize("k,W,min_parts", [(31, 1, 1), (63, 1, 1), (31, 3, 1), (31, 1, 300), (31, 2, 5000)])

@@ -268,7 +268,7 @@ def test_partition_planner_invariants_and_rank_agreement(L, world, level):
     np.minimum.at(first, b2p, np.arange(nb)); np.maximum.at(last, b2p, np.arange(nb))
     assert (last - first + 1 == nbins_of).all()
     # partitions beyond the reach of the shared-memory path (AUTO mode) are numbered after all the others, in bin order
-    lim = int(slots * 0.75 / density * 2)                              # fit x 2^max_split0 (default 1)
+    lim = int(slots * 0.75 / density * 16)                             # fit x 2^max_split0 (default 4: 16 record sub-passes)
     heavy = np.nonzero(pk > lim)[0]
     assert len(heavy) >= 5
     light = np.nonzero(pk <= lim)[0]

@@ -7,7 +7,7 @@ for step in "$@"; do
   case "$step" in
     pynew)    timeout 1500 python -m pytest tests/test_gpu_round2.py tests/test_cli_dropin.py -x -q > "$OUT/pytest_new.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_new.log"; tail -15 "$OUT/pytest_new.log" ;;
     pycount)  timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "reference_runs or tiny_smem or synthetic or histo2d or heavy or multi_rank or forced or regrown or pass_loop" > "$OUT/pytest_count.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_count.log"; tail -4 "$OUT/pytest_count.log" ;;
-    pyfast)   timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "device_planner or packed_bin or msd_multi or solid_set_ordering or multi_rank or multi_finish or synthetic_vs_oracle or tiny_smem or heavy or forced or regrown or pass_loop or auto_cutoff" > "$OUT/pytest_fast.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_fast.log"; tail -25 "$OUT/pytest_fast.log" ;;
+    pyfast)   timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "device_planner or packed_bin or fine_histogram or record_sub or msd_multi or solid_set_ordering or multi_rank or multi_finish or synthetic_vs_oracle or tiny_smem or heavy or forced or regrown or pass_loop or auto_cutoff" > "$OUT/pytest_fast.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_fast.log"; tail -25 "$OUT/pytest_fast.log" ;;
     pytest)   timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_gpu.log"; tail -5 "$OUT/pytest_gpu.log" ;;
     bench)    timeout 600 python bench.py > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json"; tail -3 "$OUT/bench_n1.err" ;;
     benchq)   timeout 600 python bench.py --no-cpu-baseline > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"; tail -c 3000 "$OUT/bench_n1.json"; tail -3 "$OUT/bench_n1.err" ;;
