@@ -505,6 +505,9 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                     // 32 consecutive items per iteration, whatever records they belong to: 32 items span at most 32 records, so
                     // the owner of item x is found among the prefixes of records rcur .. rcur + 31 (one value per lane)
                     for (u32 x0 = lo; x0 < hi; x0 += 32) {
+                        // the table overflowed (somebody ran out of probes): the pass is lost, every further insert into the full
+                        // table would walk CS_MAXPROBE slots for nothing -- drop the ring and leave (the split passes redo it all)
+                        if (__any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile u32*>(&s_ovf) != ovf_seen)) { qc = 0; break; }
                         const u32 x = x0 + (u32)lane;
                         const u32 rl = rcur + (u32)lane;
                         const u32 el = rl < nc ? s_pref[rl] : 0xFFFFFFFFu;             // (item prefix | record << 16) of compacted record rcur + lane
@@ -574,8 +577,14 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                         }
                     }
                 }
-                while (qc) ring_serve();
+                while (qc) {
+                    if (__any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile u32*>(&s_ovf) != ovf_seen)) { qc = 0; break; }
+                    ring_serve();
+                }
                 __syncthreads();                                                   // inserts of the slice done, job buffer free
+                // (uniform: nobody inserts between this barrier and the next ones)  a lost pass skips its remaining slices; the
+                // buffer state of a multi-slice job already says "reload slice 0"
+                if (*reinterpret_cast<volatile u32*>(&s_ovf) != ovf_seen) break;
             }
             const u32 ovf_now = *reinterpret_cast<volatile u32*>(&s_ovf);          // stable: nobody inserts until after the next barriers
             const bool overflowed = ovf_now != ovf_seen;

@@ -93,7 +93,7 @@ struct dskgpu_ctx {
     bool sample_queued = false; u64 sample_nkm = 0, sample_distinct = 0; double sample_wmult = 0.0;   // wmult: occurrence-weighted multiplicity (this rank's sample)
     bool global_set = false; u64 g_total_kmers = 0, g_total_recs = 0; double density = 1.0; bool density_known = false;
     int bin_level = NBINS_LOG2; bool hist_fetched = false;
-    int fine_log2 = 22;                              // fine histogram bins (22; 24 with 14-letter minimizers)
+    int fine_log2 = 22;                              // fine histogram bins (2^22 = 32 MB: stays L2-resident under the record stream)
     // records in q order (owner-major partition order): what the counting kernels read on one GPU, what crosses NVLink as
     // W - 1 contiguous chunks on several (precs is then the receive buffer)
     DevBuf lrecs, xpeers, bcur, ghist, mkeys;
@@ -230,7 +230,9 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     CK(cudaMallocHost((void**)&ctx->h_hll, sizeof(u32) * HLL_M));
     CK(cudaMallocHost((void**)&ctx->h_xtab, sizeof(XchgTab)));
     int rc;
-    ctx->fine_log2 = ctx->m >= 14 ? NBINS_FINE_LOG2_MAX : 22;
+    // 2^22 bins (32 MB) stay L2-resident while the records stream by; 2^24 bins (128 MB > L2) tripled k_superkmers on the 9 G
+    // k-mer-per-GPU job (69 -> 190 ms, profiles/r03f against r03b).  Partitions finer than a bin come from the record sub-bins.
+    ctx->fine_log2 = 22;
     if (const char* e = getenv("DSKGPU_FINE_LOG2")) ctx->fine_log2 = std::min(NBINS_FINE_LOG2_MAX, std::max(NBINS_LOG2, atoi(e)));
     if ((rc = ensure(ctx, ctx->bin_hist, sizeof(unsigned long long) << ctx->fine_log2))) return rc;
     if ((rc = ensure(ctx, ctx->bin_fold, (sizeof(unsigned long long) * 2) << ctx->fine_log2))) return rc;
@@ -306,6 +308,11 @@ int dskgpu_suggest_minimizer_size(uint64_t expected_kmers, int kmer_size)
     } else {
         if (n > 40e6) m = 12;
         if (n > 150e6) m = 14;
+        // 128-bit keys: a table takes ~12 K k-mers, and ONE minimizer cannot be split by records.  The hottest 14-letter minimizers
+        // hold w / (4^14 / 2) = 3.7e-7 of the k-mers of a random genome (w = k - m + 1 windows): 19.7 K k-mers of BASELINE
+        // configs[3] (52.8 G k-mers) -- 37 % of its k-mers sat in minimizers heavier than a table (profiles/r03f: 229 787
+        // overflow splits per rank).  One more letter: 4.8 K.
+        if (n > 16e9) m = 15;
     }
     if (m > kmer_size - 1) m = kmer_size - 1;
     if (m < 2) m = 2;

@@ -146,7 +146,7 @@ DSK_HD u32 mmer_order(u32 x, int m)
     const u32 mask_ma1 = 0x55555555u & ((1u << ((m - 2) * 2)) - 1u);
     u32 a1 = ~(v | (v >> 2));
     a1 = ((a1 >> 1) & a1) & mask_ma1;
-    return a1 ? (v | (1u << (2 * m))) : v;                    // m <= 14: 29 bits
+    return a1 ? (v | (1u << (2 * m))) : v;                    // m <= 15: 31 bits
 }
 
 // minimizer -> bin (the role of Repartitor::operator(), K/PartiInfo.hpp:323; any deterministic map is legal --
@@ -156,9 +156,9 @@ DSK_HD u32 mmer_order(u32 x, int m)
 // consecutive bins of that level into partitions of the size the counting kernel wants (balanced on exact counts,
 // the job the reference gives to its sampled LPT table, K/PartiInfo.cpp:48-106).
 // A record carries the top META_BIN_BITS bits of the minimizer hash ("bin24"); the fine histogram has 2^fine_log2 bins
-// (fine bin = bin24 >> (24 - fine_log2)): 2^22 normally, 2^24 for the jobs that run with 14-letter minimizers (tens of G
-// k-mers: at 2^22 bins the AVERAGE bin of a 72 G k-mer job already is a whole shared-memory table, and 3 % of the k=31 /
-// 48 % of the k=63 k-mers of BASELINE configs[2]/[3] at 8 GPUs ended up in partitions too heavy for it, profiles/r03b).
+// (fine bin = bin24 >> (24 - fine_log2)): 2^22 (32 MB, L2-resident under the record stream; DSKGPU_FINE_LOG2 picks another
+// level up to 2^24, which costs k_superkmers 3x on multi-G k-mer jobs: the REDs then miss L2).  At 2^22 bins the AVERAGE bin of
+// a 72 G k-mer job already is a whole shared-memory table: such partitions are counted as record sub-passes (sub-bins below).
 constexpr int META_BIN_BITS = 24;
 constexpr u32 META_BIN_MASK = (1u << META_BIN_BITS) - 1u;
 constexpr int NBINS_FINE_LOG2_MAX = 24;

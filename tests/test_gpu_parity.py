@@ -182,9 +182,9 @@ def test_synthetic_vs_oracle(k):
     compare_with_oracle([buf[:n].tobytes()], k)
 
 
-@pytest.mark.parametrize("k,m", [(31, 8), (31, 12), (31, 14), (63, 12), (63, 14), (21, 13)])
+@pytest.mark.parametrize("k,m", [(31, 8), (31, 12), (31, 14), (63, 12), (63, 14), (21, 13), (63, 15), (31, 15), (33, 16)])
 def test_minimizer_sizes(k, m):
-    # -minimizer-size only moves k-mers between partitions: same counts whatever m (big jobs run with m = 12 / 14)
+    # -minimizer-size only moves k-mers between partitions: same counts whatever m (big jobs run with m = 12 / 14 / 15; 16 is clipped to 15)
     buf, n, _ = reads_fasta(G=300_000, coverage=30, L=150, err=0.01, seed=300 + m)
     data = buf[:n].tobytes()
     ref = oracle.count_files([data], k, abundance_min=2)

@@ -113,7 +113,7 @@ def test_scanner_flags_fastq_in_fasta(L):
     assert L.dskgpu_selftest_scan(arr.ctypes.data, arr.size, 1, out.ctypes.data, out.size) < 0
 
 
-@pytest.mark.parametrize("k,m", [(31, 10), (63, 10), (15, 7), (12, 5), (32, 10), (21, 8), (5, 4), (31, 12), (31, 14), (63, 14), (21, 13), (47, 11)])
+@pytest.mark.parametrize("k,m", [(31, 10), (63, 10), (15, 7), (12, 5), (32, 10), (21, 8), (5, 4), (31, 12), (31, 14), (63, 14), (21, 13), (47, 11), (63, 15), (31, 15), (16, 15)])
 def test_minimizer_function_matches_oracle(L, k, m):
     rng = np.random.default_rng(k * 100 + m)
     seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 600).tobytes())
@@ -196,7 +196,7 @@ def test_suggested_minimizer_size_grows_with_the_job(L):
     f = L.dskgpu_suggest_minimizer_size
     assert f(0, 31) == 10 and f(100_000_000, 31) == 10 and f(400_000_000, 31) == 11 and f(3_000_000_000, 31) == 12
     assert f(30_000_000, 63) == 10 and f(100_000_000, 63) == 12 and f(293_000_000, 63) == 14
-    assert f(72_000_000_000, 31) == 14 and f(72_000_000_000, 63) == 14
+    assert f(72_000_000_000, 31) == 14 and f(6_600_000_000, 63) == 14 and f(52_800_000_000, 63) == 15
     assert f(72_000_000_000, 11) == 10 and f(10, 5) == 4                      # clipped to k-1 (ConfigurationAlgorithm.cpp:249-251)
 
 

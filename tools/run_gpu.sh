@@ -32,6 +32,22 @@ for step in "$@"; do
                 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$kn" -s "$sk" -c 1 -f -o "$OUT/ncu_$kn" python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/ncu_$kn.log" 2>&1; echo "ncu $kn exit $?"
               done; ls -la "$OUT" ;;
     cli)      timeout 900 bash tools/run_cli_check.sh "$OUT" ;;
+    proxy)    # one GPU standing in for one of the 8 ranks of configs[2]/[3]: same k-mers per rank, 2^19 fine bins = the k-mers per bin
+              # of 2^22 bins at 8 GPUs.  PROXY_RUNS="k:m:fine ..."
+              for r in ${PROXY_RUNS:-31:14:19 63:14:19 63:13:19 63:15:22}; do
+                IFS=: read -r pk pm pf <<< "$r"
+                DSKGPU_FINE_LOG2=$pf timeout 600 python bench.py --kmer-size $pk --genome 375000000 --coverage 30 --device-synth --minimizer-size $pm --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/proxy_k${pk}_m${pm}_f${pf}.json" 2> "$OUT/proxy_k${pk}_m${pm}_f${pf}.err"
+                python - "$OUT/proxy_k${pk}_m${pm}_f${pf}.json" <<'PYEOF'
+import json, sys
+for line in open(sys.argv[1]):
+    if line.startswith('{'):
+        d = json.loads(line)
+        print(sys.argv[1], '%.1f G/s %.1f ms' % (d['value'], d['ms_per_step']), {k: round(v, 1) for k, v in d['stage_ms'].items()},
+              {k: d['engine'][k] for k in ('log2_bins', 'partitions', 'smem_splits', 'hash_groups', 'sampled_density')}, d['checks'])
+PYEOF
+                tail -2 "$OUT/proxy_k${pk}_m${pm}_f${pf}.err"
+              done ;;
+    pymin)    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "minimizer_sizes or tiny_smem or record_sub or fine_histogram or heavy" > "$OUT/pytest_min.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_min.log"; tail -6 "$OUT/pytest_min.log" ;;
     *)        echo "unknown step $step" ;;
   esac
 done
