@@ -13,6 +13,7 @@
 #pragma once
 #include <cmath>
 #include "kmer_bits.cuh"
+#include "kmer_wide.cuh"
 #include "superk.cuh"
 
 namespace dsk {
@@ -415,7 +416,11 @@ __global__ void __launch_bounds__(256) k_expand_keys(const u64* __restrict__ rec
         if (i < rec_end) {
             const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
             if constexpr (RW == 2) { ulonglong2 v = __ldg(src + i); r[0] = v.x; r[1] = v.y; }
-            else { ulonglong2 v = __ldg(src + 2 * i), u = __ldg(src + 2 * i + 1); r[0] = v.x; r[1] = v.y; r[2] = u.x; r[3] = u.y; }
+            else if constexpr (RW == 4) { ulonglong2 v = __ldg(src + 2 * i), u = __ldg(src + 2 * i + 1); r[0] = v.x; r[1] = v.y; r[2] = u.x; r[3] = u.y; }
+            else {
+#pragma unroll
+                for (int x = 0; x < RW / 2; x++) { const ulonglong2 v = __ldg(src + (RW / 2) * i + x); r[2 * x] = v.x; r[2 * x + 1] = v.y; }
+            }
             nk = (int)((r[RW - 1] >> 8) & 0xFFu);
         }
         u32 inc = (u32)nk;
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(256) k_expand_keys(const u64* __restrict__ rec
         u64 pos = base + inc - nk;
         const u32 bank = (u32)(r[RW - 1] & 0xFu);
         Kmer<KW> f, rc;
-        if constexpr (KW == 1) f = rec_first_kmer1(r, k); else f = rec_first_kmer2(r, k);
+        if constexpr (KW == 1) f = rec_first_kmer1(r, k); else if constexpr (KW == 2) f = rec_first_kmer2(r, k); else f = rec_first_kmer<KW>(r, k);
         rc = kmer_revcomp(f, k);
         for (int j = 0; j < nk; j++) {
             if (j) kmer_roll(f, rc, rec_base<RW>(r, k - 1 + j), k);

@@ -111,6 +111,9 @@ struct dskgpu_ctx {
     if (ctx) ctx->err = b_; g_last_error = b_; return DSKGPU_ERR_CUDA; } } while (0)
 #define FAIL(code, ...) do { char b_[512]; snprintf(b_, sizeof b_, __VA_ARGS__); if (ctx) ctx->err = b_; g_last_error = b_; return (code); } while (0)
 #define LAUNCHED() do { ctx->st.gpu_launches++; } while (0)
+// key width dispatch: KW = 64-bit words per k-mer (1: k < 32, 2: k < 64, 3: k < 96, 4: k < 128 -- Integer.hpp:463, KSIZE_LIST "32 64 96 128")
+#define KW_DISPATCH(ctx_, fn, ...) ((ctx_)->KW == 1 ? fn<1>(__VA_ARGS__) : (ctx_)->KW == 2 ? fn<2>(__VA_ARGS__) : (ctx_)->KW == 3 ? fn<3>(__VA_ARGS__) : fn<4>(__VA_ARGS__))
+static inline int kw_of(int k) { return k < 32 ? 1 : k < 64 ? 2 : k < 96 ? 3 : 4; }
 // every ABI entry point runs on the context's device, whatever the caller's current device is (several contexts, one per
 // GPU, can live in one process: host/GpuSortingCount.hpp with DSKGPU_DEVICES, dskgpu_multi_finish)
 static inline void use_device(const dskgpu_ctx* ctx) { int d = -1; if (cudaGetDevice(&d) != cudaSuccess || d != ctx->cfg.device) cudaSetDevice(ctx->cfg.device); }
@@ -206,7 +209,11 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     if (m < 2) m = 2;
     if (m > ctx->k) m = ctx->k;
     ctx->m = m;
-    ctx->KW = (ctx->k < 32) ? 1 : 2;                 // Integer.hpp:463 : span = first K in KSIZE_LIST with k < K
+    ctx->KW = kw_of(ctx->k);                         // Integer.hpp:463 : span = first K in KSIZE_LIST with k < K
+    // spans 96 / 128: 192/256-bit keys have no single-instruction claim (the widest CAS is 128 bits), so
+    // their partitions are counted by the sort path -- what the reference itself does for every partition that does not
+    // take its hash path (PartitionsByVectorCommand, K/PartitionsCommand.cpp:1600-1805)
+    if (ctx->KW > 2) ctx->cfg.count_mode = DSKGPU_COUNT_SORT;
     ctx->RW = 2 * ctx->KW;
     ctx->NB = (cfg->per_bank_counts && cfg->nb_banks > 1) ? cfg->nb_banks : 1;
     if (cfg->push_chunk_bytes > 0) ctx->push_chunk = (size_t)std::max(cfg->push_chunk_bytes, 64);
@@ -245,18 +252,26 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     if (ctx->NB > 1 && cfg->bank_histograms && (rc = ensure(ctx, ctx->bank_hist, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * (size_t)ctx->NB))) return rc;
     // dynamic shared memory opt-in for the one-sweep kernels
     const int smem1 = RsCfg<1>::TILE * 8 + RsCfg<1>::TILE * 4, smem2 = RsCfg<2>::TILE * 16 + RsCfg<2>::TILE * 4;
+    const int smem3 = RsCfg<3>::TILE * 24 + RsCfg<3>::TILE * 4, smem4 = RsCfg<4>::TILE * 32 + RsCfg<4>::TILE * 4;
     CK(cudaFuncSetAttribute(k_rs_onesweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CK(cudaFuncSetAttribute(k_rs_onesweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     CK(cudaFuncSetAttribute(k_rs_onesweep<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
     CK(cudaFuncSetAttribute(k_rs_onesweep<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    CK(cudaFuncSetAttribute(k_rs_onesweep<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    CK(cudaFuncSetAttribute(k_rs_onesweep<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    CK(cudaFuncSetAttribute(k_rs_onesweep<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    CK(cudaFuncSetAttribute(k_rs_onesweep<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
     // shared-memory counting path: CS_CTAS_PER_SM CTAs share the SM's shared memory; each table takes what is left of its share
     {
-        int max_optin = 0, per_sm = 0, nsm = 0, reserved = 0;
+        int nsm = 0;
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device));
+        ctx->num_sms = nsm > 0 ? nsm : 148;
+    }
+    if (ctx->KW <= 2) {
+        int max_optin = 0, per_sm = 0, reserved = 0;
         CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
         CK(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device));
         CK(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, cfg->device));
-        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device));
-        ctx->num_sms = nsm > 0 ? nsm : 148;
         // the kernel variant this context will launch: 64/128-bit keys x (one summed count | one count per bank)
         const bool mb = ctx->NB > 1;
         const void* fn = ctx->KW == 1 ? (mb ? (const void*)k_count_smem<1, true> : (const void*)k_count_smem<1, false>)
@@ -404,7 +419,7 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
     int rc;
     if ((rc = ensure(ctx, ctx->tabs, ntiles * sizeof(TileTab)))) return rc;
     if ((rc = ensure(ctx, ctx->tin, ntiles * sizeof(TileIn)))) return rc;
-    if ((rc = ensure(ctx, ctx->codes, std::max<u64>(n, 2 * ctx->push_chunk) + 64 + SK_TP + 1024, true, 64))) return rc;
+    if ((rc = ensure(ctx, ctx->codes, std::max<u64>(n, 2 * ctx->push_chunk) + 128 + SK_TP + 1024, true, 128))) return rc;   // (128 >= k - 1: the carry)
     // record capacity: worst case one record per position of this chunk on top of what is known to be used
     // The host may run two chunks ahead of the device: a chunk still in flight is charged at its worst case (one record per
     // byte) until its probe (the record counter copied out behind its kernels) has landed.
@@ -451,12 +466,13 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
     }
     {
         SpanGuard g(ctx, SPAN_SUPERK);
-        const unsigned gk = (unsigned)((n + 64 + SK_TP - 1) / SK_TP);
+        const unsigned gk = (unsigned)((n + (ctx->KW <= 2 ? 64 : 128) + SK_TP - 1) / SK_TP);
         const int bank = ctx->NB > 1 ? ctx->cur_bank : 0;
-        if (ctx->KW == 1) k_superkmers<1><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p, (u32)ctx->nb_passes, (u32)ctx->pass_id, META_BIN_BITS - ctx->fine_log2);
-        else              k_superkmers<2><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p, (u32)ctx->nb_passes, (u32)ctx->pass_id, META_BIN_BITS - ctx->fine_log2);
+#define SUPERK_LAUNCH(W_) k_superkmers<W_><<<gk, SK_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, ctx->m, bank, (u64*)ctx->recs.p, (u32*)ctx->meta.p, ctx->rec_cap, (Counters*)ctx->ctr.p, (unsigned long long*)ctx->bin_hist.p, (u32)ctx->nb_passes, (u32)ctx->pass_id, META_BIN_BITS - ctx->fine_log2)
+        if (ctx->KW == 1) SUPERK_LAUNCH(1); else if (ctx->KW == 2) SUPERK_LAUNCH(2); else if (ctx->KW == 3) SUPERK_LAUNCH(3); else SUPERK_LAUNCH(4);
+#undef SUPERK_LAUNCH
         LAUNCHED();
-        k_scan_carry<<<1, 64, 0, ctx->stream>>>((u8*)ctx->codes.p, ss, ctx->k); LAUNCHED();
+        k_scan_carry<<<1, 128, 0, ctx->stream>>>((u8*)ctx->codes.p, ss, ctx->k); LAUNCHED();
     }
     {
         const int sl = ctx->probe_slot; ctx->probe_slot = (sl + 1) & 3;
@@ -649,8 +665,9 @@ static int sort_solid(dskgpu_ctx* ctx, bool full, int start_buf)
     int lg = 1; while (((u64)1 << lg) < n) lg++;
     const int msd = (lg + 7) / 8;
     ctx->sort_fixup = false;
-    if (full || getenv("DSKGPU_SORT_FULL") || msd + 1 >= npass_full)
+    if (KW > 2 || full || getenv("DSKGPU_SORT_FULL") || msd + 1 >= npass_full)
         return radix_sort<KW, true>(ctx, kk, vv, n, npass_full, &ctx->solid_buf, 0, start_buf);
+    if constexpr (KW <= 2) {
     int r = start_buf, rc;
     if ((rc = radix_sort<KW, true>(ctx, kk, vv, n, npass_full, &r, npass_full - msd, start_buf))) return rc;
     Counters* ctr = (Counters*)ctx->ctr.p;
@@ -662,6 +679,7 @@ static int sort_solid(dskgpu_ctx* ctx, bool full, int start_buf)
     ctx->sort_src = r; ctx->solid_buf = r ^ 1; ctx->sort_fixup = true;
     CK(cudaMemcpyAsync(ctx->h_nrec_probe + 7, &ctr->sort_fallback, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -716,10 +734,21 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
     const SolidityParams sp = make_sp(ctx);
     int rc;
     const int mode = ctx->cfg.count_mode;
+    const u64 sort_cap = (u64)1 << 28;                             // keys per sort-path group
+    if (mode == DSKGPU_COUNT_SORT || KW > 2) {                     // (wide spans: always -- dskgpu_create forces the mode)
+        size_t p = 0;
+        while (p < np) {
+            size_t q = p; u64 km = 0;
+            while (q < np && (q == p || km + pkm[q] <= sort_cap)) { km += pkm[q]; q++; }
+            if ((rc = count_by_sort<KW>(ctx, recs, off[p], off[q], km, out_cap))) return rc;
+            p = q;
+        }
+        return 0;
+    }
+    if constexpr (KW <= 2) {
     const int log2s = ctx->cfg.hash_log2_slots > 0 ? std::max(10, ctx->cfg.hash_log2_slots) : 23;
     u64 nslots = (u64)1 << log2s;
     const double load_max = 0.6;
-    const u64 sort_cap = (u64)1 << 28;                             // keys per sort-path group
 
     auto init_table = [&](u64 slots) -> int {
         int rc2;
@@ -766,16 +795,6 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
         return 0;
     };
 
-    if (mode == DSKGPU_COUNT_SORT) {
-        size_t p = 0;
-        while (p < np) {
-            size_t q = p; u64 km = 0;
-            while (q < np && (q == p || km + pkm[q] <= sort_cap)) { km += pkm[q]; q++; }
-            if ((rc = count_by_sort<KW>(ctx, recs, off[p], off[q], km, out_cap))) return rc;
-            p = q;
-        }
-        return 0;
-    }
     // hash (forced) or auto.  The table is sized once; groups of consecutive partitions are sized so that the
     // estimated number of distinct k-mers stays under load_max * nslots.  The distinct/total ratio r comes from the
     // density sample (or is measured on a first group sized for the worst case r = 1).  It is an estimate: a group whose
@@ -824,6 +843,7 @@ static int count_all(dskgpu_ctx* ctx, const u64* recs, const std::vector<u64>& p
     };
     if ((rc = run_range(0, np, r))) return rc;
     CK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -909,7 +929,8 @@ static int stage_totals(dskgpu_ctx* ctx)
     if (ctx->totals_done) return 0;
     Counters* ctr = (Counters*)ctx->ctr.p;
     if (ctx->stream_open) close_stream(ctx);
-    { int rc = ctx->KW == 1 ? queue_sample<1>(ctx) : queue_sample<2>(ctx); if (rc) return rc; }
+    // (wide spans: no density sample -- the sort path needs no table sizing; the solid-set buffers start from the default share)
+    if (ctx->KW <= 2) { int rc = ctx->KW == 1 ? queue_sample<1>(ctx) : queue_sample<2>(ctx); if (rc) return rc; }
     {
         // packed bin histogram: could a record field have wrapped?  (test hook: a lower limit exercises the exact rebuild)
         unsigned long long lim = 1ULL << 28;
@@ -966,7 +987,7 @@ static int fold_local_hist(dskgpu_ctx* ctx, const void** d_hist)
 static bool use_smem_path(const dskgpu_ctx* ctx)
 {
     const int mode = ctx->cfg.count_mode;
-    return ctx->NB <= CS_MAX_BANKS && (mode == DSKGPU_COUNT_AUTO || mode == DSKGPU_COUNT_SMEM) && ctx->smem_cap >= 64;
+    return ctx->KW <= 2 && ctx->NB <= CS_MAX_BANKS && (mode == DSKGPU_COUNT_AUTO || mode == DSKGPU_COUNT_SMEM) && ctx->smem_cap >= 64;
 }
 
 // Shared-memory path limits.  One pass over a partition takes `fit` k-mers (table filled to 75 % at the sampled density);
@@ -1006,7 +1027,7 @@ static u64 plan_target_kmers(const dskgpu_ctx* ctx, u64 global_kmers)
         // bulk copy that runs under the previous job's sweep
         if (ctx->g_total_recs > 0 && ctx->cfg.count_mode == DSKGPU_COUNT_AUTO && ctx->cfg.smem_table_slots <= 0) {
             const double avg_nk = (double)ctx->g_total_kmers / (double)ctx->g_total_recs;
-            t = std::min(t, (double)(ctx->KW == 1 ? cs_bufrec<1>() : cs_bufrec<2>()) * avg_nk * 0.93);
+            t = std::min(t, (double)(ctx->KW == 1 ? cs_bufrec<1>() : cs_bufrec<2>()) * avg_nk * 0.93);   // (KW <= 2 here: use_smem_path)
         }
         return (u64)std::max(t, 64.0);
     }
@@ -1316,7 +1337,8 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
             if ((rc = ensure(ctx, ctx->svals[i], out_cap * 4))) return rc;
         }
         SpanGuard g(ctx, SPAN_COUNT);
-        if (ctx->nl_me) {
+        if constexpr (KW > 2) { if (ctx->nl_me) FAIL(DSKGPU_ERR_STATE, "internal: shared-memory jobs planned for a wide span"); }
+        else if (ctx->nl_me) {
             // occupancy picks the path of every partition (K/SortingCountAlgorithm.cpp:1489-1497): the planner already put
             // the partitions within reach of a few split passes first.  A partition expected to fill the table beyond 75 %
             // (k-mers x sampled density) starts as 2^split0 sub-passes over hash residues (computed by the kernel from gk_q);
@@ -1373,8 +1395,9 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
                 hp = (const u64*)ctx->hrecs.p;
             }
             if (hrec) {
-                if (heavy_by_buckets(ctx)) rc = count_by_buckets<KW>(ctx, hp, ctx->heavy_recs, ctx->heavy_kmers, out_cap);
-                else rc = count_all<KW>(ctx, hp, ctx->heavy_recs, ctx->heavy_kmers, out_cap);
+                bool buckets = false;
+                if constexpr (KW <= 2) { if (heavy_by_buckets(ctx)) { buckets = true; rc = count_by_buckets<KW>(ctx, hp, ctx->heavy_recs, ctx->heavy_kmers, out_cap); } }
+                if (!buckets) rc = count_all<KW>(ctx, hp, ctx->heavy_recs, ctx->heavy_kmers, out_cap);
                 if (rc) return rc;
             }
         }
@@ -1510,8 +1533,8 @@ int dskgpu_finish(dskgpu_ctx* ctx)
     if (!ctx) return DSKGPU_ERR_ARG;
     use_device(ctx);
     if (ctx->state != 0) FAIL(DSKGPU_ERR_STATE, "finish called twice");
-    if (ctx->cfg.world_size > 1) return ctx->KW == 1 ? finish_owned<1>(ctx) : finish_owned<2>(ctx);
-    return ctx->KW == 1 ? finish_single<1>(ctx) : finish_single<2>(ctx);
+    if (ctx->cfg.world_size > 1) return KW_DISPATCH(ctx, finish_owned, ctx);
+    return KW_DISPATCH(ctx, finish_single, ctx);
 }
 
 // ---- multi-GPU exchange ----------------------------------------------------------------------------------------------
@@ -1664,7 +1687,7 @@ int dskgpu_xchg_scatter(dskgpu_ctx* ctx, const void* d_recv_counts, const void* 
     if (W < 2) FAIL(DSKGPU_ERR_STATE, "xchg_scatter needs world_size > 1");
     if (!ctx->xchg_planned || ctx->peer_recv.size() != (size_t)W) FAIL(DSKGPU_ERR_STATE, "xchg_scatter before xchg_ensure_recv / xchg_set_peers");
     if (ctx->precs.cap < ctx->h_hdr->need_recs[me] * (u64)ctx->RW * 8) FAIL(DSKGPU_ERR_STATE, "receive buffer smaller than the planned layout");
-    int rc = ctx->KW == 1 ? stage_scatter<1>(ctx) : stage_scatter<2>(ctx);
+    int rc = KW_DISPATCH(ctx, stage_scatter, ctx);
     if (rc) return rc;
     if ((rc = stage_bases(ctx, d_recv_counts, d_send_matrix))) return rc;
     u64 remote = 0;
@@ -1731,7 +1754,7 @@ int dskgpu_suggest_nb_passes(uint64_t expected_kmers, int kmer_size, int world_s
         if (cur >= 0 && cur != device) cudaSetDevice(cur);
         hbm_bytes = fr;
     }
-    const int KW = kmer_size < 32 ? 1 : 2;
+    const int KW = kw_of(kmer_size);
     const double s = kmer_size < 32 ? 9.0 : 18.0;
     const double per_kmer = ((world_size > 1 ? 3.0 : 2.0) * 16.0 * KW + 4.0) / s + 2.0 * 0.10 * (8.0 * KW + 4.0);
     const double fixed = 2.0 * 1024 * 1024 * 1024;
@@ -1864,7 +1887,7 @@ int dskgpu_recount(dskgpu_ctx* ctx, const int64_t* abundance_min)
     const u64 cap_request = ctx->st.kmers_nb_distinct + 1024;
     int rc = reset_count_state(ctx); if (rc) return rc;
     ctx->state = 0;
-    rc = ctx->KW == 1 ? stage_count<1>(ctx, cap_request) : stage_count<2>(ctx, cap_request);
+    rc = KW_DISPATCH(ctx, stage_count, ctx, cap_request);
     if (rc) ctx->state = 2;                                        // failed: only reset / destroy are valid now
     return rc;
 }

@@ -1,8 +1,9 @@
 // kmer_wide.cuh -- N-word k-mer logic for the spans beyond 64 (KSIZE_LIST 96 / 128: k <= 95 in three 64-bit words,
-// k <= 127 in four).  Groundwork: the device path still rejects k >= 64 (dskgpu_create), nothing in a
-// kernel uses this header yet.  Like kmer_bits.cuh everything is a pure host+device function, pinned on the CPU
-// (tests/test_host_logic.py::test_wide_kmer_logic_matches_the_wide_oracle) against oracle/liboracle_wide.so, which is
-// itself pinned against the reference built with KSIZE_LIST "32 64 96 128".
+// k <= 127 in four).  The wide spans run on the device through the sort path (k_superkmers<3|4>, partition
+// scatter, k_expand_keys, one-sweep radix sort, k_rle_emit); the overloads at the end of this header plug the N-word logic
+// into the names the kernels use (kmer_roll, kmer_revcomp, kmer_less, ...).  Like kmer_bits.cuh everything is a pure
+// host+device function, pinned on the CPU (tests/test_host_logic.py::test_wide_kmer_logic_matches_the_wide_oracle) against
+// oracle/liboracle_wide.so, which is itself pinned against the reference built with KSIZE_LIST "32 64 96 128".
 //
 // Reference semantics restated: LargeInt<precision> value = sum code_i * 4^(k-1-i) (K/Model.hpp:636-657), compared most
 // significant word first (LargeInt.hpp:502-509); rolling update K/Model.hpp:877-884; revcomp LargeInt.hpp:722-735.
@@ -103,6 +104,26 @@ template <int KW> DSK_HD u64 kmern_hash(const Kmer<KW>& a)
 #pragma unroll
     for (int i = 0; i < KW; i++) h = mix64(h ^ a.w[i]);
     return h;
+}
+
+// ---- the names the kernels use, for the wide key types (Kmer<1> / Kmer<2> keep their hand-written versions in kmer_bits.cuh) ----
+DSK_HD bool kmer_less(const Kmer<3>& a, const Kmer<3>& b) { return kmern_less<3>(a, b); }
+DSK_HD bool kmer_less(const Kmer<4>& a, const Kmer<4>& b) { return kmern_less<4>(a, b); }
+DSK_HD bool kmer_eq(const Kmer<3>& a, const Kmer<3>& b) { return kmern_eq<3>(a, b); }
+DSK_HD bool kmer_eq(const Kmer<4>& a, const Kmer<4>& b) { return kmern_eq<4>(a, b); }
+DSK_HD void kmer_roll(Kmer<3>& f, Kmer<3>& r, int c, int k) { kmern_roll<3>(f, r, c, k); }
+DSK_HD void kmer_roll(Kmer<4>& f, Kmer<4>& r, int c, int k) { kmern_roll<4>(f, r, c, k); }
+DSK_HD Kmer<3> kmer_revcomp(const Kmer<3>& f, int k) { return kmern_revcomp<3>(f, k); }
+DSK_HD Kmer<4> kmer_revcomp(const Kmer<4>& f, int k) { return kmern_revcomp<4>(f, k); }
+DSK_HD u64 kmer_hash(const Kmer<3>& a) { return kmern_hash<3>(a); }
+DSK_HD u64 kmer_hash(const Kmer<4>& a) { return kmern_hash<4>(a); }
+
+// first k-mer (forward strand) of a record, any key width
+template <int KW> DSK_HD Kmer<KW> rec_first_kmer(const u64* r, int k)
+{
+    if constexpr (KW == 1) return rec_first_kmer1(r, k);
+    else if constexpr (KW == 2) return rec_first_kmer2(r, k);
+    else return recn_kmer_at<KW, 2 * KW>(r, 0, k);
 }
 
 }  // namespace dsk

@@ -26,13 +26,15 @@ constexpr u32 RS_FLAG_AGG = 1u << 30, RS_FLAG_INC = 2u << 30, RS_MASK = (1u << 3
 #ifndef RS_MINB
 #define RS_MINB 4
 #endif
-template <int KW> struct RsCfg { static constexpr int ITEMS = (KW == 1) ? RS_ITEMS1 : RS_ITEMS2; static constexpr int TILE = RS_THREADS * ITEMS; };
+template <int KW> struct RsCfg { static constexpr int ITEMS = (KW == 1) ? RS_ITEMS1 : (KW == 2) ? RS_ITEMS2 : 4; static constexpr int TILE = RS_THREADS * ITEMS; };
 
 template <int KW> __device__ __forceinline__ u32 rs_digit(const u64* key, int pass)
 {
     // no dynamic indexing: it would push the caller's key registers into local memory
     u64 w = key[0];
     if constexpr (KW == 2) w = (pass & 8) ? key[1] : key[0];
+    if constexpr (KW == 3) { const int q = pass >> 3; w = q == 0 ? key[0] : q == 1 ? key[1] : key[2]; }
+    if constexpr (KW == 4) { const int q = pass >> 3; w = q == 0 ? key[0] : q == 1 ? key[1] : q == 2 ? key[2] : key[3]; }
     return (u32)(w >> ((pass & 7) * 8)) & 0xFFu;
 }
 

@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_emit(const u8* __restrict
 // after the super-k-mer pass: keep the last k-1 codes as the carry of the next chunk
 __global__ void k_scan_carry(u8* codes, StreamState* ss, int k)
 {
-    __shared__ u8 s[64];
+    __shared__ u8 s[128];                                          // k - 1 <= 126 codes, one per thread (launched with 128 threads)
     u64 total = ss->total;
     u64 c = (total < (u64)(k - 1)) ? total : (u64)(k - 1);
     if (threadIdx.x < c) s[threadIdx.x] = codes[total - c + threadIdx.x];

@@ -20,7 +20,8 @@ namespace dsk {
 constexpr int SK_THREADS = 256;
 constexpr int SK_PPT = 8;                         // positions per thread
 constexpr int SK_TP = SK_THREADS * SK_PPT;        // 2048 positions per tile
-constexpr int SK_HALO = 64;                       // >= k-1
+constexpr int SK_HALO = 64;                       // >= k-1 (k <= 63); the wide spans (k <= 127) take 128: sk_halo<KW>()
+template <int KW> DSK_HD constexpr int sk_halo() { return KW <= 2 ? SK_HALO : 128; }
 constexpr u32 SK_NOMIN = 0xFFFFFFFFu;
 
 struct Counters {
@@ -65,9 +66,10 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
                                                            u32 nb_passes, u32 pass_id, int fine_shift /*24 - fine_log2*/)
 {
     constexpr int RW = 2 * KW;
-    __shared__ u64 s_pk[SK_TP / 32 + 8];                         // 2-bit bases, MSB first, 32 per word
-    __shared__ u64 s_bad[(SK_TP + SK_HALO) / 64 + 2];            // invalid flags, MSB first, 64 per word
-    __shared__ u32 s_mv[SK_TP + SK_HALO + (SK_TP + SK_HALO) / 8 + 8];
+    constexpr int HALO = sk_halo<KW>();
+    __shared__ u64 s_pk[(SK_TP + HALO) / 32 + 6];                // 2-bit bases, MSB first, 32 per word
+    __shared__ u64 s_bad[(SK_TP + HALO) / 64 + 2 + (KW > 2 ? 1 : 0)];   // invalid flags, MSB first, 64 per word
+    __shared__ u32 s_mv[SK_TP + HALO + (SK_TP + HALO) / 8 + 8];
     __shared__ u32 s_start[SK_TP / 32];                          // super-k-mer run starts, MSB first
     __shared__ u32 s_brk[SK_TP / 32 + 9];                        // run start or invalid window
     __shared__ u32 s_last[SK_THREADS];                           // minimizer of each thread's last window
@@ -96,9 +98,9 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
         reinterpret_cast<u8*>(s_bad)[(ti >> 3) * 8 + (7 - (ti & 7))] = (u8)b8;
     };
     load8(t);
-    if (t < SK_HALO / 8) load8(SK_THREADS + t);
-    if (t < 6) s_pk[(SK_TP + SK_HALO) / 32 + t] = 0;
-    if (t < 2) s_bad[(SK_TP + SK_HALO) / 64 + t] = ~0ULL;
+    if (t < HALO / 8) load8(SK_THREADS + t);
+    if (t < 6) s_pk[(SK_TP + HALO) / 32 + t] = 0;
+    if (t < 2 + (KW > 2 ? 1 : 0)) s_bad[(SK_TP + HALO) / 64 + t] = ~0ULL;
     if (t < 9) s_brk[SK_TP / 32 + t] = 0xFFFFFFFFu;
     if (t == 0) s_nvalid = 0;
     __syncthreads();
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
         }
     };
     mvals8(t);
-    if (t < SK_HALO / 8) mvals8(SK_THREADS + t);
+    if (t < HALO / 8) mvals8(SK_THREADS + t);
     __syncthreads();
 
     // ---- 3. sliding minimum over w m-mers for my 8 windows, validity, run-start flags ----------------------
@@ -158,11 +160,23 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
     u32 validmask = 0;                                            // bit (7-j): window j is a valid k-mer
     {
         u64 b0 = getbad64(p0), b1 = getbad64(p0 + 64);
+        if constexpr (KW <= 2) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            u64 x = j ? ((b0 << j) | (b1 >> (64 - j))) : b0;
-            bool ok = ((x >> (64 - k)) == 0) && (tile0 + p0 + j < limit);
-            validmask |= (ok ? 1u : 0u) << (7 - j);
+            for (int j = 0; j < 8; j++) {
+                u64 x = j ? ((b0 << j) | (b1 >> (64 - j))) : b0;
+                bool ok = ((x >> (64 - k)) == 0) && (tile0 + p0 + j < limit);
+                validmask |= (ok ? 1u : 0u) << (7 - j);
+            }
+        } else {
+            // 64 < k <= 127: the window's first 64 flags, then its last k - 64
+            const u64 b2 = getbad64(p0 + 128);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const u64 x = j ? ((b0 << j) | (b1 >> (64 - j))) : b0;
+                const u64 y = j ? ((b1 << j) | (b2 >> (64 - j))) : b1;
+                const bool ok = x == 0 && (k == 64 || (y >> (128 - k)) == 0) && (tile0 + p0 + j < limit);
+                validmask |= (ok ? 1u : 0u) << (7 - j);
+            }
         }
     }
     s_last[t] = ((validmask & 1u) ? mn[7] : SK_NOMIN);
@@ -257,9 +271,12 @@ __global__ void __launch_bounds__(SK_THREADS) k_superkmers(const u8* __restrict_
         const u64 ri = goff + i;
         if constexpr (RW == 2) {
             reinterpret_cast<ulonglong2*>(recs)[ri] = make_ulonglong2(rw[0], rw[1]);
-        } else {
+        } else if constexpr (RW == 4) {
             reinterpret_cast<ulonglong2*>(recs)[2 * ri] = make_ulonglong2(rw[0], rw[1]);
             reinterpret_cast<ulonglong2*>(recs)[2 * ri + 1] = make_ulonglong2(rw[2], rw[3]);
+        } else {
+#pragma unroll
+            for (int x = 0; x < RW / 2; x++) reinterpret_cast<ulonglong2*>(recs)[(RW / 2) * ri + x] = make_ulonglong2(rw[2 * x], rw[2 * x + 1]);
         }
         // fine histogram of the bins while the records are produced (fire-and-forget REDs under an ALU-bound kernel)
         const u32 bin = hmin >> (32 - META_BIN_BITS);
@@ -288,11 +305,20 @@ __global__ void __launch_bounds__(SC_THREADS) k_part_scatter(const u64* __restri
     ulonglong2* dst = reinterpret_cast<ulonglong2*>(out);
     for (u64 i = (u64)blockIdx.x * SC_THREADS + threadIdx.x; i < nrec; i += (u64)gridDim.x * SC_THREADS) {
         const u32 q = __ldg(bin2q + ((rec_meta[i] & META_BIN_MASK) >> bin_shift));
-        ulonglong2 a = src[(RW / 2) * i], b;
-        if constexpr (RW == 4) b = src[2 * i + 1];
-        const u64 d = atomicAdd(&cursor[q], 1ULL);
-        if constexpr (RW == 2) dst[d] = a;
-        else { dst[2 * d] = a; dst[2 * d + 1] = b; }
+        if constexpr (RW <= 4) {
+            ulonglong2 a = src[(RW / 2) * i], b;
+            if constexpr (RW == 4) b = src[2 * i + 1];
+            const u64 d = atomicAdd(&cursor[q], 1ULL);
+            if constexpr (RW == 2) dst[d] = a;
+            else { dst[2 * d] = a; dst[2 * d + 1] = b; }
+        } else {
+            ulonglong2 v[RW / 2];
+#pragma unroll
+            for (int x = 0; x < RW / 2; x++) v[x] = src[(RW / 2) * i + x];
+            const u64 d = atomicAdd(&cursor[q], 1ULL);
+#pragma unroll
+            for (int x = 0; x < RW / 2; x++) dst[(RW / 2) * d + x] = v[x];
+        }
     }
 }
 
@@ -339,7 +365,7 @@ __global__ void __launch_bounds__(MS_THREADS) k_msd_pass(const u64* __restrict__
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (u64 base = (u64)blockIdx.x * TILE; base < nrec; base += (u64)gridDim.x * TILE) {
         for (u32 i = t; i < MS_CAP; i += MS_THREADS) s_cnt[i] = 0;
-        u32 q[RPT]; ulonglong2 ra[RPT], rb[RPT];
+        u32 q[RPT]; ulonglong2 ra[RPT], rb[RPT], rx[KW > 2 ? RPT : 1][KW > 2 ? VPR - 2 : 1];   // rx: vectors 2 .. of a wide record
 #pragma unroll
         for (int j = 0; j < RPT; j++) {
             const u64 i = base + (u64)j * MS_THREADS + t;
@@ -347,7 +373,11 @@ __global__ void __launch_bounds__(MS_THREADS) k_msd_pass(const u64* __restrict__
             if (i < nrec) {
                 q[j] = FIRST ? __ldg(bin2q + ((src_key[i] & META_BIN_MASK) >> bin_shift)) : src_key[i];
                 ra[j] = in[VPR * i];
-                if constexpr (KW == 2) rb[j] = in[2 * i + 1];
+                if constexpr (KW >= 2) rb[j] = in[VPR * i + 1];
+                if constexpr (KW > 2) {
+#pragma unroll
+                    for (int x = 2; x < VPR; x++) rx[j][x - 2] = in[VPR * i + x];
+                }
             }
         }
         // bins of this tile start at the first child of the first record's parent (the input is grouped by parent, parents in
@@ -389,12 +419,20 @@ __global__ void __launch_bounds__(MS_THREADS) k_msd_pass(const u64* __restrict__
             if (r[j] != 0xFFFFFFFFu) {
                 const u32 p = s_off[g - g0] + r[j];
                 s_rec[(size_t)p * VPR] = ra[j];
-                if constexpr (KW == 2) s_rec[(size_t)p * VPR + 1] = rb[j];
+                if constexpr (KW >= 2) s_rec[(size_t)p * VPR + 1] = rb[j];
+                if constexpr (KW > 2) {
+#pragma unroll
+                    for (int x = 2; x < VPR; x++) s_rec[(size_t)p * VPR + x] = rx[j][x - 2];
+                }
                 s_key[p] = q[j];
             } else {                                               // a bin outside the window of this tile (tiny jobs): per-record cursor
                 const u64 pos = atomicAdd(&cursor[g], 1ULL);
                 out[VPR * pos] = ra[j];
-                if constexpr (KW == 2) out[2 * pos + 1] = rb[j];
+                if constexpr (KW >= 2) out[VPR * pos + 1] = rb[j];
+                if constexpr (KW > 2) {
+#pragma unroll
+                    for (int x = 2; x < VPR; x++) out[VPR * pos + x] = rx[j][x - 2];
+                }
                 if constexpr (!LAST) dst_key[pos] = q[j];
             }
         }
@@ -404,7 +442,11 @@ __global__ void __launch_bounds__(MS_THREADS) k_msd_pass(const u64* __restrict__
             const u32 qq = s_key[i], idx = (qq >> shift) - g0;
             const u64 pos = s_base[idx] + (u64)(i - s_off[idx]);
             out[VPR * pos] = s_rec[(size_t)i * VPR];
-            if constexpr (KW == 2) out[2 * pos + 1] = s_rec[(size_t)i * VPR + 1];
+            if constexpr (KW >= 2) out[VPR * pos + 1] = s_rec[(size_t)i * VPR + 1];
+            if constexpr (KW > 2) {
+#pragma unroll
+                for (int x = 2; x < VPR; x++) out[VPR * pos + x] = s_rec[(size_t)i * VPR + x];
+            }
             if constexpr (!LAST) dst_key[pos] = qq;
         }
         __syncthreads();                                           // staging buffer and counters are reused by the next tile

@@ -26,7 +26,7 @@ extern "C" {
 #define DSKGPU_HISTO_LEN     10001          /* bins 0..10000 (Histogram.hpp:92, length 10000) */
 #define DSKGPU_HISTO2D_DIM2  11             /* bins 0..10   (CountProcessorHistogram.hpp:173-184) */
 #define DSKGPU_MAX_MINIMIZER 15             /* -minimizer-size is clipped to this (32-bit m-mer arithmetic) */
-#define DSKGPU_MAX_KMER      63             /* KSIZE_LIST "32 64": k<32 -> 64-bit keys, k<64 -> 128-bit */
+#define DSKGPU_MAX_KMER      127            /* KSIZE_LIST "32 64 96 128": k<32 -> 64-bit keys, k<64 -> 128-bit, k<96 -> 192-bit, k<128 -> 256-bit */
 #define DSKGPU_NBINS         65536          /* minimizer bins packed into partitions at finish: the coarsest level ... */
 #define DSKGPU_NBINS_MAX     (1u << 24)     /* ... and the finest (jobs of tens of G k-mers); the level is picked from the job size */
 

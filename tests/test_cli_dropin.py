@@ -122,11 +122,36 @@ def test_cli_shell_goldens(tmp_path):
             assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]
 
 
+WIDEBIN = os.path.join(ROOT, "oracle", "_ref", "wide", "bin")
+WIDE_RUNS = [t for t in load_json("ref_runs_wide.json")["runs"] if t["name"] in ("c1_k64", "c1_k95", "longreads250_k96", "longreads250_k127", "c123_k71_all", "histo2d_k95")]
+
+
+@need_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(WIDEBIN, "dsk2ascii")), reason="reference readers built with KSIZE_LIST '32 64 96 128' not on this box (oracle/build_ref_wide.sh)")
+@pytest.mark.parametrize("t", WIDE_RUNS, ids=[t["name"] for t in WIDE_RUNS])
+def test_cli_wide_spans_against_committed_reference_outputs(t, tmp_path):
+    """spans 96 / 128 (64 <= k <= 127) through the C++ host side: GpuSortingCount<96> / <128>, dsk/solid items of 192 / 256
+    bits, read back by the unmodified reference dsk2ascii built with the reference's default KSIZE_LIST"""
+    tmp = str(tmp_path)
+    out = os.path.join(tmp, "gpu_out")
+    run([DSK_GPU] + dsk_args(t, out), tmp)
+    txt = out + ".txt"
+    run([os.path.join(WIDEBIN, "dsk2ascii"), "-file", out + ".h5", "-out", txt, "-verbose", "0"], tmp)
+    lines = sorted(open(txt, "rb").read().splitlines())
+    assert len(lines) == t["nb_solid"]
+    m = hashlib.sha256()
+    for ln in lines:
+        m.update(ln + b"\n")
+    assert m.hexdigest() == t["kmers_sha256"]
+    rows = open(out + ".histo").read().splitlines()
+    assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]
+
+
 @need_bins
 def test_cli_unhandled_kmer_size(tmp_path):
-    p = subprocess.run([DSK_GPU, "-file", os.path.join(INPUTS, "shortread.fasta"), "-kmer-size", "64", "-out", str(tmp_path / "x")],
+    p = subprocess.run([DSK_GPU, "-file", os.path.join(INPUTS, "shortread.fasta"), "-kmer-size", "128", "-out", str(tmp_path / "x")],
                        cwd=str(tmp_path), capture_output=True, text=True)
-    assert p.returncode != 0 and "unhandled kmer size 64" in (p.stdout + p.stderr)
+    assert p.returncode != 0 and "unhandled kmer size 128" in (p.stdout + p.stderr)
 
 
 AUTO = load_json("ref_runs_auto.json")["runs"]

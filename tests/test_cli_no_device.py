@@ -45,6 +45,6 @@ def test_options_outside_the_device_path_are_refused(tmp_path, opt, val, msg):
 
 
 def test_unhandled_kmer_size_message(tmp_path):
-    p = subprocess.run([DSK_GPU, "-file", os.path.join(INPUTS, "shortread.fasta"), "-kmer-size", "64", "-out", str(tmp_path / "x")],
+    p = subprocess.run([DSK_GPU, "-file", os.path.join(INPUTS, "shortread.fasta"), "-kmer-size", "128", "-out", str(tmp_path / "x")],
                        cwd=str(tmp_path), capture_output=True, text=True)
-    assert p.returncode != 0 and "unhandled kmer size 64" in (p.stdout + p.stderr)
+    assert p.returncode != 0 and "unhandled kmer size 128" in (p.stdout + p.stderr)

@@ -135,8 +135,8 @@ def test_dsk_perbank_literals(name):
 
 
 def test_unhandled_kmer_size():
-    with pytest.raises(RuntimeError, match="unhandled kmer size 64"):
-        SortingCountAlgorithm(BankStrings("ACGT" * 40), {"-kmer-size": 64}).execute()
+    with pytest.raises(RuntimeError, match="unhandled kmer size 128"):
+        SortingCountAlgorithm(BankStrings("ACGT" * 40), {"-kmer-size": 128}).execute()
 
 
 def test_empty_and_short_inputs():

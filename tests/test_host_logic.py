@@ -55,10 +55,10 @@ def test_no_device_fails_loudly(L):
 def test_unhandled_kmer_size(L):
     cfg = _lib.Config()
     L.dskgpu_config_default(C.byref(cfg))
-    cfg.kmer_size = 64
+    cfg.kmer_size = 128                                     # KSIZE_LIST "32 64 96 128": k <= 127
     h = C.c_void_p()
     assert L.dskgpu_create(C.byref(cfg), C.byref(h)) == -1
-    assert b"unhandled kmer size 64" in L.dskgpu_last_error(None)
+    assert b"unhandled kmer size 128" in L.dskgpu_last_error(None)
 
 
 def encode(seq):
