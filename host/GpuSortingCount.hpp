@@ -70,13 +70,29 @@ class GpuSortingCount : public Algorithm
 public:
     typedef typename Kmer<span>::Type  Type;
     typedef typename Kmer<span>::Count Count;
+    typedef ICountProcessor<span>      CountProcessor;
 
     /** Same meaning as SortingCountAlgorithm(IBank*, IProperties*) (K/SortingCountAlgorithm.cpp:119-133). */
     GpuSortingCount(IBank* bank, IProperties* params)
-        : Algorithm("dsk", -1, params), _bank(0), _storage(0), _ctx(0), _solidCounts(0), _nbPasses(1)
+        : Algorithm("dsk", -1, params), _bank(0), _storage(0), _ctx(0), _solidCounts(0), _nbPasses(1), _repartitor(0), _haveConfig(false)
     {
         setBank(bank);
         memset(&_st, 0, sizeof _st);
+    }
+
+    /** Same meaning as SortingCountAlgorithm(bank, config, repartitor, processors, params) (K/SortingCountAlgorithm.cpp:128-146,
+     *  the constructor G/src/gatb/debruijn/impl/Graph.cpp:399-407 uses): the caller brings the Configuration and the count
+     *  processors (ICountProcessor, G/src/gatb/kmer/api/ICountProcessor.hpp:105-173).  The repartitor is held and released
+     *  but not consulted: the device path plans its own partitions from exact minimizer-bin counts, and which partition a
+     *  k-mer lands in is unobservable to a count processor (it sees every distinct k-mer once, with its counts). */
+    GpuSortingCount(IBank* bank, const Configuration& config, Repartitor* repartitor, std::vector<CountProcessor*> processors, IProperties* params)
+        : Algorithm("dsk", config._nbCores, params), _bank(0), _storage(0), _config(config), _ctx(0), _solidCounts(0), _nbPasses(1),
+          _repartitor(0), _haveConfig(true)
+    {
+        setBank(bank);
+        setRepartitor(repartitor);
+        memset(&_st, 0, sizeof _st);
+        for (size_t i = 0; i < processors.size(); i++) addProcessor(processors[i]);
     }
 
     ~GpuSortingCount()
@@ -84,7 +100,17 @@ public:
         for (size_t i = 0; i < _ctxs.size(); i++) if (_ctxs[i]) dskgpu_destroy(_ctxs[i]);
         setBank(0);
         setStorage(0);
+        setRepartitor(0);
+        for (size_t i = 0; i < _processors.size(); i++) _processors[i]->forget();
     }
+
+    /** The plug-in surface of SortingCountAlgorithm (K/SortingCountAlgorithm.hpp:151-166).  With at least one processor the
+     *  device delivers EVERY distinct k-mer with its count and the processors decide what happens to it, exactly as in the
+     *  reference's fillSolidKmers_aux (K/SortingCountAlgorithm.cpp:1391-1607); without any, the default chain (histogram ->
+     *  solidity -> dump) runs fused on the device (the fast path `dsk_gpu` uses). */
+    size_t          getProcessorNumber() const       { return _processors.size(); }
+    CountProcessor* getProcessor(size_t idx)         { return _processors[idx]; }
+    void            addProcessor(CountProcessor* p)  { p->use(); _processors.push_back(p); }
 
     /** Same option parser as the reference (static, library code reused as is). */
     static IOptionsParser* getOptionsParser(bool mandatory = true) { return SortingCountAlgorithm<span>::getOptionsParser(mandatory); }
@@ -96,6 +122,7 @@ public:
     void execute()
     {
         configure();
+        if (!_processors.empty()) { executeWithProcessors(); return; }
         // The device scanner takes what dsk is fed in practice: FASTA (single- or multi-line) and 4-line FASTQ, plain or
         // gzip.  Whatever else BankFasta accepts (multi-line FASTQ, '+' lines inside FASTA, ...; BankFasta.cpp:485-572) is
         // rejected by the scanner, never mis-parsed; the same banks then go through the reference's own parser, sequence by
@@ -120,6 +147,10 @@ private:
     void setStorage(Storage* storage) { SP_SETATTR(storage); }
 
     Configuration     _config;
+    Repartitor*       _repartitor;
+    void setRepartitor(Repartitor* repartitor) { SP_SETATTR(repartitor); }
+    bool              _haveConfig;                 // the Configuration came with the constructor (5-argument form)
+    std::vector<CountProcessor*> _processors;      // plug-in mode when not empty
     bool              _viaIterator = false;        // second attempt: banks parsed by the reference's own reader
     dskgpu_ctx*       _ctx;                        // context of rank 0 (== _ctxs[0])
     std::vector<dskgpu_ctx*> _ctxs;                // one context per device (rank r = _ctxs[r])
@@ -140,30 +171,35 @@ private:
         IProperties* in = getInput();
         if (_bank == 0) { setBank(Bank::open(in->getStr(STR_URI_INPUT))); }
 
-        std::string output = in->get(STR_URI_OUTPUT) ? in->getStr(STR_URI_OUTPUT)
-                                                     : (in->getStr(STR_URI_OUTPUT_DIR) + "/" + System::file().getBaseName(_bank->getId()));
-        if (!System::file().doesExist(in->getStr(STR_URI_OUTPUT_DIR))) {
-            if (System::file().mkdir(in->getStr(STR_URI_OUTPUT_DIR), 0755) != 0) throw Exception("Error: can't create output directory");
+        const bool plugin = !_processors.empty();
+        // a default storage only when the caller did not bring processors of their own (K/SortingCountAlgorithm.cpp:534-575)
+        if (!plugin || !_haveConfig) {
+            std::string output = in->get(STR_URI_OUTPUT) ? in->getStr(STR_URI_OUTPUT)
+                                                         : (in->getStr(STR_URI_OUTPUT_DIR) + "/" + System::file().getBaseName(_bank->getId()));
+            if (!System::file().doesExist(in->getStr(STR_URI_OUTPUT_DIR))) {
+                if (System::file().mkdir(in->getStr(STR_URI_OUTPUT_DIR), 0755) != 0) throw Exception("Error: can't create output directory");
+            }
+            std::string storage_type = in->getStr(STR_STORAGE_TYPE);
+            StorageMode_e mode;
+            if (storage_type == "hdf5") mode = STORAGE_HDF5;
+            else if (storage_type == "file") mode = STORAGE_FILE;
+            else throw Exception("Error: unknown storage type specified: %s", storage_type.c_str());
+            setStorage(StorageFactory(mode).create(output, true, false));
         }
-        std::string storage_type = in->getStr(STR_STORAGE_TYPE);
-        StorageMode_e mode;
-        if (storage_type == "hdf5") mode = STORAGE_HDF5;
-        else if (storage_type == "file") mode = STORAGE_FILE;
-        else throw Exception("Error: unknown storage type specified: %s", storage_type.c_str());
-        setStorage(StorageFactory(mode).create(output, true, false));
-
-        // the reference's own configuration step: parses thresholds / solidity kind / banks, estimates the volume
-        ConfigurationAlgorithm<span> configAlgo(_bank, in);
-        configAlgo.execute();
-        _config = configAlgo.getConfiguration();
+        if (!_haveConfig) {
+            // the reference's own configuration step: parses thresholds / solidity kind / banks, estimates the volume
+            ConfigurationAlgorithm<span> configAlgo(_bank, in);
+            configAlgo.execute();
+            _config = configAlgo.getConfiguration();
+            _storage->getGroup(configAlgo.getName()).setProperty("xml", std::string("\n") + configAlgo.getInfo()->getXML());
+        }
         // passes / partitions are a property of the device path (set below, once the devices are known): no disk tier, one
         // ordered output collection per device and pass
         _config._nb_passes = 1;
         _config._nb_partitions = 1;
-        _storage->getGroup(configAlgo.getName()).setProperty("xml", std::string("\n") + configAlgo.getInfo()->getXML());
 
-        const bool histo2D = in->get(STR_HISTO2D) && in->getInt(STR_HISTO2D) != 0;
-        const bool histo1D = in->get(STR_HISTO) && in->getInt(STR_HISTO) != 0;
+        const bool histo2D = !plugin && in->get(STR_HISTO2D) && in->getInt(STR_HISTO2D) != 0;   // (plug-in mode: histograms are the processors' business)
+        const bool histo1D = !plugin && in->get(STR_HISTO) && in->getInt(STR_HISTO) != 0;
         if (histo2D) {                                              // K/SortingCountAlgorithm.cpp:604-620
             if (_bank->getBanks().size() < 2) throw Exception("There must be at least 2 input banks when using -histo2D");
         }
@@ -177,7 +213,7 @@ private:
         _histoName = histo1D ? base + ".histo" : std::string();
         _histo2DName = histo2D ? base + ".histo2D" : std::string();
 
-        if (in->getInt(STR_HISTOGRAM_MAX) != 10000)
+        if (!plugin && in->getInt(STR_HISTOGRAM_MAX) != 10000)
             throw Exception("the device histogram has the reference's default length (-histo-max 10000) only");
         if (in->getInt(STR_MINIMIZER_TYPE) != 0 || in->getInt(STR_REPARTITION_TYPE) != 0)
             throw Exception("-minimizer-type 1 / -repartition-type 1 are outside the device path (SURVEY.md 8(f)-4)");
@@ -224,6 +260,15 @@ private:
         c.bank_histograms = _autoPerBank ? 1 : 0;
         c.abundance_max = _config._abundance.empty() ? 2147483647LL : (long long)_config._abundance[0].getEnd();
         for (size_t i = 0; i < (size_t)DSKGPU_MAX_BANKS; i++) c.solid_vec[i] = (i < _config._solidVec.size()) ? (_config._solidVec[i] ? 1 : 0) : 1;
+        if (plugin) {
+            // every distinct k-mer goes to the processors, with its count: nothing is filtered or histogrammed on the device.
+            // A CountVector holds one count per bank (K/PartitionsCommand.cpp:540-541); the C ABI delivers one count per k-mer.
+            if (c.nb_banks != 1) throw Exception("count processors plugged into the device path see one count per k-mer: %d banks given (use the default processors)", (int)c.nb_banks);
+            c.solidity_kind = DSKGPU_SOLIDITY_SUM; c.per_bank_counts = 0; c.histo2d = 0; c.bank_histograms = 0;
+            for (size_t i = 0; i < (size_t)DSKGPU_MAX_BANKS; i++) c.abundance_min[i] = 1;
+            c.abundance_max = 2147483647LL;
+            _autoCutoff = false; _autoPerBank = false;
+        }
         // devices: DSKGPU_DEVICES = "all" | a count | a comma list of ordinals; default one device (DSKGPU_DEVICE, 0)
         std::vector<int> devs;
         const char* dl = getenv("DSKGPU_DEVICES");
@@ -504,6 +549,76 @@ private:
             collectPass(pass);
         }
         _solidCounts->flush();
+    }
+
+    // ---- plug-in mode: the loop of SortingCountAlgorithm::execute / fillSolidKmers (K/SortingCountAlgorithm.cpp:671-692,
+    // :1391-1402, :1414-1607) with the device in the place of the partition commands ------------------------------------------
+    void executeWithProcessors()
+    {
+        const size_t W = _ctxs.size();
+        memset(&_st, 0, sizeof _st); _nbSolidWritten = 0;
+        for (size_t i = 0; i < _processors.size(); i++) _processors[i]->begin(_config);
+        for (int pass = 0; pass < _nbPasses; pass++) {
+            for (int attempt = 0; ; attempt++) {
+                try {
+                    if (_nbPasses > 1 || attempt > 0) beginPass(pass);
+                    { TIME_INFO(getTimeInfo(), "fill_partitions"); feedBanks(); }
+                    { TIME_INFO(getTimeInfo(), "fill_solid_kmers"); finishAll(); }
+                    break;
+                } catch (FormatRejected& e) {
+                    if (attempt > 0 || _viaIterator) throw Exception("dskgpu: input rejected by the record scanner (%s)", e.what.c_str());
+                    _viaIterator = true;
+                }
+            }
+            TIME_INFO(getTimeInfo(), "processors");
+            for (size_t i = 0; i < _processors.size(); i++) {
+                CountProcessor* proc = _processors[i];
+                proc->beginPass((size_t)pass);
+                std::vector<CountProcessor*> clones;
+                for (size_t r = 0; r < W; r++) {                       // one "partition" per device: its k-mers, ascending
+                    CountProcessor* clone = proc->clone();
+                    clone->use();
+                    clones.push_back(clone);
+                    const uint64_t* kmers = 0; const uint32_t* counts = 0; uint64_t n = 0; int words = 0;
+                    check(dskgpu_partition(_ctxs[r], 0, &kmers, &counts, &n, &words), _ctxs[r], "dskgpu_partition");
+                    clone->beginPart((size_t)pass, r, 200 * 1000, "device");
+                    CountVector cv(1);
+                    for (uint64_t j = 0; j < n; j++) {
+                        Type v; setValue(v, kmers + j * words, words);
+                        cv[0] = (CountNumber)counts[j];
+                        clone->process(r, v, cv, (CountNumber)counts[j]);
+                    }
+                    clone->endPart((size_t)pass, r);
+                    if (i == 0) {
+                        dskgpu_stats st;
+                        check(dskgpu_get_stats(_ctxs[r], &st), _ctxs[r], "dskgpu_get_stats");
+                        if (pass == 0) { _st.nb_sequences += st.nb_sequences; _st.nb_nucleotides += st.nb_nucleotides; _st.kmers_nb_valid += st.kmers_nb_valid; }
+                        _st.nb_superkmers += st.nb_superkmers; _st.superkmer_bytes += st.superkmer_bytes; _st.kmers_nb_distinct += st.kmers_nb_distinct;
+                        _st.gpu_launches += st.gpu_launches;
+                    }
+                }
+                proc->finishClones(clones);
+                for (size_t r = 0; r < clones.size(); r++) clones[r]->forget();
+                proc->endPass((size_t)pass);
+            }
+        }
+        for (size_t i = 0; i < _processors.size(); i++) _processors[i]->end();
+        // statistics: the keys of K/SortingCountAlgorithm.cpp:728-780 that exist without the default chain
+        getInfo()->add(1, "bank");
+        getInfo()->add(2, "bank_uri", "%s", _bank->getId().c_str());
+        getInfo()->add(2, "bank_total_nt", "%lld", (long long)_st.nb_nucleotides);
+        getInfo()->add(2, "sequences");
+        getInfo()->add(3, "seq_number", "%ld", (long)_st.nb_sequences);
+        getInfo()->add(2, "kmers");
+        getInfo()->add(3, "kmers_nb_valid", "%lld", (long long)_st.kmers_nb_valid);
+        getInfo()->add(1, "stats");
+        getInfo()->add(2, "temp_files");
+        getInfo()->add(3, "nb_superkmers", "%lld", (long long)_st.nb_superkmers);
+        getInfo()->add(2, "kmers");
+        getInfo()->add(3, "kmers_nb_distinct", "%ld", (long)_st.kmers_nb_distinct);
+        if (_processors.size() == 1) getInfo()->add(2, _processors[0]->getProperties());
+        else for (size_t i = 0; i < _processors.size(); i++) { getInfo()->add(2, _processors[i]->getName()); getInfo()->add(3, _processors[i]->getProperties()); }
+        getInfo()->add(1, getTimeInfo().getProperties("time"));
     }
 
     void beginPass(int pass)

@@ -25,14 +25,22 @@ if [ ! -f "$B/ext/gatb-core/lib/Release/libgatbcore.a" ]; then
 fi
 G="$REF/thirdparty/gatb-core/gatb-core"
 mkdir -p "$OUT"
-if [ -x "$OUT/dsk_gpu" ] && [ "$OUT/dsk_gpu" -nt "$HERE/GpuSortingCount.hpp" ] && [ "$OUT/dsk_gpu" -nt "$HERE/dsk_gpu_main.cpp" ] \
+if [ -x "$OUT/dsk_gpu" ] && [ -x "$OUT/plugin_check" ] && [ "$OUT/dsk_gpu" -nt "$HERE/GpuSortingCount.hpp" ] && [ "$OUT/dsk_gpu" -nt "$HERE/dsk_gpu_main.cpp" ] \
+   && [ "$OUT/plugin_check" -nt "$HERE/GpuSortingCount.hpp" ] && [ "$OUT/plugin_check" -nt "$HERE/plugin_check.cpp" ] \
    && [ "$OUT/dsk_gpu" -nt "$ROOT/include/dskgpu.h" ] && [ -f "$OUT/.built_against" ] && [ "$(cat "$OUT/.built_against")" = "$B" ]; then echo "host/_build/dsk_gpu up to date"; exit 0; fi
-g++ -std=c++11 -O2 -DNDEBUG -D_FILE_OFFSET_BITS=64 -D_GNU_SOURCE -D_LARGEFILE64_SOURCE -D_LARGEFILE_SOURCE -DINT128_FOUND \
-    -include cstdint -Wno-invalid-offsetof -Wno-format -Wno-unknown-pragmas \
-    -I"$B/ext/gatb-core/include" -I"$B/ext/gatb-core/include/Release" -I"$G/src" -I"$G/thirdparty" \
-    -I"$B/ext/gatb-core/thirdparty/hdf5/src" -I"$G/thirdparty/hdf5/src" \
-    "$HERE/dsk_gpu_main.cpp" -o "$OUT/dsk_gpu" \
-    -L"$B/ext/gatb-core/lib/Release" -lgatbcore -lhdf5 -L"$ROOT/dsk_b200" -ldskgpu \
-    -Wl,-rpath,'$ORIGIN/../../dsk_b200' -ldl -lpthread -lz
+# dsk_gpu = the `dsk` command line over the device path; plugin_check = the 5-argument constructor + ICountProcessor surface
+# driven the way Graph.cpp drives SortingCountAlgorithm (GPU tests)
+for prog in dsk_gpu:dsk_gpu_main.cpp plugin_check:plugin_check.cpp; do
+  exe="${prog%%:*}"; src="${prog##*:}"
+  g++ -std=c++11 -O2 -DNDEBUG -D_FILE_OFFSET_BITS=64 -D_GNU_SOURCE -D_LARGEFILE64_SOURCE -D_LARGEFILE_SOURCE -DINT128_FOUND \
+      -include cstdint -Wno-invalid-offsetof -Wno-format -Wno-unknown-pragmas \
+      -I"$B/ext/gatb-core/include" -I"$B/ext/gatb-core/include/Release" -I"$G/src" -I"$G/thirdparty" \
+      -I"$B/ext/gatb-core/thirdparty/hdf5/src" -I"$G/thirdparty/hdf5/src" \
+      "$HERE/$src" -o "$OUT/$exe" \
+      -L"$B/ext/gatb-core/lib/Release" -lgatbcore -lhdf5 -L"$ROOT/dsk_b200" -ldskgpu \
+      -Wl,-rpath,'$ORIGIN/../../dsk_b200' -ldl -lpthread -lz &
+done
+wait
+[ -x "$OUT/dsk_gpu" ] && [ -x "$OUT/plugin_check" ] || { echo "host build failed"; exit 1; }
 echo "$B" > "$OUT/.built_against"
-echo "built $OUT/dsk_gpu (against $B)"
+echo "built $OUT/dsk_gpu and $OUT/plugin_check (against $B)"

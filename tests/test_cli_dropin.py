@@ -122,6 +122,44 @@ def test_cli_shell_goldens(tmp_path):
             assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]
 
 
+PLUGIN = os.path.join(ROOT, "host", "_build", "plugin_check")
+AUTO = load_json("ref_runs_auto.json")["runs"]
+PLUGIN_RUNS = [t for t in RUNS if t["name"] in ("c1_k31", "c1_k63", "c1_k31_min3_max20", "longread_k63", "reads.fastq_k31")] + \
+              [t for t in AUTO if t["name"] in ("auto_c1_k31", "auto_asmreads_k21")]
+
+
+@need_bins
+@pytest.mark.skipif(not os.path.exists(PLUGIN), reason="host/_build/plugin_check not built (python __graft_entry__.py)")
+@pytest.mark.parametrize("t", PLUGIN_RUNS, ids=[t["name"] for t in PLUGIN_RUNS])
+def test_plugin_surface_with_the_reference_processors(t, tmp_path):
+    """the ICountProcessor plug-in surface (5-argument constructor, G/src/gatb/debruijn/impl/Graph.cpp:399-407): the REFERENCE'S
+    OWN processor chain (getDefaultProcessorVector: histogram -> solidity -> dump; cutoff processor first for 'auto') is fed
+    by the device path with every distinct k-mer; the .h5 its dump processor writes must hold what the reference dsk wrote,
+    and our audit processor must have seen every distinct k-mer once, ascending, with a one-entry CountVector"""
+    tmp = str(tmp_path)
+    out = os.path.join(tmp, "plug")
+    a = ["-file", ",".join(os.path.join(INPUTS, f) for f in t["files"]), "-kmer-size", str(t["k"]), "-abundance-min", str(t["abundance_min"]), "-out", out, "-histo", "1"]
+    if t.get("abundance_max") is not None:
+        a += ["-abundance-max", str(t["abundance_max"])]
+    stdout = run([PLUGIN] + a, tmp)
+    audit = [ln for ln in stdout.splitlines() if ln.startswith("audit ")][-1].split()
+    got = dict(zip(audit[1::2], (int(x) for x in audit[2::2])))
+    if "kmers_nb_distinct" in t:                                                  # (the 'auto' goldens only carry the solid side)
+        assert got["distinct"] == t["kmers_nb_distinct"] and got["occurrences"] == t["kmers_nb_valid"]
+    else:
+        assert got["distinct"] >= t["nb_solid"] and got["occurrences"] >= t["sum_counts"]
+    assert got["unordered"] == 0 and got["bad_vectors"] == 0 and got["parts"] >= 1
+    assert got["processors"] == (3 if t["abundance_min"] == "auto" else 2)          # (cutoff,) default chain, audit
+    lines, histo, header = read_back(out + ".h5", tmp)
+    assert len(lines) == t["nb_solid"]
+    m = hashlib.sha256()
+    for ln in lines:
+        m.update(ln + b"\n")
+    assert m.hexdigest() == t["kmers_sha256"]
+    rows = open(out + ".histo").read().splitlines()
+    assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]
+
+
 WIDEBIN = os.path.join(ROOT, "oracle", "_ref", "wide", "bin")
 WIDE_RUNS = [t for t in load_json("ref_runs_wide.json")["runs"] if t["name"] in ("c1_k64", "c1_k95", "longreads250_k96", "longreads250_k127", "c123_k71_all", "histo2d_k95")]
 

@@ -48,6 +48,7 @@ PYEOF
                 tail -2 "$OUT/proxy_k${pk}_m${pm}_f${pf}.err"
               done ;;
     pywide)   timeout 900 python -m pytest tests/test_gpu_wide.py tests/test_cli_dropin.py -q -k "wide or unhandled" > "$OUT/pytest_wide.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_wide.log"; tail -30 "$OUT/pytest_wide.log" | cut -c1-400 ;;
+    pyplug)   timeout 900 python -m pytest tests/test_cli_dropin.py -q -k "plugin" > "$OUT/pytest_plugin.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_plugin.log"; tail -40 "$OUT/pytest_plugin.log" | cut -c1-600 ;;
     pymin)    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "minimizer_sizes or tiny_smem or record_sub or fine_histogram or heavy" > "$OUT/pytest_min.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_min.log"; tail -6 "$OUT/pytest_min.log" ;;
     *)        echo "unknown step $step" ;;
   esac
