@@ -37,10 +37,10 @@ C3_GENOME_PER_GPU = 375_000_000          # configs[2] is 3 Gbp over 8 GPUs
 
 def algorithmic_bytes_per_kmer(k, L=150, s=None):
     """SURVEY.md 8(d) formula. W = key bytes, P = digit passes, s = mean k-mers per super-k-mer."""
-    W = 8 if k < 32 else 16
+    W = 8 if k < 32 else 16 if k < 64 else 24 if k < 96 else 32
     P = (2 * k + 7) // 8
     if s is None:
-        s = 11.22 if k < 32 else 22.34
+        s = 11.22 if k < 32 else 22.34 if k < 64 else (k - 10 + 2) / 2.0      # ~ half a window of k - m + 1 m-mers (m = 10)
     b_sk = (1 + (k - 1 + s) / 4) / s
     rho = 0.0324 if k < 32 else 0.0337
     s1 = L / (L - k + 1) + b_sk
@@ -48,6 +48,10 @@ def algorithmic_bytes_per_kmer(k, L=150, s=None):
     s3 = W + 2 * W * P
     s4 = W + (W + 4) * rho
     return {"S1_scan_superk": s1, "S2_expand": s2, "S3_sort": s3, "S4_reduce": s4, "total": s1 + s2 + s3 + s4}
+
+
+def key_dtype(k):
+    return "u64" if k < 32 else "u128" if k < 64 else "u192" if k < 96 else "u256"
 
 
 def peaks():
@@ -370,7 +374,7 @@ def reference_arm(args, world, cfg, json_out):
     val = tot_k / tot_t / 1e9
     line = {"impl": "reference", "metric": "Gk-mers/s counted", "value": val, "unit": "Gk-mers/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(vals)), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64" if args.kmer_size < 32 else "u128", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": key_dtype(args.kmer_size), "data": "synthetic",
             "config": cfg, "kmers_per_step": vals[0][0] if vals else 0,
             "cpu_baseline": {"value": val, "unit": "Gk-mers/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Gk-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -667,7 +671,7 @@ def main():
                              "source": "profiles/%s (ncu --set full, one gpurun call at HEAD)" % nk.get("tag")} if kd else None)}
         line = {
             "metric": "Gk-mers/s counted", "value": value, "unit": "Gk-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if args.kmer_size < 32 else "u128",
+            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": key_dtype(args.kmer_size),
             "data": "synthetic (reads drawn on the device)" if args.device_synth else "synthetic",
             "config": cfg,
             "engine": engine_info,

@@ -1427,6 +1427,7 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
         CK(cudaMemcpyAsync(ctx->h_hist, ctx->hist.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_hist + DSKGPU_HISTO_LEN, ctx->hist2d.p, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2,
                            cudaMemcpyDeviceToHost, ctx->stream));
+        trace("ordering queued");
         if (!ctx->cfg.keep_results_on_device && ctx->n_solid) {
             if (ctx->n_solid > ctx->h_solid_cap) {
                 if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
@@ -1436,11 +1437,13 @@ static int stage_count_once(dskgpu_ctx* ctx, u64 cap_request, u64* need_cap)
                 CK(cudaMallocHost((void**)&ctx->h_skeys, ctx->h_solid_cap * KW * 8));
                 CK(cudaMallocHost((void**)&ctx->h_svals, ctx->h_solid_cap * 4));
             }
+            trace("host result buffers ready");
             CK(cudaMemcpyAsync(ctx->h_skeys, ctx->skeys[ctx->solid_buf].p, ctx->n_solid * KW * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(ctx->h_svals, ctx->svals[ctx->solid_buf].p, ctx->n_solid * 4, cudaMemcpyDeviceToHost, ctx->stream));
             ctx->results_on_host = true;
         }
         CK(cudaStreamSynchronize(ctx->stream));
+        trace("results on the host");
         return 0;
     };
     *(volatile unsigned int*)(ctx->h_nrec_probe + 7) = 0;
@@ -1508,6 +1511,7 @@ static int finish_single(dskgpu_ctx* ctx)
     trace(nullptr);
     if ((rc = stage_totals(ctx))) return rc;
     trace("totals (push kernels done)");
+    if (g_trace) { const void* dh = nullptr; if ((rc = fold_local_hist(ctx, &dh))) return rc; CK(cudaStreamSynchronize(ctx->stream)); trace("bin histogram folded (sync: tracing only)"); }
     if ((rc = plan_device(ctx, nullptr))) return rc;
     trace("plan (device) + header");
     if ((rc = stage_scatter<KW>(ctx))) return rc;

@@ -25,6 +25,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -53,6 +54,14 @@ inline void check(int rc, dskgpu_ctx* ctx, const char* what)
     if (rc == DSKGPU_OK) return;
     const char* detail = dskgpu_last_error(ctx);
     throw Exception("%s: %s (%s)", what, dskgpu_strerror(rc), detail ? detail : "");
+}
+
+/** DSKGPU_TRACE=1: host wall-clock of the adapter's phases on stderr, next to libdskgpu's own trace (tuning aid). */
+inline void hostTrace(const char* what)
+{
+    static const bool on = getenv("DSKGPU_TRACE") != 0;
+    static const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    if (on) fprintf(stderr, "[dsk_gpu host] %-44s @%9.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 }
 
 /** Thrown instead of Exception when the device record scanner rejects the input layout (DSKGPU_ERR_FORMAT): the adapter
@@ -121,7 +130,9 @@ public:
 
     void execute()
     {
+        hostTrace("execute: start");
         configure();
+        hostTrace("configured (bank estimate, storage, device contexts)");
         if (!_processors.empty()) { executeWithProcessors(); return; }
         // The device scanner takes what dsk is fed in practice: FASTA (single- or multi-line) and 4-line FASTQ, plain or
         // gzip.  Whatever else BankFasta accepts (multi-line FASTQ, '+' lines inside FASTA, ...; BankFasta.cpp:485-572) is
@@ -137,7 +148,9 @@ public:
                 for (size_t r = 0; r < _ctxs.size(); r++) check(dskgpu_reset(_ctxs[r]), _ctxs[r], "dskgpu_reset");
             }
         }
+        hostTrace("all passes done (solid collections written)");
         writeResults();
+        hostTrace("results written (histogram, minimRepart, stats)");
     }
 
 private:
@@ -160,6 +173,8 @@ private:
     std::vector<uint64_t> _h1, _h2;                // histograms summed over the devices and the passes
     u_int64_t         _nbSolidWritten;
     std::string       _histoName, _histo2DName;
+    size_t            _histoMax = 10000;
+    int               _minimizerType = 0, _repartitionType = 0;
     bool              _autoCutoff;
     bool              _autoPerBank;
     std::vector<long long> _userAbundanceMin;      // -1 = auto
@@ -213,10 +228,16 @@ private:
         _histoName = histo1D ? base + ".histo" : std::string();
         _histo2DName = histo2D ? base + ".histo2D" : std::string();
 
-        if (!plugin && in->getInt(STR_HISTOGRAM_MAX) != 10000)
-            throw Exception("the device histogram has the reference's default length (-histo-max 10000) only");
-        if (in->getInt(STR_MINIMIZER_TYPE) != 0 || in->getInt(STR_REPARTITION_TYPE) != 0)
-            throw Exception("-minimizer-type 1 / -repartition-type 1 are outside the device path (SURVEY.md 8(f)-4)");
+        // -histo-max N (K/SortingCountAlgorithm.cpp:213): counts >= N fall into a clamp bin that is never merged
+        // (Histogram.hpp:92,221), so a histogram of length N is the first N bins of the device's 10000-bin histogram
+        _histoMax = (size_t)in->getInt(STR_HISTOGRAM_MAX);
+        if (!plugin && (_histoMax < 1 || _histoMax > 10000))
+            throw Exception("the device histogram holds 10000 bins: -histo-max %d is outside 1..10000", (int)_histoMax);
+        // -minimizer-type 1 (frequency order, K/Model.hpp:957-973) and -repartition-type 1 (ordered repartition,
+        // K/RepartitionAlgorithm.cpp:311-384) only change WHICH PARTITION a k-mer is counted in -- the reference uses them to
+        // balance its partition files.  The device path balances its partitions itself, from exact minimizer-bin counts, and
+        // delivers one ordered collection per device: both options are accepted and have nothing left to influence.
+        _minimizerType = (int)in->getInt(STR_MINIMIZER_TYPE); _repartitionType = (int)in->getInt(STR_REPARTITION_TYPE);
 
         // ---- device context ---------------------------------------------------------------------------------------
         dskgpu_config c;
@@ -533,6 +554,7 @@ private:
                 TIME_INFO(getTimeInfo(), "fill_partitions");          // same labels as K/SortingCountAlgorithm.cpp:1218
                 feedBanks();
             }
+            hostTrace("banks fed (file bytes queued to the device)");
             {
                 TIME_INFO(getTimeInfo(), "fill_solid_kmers");         // K/SortingCountAlgorithm.cpp:1391
                 finishAll();
@@ -545,6 +567,7 @@ private:
                     recountAll(amin);
                 }
             }
+            hostTrace("finish done (counted, results on the host)");
             TIME_INFO(getTimeInfo(), "dump");
             collectPass(pass);
         }
@@ -636,8 +659,8 @@ private:
     {
         _cutoffs.clear();
         for (size_t b = 0; b < nbHist; b++) {
-            Histogram H(10000);
-            for (size_t i = 0; i <= 10000; i++) H.get((u_int16_t)i) = hs[b * DSKGPU_HISTO_LEN + i];
+            Histogram H(_histoMax);
+            for (size_t i = 0; i <= _histoMax; i++) H.get((u_int16_t)i) = i < _histoMax ? hs[b * DSKGPU_HISTO_LEN + i] : 0;
             H.compute_threshold(3);
             _cutoffs.push_back((CountNumber)H.get_solid_cutoff());
         }
@@ -658,13 +681,28 @@ private:
             const size_t coll = (size_t)pass * W + r;               // CountProcessorDump: partId + passId * nbPartsPerPass
             const uint64_t* kmers = 0; const uint32_t* counts = 0; uint64_t n = 0; int words = 0;
             check(dskgpu_partition(ctx, 0, &kmers, &counts, &n, &words), ctx, "dskgpu_partition");
-            const size_t B = 1 << 20;
+            // The device hands back two arrays (keys, abundances) in pinned memory; the dataset is an array of Count{value,
+            // abundance}.  Blocks of 4 M items are interleaved by a few threads (a straight word copy when Type is laid out
+            // as its 64-bit words, least significant first -- checked on the first item -- else through the arithmetic
+            // interface) and each block is ONE H5Dset_extent + H5Dwrite (BagHDF5::insert, CollectionHDF5.hpp:79-117): no
+            // BagCache, no per-item insert, no synchronizer on the path.
+            const size_t B = (size_t)4 << 20;
+            const bool raw = n > 0 && rawLayoutOk(kmers, words);
+            const size_t nthr = std::max<size_t>(1, std::min<size_t>(8, std::thread::hardware_concurrency()));
             for (uint64_t i = 0; i < n; i += B) {
                 const size_t m = (size_t)std::min<uint64_t>(B, n - i);
                 block.resize(m);
-                for (size_t j = 0; j < m; j++) {
-                    Type v; setValue(v, kmers + (i + j) * words, words);
-                    block[j] = Count(v, (CountNumber)counts[i + j]);
+                auto fill = [&](size_t a, size_t b) {
+                    for (size_t j = a; j < b; j++) {
+                        if (raw) { memcpy((void*)&block[j].value, kmers + (i + j) * words, sizeof(uint64_t) * (size_t)words); block[j].abundance = (CountNumber)counts[i + j]; }
+                        else { Type v; setValue(v, kmers + (i + j) * words, words); block[j] = Count(v, (CountNumber)counts[i + j]); }
+                    }
+                };
+                if (m < ((size_t)1 << 16) || nthr == 1) fill(0, m);
+                else {
+                    std::vector<std::thread> th;
+                    for (size_t t = 0; t < nthr; t++) th.push_back(std::thread(fill, m * t / nthr, m * (t + 1) / nthr));
+                    for (size_t t = 0; t < nthr; t++) th[t].join();
                 }
                 (*_solidCounts)[coll].insert(block.data(), m);
             }
@@ -722,11 +760,18 @@ private:
         // was filled from the device bins (K/CountProcessorHistogram.hpp:104-159, Histogram.cpp:43-190)
         const std::vector<uint64_t>& h1 = _h1; const std::vector<uint64_t>& h2 = _h2;
         const bool histo2D = !_histo2DName.empty(), histo1D = !_histoName.empty();
-        CountProcessorHistogram<span> ph(&_storage->getGroup("histogram"), 10000, in->getInt(STR_KMER_ABUNDANCE_MIN_THRESHOLD),
+        CountProcessorHistogram<span> ph(&_storage->getGroup("histogram"), _histoMax, in->getInt(STR_KMER_ABUNDANCE_MIN_THRESHOLD),
                                          histo2D, histo1D, _histo2DName, _histoName);
         IHistogram* H = ph.getHistogram();
-        for (size_t i = 0; i <= 10000; i++) H->get((u_int16_t)i) = h1[i];
-        for (size_t j = 0; j <= 10; j++) for (size_t i = 0; i <= 10000; i++) H->get2D((u_int16_t)i, (u_int16_t)j) = h2[j * DSKGPU_HISTO_LEN + i];
+        // 1-D: bins below the length as they are, the clamp bin stays empty (never merged: Histogram.hpp:221); 2-D: the clamp
+        // column collects everything at or above the length (Histogram.hpp:97)
+        for (size_t i = 0; i <= _histoMax; i++) H->get((u_int16_t)i) = i < _histoMax ? h1[i] : 0;
+        for (size_t j = 0; j <= 10; j++) {
+            for (size_t i = 0; i < _histoMax; i++) H->get2D((u_int16_t)i, (u_int16_t)j) = h2[j * DSKGPU_HISTO_LEN + i];
+            u_int64_t tail = 0;
+            for (size_t i = _histoMax; i <= 10000; i++) tail += h2[j * DSKGPU_HISTO_LEN + i];
+            H->get2D((u_int16_t)_histoMax, (u_int16_t)j) = tail;
+        }
         ph.end();
 
         // ---- statistics: keys of K/SortingCountAlgorithm.cpp:728-780 ----------------------------------------------------
@@ -761,6 +806,8 @@ private:
         getInfo()->add(3, "nb_items", "%ld", (long)nbSolid);
         getInfo()->add(3, "nb_passes", "%ld", (long)_nbPasses);
         getInfo()->add(3, "nb_devices", "%ld", (long)_ctxs.size());
+        if (_minimizerType != 0 || _repartitionType != 0)
+            getInfo()->add(3, "partition_balance", "%s", "-minimizer-type / -repartition-type accepted; the device path balances from exact minimizer-bin counts");
         getInfo()->add(3, "device_partitions", "%ld", (long)_st.nb_partitions);
         getInfo()->add(3, "kind");
         getInfo()->add(4, "vector", "%ld", (long)_st.nb_groups_sort);
@@ -777,6 +824,15 @@ private:
 
     // Type = LargeInt<1> (u64) for span 32, LargeInt<2> (__uint128_t or 2 x u64) for span 64: both expose their
     // words through getVal()/setVal or operator[]; going through shifts keeps this independent of the representation
+    /** true when a Type is stored as its `words` 64-bit words, least significant first (LargeInt<1>: one u64; LargeInt<2>:
+     *  __uint128_t or u64[2]; LargeInt<3|4>: u64[N]) -- verified against the arithmetic interface on a real key */
+    static bool rawLayoutOk(const uint64_t* w, int words)
+    {
+        if (sizeof(Type) != sizeof(uint64_t) * (size_t)words) return false;
+        Type v; setValue(v, w, words);
+        return memcmp((const void*)&v, w, sizeof(Type)) == 0;
+    }
+
     static void setValue(Type& v, const uint64_t* w, int words)
     {
         v.setVal(w[words - 1]);

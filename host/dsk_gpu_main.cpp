@@ -51,7 +51,9 @@ int main(int argc, char* argv[])
 {
     try
     {
+        hostTrace("main");
         DSKGpu().run(argc, argv);
+        hostTrace("run returned");
     }
     catch (OptionFailure& e)
     {

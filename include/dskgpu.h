@@ -180,8 +180,9 @@ int dskgpu_finish(dskgpu_ctx* ctx);
 
 /* replaces: Partition<Count>& getSolidCounts() (SortingCountAlgorithm.hpp:66-192) */
 int dskgpu_num_partitions(dskgpu_ctx* ctx);
-/* partition p: *kmers -> n values of `words` little-endian uint64 each (words = 1 for k<32, 2 for k<64,
- * low word first), ascending; *counts -> n uint32 abundances (Count::abundance, Abundance.hpp:108-125).
+/* partition p: *kmers -> n values of `words` little-endian uint64 each (words = 1 for k<32, 2 for k<64, 3 for k<96,
+ * 4 for k<128 -- the spans of KSIZE_LIST "32 64 96 128", Integer.hpp:453-471; low word first), ascending as
+ * LargeInt compares (most significant word first, LargeInt.hpp:502-509); *counts -> n uint32 abundances (Count::abundance, Abundance.hpp:108-125).
  * Host pointers owned by the context until destroy/reset. */
 int dskgpu_partition(dskgpu_ctx* ctx, int p, const uint64_t** kmers, const uint32_t** counts, uint64_t* n, int* words);
 /* same data, device pointers (valid until destroy/reset) */

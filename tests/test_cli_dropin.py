@@ -160,6 +160,29 @@ def test_plugin_surface_with_the_reference_processors(t, tmp_path):
     assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]
 
 
+HISTOMAX = load_json("ref_runs_histomax.json")["runs"]
+
+
+@need_bins
+@pytest.mark.parametrize("t", HISTOMAX, ids=[t["name"] for t in HISTOMAX])
+def test_cli_histo_max_and_partition_balance_options(t, tmp_path):
+    """-histo-max N (N < 10000): <out>.histo / <out>.histo2D byte-identical to the reference's (N lines, clamp bin empty in 1-D,
+    populated in 2-D), 'auto' cutoff computed on the shortened histogram; -minimizer-type 1 / -repartition-type 1 ride along:
+    they only change partition balance in the reference and nothing in the results"""
+    tmp = str(tmp_path)
+    out = os.path.join(tmp, "gpu_out")
+    run([DSK_GPU] + dsk_args(t, out) + ["-histo-max", str(t["histo_max"]), "-minimizer-type", "1", "-repartition-type", "1"], tmp)
+    assert open(out + ".histo").read() == t["histo_text"]
+    if t.get("histo2d"):
+        assert open(out + ".histo2D").read() == t["histo2d_text"]
+    lines, _, _ = read_back(out + ".h5", tmp)
+    assert len(lines) == t["nb_solid"]
+    m = hashlib.sha256()
+    for ln in lines:
+        m.update(ln + b"\n")
+    assert m.hexdigest() == t["kmers_sha256"]
+
+
 WIDEBIN = os.path.join(ROOT, "oracle", "_ref", "wide", "bin")
 WIDE_RUNS = [t for t in load_json("ref_runs_wide.json")["runs"] if t["name"] in ("c1_k64", "c1_k95", "longreads250_k96", "longreads250_k127", "c123_k71_all", "histo2d_k95")]
 

@@ -36,12 +36,20 @@ def test_no_device_fails_loudly_no_cpu_fallback(tmp_path):
     assert "no CUDA device" in (p.stdout + p.stderr) and "no CPU fallback" in (p.stdout + p.stderr)
 
 
-@pytest.mark.parametrize("opt,val,msg", [("-minimizer-type", "1", "outside the device path"), ("-repartition-type", "1", "outside the device path"),
-                                         ("-histo-max", "5000", "-histo-max 10000")])
+@pytest.mark.parametrize("opt,val,msg", [("-histo-max", "20000", "outside 1..10000"), ("-histo-max", "0", "outside 1..10000")])
 def test_options_outside_the_device_path_are_refused(tmp_path, opt, val, msg):
     p = run_cli(tmp_path, opt, val)
     assert p.returncode != 0
     assert "EXCEPTION" in (p.stdout + p.stderr) and msg in (p.stdout + p.stderr)      # refused for what it is, before any device call
+
+
+@pytest.mark.parametrize("opt,val", [("-minimizer-type", "1"), ("-repartition-type", "1"), ("-histo-max", "5000")])
+def test_partition_balance_options_are_accepted(tmp_path, opt, val):
+    # they only move k-mers between partitions (unobservable) / shorten the histogram: accepted; without a device the run then
+    # fails for the one reason it should
+    p = run_cli(tmp_path, opt, val)
+    assert p.returncode != 0
+    assert "no CUDA device" in (p.stdout + p.stderr) and "outside" not in (p.stdout + p.stderr)
 
 
 def test_unhandled_kmer_size_message(tmp_path):

@@ -49,6 +49,17 @@ PYEOF
               done ;;
     pywide)   timeout 900 python -m pytest tests/test_gpu_wide.py tests/test_cli_dropin.py -q -k "wide or unhandled" > "$OUT/pytest_wide.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_wide.log"; tail -30 "$OUT/pytest_wide.log" | cut -c1-400 ;;
     pyplug)   timeout 900 python -m pytest tests/test_cli_dropin.py -q -k "plugin" > "$OUT/pytest_plugin.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_plugin.log"; tail -40 "$OUT/pytest_plugin.log" | cut -c1-600 ;;
+    clitime)  # wall-clock of the drop-in CLI on the C2 read set (file on tmpfs -> .h5 on tmpfs) with the host / device phase timeline
+              python - <<'PYEOF'
+from dsk_b200.synth import reads_fasta
+buf, n, _ = reads_fasta(G=5_000_000, coverage=100, L=150, err=0.01, seed=42)
+open("/dev/shm/c2.fa", "wb").write(buf[:n].tobytes())
+PYEOF
+              for i in 1 2 3; do s=$(date +%s.%N); DSKGPU_TRACE=1 host/_build/dsk_gpu -file /dev/shm/c2.fa -kmer-size 31 -abundance-min 2 -out /dev/shm/c2_gpu -histo 1 -verbose 0 > "$OUT/clitime_gpu_$i.log" 2>&1; e=$(date +%s.%N); echo "dsk_gpu run $i wall $(echo "$e - $s" | bc) s"; done
+              s=$(date +%s.%N); oracle/_ref/bin/dsk -file /dev/shm/c2.fa -kmer-size 31 -abundance-min 2 -out /dev/shm/c2_ref -histo 1 -verbose 0 -out-tmp /dev/shm > "$OUT/clitime_ref.log" 2>&1; e=$(date +%s.%N); echo "reference dsk wall $(echo "$e - $s" | bc) s"
+              cat "$OUT/clitime_gpu_3.log" | cut -c1-160
+              rm -f /dev/shm/c2.fa /dev/shm/c2_gpu* /dev/shm/c2_ref* ;;
+    pycli)    timeout 900 python -m pytest tests/test_cli_dropin.py tests/test_zz_cli_scanner_fallback.py -q > "$OUT/pytest_cli.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_cli.log"; tail -30 "$OUT/pytest_cli.log" | cut -c1-500 ;;
     pymin)    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "minimizer_sizes or tiny_smem or record_sub or fine_histogram or heavy" > "$OUT/pytest_min.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_min.log"; tail -6 "$OUT/pytest_min.log" ;;
     *)        echo "unknown step $step" ;;
   esac
