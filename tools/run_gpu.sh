@@ -28,7 +28,7 @@ for step in "$@"; do
     biglaunches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$OUT/launches_big.csv" python bench.py --genome 375000000 --coverage 30 --device-synth --minimizer-size ${BIG_M:-14} --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/launches_big.log" 2>&1; echo "biglaunches exit $?" ;;
     ncuk)     # one full capture per named kernel (small report): NCU_LIST="k_scan_emit k_superkmers ..."
               for kn in ${NCU_LIST:-k_scan_tables k_scan_emit k_superkmers k_rs_onesweep k_msd_pass k_count_smem}; do
-                case "$kn" in k_count_smem) sk=1 ;; k_msd_pass) sk=2 ;; k_rs_onesweep) sk=12 ;; *) sk=6 ;; esac   # a launch of the second (timed) step
+                case "$kn" in k_count_smem) sk=1 ;; k_msd_pass) sk=2 ;; k_rs_onesweep) sk=3 ;; k_rs_fix) sk=1 ;; *) sk=6 ;; esac   # a launch of the second (timed) step (C2, device-resident input: 5 pieces of 128 MiB, 2 scatter passes, 3 ordering passes per step)
                 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$kn" -s "$sk" -c 1 -f -o "$OUT/ncu_$kn" python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/ncu_$kn.log" 2>&1; echo "ncu $kn exit $?"
               done; ls -la "$OUT" ;;
     cli)      timeout 900 bash tools/run_cli_check.sh "$OUT" ;;
@@ -60,6 +60,12 @@ PYEOF
               cat "$OUT/clitime_gpu_3.log" | cut -c1-160
               rm -f /dev/shm/c2.fa /dev/shm/c2_gpu* /dev/shm/c2_ref* ;;
     pycli)    timeout 900 python -m pytest tests/test_cli_dropin.py tests/test_zz_cli_scanner_fallback.py -q > "$OUT/pytest_cli.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_cli.log"; tail -30 "$OUT/pytest_cli.log" | cut -c1-500 ;;
+    sanitize2) # the code added after r03a: wide-span kernels (memcheck: shared-memory indexing of the 128-position halo) and the early
+              # exit of a lost table pass (racecheck on the split tests)
+              timeout 900 compute-sanitizer --tool memcheck --log-file "$OUT/sanitizer_memcheck_wide.log" python -m pytest tests/test_gpu_wide.py -x -q -k "c1_k64 or longreads250_k127-min1 or histo2d_k95 or scatter_paths and 100 or multi_rank and 80" > "$OUT/sanitizer_memcheck_wide.out" 2>&1
+              echo "memcheck wide exit $?"; tail -3 "$OUT/sanitizer_memcheck_wide.log"; tail -2 "$OUT/sanitizer_memcheck_wide.out"
+              timeout 900 compute-sanitizer --tool racecheck --log-file "$OUT/sanitizer_racecheck_split.log" python -m pytest tests/test_gpu_parity.py -x -q -k "tiny_smem_table_overflow_splits and (c1_k31 or c1_k63) and 64" > "$OUT/sanitizer_racecheck_split.out" 2>&1
+              echo "racecheck split exit $?"; tail -3 "$OUT/sanitizer_racecheck_split.log"; tail -2 "$OUT/sanitizer_racecheck_split.out" ;;
     pymin)    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "minimizer_sizes or tiny_smem or record_sub or fine_histogram or heavy" > "$OUT/pytest_min.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_min.log"; tail -6 "$OUT/pytest_min.log" ;;
     *)        echo "unknown step $step" ;;
   esac
