@@ -24,7 +24,7 @@ class Config(C.Structure):
         ("histo2d", C.c_int32), ("device", C.c_int32), ("count_mode", C.c_int32), ("hash_log2_slots", C.c_int32),
         ("nb_partitions", C.c_int32), ("keep_results_on_device", C.c_int32),
         ("stream", C.c_void_p), ("rank", C.c_int32), ("world_size", C.c_int32), ("push_chunk_bytes", C.c_int32), ("smem_table_slots", C.c_int32), ("bank_histograms", C.c_int32),
-        ("nb_passes", C.c_int32), ("pass_id", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("nb_passes", C.c_int32), ("pass_id", C.c_int32), ("sequence_stats", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -40,6 +40,8 @@ class Stats(C.Structure):
         ("smem_table_slots", C.c_uint32), ("density_ppm", C.c_uint32), ("log2_bins", C.c_uint32), ("nb_groups_bucket", C.c_uint32), ("nb_hash_regroups", C.c_uint32),
         ("exchange_bytes_out", C.c_uint64), ("ms_exchange", C.c_float), ("nb_solid_regrows", C.c_uint32), ("kmers_in_pass", C.c_uint64),
         ("ms_plan", C.c_float), ("ms_push_wall", C.c_float), ("hist_rebuilt", C.c_uint32), ("scatter_passes", C.c_uint32), ("ms_count_heavy", C.c_float), ("sort_fallbacks", C.c_uint32),
+        ("seq_stats_sequences", C.c_uint64), ("seq_len_min", C.c_uint64), ("seq_len_max", C.c_uint64), ("seq_len_sum", C.c_uint64),
+        ("seq_len_sumsq", C.c_uint64), ("kmers_nb_invalid", C.c_uint64),
     ]
 
     def as_dict(self):

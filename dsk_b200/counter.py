@@ -22,7 +22,7 @@ class GpuCounter:
     def __init__(self, kmer_size=31, abundance_min=2, abundance_max=2**31 - 1, nb_banks=1, per_bank_counts=False,
                  solidity_kind="sum", solid_vec=None, histo2d=False, minimizer_size=10, device=0, count_mode="auto",
                  hash_log2_slots=0, nb_partitions=0, keep_results_on_device=False, stream=None, rank=0, world_size=1, push_chunk_bytes=0,
-                 smem_table_slots=0, bank_histograms=False, nb_passes=1, pass_id=0):
+                 smem_table_slots=0, bank_histograms=False, nb_passes=1, pass_id=0, sequence_stats=False):
         self.L = _lib.lib()
         cfg = _lib.Config()
         self.L.dskgpu_config_default(C.byref(cfg))
@@ -52,6 +52,7 @@ class GpuCounter:
         cfg.smem_table_slots = smem_table_slots
         cfg.bank_histograms = int(bank_histograms)
         cfg.nb_passes, cfg.pass_id = nb_passes, pass_id
+        cfg.sequence_stats = int(sequence_stats)
         self.cfg = cfg
         self.k = kmer_size
         self.h = C.c_void_p()

@@ -20,6 +20,7 @@
 #include "../../include/dskgpu.h"
 #include "kmer_bits.cuh"
 #include "scan.cuh"
+#include "seqstats.cuh"
 #include "superk.cuh"
 #include "count.cuh"
 #include "plan.cuh"
@@ -46,6 +47,7 @@ struct dskgpu_ctx {
     std::string err;
     // device state
     DevBuf ss, ctr, hist, hist2d, bank_hist, raw[2], codes, tabs, tin;
+    DevBuf seqst, seqtab; SeqStats* h_seqst = nullptr;   // per-sequence statistics (cfg.sequence_stats): accumulators, per-tile separator table
     DevBuf recs, meta;                               // staging records (input order)
     DevBuf precs;                                    // partitioned records
     DevBuf cursor, bin_hist, bin_fold, bin2part, work_ctr;
@@ -236,7 +238,10 @@ int dskgpu_create(const dskgpu_config* cfg, dskgpu_ctx** out)
     CK(cudaMallocHost((void**)&ctx->h_hdr, sizeof(PlanHdr)));
     CK(cudaMallocHost((void**)&ctx->h_hll, sizeof(u32) * HLL_M));
     CK(cudaMallocHost((void**)&ctx->h_xtab, sizeof(XchgTab)));
+    CK(cudaMallocHost((void**)&ctx->h_seqst, sizeof(SeqStats)));
+    memset(ctx->h_seqst, 0, sizeof(SeqStats));
     int rc;
+    if ((rc = ensure(ctx, ctx->seqst, sizeof(SeqStats)))) return rc;
     // 2^22 bins (32 MB) stay L2-resident while the records stream by; 2^24 bins (128 MB > L2) tripled k_superkmers on the 9 G
     // k-mer-per-GPU job (69 -> 190 ms, profiles/r03f against r03b).  Partitions finer than a bin come from the record sub-bins.
     ctx->fine_log2 = 22;
@@ -340,6 +345,7 @@ int dskgpu_reset(dskgpu_ctx* ctx)
     use_device(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemsetAsync(ctx->ss.p, 0, sizeof(StreamState), ctx->stream));
+    CK(cudaMemsetAsync(ctx->seqst.p, 0, sizeof(SeqStats), ctx->stream));
     CK(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
     CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN, ctx->stream));
     CK(cudaMemsetAsync(ctx->hist2d.p, 0, sizeof(unsigned long long) * DSKGPU_HISTO_LEN * DSKGPU_HISTO2D_DIM2, ctx->stream));
@@ -365,7 +371,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->bank_hist, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
-                     &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->hll, &ctx->bin2part, &ctx->work_ctr,
+                     &ctx->seqst, &ctx->seqtab, &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->hll, &ctx->bin2part, &ctx->work_ctr,
                      &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
                      &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr,
                      &ctx->lrecs, &ctx->xpeers, &ctx->bcur, &ctx->ghist, &ctx->mkeys, &ctx->pl_ex, &ctx->pl_E, &ctx->pl_H, &ctx->pl_bsum, &ctx->pl_pk, &ctx->pl_pr, &ctx->pl_pl,
@@ -384,6 +390,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     if (ctx->h_hdr) cudaFreeHost(ctx->h_hdr);
     if (ctx->h_hll) cudaFreeHost(ctx->h_hll);
     if (ctx->h_xtab) cudaFreeHost(ctx->h_xtab);
+    if (ctx->h_seqst) cudaFreeHost(ctx->h_seqst);
     if (ctx->h_heavy) cudaFreeHost(ctx->h_heavy);
     if (ctx->h_skeys) cudaFreeHost(ctx->h_skeys);
     if (ctx->h_svals) cudaFreeHost(ctx->h_svals);
@@ -405,7 +412,12 @@ static int open_stream(dskgpu_ctx* ctx, int bank, int fmt)
     ctx->stream_open = true; ctx->cur_bank = bank; ctx->cur_fmt = fmt; ctx->pending_cr = 0;
     return 0;
 }
-static void close_stream(dskgpu_ctx* ctx) { ctx->stream_open = false; ctx->cur_bank = -1; ctx->pending_cr = 0; }
+static void close_stream(dskgpu_ctx* ctx)
+{
+    // the run of codes still open at the end of a bank is a sequence (seqstats.cuh)
+    if (ctx->cfg.sequence_stats && ctx->stream_open) { k_seqstat_close<<<1, 1, 0, ctx->stream>>>(ctx->k, ctx->cur_fmt == FMT_FASTA ? 1 : 0, (SeqStats*)ctx->seqst.p); LAUNCHED(); }
+    ctx->stream_open = false; ctx->cur_bank = -1; ctx->pending_cr = 0;
+}
 
 // scans bytes [lo, hi) of the 16-byte aligned device buffer `raw` and appends super-k-mer records
 static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int next_after)
@@ -463,6 +475,13 @@ static int process_chunk(dskgpu_ctx* ctx, const u8* raw, u64 lo, u64 hi, int nex
         default:        k_scan_emit<FMT_LINES><<<gt, SCAN_THREADS, 0, ctx->stream>>>(raw, lo, hi, tile_first, ss, ss, next_after, (const TileIn*)ctx->tin.p, (u8*)ctx->codes.p); break;
         }
         LAUNCHED();
+    }
+    if (ctx->cfg.sequence_stats) {
+        // sequence lengths from the separators of the codes this chunk added ([carry, total): both still on the device)
+        const u64 ntl = (n + 15 + SQ_TILE - 1) / SQ_TILE + 1;
+        if ((rc = ensure(ctx, ctx->seqtab, ntl * 16))) return rc;
+        k_seqstat_tiles<<<(unsigned)ntl, SQ_THREADS, 0, ctx->stream>>>((const u8*)ctx->codes.p, ss, ctx->k, (unsigned long long*)ctx->seqtab.p, (SeqStats*)ctx->seqst.p); LAUNCHED();
+        k_seqstat_stitch<<<1, 1024, 0, ctx->stream>>>(ss, ctx->k, fmt == FMT_FASTA ? 1 : 0, ntl, (const unsigned long long*)ctx->seqtab.p, (SeqStats*)ctx->seqst.p); LAUNCHED();
     }
     {
         SpanGuard g(ctx, SPAN_SUPERK);
@@ -940,6 +959,7 @@ static int stage_totals(dskgpu_ctx* ctx)
     CK(cudaMemcpyAsync(ctx->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_ss, ctx->ss.p, sizeof(StreamState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_hll, ctx->hll.p, sizeof(u32) * HLL_M, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->cfg.sequence_stats) CK(cudaMemcpyAsync(ctx->h_seqst, ctx->seqst.p, sizeof(SeqStats), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->probes.clear();
     if (ctx->h_ss->err) FAIL(DSKGPU_ERR_FORMAT, "device record scanner rejected the input (flags 0x%x): not plain FASTA / 4-line FASTQ", ctx->h_ss->err);
@@ -952,6 +972,12 @@ static int stage_totals(dskgpu_ctx* ctx)
     ctx->sample_nkm = ctx->h_ctr->sample_nkm; ctx->sample_distinct = ctx->h_ctr->sample_distinct;
     ctx->sample_wmult = ctx->sample_nkm >= 4096 ? (double)ctx->h_ctr->sample_sumsq / (double)ctx->sample_nkm : 0.0;
     ctx->st.nb_sequences = ctx->h_ss->nsep; ctx->st.nb_nucleotides = ctx->h_ss->nbase;
+    if (ctx->cfg.sequence_stats) {
+        const SeqStats& q = *ctx->h_seqst;
+        ctx->st.seq_stats_sequences = q.n; ctx->st.seq_len_sum = q.sum; ctx->st.seq_len_sumsq = q.sumsq;
+        ctx->st.seq_len_max = q.max_len; ctx->st.seq_len_min = q.n ? ~q.min_inv : 0;
+        ctx->st.kmers_nb_invalid = q.windows >= ctx->h_ctr->kmers_valid ? q.windows - ctx->h_ctr->kmers_valid : 0;
+    }
     ctx->st.kmers_nb_valid = ctx->bank_nkm; ctx->st.kmers_in_pass = ctx->local_nkm; ctx->st.nb_superkmers = ctx->local_nrec;
     ctx->st.superkmer_bytes = ctx->local_nrec * (u64)ctx->RW * 8;
     ctx->totals_done = true;

@@ -26,6 +26,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -243,6 +247,7 @@ private:
         dskgpu_config c;
         dskgpu_config_default(&c);
         c.kmer_size = (int32_t)_config._kmerSize;
+        c.sequence_stats = 1;                                      // BankStats (K/BankKmers.hpp:166-215): seq_size_min/max/deviation, kmers_nb_invalid
         // -minimizer-size left at the reference default: sized from the estimated volume, the way ConfigurationAlgorithm
         // sizes nb_partitions (bins must shrink as the job grows; which partition a k-mer lands in is unobservable)
         c.minimizer_size = (int32_t)in->getInt(STR_MINIMIZER_SIZE);
@@ -397,6 +402,63 @@ private:
         checkFormat(dskgpu_push_sync(ctx), ctx, "dskgpu_push_sync");       // the buffers are about to be freed / reused
     }
 
+    /** Decompression ahead of the device: a gzip stream is serial (zlib, ~0.3-0.4 GB/s per stream), but the FILES of an album
+     *  (paired-end R1 / R2, one file per lane, ...) are independent streams.  A device's task list is served in order by its
+     *  reader thread while up to `ahead` helper threads inflate the next files into bounded queues of blocks: several zlib
+     *  streams run at once, the device still sees every bank as one ordered byte stream.  (BankAlbum.cpp:310-348 reads its
+     *  files one after the other on the calling thread.) */
+    struct BlockQueue {
+        std::mutex m; std::condition_variable cv; std::deque<std::vector<char> > q; bool done, cancel; std::string err;
+        BlockQueue() : done(false), cancel(false) {}
+    };
+    static void inflateFile(const std::string& path, BlockQueue* Q, size_t blk, size_t depth)
+    {
+        gzFile gz = gzopen(path.c_str(), "rb");
+        if (!gz) { std::unique_lock<std::mutex> lk(Q->m); Q->err = "unable to open file " + path; Q->done = true; Q->cv.notify_all(); return; }
+        gzbuffer(gz, 1 << 20);
+        for (;;) {
+            std::vector<char> b(blk);
+            const int r = gzread(gz, b.data(), (unsigned)blk);
+            std::unique_lock<std::mutex> lk(Q->m);
+            if (r < 0) { Q->err = "read error on " + path; break; }
+            if (r == 0) break;
+            b.resize((size_t)r);
+            while (Q->q.size() >= depth && !Q->cancel) Q->cv.wait(lk);
+            if (Q->cancel) break;
+            Q->q.push_back(std::vector<char>()); Q->q.back().swap(b);
+            Q->cv.notify_all();
+            if ((size_t)r < blk) break;
+        }
+        gzclose(gz);
+        std::unique_lock<std::mutex> lk(Q->m);
+        Q->done = true; Q->cv.notify_all();
+    }
+    /** next block of a queue (empty vector = end of the file) */
+    static std::vector<char> popBlock(BlockQueue* Q)
+    {
+        std::unique_lock<std::mutex> lk(Q->m);
+        while (Q->q.empty() && !Q->done) Q->cv.wait(lk);
+        if (!Q->err.empty()) throw Exception("%s", Q->err.c_str());
+        std::vector<char> b;
+        if (!Q->q.empty()) { b.swap(Q->q.front()); Q->q.pop_front(); Q->cv.notify_all(); }
+        return b;
+    }
+    /** one whole file from its queue into the context: blocks come from pageable memory, which push_bytes may read
+     *  synchronously (include/dskgpu.h); the block after the current one tells whether the current one is the last */
+    static void feedQueue(dskgpu_ctx* ctx, const FeedTask& t, BlockQueue* Q)
+    {
+        std::vector<char> cur = popBlock(Q);
+        for (;;) {
+            std::vector<char> next;
+            if (!cur.empty()) next = popBlock(Q);
+            const bool last = next.empty();
+            checkFormat(dskgpu_push_bytes(ctx, t.bank, cur.empty() ? "" : cur.data(), cur.size(), DSKGPU_FMT_AUTO, last ? DSKGPU_PUSH_LAST : 0), ctx, "dskgpu_push_bytes");
+            if (last) break;
+            cur.swap(next);
+        }
+        checkFormat(dskgpu_push_sync(ctx), ctx, "dskgpu_push_sync");
+    }
+
     static void feedSequences(dskgpu_ctx* ctx, int bankId, IBank* b)
     {
         // non-file banks (BankStrings, BankRandom, ...): IBank::iterator() -> concatenated sequences
@@ -461,19 +523,41 @@ private:
         }
         const size_t cap = (size_t)64 << 20;
         std::vector<ThreadError> errs(W);
+        // whole files of a task list with at least two of them are inflated ahead by helper threads (DSKGPU_READ_AHEAD files
+        // at a time, default 4 minus the devices sharing the host; 0 = the reader thread alone)
+        const char* ra = getenv("DSKGPU_READ_AHEAD");
+        const size_t ahead = ra ? (size_t)std::max(0, atoi(ra)) : (size_t)std::max<int>(1, 4 / (int)W);
         auto worker = [&](size_t r) {
             char* buf[2] = {(char*)dskgpu_host_alloc(cap), (char*)dskgpu_host_alloc(cap)};
+            const std::vector<FeedTask>& tl = tasks[r];
+            std::vector<size_t> files;                               // tasks served from a queue
+            for (size_t i = 0; i < tl.size(); i++) if (!tl[i].path.empty() && tl[i].whole) files.push_back(i);
+            const bool queued = ahead > 0 && files.size() >= 2;
+            std::vector<BlockQueue*> queues(tl.size(), (BlockQueue*)0);
+            std::vector<std::thread> helpers;
+            size_t started = 0;                                      // files[0 .. started) have a helper
+            auto startUpTo = [&](size_t n) {
+                for (; started < std::min(n, files.size()); started++) {
+                    BlockQueue* Q = new BlockQueue(); queues[files[started]] = Q;
+                    helpers.push_back(std::thread(inflateFile, tl[files[started]].path, Q, (size_t)16 << 20, (size_t)4));
+                }
+            };
             try {
                 if (!buf[0] || !buf[1]) throw Exception("pinned staging allocation failed");
-                for (size_t i = 0; i < tasks[r].size(); i++) {
-                    const FeedTask& ft = tasks[r][i];
+                size_t served = 0;                                   // files already consumed
+                for (size_t i = 0; i < tl.size(); i++) {
+                    const FeedTask& ft = tl[i];
                     if (ft.path.empty()) feedSequences(_ctxs[r], ft.bank, ft.leaf);
+                    else if (queued && ft.whole) { startUpTo(served + 1 + ahead); feedQueue(_ctxs[r], ft, queues[i]); served++; }
                     else feedRange(_ctxs[r], ft, buf, cap);
                 }
             }
             catch (FormatRejected& e) { errs[r].failed = true; errs[r].format = true; errs[r].what = e.what; }
             catch (Exception& e) { errs[r].failed = true; errs[r].what = e.getMessage(); }
             catch (std::exception& e) { errs[r].failed = true; errs[r].what = e.what(); }
+            for (size_t i = 0; i < queues.size(); i++) if (queues[i]) { std::unique_lock<std::mutex> lk(queues[i]->m); queues[i]->cancel = true; queues[i]->cv.notify_all(); }
+            for (size_t i = 0; i < helpers.size(); i++) helpers[i].join();
+            for (size_t i = 0; i < queues.size(); i++) delete queues[i];
             dskgpu_host_free(buf[0]); dskgpu_host_free(buf[1]);
         };
         if (W == 1) worker(0);
@@ -715,6 +799,13 @@ private:
             check(dskgpu_get_stats(ctx, &st), ctx, "dskgpu_get_stats");
             if (pass == 0) {                                         // every pass parses the whole bank: report it once
                 _st.nb_sequences += st.nb_sequences; _st.nb_nucleotides += st.nb_nucleotides; _st.kmers_nb_valid += st.kmers_nb_valid;
+                // BankStats::operator+= over the devices' slices (K/BankKmers.hpp:184-194)
+                if (st.seq_stats_sequences) {
+                    _st.seq_len_min = _st.seq_stats_sequences ? std::min(_st.seq_len_min, st.seq_len_min) : st.seq_len_min;
+                    _st.seq_len_max = std::max(_st.seq_len_max, st.seq_len_max);
+                }
+                _st.seq_stats_sequences += st.seq_stats_sequences; _st.seq_len_sum += st.seq_len_sum; _st.seq_len_sumsq += st.seq_len_sumsq;
+                _st.kmers_nb_invalid += st.kmers_nb_invalid;
             }
             _st.nb_superkmers += st.nb_superkmers; _st.superkmer_bytes += st.superkmer_bytes;
             _st.kmers_nb_distinct += st.kmers_nb_distinct; _st.kmers_nb_solid += st.kmers_nb_solid;
@@ -781,9 +872,17 @@ private:
         getInfo()->add(2, "bank_total_nt", "%lld", (long long)_st.nb_nucleotides);
         getInfo()->add(2, "sequences");
         getInfo()->add(3, "seq_number", "%ld", (long)_st.nb_sequences);
-        getInfo()->add(3, "seq_size_mean", "%.1f", _st.nb_sequences ? (double)_st.nb_nucleotides / (double)_st.nb_sequences : 0.0);
+        const double seqMean = _st.nb_sequences ? (double)_st.nb_nucleotides / (double)_st.nb_sequences : 0.0;
+        if (_st.seq_stats_sequences) {                              // K/SortingCountAlgorithm.cpp:735-738, BankStats::getSeqDeviation
+            getInfo()->add(3, "seq_size_min", "%ld", (long)_st.seq_len_min);
+            getInfo()->add(3, "seq_size_max", "%ld", (long)_st.seq_len_max);
+        }
+        getInfo()->add(3, "seq_size_mean", "%.1f", seqMean);
+        if (_st.seq_stats_sequences)
+            getInfo()->add(3, "seq_size_deviation", "%.1f", sqrt(std::max(0.0, (double)_st.seq_len_sumsq / (double)_st.seq_stats_sequences - seqMean * seqMean)));
         getInfo()->add(2, "kmers");
         getInfo()->add(3, "kmers_nb_valid", "%lld", (long long)_st.kmers_nb_valid);
+        if (_st.seq_stats_sequences) getInfo()->add(3, "kmers_nb_invalid", "%lld", (long long)_st.kmers_nb_invalid);
         getInfo()->add(1, "stats");
         getInfo()->add(2, "temp_files");
         getInfo()->add(3, "nb_superkmers", "%lld", (long long)_st.nb_superkmers);

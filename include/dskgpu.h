@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DSKGPU_ABI_VERSION   3
+#define DSKGPU_ABI_VERSION   4
 #define DSKGPU_MAX_BANKS     16
 #define DSKGPU_HISTO_LEN     10001          /* bins 0..10000 (Histogram.hpp:92, length 10000) */
 #define DSKGPU_HISTO2D_DIM2  11             /* bins 0..10   (CountProcessorHistogram.hpp:173-184) */
@@ -90,7 +90,10 @@ typedef struct dskgpu_config {
     int32_t  pass_id;                            /*   pass `pass_id` (the reference's `minimizer % nbPass == pass`, SortingCountAlgorithm.cpp:1086); the
                                                     caller pushes the whole input once per pass (dskgpu_set_pass + dskgpu_reset in between) and the
                                                     results of the passes are disjoint: what makes a job whose records exceed HBM fit */
-    int32_t  reserved[3];
+    int32_t  sequence_stats;                     /* 1: also gather the per-sequence statistics of BankStats (K/BankKmers.hpp:166-215): seq_size_min/max,
+                                                  *    sum of squares (deviation) and the k-mer windows of every sequence (kmers_nb_invalid = windows - valid).
+                                                  *    One more read of the code stream per chunk; the reference gets them for free while parsing */
+    int32_t  reserved[2];
 } dskgpu_config;
 
 /* stats block: the keys of SortingCountAlgorithm::getInfo() (SortingCountAlgorithm.cpp:728-780) */
@@ -128,6 +131,12 @@ typedef struct dskgpu_stats {
     uint32_t scatter_passes;        /* 0: single-pass partition scatter; n: MSD multi-split passes (jobs with millions of partitions) */
     float    ms_count_heavy;        /* part of ms_count spent on the heavy partitions (gather + global table / sort / bucket paths) */
     uint32_t sort_fallbacks;        /* ordering of the solid set: neighbourhood fix-up gave up (long groups of equal prefixes), full-width sort ran */
+    /* per-sequence statistics (cfg.sequence_stats = 1; else all zero): bank/sequences/seq_size_{min,max,mean,deviation}, bank/kmers/kmers_nb_invalid */
+    uint64_t seq_stats_sequences;   /* sequences measured (== nb_sequences) */
+    uint64_t seq_len_min, seq_len_max;
+    uint64_t seq_len_sum;           /* == nb_nucleotides */
+    uint64_t seq_len_sumsq;         /* BankStats::sequencesTotalLengthSquare */
+    uint64_t kmers_nb_invalid;      /* k-mer windows of all sequences that hold a non-ACGT letter (K/Sequence2SuperKmer.hpp:95-108) */
 } dskgpu_stats;
 
 /* fills *cfg with the reference defaults (SortingCountAlgorithm.cpp:208-231) */
@@ -136,7 +145,7 @@ void dskgpu_config_default(dskgpu_config* cfg);
 /* replaces: the part of ConfigurationAlgorithm::execute (ConfigurationAlgorithm.cpp:245-467) that sizes the partitioning
  * from the estimated volume.  Returns the minimizer length to put in cfg->minimizer_size for a job of `expected_kmers`
  * k-mers over ALL ranks (k < 32: 10 up to 150 M k-mers, 11 up to 1.5 G, 12 up to 12 G, 14 beyond; k >= 32, whose 128-bit
- * tables hold fewer k-mers: 10 up to 40 M, 12 up to 150 M, 14 beyond; clipped to kmer_size-1): a partition cannot be lighter
+ * tables hold fewer k-mers: 10 up to 40 M, 12 up to 150 M, 14 up to 16 G, 15 beyond; clipped to kmer_size-1): a partition cannot be lighter
  * than its heaviest minimizer bin, so the bins must shrink as the job grows to stay inside a shared-memory table.
  * Which partition a k-mer lands in is unobservable in the results.  Host-only, no device needed. */
 int dskgpu_suggest_minimizer_size(uint64_t expected_kmers, int kmer_size);

@@ -160,6 +160,23 @@ def test_plugin_surface_with_the_reference_processors(t, tmp_path):
     assert {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows if int(r.split("\t")[1])} == t["hist"]
 
 
+BANKSTATS = load_json("ref_bankstats.json")["runs"]
+
+
+@need_bins
+@pytest.mark.parametrize("t", BANKSTATS, ids=["+".join(t["files"]) for t in BANKSTATS])
+def test_cli_bank_statistics_as_the_reference_prints_them(t, tmp_path):
+    """bank / sequences / kmers keys of `dsk -verbose 1` (K/SortingCountAlgorithm.cpp:728-742): same strings from `dsk_gpu`"""
+    import re
+    tmp = str(tmp_path)
+    a = ["-file", ",".join(os.path.join(INPUTS, f) for f in t["files"]), "-kmer-size", str(t["k"]), "-abundance-min", "2", "-out", os.path.join(tmp, "o"), "-verbose", "1"]
+    out = run([DSK_GPU] + a, tmp)
+    for key in ("bank_total_nt", "seq_number", "seq_size_min", "seq_size_max", "seq_size_mean", "seq_size_deviation", "kmers_nb_valid", "kmers_nb_invalid"):
+        m = re.search(r"^\s*%s\s*:\s*(\S+)\s*$" % re.escape(key), out, re.M)
+        assert m, key
+        assert m.group(1) == t[key], (key, m.group(1), t[key])
+
+
 HISTOMAX = load_json("ref_runs_histomax.json")["runs"]
 
 

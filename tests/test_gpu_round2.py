@@ -359,3 +359,50 @@ def test_multi_process_exchange_under_torchrun():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, MGPU_SHORT="1"))
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "MISMATCH" not in p.stdout
+
+
+# ---------------------------------------------------------------- per-sequence statistics (K/BankKmers.hpp:166-215)
+BANKSTATS = __import__("util").load_json("ref_bankstats.json")["runs"]
+
+
+@pytest.mark.parametrize("chunk", [0, 4096, 1 << 16])
+@pytest.mark.parametrize("t", BANKSTATS, ids=["+".join(t["files"]) for t in BANKSTATS])
+def test_sequence_statistics_match_the_reference(t, chunk):
+    """seq_number / seq_size_min / max / mean / deviation and kmers_nb_invalid as `dsk -verbose 1` prints them (goldens from the
+    unmodified reference), computed on the device from the record separators of the code stream (seqstats.cuh): FASTA
+    (separator in front of a record: the last sequence is closed by the end of the stream), FASTQ (separator behind), empty
+    records, sequences longer than a tile, several banks; push granularities that cut sequences at chunk boundaries"""
+    from util import read_input
+    import math
+    with GpuCounter(kmer_size=t["k"], abundance_min=2, nb_banks=len(t["files"]), sequence_stats=True, push_chunk_bytes=chunk) as eng:
+        for b, f in enumerate(t["files"]):
+            eng.push_bytes(read_input(f), bank=b)
+        eng.finish()
+        st = eng.stats()
+    n = st["seq_stats_sequences"]
+    assert n == st["nb_sequences"] == int(t["seq_number"])
+    assert st["seq_len_sum"] == st["nb_nucleotides"] == int(t["bank_total_nt"])
+    assert st["seq_len_min"] == int(t["seq_size_min"]) and st["seq_len_max"] == int(t["seq_size_max"])
+    mean = st["seq_len_sum"] / n
+    assert "%.1f" % mean == t["seq_size_mean"]
+    assert "%.1f" % math.sqrt(max(0.0, st["seq_len_sumsq"] / n - mean * mean)) == t["seq_size_deviation"]
+    assert st["kmers_nb_valid"] == int(t["kmers_nb_valid"]) and st["kmers_nb_invalid"] == int(t["kmers_nb_invalid"])
+
+
+def test_sequence_statistics_of_pushed_reads_and_default_off():
+    # one-sequence-per-line pushes (dskgpu_push_reads: what the adapter feeds from IBank::iterator), a last line without newline
+    seqs = ["ACGTACGTAC" * 7, "A" * 40, "", "ACGTNACGT" * 9, "C" * 5]
+    k = 21
+    with GpuCounter(kmer_size=k, abundance_min=1, sequence_stats=True) as eng:
+        eng.push_reads([s.encode() for s in seqs if s])
+        eng.finish()
+        st = eng.stats()
+    lens = [len(s) for s in seqs if s]
+    assert st["seq_stats_sequences"] == len(lens) and st["seq_len_min"] == min(lens) and st["seq_len_max"] == max(lens)
+    assert st["seq_len_sum"] == sum(lens) and st["seq_len_sumsq"] == sum(x * x for x in lens)
+    assert st["kmers_nb_invalid"] == sum(max(0, x - k + 1) for x in lens) - st["kmers_nb_valid"]
+    with GpuCounter(kmer_size=k, abundance_min=1) as eng:                    # not asked for: nothing gathered, nothing launched for it
+        eng.push_reads([s.encode() for s in seqs if s])
+        eng.finish()
+        st = eng.stats()
+    assert st["seq_stats_sequences"] == 0 and st["kmers_nb_invalid"] == 0

@@ -31,7 +31,7 @@ def test_abi_exports_every_declared_symbol(L):
     assert declared == set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.dskgpu_abi_version() == 3
+    assert L.dskgpu_abi_version() == 4
 
 
 def test_struct_sizes_match(L):

@@ -66,6 +66,7 @@ PYEOF
               echo "memcheck wide exit $?"; tail -3 "$OUT/sanitizer_memcheck_wide.log"; tail -2 "$OUT/sanitizer_memcheck_wide.out"
               timeout 900 compute-sanitizer --tool racecheck --log-file "$OUT/sanitizer_racecheck_split.log" python -m pytest tests/test_gpu_parity.py -x -q -k "tiny_smem_table_overflow_splits and (c1_k31 or c1_k63) and 64" > "$OUT/sanitizer_racecheck_split.out" 2>&1
               echo "racecheck split exit $?"; tail -3 "$OUT/sanitizer_racecheck_split.log"; tail -2 "$OUT/sanitizer_racecheck_split.out" ;;
+    pyseq)    timeout 900 python -m pytest tests/test_gpu_round2.py tests/test_cli_dropin.py -q -k "sequence_statistics or bank_statistics or c123 or c1234 or two_contexts or larger_than_one" > "$OUT/pytest_seq.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_seq.log"; tail -40 "$OUT/pytest_seq.log" | cut -c1-700 ;;
     pymin)    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "minimizer_sizes or tiny_smem or record_sub or fine_histogram or heavy" > "$OUT/pytest_min.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_min.log"; tail -6 "$OUT/pytest_min.log" ;;
     *)        echo "unknown step $step" ;;
   esac
