@@ -562,5 +562,92 @@ __global__ void __launch_bounds__(256) k_rle_emit(const u64* __restrict__ keys, 
     if (threadIdx.x == 0 && s_distinct) atomicAdd(&ctr->distinct_n, (unsigned long long)s_distinct);
 }
 
+// ---- sort path of the wide spans (192 / 256-bit keys): order by a 64-bit hash, verify, count ---------------------------------
+// A full-width LSD sort of 24 / 32-byte keys costs 24 - 32 passes over the whole array (k = 95: 104 of the 116 ms of a 187 M
+// k-mer step, profiles/r04j).  Equal k-mers only have to MEET, not to be in k-mer order (the solid set is ordered afterwards):
+// the keys stay where k_expand_keys wrote them, a (64-bit hash, index) pair per key is sorted in 8 passes, and
+//   k_verify_hashed : every element compares its FULL key with its predecessor's when their hashes are equal -- if any pair
+//                     differs, two different k-mers share a hash (probability ~2^-8 per 2^28-key group) and the group is
+//                     redone by the full-width sort: the result is exact either way;
+//   k_rle_emit_hashed: heads of hash runs gallop to the run end on the hash array, gather their key through the index, run the
+//                     processor chain (per-bank counts through the index as well).
+template <int KW>
+__global__ void __launch_bounds__(256) k_hash_keys(const u64* __restrict__ keys, u64 n, u64* __restrict__ hashes, u32* __restrict__ idx, u64 hmask)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        Kmer<KW> x;
+#pragma unroll
+        for (int q = 0; q < KW; q++) x.w[q] = keys[i * KW + q];
+        hashes[i] = kmer_hash(x) & hmask;                          // (hmask: all ones; the tests narrow it to provoke collisions)
+        idx[i] = (u32)i;
+    }
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256) k_verify_hashed(const u64* __restrict__ hashes, const u32* __restrict__ idx, const u64* __restrict__ keys, u64 n,
+                                                       unsigned int* flag)
+{
+    bool bad = false;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (u64)gridDim.x * blockDim.x) {
+        if (hashes[i] != hashes[i - 1]) continue;
+        const u64 a = idx[i], b = idx[i - 1];
+#pragma unroll
+        for (int q = 0; q < KW; q++) bad |= keys[a * KW + q] != keys[b * KW + q];
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicExch(flag, 1u);
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256) k_rle_emit_hashed(const u64* __restrict__ hashes, const u32* __restrict__ idx, const u64* __restrict__ keys,
+                                                         const u32* __restrict__ banks, u64 n, SolidityParams sp, u64* out_keys, u32* out_vals, u64 out_cap,
+                                                         unsigned long long* g_hist, unsigned long long* g_hist2d, Counters* ctr)
+{
+    __shared__ u32 s_hist[HIST_SMEM_BINS];
+    __shared__ u32 s_h2[11 * H2_SMEM_I1];
+    __shared__ u32 s_distinct;
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < 11 * H2_SMEM_I1; i += blockDim.x) s_h2[i] = 0;
+    if (threadIdx.x == 0) s_distinct = 0;
+    __syncthreads();
+    constexpr int RI = 4;
+    __shared__ AppendSmem s_app;
+    u32 ndist = 0;
+    const u64 per_it = (u64)blockDim.x * gridDim.x * RI;
+    const u64 nloop = (n + per_it - 1) / per_it;
+    for (u64 it = 0; it < nloop; it++) {
+        Kmer<KW> sk[RI]; int32_t sv[RI]; u32 solidm = 0;
+#pragma unroll
+        for (int r = 0; r < RI; r++) {
+            const u64 i = it * per_it + ((u64)r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+            sv[r] = 0;
+            if (i >= n) continue;
+            const u64 h = hashes[i];
+            if (i != 0 && hashes[i - 1] == h) continue;            // not the head of its run
+            u64 step = 1, lo = i;                                  // hashes[lo] == h ; find the last equal
+            while (lo + step < n && hashes[lo + step] == h) { lo += step; step <<= 1; }
+            u64 hi = (lo + step < n) ? lo + step : n;
+            while (hi - lo > 1) { const u64 mid = lo + (hi - lo) / 2; if (hashes[mid] == h) lo = mid; else hi = mid; }
+            const u64 cnt = lo - i + 1;
+            u32 cv[MAXB]; int32_t sum = 0;
+            if (sp.nbanks == 1) cv[0] = (u32)cnt;
+            else { for (int b = 0; b < sp.nbanks; b++) cv[b] = 0; for (u64 j = i; j <= lo; j++) cv[banks[idx[j]]]++; }
+            ndist++;
+            if (process_counts(cv, sp, s_hist, g_hist, g_hist2d, &sum, s_h2)) {
+                const u64 a = idx[i];
+#pragma unroll
+                for (int q = 0; q < KW; q++) sk[r].w[q] = keys[a * KW + q];
+                sv[r] = sum; solidm |= 1u << r;
+            }
+        }
+        block_append<KW, RI>(solidm, sk, sv, out_keys, out_vals, out_cap, ctr, &s_app, (int)(it & 1));
+    }
+    ndist = __reduce_add_sync(0xFFFFFFFFu, ndist);
+    if ((threadIdx.x & 31) == 0 && ndist) atomicAdd(&s_distinct, ndist);
+    __syncthreads();
+    flush_hist(s_hist, g_hist);
+    if (sp.histo2d) flush_hist2d(s_h2, g_hist2d);
+    if (threadIdx.x == 0 && s_distinct) atomicAdd(&ctr->distinct_n, (unsigned long long)s_distinct);
+}
+
 #endif  // __CUDACC__
 }  // namespace dsk

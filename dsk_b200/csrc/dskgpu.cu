@@ -56,6 +56,7 @@ struct dskgpu_ctx {
     DevBuf tkeys, tcounts;                           // hash table
     DevBuf skeys[2], svals[2];                       // solid (k-mer, abundance) ping-pong
     DevBuf keys[2], banks[2];                        // sort path ping-pong
+    DevBuf whash[2], widx[2];                        // wide spans: (64-bit hash, index) pairs of the keys, ping-pong
     DevBuf rs_hist, rs_status, rs_tilectr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_probe[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_push0 = nullptr, ev_push1 = nullptr; bool push_timed = false;   // first / last push kernel of the job (wall time of the push phase)
@@ -372,7 +373,7 @@ void dskgpu_destroy(dskgpu_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->ss, &ctx->ctr, &ctx->hist, &ctx->hist2d, &ctx->bank_hist, &ctx->raw[0], &ctx->raw[1], &ctx->codes, &ctx->tabs, &ctx->tin,
                      &ctx->seqst, &ctx->seqtab, &ctx->recs, &ctx->meta, &ctx->precs, &ctx->cursor, &ctx->bin_hist, &ctx->bin_fold, &ctx->sample_recs, &ctx->stab_keys, &ctx->stab_counts, &ctx->hll, &ctx->bin2part, &ctx->work_ctr,
-                     &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->keys[0],
+                     &ctx->tkeys, &ctx->tcounts, &ctx->skeys[0], &ctx->skeys[1], &ctx->svals[0], &ctx->svals[1], &ctx->whash[0], &ctx->whash[1], &ctx->widx[0], &ctx->widx[1], &ctx->keys[0],
                      &ctx->keys[1], &ctx->banks[0], &ctx->banks[1], &ctx->rs_hist, &ctx->rs_status, &ctx->rs_tilectr,
                      &ctx->lrecs, &ctx->xpeers, &ctx->bcur, &ctx->ghist, &ctx->mkeys, &ctx->pl_ex, &ctx->pl_E, &ctx->pl_H, &ctx->pl_bsum, &ctx->pl_pk, &ctx->pl_pr, &ctx->pl_pl,
                      &ctx->pl_newid, &ctx->pl_nvals, &ctx->pl_hdr, &ctx->gk_q, &ctx->gr_q, &ctx->lcnt_q, &ctx->loff, &ctx->xX, &ctx->xtab, &ctx->xS, &ctx->hoff, &ctx->hrecs};
@@ -727,6 +728,41 @@ static int count_by_sort(dskgpu_ctx* ctx, const u64* recs, u64 rb, u64 re, u64 n
     CK(cudaMemsetAsync(&ctr->expand_cursor, 0, 8, ctx->stream));
     const unsigned gb = (unsigned)std::min<u64>((re - rb + 255) / 256, 148 * 16);
     k_expand_keys<KW><<<gb, 256, 0, ctx->stream>>>(recs, rb, re, ctx->k, (u64*)ctx->keys[0].p, (u32*)ctx->banks[0].p, ctx->NB, ctr); LAUNCHED();
+    if constexpr (KW > 2) {
+        // wide keys: equal k-mers are brought together by a 64-bit hash (8 passes over 12 bytes per key instead of 24 - 32 passes
+        // over 24 - 32), the full keys are only compared (count.cuh).  DSKGPU_WIDE_FULLSORT=1 keeps the full-width sort;
+        // DSKGPU_TEST_HASH_BITS narrows the hash so that the tests see collisions (-> verified, redone by the full sort)
+        if (!getenv("DSKGPU_WIDE_FULLSORT") && nk < ((u64)1 << 31)) {
+            u64 hmask = ~0ULL;
+            if (const char* e = getenv("DSKGPU_TEST_HASH_BITS")) { const int b = std::min(64, std::max(1, atoi(e))); hmask = b >= 64 ? ~0ULL : (((u64)1 << b) - 1); }
+            for (int i = 0; i < 2; i++) {
+                if ((rc = ensure(ctx, ctx->whash[i], nk * 8 + 64))) return rc;
+                if ((rc = ensure(ctx, ctx->widx[i], nk * 4 + 64))) return rc;
+            }
+            const unsigned gh = (unsigned)std::min<u64>((nk + 255) / 256, (u64)ctx->num_sms * 16);
+            k_hash_keys<KW><<<gh, 256, 0, ctx->stream>>>((const u64*)ctx->keys[0].p, nk, (u64*)ctx->whash[0].p, (u32*)ctx->widx[0].p, hmask); LAUNCHED();
+            u64* hk[2] = {(u64*)ctx->whash[0].p, (u64*)ctx->whash[1].p};
+            u32* hv[2] = {(u32*)ctx->widx[0].p, (u32*)ctx->widx[1].p};
+            int hres = 0;
+            if ((rc = radix_sort<1, true>(ctx, hk, hv, nk, 8, &hres))) return rc;
+            CK(cudaMemsetAsync(&ctr->sort_fallback, 0, sizeof(unsigned int), ctx->stream));
+            k_verify_hashed<KW><<<gh, 256, 0, ctx->stream>>>(hk[hres], hv[hres], (const u64*)ctx->keys[0].p, nk, &ctr->sort_fallback); LAUNCHED();
+            CK(cudaMemcpyAsync(ctx->h_nrec_probe + 6, &ctr->sort_fallback, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const bool collided = *(volatile unsigned int*)(ctx->h_nrec_probe + 6) != 0;
+            CK(cudaMemsetAsync(&ctr->sort_fallback, 0, sizeof(unsigned int), ctx->stream));
+            if (!collided) {
+                const unsigned gr = (unsigned)std::min<u64>((nk + 255) / 256, 148 * 16);
+                k_rle_emit_hashed<KW><<<gr, 256, 0, ctx->stream>>>(hk[hres], hv[hres], (const u64*)ctx->keys[0].p, (const u32*)ctx->banks[0].p, nk, make_sp(ctx),
+                                                                   (u64*)ctx->skeys[0].p, (u32*)ctx->svals[0].p, out_cap,
+                                                                   (unsigned long long*)ctx->hist.p, (unsigned long long*)ctx->hist2d.p, ctr); LAUNCHED();
+                ctx->st.nb_groups_sort++;
+                CK(cudaGetLastError());
+                return 0;
+            }
+            ctx->st.sort_fallbacks++;                               // two k-mers shared a hash: the exact full-width sort (keys[0] is intact)
+        }
+    }
     u64* kk[2] = {(u64*)ctx->keys[0].p, (u64*)ctx->keys[1].p};
     u32* vv[2] = {(u32*)ctx->banks[0].p, (u32*)ctx->banks[1].p};
     const int npass = (2 * ctx->k + 7) / 8;

@@ -175,3 +175,30 @@ def test_wide_pass_loop_and_auto_cutoff():
     assert sc.getInfo()["cutoffs_auto"] == ref.cutoffs
     keys, cnt = sc.getSolidCounts()
     assert_equals_wide_oracle(keys, cnt, sc.getHistogram()[0], ref, 100)
+
+
+@pytest.mark.parametrize("k,bits", [(80, 12), (127, 20), (100, 64)])
+def test_wide_hash_ordering_collisions_fall_back_to_the_full_sort(k, bits, monkeypatch):
+    """the wide spans bring equal k-mers together by sorting a 64-bit hash of the key; when two different k-mers share a hash
+    (forced here by narrowing the hash) the verification pass must notice and the group must be redone by the exact
+    full-width sort; with the full hash the fast path runs.  Same results either way, and with DSKGPU_WIDE_FULLSORT=1."""
+    buf, n, _ = reads_fasta(G=150_000, coverage=25, L=250, err=0.01, seed=1200 + k)
+    data = buf[:n].tobytes()
+    ref = oracle.count_files([data], k, abundance_min=2)
+    monkeypatch.setenv("DSKGPU_TEST_HASH_BITS", str(bits))
+    with GpuCounter(kmer_size=k, abundance_min=2) as eng:
+        eng.push_bytes(data)
+        eng.finish()
+        st = eng.stats()
+        assert (st["sort_fallbacks"] > 0) == (bits < 64)
+        kk, cc = eng.solid()
+        assert st["kmers_nb_distinct"] == ref.nb_distinct
+        assert_equals_wide_oracle(kk, cc, eng.histogram()[0], ref, k)
+    monkeypatch.delenv("DSKGPU_TEST_HASH_BITS")
+    monkeypatch.setenv("DSKGPU_WIDE_FULLSORT", "1")
+    with GpuCounter(kmer_size=k, abundance_min=2) as eng:
+        eng.push_bytes(data)
+        eng.finish()
+        kk, cc = eng.solid()
+        assert eng.stats()["sort_fallbacks"] == 0
+        assert_equals_wide_oracle(kk, cc, eng.histogram()[0], ref, k)

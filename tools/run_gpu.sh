@@ -67,6 +67,14 @@ PYEOF
               timeout 900 compute-sanitizer --tool racecheck --log-file "$OUT/sanitizer_racecheck_split.log" python -m pytest tests/test_gpu_parity.py -x -q -k "tiny_smem_table_overflow_splits and (c1_k31 or c1_k63) and 64" > "$OUT/sanitizer_racecheck_split.out" 2>&1
               echo "racecheck split exit $?"; tail -3 "$OUT/sanitizer_racecheck_split.log"; tail -2 "$OUT/sanitizer_racecheck_split.out" ;;
     pyseq)    timeout 900 python -m pytest tests/test_gpu_round2.py tests/test_cli_dropin.py -q -k "sequence_statistics or bank_statistics or c123 or c1234 or two_contexts or larger_than_one" > "$OUT/pytest_seq.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_seq.log"; tail -40 "$OUT/pytest_seq.log" | cut -c1-700 ;;
+    benchwide) for kk in ${WIDE_KS:-95 127}; do timeout 600 python bench.py --kmer-size $kk --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > "$OUT/bench_k$kk.json" 2> "$OUT/bench_k$kk.err"; python - "$OUT/bench_k$kk.json" <<'PYEOF'
+import json, sys
+for line in open(sys.argv[1]):
+    if line.startswith('{'):
+        d = json.loads(line)
+        print(sys.argv[1], '%.2f G/s %.1f ms' % (d['value'], d['ms_per_step']), {k: round(v, 1) for k, v in d['stage_ms'].items()}, d['engine'], d['checks'])
+PYEOF
+              tail -2 "$OUT/bench_k$kk.err"; done ;;
     pymin)    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "minimizer_sizes or tiny_smem or record_sub or fine_histogram or heavy" > "$OUT/pytest_min.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_min.log"; tail -6 "$OUT/pytest_min.log" ;;
     *)        echo "unknown step $step" ;;
   esac
