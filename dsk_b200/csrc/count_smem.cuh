@@ -506,8 +506,10 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                     // the owner of item x is found among the prefixes of records rcur .. rcur + 31 (one value per lane)
                     for (u32 x0 = lo; x0 < hi; x0 += 32) {
                         // the table overflowed (somebody ran out of probes): the pass is lost, every further insert into the full
-                        // table would walk CS_MAXPROBE slots for nothing -- drop the ring and leave (the split passes redo it all)
-                        if (__any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile u32*>(&s_ovf) != ovf_seen)) { qc = 0; break; }
+                        // table would walk CS_MAXPROBE slots for nothing -- drop the ring and leave (the split passes redo it all).
+                        // The flag is READ here and TESTED at the bottom of the iteration: its shared-memory latency hides behind
+                        // the iteration instead of stalling its first instruction (measured: 3 % of the kernel when tested at once)
+                        const u32 ovf_peek = *reinterpret_cast<volatile u32*>(&s_ovf);
                         const u32 x = x0 + (u32)lane;
                         const u32 rl = rcur + (u32)lane;
                         const u32 el = rl < nc ? s_pref[rl] : 0xFFFFFFFFu;             // (item prefix | record << 16) of compacted record rcur + lane
@@ -575,11 +577,13 @@ __global__ void __launch_bounds__(CS_THREADS, CS_CTAS_PER_SM) k_count_smem(const
                                 while (qc >= 32u) ring_serve();                        // (a round may hand every entry back: the ring must be under 32 before the next push)
                             }
                         }
+                        if (__any_sync(0xFFFFFFFFu, ovf_peek != ovf_seen)) { qc = 0; break; }
                     }
                 }
                 while (qc) {
-                    if (__any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile u32*>(&s_ovf) != ovf_seen)) { qc = 0; break; }
+                    const u32 ovf_peek = *reinterpret_cast<volatile u32*>(&s_ovf);
                     ring_serve();
+                    if (__any_sync(0xFFFFFFFFu, ovf_peek != ovf_seen)) { qc = 0; break; }
                 }
                 __syncthreads();                                                   // inserts of the slice done, job buffer free
                 // (uniform: nobody inserts between this barrier and the next ones)  a lost pass skips its remaining slices; the

@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const TileTab* __restrict__
     u64 b = (u64)t * per, e = b + per; if (e > ntiles) e = ntiles; if (b > ntiles) b = ntiles;
     // phase 1: table of my run, for all 4 start states
     u32 st[4] = {0, 1, 2, 3}; u32 cn[4] = {0, 0, 0, 0};
+#pragma unroll 8                                                  // the loads of a batch do not depend on the chain: issued together
     for (u64 i = b; i < e; i++) {
         TileTab tt = tabs[i];
 #pragma unroll
@@ -440,6 +441,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const TileTab* __restrict__
     u32 s = (exl.st >> (2 * s0)) & 3;
     u64 base = s0 == 0 ? exl.cnt[0] : s0 == 1 ? exl.cnt[1] : s0 == 2 ? exl.cnt[2] : exl.cnt[3];
     // phase 3: replay my run with the true start state
+#pragma unroll 8
     for (u64 i = b; i < e; i++) {
         TileTab tt = tabs[i];
         TileIn ti; ti.base = base; ti.state = s; ti.pad = 0; tin[i] = ti;

@@ -494,15 +494,24 @@ __global__ void __launch_bounds__(256) k_sample_select(const u64* __restrict__ r
     const ulonglong2* src = reinterpret_cast<const ulonglong2*>(recs);
     ulonglong2* dst = reinterpret_cast<ulonglong2*>(out);
     const u64 nrec = *nrec_dev;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (u64)gridDim.x * blockDim.x) {
-        const u32 mt = rec_meta[i];
-        if ((mt & META_BIN_MASK) >= thresh) continue;
+    auto take = [&](u64 i, u32 mt) {
         const unsigned long long nk = mt >> 24;
-        if (atomicAdd(&ctr->sample_nkm, nk) + nk > km_cap) { atomicAdd(&ctr->sample_nkm, ~nk + 1ULL); continue; }   // sample full (a record holds >= 1 k-mer,
-        const u64 d = atomicAdd(&ctr->sample_nrec, 1ULL);                                                              //  so records <= km_cap as well)
+        if (atomicAdd(&ctr->sample_nkm, nk) + nk > km_cap) { atomicAdd(&ctr->sample_nkm, ~nk + 1ULL); return; }   // sample full (a record holds >= 1 k-mer,
+        const u64 d = atomicAdd(&ctr->sample_nrec, 1ULL);                                                            //  so records <= km_cap as well)
 #pragma unroll
         for (int q = 0; q < RW / 2; q++) dst[(RW / 2) * d + q] = src[(RW / 2) * i + q];
+    };
+    // four metas per 16-byte load (the buffer is 256-byte aligned); one record in ~750 is selected
+    const uint4* m4 = reinterpret_cast<const uint4*>(rec_meta);
+    const u64 n4 = nrec / 4;
+    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (u64)gridDim.x * blockDim.x) {
+        const uint4 v = m4[g];
+        if ((v.x & META_BIN_MASK) < thresh) take(4 * g, v.x);
+        if ((v.y & META_BIN_MASK) < thresh) take(4 * g + 1, v.y);
+        if ((v.z & META_BIN_MASK) < thresh) take(4 * g + 2, v.z);
+        if ((v.w & META_BIN_MASK) < thresh) take(4 * g + 3, v.w);
     }
+    if (blockIdx.x == 0 && threadIdx.x < (nrec & 3)) { const u64 i = 4 * n4 + threadIdx.x; const u32 mt = rec_meta[i]; if ((mt & META_BIN_MASK) < thresh) take(i, mt); }
 }
 
 #endif  // __CUDACC__
