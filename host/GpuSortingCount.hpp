@@ -289,7 +289,7 @@ private:
         if (plugin) {
             // every distinct k-mer goes to the processors, with its count: nothing is filtered or histogrammed on the device.
             // A CountVector holds one count per bank (K/PartitionsCommand.cpp:540-541); the C ABI delivers one count per k-mer.
-            if (c.nb_banks != 1) throw Exception("count processors plugged into the device path see one count per k-mer: %d banks given (use the default processors)", (int)c.nb_banks);
+            // Several banks: one device job per bank, merged on the host into one CountVector per k-mer (executeWithProcessors).
             c.solidity_kind = DSKGPU_SOLIDITY_SUM; c.per_bank_counts = 0; c.histo2d = 0; c.bank_histograms = 0;
             for (size_t i = 0; i < (size_t)DSKGPU_MAX_BANKS; i++) c.abundance_min[i] = 1;
             c.abundance_max = 2147483647LL;
@@ -485,7 +485,7 @@ private:
     }
 
     /** Splits the banks into per-device task lists and runs one reader thread per device. */
-    void feedBanks()
+    void feedBanks(int onlyBank = -1)
     {
         const size_t W = _ctxs.size();
         std::vector<std::vector<FeedTask> > tasks(W);
@@ -494,6 +494,7 @@ private:
         const std::vector<IBank*> top = _bank->getBanks();
         const bool composite = _config._nb_banks > 1 && top.size() == _config._nb_banks;
         for (size_t t = 0; t < (composite ? top.size() : 1); t++) {
+            if (onlyBank >= 0 && (int)t != onlyBank) continue;     // plug-in mode with several banks: one device job per bank
             std::vector<IBank*> leaves;
             collectLeaves(composite ? top[t] : _bank, leaves);
             for (size_t i = 0; i < leaves.size(); i++) {
@@ -664,12 +665,15 @@ private:
     {
         const size_t W = _ctxs.size();
         memset(&_st, 0, sizeof _st); _nbSolidWritten = 0;
+        const size_t B = (size_t)std::max<size_t>(1, _config._nb_banks);
+        if (B > 1) _config._nb_partitions = 1;                      // the merged stream of a pass is ONE ordered partition
         for (size_t i = 0; i < _processors.size(); i++) _processors[i]->begin(_config);
-        for (int pass = 0; pass < _nbPasses; pass++) {
+        // one device job: every distinct k-mer of `onlyBank` (or of everything) with its count
+        auto runJob = [&](int pass, int onlyBank, bool resetFirst) {
             for (int attempt = 0; ; attempt++) {
                 try {
-                    if (_nbPasses > 1 || attempt > 0) beginPass(pass);
-                    { TIME_INFO(getTimeInfo(), "fill_partitions"); feedBanks(); }
+                    if (resetFirst || attempt > 0) beginPass(pass);
+                    { TIME_INFO(getTimeInfo(), "fill_partitions"); feedBanks(onlyBank); }
                     { TIME_INFO(getTimeInfo(), "fill_solid_kmers"); finishAll(); }
                     break;
                 } catch (FormatRejected& e) {
@@ -677,35 +681,104 @@ private:
                     _viaIterator = true;
                 }
             }
+            for (size_t r = 0; r < W; r++) {
+                dskgpu_stats st;
+                check(dskgpu_get_stats(_ctxs[r], &st), _ctxs[r], "dskgpu_get_stats");
+                if (pass == 0) { _st.nb_sequences += st.nb_sequences; _st.nb_nucleotides += st.nb_nucleotides; _st.kmers_nb_valid += st.kmers_nb_valid; }
+                _st.nb_superkmers += st.nb_superkmers; _st.superkmer_bytes += st.superkmer_bytes; _st.gpu_launches += st.gpu_launches;
+                if (B == 1) _st.kmers_nb_distinct += st.kmers_nb_distinct;
+            }
+        };
+        // feeds one ordered stream of (k-mer, CountVector, sum) to every processor, the protocol of fillSolidKmers_aux
+        for (int pass = 0; pass < _nbPasses; pass++) {
+            if (B == 1) {
+                runJob(pass, -1, _nbPasses > 1);
+                TIME_INFO(getTimeInfo(), "processors");
+                for (size_t i = 0; i < _processors.size(); i++) {
+                    CountProcessor* proc = _processors[i];
+                    proc->beginPass((size_t)pass);
+                    std::vector<CountProcessor*> clones;
+                    for (size_t r = 0; r < W; r++) {                   // one "partition" per device: its k-mers, ascending
+                        CountProcessor* clone = proc->clone();
+                        clone->use();
+                        clones.push_back(clone);
+                        const uint64_t* kmers = 0; const uint32_t* counts = 0; uint64_t n = 0; int words = 0;
+                        check(dskgpu_partition(_ctxs[r], 0, &kmers, &counts, &n, &words), _ctxs[r], "dskgpu_partition");
+                        clone->beginPart((size_t)pass, r, 200 * 1000, "device");
+                        CountVector cv(1);
+                        for (uint64_t j = 0; j < n; j++) {
+                            Type v; setValue(v, kmers + j * words, words);
+                            cv[0] = (CountNumber)counts[j];
+                            clone->process(r, v, cv);                  // (sum left at 0, as PartitionsCommand.cpp:119,167 does: a chain computes it)
+                        }
+                        clone->endPart((size_t)pass, r);
+                    }
+                    proc->finishClones(clones);
+                    for (size_t r = 0; r < clones.size(); r++) clones[r]->forget();
+                    proc->endPass((size_t)pass);
+                }
+                continue;
+            }
+            // several banks: a CountVector holds one count per bank (K/PartitionsCommand.cpp:540-541).  Each bank is counted by a
+            // device job of its own -- the counts of a k-mer in bank b are exactly what a job fed with bank b alone delivers --
+            // and the W x B ordered lists are merged on the host (a k-mer's pass is a function of its minimizer, so with several
+            // passes every list of a pass holds the same slice of the k-mer space).
+            struct List { std::vector<uint64_t> keys; std::vector<uint32_t> cnt; size_t bank, pos; };
+            std::vector<List> lists;
+            int words = 1;
+            for (size_t b = 0; b < B; b++) {
+                runJob(pass, (int)b, _nbPasses > 1 || b > 0);
+                for (size_t r = 0; r < W; r++) {
+                    const uint64_t* kmers = 0; const uint32_t* counts = 0; uint64_t n = 0;
+                    check(dskgpu_partition(_ctxs[r], 0, &kmers, &counts, &n, &words), _ctxs[r], "dskgpu_partition");
+                    lists.push_back(List());
+                    List& L = lists.back();
+                    L.bank = b; L.pos = 0;
+                    L.keys.assign(kmers, kmers + n * (uint64_t)words); L.cnt.assign(counts, counts + n);
+                }
+            }
             TIME_INFO(getTimeInfo(), "processors");
+            const int KWn = words;
+            auto less = [&](const uint64_t* a, const uint64_t* c) { for (int q = KWn - 1; q >= 0; q--) if (a[q] != c[q]) return a[q] < c[q]; return false; };
+            auto same = [&](const uint64_t* a, const uint64_t* c) { for (int q = 0; q < KWn; q++) if (a[q] != c[q]) return false; return true; };
+            // merged stream, materialised once (every processor walks it): keys + B counts per k-mer
+            std::vector<uint64_t> mk; std::vector<CountNumber> mc;
+            {
+                std::vector<size_t> heap;                              // indices of the lists that still have items, min-heap on their head key
+                auto head = [&](size_t l) { return lists[l].keys.data() + lists[l].pos * (size_t)KWn; };
+                auto cmp = [&](size_t x, size_t y) { return less(head(y), head(x)); };   // std heap = max-heap: invert
+                for (size_t l = 0; l < lists.size(); l++) if (!lists[l].cnt.empty()) heap.push_back(l);
+                std::make_heap(heap.begin(), heap.end(), cmp);
+                while (!heap.empty()) {
+                    std::pop_heap(heap.begin(), heap.end(), cmp);
+                    const size_t l = heap.back();
+                    const uint64_t* k0 = head(l);
+                    const bool fresh = mk.empty() || !same(&mk[mk.size() - (size_t)KWn], k0);
+                    if (fresh) { mk.insert(mk.end(), k0, k0 + KWn); mc.insert(mc.end(), B, (CountNumber)0); }
+                    mc[mc.size() - B + lists[l].bank] += (CountNumber)lists[l].cnt[lists[l].pos];
+                    if (++lists[l].pos < lists[l].cnt.size()) std::push_heap(heap.begin(), heap.end(), cmp); else heap.pop_back();
+                }
+            }
+            lists.clear();
+            const uint64_t n = mk.size() / (size_t)KWn;
+            _st.kmers_nb_distinct += n;
             for (size_t i = 0; i < _processors.size(); i++) {
                 CountProcessor* proc = _processors[i];
                 proc->beginPass((size_t)pass);
                 std::vector<CountProcessor*> clones;
-                for (size_t r = 0; r < W; r++) {                       // one "partition" per device: its k-mers, ascending
-                    CountProcessor* clone = proc->clone();
-                    clone->use();
-                    clones.push_back(clone);
-                    const uint64_t* kmers = 0; const uint32_t* counts = 0; uint64_t n = 0; int words = 0;
-                    check(dskgpu_partition(_ctxs[r], 0, &kmers, &counts, &n, &words), _ctxs[r], "dskgpu_partition");
-                    clone->beginPart((size_t)pass, r, 200 * 1000, "device");
-                    CountVector cv(1);
-                    for (uint64_t j = 0; j < n; j++) {
-                        Type v; setValue(v, kmers + j * words, words);
-                        cv[0] = (CountNumber)counts[j];
-                        clone->process(r, v, cv, (CountNumber)counts[j]);
-                    }
-                    clone->endPart((size_t)pass, r);
-                    if (i == 0) {
-                        dskgpu_stats st;
-                        check(dskgpu_get_stats(_ctxs[r], &st), _ctxs[r], "dskgpu_get_stats");
-                        if (pass == 0) { _st.nb_sequences += st.nb_sequences; _st.nb_nucleotides += st.nb_nucleotides; _st.kmers_nb_valid += st.kmers_nb_valid; }
-                        _st.nb_superkmers += st.nb_superkmers; _st.superkmer_bytes += st.superkmer_bytes; _st.kmers_nb_distinct += st.kmers_nb_distinct;
-                        _st.gpu_launches += st.gpu_launches;
-                    }
+                CountProcessor* clone = proc->clone();
+                clone->use();
+                clones.push_back(clone);
+                clone->beginPart((size_t)pass, 0, 200 * 1000, "device");
+                CountVector cv(B);
+                for (uint64_t j = 0; j < n; j++) {
+                    Type v; setValue(v, &mk[j * (size_t)KWn], KWn);
+                    for (size_t b = 0; b < B; b++) cv[b] = mc[j * B + b];
+                    clone->process(0, v, cv);                          // (sum = 0: CountProcessorChain::computeSum applies -solidity-custom's vector)
                 }
+                clone->endPart((size_t)pass, 0);
                 proc->finishClones(clones);
-                for (size_t r = 0; r < clones.size(); r++) clones[r]->forget();
+                clone->forget();
                 proc->endPass((size_t)pass);
             }
         }

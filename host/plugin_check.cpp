@@ -21,16 +21,19 @@ public:
     typedef typename Kmer<span>::Type Type;
     struct Totals { u_int64_t distinct, occurrences, unordered, badVector, parts; Totals() : distinct(0), occurrences(0), unordered(0), badVector(0), parts(0) {} };
 
-    AuditProcessor(Totals* shared = 0) : CountProcessorAbstract<span>("audit"), _shared(shared ? shared : &_own), _first(true) {}
+    AuditProcessor(size_t nbBanks, Totals* shared = 0) : CountProcessorAbstract<span>("audit"), _nbBanks(nbBanks), _shared(shared ? shared : &_own), _first(true) {}
 
-    CountProcessorAbstract<span>* clone() { return new AuditProcessor(_shared); }
+    CountProcessorAbstract<span>* clone() { return new AuditProcessor(_nbBanks, _shared); }
     void beginPart(size_t passId, size_t partId, size_t cacheSize, const char* name) { _first = true; _local = Totals(); }
     bool process(size_t partId, const Type& kmer, const CountVector& count, CountNumber sum)
     {
-        if (count.size() != 1 || count[0] != sum || sum < 1) _local.badVector++;
+        // one count per bank, at least one occurrence, sum left to the processors (the reference passes 0: PartitionsCommand.cpp:119)
+        CountNumber total = 0; bool neg = false;
+        for (size_t b = 0; b < count.size(); b++) { total += count[b]; neg = neg || count[b] < 0; }
+        if (count.size() != _nbBanks || neg || total < 1 || sum != 0) _local.badVector++;
         if (!_first && !(_prev < kmer)) _local.unordered++;         // ascending inside a partition (K/PartitionsCommand.cpp:540-541)
         _prev = kmer; _first = false;
-        _local.distinct++; _local.occurrences += (u_int64_t)sum;
+        _local.distinct++; _local.occurrences += (u_int64_t)total;
         return true;
     }
     void endPart(size_t passId, size_t partId)
@@ -42,7 +45,7 @@ public:
     const Totals& totals() const { return *_shared; }
 
 private:
-    Totals _own, _local; Totals* _shared;
+    size_t _nbBanks; Totals _own, _local; Totals* _shared;
     Type _prev; bool _first;
 };
 
@@ -60,7 +63,7 @@ template <size_t span> struct Functor { void operator()(Parameter parameter)
     configAlgo.execute();
     Configuration config = configAlgo.getConfiguration();
     std::vector<ICountProcessor<span>*> processors = SortingCountAlgorithm<span>::getDefaultProcessorVector(config, props, storage, storage);
-    AuditProcessor<span>* audit = new AuditProcessor<span>();
+    AuditProcessor<span>* audit = new AuditProcessor<span>(config._nb_banks);
     processors.push_back(audit);
 
     GpuSortingCount<span> sortingCount(bank, config, 0, processors, props);

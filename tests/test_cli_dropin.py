@@ -124,8 +124,9 @@ def test_cli_shell_goldens(tmp_path):
 
 PLUGIN = os.path.join(ROOT, "host", "_build", "plugin_check")
 AUTO = load_json("ref_runs_auto.json")["runs"]
-PLUGIN_RUNS = [t for t in RUNS if t["name"] in ("c1_k31", "c1_k63", "c1_k31_min3_max20", "longread_k63", "reads.fastq_k31")] + \
-              [t for t in AUTO if t["name"] in ("auto_c1_k31", "auto_asmreads_k21")]
+PLUGIN_RUNS = [t for t in RUNS if t["name"] in ("c1_k31", "c1_k63", "c1_k31_min3_max20", "longread_k63", "reads.fastq_k31",
+                                               "c1234_k31", "c123_k31_min", "c123_k31_one", "c123_k31_all", "histo2d_k31", "histo2d_c123_k31")] + \
+              [t for t in AUTO if t["name"] in ("auto_c1_k31", "auto_asmreads_k21", "auto_c123_k31_all", "auto_c123_k15_mixed_all", "auto_asm_reads_k21_one")]
 
 
 @need_bins
@@ -135,12 +136,17 @@ def test_plugin_surface_with_the_reference_processors(t, tmp_path):
     """the ICountProcessor plug-in surface (5-argument constructor, G/src/gatb/debruijn/impl/Graph.cpp:399-407): the REFERENCE'S
     OWN processor chain (getDefaultProcessorVector: histogram -> solidity -> dump; cutoff processor first for 'auto') is fed
     by the device path with every distinct k-mer; the .h5 its dump processor writes must hold what the reference dsk wrote,
-    and our audit processor must have seen every distinct k-mer once, ascending, with a one-entry CountVector"""
+    and our audit processor must have seen every distinct k-mer once, ascending, with one count per bank (several banks: one
+    device job per bank, merged on the host -- the solidity kinds min / one / all and -histo2D read the per-bank counts)"""
     tmp = str(tmp_path)
     out = os.path.join(tmp, "plug")
     a = ["-file", ",".join(os.path.join(INPUTS, f) for f in t["files"]), "-kmer-size", str(t["k"]), "-abundance-min", str(t["abundance_min"]), "-out", out, "-histo", "1"]
     if t.get("abundance_max") is not None:
         a += ["-abundance-max", str(t["abundance_max"])]
+    if t.get("solidity_kind"):
+        a += ["-solidity-kind", t["solidity_kind"]]
+    if t.get("histo2d"):
+        a += ["-histo2D", "1"]
     stdout = run([PLUGIN] + a, tmp)
     audit = [ln for ln in stdout.splitlines() if ln.startswith("audit ")][-1].split()
     got = dict(zip(audit[1::2], (int(x) for x in audit[2::2])))
@@ -149,7 +155,7 @@ def test_plugin_surface_with_the_reference_processors(t, tmp_path):
     else:
         assert got["distinct"] >= t["nb_solid"] and got["occurrences"] >= t["sum_counts"]
     assert got["unordered"] == 0 and got["bad_vectors"] == 0 and got["parts"] >= 1
-    assert got["processors"] == (3 if t["abundance_min"] == "auto" else 2)          # (cutoff,) default chain, audit
+    assert got["processors"] == (3 if "auto" in str(t["abundance_min"]) else 2)     # (cutoff,) default chain, audit
     lines, histo, header = read_back(out + ".h5", tmp)
     assert len(lines) == t["nb_solid"]
     m = hashlib.sha256()
