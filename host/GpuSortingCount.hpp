@@ -190,7 +190,7 @@ private:
         IProperties* in = getInput();
         if (_bank == 0) { setBank(Bank::open(in->getStr(STR_URI_INPUT))); }
 
-        const bool plugin = !_processors.empty();
+        bool plugin = !_processors.empty();
         // a default storage only when the caller did not bring processors of their own (K/SortingCountAlgorithm.cpp:534-575)
         if (!plugin || !_haveConfig) {
             std::string output = in->get(STR_URI_OUTPUT) ? in->getStr(STR_URI_OUTPUT)
@@ -211,6 +211,15 @@ private:
             configAlgo.execute();
             _config = configAlgo.getConfiguration();
             _storage->getGroup(configAlgo.getName()).setProperty("xml", std::string("\n") + configAlgo.getInfo()->getXML());
+        }
+        // -kff (KFF output next to the .h5): the reference's CountProcessorDumpKff sits in its default processor chain
+        // (K/SortingCountAlgorithm.cpp:335-400).  The fused device chain has no KFF writer, so the job runs in plug-in mode with
+        // the reference's own default processors -- histogram, solidity, dump and KFF dump are then all reference code fed by
+        // the device.
+        if (!plugin && in->get(STR_KFF)) {
+            std::vector<CountProcessor*> dflt = SortingCountAlgorithm<span>::getDefaultProcessorVector(_config, in, _storage, _storage);
+            for (size_t i = 0; i < dflt.size(); i++) addProcessor(dflt[i]);
+            plugin = true;
         }
         // passes / partitions are a property of the device path (set below, once the devices are known): no disk tier, one
         // ordered output collection per device and pass

@@ -183,6 +183,58 @@ def test_cli_bank_statistics_as_the_reference_prints_them(t, tmp_path):
         assert m.group(1) == t[key], (key, m.group(1), t[key])
 
 
+def kff_records(path):
+    """(k, data_size, sorted list of (2-bit sequence bytes, data bytes)) of a KFF file whose raw sections hold one k-mer per
+    block (max = 1), as CountProcessorDumpKff writes them: header, then sections 'v' (variables), 'r' (raw blocks), 'i' (index)"""
+    d = open(path, "rb").read()
+    assert d[:3] == b"KFF" and d[-3:] == b"KFF"
+    pos = 3 + 2 + 1 + 1 + 1                                   # signature, version, encoding, uniqueness, canonicity
+    free = int.from_bytes(d[pos:pos + 4], "big"); pos += 4 + free
+    var, recs = {}, []
+    while pos < len(d) - 3:
+        t = d[pos:pos + 1]; pos += 1
+        if t == b"v":
+            n = int.from_bytes(d[pos:pos + 8], "big"); pos += 8
+            for _ in range(n):
+                e = d.index(b"\0", pos); name = d[pos:e].decode(); pos = e + 1
+                var[name] = int.from_bytes(d[pos:pos + 8], "big"); pos += 8
+        elif t == b"r":
+            assert var["max"] == 1
+            n = int.from_bytes(d[pos:pos + 8], "big"); pos += 8
+            sb, db = (var["k"] * 2 + 7) // 8, var["data_size"]
+            for _ in range(n):
+                recs.append((d[pos:pos + sb], d[pos + sb:pos + sb + db])); pos += sb + db
+        elif t == b"i":
+            n = int.from_bytes(d[pos:pos + 8], "big"); pos += 8 + n * 9 + 8
+        else:
+            raise AssertionError("unknown KFF section %r at %d" % (t, pos - 1))
+    return var["k"], var["data_size"], sorted(recs)
+
+
+@need_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFBIN, "dsk")), reason="reference dsk binary not on this box")
+@pytest.mark.parametrize("name", ["c1_k31", "c1_k63"])
+def test_cli_kff_output_through_the_reference_dump_processor(name, tmp_path):
+    """-kff: the job runs in plug-in mode with the reference's default processor chain (CountProcessorDumpKff included); the
+    k-mers and counts in the .kff are the ones the reference dsk writes (section layout differs with the partition count),
+    and the .h5 / .histo stay identical"""
+    t = [r for r in RUNS if r["name"] == name][0]
+    tmp = str(tmp_path)
+    a, b = os.path.join(tmp, "gpu_out"), os.path.join(tmp, "ref_out")
+    run([DSK_GPU] + dsk_args(t, a) + ["-kff"], tmp)
+    run([os.path.join(REFBIN, "dsk")] + dsk_args(t, b) + ["-kff", "-out-tmp", tmp], tmp)
+    ka = [f for f in os.listdir(tmp) if f.startswith("gpu_out") and f.endswith(".kff")]
+    kb = [f for f in os.listdir(tmp) if f.startswith("ref_out") and f.endswith(".kff")]
+    assert len(ka) == 1 and len(kb) == 1, (ka, kb)
+    ra, rb = kff_records(os.path.join(tmp, ka[0])), kff_records(os.path.join(tmp, kb[0]))
+    assert ra[0] == rb[0] == t["k"] and ra[1] == rb[1]
+    assert len(ra[2]) == t["nb_solid"] and ra[2] == rb[2]
+    la, ha, _ = read_back(a + ".h5", tmp)
+    lb, hb, _ = read_back(b + ".h5", tmp)
+    assert la == lb and ha == hb
+    assert open(a + ".histo", "rb").read() == open(b + ".histo", "rb").read()
+
+
 HISTOMAX = load_json("ref_runs_histomax.json")["runs"]
 
 

@@ -75,6 +75,7 @@ for line in open(sys.argv[1]):
         print(sys.argv[1], '%.2f G/s %.1f ms' % (d['value'], d['ms_per_step']), {k: round(v, 1) for k, v in d['stage_ms'].items()}, d['engine'], d['checks'])
 PYEOF
               tail -2 "$OUT/bench_k$kk.err"; done ;;
+    pykff)    timeout 600 python -m pytest tests/test_cli_dropin.py -q -k "kff" > "$OUT/pytest_kff.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_kff.log"; tail -40 "$OUT/pytest_kff.log" | cut -c1-700 ;;
     pymin)    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "minimizer_sizes or tiny_smem or record_sub or fine_histogram or heavy" > "$OUT/pytest_min.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_min.log"; tail -6 "$OUT/pytest_min.log" ;;
     *)        echo "unknown step $step" ;;
   esac
