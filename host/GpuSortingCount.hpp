@@ -121,6 +121,9 @@ public:
      *  device delivers EVERY distinct k-mer with its count and the processors decide what happens to it, exactly as in the
      *  reference's fillSolidKmers_aux (K/SortingCountAlgorithm.cpp:1391-1607); without any, the default chain (histogram ->
      *  solidity -> dump) runs fused on the device (the fast path `dsk_gpu` uses). */
+    /** The caller saw -minimizer-size on the command line (IOptionsParser::saw): the value is used as given, even when it is
+     *  the reference default, instead of being sized from the estimated volume (dskgpu_suggest_minimizer_size). */
+    void            keepMinimizerSize(bool keep)     { _keepMinimizerSize = keep; }
     size_t          getProcessorNumber() const       { return _processors.size(); }
     CountProcessor* getProcessor(size_t idx)         { return _processors[idx]; }
     void            addProcessor(CountProcessor* p)  { p->use(); _processors.push_back(p); }
@@ -179,6 +182,8 @@ private:
     std::string       _histoName, _histo2DName;
     size_t            _histoMax = 10000;
     int               _minimizerType = 0, _repartitionType = 0;
+    bool              _keepMinimizerSize = false;
+    int               _minimizerSizeUsed = 10;
     bool              _autoCutoff;
     bool              _autoPerBank;
     std::vector<long long> _userAbundanceMin;      // -1 = auto
@@ -260,7 +265,8 @@ private:
         // -minimizer-size left at the reference default: sized from the estimated volume, the way ConfigurationAlgorithm
         // sizes nb_partitions (bins must shrink as the job grows; which partition a k-mer lands in is unobservable)
         c.minimizer_size = (int32_t)in->getInt(STR_MINIMIZER_SIZE);
-        if (c.minimizer_size == 10) c.minimizer_size = dskgpu_suggest_minimizer_size((uint64_t)_config._kmersNb, c.kmer_size);
+        if (c.minimizer_size == 10 && !_keepMinimizerSize) c.minimizer_size = dskgpu_suggest_minimizer_size((uint64_t)_config._kmersNb, c.kmer_size);
+        _minimizerSizeUsed = c.minimizer_size;
         c.nb_banks = (int32_t)_config._nb_banks;
         if (c.nb_banks > DSKGPU_MAX_BANKS) throw Exception("at most %d banks are supported by the device path", DSKGPU_MAX_BANKS);
         // kind of the FILTER: created from -solidity-kind before -histo2D forces the counting path to per-bank
@@ -987,6 +993,7 @@ private:
         getInfo()->add(3, "nb_items", "%ld", (long)nbSolid);
         getInfo()->add(3, "nb_passes", "%ld", (long)_nbPasses);
         getInfo()->add(3, "nb_devices", "%ld", (long)_ctxs.size());
+        getInfo()->add(3, "minimizer_size_used", "%ld", (long)_minimizerSizeUsed);
         if (_minimizerType != 0 || _repartitionType != 0)
             getInfo()->add(3, "partition_balance", "%s", "-minimizer-type / -repartition-type accepted; the device path balances from exact minimizer-bin counts");
         getInfo()->add(3, "device_partitions", "%ld", (long)_st.nb_partitions);

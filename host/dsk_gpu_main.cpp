@@ -33,6 +33,7 @@ template <size_t span> struct Functor { void operator()(Parameter parameter)
     LOCAL(bank);
 
     GpuSortingCount<span> sortingCount(bank, props);
+    sortingCount.keepMinimizerSize(dsk.getParser()->saw(STR_MINIMIZER_SIZE));     // an explicit -minimizer-size is honoured as given
     sortingCount.getInput()->add(0, STR_VERBOSE, props->getStr(STR_VERBOSE));
     sortingCount.execute();
 

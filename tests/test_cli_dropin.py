@@ -235,6 +235,21 @@ def test_cli_kff_output_through_the_reference_dump_processor(name, tmp_path):
     assert open(a + ".histo", "rb").read() == open(b + ".histo", "rb").read()
 
 
+@need_bins
+@pytest.mark.parametrize("given,used", [(None, "10"), ("10", "10"), ("12", "12"), ("8", "8")])
+def test_cli_minimizer_size_used_is_reported(given, used, tmp_path):
+    """-minimizer-size on the command line is honoured as given (IOptionsParser::saw tells an explicit 10 from the default, which
+    big jobs replace by dskgpu_suggest_minimizer_size); the value in use is part of the statistics"""
+    import re
+    tmp = str(tmp_path)
+    a = ["-file", os.path.join(INPUTS, "read50x_ref10K_e001.fasta.gz"), "-kmer-size", "31", "-out", os.path.join(tmp, "o"), "-verbose", "1"]
+    if given:
+        a += ["-minimizer-size", given]
+    out = run([DSK_GPU] + a, tmp)
+    m = re.search(r"^\s*minimizer_size_used\s*:\s*(\S+)\s*$", out, re.M)
+    assert m and m.group(1) == used
+
+
 HISTOMAX = load_json("ref_runs_histomax.json")["runs"]
 
 
