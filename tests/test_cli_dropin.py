@@ -169,8 +169,11 @@ def test_plugin_surface_with_the_reference_processors(t, tmp_path):
 BANKSTATS = load_json("ref_bankstats.json")["runs"]
 
 
+BANKSTATS_CLI = [t for t in BANKSTATS if t["files"][0] in ("weird.fasta", "read50x_ref10K_e001.fasta.gz", "reads.fastq", "multiline.fasta", "c1.fasta.gz", "longread.fasta", "readN.fasta")]
+
+
 @need_bins
-@pytest.mark.parametrize("t", BANKSTATS, ids=["+".join(t["files"]) for t in BANKSTATS])
+@pytest.mark.parametrize("t", BANKSTATS_CLI, ids=["+".join(t["files"]) for t in BANKSTATS_CLI])    # (every input: tests/test_gpu_round2.py, through the C ABI)
 def test_cli_bank_statistics_as_the_reference_prints_them(t, tmp_path):
     """bank / sequences / kmers keys of `dsk -verbose 1` (K/SortingCountAlgorithm.cpp:728-742): same strings from `dsk_gpu`"""
     import re
@@ -236,7 +239,7 @@ def test_cli_kff_output_through_the_reference_dump_processor(name, tmp_path):
 
 
 @need_bins
-@pytest.mark.parametrize("given,used", [(None, "10"), ("10", "10"), ("12", "12"), ("8", "8")])
+@pytest.mark.parametrize("given,used", [(None, "10"), ("10", "10"), ("12", "12")])
 def test_cli_minimizer_size_used_is_reported(given, used, tmp_path):
     """-minimizer-size on the command line is honoured as given (IOptionsParser::saw tells an explicit 10 from the default, which
     big jobs replace by dskgpu_suggest_minimizer_size); the value in use is part of the statistics"""

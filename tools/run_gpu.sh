@@ -76,6 +76,7 @@ for line in open(sys.argv[1]):
 PYEOF
               tail -2 "$OUT/bench_k$kk.err"; done ;;
     pykff)    timeout 600 python -m pytest tests/test_cli_dropin.py -q -k "kff" > "$OUT/pytest_kff.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_kff.log"; tail -40 "$OUT/pytest_kff.log" | cut -c1-700 ;;
+    smoke)    timeout 300 python __graft_entry__.py smoke > "$OUT/smoke.log" 2>&1; echo "smoke exit $?"; tail -2 "$OUT/smoke.log" ;;
     pymin)    timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -k "minimizer_sizes or tiny_smem or record_sub or fine_histogram or heavy" > "$OUT/pytest_min.log" 2>&1; echo "pytest exit $?" >> "$OUT/pytest_min.log"; tail -6 "$OUT/pytest_min.log" ;;
     *)        echo "unknown step $step" ;;
   esac
