@@ -7,7 +7,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "libdskgpu.so")
 SRC = os.path.join(PKG, "csrc", "dskgpu.cu")
-DEPS = [os.path.join(PKG, "csrc", f) for f in ("dskgpu.cu", "kmer_bits.cuh", "scan.cuh", "superk.cuh", "count.cuh", "count_smem.cuh", "radix.cuh", "kmer_wide.cuh", "plan.cuh")]
+DEPS = [os.path.join(PKG, "csrc", f) for f in ("dskgpu.cu", "kmer_bits.cuh", "scan.cuh", "superk.cuh", "count.cuh", "count_smem.cuh", "radix.cuh", "kmer_wide.cuh", "plan.cuh", "seqstats.cuh")]
 DEPS.append(os.path.join(ROOT, "include", "dskgpu.h"))
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
