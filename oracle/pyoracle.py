@@ -37,7 +37,7 @@ def _lib(k=31):
     L.orc_add_sequence.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
     L.orc_add_file.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.orc_finish.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int64, C.c_int, C.c_char_p, C.c_int]
-    for name in ("nb_valid", "nb_invalid", "nb_seq", "nb_nt", "nb_superkmers", "nb_distinct", "nb_solid"):
+    for name in ("nb_valid", "nb_invalid", "nb_seq", "nb_nt", "nb_superkmers", "nb_distinct", "nb_solid", "seq_min", "seq_max", "seq_sumsq"):
         f = getattr(L, "orc_" + name)
         f.restype = C.c_uint64
         f.argtypes = [C.c_void_p]
@@ -93,6 +93,19 @@ class OracleResult:
     hist: np.ndarray         # uint64[10001]  (index = abundance; bins 0 and 10000 are always 0)
     hist2d: np.ndarray       # uint64[11, 10001]  ([dim2, dim1])
     cutoffs: object = None   # -abundance-min auto: the cutoffs of the first pass
+    seq_min: int = 0         # BankStats (K/BankKmers.hpp:166-215): shortest / longest sequence, sum of squared lengths
+    seq_max: int = 0
+    seq_sumsq: int = 0
+
+    def bank_stats_strings(self):
+        """the bank / sequences / kmers keys as SortingCountAlgorithm::getInfo() formats them (K/SortingCountAlgorithm.cpp:733-742)"""
+        import math
+        n = self.nb_seq
+        mean = self.nb_nt / n if n else 0.0
+        dev = math.sqrt(max(0.0, self.seq_sumsq / n - mean * mean)) if n else 0.0
+        return {"bank_total_nt": str(self.nb_nt), "seq_number": str(n), "seq_size_min": str(self.seq_min), "seq_size_max": str(self.seq_max),
+                "seq_size_mean": "%.1f" % mean, "seq_size_deviation": "%.1f" % dev,
+                "kmers_nb_valid": str(self.kmers_nb_valid), "kmers_nb_invalid": str(self.kmers_nb_invalid)}
 
     @property
     def nb_distinct(self):
@@ -160,6 +173,7 @@ class Oracle:
             solid=_np_from(L.orc_solid(h), np.uint8, nd).astype(bool),
             hist=_np_from(L.orc_hist(h), np.uint64, 10001),
             hist2d=_np_from(L.orc_hist2d(h), np.uint64, 10001 * 11).reshape(11, 10001),
+            seq_min=L.orc_seq_min(h), seq_max=L.orc_seq_max(h), seq_sumsq=L.orc_seq_sumsq(h),
         )
         L.orc_destroy(h)
         self.h = None

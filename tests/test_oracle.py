@@ -172,3 +172,18 @@ def test_reference_auto_cutoff_runs(t):
     lo, hi, cnt = r.solid_kmers()
     dg, _ = digest(lo, hi, cnt, t["k"])
     assert dg == t["kmers_sha256"]
+
+
+BANKSTATS = load_json("ref_bankstats.json")["runs"]
+
+
+@pytest.mark.parametrize("t", BANKSTATS, ids=["+".join(t["files"]) for t in BANKSTATS])
+def test_oracle_bank_statistics_against_the_reference(t):
+    """BankStats (K/BankKmers.hpp:166-215) + kmersNbInvalid (K/Sequence2SuperKmer.hpp:95-108) as `dsk -verbose 1` prints them
+    (tests/golden/ref_bankstats.json, from the unmodified reference): pins the oracle's record parser on sequence boundaries
+    (empty records, multi-line FASTA, FASTQ, several banks) and its validity window on the invalid-window count"""
+    res = oracle.count_files([read_input(f) for f in t["files"]], t["k"], abundance_min=2)
+    got = res.bank_stats_strings()
+    for key, want in t.items():
+        if key in got:
+            assert got[key] == want, (key, got[key], want)
