@@ -187,3 +187,27 @@ def test_oracle_bank_statistics_against_the_reference(t):
     for key, want in t.items():
         if key in got:
             assert got[key] == want, (key, got[key], want)
+
+
+HISTOMAX = load_json("ref_runs_histomax.json")["runs"]
+
+
+@pytest.mark.parametrize("t", HISTOMAX, ids=[t["name"] for t in HISTOMAX])
+def test_histo_max_rule_against_the_reference(t):
+    """-histo-max N: the <out>.histo of the reference is the first N bins of the 10000-bin histogram with bin N empty (counts >= N
+    are clamped into a bin that is never merged: Histogram.hpp:92,221); the 2-D clamp column collects everything >= N
+    (Histogram.hpp:97).  This is the rule host/GpuSortingCount.hpp applies to the device bins."""
+    amin = -1 if t["abundance_min"] == "auto" else t["abundance_min"]
+    res = oracle.count_files([read_input(f) for f in t["files"]], t["k"], abundance_min=amin, histo2d=bool(t.get("histo2d")))
+    N = t["histo_max"]
+    want = "".join("%d\t%d\n" % (i, int(res.hist[i]) if i < N else 0) for i in range(1, N + 1))
+    assert want == t["histo_text"]
+    assert res.nb_solid == t["nb_solid"]
+    if t.get("histo2d"):
+        rows = t["histo2d_text"].splitlines()
+        assert len(rows) == N + 1
+        for i, row in enumerate(rows):
+            vals = [int(x) for x in row.split(":")[1].split()]
+            for j in range(11):
+                exp = int(res.hist2d[j, i]) if i < N else int(res.hist2d[j, N:].sum())
+                assert vals[j] == exp, (i, j)
